@@ -1,0 +1,217 @@
+/* vio_b200.h — C-ABI of the B200-native backend::Problem least-squares hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handle, int error codes, caller-owned
+ * host arrays borrowed for the duration of a call, no C++/Eigen/torch types.  The C++
+ * `myslam::backend::Problem` mirror (include/backend/problem.h) and the ctypes binding
+ * (visual-inertial-odometry_b200/capi.py) are both thin clients of exactly these symbols.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/workspace/assignments;
+ * A15 = 15-vio-backend, A17 = 17-vins-initialization/vins-mono):
+ *   vio_set_graph          <- Problem::AddVertex/AddEdge + SetOrdering   A15/backend/problem.cc:40-54,91-103,224-262
+ *                                                                         A17/src/backend/problem.cc:44-58,108-121,256-285
+ *   vio_set_prior/get_prior<- Set/Get{HessianPrior,bPrior,ErrPrior,JtPrior}, ExtendHessiansPriorSize
+ *                                                                         A17/include/backend/problem.h:78-88, A17/src/backend/problem.cc:83-92
+ *   vio_linearize          <- Problem::MakeHessian                        A15/backend/problem.cc:280-337, A17/src/backend/problem.cc:303-389
+ *   vio_solve_step         <- Problem::SolveLinearSystem                  A15/backend/problem.cc:342-423, A17/src/backend/problem.cc:394-449
+ *   vio_solve              <- Problem::Solve(iterations)                  A15/backend/problem.cc:155-222, A17/src/backend/problem.cc:169-250
+ *   vio_chi2               <- Σ Edge::Chi2 / RobustChi2 (+ prior)         A15/backend/problem.cc:457-462,501-507, A17/src/backend/problem.cc:501-507,549-556
+ *   vio_get_vertices       <- Vertex::Parameters() read-back after Solve  A15/app/TestMonoBA.cpp:193-216
+ *
+ * All floating point is IEEE double.  Quaternions are stored [x y z w] inside a pose
+ * record [tx ty tz qx qy qz qw] exactly like VertexPose::Parameters() (A15/backend/vertex_pose.h:12-14).
+ */
+#ifndef VIO_B200_H
+#define VIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vio_problem vio_problem; /* opaque; one per host thread + CUDA stream */
+
+/* ---- error codes (0 = success) ------------------------------------------------------- */
+enum {
+    VIO_OK = 0,
+    VIO_ERR_INVALID = 1,     /* bad argument / inconsistent graph description            */
+    VIO_ERR_CUDA = 2,        /* a CUDA runtime call failed (see vio_last_error)          */
+    VIO_ERR_UNSUPPORTED = 3, /* graph uses a feature outside the device path (documented)*/
+    VIO_ERR_EMPTY = 4,       /* Solve on a graph without edges or vertices (reference: Solve returns false) */
+    VIO_ERR_NO_DEVICE = 5,   /* no CUDA device: the product path never falls back to CPU  */
+    VIO_ERR_STATE = 6        /* call order violated (e.g. solve before set_graph)        */
+};
+
+/* ---- enumerations ---------------------------------------------------------------------- */
+enum { VIO_LM_V15 = 0, VIO_LM_V17 = 1 };       /* which reference generation's LM constants  */
+enum {
+    VIO_SOLVER_AUTO = 0,
+    VIO_SOLVER_DENSE_CHOL = 1, /* v17: S.ldlt().solve  (A17/src/backend/problem.cc:439)      */
+    VIO_SOLVER_REF_PCG = 2,    /* v15: PCGSolver incl. its missing first x update
+                                  (A15/backend/problem.cc:530-560)                          */
+    VIO_SOLVER_BLOCK_PCG = 3   /* large BA: 6x6 block-Jacobi PCG on block-sparse S           */
+};
+enum { VIO_LOSS_TRIVIAL = 0, VIO_LOSS_HUBER = 1, VIO_LOSS_CAUCHY = 2, VIO_LOSS_TUKEY = 3 };
+enum { VIO_STORAGE_AUTO = 0, VIO_STORAGE_DENSE = 1, VIO_STORAGE_BSR = 2 };
+
+/* ---- graph description (host SoA, borrowed during vio_set_graph) ------------------------ */
+typedef struct vio_graph {
+    /* pose-class vertices.  Reference SetOrdering gives every pose-class vertex a slot in
+     * creation order, fixed or not (A17/src/backend/problem.cc:256-285). */
+    int32_t n_pose;
+    const double *pose;          /* n_pose x 7  [t(3) q(xyzw)]                             */
+    const uint8_t *pose_fixed;   /* n_pose, may be NULL (= none fixed)                     */
+    int32_t n_speedbias;
+    const double *speedbias;     /* n_speedbias x 9 [v ba bg]  (v17 VertexSpeedBias)       */
+    const uint8_t *speedbias_fixed;
+    /* creation order of the pose-class vertices: entry >= 0 -> pose index, entry < 0 ->
+     * speed-bias index ~entry.  NULL = all poses first, then all speed-biases.            */
+    const int32_t *pclass_order; /* n_pose + n_speedbias                                   */
+
+    /* landmarks: VertexInverseDepth (A15/backend/vertex_inverse_depth.h:12-18)            */
+    int32_t n_landmark;
+    const double *inv_depth;     /* n_landmark                                             */
+
+    /* EdgeReprojection (A15/backend/edge_reprojection.cc:20-111; A17/src/backend/edge_reprojection.cc:18-108).
+     * Preconditions checked by vio_set_graph (all reference drivers satisfy them): every edge of a
+     * landmark names the same host pose and the same host observation pts_i; information = rp_info*I2. */
+    int64_t n_reproj;
+    const int32_t *rp_landmark;  /* n_reproj                                               */
+    const int32_t *rp_pose_i;    /* host pose index                                        */
+    const int32_t *rp_pose_j;    /* observing pose index                                   */
+    const double *rp_pts_i;      /* n_reproj x 3                                           */
+    const double *rp_pts_j;      /* n_reproj x 2 (only x,y of pts_j are read by the reference) */
+    double rp_info;              /* information = rp_info * I2                             */
+    int32_t rp_loss;             /* VIO_LOSS_*  (A17/src/backend/loss_function.cc)          */
+    double rp_loss_delta;
+    /* camera->body extrinsics.  ext_pose < 0: constants q_ic/t_ic (v15 SetTranslationImuFromCamera,
+     * A15/backend/edge_reprojection.cc:42-45).  ext_pose >= 0: index of the extrinsic VertexPose
+     * (v17 4-vertex edge); it must be fixed (ESTIMATE_EXTRINSIC=0 path, A17/src/estimator.cpp:915-932). */
+    int32_t ext_pose;
+    double q_ic[4];              /* xyzw                                                   */
+    double t_ic[3];
+
+    /* EdgeSE3Prior (A15/backend/edge_prior.cpp:39-80)                                      */
+    int32_t n_se3prior;
+    const int32_t *sp_pose;
+    const double *sp_p;          /* n x 3                                                  */
+    const double *sp_q;          /* n x 4 xyzw                                             */
+    const double *sp_info;       /* n x 36 row-major 6x6                                   */
+
+    /* EdgeImu (A17/src/backend/edge_imu.cc:13-157) + IntegrationBase constants
+     * (A17/include/factor/integration_base.h:160-186)                                      */
+    int32_t n_imu;
+    const int32_t *imu_pose_i, *imu_sb_i, *imu_pose_j, *imu_sb_j;
+    const double *imu_sum_dt;    /* n                                                      */
+    const double *imu_delta_p;   /* n x 3                                                  */
+    const double *imu_delta_q;   /* n x 4 xyzw                                             */
+    const double *imu_delta_v;   /* n x 3                                                  */
+    const double *imu_lin_ba;    /* n x 3                                                  */
+    const double *imu_lin_bg;    /* n x 3                                                  */
+    const double *imu_jacobian;  /* n x 225 row-major 15x15                                */
+    const double *imu_covariance;/* n x 225 row-major 15x15                                */
+    double gravity[3];           /* global G (A17/include/parameters.h:49)                 */
+
+    int32_t storage;             /* VIO_STORAGE_* for the reduced camera system            */
+} vio_graph;
+
+/* ---- LM options / statistics -------------------------------------------------------------- */
+typedef struct vio_lm_opts {
+    int32_t flavour;        /* VIO_LM_V15 | VIO_LM_V17                                       */
+    int32_t solver;         /* VIO_SOLVER_*                                                  */
+    int32_t verbose;        /* 1: print the reference's "iter: i , chi= .. , Lambda= .." lines */
+    int32_t pcg_max_iter;   /* block PCG cap; <=0: 2*P like the reference call site          */
+    double pcg_tol;         /* relative residual; <=0: 1e-6 (A15/backend/problem.cc:544)      */
+    int32_t fixed_iterations; /* 1: ignore the reference's convergence stop rules (benchmark) */
+    int32_t reserved;
+} vio_lm_opts;
+
+#define VIO_TRACE_MAX 256
+typedef struct vio_stats {
+    int32_t iterations;       /* outer LM iterations executed                               */
+    int32_t linearizations;   /* MakeHessian-equivalent passes                              */
+    int32_t trial_steps;      /* SolveLinearSystem-equivalent solves                        */
+    int32_t accepted_steps;
+    int64_t pcg_iterations;   /* summed over all reduced solves                             */
+    double chi2_initial, chi2_final;
+    double lambda_initial, lambda_final;
+    double ms_total;          /* CUDA-event time of the whole solve on the handle's stream  */
+    double ms_linearize;      /* Σ linearise+accumulate+Schur kernels                       */
+    double ms_reduced_solve;
+    double ms_backsub_update;
+    double ms_chi2;
+    int32_t n_trace;          /* min(iterations, VIO_TRACE_MAX)                             */
+    double chi2_trace[VIO_TRACE_MAX];   /* currentChi_ printed at the top of each iteration */
+    double lambda_trace[VIO_TRACE_MAX];
+} vio_stats;
+
+/* sizes of the assembled system, for the debug taps */
+typedef struct vio_dims {
+    int32_t P;                /* pose-class dimension (ordering_poses_)                     */
+    int32_t M;                /* landmark dimension   (ordering_landmarks_)                 */
+    int32_t n_pose_blocks;    /* number of pose-class vertices                              */
+    int32_t storage;          /* resolved VIO_STORAGE_*                                     */
+    int64_t nnz_blocks;       /* BSR: number of stored 6x6 blocks; dense: 0                 */
+    int64_t n_reproj;
+    int32_t n_groups;         /* landmark groups (CTA work items) built by the packer       */
+    int32_t reserved;
+} vio_dims;
+
+/* collective hook for the landmark-sharded multi-GPU path: sum `count` doubles in place at
+ * device pointer `dev_ptr` across ranks, ordered on `cuda_stream`.  NULL = single GPU.      */
+typedef int (*vio_allreduce_fn)(void *dev_ptr, int64_t count, void *cuda_stream, void *user);
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int vio_create(int device, void *cuda_stream /* cudaStream_t or NULL = own stream */, vio_problem **out);
+void vio_destroy(vio_problem *p);
+const char *vio_last_error(const vio_problem *p);
+const char *vio_version(void);
+int vio_device_count(void);
+
+/* ---- graph / state -------------------------------------------------------------------------- */
+int vio_set_graph(vio_problem *p, const vio_graph *g);
+int vio_get_dims(const vio_problem *p, vio_dims *out);
+int vio_set_allreduce(vio_problem *p, vio_allreduce_fn fn, void *user);
+/* v17 marginalisation prior; dim must equal P (after ExtendHessiansPriorSize semantics applied by caller).
+ * err/jt_inv may be NULL (no err_prior_ => chi2 has no prior term, like an empty err_prior_). err_dim rows of jt_inv (err_dim x err_dim used on head(P-15)). */
+int vio_set_prior(vio_problem *p, int32_t dim, const double *H_prior, const double *b_prior,
+                  int32_t err_dim, const double *err_prior, const double *Jt_prior_inv);
+int vio_get_prior(vio_problem *p, double *b_prior /* P */, double *err_prior /* err_dim */);
+/* overwrite the current estimates (used by per-iteration re-synchronised parity tests)       */
+int vio_set_vertices(vio_problem *p, const double *pose, const double *speedbias, const double *inv_depth);
+int vio_get_vertices(vio_problem *p, double *pose, double *speedbias, double *inv_depth);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_stats *stats);
+
+/* step-level entry points (what Solve is made of; also the parity taps)                      */
+int vio_linearize(vio_problem *p, const vio_lm_opts *opts);         /* MakeHessian + Schur, at current state  */
+int vio_chi2(vio_problem *p, const vio_lm_opts *opts, double *chi2);/* Σ (Robust)Chi2 (+prior) with flavour's ½ */
+int vio_solve_step(vio_problem *p, const vio_lm_opts *opts, double lambda, int64_t *pcg_iters); /* SolveLinearSystem */
+int vio_apply_step(vio_problem *p, const vio_lm_opts *opts);        /* UpdateStates                           */
+int vio_rollback_step(vio_problem *p, const vio_lm_opts *opts);     /* RollbackStates                         */
+
+/* debug taps (host output arrays).  Any pointer may be NULL.                                 */
+/* full (P+M)^2 Hessian_ and b_ as the reference holds them after MakeHessian (small graphs only: (P+M) <= 8192) */
+int vio_get_hessian(vio_problem *p, const vio_lm_opts *opts, double *H /* (P+M)^2 row-major */, double *b /* P+M */);
+/* undamped reduced system: dense P x P (lambda not added) and b_pp_schur_                    */
+int vio_get_schur(vio_problem *p, double *S /* P*P row-major */, double *bS /* P */);
+/* block-sparse view of the same (BSR storage only)                                          */
+int vio_get_schur_bsr(vio_problem *p, int32_t *rowptr /* nb+1 */, int32_t *col /* nnzb */, double *val /* nnzb*36 */, double *bS);
+int vio_get_delta(vio_problem *p, double *dx_pose /* P */, double *dx_landmark /* M */);
+int vio_get_b(vio_problem *p, double *b_pose /* P */, double *b_landmark /* M */);
+int vio_get_landmark_diag(vio_problem *p, double *Hmm /* M */);
+
+/* last-kernel timing tap for bench.py: average ms of the linearise kernel over the last solve */
+int vio_get_kernel_ms(vio_problem *p, double *ms_linearize_kernel, int64_t *launches);
+/* total number of kernel launches issued by this handle since creation                      */
+int64_t vio_launch_count(const vio_problem *p);
+
+/* FP64 FMA micro-benchmark (roofline denominator for the FP64-bound kernels): returns TFLOP/s */
+int vio_measure_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIO_B200_H */
