@@ -173,6 +173,11 @@ int vio_device_count(void);
 int vio_set_graph(vio_problem *p, const vio_graph *g);
 int vio_get_dims(const vio_problem *p, vio_dims *out);
 int vio_set_allreduce(vio_problem *p, vio_allreduce_fn fn, void *user);
+/* landmark sharding (call before vio_set_graph with the FULL graph on every rank): rank r keeps a
+ * contiguous, edge-balanced range of landmarks and their observations; pose-class vertices, the
+ * reduced-system sparsity pattern and the LM scalars are replicated. Pose-only factors (SE3 prior,
+ * IMU, dense prior) are accumulated by rank 0.                                                     */
+int vio_set_shard(vio_problem *p, int rank, int world);
 /* v17 marginalisation prior; dim must equal P (after ExtendHessiansPriorSize semantics applied by caller).
  * err/jt_inv may be NULL (no err_prior_ => chi2 has no prior term, like an empty err_prior_). err_dim rows of jt_inv (err_dim x err_dim used on head(P-15)). */
 int vio_set_prior(vio_problem *p, int32_t dim, const double *H_prior, const double *b_prior,

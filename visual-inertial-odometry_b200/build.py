@@ -1,0 +1,59 @@
+"""In-tree build of the native libraries (no JIT cache: the .so files travel with the repo snapshot).
+
+  libvio_b200.so    CUDA kernels + C-ABI (include/vio_b200.h), sm_100a only
+  libvio_scenes.so  host-only synthetic scene generators
+  libvio_backend.so C++ drop-in `myslam::backend` layer (needs Eigen headers)
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+
+
+def build_cuda(force=False):
+    out = os.path.join(HERE, "libvio_b200.so")
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs.append(os.path.join(ROOT, "include", "vio_b200.h"))
+    if force or _newer(out, srcs):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        _run([nvcc] + NVCC_FLAGS + ["-o", out, os.path.join(CSRC, "vio_b200.cu")])
+    return out
+
+
+def build_scenes(force=False):
+    out = os.path.join(HERE, "libvio_scenes.so")
+    src = os.path.join(CSRC, "scene_gen.cc")
+    if force or _newer(out, [src]):
+        _run(["g++", "-O2", "-std=c++14", "-shared", "-fPIC", "-o", out, src])
+    return out
+
+
+def build_all(force=False):
+    return build_cuda(force), build_scenes(force)
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv))

@@ -1,0 +1,971 @@
+// vio_b200.cu — C-ABI implementation (include/vio_b200.h): graph packer, LM control, kernel launches.
+// Host code is C++; every numeric step of Problem::Solve runs in the kernels of vio_kernels.cuh /
+// vio_solvers.cuh / vio_imu.cuh.  There is no CPU fallback: without a CUDA device vio_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/vio_b200.h"
+#include "vio_host.h"
+#include "vio_pack.h"
+#include "vio_dev.h"
+#include "vio_kernels.cuh"
+#include "vio_solvers.cuh"
+#include "vio_imu.cuh"
+
+#define VIO_VERSION_STR "vio_b200 0.1 (sm_100a)"
+
+namespace {
+
+struct EvPair {
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct vio_problem {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    bool has_graph = false;
+    bool linearized = false;
+    int64_t launches = 0;
+    vio_allreduce_fn allreduce = nullptr;
+    void *allreduce_user = nullptr;
+    int shard_rank = 0, shard_world = 1;
+
+    // sizes
+    int C = 0, NSB = 0, L = 0, P = 0, NB = 0, storage = 1;
+    long long E = 0, nnzb = 0;
+    int n_se3 = 0, n_imu = 0;
+    int Lglobal = 0;
+    std::vector<int> lm_global;  // local landmark -> caller's landmark index
+    std::vector<int> h_pose_off, h_sb_off;
+
+    // device buffers
+    DBuf<double> pose, pose_bak, sb, sb_bak, invdep, invdep_bak, poseRT;
+    DBuf<uint8_t> pose_fixed, sb_fixed;
+    DBuf<int> pose_off, sb_off, pose_blk;
+    DBuf<int> lm_host, lm_eptr, e_pose_j;
+    DBuf<double> lm_pix, lm_piy, lm_piz, e_pjx, e_pjy;
+    DBuf<double> Hll, bl, wh, wo;
+    DBuf<double> sys;  // [S | bcorr | bp | hdiag]
+    DBuf<double> bS, dxp, dxl;
+    DBuf<int> bsr_rowptr, bsr_col, bsr_tr, bsr_diag;
+    std::vector<int> h_rowptr, h_col;
+    size_t s_count = 0;  // number of doubles in S
+    // se3 priors
+    DBuf<int> sp_pose;
+    DBuf<double> sp_p, sp_q, sp_info;
+    // imu
+    ImuBuffers imu;
+    double gravity[3] = {0, 0, 9.81};
+    // dense v17 prior
+    int prior_dim = 0, err_dim = 0;
+    DBuf<double> Hprior, bprior, bprior_bak, errprior, errprior_bak, Jtinv;
+    // solver workspaces
+    DBuf<double> chol_work;
+    DBuf<int> info;
+    DBuf<double> bpcg_minv, bpcg_x, bpcg_r, bpcg_z, bpcg_p, bpcg_w, bpcg_parta, bpcg_partb, bpcg_scal;
+    // reductions
+    DBuf<double> partial, partial2, scal;
+    double *h_scal = nullptr;  // pinned
+    // timing
+    std::vector<EvPair> ev_lin;
+    size_t ev_lin_used = 0;
+    double last_lin_ms = 0.0;
+    int64_t last_lin_launches = 0;
+
+    DevView view{};
+};
+
+namespace {
+
+int fail(vio_problem *p, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (p) p->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(p, VIO_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,   \
+                                           cudaGetErrorString(e_));                                       \
+    } while (0)
+
+inline int grid_for(long long n, int block, int cap = 1 << 30) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+const int RED_BLOCKS = 592;  // 4 CTAs per SM x 148 SMs for the grid-stride reduction kernels
+
+void fill_view(vio_problem *p) {
+    DevView &v = p->view;
+    v.C = p->C; v.NSB = p->NSB; v.L = p->L; v.P = p->P; v.NB = p->NB; v.E = p->E;
+    v.storage = p->storage; v.nnzb = p->nnzb;
+    v.pose = p->pose.p; v.pose_bak = p->pose_bak.p; v.sb = p->sb.p; v.sb_bak = p->sb_bak.p;
+    v.invdep = p->invdep.p; v.invdep_bak = p->invdep_bak.p;
+    v.pose_fixed = p->pose_fixed.p; v.sb_fixed = p->sb_fixed.p;
+    v.pose_off = p->pose_off.p; v.sb_off = p->sb_off.p; v.pose_blk = p->pose_blk.p;
+    v.poseRT = p->poseRT.p;
+    v.lm_host = p->lm_host.p; v.lm_eptr = p->lm_eptr.p;
+    v.lm_pix = p->lm_pix.p; v.lm_piy = p->lm_piy.p; v.lm_piz = p->lm_piz.p;
+    v.e_pose_j = p->e_pose_j.p; v.e_pjx = p->e_pjx.p; v.e_pjy = p->e_pjy.p;
+    v.Hll = p->Hll.p; v.bl = p->bl.p; v.wh = p->wh.p; v.wo = p->wo.p;
+    v.S = p->sys.p;
+    v.bcorr = p->sys.p + p->s_count;
+    v.bp = v.bcorr + p->P;
+    v.hdiag = v.bp + p->P;
+    v.bS = p->bS.p;
+    v.bsr_rowptr = p->bsr_rowptr.p; v.bsr_col = p->bsr_col.p; v.bsr_tr = p->bsr_tr.p;
+    v.dxp = p->dxp.p; v.dxl = p->dxl.p;
+}
+
+Se3PriorView se3_view(vio_problem *p) {
+    Se3PriorView s;
+    s.n = p->n_se3; s.pose = p->sp_pose.p; s.p = p->sp_p.p; s.q = p->sp_q.p; s.info = p->sp_info.p;
+    return s;
+}
+
+vio_lm_opts default_opts() {
+    vio_lm_opts o;
+    memset(&o, 0, sizeof(o));
+    o.flavour = VIO_LM_V17;
+    return o;
+}
+
+int resolve_solver(const vio_problem *p, const vio_lm_opts &o) {
+    if (o.solver != VIO_SOLVER_AUTO) return o.solver;
+    if (p->storage == VIO_STORAGE_BSR) return VIO_SOLVER_BLOCK_PCG;
+    return o.flavour == VIO_LM_V15 ? VIO_SOLVER_REF_PCG : VIO_SOLVER_DENSE_CHOL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// linearise: MakeHessian + Schur (+ all-reduce of the reduced system when sharded)
+// ---------------------------------------------------------------------------------------------
+int do_pose_prep(vio_problem *p) {
+    k_pose_prep<<<grid_for(p->C, 128), 128, 0, p->stream>>>(p->view);
+    p->launches++;
+    return VIO_OK;
+}
+
+int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
+    const DevView &v = p->view;
+    const size_t sys_n = p->s_count + 3 * (size_t)p->P;
+    CK(cudaMemsetAsync(p->sys.p, 0, sys_n * sizeof(double), p->stream));
+    do_pose_prep(p);
+    EvPair *ev = nullptr;
+    if (p->ev_lin_used < p->ev_lin.size()) ev = &p->ev_lin[p->ev_lin_used++];
+    if (ev) CK(cudaEventRecord(ev->a, p->stream));
+    if (p->L > 0) {
+        if (with_schur) k_linearize_lm<true><<<grid_for(p->L, 128), 128, 0, p->stream>>>(v);
+        else k_linearize_lm<false><<<grid_for(p->L, 128), 128, 0, p->stream>>>(v);
+        p->launches++;
+    }
+    if (ev) CK(cudaEventRecord(ev->b, p->stream));
+    // pose-only factors are owned by shard 0 so the all-reduce counts them once
+    if (p->shard_rank == 0) {
+        if (p->n_se3 > 0) {
+            k_se3prior<<<grid_for(p->n_se3, 64), 64, 0, p->stream>>>(v, se3_view(p));
+            p->launches++;
+        }
+        if (p->n_imu > 0) {
+            imu_linearize(p->imu, v, p->gravity, p->stream);
+            p->launches++;
+        }
+        if (p->prior_dim > 0 && o.flavour == VIO_LM_V17) {
+            k_add_dense_prior<<<grid_for((long long)p->P * p->P, 256), 256, 0, p->stream>>>(v, p->Hprior.p, p->bprior.p,
+                                                                                         p->imu.row_fixed.p);
+            p->launches++;
+        }
+    }
+    if (p->allreduce && p->shard_world > 1) {
+        int rc = p->allreduce(p->sys.p, (int64_t)sys_n, (void *)p->stream, p->allreduce_user);
+        if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+    }
+    if (p->storage == VIO_STORAGE_DENSE) {
+        dim3 b(32, 8), g((p->P + 31) / 32, (p->P + 7) / 8);
+        k_mirror_dense<<<g, b, 0, p->stream>>>(p->sys.p, p->P);
+    } else {
+        k_mirror_bsr<<<grid_for(p->nnzb * 36, 256), 256, 0, p->stream>>>(v);
+    }
+    k_finalize_b<<<grid_for(p->P, 128), 128, 0, p->stream>>>(v);
+    p->launches += 2;
+    CK(cudaGetLastError());
+    p->linearized = with_schur;
+    return VIO_OK;
+}
+
+// chi2 at the current state -> host double (synchronises)
+int do_chi2(vio_problem *p, const vio_lm_opts &o, double *out) {
+    const DevView &v = p->view;
+    do_pose_prep(p);
+    double *acc = p->scal.p + 0;
+    if (p->L > 0) {
+        k_chi2_lm<<<RED_BLOCKS, 256, 0, p->stream>>>(v, p->partial.p);
+        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p, RED_BLOCKS, acc, 0);
+        p->launches += 2;
+    } else {
+        CK(cudaMemsetAsync(acc, 0, sizeof(double), p->stream));
+    }
+    double *other = p->scal.p + 1;
+    CK(cudaMemsetAsync(other, 0, sizeof(double), p->stream));
+    if (p->shard_rank == 0) {
+        if (p->n_se3 > 0) {
+            k_se3prior_chi2<<<1, 32, 0, p->stream>>>(v, se3_view(p), other);
+            p->launches++;
+        }
+        if (p->n_imu > 0) {
+            imu_chi2(p->imu, v, p->gravity, other, p->stream);
+            p->launches++;
+        }
+        if (p->err_dim > 0 && o.flavour == VIO_LM_V17) {
+            k_vec_norm_add<<<1, 256, 0, p->stream>>>(p->errprior.p, p->err_dim, other);
+            p->launches++;
+        }
+    }
+    if (p->allreduce && p->shard_world > 1) {
+        // scal[0] + scal[1] are contiguous
+        int rc = p->allreduce(p->scal.p, 2, (void *)p->stream, p->allreduce_user);
+        if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+    }
+    CK(cudaMemcpyAsync(p->h_scal, p->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    double chi = p->h_scal[0] + p->h_scal[1];
+    if (o.flavour == VIO_LM_V17) chi *= 0.5;
+    *out = chi;
+    return VIO_OK;
+}
+
+int do_maxdiag(vio_problem *p, double *out) {
+    k_maxdiag<<<RED_BLOCKS, 256, 0, p->stream>>>(p->view, p->partial.p);
+    k_max_partials<<<1, 256, 0, p->stream>>>(p->partial.p, RED_BLOCKS, p->scal.p + 2);
+    p->launches += 2;
+    CK(cudaMemcpyAsync(p->h_scal + 2, p->scal.p + 2, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    double m = p->h_scal[2];
+    if (p->allreduce && p->shard_world > 1) {
+        // max over ranks through the sum hook: one-hot slots
+        std::vector<double> slots(p->shard_world, 0.0);
+        slots[p->shard_rank] = m;
+        CK(cudaMemcpyAsync(p->partial.p, slots.data(), slots.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        int rc = p->allreduce(p->partial.p, p->shard_world, (void *)p->stream, p->allreduce_user);
+        if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+        CK(cudaMemcpyAsync(slots.data(), p->partial.p, slots.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        for (double s : slots) m = std::max(m, s);
+    }
+    *out = m;
+    return VIO_OK;
+}
+
+// SolveLinearSystem: reduced solve + back-substitution.  Leaves scale/|dx|^2 partial sums in scal[4..7].
+int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *pcg_iters) {
+    const DevView &v = p->view;
+    const int solver = resolve_solver(p, o);
+    const int P = p->P;
+    if (pcg_iters) *pcg_iters = 0;
+    if (solver == VIO_SOLVER_DENSE_CHOL) {
+        if (p->storage != VIO_STORAGE_DENSE) return fail(p, VIO_ERR_INVALID, "dense Cholesky needs dense storage");
+        if (p->chol_work.n < (size_t)P * P) CK(p->chol_work.alloc((size_t)P * P));
+        k_dense_chol_solve<<<1, 1024, P * sizeof(double), p->stream>>>(v.S, v.bS, lambda, P, p->chol_work.p, v.dxp, p->info.p);
+        p->launches++;
+    } else if (solver == VIO_SOLVER_REF_PCG) {
+        if (p->storage != VIO_STORAGE_DENSE) return fail(p, VIO_ERR_INVALID, "reference PCG needs dense storage");
+        const size_t smem = 5 * (size_t)P * sizeof(double);
+        if (smem > 200 * 1024) return fail(p, VIO_ERR_UNSUPPORTED, "reference PCG: P=%d too large for one CTA", P);
+        CK(cudaFuncSetAttribute(k_ref_pcg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ref_pcg<<<1, 1024, smem, p->stream>>>(v.S, v.bS, lambda, P, 2 * P, v.dxp, p->info.p);
+        p->launches++;
+        if (pcg_iters) {
+            int it = 0;
+            CK(cudaMemcpyAsync(&it, p->info.p, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+            CK(cudaStreamSynchronize(p->stream));
+            *pcg_iters = it;
+        }
+    } else if (solver == VIO_SOLVER_BLOCK_PCG) {
+        if (p->storage != VIO_STORAGE_BSR) return fail(p, VIO_ERR_INVALID, "block PCG needs BSR storage");
+        const int nb = p->NB;
+        if (p->bpcg_x.n < (size_t)P) {
+            CK(p->bpcg_minv.alloc(36 * (size_t)nb)); CK(p->bpcg_x.alloc(P)); CK(p->bpcg_r.alloc(P));
+            CK(p->bpcg_z.alloc(P)); CK(p->bpcg_p.alloc(P)); CK(p->bpcg_w.alloc(P));
+            CK(p->bpcg_parta.alloc(2 * BPCG_MAXPART)); CK(p->bpcg_partb.alloc(BPCG_MAXPART));
+            CK(p->bpcg_scal.alloc(16));
+        }
+        BpcgView s;
+        s.nb = nb; s.rowptr = p->bsr_rowptr.p; s.col = p->bsr_col.p; s.diag = p->bsr_diag.p;
+        s.val = v.S; s.b = v.bS; s.minv = p->bpcg_minv.p; s.x = v.dxp; s.r = p->bpcg_r.p; s.z = p->bpcg_z.p;
+        s.p = p->bpcg_p.p; s.w = p->bpcg_w.p; s.part_a = p->bpcg_parta.p; s.part_b = p->bpcg_partb.p;
+        s.scal = p->bpcg_scal.p; s.lambda = lambda; s.tol = o.pcg_tol > 0 ? o.pcg_tol : 1e-6;
+        const int max_iter = o.pcg_max_iter > 0 ? o.pcg_max_iter : 2 * P;
+        const int g_init = grid_for(nb, 256, BPCG_MAXPART);
+        const int g_spmv = grid_for(6LL * nb, 192, BPCG_MAXPART);
+        const int g_upd = grid_for(nb, 128, BPCG_MAXPART);
+        const int g_dir = grid_for(6LL * nb, 256, BPCG_MAXPART);
+        k_bpcg_init<<<g_init, 256, 0, p->stream>>>(s);
+        k_bpcg_init2<<<1, 256, 0, p->stream>>>(s, g_init);
+        p->launches += 2;
+        int par = 0;
+        double hs[8];
+        const int batch = 32;
+        for (int done_it = 0; done_it < max_iter;) {
+            for (int k = 0; k < batch; ++k) {
+                k_bpcg_spmv<<<g_spmv, 192, 0, p->stream>>>(s);
+                k_bpcg_update<<<g_upd, 128, 0, p->stream>>>(s, g_spmv, par);
+                k_bpcg_dir<<<g_dir, 256, 0, p->stream>>>(s, g_upd, par, max_iter);
+                k_bpcg_commit<<<1, 1, 0, p->stream>>>(s);
+                p->launches += 4;
+                par ^= 1;
+            }
+            done_it += batch;
+            CK(cudaMemcpyAsync(hs, s.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+            CK(cudaStreamSynchronize(p->stream));
+            if (hs[3] != 0.0) break;
+        }
+        CK(cudaMemcpyAsync(hs, s.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        if (pcg_iters) *pcg_iters = (int64_t)hs[4];
+    } else {
+        return fail(p, VIO_ERR_INVALID, "unknown solver %d", solver);
+    }
+    // landmarks + LM scalars
+    if (p->L > 0) {
+        k_backsub<<<RED_BLOCKS, 256, 0, p->stream>>>(v, lambda, p->partial.p, p->partial2.p);
+        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p, RED_BLOCKS, p->scal.p + 4, 0);
+        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p, RED_BLOCKS, p->scal.p + 5, 0);
+        p->launches += 3;
+    } else {
+        CK(cudaMemsetAsync(p->scal.p + 4, 0, 2 * sizeof(double), p->stream));
+    }
+    if (p->allreduce && p->shard_world > 1) {
+        int rc = p->allreduce(p->scal.p + 4, 2, (void *)p->stream, p->allreduce_user);
+        if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+    }
+    k_pose_scale<<<1, 256, 0, p->stream>>>(v, lambda, p->scal.p + 6, p->scal.p + 7);
+    p->launches++;
+    CK(cudaGetLastError());
+    return VIO_OK;
+}
+
+int do_apply(vio_problem *p, const vio_lm_opts &o) {
+    const DevView &v = p->view;
+    k_update_pose<<<grid_for(p->C, 128), 128, 0, p->stream>>>(v, 1.0, 1);
+    if (p->NSB > 0) k_update_sb<<<grid_for(p->NSB, 128), 128, 0, p->stream>>>(v, 1.0, 1);
+    if (p->L > 0) k_update_lm<<<grid_for(p->L, 256), 256, 0, p->stream>>>(v, 1.0, 1);
+    p->launches += 1 + (p->NSB > 0) + (p->L > 0);
+    if (p->prior_dim > 0 && p->err_dim > 0 && o.flavour == VIO_LM_V17) {
+        // b_prior -= H_prior dx_p ; err_prior = -Jt_prior_inv b_prior.head(P-15)   (A17/src/backend/problem.cc:465-474)
+        k_prior_update<<<1, 256, 0, p->stream>>>(p->Hprior.p, p->bprior.p, p->bprior_bak.p, p->errprior.p,
+                                                p->errprior_bak.p, p->Jtinv.p, v.dxp, p->P, p->err_dim);
+        p->launches++;
+    }
+    CK(cudaGetLastError());
+    return VIO_OK;
+}
+
+int do_rollback(vio_problem *p, const vio_lm_opts &o) {
+    const DevView &v = p->view;
+    if (o.flavour == VIO_LM_V15) {
+        // v15: Plus(-delta) (A15/backend/problem.cc:439-450) - restores poses only to rounding
+        k_update_pose<<<grid_for(p->C, 128), 128, 0, p->stream>>>(v, -1.0, 0);
+        if (p->NSB > 0) k_update_sb<<<grid_for(p->NSB, 128), 128, 0, p->stream>>>(v, -1.0, 0);
+        if (p->L > 0) k_update_lm<<<grid_for(p->L, 256), 256, 0, p->stream>>>(v, -1.0, 0);
+        p->launches += 1 + (p->NSB > 0) + (p->L > 0);
+    } else {
+        long long n = std::max<long long>(std::max<long long>(7LL * p->C, 9LL * p->NSB), p->L);
+        k_restore<<<grid_for(n, 256), 256, 0, p->stream>>>(v);
+        p->launches++;
+        if (p->prior_dim > 0 && p->err_dim > 0) {
+            CK(cudaMemcpyAsync(p->bprior.p, p->bprior_bak.p, p->P * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+            CK(cudaMemcpyAsync(p->errprior.p, p->errprior_bak.p, p->err_dim * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        }
+    }
+    CK(cudaGetLastError());
+    return VIO_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+const char *vio_version(void) { return VIO_VERSION_STR; }
+
+int vio_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int vio_create(int device, void *cuda_stream, vio_problem **out) {
+    if (!out) return VIO_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return VIO_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return VIO_ERR_CUDA;
+    vio_problem *p = new vio_problem();
+    p->device = device;
+    if (cuda_stream) {
+        p->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete p;
+            return VIO_ERR_CUDA;
+        }
+        p->own_stream = true;
+    }
+    if (cudaMallocHost((void **)&p->h_scal, 64 * sizeof(double)) != cudaSuccess) {
+        delete p;
+        return VIO_ERR_CUDA;
+    }
+    p->ev_lin.resize(VIO_TRACE_MAX + 8);
+    for (auto &e : p->ev_lin) {
+        cudaEventCreate(&e.a);
+        cudaEventCreate(&e.b);
+    }
+    if (p->partial.alloc(2048) != cudaSuccess || p->partial2.alloc(2048) != cudaSuccess ||
+        p->scal.alloc(64) != cudaSuccess || p->info.alloc(4) != cudaSuccess) {
+        delete p;
+        return VIO_ERR_CUDA;
+    }
+    *out = p;
+    return VIO_OK;
+}
+
+void vio_destroy(vio_problem *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    for (auto &e : p->ev_lin) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    if (p->h_scal) cudaFreeHost(p->h_scal);
+    if (p->own_stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+const char *vio_last_error(const vio_problem *p) { return p ? p->err.c_str() : "null handle"; }
+
+int64_t vio_launch_count(const vio_problem *p) { return p ? p->launches : 0; }
+
+int vio_set_allreduce(vio_problem *p, vio_allreduce_fn fn, void *user) {
+    if (!p) return VIO_ERR_INVALID;
+    p->allreduce = fn;
+    p->allreduce_user = user;
+    return VIO_OK;
+}
+
+int vio_set_shard(vio_problem *p, int rank, int world) {
+    if (!p || world < 1 || rank < 0 || rank >= world) return VIO_ERR_INVALID;
+    p->shard_rank = rank;
+    p->shard_world = world;
+    return VIO_OK;
+}
+
+int vio_set_graph(vio_problem *p, const vio_graph *g) {
+    if (!p || !g) return VIO_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    p->has_graph = false;
+    p->linearized = false;
+    PackedGraph K;
+    {
+        int rc = pack_graph(g, p->shard_rank, p->shard_world, K, p->err);
+        if (rc) return rc;
+    }
+    const int C = K.C, NSB = K.NSB, L = K.L, P = K.P, NB = K.NB;
+    const long long E = K.E;
+    p->C = C; p->NSB = NSB; p->L = L; p->P = P; p->NB = NB; p->E = E; p->storage = K.storage; p->nnzb = K.nnzb;
+    p->Lglobal = K.Lglobal; p->s_count = K.s_count; p->n_se3 = g->n_se3prior; p->n_imu = g->n_imu;
+    p->h_pose_off = K.pose_off; p->h_sb_off = K.sb_off; p->h_rowptr = K.rowptr; p->h_col = K.col;
+    p->lm_global = K.lm_global;
+    cudaStream_t s = p->stream;
+    CK(upload(p->pose, g->pose, 7 * (size_t)C, s)); CK(p->pose_bak.alloc(7 * (size_t)C));
+    CK(upload(p->sb, g->speedbias, 9 * (size_t)NSB, s)); CK(p->sb_bak.alloc(9 * (size_t)NSB));
+    CK(upload(p->invdep, K.invd.data(), (size_t)L, s)); CK(p->invdep_bak.alloc(L));
+    CK(upload(p->pose_fixed, K.pose_fixed.data(), (size_t)C, s)); CK(upload(p->sb_fixed, K.sb_fixed.data(), (size_t)NSB, s));
+    CK(upload(p->pose_off, K.pose_off.data(), (size_t)C, s)); CK(upload(p->sb_off, K.sb_off.data(), (size_t)NSB, s));
+    CK(upload(p->pose_blk, K.pose_blk.data(), (size_t)C, s));
+    CK(p->poseRT.alloc(16 * (size_t)C));
+    CK(upload(p->lm_host, K.lm_host.data(), (size_t)L, s)); CK(upload(p->lm_eptr, K.lm_eptr.data(), (size_t)L + 1, s));
+    CK(upload(p->lm_pix, K.pix.data(), (size_t)L, s)); CK(upload(p->lm_piy, K.piy.data(), (size_t)L, s));
+    CK(upload(p->lm_piz, K.piz.data(), (size_t)L, s));
+    CK(upload(p->e_pose_j, K.e_pose_j.data(), (size_t)E, s));
+    CK(upload(p->e_pjx, K.pjx.data(), (size_t)E, s)); CK(upload(p->e_pjy, K.pjy.data(), (size_t)E, s));
+    CK(p->Hll.alloc(L)); CK(p->bl.alloc(L)); CK(p->wh.alloc(6 * (size_t)L)); CK(p->wo.alloc(6 * (size_t)E));
+    CK(p->sys.alloc(K.s_count + 3 * (size_t)P)); CK(p->bS.alloc(P)); CK(p->dxp.alloc(P)); CK(p->dxl.alloc(L));
+    CK(cudaMemsetAsync(p->dxp.p, 0, P * sizeof(double), s));
+    if (L > 0) CK(cudaMemsetAsync(p->dxl.p, 0, L * sizeof(double), s));
+    if (K.storage == VIO_STORAGE_BSR) {
+        CK(upload(p->bsr_rowptr, K.rowptr.data(), K.rowptr.size(), s)); CK(upload(p->bsr_col, K.col.data(), K.col.size(), s));
+        CK(upload(p->bsr_tr, K.tr.data(), K.tr.size(), s)); CK(upload(p->bsr_diag, K.diag.data(), K.diag.size(), s));
+    } else {
+        p->bsr_rowptr.release(); p->bsr_col.release(); p->bsr_tr.release(); p->bsr_diag.release();
+    }
+    if (g->n_se3prior > 0) {
+        CK(upload(p->sp_pose, g->sp_pose, (size_t)g->n_se3prior, s)); CK(upload(p->sp_p, g->sp_p, 3 * (size_t)g->n_se3prior, s));
+        CK(upload(p->sp_q, g->sp_q, 4 * (size_t)g->n_se3prior, s)); CK(upload(p->sp_info, g->sp_info, 36 * (size_t)g->n_se3prior, s));
+    }
+    CK(upload(p->imu.blk_off, K.blk_off.data(), (size_t)NB, s)); CK(upload(p->imu.blk_dim, K.blk_dim.data(), (size_t)NB, s));
+    CK(upload(p->imu.blk_fixed, K.blk_fixed.data(), (size_t)NB, s));
+    CK(upload(p->imu.row_fixed, K.row_fixed.data(), (size_t)P, s));
+    for (int k = 0; k < 3; ++k) p->gravity[k] = g->gravity[k];
+    if (g->n_imu > 0) {
+        if (K.storage != VIO_STORAGE_DENSE) return fail(p, VIO_ERR_UNSUPPORTED, "IMU edges need dense storage");
+        int rc = imu_upload(p->imu, g, s);
+        if (rc != 0) return fail(p, rc, "bad IMU edge description");
+        p->launches++;
+    }
+    p->prior_dim = 0; p->err_dim = 0;
+
+    fill_view(p);
+    DevView &v = p->view;
+    quat_to_R(K.qic, v.Ric);
+    v.tic[0] = K.tic[0]; v.tic[1] = K.tic[1]; v.tic[2] = K.tic[2];
+    v.rp_info = g->rp_info; v.rp_loss = g->rp_loss; v.rp_delta = g->rp_loss_delta;
+    CK(cudaStreamSynchronize(s));  // host staging vectors go out of scope
+    p->has_graph = true;
+    return VIO_OK;
+}
+
+int vio_get_dims(const vio_problem *p, vio_dims *out) {
+    if (!p || !out || !p->has_graph) return VIO_ERR_STATE;
+    out->P = p->P; out->M = p->Lglobal; out->n_pose_blocks = p->NB; out->storage = p->storage;
+    out->nnz_blocks = p->nnzb; out->n_reproj = p->E; out->n_groups = 0; out->reserved = p->L;
+    return VIO_OK;
+}
+
+int vio_set_prior(vio_problem *p, int32_t dim, const double *H, const double *b, int32_t err_dim, const double *err,
+                  const double *jt) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    if (dim == 0) { p->prior_dim = 0; p->err_dim = 0; return VIO_OK; }
+    if (dim != p->P || !H || !b) return fail(p, VIO_ERR_INVALID, "prior dim %d != P %d", dim, p->P);
+    if (p->storage != VIO_STORAGE_DENSE) return fail(p, VIO_ERR_UNSUPPORTED, "dense prior needs dense storage");
+    if (err_dim < 0 || err_dim > dim) return fail(p, VIO_ERR_INVALID, "bad err_dim");
+    CK(cudaSetDevice(p->device));
+    CK(upload(p->Hprior, H, (size_t)dim * dim, p->stream)); CK(upload(p->bprior, b, (size_t)dim, p->stream));
+    CK(p->bprior_bak.alloc(dim));
+    if (err_dim > 0) {
+        if (!err || !jt) return fail(p, VIO_ERR_INVALID, "err_prior / Jt_prior_inv missing");
+        CK(upload(p->errprior, err, (size_t)err_dim, p->stream)); CK(upload(p->Jtinv, jt, (size_t)err_dim * err_dim, p->stream));
+        CK(p->errprior_bak.alloc(err_dim));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    p->prior_dim = dim; p->err_dim = err_dim;
+    return VIO_OK;
+}
+
+int vio_get_prior(vio_problem *p, double *b, double *err) {
+    if (!p || !p->has_graph || p->prior_dim == 0) return VIO_ERR_STATE;
+    if (b) CK(cudaMemcpyAsync(b, p->bprior.p, p->P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (err && p->err_dim > 0) CK(cudaMemcpyAsync(err, p->errprior.p, p->err_dim * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+int vio_set_vertices(vio_problem *p, const double *pose, const double *sb, const double *invd) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    if (pose) CK(cudaMemcpyAsync(p->pose.p, pose, 7 * (size_t)p->C * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (sb && p->NSB) CK(cudaMemcpyAsync(p->sb.p, sb, 9 * (size_t)p->NSB * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (invd && p->L) {
+        std::vector<double> loc(p->L);
+        for (int l = 0; l < p->L; ++l) loc[l] = invd[p->lm_global[l]];
+        CK(cudaMemcpyAsync(p->invdep.p, loc.data(), (size_t)p->L * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    p->linearized = false;
+    return VIO_OK;
+}
+
+int vio_get_vertices(vio_problem *p, double *pose, double *sb, double *invd) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    if (pose) CK(cudaMemcpyAsync(pose, p->pose.p, 7 * (size_t)p->C * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (sb && p->NSB) CK(cudaMemcpyAsync(sb, p->sb.p, 9 * (size_t)p->NSB * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    std::vector<double> loc;
+    if (invd && p->L) {
+        loc.resize(p->L);
+        CK(cudaMemcpyAsync(loc.data(), p->invdep.p, (size_t)p->L * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    // a shard only writes the landmarks it owns
+    for (int l = 0; l < (int)loc.size(); ++l) invd[p->lm_global[l]] = loc[l];
+    return VIO_OK;
+}
+
+int vio_linearize(vio_problem *p, const vio_lm_opts *opts) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    vio_lm_opts o = opts ? *opts : default_opts();
+    p->ev_lin_used = 0;
+    int rc = do_linearize(p, o, true);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+int vio_chi2(vio_problem *p, const vio_lm_opts *opts, double *chi2) {
+    if (!p || !p->has_graph || !chi2) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    vio_lm_opts o = opts ? *opts : default_opts();
+    return do_chi2(p, o, chi2);
+}
+
+int vio_solve_step(vio_problem *p, const vio_lm_opts *opts, double lambda, int64_t *pcg_iters) {
+    if (!p || !p->has_graph || !p->linearized) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    vio_lm_opts o = opts ? *opts : default_opts();
+    int rc = do_solve_step(p, o, lambda, pcg_iters);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+int vio_apply_step(vio_problem *p, const vio_lm_opts *opts) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    vio_lm_opts o = opts ? *opts : default_opts();
+    int rc = do_apply(p, o);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+int vio_rollback_step(vio_problem *p, const vio_lm_opts *opts) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    vio_lm_opts o = opts ? *opts : default_opts();
+    int rc = do_rollback(p, o);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Problem::Solve
+// -------------------------------------------------------------------------------------------------
+int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_stats *st) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    vio_lm_opts o = opts ? *opts : default_opts();
+    vio_stats local;
+    if (!st) st = &local;
+    memset(st, 0, sizeof(*st));
+    if ((p->Lglobal == 0 && p->C + p->NSB == 0) || (p->E == 0 && p->n_se3 == 0 && p->n_imu == 0 && p->shard_world == 1))
+        return fail(p, VIO_ERR_EMPTY, "Cannot solve problem without edges or verticies");
+    const bool v15 = o.flavour == VIO_LM_V15;
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, p->stream));
+    p->ev_lin_used = 0;
+    int rc;
+#define RC(x)                       \
+    do {                            \
+        rc = (x);                   \
+        if (rc) return rc;          \
+    } while (0)
+    // MakeHessian ; ComputeLambdaInitLM
+    RC(do_linearize(p, o, true));
+    st->linearizations++;
+    double chi = 0.0, maxdiag = 0.0;
+    RC(do_chi2(p, o, &chi));
+    RC(do_maxdiag(p, &maxdiag));
+    if (!v15) maxdiag = std::min(5e10, maxdiag);
+    double lambda = 1e-5 * maxdiag;
+    double ni = 2.0;
+    const double stop_thr = 1e-6 * chi;  // v15 only
+    st->chi2_initial = chi;
+    st->lambda_initial = lambda;
+    bool stop = false;
+    int iter = 0;
+    double last_chi = 1e20;
+    while (!stop && iter < iterations) {
+        if (o.verbose) printf("iter: %d , chi= %g , Lambda= %g\n", iter, chi, lambda);
+        if (iter < VIO_TRACE_MAX) {
+            st->chi2_trace[iter] = chi;
+            st->lambda_trace[iter] = lambda;
+        }
+        bool ok = false;
+        int false_cnt = 0;
+        while (!ok && (v15 || false_cnt < 10)) {
+            int64_t pit = 0;
+            RC(do_solve_step(p, o, lambda, resolve_solver(p, o) == VIO_SOLVER_DENSE_CHOL ? nullptr : &pit));
+            st->trial_steps++;
+            st->pcg_iterations += pit;
+            // scalars of this trial step: scale and |dx|^2
+            CK(cudaMemcpyAsync(p->h_scal + 4, p->scal.p + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+            CK(cudaStreamSynchronize(p->stream));
+            const double dot = p->h_scal[4] + p->h_scal[6];
+            const double dx2 = p->h_scal[5] + p->h_scal[7];
+            if (v15 && !o.fixed_iterations && (dx2 <= 1e-6 || false_cnt > 10)) {
+                stop = true;
+                break;
+            }
+            if (v15 && o.fixed_iterations && false_cnt > 10) {
+                stop = true;
+                break;
+            }
+            RC(do_apply(p, o));
+            // IsGoodStepInLM
+            const double scale = v15 ? dot + 1e-3 : 0.5 * dot + 1e-6;
+            double temp_chi = 0.0;
+            RC(do_chi2(p, o, &temp_chi));
+            const double rho = (chi - temp_chi) / scale;
+            if (rho > 0 && std::isfinite(temp_chi)) {
+                double alpha = 1.0 - std::pow(2 * rho - 1, 3);
+                alpha = std::min(alpha, 2.0 / 3.0);
+                lambda *= std::max(1.0 / 3.0, alpha);
+                ni = 2;
+                chi = temp_chi;
+                ok = true;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+                ok = false;
+            }
+            if (ok) {
+                RC(do_linearize(p, o, true));
+                st->linearizations++;
+                st->accepted_steps++;
+                false_cnt = 0;
+            } else {
+                false_cnt++;
+                RC(do_rollback(p, o));
+            }
+        }
+        iter++;
+        if (!o.fixed_iterations) {
+            if (v15) {
+                if (std::sqrt(chi) <= stop_thr) stop = true;
+            } else {
+                if (last_chi - chi < 1e-5) stop = true;
+            }
+        }
+        last_chi = chi;
+    }
+#undef RC
+    CK(cudaEventRecord(ev1, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    st->ms_total = ms;
+    double lin = 0;
+    for (size_t i = 0; i < p->ev_lin_used; ++i) {
+        float t = 0;
+        cudaEventElapsedTime(&t, p->ev_lin[i].a, p->ev_lin[i].b);
+        lin += t;
+    }
+    st->ms_linearize = lin;
+    p->last_lin_ms = p->ev_lin_used ? lin / p->ev_lin_used : 0.0;
+    p->last_lin_launches = (int64_t)p->ev_lin_used;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    st->iterations = iter;
+    st->n_trace = std::min(iter, VIO_TRACE_MAX);
+    st->chi2_final = chi;
+    st->lambda_final = lambda;
+    return VIO_OK;
+}
+
+int vio_get_kernel_ms(vio_problem *p, double *ms, int64_t *launches) {
+    if (!p) return VIO_ERR_INVALID;
+    if (ms) *ms = p->last_lin_ms;
+    if (launches) *launches = p->last_lin_launches;
+    return VIO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// debug taps
+// -------------------------------------------------------------------------------------------------
+int vio_get_schur(vio_problem *p, double *S, double *bS) {
+    if (!p || !p->has_graph || !p->linearized) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    const int P = p->P;
+    if (S) {
+        if (p->storage == VIO_STORAGE_DENSE) {
+            CK(cudaMemcpyAsync(S, p->sys.p, (size_t)P * P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        } else {
+            std::vector<double> val(p->s_count);
+            CK(cudaMemcpyAsync(val.data(), p->sys.p, p->s_count * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+            CK(cudaStreamSynchronize(p->stream));
+            memset(S, 0, (size_t)P * P * sizeof(double));
+            for (int a = 0; a < p->NB; ++a)
+                for (int k = p->h_rowptr[a]; k < p->h_rowptr[a + 1]; ++k) {
+                    const int b = p->h_col[k];
+                    for (int r = 0; r < 6; ++r)
+                        for (int c = 0; c < 6; ++c) S[(size_t)(6 * a + r) * P + 6 * b + c] = val[36 * (size_t)k + 6 * r + c];
+                }
+        }
+    }
+    if (bS) CK(cudaMemcpyAsync(bS, p->bS.p, P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+int vio_get_schur_bsr(vio_problem *p, int32_t *rowptr, int32_t *col, double *val, double *bS) {
+    if (!p || !p->has_graph || !p->linearized || p->storage != VIO_STORAGE_BSR) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    if (rowptr) memcpy(rowptr, p->h_rowptr.data(), p->h_rowptr.size() * sizeof(int));
+    if (col) memcpy(col, p->h_col.data(), p->h_col.size() * sizeof(int));
+    if (val) CK(cudaMemcpyAsync(val, p->sys.p, p->s_count * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (bS) CK(cudaMemcpyAsync(bS, p->bS.p, p->P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+int vio_get_delta(vio_problem *p, double *dxp, double *dxl) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    if (dxp) CK(cudaMemcpyAsync(dxp, p->dxp.p, p->P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    std::vector<double> loc(p->L);
+    if (dxl && p->L) CK(cudaMemcpyAsync(loc.data(), p->dxl.p, (size_t)p->L * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (dxl) for (int l = 0; l < p->L; ++l) dxl[p->lm_global[l]] = loc[l];
+    return VIO_OK;
+}
+
+int vio_get_b(vio_problem *p, double *bp, double *blm) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    if (bp) CK(cudaMemcpyAsync(bp, p->view.bp, p->P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    std::vector<double> loc(p->L);
+    if (blm && p->L) CK(cudaMemcpyAsync(loc.data(), p->bl.p, (size_t)p->L * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (blm) for (int l = 0; l < p->L; ++l) blm[p->lm_global[l]] = loc[l];
+    return VIO_OK;
+}
+
+int vio_get_landmark_diag(vio_problem *p, double *Hmm) {
+    if (!p || !p->has_graph || !Hmm) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    std::vector<double> loc(p->L);
+    if (p->L) CK(cudaMemcpyAsync(loc.data(), p->Hll.p, (size_t)p->L * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int l = 0; l < p->L; ++l) Hmm[p->lm_global[l]] = loc[l];
+    return VIO_OK;
+}
+
+// Hessian_ and b_ exactly as the reference holds them after MakeHessian (single shard, small graphs).
+int vio_get_hessian(vio_problem *p, const vio_lm_opts *opts, double *H, double *b) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    if (p->shard_world != 1) return fail(p, VIO_ERR_UNSUPPORTED, "full Hessian tap is single-shard");
+    CK(cudaSetDevice(p->device));
+    vio_lm_opts o = opts ? *opts : default_opts();
+    const int P = p->P, M = p->L, n = P + M;
+    if (n > 8192) return fail(p, VIO_ERR_UNSUPPORTED, "full Hessian tap limited to P+M <= 8192");
+    p->ev_lin_used = 0;
+    int rc = do_linearize(p, o, false);  // S buffer = Hpp (no Schur), bp = b_ pose part
+    if (rc) return rc;
+    p->linearized = false;
+    std::vector<double> Hpp((size_t)P * P), bp(P), Hll(M), bl(M), wh(6 * (size_t)M), wo(6 * (size_t)p->E);
+    std::vector<int> host(M), eptr(M + 1), ej(p->E);
+    {
+        // reuse the BSR->dense expansion of vio_get_schur
+        p->linearized = true;
+        rc = vio_get_schur(p, Hpp.data(), nullptr);
+        p->linearized = false;
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(bp.data(), p->view.bp, P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (M) {
+        CK(cudaMemcpyAsync(Hll.data(), p->Hll.p, M * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaMemcpyAsync(bl.data(), p->bl.p, M * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaMemcpyAsync(wh.data(), p->wh.p, wh.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaMemcpyAsync(host.data(), p->lm_host.p, M * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaMemcpyAsync(eptr.data(), p->lm_eptr.p, (M + 1) * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    }
+    if (p->E) {
+        CK(cudaMemcpyAsync(wo.data(), p->wo.p, wo.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaMemcpyAsync(ej.data(), p->e_pose_j.p, p->E * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    if (H) {
+        memset(H, 0, (size_t)n * n * sizeof(double));
+        for (int r = 0; r < P; ++r) memcpy(H + (size_t)r * n, Hpp.data() + (size_t)r * P, P * sizeof(double));
+        for (int l = 0; l < M; ++l) {
+            const int gl = P + p->lm_global[l];
+            H[(size_t)gl * n + gl] = Hll[l];
+            auto put = [&](int pose, const double *w) {
+                const int off = p->h_pose_off[pose];
+                for (int k = 0; k < 6; ++k) {
+                    H[(size_t)(off + k) * n + gl] += w[k];
+                    H[(size_t)gl * n + off + k] += w[k];
+                }
+            };
+            if (eptr[l] != eptr[l + 1]) put(host[l], &wh[6 * (size_t)l]);
+            for (int e = eptr[l]; e < eptr[l + 1]; ++e) put(ej[e], &wo[6 * (size_t)e]);
+        }
+    }
+    if (b) {
+        for (int i = 0; i < P; ++i) b[i] = bp[i];
+        for (int l = 0; l < M; ++l) b[P + p->lm_global[l]] = bl[l];
+    }
+    return VIO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// FP64 FMA peak (roofline denominator)
+// -------------------------------------------------------------------------------------------------
+__global__ void k_dfma_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int vio_measure_fp64_peak(int device, double *tflops) {
+    if (!tflops) return VIO_ERR_INVALID;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n) return VIO_ERR_NO_DEVICE;
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double *d = nullptr;
+    if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return VIO_ERR_CUDA;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        k_dfma_peak<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
+    return cudaGetLastError() == cudaSuccess ? VIO_OK : VIO_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,674 @@
+// vio_kernels.cuh — hand-written sm_100a kernels of the LM hot path.
+// Reference functions restated (A15 = 15-vio-backend, A17 = 17-vins-initialization/vins-mono under
+// /root/reference/workspace/assignments):
+//   k_pose_prep            VertexPose params -> R,t                (A15/backend/edge_reprojection.cc:23-29,68-70)
+//   k_linearize_lm         EdgeReprojection::ComputeResidual/ComputeJacobians + MakeHessian + Schur
+//                          (A15/backend/edge_reprojection.cc:20-111, A15/backend/problem.cc:280-337,353-399;
+//                           A17/src/backend/edge.cc:50-74, A17/src/backend/problem.cc:303-389,406-437)
+//   k_se3prior             EdgeSE3Prior                            (A15/backend/edge_prior.cpp:39-80)
+//   k_chi2_lm              Σ Chi2 / RobustChi2                     (A15/backend/problem.cc:457-462,501-507)
+//   k_backsub              landmark back-substitution              (A15/backend/problem.cc:407-421)
+//   k_update_*             UpdateStates / RollbackStates           (A15/backend/problem.cc:425-450, A15/backend/vertex_pose.cc:7-16)
+#pragma once
+#include "vio_dev.h"
+#include "vio_math.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+// FP64 accumulate into global memory: RED.E.ADD.F64 on the device.  The host branch exists only so
+// tests/host_emul.cu can run the same per-landmark bodies on the CPU as a debugging/unit-test aid.
+VIO_HD void vio_add(double *p, double x) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, x);
+#else
+    *p += x;
+#endif
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-level deterministic sum -> partial[blockIdx.x]   (blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ void block_sum_to(double v, double *partial) {
+    __shared__ double sm[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sm[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        double t = lane < nw ? sm[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) partial[blockIdx.x] = t;
+    }
+    __syncthreads();
+}
+
+// out[idx] (+)= Σ partial[0..n)  in fixed order (single block)
+__global__ void k_sum_partials(const double *partial, int n, double *out, int accumulate) {
+    __shared__ double sm[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t += partial[i];
+    sm[threadIdx.x] = t;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = accumulate ? (*out + sm[0]) : sm[0];
+}
+
+__global__ void k_max_partials(const double *partial, int n, double *out) {
+    __shared__ double sm[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t = fmax(t, partial[i]);
+    sm[threadIdx.x] = t;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sm[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// pose preparation: q -> R once per state (instead of 2x per edge in the reference)
+// ------------------------------------------------------------------------------------------------
+VIO_HD void pose_prep(const DevView &v, int i) {
+    const double *p = v.pose + 7 * (size_t)i;
+    double q[4] = {p[3], p[4], p[5], p[6]};
+    double R[9];
+    quat_to_R(q, R);
+    double *o = v.poseRT + 16 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = R[k];
+    o[9] = p[0];
+    o[10] = p[1];
+    o[11] = p[2];
+    // R^T t is not needed; pad
+    o[12] = 0; o[13] = 0; o[14] = 0; o[15] = 0;
+}
+
+__global__ void k_pose_prep(DevView v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v.C) pose_prep(v, i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduced-system addressing
+// ------------------------------------------------------------------------------------------------
+// Pointer to element (0,0) of the 6x6 block (pose a, pose b) with ordering offset(a) <= offset(b).
+VIO_HD double *s_block(const DevView &v, int a, int b, int &ld) {
+    if (v.storage == 1) {
+        ld = v.P;
+        return v.S + (size_t)v.pose_off[a] * v.P + v.pose_off[b];
+    }
+    ld = 6;
+    const int ra = v.pose_blk[a], cb = v.pose_blk[b];
+    int lo = v.bsr_rowptr[ra], hi = v.bsr_rowptr[ra + 1] - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (v.bsr_col[mid] < cb) lo = mid + 1; else hi = mid;
+    }
+    return v.S + 36 * (size_t)lo;
+}
+
+// S(block a,b) += sgn * X (6x6, row-major X) where X is the (a,b) block; handles orientation so that
+// only the upper block-triangle (and upper element-triangle of diagonal blocks) is touched.
+VIO_HD void s_add_block(const DevView &v, int a, int b, const double X[36], double sgn) {
+    int ld;
+    if (a == b) {
+        // X + X^T contribution when both ends of an edge hit the same vertex
+        double *p = s_block(v, a, a, ld);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = r; c < 6; ++c) vio_add(p + (size_t)r * ld + c, sgn * (X[6 * r + c] + X[6 * c + r]));
+        return;
+    }
+    if (v.pose_off[a] < v.pose_off[b]) {
+        double *p = s_block(v, a, b, ld);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) vio_add(p + (size_t)r * ld + c, sgn * X[6 * r + c]);
+    } else {
+        double *p = s_block(v, b, a, ld);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) vio_add(p + (size_t)r * ld + c, sgn * X[6 * c + r]);
+    }
+}
+// diagonal block (a,a) += sgn * X, X symmetric: only the upper element-triangle is stored
+VIO_HD void s_add_diag(const DevView &v, int a, const double X[36], double sgn) {
+    int ld;
+    double *p = s_block(v, a, a, ld);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) vio_add(p + (size_t)r * ld + c, sgn * X[6 * r + c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-edge reprojection chain (shared by linearise and chi2)
+// ------------------------------------------------------------------------------------------------
+struct EdgeLin {
+    double r[2];
+    double B[6];  // 2x3: reduce * Ric^T * Rj^T ; J_lambda = B g, J_i = B [I G], J_j = B [-I N]
+    double N[9];  // Rj * hat(p_bj)
+};
+
+VIO_HD void reproj_residual(const double Ric[9], const double tic[3], const double *RTj,
+                                                const double pw[3], double pjx, double pjy, double pcj[3],
+                                                double pbj[3], double r[2]) {
+    const double d[3] = {pw[0] - RTj[9], pw[1] - RTj[10], pw[2] - RTj[11]};
+    mat3t_mul_vec(RTj, d, pbj);
+    const double e[3] = {pbj[0] - tic[0], pbj[1] - tic[1], pbj[2] - tic[2]};
+    mat3t_mul_vec(Ric, e, pcj);
+    const double z = pcj[2];
+    r[0] = pcj[0] / z - pjx;
+    r[1] = pcj[1] / z - pjy;
+}
+
+// robust weights (A17/src/backend/edge.cc:39-74) for information = c*I2:
+//   e2 = c r.r ; rho = loss(e2); W = c*(rho1 I + [rho1+2rho2 e2>0] 2 rho2 c r r^T); b uses drho*c
+VIO_HD void robust_weights(int loss, double delta, double c, const double r[2], double &rho0,
+                                               double &drho, double W[3]) {
+    const double e2 = c * (r[0] * r[0] + r[1] * r[1]);
+    if (loss == 0) {
+        rho0 = e2; drho = 1.0;
+        W[0] = c; W[1] = 0.0; W[2] = c;
+        return;
+    }
+    double rho[3];
+    loss_compute(loss, delta, e2, rho);
+    rho0 = rho[0];
+    drho = rho[1];
+    double a = rho[1], k = 0.0;
+    if (rho[1] + 2.0 * rho[2] * e2 > 0.0) k = 2.0 * rho[2] * c;  // weight_err = sqrt(c) r
+    W[0] = c * (a + k * r[0] * r[0]);
+    W[1] = c * (k * r[0] * r[1]);
+    W[2] = c * (a + k * r[1] * r[1]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// v0 linearise + accumulate + Schur: one thread per landmark, global FP64 atomics into the
+// upper block-triangle of the reduced system.  (The grouped shared-memory version replaces this
+// for large scenes; this generic kernel stays as the fallback for irregular graphs.)
+// ------------------------------------------------------------------------------------------------
+template <bool WITH_SCHUR>
+VIO_HD void linearize_landmark(const DevView &v, int l) {
+    const int h = v.lm_host[l];
+    const int e0 = v.lm_eptr[l], e1 = v.lm_eptr[l + 1];
+    if (e0 == e1) {  // landmark without edges: Hmm block is 0 (reference would divide by zero)
+        v.Hll[l] = 0.0; v.bl[l] = 0.0;
+        for (int k = 0; k < 6; ++k) v.wh[6 * (size_t)l + k] = 0.0;
+        return;
+    }
+    const double lam = v.invdep[l];
+    const double pts_i[3] = {v.lm_pix[l], v.lm_piy[l], v.lm_piz[l]};
+    const double *RTh = v.poseRT + 16 * (size_t)h;
+    const bool hfix = v.pose_fixed[h] != 0;
+
+    // host chain: p_ci = pts_i / lambda ; p_bi = Ric p_ci + tic ; p_w = Ri p_bi + Pi
+    const double pci[3] = {pts_i[0] / lam, pts_i[1] / lam, pts_i[2] / lam};
+    double pbi[3], pw[3], tmp[3];
+    mat3_mul_vec(v.Ric, pci, pbi);
+    pbi[0] += v.tic[0]; pbi[1] += v.tic[1]; pbi[2] += v.tic[2];
+    mat3_mul_vec(RTh, pbi, pw);
+    pw[0] += RTh[9]; pw[1] += RTh[10]; pw[2] += RTh[11];
+    // g = Ri Ric pts_i * (-1/lambda^2)
+    double g[3];
+    mat3_mul_vec(v.Ric, pts_i, tmp);
+    mat3_mul_vec(RTh, tmp, g);
+    const double il2 = -1.0 / (lam * lam);
+    g[0] *= il2; g[1] *= il2; g[2] *= il2;
+    // G = -Ri hat(p_bi)
+    double G[9];
+    mat3_mul_hat(RTh, pbi, G);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) G[k] = -G[k];
+
+    double Ms[6] = {0, 0, 0, 0, 0, 0};  // Σ M_e, symmetric 3x3: 00 01 02 11 12 22
+    double ms[3] = {0, 0, 0};           // Σ drho c B^T r
+
+    for (int e = e0; e < e1; ++e) {
+        const int j = v.e_pose_j[e];
+        const double *RTj = v.poseRT + 16 * (size_t)j;
+        double pcj[3], pbj[3], r[2];
+        reproj_residual(v.Ric, v.tic, RTj, pw, v.e_pjx[e], v.e_pjy[e], pcj, pbj, r);
+        const double iz = 1.0 / pcj[2];
+        const double red[6] = {iz, 0.0, -pcj[0] * iz * iz, 0.0, iz, -pcj[1] * iz * iz};
+        // A = Ric^T Rj^T  ;  B = red * A
+        double A[9];
+        {
+            // (Rj Ric)^T
+            double RjRic[9];
+            mat3_mul(RTj, v.Ric, RjRic);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) A[3 * a + b] = RjRic[3 * b + a];
+        }
+        double B[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            B[c] = red[0] * A[c] + red[2] * A[6 + c];
+            B[3 + c] = red[4] * A[3 + c] + red[5] * A[6 + c];
+        }
+        double rho0, drho, W[3];
+        robust_weights(v.rp_loss, v.rp_delta, v.rp_info, r, rho0, drho, W);
+        // WB = W B (2x3) ; M = B^T W B (sym 3x3) ; m = drho c B^T r
+        double WB[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            WB[c] = W[0] * B[c] + W[1] * B[3 + c];
+            WB[3 + c] = W[1] * B[c] + W[2] * B[3 + c];
+        }
+        double M[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) M[3 * a + b] = B[a] * WB[b] + B[3 + a] * WB[3 + b];
+        const double dc = drho * v.rp_info;
+        const double m[3] = {dc * (B[0] * r[0] + B[3] * r[1]), dc * (B[1] * r[0] + B[4] * r[1]),
+                             dc * (B[2] * r[0] + B[5] * r[1])};
+        Ms[0] += M[0]; Ms[1] += M[1]; Ms[2] += M[2]; Ms[3] += M[4]; Ms[4] += M[5]; Ms[5] += M[8];
+        ms[0] += m[0]; ms[1] += m[1]; ms[2] += m[2];
+
+        double *wj = v.wo + 6 * (size_t)e;
+        if (v.pose_fixed[j]) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) wj[k] = 0.0;
+            continue;
+        }
+        // N = Rj hat(p_bj);  J_j = B [-I N]
+        double N[9], MN[9], NMN[9];
+        mat3_mul_hat(RTj, pbj, N);
+        mat3_mul(M, N, MN);
+        mat3t_mul(N, MN, NMN);
+        // (j,j) += [[M, -MN],[-MN^T, N^T M N]]
+        double X[36];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                X[6 * a + b] = M[3 * a + b];
+                X[6 * a + 3 + b] = -MN[3 * a + b];
+                X[6 * (3 + a) + b] = -MN[3 * b + a];
+                X[6 * (3 + a) + 3 + b] = NMN[3 * a + b];
+            }
+        s_add_diag(v, j, X, 1.0);
+        {
+            double *hd = v.hdiag + v.pose_off[j];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) vio_add(hd + k, X[7 * k]);
+        }
+        // b_j -= [-I; N^T] m
+        double Ntm[3];
+        mat3t_mul_vec(N, m, Ntm);
+        {
+            double *bj = v.bp + v.pose_off[j];
+            vio_add(bj + 0, m[0]); vio_add(bj + 1, m[1]); vio_add(bj + 2, m[2]);
+            vio_add(bj + 3, -Ntm[0]); vio_add(bj + 4, -Ntm[1]); vio_add(bj + 5, -Ntm[2]);
+        }
+        // w_j = J_j^T W J_lambda = [-I; N^T] M g
+        double Mg[3], NtMg[3];
+        mat3_mul_vec(M, g, Mg);
+        mat3t_mul_vec(N, Mg, NtMg);
+        wj[0] = -Mg[0]; wj[1] = -Mg[1]; wj[2] = -Mg[2];
+        wj[3] = NtMg[0]; wj[4] = NtMg[1]; wj[5] = NtMg[2];
+        if (!hfix) {
+            // (h,j) = [I; G^T] M [-I N] = [[-M, MN],[-G^T M, G^T M N]]
+            double GtM[9], GtMN[9];
+            mat3t_mul(G, M, GtM);
+            mat3t_mul(G, MN, GtMN);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    X[6 * a + b] = -M[3 * a + b];
+                    X[6 * a + 3 + b] = MN[3 * a + b];
+                    X[6 * (3 + a) + b] = -GtM[3 * a + b];
+                    X[6 * (3 + a) + 3 + b] = GtMN[3 * a + b];
+                }
+            s_add_block(v, h, j, X, 1.0);
+        }
+    }
+    // landmark block and host blocks from the summed M
+    const double Msf[9] = {Ms[0], Ms[1], Ms[2], Ms[1], Ms[3], Ms[4], Ms[2], Ms[4], Ms[5]};
+    double Mg[3];
+    mat3_mul_vec(Msf, g, Mg);
+    const double Hll = g[0] * Mg[0] + g[1] * Mg[1] + g[2] * Mg[2];
+    const double bl = -(g[0] * ms[0] + g[1] * ms[1] + g[2] * ms[2]);
+    v.Hll[l] = Hll;
+    v.bl[l] = bl;
+    double wh[6] = {0, 0, 0, 0, 0, 0};
+    if (!hfix) {
+        double GtMg[3];
+        mat3t_mul_vec(G, Mg, GtMg);
+        wh[0] = Mg[0]; wh[1] = Mg[1]; wh[2] = Mg[2];
+        wh[3] = GtMg[0]; wh[4] = GtMg[1]; wh[5] = GtMg[2];
+        double MG[9], GtMG[9], X[36];
+        mat3_mul(Msf, G, MG);
+        mat3t_mul(G, MG, GtMG);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                X[6 * a + b] = Msf[3 * a + b];
+                X[6 * a + 3 + b] = MG[3 * a + b];
+                X[6 * (3 + a) + b] = MG[3 * b + a];
+                X[6 * (3 + a) + 3 + b] = GtMG[3 * a + b];
+            }
+        s_add_diag(v, h, X, 1.0);
+        double *hd = v.hdiag + v.pose_off[h];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) vio_add(hd + k, X[7 * k]);
+        double Gtm[3];
+        mat3t_mul_vec(G, ms, Gtm);
+        double *bh = v.bp + v.pose_off[h];
+        vio_add(bh + 0, -ms[0]); vio_add(bh + 1, -ms[1]); vio_add(bh + 2, -ms[2]);
+        vio_add(bh + 3, -Gtm[0]); vio_add(bh + 4, -Gtm[1]); vio_add(bh + 5, -Gtm[2]);
+    }
+    double *whp = v.wh + 6 * (size_t)l;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) whp[k] = wh[k];
+
+    if (!WITH_SCHUR) return;
+    // Schur complement: S -= Hpl Hll^-1 Hlp ; bS -= Hpl Hll^-1 bl     (landmark diagonal is never damped)
+    const double inv = 1.0 / Hll;
+    const int n = e1 - e0;
+    for (int a = -1; a < n; ++a) {
+        const int pa = a < 0 ? h : v.e_pose_j[e0 + a];
+        if (v.pose_fixed[pa]) continue;
+        double wa[6];
+        const double *wap = a < 0 ? whp : v.wo + 6 * (size_t)(e0 + a);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) wa[k] = wap[k] * inv;
+        double *bc = v.bcorr + v.pose_off[pa];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) vio_add(bc + k, wa[k] * bl);
+        for (int b = a; b < n; ++b) {
+            const int pb = b < 0 ? h : v.e_pose_j[e0 + b];
+            if (v.pose_fixed[pb]) continue;
+            const double *wbp = b < 0 ? whp : v.wo + 6 * (size_t)(e0 + b);
+            double X[36];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) X[6 * r + c] = wa[r] * wbp[c];
+            if (a == b) s_add_diag(v, pa, X, -1.0);
+            else s_add_block(v, pa, pb, X, -1.0);
+        }
+    }
+}
+
+template <bool WITH_SCHUR>
+__global__ void __launch_bounds__(128) k_linearize_lm(DevView v) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < v.L) linearize_landmark<WITH_SCHUR>(v, l);
+}
+
+// ------------------------------------------------------------------------------------------------
+// EdgeSE3Prior: r = [log(Rp^-1 Ri); Pi - Pp], J = [[0, JrInv(r_R)],[I, 0]]
+// ------------------------------------------------------------------------------------------------
+struct Se3PriorView {
+    int n;
+    const int *pose;
+    const double *p, *q, *info;
+};
+
+VIO_HD void se3prior_residual(const double *pose7, const double *pp, const double *qp, double r[6]) {
+    // SO3(Qi), SO3(Qp): both normalised by the Sophus constructor
+    double qi[4] = {pose7[3], pose7[4], pose7[5], pose7[6]};
+    double qpn[4] = {qp[0], qp[1], qp[2], qp[3]};
+    double ni = sqrt(qi[0] * qi[0] + qi[1] * qi[1] + qi[2] * qi[2] + qi[3] * qi[3]);
+    double np = sqrt(qpn[0] * qpn[0] + qpn[1] * qpn[1] + qpn[2] * qpn[2] + qpn[3] * qpn[3]);
+    for (int k = 0; k < 4; ++k) { qi[k] /= ni; qpn[k] /= np; }
+    const double qpc[4] = {-qpn[0], -qpn[1], -qpn[2], qpn[3]};  // SO3::inverse = conjugate
+    double qr[4];
+    quat_mul(qpc, qi, qr);
+    const double nr = sqrt(qr[0] * qr[0] + qr[1] * qr[1] + qr[2] * qr[2] + qr[3] * qr[3]);
+    for (int k = 0; k < 4; ++k) qr[k] /= nr;  // operator*= normalises
+    so3_log(qr, r);
+    r[3] = pose7[0] - pp[0];
+    r[4] = pose7[1] - pp[1];
+    r[5] = pose7[2] - pp[2];
+}
+
+VIO_HD void se3prior_edge(const DevView &v, const Se3PriorView &s, int i) {
+    const int a = s.pose[i];
+    if (v.pose_fixed[a]) return;
+    double r[6];
+    se3prior_residual(v.pose + 7 * (size_t)a, s.p + 3 * i, s.q + 4 * i, r);
+    double Jr[9];
+    so3_jr_inv(r, Jr);
+    double J[36];
+    for (int k = 0; k < 36; ++k) J[k] = 0.0;
+    for (int rr = 0; rr < 3; ++rr)
+        for (int c = 0; c < 3; ++c) J[6 * rr + 3 + c] = Jr[3 * rr + c];
+    J[6 * 3 + 0] = 1.0; J[6 * 4 + 1] = 1.0; J[6 * 5 + 2] = 1.0;
+    const double *Om = s.info + 36 * (size_t)i;
+    // JtW = J^T Om ; H = JtW J ; b -= JtW r
+    double JtW[36], X[36];
+    for (int rr = 0; rr < 6; ++rr)
+        for (int c = 0; c < 6; ++c) {
+            double t = 0;
+            for (int k = 0; k < 6; ++k) t += J[6 * k + rr] * Om[6 * k + c];
+            JtW[6 * rr + c] = t;
+        }
+    for (int rr = 0; rr < 6; ++rr)
+        for (int c = 0; c < 6; ++c) {
+            double t = 0;
+            for (int k = 0; k < 6; ++k) t += JtW[6 * rr + k] * J[6 * k + c];
+            X[6 * rr + c] = t;
+        }
+    s_add_diag(v, a, X, 1.0);
+    double *hd = v.hdiag + v.pose_off[a];
+    double *bp = v.bp + v.pose_off[a];
+    for (int rr = 0; rr < 6; ++rr) {
+        vio_add(hd + rr, X[7 * rr]);
+        double t = 0;
+        for (int k = 0; k < 6; ++k) t += JtW[6 * rr + k] * r[k];
+        vio_add(bp + rr, -t);
+    }
+}
+
+__global__ void k_se3prior(DevView v, Se3PriorView s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < s.n) se3prior_edge(v, s, i);
+}
+
+__global__ void k_se3prior_chi2(DevView v, Se3PriorView s, double *out /* accumulates */) {
+    // few edges: a single thread keeps the summation order fixed
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double chi = 0.0;
+    for (int i = 0; i < s.n; ++i) {
+        double r[6];
+        se3prior_residual(v.pose + 7 * (size_t)s.pose[i], s.p + 3 * i, s.q + 4 * i, r);
+        const double *Om = s.info + 36 * (size_t)i;
+        for (int a = 0; a < 6; ++a) {
+            double t = 0;
+            for (int b = 0; b < 6; ++b) t += Om[6 * a + b] * r[b];
+            chi += r[a] * t;
+        }
+    }
+    *out += chi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chi2 pass: Σ rho(c r.r) over reprojection edges; one thread per landmark (host chain shared)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_chi2_lm(DevView v, double *partial) {
+    double chi = 0.0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < v.L; l += gridDim.x * blockDim.x) {
+        const int e0 = v.lm_eptr[l], e1 = v.lm_eptr[l + 1];
+        if (e0 == e1) continue;
+        const int h = v.lm_host[l];
+        const double lam = v.invdep[l];
+        const double *RTh = v.poseRT + 16 * (size_t)h;
+        const double pci[3] = {v.lm_pix[l] / lam, v.lm_piy[l] / lam, v.lm_piz[l] / lam};
+        double pbi[3], pw[3];
+        mat3_mul_vec(v.Ric, pci, pbi);
+        pbi[0] += v.tic[0]; pbi[1] += v.tic[1]; pbi[2] += v.tic[2];
+        mat3_mul_vec(RTh, pbi, pw);
+        pw[0] += RTh[9]; pw[1] += RTh[10]; pw[2] += RTh[11];
+        for (int e = e0; e < e1; ++e) {
+            const double *RTj = v.poseRT + 16 * (size_t)v.e_pose_j[e];
+            double pcj[3], pbj[3], r[2];
+            reproj_residual(v.Ric, v.tic, RTj, pw, v.e_pjx[e], v.e_pjy[e], pcj, pbj, r);
+            const double e2 = v.rp_info * (r[0] * r[0] + r[1] * r[1]);
+            if (v.rp_loss == 0) chi += e2;
+            else {
+                double rho[3];
+                loss_compute(v.rp_loss, v.rp_delta, e2, rho);
+                chi += rho[0];
+            }
+        }
+    }
+    block_sum_to(chi, partial);
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize reduced system after (all-reduced) accumulation: mirror the upper triangle, bS = bp - bcorr
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mirror_dense(double *S, int P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (r < P && c < P && r > c) S[(size_t)r * P + c] = S[(size_t)c * P + r];
+}
+__global__ void k_mirror_bsr(DevView v) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= v.nnzb * 36) return;
+    const int id = (int)(t / 36), k = (int)(t % 36), r = k / 6, c = k % 6;
+    const int tr = v.bsr_tr[id];
+    if (tr == id) {  // diagonal block
+        if (r > c) v.S[36 * (size_t)id + k] = v.S[36 * (size_t)id + 6 * c + r];
+    } else if (tr < id) {  // lower block = transpose of its upper partner
+        v.S[36 * (size_t)id + k] = v.S[36 * (size_t)tr + 6 * c + r];
+    }
+}
+__global__ void k_finalize_b(DevView v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v.P) v.bS[i] = v.bp[i] - v.bcorr[i];
+}
+
+// max |diag(Hessian_)| : pose part from hdiag, landmark part from Hll
+__global__ void k_maxdiag(DevView v, double *partial) {
+    double m = 0.0;
+    const int n = v.P + v.L;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        m = fmax(m, fabs(i < v.P ? v.hdiag[i] : v.Hll[i - v.P]));
+    __shared__ double sm[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    m = warp_max(m);
+    if (lane == 0) sm[wid] = m;
+    __syncthreads();
+    if (wid == 0) {
+        double t = lane < ((blockDim.x + 31) >> 5) ? sm[lane] : 0.0;
+        t = warp_max(t);
+        if (lane == 0) partial[blockIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// back-substitution and the LM scalars of IsGoodStepInLM
+// ------------------------------------------------------------------------------------------------
+// dxl = Hll^-1 (bl - Hlp dxp); also partial sums of  dx_l (lambda dx_l + b_l)  and dx_l^2
+__global__ void __launch_bounds__(256) k_backsub(DevView v, double lambda, double *partial_scale, double *partial_n2) {
+    double sc = 0.0, n2 = 0.0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < v.L; l += gridDim.x * blockDim.x) {
+        const int e0 = v.lm_eptr[l], e1 = v.lm_eptr[l + 1];
+        if (e0 == e1) { v.dxl[l] = 0.0; continue; }
+        const double bl = v.bl[l];
+        double t = bl;
+        const double *wh = v.wh + 6 * (size_t)l;
+        const double *dh = v.dxp + v.pose_off[v.lm_host[l]];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) t -= wh[k] * dh[k];
+        for (int e = e0; e < e1; ++e) {
+            const double *w = v.wo + 6 * (size_t)e;
+            const double *dj = v.dxp + v.pose_off[v.e_pose_j[e]];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) t -= w[k] * dj[k];
+        }
+        const double d = t / v.Hll[l];
+        v.dxl[l] = d;
+        sc += d * (lambda * d + bl);
+        n2 += d * d;
+    }
+    block_sum_to(sc, partial_scale);
+    block_sum_to(n2, partial_n2);
+}
+
+__global__ void k_pose_scale(DevView v, double lambda, double *out_scale, double *out_n2) {
+    // P is small relative to M; single block, fixed order
+    __shared__ double s1[256], s2[256];
+    double sc = 0.0, n2 = 0.0;
+    for (int i = threadIdx.x; i < v.P; i += blockDim.x) {
+        const double d = v.dxp[i];
+        sc += d * (lambda * d + v.bp[i]);
+        n2 += d * d;
+    }
+    s1[threadIdx.x] = sc; s2[threadIdx.x] = n2;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { s1[threadIdx.x] += s1[threadIdx.x + s]; s2[threadIdx.x] += s2[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *out_scale = s1[0]; *out_n2 = s2[0]; }
+}
+
+// UpdateStates: backup + Plus.  sign = +1 (update) ; v15 rollback calls it again with sign = -1, no backup.
+VIO_HD void update_pose(const DevView &v, int i, double sign, int backup) {
+    double *p = v.pose + 7 * (size_t)i;
+    if (backup) {
+        double *b = v.pose_bak + 7 * (size_t)i;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) b[k] = p[k];
+    }
+    const double *d = v.dxp + v.pose_off[i];
+    p[0] += sign * d[0]; p[1] += sign * d[1]; p[2] += sign * d[2];
+    const double w[3] = {sign * d[3], sign * d[4], sign * d[5]};
+    double dq[4], q[4] = {p[3], p[4], p[5], p[6]}, qn[4];
+    so3_exp(w, dq);
+    quat_mul(q, dq, qn);  // right multiplication; the reference's q.normalized() result is discarded
+    p[3] = qn[0]; p[4] = qn[1]; p[5] = qn[2]; p[6] = qn[3];
+}
+__global__ void k_update_pose(DevView v, double sign, int backup) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v.C) update_pose(v, i, sign, backup);
+}
+__global__ void k_update_sb(DevView v, double sign, int backup) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.NSB) return;
+    double *p = v.sb + 9 * (size_t)i;
+    const double *d = v.dxp + v.sb_off[i];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        if (backup) v.sb_bak[9 * (size_t)i + k] = p[k];
+        p[k] += sign * d[k];
+    }
+}
+__global__ void k_update_lm(DevView v, double sign, int backup) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= v.L) return;
+    if (backup) v.invdep_bak[l] = v.invdep[l];
+    v.invdep[l] += sign * v.dxl[l];
+}
+__global__ void k_restore(DevView v) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)v.C * 7) v.pose[t] = v.pose_bak[t];
+    if (t < (long long)v.NSB * 9) v.sb[t] = v.sb_bak[t];
+    if (t < v.L) v.invdep[t] = v.invdep_bak[t];
+}

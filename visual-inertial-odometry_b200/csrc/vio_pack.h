@@ -1,0 +1,199 @@
+// vio_pack.h — host-side graph packer: vio_graph (caller's arrays) -> landmark-sorted SoA + ordering +
+// reduced-system sparsity pattern.  Pure C++ (no CUDA) so the same code feeds the device upload in
+// vio_set_graph and the CPU emulation harness in tests/.  Mirrors Problem::SetOrdering
+// (/root/reference/workspace/assignments/17-vins-initialization/vins-mono/src/backend/problem.cc:256-285):
+// pose-class vertices get consecutive offsets in creation order, landmarks follow.
+#pragma once
+#include <algorithm>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/vio_b200.h"
+
+struct PackedGraph {
+    int C = 0, NSB = 0, NB = 0, P = 0, L = 0, Lglobal = 0, storage = 1;
+    long long E = 0, nnzb = 0;
+    size_t s_count = 0;
+    std::vector<int> pose_off, sb_off, pose_blk, blk_off, blk_dim;
+    std::vector<uint8_t> blk_fixed, pose_fixed, sb_fixed, row_fixed;
+    double qic[4], tic[3];
+    std::vector<int> lm_global, lm_host, lm_eptr, e_pose_j;
+    std::vector<double> pix, piy, piz, pjx, pjy, invd;
+    std::vector<int> rowptr, col, tr, diag;
+};
+
+inline int pack_fail(std::string &err, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+}
+
+inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, PackedGraph &K, std::string &err) {
+    const int C = g->n_pose, NSB = g->n_speedbias, Lg = g->n_landmark;
+    const long long Eg = g->n_reproj;
+    if (C < 0 || NSB < 0 || Lg < 0 || Eg < 0) return pack_fail(err, VIO_ERR_INVALID, "negative size");
+    if (C > 0 && !g->pose) return pack_fail(err, VIO_ERR_INVALID, "pose array missing");
+    if (Eg > 0 && (!g->rp_landmark || !g->rp_pose_i || !g->rp_pose_j || !g->rp_pts_i || !g->rp_pts_j))
+        return pack_fail(err, VIO_ERR_INVALID, "reprojection arrays missing");
+    if (Eg > 0x7fffffffLL) return pack_fail(err, VIO_ERR_UNSUPPORTED, "more than 2^31 edges per shard");
+    // ---- ordering of the pose-class vertices (reference SetOrdering) -------------------------
+    const int NB = C + NSB;
+    std::vector<int> &pose_off = K.pose_off, &sb_off = K.sb_off, &pose_blk = K.pose_blk, &blk_off = K.blk_off, &blk_dim = K.blk_dim;
+    std::vector<uint8_t> &blk_fixed = K.blk_fixed;
+    pose_off.assign(C, -1); sb_off.assign(NSB, -1); pose_blk.assign(C, -1); blk_off.assign(NB, 0); blk_dim.assign(NB, 0); blk_fixed.assign(NB, 0);
+    int P = 0;
+    for (int k = 0; k < NB; ++k) {
+        int ent = g->pclass_order ? g->pclass_order[k] : (k < C ? k : ~(k - C));
+        if (ent >= 0) {
+            if (ent >= C || pose_off[ent] >= 0) return pack_fail(err, VIO_ERR_INVALID, "bad pclass_order entry %d", k);
+            pose_off[ent] = P; pose_blk[ent] = k; blk_off[k] = P; blk_dim[k] = 6;
+            blk_fixed[k] = g->pose_fixed ? g->pose_fixed[ent] : 0;
+            P += 6;
+        } else {
+            int i = ~ent;
+            if (i >= NSB || sb_off[i] >= 0) return pack_fail(err, VIO_ERR_INVALID, "bad pclass_order entry %d", k);
+            sb_off[i] = P; blk_off[k] = P; blk_dim[k] = 9;
+            blk_fixed[k] = g->speedbias_fixed ? g->speedbias_fixed[i] : 0;
+            P += 9;
+        }
+    }
+    // ---- extrinsics -----------------------------------------------------------------------------
+    double *qic = K.qic, *tic = K.tic;
+    if (g->ext_pose >= 0) {
+        if (g->ext_pose >= C) return pack_fail(err, VIO_ERR_INVALID, "ext_pose out of range");
+        if (!(g->pose_fixed && g->pose_fixed[g->ext_pose]))
+            return pack_fail(err, VIO_ERR_UNSUPPORTED, "extrinsic vertex must be fixed (ESTIMATE_EXTRINSIC=0 path)");
+        const double *e = g->pose + 7 * (size_t)g->ext_pose;
+        tic[0] = e[0]; tic[1] = e[1]; tic[2] = e[2];
+        qic[0] = e[3]; qic[1] = e[4]; qic[2] = e[5]; qic[3] = e[6];
+    } else {
+        for (int k = 0; k < 4; ++k) qic[k] = g->q_ic[k];
+        for (int k = 0; k < 3; ++k) tic[k] = g->t_ic[k];
+    }
+    // ---- landmark-sorted edge CSR (global), checks -------------------------------------------
+    std::vector<int> cnt(Lg + 1, 0);
+    for (long long e = 0; e < Eg; ++e) {
+        int l = g->rp_landmark[e];
+        if (l < 0 || l >= Lg) return pack_fail(err, VIO_ERR_INVALID, "edge %lld: landmark out of range", e);
+        int a = g->rp_pose_i[e], b = g->rp_pose_j[e];
+        if (a < 0 || a >= C || b < 0 || b >= C) return pack_fail(err, VIO_ERR_INVALID, "edge %lld: pose out of range", e);
+        cnt[l + 1]++;
+    }
+    for (int l = 0; l < Lg; ++l) cnt[l + 1] += cnt[l];
+    std::vector<int> eorder(Eg);
+    {
+        std::vector<int> cur(cnt.begin(), cnt.end() - 1);
+        for (long long e = 0; e < Eg; ++e) eorder[cur[g->rp_landmark[e]]++] = (int)e;
+    }
+    // shard: contiguous landmark ranges balanced by edge count
+    int l_begin = 0, l_end = Lg;
+    if (shard_world > 1) {
+        auto cut = [&](int r) -> int {
+            if (r <= 0) return 0;
+            if (r >= shard_world) return Lg;
+            long long target = Eg * r / shard_world;
+            return (int)(std::lower_bound(cnt.begin(), cnt.end(), (int)target) - cnt.begin());
+        };
+        l_begin = std::min(cut(shard_rank), Lg);
+        l_end = std::min(cut(shard_rank + 1), Lg);
+        if (l_end < l_begin) l_end = l_begin;
+    }
+    const int L = l_end - l_begin;
+    const long long E = (long long)cnt[l_end] - cnt[l_begin];
+    std::vector<int> &lm_host = K.lm_host, &lm_eptr = K.lm_eptr, &e_pose_j = K.e_pose_j;
+    std::vector<double> &pix = K.pix, &piy = K.piy, &piz = K.piz, &pjx = K.pjx, &pjy = K.pjy, &invd = K.invd;
+    lm_host.assign(L, 0); lm_eptr.assign(L + 1, 0); e_pose_j.assign(E, 0);
+    pix.assign(L, 0.0); piy.assign(L, 0.0); piz.assign(L, 1.0); pjx.assign(E, 0.0); pjy.assign(E, 0.0); invd.assign(L, 0.0);
+    K.lm_global.resize(L);
+    for (int ll = 0; ll < L; ++ll) {
+        const int l = l_begin + ll;
+        K.lm_global[ll] = l;
+        invd[ll] = g->inv_depth[l];
+        lm_eptr[ll] = cnt[l] - cnt[l_begin];
+        for (int k = cnt[l]; k < cnt[l + 1]; ++k) {
+            const int e = eorder[k];
+            const int le = k - cnt[l_begin];
+            if (k == cnt[l]) {
+                lm_host[ll] = g->rp_pose_i[e];
+                pix[ll] = g->rp_pts_i[3 * (size_t)e]; piy[ll] = g->rp_pts_i[3 * (size_t)e + 1]; piz[ll] = g->rp_pts_i[3 * (size_t)e + 2];
+            } else if (g->rp_pose_i[e] != lm_host[ll] || g->rp_pts_i[3 * (size_t)e] != pix[ll] ||
+                       g->rp_pts_i[3 * (size_t)e + 1] != piy[ll] || g->rp_pts_i[3 * (size_t)e + 2] != piz[ll]) {
+                return pack_fail(err, VIO_ERR_UNSUPPORTED,
+                            "landmark %d: edges disagree on host pose / host observation (see vio_b200.h preconditions)", l);
+            }
+            e_pose_j[le] = g->rp_pose_j[e];
+            pjx[le] = g->rp_pts_j[2 * (size_t)e];
+            pjy[le] = g->rp_pts_j[2 * (size_t)e + 1];
+        }
+    }
+    lm_eptr[L] = (int)E;
+
+    // ---- storage of the reduced system ----------------------------------------------------------
+    int storage = g->storage;
+    if (storage == VIO_STORAGE_AUTO) storage = (NSB == 0 && P > 2048) ? VIO_STORAGE_BSR : VIO_STORAGE_DENSE;
+    if (storage == VIO_STORAGE_BSR && (NSB != 0 || g->n_imu != 0))
+        return pack_fail(err, VIO_ERR_UNSUPPORTED, "BSR storage supports 6-dof pose vertices only");
+    size_t s_count;
+    long long nnzb = 0;
+    std::vector<int> &rowptr = K.rowptr, &col = K.col, &tr = K.tr, &diag = K.diag;
+    rowptr.clear(); col.clear(); tr.clear(); diag.clear();
+    if (storage == VIO_STORAGE_DENSE) {
+        if ((size_t)P * P * sizeof(double) > (size_t)16 << 30) return pack_fail(err, VIO_ERR_UNSUPPORTED, "dense S too large");
+        s_count = (size_t)P * P;
+    } else {
+        // global pattern (all shards must agree): co-visibility of every landmark + diagonal
+        std::vector<std::vector<int>> rows(NB);
+        for (int k = 0; k < NB; ++k) rows[k].push_back(k);
+        auto add = [&](int a, int b) {
+            auto &r = rows[a];
+            if (std::find(r.begin(), r.end(), b) == r.end()) r.push_back(b);
+        };
+        std::vector<int> set, last;
+        for (int l = 0; l < Lg; ++l) {
+            set.clear();
+            if (cnt[l] == cnt[l + 1]) continue;
+            set.push_back(pose_blk[g->rp_pose_i[eorder[cnt[l]]]]);
+            for (int k = cnt[l]; k < cnt[l + 1]; ++k) set.push_back(pose_blk[g->rp_pose_j[eorder[k]]]);
+            if (set == last) continue;
+            for (size_t a = 0; a < set.size(); ++a)
+                for (size_t b = 0; b < set.size(); ++b) add(set[a], set[b]);
+            last = set;
+        }
+        rowptr.assign(NB + 1, 0);
+        for (int k = 0; k < NB; ++k) {
+            std::sort(rows[k].begin(), rows[k].end());
+            rowptr[k + 1] = rowptr[k] + (int)rows[k].size();
+        }
+        nnzb = rowptr[NB];
+        col.resize(nnzb); tr.resize(nnzb); diag.resize(NB);
+        for (int k = 0; k < NB; ++k) std::copy(rows[k].begin(), rows[k].end(), col.begin() + rowptr[k]);
+        auto find = [&](int a, int b) -> int {
+            auto it = std::lower_bound(col.begin() + rowptr[a], col.begin() + rowptr[a + 1], b);
+            return (int)(it - col.begin());
+        };
+        for (int a = 0; a < NB; ++a)
+            for (int k = rowptr[a]; k < rowptr[a + 1]; ++k) {
+                tr[k] = find(col[k], a);
+                if (col[k] == a) diag[a] = k;
+            }
+        s_count = (size_t)nnzb * 36;
+    }
+
+    K.C = C; K.NSB = NSB; K.NB = NB; K.P = P; K.L = L; K.Lglobal = Lg; K.E = E; K.storage = storage; K.nnzb = nnzb;
+    K.s_count = s_count;
+    K.pose_fixed.assign(C, 0); K.sb_fixed.assign(NSB, 0);
+    if (g->pose_fixed) K.pose_fixed.assign(g->pose_fixed, g->pose_fixed + C);
+    if (g->speedbias_fixed) K.sb_fixed.assign(g->speedbias_fixed, g->speedbias_fixed + NSB);
+    K.row_fixed.assign(P, 0);
+    for (int k = 0; k < NB; ++k)
+        for (int d = 0; d < blk_dim[k]; ++d) K.row_fixed[blk_off[k] + d] = blk_fixed[k];
+    for (int i = 0; i < g->n_se3prior; ++i)
+        if (g->sp_pose[i] < 0 || g->sp_pose[i] >= C) return pack_fail(err, VIO_ERR_INVALID, "se3 prior %d: pose out of range", i);
+    return VIO_OK;
+}

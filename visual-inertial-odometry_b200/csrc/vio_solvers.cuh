@@ -1,0 +1,316 @@
+// vio_solvers.cuh — reduced camera system solvers (FP64).
+//   k_dense_chol_solve   (S + lambda I) x = b by Cholesky; replaces S.ldlt().solve  (A17/src/backend/problem.cc:434-440)
+//   k_ref_pcg            Problem::PCGSolver restated verbatim, including the missing first x update
+//                        (A15/backend/problem.cc:530-560)
+//   k_bpcg_*             6x6 block-Jacobi PCG on the block-sparse reduced system (large BA)
+#pragma once
+#include "vio_dev.h"
+#include "vio_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// dense Cholesky, one CTA.  A (P*P workspace) holds the lower triangle of S + lambda I.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_dense_chol_solve(const double *__restrict__ S, const double *__restrict__ b,
+                                                            double lambda, int P, double *__restrict__ A,
+                                                            double *__restrict__ x, int *info) {
+    extern __shared__ double colk[];  // P doubles: current column
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    for (size_t idx = tid; idx < (size_t)P * P; idx += nt) {
+        const int r = (int)(idx / P), c = (int)(idx % P);
+        if (c <= r) A[idx] = S[idx] + (r == c ? lambda : 0.0);
+    }
+    if (tid == 0) *info = 0;
+    __syncthreads();
+    for (int k = 0; k < P; ++k) {
+        const double d = A[(size_t)k * P + k];
+        if (tid == 0 && !(d > 0.0)) *info = k + 1;
+        const double dkk = sqrt(d);
+        for (int i = k + tid; i < P; i += nt) {
+            const double vv = (i == k) ? dkk : A[(size_t)i * P + k] / dkk;
+            colk[i] = vv;
+        }
+        __syncthreads();
+        for (int i = k + tid; i < P; i += nt) A[(size_t)i * P + k] = colk[i];
+        for (int i = k + 1 + warp; i < P; i += nw) {
+            const double aik = colk[i];
+            double *row = A + (size_t)i * P;
+            for (int j = k + 1 + lane; j <= i; j += 32) row[j] -= aik * colk[j];
+        }
+        __syncthreads();
+    }
+    // forward substitution L y = b (y in x)
+    for (int i = tid; i < P; i += nt) x[i] = b[i];
+    __syncthreads();
+    for (int k = 0; k < P; ++k) {
+        const double xk = x[k] / A[(size_t)k * P + k];
+        __syncthreads();
+        if (tid == 0) x[k] = xk;
+        for (int i = k + 1 + tid; i < P; i += nt) x[i] -= A[(size_t)i * P + k] * xk;
+        __syncthreads();
+    }
+    // backward substitution L^T z = y
+    for (int k = P - 1; k >= 0; --k) {
+        const double xk = x[k] / A[(size_t)k * P + k];
+        __syncthreads();
+        if (tid == 0) x[k] = xk;
+        for (int i = tid; i < k; i += nt) x[i] -= A[(size_t)k * P + i] * xk;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reference PCG (Jacobi preconditioner) on the dense reduced system, one CTA.
+// Vectors live in dynamic shared memory: x, r, p, w, minv (5*P doubles).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cta_sum(double v, double *red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int i = 0; i < nw; ++i) t += red[i];  // every thread sums in the same order
+    return t;
+}
+
+__global__ void __launch_bounds__(1024) k_ref_pcg(const double *__restrict__ S, const double *__restrict__ b,
+                                                   double lambda, int P, int max_iter, double *__restrict__ xout,
+                                                   int *iters_out) {
+    extern __shared__ double sm[];
+    double *x = sm, *r = sm + P, *p = sm + 2 * P, *w = sm + 3 * P, *minv = sm + 4 * P;
+    __shared__ double red[32];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    auto matvec = [&]() {  // w = (S + lambda I) p
+        for (int i = warp; i < P; i += nw) {
+            const double *row = S + (size_t)i * P;
+            double t = 0.0;
+            for (int j = lane; j < P; j += 32) t += row[j] * p[j];
+            t = warp_sum(t);
+            if (lane == 0) w[i] = t + lambda * p[i];
+        }
+        __syncthreads();
+    };
+    double l_r0z0 = 0.0, l_pw = 0.0, l_r0n = 0.0;
+    for (int i = tid; i < P; i += nt) {
+        x[i] = 0.0;
+        const double mi = 1.0 / (S[(size_t)i * P + i] + lambda);
+        minv[i] = mi;
+        const double ri = b[i];
+        r[i] = ri;
+        const double zi = mi * ri;
+        p[i] = zi;
+        l_r0z0 += ri * zi;
+        l_r0n += ri * ri;
+    }
+    __syncthreads();
+    double r0z0 = cta_sum(l_r0z0, red);
+    const double thr = 1e-6 * sqrt(cta_sum(l_r0n, red));
+    matvec();
+    for (int i = tid; i < P; i += nt) l_pw += p[i] * w[i];
+    double alpha = r0z0 / cta_sum(l_pw, red);
+    double l_rn = 0.0;
+    for (int i = tid; i < P; i += nt) {
+        r[i] -= alpha * w[i];  // r1 = r0 - alpha w ; NOTE: x is NOT updated here (reference defect)
+        l_rn += r[i] * r[i];
+    }
+    double rn = sqrt(cta_sum(l_rn, red));
+    int it = 0;
+    while (rn > thr && it < max_iter) {
+        ++it;
+        double l_r1z1 = 0.0;
+        for (int i = tid; i < P; i += nt) l_r1z1 += r[i] * (minv[i] * r[i]);
+        const double r1z1 = cta_sum(l_r1z1, red);
+        const double beta = r1z1 / r0z0;
+        r0z0 = r1z1;
+        for (int i = tid; i < P; i += nt) p[i] = beta * p[i] + minv[i] * r[i];
+        __syncthreads();
+        matvec();
+        double l2 = 0.0;
+        for (int i = tid; i < P; i += nt) l2 += p[i] * w[i];
+        alpha = r1z1 / cta_sum(l2, red);
+        double l3 = 0.0;
+        for (int i = tid; i < P; i += nt) {
+            x[i] += alpha * p[i];
+            r[i] -= alpha * w[i];
+            l3 += r[i] * r[i];
+        }
+        rn = sqrt(cta_sum(l3, red));
+    }
+    __syncthreads();
+    for (int i = tid; i < P; i += nt) xout[i] = x[i];
+    if (tid == 0) *iters_out = it;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-Jacobi PCG on BSR (6x6 blocks).  Three kernels per iteration, no host round trip:
+// every block re-sums the previous kernel's partials in a fixed order, so all blocks see bitwise
+// identical scalars and the run is deterministic.
+//   scal[0]=rz (parity 0) scal[1]=rz (parity 1) scal[2]=bnorm2 scal[3]=done scal[4]=iterations scal[5]=rr
+// ------------------------------------------------------------------------------------------------
+#define BPCG_MAXPART 1024
+
+__device__ __forceinline__ double sum_partials_all(const double *part, int n, double *red) {
+    // all threads of the block return the same, order-fixed sum
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t += part[i];
+    return cta_sum(t, red);
+}
+
+__device__ __forceinline__ void inv6_spd(const double *A /*36 row-major*/, double *Ai) {
+    // Cholesky based inverse of a 6x6 SPD block
+    double L[36];
+    for (int k = 0; k < 36; ++k) L[k] = 0.0;
+    for (int j = 0; j < 6; ++j) {
+        double d = A[7 * j];
+        for (int k = 0; k < j; ++k) d -= L[6 * j + k] * L[6 * j + k];
+        d = sqrt(d);
+        L[7 * j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = A[6 * i + j];
+            for (int k = 0; k < j; ++k) s -= L[6 * i + k] * L[6 * j + k];
+            L[6 * i + j] = s / d;
+        }
+    }
+    // invert L (lower) -> Li
+    double Li[36];
+    for (int k = 0; k < 36; ++k) Li[k] = 0.0;
+    for (int j = 0; j < 6; ++j) {
+        Li[7 * j] = 1.0 / L[7 * j];
+        for (int i = j + 1; i < 6; ++i) {
+            double s = 0.0;
+            for (int k = j; k < i; ++k) s -= L[6 * i + k] * Li[6 * k + j];
+            Li[6 * i + j] = s / L[7 * i];
+        }
+    }
+    // Ai = Li^T Li
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+            for (int k = (r > c ? r : c); k < 6; ++k) s += Li[6 * k + r] * Li[6 * k + c];
+            Ai[6 * r + c] = s;
+        }
+}
+
+struct BpcgView {
+    int nb;  // block rows
+    const int *rowptr, *col, *diag;
+    const double *val, *b;
+    double *minv, *x, *r, *z, *p, *w;
+    double *part_a, *part_b;  // BPCG_MAXPART each
+    double *scal;
+    double lambda, tol;
+};
+
+__global__ void __launch_bounds__(256) k_bpcg_init(BpcgView s) {
+    __shared__ double red[32];
+    double l_rz = 0.0, l_bb = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.nb; i += gridDim.x * blockDim.x) {
+        double A[36], Ai[36];
+        const double *d = s.val + 36 * (size_t)s.diag[i];
+        for (int k = 0; k < 36; ++k) A[k] = d[k];
+        for (int k = 0; k < 6; ++k) A[7 * k] += s.lambda;
+        inv6_spd(A, Ai);
+        double *mo = s.minv + 36 * (size_t)i;
+        for (int k = 0; k < 36; ++k) mo[k] = Ai[k];
+        double rb[6];
+        for (int k = 0; k < 6; ++k) rb[k] = s.b[6 * (size_t)i + k];
+        for (int r = 0; r < 6; ++r) {
+            double z = 0.0;
+            for (int c = 0; c < 6; ++c) z += Ai[6 * r + c] * rb[c];
+            const size_t o = 6 * (size_t)i + r;
+            s.x[o] = 0.0; s.r[o] = rb[r]; s.z[o] = z; s.p[o] = z;
+            l_rz += rb[r] * z;
+            l_bb += rb[r] * rb[r];
+        }
+    }
+    const double a = cta_sum(l_rz, red), bb = cta_sum(l_bb, red);
+    if (threadIdx.x == 0) { s.part_a[blockIdx.x] = a; s.part_b[blockIdx.x] = bb; }
+}
+__global__ void k_bpcg_init2(BpcgView s, int nparts) {
+    __shared__ double red[32];
+    const double rz = sum_partials_all(s.part_a, nparts, red);
+    const double bb = sum_partials_all(s.part_b, nparts, red);
+    if (threadIdx.x == 0) {
+        s.scal[0] = rz; s.scal[1] = rz; s.scal[2] = bb; s.scal[4] = 0.0; s.scal[5] = bb;
+        s.scal[3] = (bb == 0.0) ? 1.0 : 0.0;
+    }
+}
+
+// w = (S + lambda I) p ; partial p.w     (6 threads per block row)
+__global__ void __launch_bounds__(192) k_bpcg_spmv(BpcgView s) {
+    __shared__ double red[32];
+    if (s.scal[3] != 0.0) return;
+    double pw = 0.0;
+    const int n = 6 * s.nb;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const int i = t / 6, rr = t % 6;
+        double acc = 0.0;
+        for (int k = s.rowptr[i]; k < s.rowptr[i + 1]; ++k) {
+            const double *a = s.val + 36 * (size_t)k + 6 * rr;
+            const double *pp = s.p + 6 * (size_t)s.col[k];
+            acc += a[0] * pp[0] + a[1] * pp[1] + a[2] * pp[2] + a[3] * pp[3] + a[4] * pp[4] + a[5] * pp[5];
+        }
+        const double pi = s.p[t];
+        acc += s.lambda * pi;
+        s.w[t] = acc;
+        pw += pi * acc;
+    }
+    const double a = cta_sum(pw, red);
+    if (threadIdx.x == 0) s.part_a[blockIdx.x] = a;
+}
+
+// alpha = rz / p.w ; x += alpha p ; r -= alpha w ; z = Minv r ; partial r.z, r.r   (thread per block row)
+__global__ void __launch_bounds__(128) k_bpcg_update(BpcgView s, int nparts_in, int par) {
+    __shared__ double red[32];
+    if (s.scal[3] != 0.0) return;
+    const double pw = sum_partials_all(s.part_a, nparts_in, red);
+    const double alpha = s.scal[par] / pw;
+    double l_rz = 0.0, l_rr = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.nb; i += gridDim.x * blockDim.x) {
+        double rn[6];
+        for (int k = 0; k < 6; ++k) {
+            const size_t o = 6 * (size_t)i + k;
+            s.x[o] += alpha * s.p[o];
+            rn[k] = s.r[o] - alpha * s.w[o];
+            s.r[o] = rn[k];
+            l_rr += rn[k] * rn[k];
+        }
+        const double *mi = s.minv + 36 * (size_t)i;
+        for (int r = 0; r < 6; ++r) {
+            double z = 0.0;
+            for (int c = 0; c < 6; ++c) z += mi[6 * r + c] * rn[c];
+            s.z[6 * (size_t)i + r] = z;
+            l_rz += rn[r] * z;
+        }
+    }
+    const double a = cta_sum(l_rz, red), b = cta_sum(l_rr, red);
+    if (threadIdx.x == 0) { s.part_b[blockIdx.x] = a; s.part_a[BPCG_MAXPART + blockIdx.x] = b; }
+}
+
+// beta = rz' / rz ; p = z + beta p ; convergence test ; bookkeeping
+__global__ void __launch_bounds__(256) k_bpcg_dir(BpcgView s, int nparts_in, int par, int max_iter) {
+    __shared__ double red[32];
+    if (s.scal[3] != 0.0) return;
+    const double rz_new = sum_partials_all(s.part_b, nparts_in, red);
+    const double rr = sum_partials_all(s.part_a + BPCG_MAXPART, nparts_in, red);
+    const double beta = rz_new / s.scal[par];
+    const bool done = !(sqrt(rr) > s.tol * sqrt(s.scal[2])) || (s.scal[4] + 1.0 >= (double)max_iter);
+    if (!done) {
+        const int n = 6 * s.nb;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            s.p[i] = s.z[i] + beta * s.p[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        s.scal[par ^ 1] = rz_new;
+        s.scal[5] = rr;
+        s.scal[6] = s.scal[4] + 1.0;  // staged; committed by k_bpcg_commit to avoid intra-kernel races
+        s.scal[7] = done ? 1.0 : 0.0;
+    }
+}
+__global__ void k_bpcg_commit(BpcgView s) {
+    if (s.scal[3] != 0.0) return;
+    s.scal[4] = s.scal[6];
+    s.scal[3] = s.scal[7];
+}
