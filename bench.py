@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — LM hot-path throughput on synthetic BA (BASELINE.json: "reprojection edges/sec + LM iters/sec").
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, landmark-sharded when N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, bounded sample
+
+A "step" is one Levenberg-Marquardt iteration of backend::Problem::Solve over the whole scene: reduced solve +
+back-substitution + state update + chi2 pass + (accepted) re-linearisation with MakeHessian + Schur.
+`value` = E x K / t with all inputs resident in HBM; `e2e` = the same through the C-ABI with HOST state buffers
+(vio_set_vertices H2D -> vio_solve(1) -> vio_get_vertices D2H per step, pinned host memory).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "visual-inertial-odometry_b200"
+
+WORKLOADS = {
+    # BASELINE.json configs[4] / configs[3]; ring generator of SURVEY.md §8(d)
+    "config5_ba_10k_cams_1m_landmarks_10m_obs": dict(n_cam=10000, n_landmark=1000000, k_obs=11, seed=5),
+    "config4_ba_1k_cams_100k_landmarks_1m_obs": dict(n_cam=1000, n_landmark=100000, k_obs=11, seed=4),
+    "tiny_ba_100_cams_10k_landmarks": dict(n_cam=100, n_landmark=10000, k_obs=11, seed=3),
+}
+DEFAULT_WORKLOAD = "config5_ba_10k_cams_1m_landmarks_10m_obs"
+METRIC = "reprojection_edges_per_sec"
+UNIT = "edges/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm, reasons, mx = [], set(), 0.0
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+                for n, v in zip(names, s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def alg_bytes_linearize(E, L, C, nnzb):
+    """SURVEY.md §8(d) per-pass figure for linearise+Schur: 52 E + 24 L + 56 C + 8 (nnz(S) + P)."""
+    return 52.0 * E + 24.0 * L + 56.0 * C + 8.0 * (36.0 * nnzb + 6.0 * C)
+
+
+def alg_flops_linearize(E, k_obs):
+    """400 linearise + 416 JtWJ/Jtr + Schur (n(n+1)+3n)/(K-1), n = 6K, per edge."""
+    n = 6.0 * k_obs
+    return E * (400.0 + 416.0 + (n * (n + 1) + 3 * n) / (k_obs - 1))
+
+
+def sub_scene(vio, s, lm_begin, lm_end, with_ext):
+    """Landmarks [lm_begin, lm_end) of a ring scene with their edges and the poses they touch (renumbered)."""
+    e0 = int(np.searchsorted(s.rp_landmark, lm_begin, side="left"))
+    e1 = int(np.searchsorted(s.rp_landmark, lm_end, side="left"))
+    poses = np.unique(np.concatenate([s.rp_pose_i[e0:e1], s.rp_pose_j[e0:e1]]))
+    remap = -np.ones(s.pose.shape[0], np.int64)
+    base = 1 if with_ext else 0
+    remap[poses] = np.arange(len(poses)) + base
+    t = vio.Scene()
+    t.pose = s.pose[poses]
+    if with_ext:
+        t.pose = np.vstack([np.array([[0, 0, 0, 0, 0, 0, 1.0]]), t.pose])
+        t.pose_fixed = np.zeros(t.pose.shape[0], np.uint8)
+        t.pose_fixed[0] = 1
+        t.ext_pose = 0
+    t.inv_depth = s.inv_depth[lm_begin:lm_end].copy()
+    t.rp_landmark = (s.rp_landmark[e0:e1] - lm_begin).astype(np.int32)
+    t.rp_pose_i = remap[s.rp_pose_i[e0:e1]].astype(np.int32)
+    t.rp_pose_j = remap[s.rp_pose_j[e0:e1]].astype(np.int32)
+    t.rp_pts_i = s.rp_pts_i[e0:e1].copy()
+    t.rp_pts_j = s.rp_pts_j[e0:e1].copy()
+    # gauge: SE3 priors on the first two cameras of the sample, like the generator's cameras 0 and 1
+    t.sp_pose = np.array([base, base + 1], np.int32)
+    t.sp_p = s.pose_gt[poses[:2], :3].copy()
+    t.sp_q = s.pose_gt[poses[:2], 3:].copy()
+    t.sp_info = np.tile((np.eye(6) * 1e4).reshape(1, 36), (2, 1))
+    return t
+
+
+def cpu_reference_rate(vio, scene, steps, warmup, target_s=12.0):
+    """The reference's own CPU path on a bounded sample of the workload.
+
+    oracle/_ref present -> the UNMODIFIED v17 backend: Problem::Solve(1) (MakeHessian + Schur + LDLT + chi2) on a
+    sample of landmarks small enough for its dense (P+M)^2 containers.  Otherwise the plain-C oracle port.
+    Single thread: the reference has no active threading.
+    """
+    from tests import oraclelib as orc
+    from tests import refshim
+    L = scene.inv_depth.shape[0]
+    out = {"cores": 1}
+    if refshim.available(17):
+        n_lm = min(2000, L)
+        sub = sub_scene(vio, scene, 0, n_lm, with_ext=True)
+        E_s = sub.rp_landmark.shape[0]
+        times = []
+        for k in range(warmup + steps):
+            # steady-state cost of one LM iteration = (t[Solve(3)] - t[Solve(1)]) / 2: removes the initial
+            # MakeHessian + ComputeLambdaInitLM that our warm-started timed region does not contain either
+            t0 = time.perf_counter()
+            r1 = refshim.solve(17, sub, 1)
+            t1 = time.perf_counter()
+            r3 = refshim.solve(17, sub, 3)
+            t3 = time.perf_counter()
+            extra = max(r3["iterations"] - r1["iterations"], 1)
+            dt = ((t3 - t1) - (t1 - t0)) / extra
+            if k >= warmup:
+                times.append(dt)
+            if sum(times) > target_s and len(times) >= 1:
+                break
+        t = float(np.mean(times))
+        out.update(kind="reference", value=E_s / t, unit=UNIT, ms_per_step=t * 1e3, steps_run=len(times),
+                   sample=f"unmodified v17 backend::Problem::Solve(1) on landmarks [0,{n_lm}) of the workload "
+                          f"({E_s} edges, {sub.pose.shape[0]} poses; dense (P+M)^2 containers cap the sample size); "
+                          f"edges/s = E_sample / steady-state time per LM iteration (t[Solve(3)]-t[Solve(1)])/2")
+    else:
+        orc.lib()
+        n_cal = min(20000, L)
+        t0 = time.perf_counter()
+        orc.linearize_sample(scene, 0, n_cal)
+        t_cal = time.perf_counter() - t0
+        n_lm = int(min(L, max(n_cal, n_cal * (target_s / max(steps, 1)) / max(t_cal, 1e-6))))
+        e1 = int(np.searchsorted(scene.rp_landmark, n_lm, side="left"))
+        times = []
+        for k in range(steps):
+            t0 = time.perf_counter()
+            orc.linearize_sample(scene, 0, n_lm)
+            times.append(time.perf_counter() - t0)
+            if sum(times) > target_s:
+                break
+        t = float(np.mean(times))
+        out.update(kind="port", value=e1 / t, unit=UNIT, ms_per_step=t * 1e3, steps_run=len(times),
+                   sample=f"plain-C oracle port, MakeHessian+Schur pass over landmarks [0,{n_lm}) ({e1} edges); reduced "
+                          f"solve not included")
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vio = importlib.import_module(PKG)
+    wl = WORKLOADS[args.workload]
+    scene = vio.scenes.ring(**wl)
+    r = cpu_reference_rate(vio, scene, args.steps, min(args.warmup, 1), target_s=60.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps_run"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, **wl},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": {"nproc": os.cpu_count()},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    vio = importlib.import_module(PKG)
+    capi = vio.capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = WORKLOADS[args.workload]
+    t0 = time.perf_counter()
+    scene = vio.scenes.ring(**wl)
+    t_gen = time.perf_counter() - t0
+    E = int(scene.rp_landmark.shape[0])
+    L = int(scene.inv_depth.shape[0])
+    C = int(scene.pose.shape[0])
+    scene.storage = capi.STORAGE_BSR
+
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        p = vio.Problem(device=local_rank, stream=stream.cuda_stream)
+        if world > 1:
+            p.set_shard(rank, world)
+            p.set_allreduce(importlib.import_module(PKG + ".dist").make_allreduce_hook())
+        t0 = time.perf_counter()
+        p.set_graph(scene)
+        t_pack = time.perf_counter() - t0
+        d = p.dims()
+        nnzb = int(d.nnz_blocks)
+        E_local = int(d.n_reproj)
+
+        def barrier():
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        cold = vio.make_opts(flavour=capi.LM_V17, solver=capi.SOLVER_BLOCK_PCG, fixed_iterations=1)
+        warm = vio.make_opts(flavour=capi.LM_V17, solver=capi.SOLVER_BLOCK_PCG, fixed_iterations=1, warm_start=1)
+        # ---- HBM-resident timing: W warm-up LM iterations, then exactly K timed ones ---------------------
+        st_w = p.solve(args.warmup, cold)
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        launches0 = p.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        st = p.solve(args.steps, warm)
+        ev1.record(stream)
+        barrier()
+        launches = p.launch_count() - launches0
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        lin_ms, lin_n = p.kernel_ms()  # CUDA events around the linearise kernel on the handle's stream
+        if dist is not None:
+            t = torch.tensor([lin_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lin_ms = float(t.item())
+        # ---- end to end through the C-ABI with host state buffers -------------------------------------------
+        pose_h = torch.empty((C, 7), dtype=torch.float64).pin_memory()
+        invd_h = torch.empty((L,), dtype=torch.float64).pin_memory()
+        pose_np, invd_np = pose_h.numpy(), invd_h.numpy()
+        pose_np[:] = scene.pose
+        invd_np[:] = scene.inv_depth
+        e2e_steps = max(1, min(args.steps, 5))
+        for k in range(2):
+            p.set_vertices(pose=pose_np, inv_depth=invd_np)
+            p.solve(1, cold)
+            p.get_vertices()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            p.set_vertices(pose=pose_np, inv_depth=invd_np)
+            p.solve(1, cold)
+            po, _, iv = p.get_vertices()
+            pose_np[:] = po
+            invd_np[:] = iv
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        if sampler:
+            sampler.stop_flag = True
+            sampler.join(timeout=2)
+        fp64_peak = capi.measure_fp64_peak(local_rank) if rank == 0 else None
+
+    if rank == 0:
+        value = E * st.iterations / (ms * 1e-3)
+        hbm_peak, peak_src = measured_peaks()
+        E_k, L_k = E_local, int(d.reserved)
+        bytes_alg = alg_bytes_linearize(E_k, L_k, C, nnzb)
+        flops_alg = alg_flops_linearize(E_k, wl["k_obs"])
+        ach_gbs = bytes_alg / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else None
+        ach_tf = flops_alg / (lin_ms * 1e-3) / 1e12 if lin_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": int(st.iterations),
+            "warmup": int(args.warmup), "ms_per_step": ms / max(st.iterations, 1), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "lm_iters_per_sec": st.iterations / (ms * 1e-3),
+            "config": {"workload": args.workload, **wl, "edges": E, "landmarks": L, "cameras": C,
+                       "lm_flavour": "v17", "reduced_solver": "block_pcg_6x6", "pcg_tol": 1e-6,
+                       "parallelism": f"landmark_shard{world}", "l2": "inputs (>=520 MB of edge records) larger than L2",
+                       "scene_gen_s": round(t_gen, 2), "pack_upload_s": round(t_pack, 2)},
+            "lm": {"trial_steps": int(st.trial_steps), "accepted": int(st.accepted_steps),
+                   "linearizations": int(st.linearizations), "pcg_iterations": int(st.pcg_iterations),
+                   "chi2_start": st.chi2_trace[0] if st.n_trace else None, "chi2_final": st.chi2_final,
+                   "warmup_chi2_initial": st_w.chi2_initial},
+            "roofline": {"bound": "hbm", "kernel": "k_linearize_lm (linearise + JtWJ + Schur)",
+                         "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": (ach_gbs / hbm_peak) if ach_gbs else None, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_alg, "kernel_ms": lin_ms, "kernel_launches_timed": int(lin_n),
+                         "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                                  "frac": (ach_tf / fp64_peak) if (ach_tf and fp64_peak) else None,
+                                  "algorithmic_flops_per_launch": flops_alg,
+                                  "peak_source": "measured DFMA micro-benchmark (vio_measure_fp64_peak) in this run"},
+                         "binding": "fp64" if (ach_tf and fp64_peak and ach_gbs and ach_tf / fp64_peak > ach_gbs / hbm_peak) else "hbm"},
+            "e2e": {"value": E * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(pose_np.nbytes + invd_np.nbytes),
+                    "d2h_bytes_per_step": int(pose_np.nbytes + invd_np.nbytes), "steps": e2e_steps,
+                    "call": "vio_set_vertices(host) -> vio_solve(1) -> vio_get_vertices(host)"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary() if sampler else None,
+        }
+        if world == 1 and not args.no_cpu:
+            cb = cpu_reference_rate(vio, scene, steps=3, warmup=1, target_s=12.0)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
+                                    "sample": cb["sample"]}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -124,7 +124,8 @@ typedef struct vio_lm_opts {
     int32_t pcg_max_iter;   /* block PCG cap; <=0: 2*P like the reference call site          */
     double pcg_tol;         /* relative residual; <=0: 1e-6 (A15/backend/problem.cc:544)      */
     int32_t fixed_iterations; /* 1: ignore the reference's convergence stop rules (benchmark) */
-    int32_t reserved;
+    int32_t warm_start;     /* 1: continue the previous vio_solve on this handle (keep its linearisation,
+                               lambda, chi2, nu) instead of MakeHessian + ComputeLambdaInitLM            */
 } vio_lm_opts;
 
 #define VIO_TRACE_MAX 256
@@ -167,6 +168,9 @@ int vio_create(int device, void *cuda_stream /* cudaStream_t or NULL = own strea
 void vio_destroy(vio_problem *p);
 const char *vio_last_error(const vio_problem *p);
 const char *vio_version(void);
+/* sizeof of the ABI structs as this library was compiled (0 vio_graph, 1 vio_lm_opts, 2 vio_stats, 3 vio_dims):
+ * lets a foreign-language binding verify its struct layout at load time */
+size_t vio_struct_size(int which);
 int vio_device_count(void);
 
 /* ---- graph / state -------------------------------------------------------------------------- */

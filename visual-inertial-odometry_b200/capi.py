@@ -45,7 +45,7 @@ class VioGraph(C.Structure):
 class VioLmOpts(C.Structure):
     _fields_ = [
         ("flavour", C.c_int32), ("solver", C.c_int32), ("verbose", C.c_int32), ("pcg_max_iter", C.c_int32),
-        ("pcg_tol", C.c_double), ("fixed_iterations", C.c_int32), ("reserved", C.c_int32),
+        ("pcg_tol", C.c_double), ("fixed_iterations", C.c_int32), ("warm_start", C.c_int32),
     ]
 
 
@@ -73,7 +73,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_
 
 # every symbol include/vio_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "vio_create", "vio_destroy", "vio_last_error", "vio_version", "vio_device_count", "vio_set_graph", "vio_get_dims",
+    "vio_create", "vio_destroy", "vio_last_error", "vio_version", "vio_struct_size", "vio_device_count", "vio_set_graph", "vio_get_dims",
     "vio_set_allreduce", "vio_set_shard", "vio_set_prior", "vio_get_prior", "vio_set_vertices", "vio_get_vertices",
     "vio_solve", "vio_linearize", "vio_chi2", "vio_solve_step", "vio_apply_step", "vio_rollback_step",
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
@@ -91,6 +91,12 @@ def lib():
             raise RuntimeError(f"{LIB_PATH} missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
         L = C.CDLL(LIB_PATH)
         L.vio_version.restype = C.c_char_p
+        L.vio_struct_size.restype = C.c_size_t
+        L.vio_struct_size.argtypes = [C.c_int]
+        for which, cls in enumerate((VioGraph, VioLmOpts, VioStats, VioDims)):
+            if L.vio_struct_size(which) != C.sizeof(cls):
+                raise RuntimeError(f"ABI mismatch: {cls.__name__} is {C.sizeof(cls)} bytes here, "
+                                   f"{L.vio_struct_size(which)} in libvio_b200.so")
         L.vio_last_error.restype = C.c_char_p
         L.vio_last_error.argtypes = [C.c_void_p]
         L.vio_launch_count.restype = C.c_int64
@@ -241,6 +247,47 @@ class Scene:
     def P(self):
         return 6 * self.pose.shape[0] + 9 * self.speedbias.shape[0]
 
+    _ARRAYS = ("pose", "pose_fixed", "speedbias", "speedbias_fixed", "pclass_order", "inv_depth", "rp_landmark",
+               "rp_pose_i", "rp_pose_j", "rp_pts_i", "rp_pts_j", "q_ic", "t_ic", "sp_pose", "sp_p", "sp_q", "sp_info",
+               "gravity", "pose_gt", "inv_depth_gt")
+    _SCALARS = ("rp_info", "rp_loss", "rp_loss_delta", "ext_pose", "storage")
+
+    def export(self):
+        """-> dict of numpy arrays (np.savez) holding the whole scene, including IMU constants and prior."""
+        self._norm()
+        d = {}
+        for k in self._ARRAYS:
+            v = getattr(self, k)
+            if v is not None:
+                d[k] = np.asarray(v)
+        for k in self._SCALARS:
+            d[k] = np.asarray(getattr(self, k))
+        if self.imu is not None:
+            for k, v in self.imu.items():
+                d["imu_" + k] = np.asarray(v)
+        if self.prior is not None:
+            for k, v in self.prior.items():
+                if v is not None:
+                    d["prior_" + k] = np.asarray(v)
+        return d
+
+    @classmethod
+    def from_dict(cls, d):
+        s = cls()
+        for k in cls._ARRAYS:
+            if k in d:
+                setattr(s, k, np.array(d[k]))
+        for k in cls._SCALARS:
+            if k in d:
+                v = d[k].item() if hasattr(d[k], "item") else d[k]
+                setattr(s, k, v)
+        imu = {k[4:]: np.array(d[k]) for k in d if k.startswith("imu_")}
+        s.imu = imu or None
+        pr = {k[6:]: np.array(d[k]) for k in d if k.startswith("prior_")}
+        s.prior = pr or None
+        s._norm()
+        return s
+
 
 class VioError(RuntimeError):
     def __init__(self, code, msg):
@@ -248,10 +295,11 @@ class VioError(RuntimeError):
         self.code = code
 
 
-def make_opts(flavour=LM_V17, solver=SOLVER_AUTO, verbose=0, pcg_max_iter=0, pcg_tol=0.0, fixed_iterations=0):
+def make_opts(flavour=LM_V17, solver=SOLVER_AUTO, verbose=0, pcg_max_iter=0, pcg_tol=0.0, fixed_iterations=0,
+              warm_start=0):
     o = VioLmOpts()
     o.flavour, o.solver, o.verbose = flavour, solver, verbose
-    o.pcg_max_iter, o.pcg_tol, o.fixed_iterations = pcg_max_iter, pcg_tol, fixed_iterations
+    o.pcg_max_iter, o.pcg_tol, o.fixed_iterations, o.warm_start = pcg_max_iter, pcg_tol, fixed_iterations, warm_start
     return o
 
 

@@ -37,6 +37,8 @@ struct vio_problem {
     std::string err;
     bool has_graph = false;
     bool linearized = false;
+    bool lm_valid = false;  // lambda/chi/ni below continue a previous vio_solve (opts.warm_start)
+    double lm_lambda = 0.0, lm_chi = 0.0, lm_ni = 2.0, lm_stop_thr = 0.0;
     int64_t launches = 0;
     vio_allreduce_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
@@ -409,6 +411,16 @@ extern "C" {
 
 const char *vio_version(void) { return VIO_VERSION_STR; }
 
+size_t vio_struct_size(int which) {
+    switch (which) {
+        case 0: return sizeof(vio_graph);
+        case 1: return sizeof(vio_lm_opts);
+        case 2: return sizeof(vio_stats);
+        case 3: return sizeof(vio_dims);
+        default: return 0;
+    }
+}
+
 int vio_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -486,6 +498,7 @@ int vio_set_graph(vio_problem *p, const vio_graph *g) {
     CK(cudaSetDevice(p->device));
     p->has_graph = false;
     p->linearized = false;
+    p->lm_valid = false;
     PackedGraph K;
     {
         int rc = pack_graph(g, p->shard_rank, p->shard_world, K, p->err);
@@ -594,6 +607,7 @@ int vio_set_vertices(vio_problem *p, const double *pose, const double *sb, const
     }
     CK(cudaStreamSynchronize(p->stream));
     p->linearized = false;
+    p->lm_valid = false;
     return VIO_OK;
 }
 
@@ -685,16 +699,20 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
         rc = (x);                   \
         if (rc) return rc;          \
     } while (0)
-    // MakeHessian ; ComputeLambdaInitLM
-    RC(do_linearize(p, o, true));
-    st->linearizations++;
-    double chi = 0.0, maxdiag = 0.0;
-    RC(do_chi2(p, o, &chi));
-    RC(do_maxdiag(p, &maxdiag));
-    if (!v15) maxdiag = std::min(5e10, maxdiag);
-    double lambda = 1e-5 * maxdiag;
-    double ni = 2.0;
-    const double stop_thr = 1e-6 * chi;  // v15 only
+    double chi = 0.0, maxdiag = 0.0, lambda, ni = 2.0, stop_thr;
+    if (o.warm_start && p->lm_valid && p->linearized) {
+        chi = p->lm_chi; lambda = p->lm_lambda; ni = p->lm_ni; stop_thr = p->lm_stop_thr;
+    } else {
+        // MakeHessian ; ComputeLambdaInitLM
+        RC(do_linearize(p, o, true));
+        st->linearizations++;
+        RC(do_chi2(p, o, &chi));
+        RC(do_maxdiag(p, &maxdiag));
+        if (!v15) maxdiag = std::min(5e10, maxdiag);
+        lambda = 1e-5 * maxdiag;
+        stop_thr = 1e-6 * chi;  // v15 only
+    }
+    p->lm_valid = false;
     st->chi2_initial = chi;
     st->lambda_initial = lambda;
     bool stop = false;
@@ -785,6 +803,7 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
     st->n_trace = std::min(iter, VIO_TRACE_MAX);
     st->chi2_final = chi;
     st->lambda_final = lambda;
+    p->lm_valid = true; p->lm_lambda = lambda; p->lm_chi = chi; p->lm_ni = ni; p->lm_stop_thr = stop_thr;
     return VIO_OK;
 }
 

@@ -1,0 +1,48 @@
+"""Landmark sharding over torch.distributed (one process per GPU, NCCL over NVLink/NVSwitch).
+
+The path shards by landmark: every rank packs the FULL graph, keeps a contiguous,
+edge-balanced landmark range (vio_set_shard) and accumulates its partial reduced system.  The only
+exchange step is an all-reduce (sum) of [S values | b_S correction | b_p | diag(H_pp)] per linearisation
+plus two tiny scalar all-reduces per trial step; the reduced solve then runs redundantly and
+deterministically on every rank, so no broadcast of the pose update is needed.
+"""
+import numpy as np
+
+
+class _CudaPtr:
+    """Zero-copy view of device memory for torch.as_tensor via __cuda_array_interface__."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
+def make_allreduce_hook():
+    import torch
+    import torch.distributed as dist
+
+    def hook(ptr, n, stream):
+        t = torch.as_tensor(_CudaPtr(ptr, n), device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return 0
+
+    return hook
+
+
+def shard_ranges(edge_ptr, world):
+    """Landmark cut points used by vio_set_shard: contiguous ranges balanced by edge count.
+
+    edge_ptr: int array (L+1) CSR offsets of the landmark-sorted edges.  Returns world+1 cut indices.
+    (Host logic mirrored here so it can be tested on CPU with gloo.)
+    """
+    edge_ptr = np.asarray(edge_ptr)
+    L = edge_ptr.shape[0] - 1
+    E = int(edge_ptr[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = E * r // world
+        cuts.append(int(min(np.searchsorted(edge_ptr, target, side="left"), L)))
+    cuts.append(L)
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return cuts
