@@ -1,0 +1,41 @@
+"""GPU test of the drop-in boundary: the reference's own driver source (15-vio-backend/app/TestMonoBA.cpp, compiled
+UNMODIFIED against include/backend/*.h + libvio_backend.so + libvio_b200.so) runs on the GPU and prints the same
+estimates as the reference's own binary (oracle/_ref/test_mono_ba15)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "build", "test_mono_ba_b200")
+REF = os.path.join(ROOT, "oracle", "_ref", "test_mono_ba15")
+
+
+def _parse(out):
+    opt = [float(x) for x in re.findall(r"opt\s+(-?[0-9.]+)", out)]
+    cams = [[float(v) for v in m.split()] for m in re.findall(r"optimized:\s+(-?[0-9.]+\s+-?[0-9.]+\s+-?[0-9.]+)", out)]
+    iters = len(re.findall(r"^iter: ", out, flags=re.M))
+    chi0 = float(re.search(r"iter: 0 , chi= ([0-9.e+-]+)", out).group(1))
+    prior = re.search(r"after marg-+\s+([0-9.e+-]+)\s+([0-9.e+-]+)\s+([0-9.e+-]+)\s+([0-9.e+-]+)", out)
+    return np.array(opt), np.array(cams), iters, chi0, [float(prior.group(k)) for k in range(1, 5)]
+
+
+def test_unmodified_reference_driver_links_and_matches():
+    if not (os.path.exists(OURS) and os.path.exists(REF)):
+        pytest.skip("drop-in demo binaries not built (need /root/reference at build time)")
+    ours = subprocess.run([OURS], capture_output=True, text=True, timeout=300)
+    assert ours.returncode == 0, ours.stderr[-2000:]
+    ref = subprocess.run([REF], capture_output=True, text=True, timeout=300)
+    o_opt, o_cam, o_it, o_chi0, o_prior = _parse(ours.stdout)
+    r_opt, r_cam, r_it, r_chi0, r_prior = _parse(ref.stdout)
+    assert len(o_opt) == len(r_opt) == 20 and o_cam.shape == r_cam.shape == (3, 3)
+    assert o_it == r_it
+    assert abs(o_chi0 - r_chi0) <= 1e-4 * r_chi0
+    # printed with 4 decimals (std::fixed, precision 4)
+    assert np.abs(o_opt - r_opt).max() <= 2e-4
+    assert np.abs(o_cam - r_cam).max() <= 2e-4
+    assert np.allclose(o_prior, r_prior, atol=1e-4)
+    assert np.allclose(o_prior, [26.5306, -8.1633, -8.1633, 10.2041], atol=1e-4)

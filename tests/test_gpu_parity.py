@@ -248,3 +248,41 @@ def test_large_scene_properties(vio):
     p2.set_graph(s)
     st2 = p2.solve(6, opts)
     assert abs(st2.chi2_final - st.chi2_final) <= 1e-9 * st.chi2_final
+
+
+@pytest.mark.parametrize("scene_name", ["monoba", "monoba_ext_fixed", "ring_bsr", "window"])
+def test_grouped_kernel_matches_generic_kernel(vio, scene_name):
+    """The production (grouped, shared-memory) linearise kernel against the simple per-landmark atomics kernel."""
+    import os
+    if scene_name == "monoba":
+        s = vio.scenes.monoba(20, 300)
+    elif scene_name == "monoba_ext_fixed":
+        s = vio.scenes.monoba(7, 90, with_ext=True)
+        s.pose_fixed[3] = 1
+        s.rp_loss, s.rp_loss_delta, s.rp_info = vio.capi.LOSS_CAUCHY, 1.0, 100.0
+    elif scene_name == "ring_bsr":
+        s = vio.scenes.ring(n_cam=60, n_landmark=6000, k_obs=11, seed=8)
+        s.storage = vio.capi.STORAGE_BSR
+    else:
+        s = _window(vio)
+    opts = vio.make_opts(flavour=vio.capi.LM_V17)
+    out = {}
+    for mode in ("generic", "grouped"):
+        os.environ["VIO_B200_LINEARIZE"] = mode
+        p = vio.Problem()
+        p.set_graph(s)
+        assert (p.dims().n_groups > 0) == (mode == "grouped")
+        p.linearize(opts)
+        S, bS = p.get_schur()
+        bp, bl = p.get_b()
+        H, b = p.get_hessian(opts) if s.P + len(s.inv_depth) <= 8192 else (None, None)
+        out[mode] = (S, bS, bp, bl, H, b)
+    os.environ.pop("VIO_B200_LINEARIZE")
+    a, g = out["generic"], out["grouped"]
+    assert rel_max(g[0], a[0]) <= 1e-12
+    assert rel_l2(g[1], a[1]) <= 1e-11
+    assert rel_l2(g[2], a[2]) <= 1e-12
+    assert rel_l2(g[3], a[3]) <= 1e-12
+    if a[4] is not None:
+        assert rel_max(g[4], a[4]) <= 1e-12
+        assert rel_l2(g[5], a[5]) <= 1e-12

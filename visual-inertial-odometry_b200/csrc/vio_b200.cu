@@ -19,6 +19,7 @@
 #include "vio_kernels.cuh"
 #include "vio_solvers.cuh"
 #include "vio_imu.cuh"
+#include "vio_grouped.cuh"
 
 #define VIO_VERSION_STR "vio_b200 0.1 (sm_100a)"
 
@@ -64,6 +65,13 @@ struct vio_problem {
     DBuf<int> bsr_rowptr, bsr_col, bsr_tr, bsr_diag;
     std::vector<int> h_rowptr, h_col;
     size_t s_count = 0;  // number of doubles in S
+    // landmark groups (vio_grouped.cuh)
+    bool use_grouped = false;
+    int n_groups = 0, group_threads = 0;
+    size_t group_smem = 0;
+    DBuf<int> g_hdr, g_slot_pose, ell_edge;
+    DBuf<long long> g_pairinfo;
+    DBuf<double> ell_pjx, ell_pjy;
     // se3 priors
     DBuf<int> sp_pose;
     DBuf<double> sp_p, sp_q, sp_info;
@@ -175,7 +183,15 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
     EvPair *ev = nullptr;
     if (p->ev_lin_used < p->ev_lin.size()) ev = &p->ev_lin[p->ev_lin_used++];
     if (ev) CK(cudaEventRecord(ev->a, p->stream));
-    if (p->L > 0) {
+    if (p->L > 0 && p->use_grouped) {
+        GroupView gv;
+        gv.n_groups = p->n_groups; gv.ld = p->storage == VIO_STORAGE_DENSE ? p->P : 6;
+        gv.hdr = (const GroupHdr *)p->g_hdr.p; gv.slot_pose = p->g_slot_pose.p; gv.pairinfo = p->g_pairinfo.p;
+        gv.ell_pjx = p->ell_pjx.p; gv.ell_pjy = p->ell_pjy.p; gv.ell_edge = p->ell_edge.p;
+        if (with_schur) k_linearize_grouped<true><<<p->n_groups, p->group_threads, p->group_smem, p->stream>>>(v, gv);
+        else k_linearize_grouped<false><<<p->n_groups, p->group_threads, p->group_smem, p->stream>>>(v, gv);
+        p->launches++;
+    } else if (p->L > 0) {
         if (with_schur) k_linearize_lm<true><<<grid_for(p->L, 128), 128, 0, p->stream>>>(v);
         else k_linearize_lm<false><<<grid_for(p->L, 128), 128, 0, p->stream>>>(v);
         p->launches++;
@@ -533,6 +549,24 @@ int vio_set_graph(vio_problem *p, const vio_graph *g) {
     } else {
         p->bsr_rowptr.release(); p->bsr_col.release(); p->bsr_tr.release(); p->bsr_diag.release();
     }
+    // grouped linearise kernel: used whenever the packer could group every landmark (VIO_B200_LINEARIZE=generic
+    // forces the per-landmark atomics kernel for A/B checks)
+    const char *force = getenv("VIO_B200_LINEARIZE");
+    p->use_grouped = K.grouped_ok && !(force && strcmp(force, "generic") == 0);
+    p->n_groups = K.n_groups; p->group_threads = K.group_threads; p->group_smem = K.group_smem_max;
+    if (p->use_grouped) {
+        CK(upload(p->g_hdr, K.g_hdr.data(), K.g_hdr.size(), s)); CK(upload(p->g_slot_pose, K.g_slot_pose.data(), K.g_slot_pose.size(), s));
+        CK(upload(p->g_pairinfo, K.g_pairinfo.data(), K.g_pairinfo.size(), s));
+        CK(upload(p->ell_pjx, K.ell_pjx.data(), K.ell_pjx.size(), s)); CK(upload(p->ell_pjy, K.ell_pjy.data(), K.ell_pjy.size(), s));
+        CK(upload(p->ell_edge, K.ell_edge.data(), K.ell_edge.size(), s));
+        CK(cudaFuncSetAttribute(k_linearize_grouped<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->group_smem));
+        CK(cudaFuncSetAttribute(k_linearize_grouped<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->group_smem));
+        // landmarks without edges are outside every group: their outputs stay zero
+        if (L > 0) {
+            CK(cudaMemsetAsync(p->Hll.p, 0, L * sizeof(double), s)); CK(cudaMemsetAsync(p->bl.p, 0, L * sizeof(double), s));
+            CK(cudaMemsetAsync(p->wh.p, 0, 6 * (size_t)L * sizeof(double), s));
+        }
+    }
     if (g->n_se3prior > 0) {
         CK(upload(p->sp_pose, g->sp_pose, (size_t)g->n_se3prior, s)); CK(upload(p->sp_p, g->sp_p, 3 * (size_t)g->n_se3prior, s));
         CK(upload(p->sp_q, g->sp_q, 4 * (size_t)g->n_se3prior, s)); CK(upload(p->sp_info, g->sp_info, 36 * (size_t)g->n_se3prior, s));
@@ -562,7 +596,7 @@ int vio_set_graph(vio_problem *p, const vio_graph *g) {
 int vio_get_dims(const vio_problem *p, vio_dims *out) {
     if (!p || !out || !p->has_graph) return VIO_ERR_STATE;
     out->P = p->P; out->M = p->Lglobal; out->n_pose_blocks = p->NB; out->storage = p->storage;
-    out->nnz_blocks = p->nnzb; out->n_reproj = p->E; out->n_groups = 0; out->reserved = p->L;
+    out->nnz_blocks = p->nnzb; out->n_reproj = p->E; out->n_groups = p->use_grouped ? p->n_groups : 0; out->reserved = p->L;
     return VIO_OK;
 }
 

@@ -1,0 +1,404 @@
+// vio_grouped.cuh — the production linearise + J^T W J + Schur kernel: one CTA per landmark GROUP.
+//
+// A group is a run of landmarks that share the host pose and whose observers fit NS_MAX pose "slots"
+// (slot 0 = host).  Everything a group touches in the reduced camera system is a set of 6x6 blocks
+// between its slots, so the CTA
+//   1. stages the slots' R,t in shared memory and builds the per-landmark host chain (p_w, g, G),
+//   2. evaluates edges slot-major (warp = slot, lanes = landmarks: coalesced ELL loads, uniform pose),
+//      keeps the per-slot J^T W J / J^T W r sums in registers and reduces them ONCE per slot with a
+//      recursive-halving shuffle reduce-scatter (no atomics),
+//   3. reduces the per-landmark sums (H_ll, b_l, H_lp) and forms the Schur outer products
+//      H_pl H_ll^-1 H_lp with every thread owning one 6x6 block pair in registers,
+//   4. flushes the finished group tile with one RED.F64 per touched element of S.
+// Reference dataflow replaced: Problem::MakeHessian + the Schur part of SolveLinearSystem
+// (A15/backend/problem.cc:280-337,353-399; A17/src/backend/problem.cc:303-389,406-437).
+//
+// Edge algebra.  With B = reduce * Ric^T Rj^T (2x3) every Jacobian of EdgeReprojection factors through B:
+//   J_lambda = B g,  J_i = B [I  G],  J_j = B [-I  N]   (g = Ri Ric pts_i (-1/l^2), G = -Ri hat(p_bi), N = Rj hat(p_bj))
+// so with M = B^T W B (3x3) all blocks are products of M, G, N, g (A15/backend/edge_reprojection.cc:47-91).
+#pragma once
+#include "vio_dev.h"
+#include "vio_kernels.cuh"
+
+#define VIO_NS_MAX 22
+#define VIO_GROUP_THREADS_MAX 320
+
+struct GroupHdr {
+    int host, ns, lm0, nlm, ell0, pair0, slot0, pad;
+};
+
+struct GroupView {
+    int n_groups, ld;
+    const GroupHdr *hdr;
+    const int *slot_pose;        // [slot0 + s]
+    const long long *pairinfo;   // [pair0 + p] = (offset << 2) | flags   (0 normal, 1 transposed, 2 diagonal, 3 skip)
+    const double *ell_pjx, *ell_pjy;  // [ell0 + (s-1)*nlm + l], NaN = no observation
+    const int *ell_edge;         // packed edge index (for H_lp observer rows), -1 = none
+};
+
+__host__ __device__ inline size_t group_smem_doubles(int ns, int nlm) {
+    const int npairs = ns * (ns + 1) / 2;
+    // pc[ns][12] lmh[nlm][16] w[nlm][ns][6] lmM[nlm][ns-1][9] hinv[nlm] blv[nlm] red[ns][48] T[npairs][36] bvec[ns][18]
+    return (size_t)ns * 12 + (size_t)nlm * 16 + (size_t)nlm * ns * 6 + (size_t)nlm * (ns - 1) * 9 + 2 * (size_t)nlm +
+           (size_t)ns * 48 + (size_t)npairs * 36 + (size_t)ns * 18;
+}
+__host__ __device__ inline size_t group_smem_bytes(int ns, int nlm) {
+    const int npairs = ns * (ns + 1) / 2;
+    // + ints: pose_id[ns] fixed[ns] off[ns] pair_a[npairs] pair_b[npairs]
+    return group_smem_doubles(ns, nlm) * sizeof(double) + (3 * (size_t)ns + 2 * (size_t)npairs) * sizeof(int);
+}
+
+template <int N>
+__device__ __forceinline__ void rs_step(double *v, bool up, int mask) {
+    constexpr int H = N / 2;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const double send = up ? v[i] : v[i + H];
+        const double keep = up ? v[i + H] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+}
+// warp sum of a 48-vector, scattered: afterwards lane holds element `base` in v[0] and (if !(lane&1)) base+1 in v[1]
+__device__ __forceinline__ int reduce_scatter48(double *v, int lane) {
+    int base = 0;
+    rs_step<48>(v, lane & 16, 16); base += (lane & 16) ? 24 : 0;
+    rs_step<24>(v, lane & 8, 8);   base += (lane & 8) ? 12 : 0;
+    rs_step<12>(v, lane & 4, 4);   base += (lane & 4) ? 6 : 0;
+    rs_step<6>(v, lane & 2, 2);    base += (lane & 2) ? 3 : 0;
+    v[3] = 0.0;
+    rs_step<4>(v, lane & 1, 1);    base += (lane & 1) ? 2 : 0;
+    return base;
+}
+__device__ __forceinline__ int reduce_scatter32(double *v, int lane) {
+    int base = 0;
+    rs_step<32>(v, lane & 16, 16); base += (lane & 16) ? 16 : 0;
+    rs_step<16>(v, lane & 8, 8);   base += (lane & 8) ? 8 : 0;
+    rs_step<8>(v, lane & 4, 4);    base += (lane & 4) ? 4 : 0;
+    rs_step<4>(v, lane & 2, 2);    base += (lane & 2) ? 2 : 0;
+    rs_step<2>(v, lane & 1, 1);    base += (lane & 1) ? 1 : 0;
+    return base;  // v[0] holds element `base`
+}
+
+__device__ __forceinline__ int sym6_index(int r, int c) {  // upper triangle, row-major
+    if (r > c) { const int t = r; r = c; c = t; }
+    return r * 6 - (r * (r - 1)) / 2 + (c - r);
+}
+__device__ __forceinline__ int sym3_index(int r, int c) {  // 00 01 02 11 12 22
+    if (r > c) { const int t = r; r = c; c = t; }
+    return r * 3 - (r * (r - 1)) / 2 + (c - r);
+}
+
+template <bool WITH_SCHUR>
+__global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(DevView v, GroupView gv) {
+    extern __shared__ double sm[];
+    const GroupHdr h = gv.hdr[blockIdx.x];
+    const int ns = h.ns, nlm = h.nlm, npairs = ns * (ns + 1) / 2;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    double *pc = sm;                                  // [ns][12]
+    double *lmh = pc + (size_t)ns * 12;               // [nlm][16]  pw(3) g(3) G(9) lam-unused
+    double *w = lmh + (size_t)nlm * 16;               // [nlm][ns][6]
+    double *lmM = w + (size_t)nlm * ns * 6;           // [nlm][ns-1][9]
+    double *hinv = lmM + (size_t)nlm * (ns - 1) * 9;  // [nlm]
+    double *blv = hinv + nlm;                         // [nlm]
+    double *red = blv + nlm;                          // [ns][48]
+    double *T = red + (size_t)ns * 48;                // [npairs][36]
+    double *bvec = T + (size_t)npairs * 36;           // [ns][18]  bp(6) bcorr(6) hdiag(6)
+    int *pose_id = (int *)(bvec + (size_t)ns * 18);   // [ns]
+    int *pfix = pose_id + ns;
+    int *poff = pfix + ns;
+    int *pair_a = poff + ns;                          // [npairs]
+    int *pair_b = pair_a + npairs;
+
+    // ---- phase 0: slot table, pose cache, zero fills ---------------------------------------------------------
+    for (int s = tid; s < ns; s += nt) {
+        const int pid = s == 0 ? h.host : gv.slot_pose[h.slot0 + s];
+        pose_id[s] = pid;
+        pfix[s] = v.pose_fixed[pid];
+        poff[s] = v.pose_off[pid];
+    }
+    for (int p = tid; p < npairs; p += nt) {
+        // invert p = a*ns - a(a-1)/2 + (b-a)
+        int a = 0, rem = p;
+        while (rem >= ns - a) { rem -= ns - a; ++a; }
+        pair_a[p] = a;
+        pair_b[p] = a + rem;
+    }
+    for (size_t i = tid; i < (size_t)nlm * ns * 6; i += nt) w[i] = 0.0;
+    for (size_t i = tid; i < (size_t)nlm * (ns - 1) * 9; i += nt) lmM[i] = 0.0;
+    for (int i = tid; i < ns * 48; i += nt) red[i] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < ns * 12; i += nt) {
+        const int s = i / 12, k = i % 12;
+        pc[i] = v.poseRT[16 * (size_t)pose_id[s] + k];
+    }
+    __syncthreads();
+    const bool hfix = pfix[0] != 0;
+
+    // ---- phase 0.5: per-landmark host chain ------------------------------------------------------------------
+    for (int l = tid; l < nlm; l += nt) {
+        const int gl = h.lm0 + l;
+        const double lam = v.invdep[gl];
+        const double pts_i[3] = {v.lm_pix[gl], v.lm_piy[gl], v.lm_piz[gl]};
+        const double pci[3] = {pts_i[0] / lam, pts_i[1] / lam, pts_i[2] / lam};
+        double pbi[3], pw[3], tmp[3], g[3], G[9];
+        mat3_mul_vec(v.Ric, pci, pbi);
+        pbi[0] += v.tic[0]; pbi[1] += v.tic[1]; pbi[2] += v.tic[2];
+        mat3_mul_vec(pc, pbi, pw);
+        pw[0] += pc[9]; pw[1] += pc[10]; pw[2] += pc[11];
+        mat3_mul_vec(v.Ric, pts_i, tmp);
+        mat3_mul_vec(pc, tmp, g);
+        const double il2 = -1.0 / (lam * lam);
+        mat3_mul_hat(pc, pbi, G);
+        double *o = lmh + 16 * (size_t)l;
+        o[0] = pw[0]; o[1] = pw[1]; o[2] = pw[2];
+        o[3] = g[0] * il2; o[4] = g[1] * il2; o[5] = g[2] * il2;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o[6 + k] = -G[k];
+    }
+    __syncthreads();
+
+    // ---- phase 1: edges, slot-major.  warp <-> slot, lanes <-> landmarks ----------------------------------------
+    for (int s = 1 + wid; s < ns; s += nw) {
+        const double *RTj = pc + 12 * (size_t)s;
+        const bool jfix = pfix[s] != 0;
+        double acc[48];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) acc[k] = 0.0;
+        for (int l = lane; l < nlm; l += 32) {
+            const size_t e = (size_t)h.ell0 + (size_t)(s - 1) * nlm + l;
+            const double pjx = gv.ell_pjx[e];
+            if (pjx != pjx) continue;  // NaN: this landmark is not observed from slot s
+            const double pjy = gv.ell_pjy[e];
+            const int edge = gv.ell_edge[e];
+            const double *lh = lmh + 16 * (size_t)l;
+            const double pw[3] = {lh[0], lh[1], lh[2]};
+            double pcj[3], pbj[3], r[2];
+            reproj_residual(v.Ric, v.tic, RTj, pw, pjx, pjy, pcj, pbj, r);
+            const double iz = 1.0 / pcj[2];
+            const double rx = -pcj[0] * iz * iz, ry = -pcj[1] * iz * iz;
+            // A = Ric^T Rj^T = (Rj Ric)^T ;  B = reduce * A
+            double RjRic[9];
+            mat3_mul(RTj, v.Ric, RjRic);
+            double B[6];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                B[c] = iz * RjRic[3 * c + 0] + rx * RjRic[3 * c + 2];
+                B[3 + c] = iz * RjRic[3 * c + 1] + ry * RjRic[3 * c + 2];
+            }
+            double rho0, drho, W[3];
+            robust_weights(v.rp_loss, v.rp_delta, v.rp_info, r, rho0, drho, W);
+            double WB[6];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                WB[c] = W[0] * B[c] + W[1] * B[3 + c];
+                WB[3 + c] = W[1] * B[c] + W[2] * B[3 + c];
+            }
+            double M[9];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) M[3 * a + b] = B[a] * WB[b] + B[3 + a] * WB[3 + b];
+            const double dc = drho * v.rp_info;
+            const double m[3] = {dc * (B[0] * r[0] + B[3] * r[1]), dc * (B[1] * r[0] + B[4] * r[1]),
+                                 dc * (B[2] * r[0] + B[5] * r[1])};
+            double *lm9 = lmM + ((size_t)l * (ns - 1) + (s - 1)) * 9;
+            lm9[0] = M[0]; lm9[1] = M[1]; lm9[2] = M[2]; lm9[3] = M[4]; lm9[4] = M[5]; lm9[5] = M[8];
+            lm9[6] = m[0]; lm9[7] = m[1]; lm9[8] = m[2];
+            double *wog = v.wo + 6 * (size_t)edge;
+            if (jfix) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) wog[k] = 0.0;
+                continue;
+            }
+            double N[9], MN[9], NMN[9], Ntm[3], Mg[3], NtMg[3];
+            mat3_mul_hat(RTj, pbj, N);
+            mat3_mul(M, N, MN);
+            mat3t_mul(N, MN, NMN);
+            mat3t_mul_vec(N, m, Ntm);
+            const double g[3] = {lh[3], lh[4], lh[5]};
+            mat3_mul_vec(M, g, Mg);
+            mat3t_mul_vec(N, Mg, NtMg);
+            double *ws = w + ((size_t)l * ns + s) * 6;
+            const double wj[6] = {-Mg[0], -Mg[1], -Mg[2], NtMg[0], NtMg[1], NtMg[2]};
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { ws[k] = wj[k]; wog[k] = wj[k]; }
+            acc[0] += M[0]; acc[1] += M[1]; acc[2] += M[2]; acc[3] += M[4]; acc[4] += M[5]; acc[5] += M[8];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[6 + k] += MN[k];
+            acc[33] += NMN[0]; acc[34] += NMN[1]; acc[35] += NMN[2]; acc[36] += NMN[4]; acc[37] += NMN[5]; acc[38] += NMN[8];
+            acc[39] += m[0]; acc[40] += m[1]; acc[41] += m[2];
+            acc[42] += Ntm[0]; acc[43] += Ntm[1]; acc[44] += Ntm[2];
+            if (!hfix) {
+                const double *G = lh + 6;
+                double GtM[9], GtMN[9];
+                mat3t_mul(G, M, GtM);
+                mat3t_mul(G, MN, GtMN);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { acc[15 + k] += GtM[k]; acc[24 + k] += GtMN[k]; }
+            }
+        }
+        const int base = reduce_scatter48(acc, lane);
+        red[48 * (size_t)s + base] = acc[0];
+        if (!(lane & 1)) red[48 * (size_t)s + base + 1] = acc[1];
+    }
+    __syncthreads();
+
+    // ---- phase 1.5: per-landmark sums -> H_ll, b_l, host row of H_lp, host blocks ------------------------------
+    {
+        double hb[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) hb[k] = 0.0;
+        for (int l = tid; l < nlm; l += nt) {
+            double Ms[6] = {0, 0, 0, 0, 0, 0}, ms[3] = {0, 0, 0};
+            const double *q = lmM + (size_t)l * (ns - 1) * 9;
+            for (int s = 0; s < ns - 1; ++s) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) Ms[k] += q[9 * s + k];
+                ms[0] += q[9 * s + 6]; ms[1] += q[9 * s + 7]; ms[2] += q[9 * s + 8];
+            }
+            const double *lh = lmh + 16 * (size_t)l;
+            const double g[3] = {lh[3], lh[4], lh[5]};
+            const double *G = lh + 6;
+            const double Msf[9] = {Ms[0], Ms[1], Ms[2], Ms[1], Ms[3], Ms[4], Ms[2], Ms[4], Ms[5]};
+            double Mg[3];
+            mat3_mul_vec(Msf, g, Mg);
+            const double Hll = g[0] * Mg[0] + g[1] * Mg[1] + g[2] * Mg[2];
+            const double bl = -(g[0] * ms[0] + g[1] * ms[1] + g[2] * ms[2]);
+            const int gl = h.lm0 + l;
+            v.Hll[gl] = Hll;
+            v.bl[gl] = bl;
+            hinv[l] = 1.0 / Hll;
+            blv[l] = bl;
+            double wh[6] = {0, 0, 0, 0, 0, 0};
+            if (!hfix) {
+                double GtMg[3], MG[9], GtMG[9], Gtm[3];
+                mat3t_mul_vec(G, Mg, GtMg);
+                wh[0] = Mg[0]; wh[1] = Mg[1]; wh[2] = Mg[2]; wh[3] = GtMg[0]; wh[4] = GtMg[1]; wh[5] = GtMg[2];
+                mat3_mul(Msf, G, MG);
+                mat3t_mul(G, MG, GtMG);
+                mat3t_mul_vec(G, ms, Gtm);
+                // host block [[Ms, Ms G],[G^T Ms, G^T Ms G]] upper triangle, row-major: rows 0..2 then 3..5
+                hb[0] += Msf[0]; hb[1] += Msf[1]; hb[2] += Msf[2]; hb[3] += MG[0]; hb[4] += MG[1]; hb[5] += MG[2];
+                hb[6] += Msf[4]; hb[7] += Msf[5]; hb[8] += MG[3]; hb[9] += MG[4]; hb[10] += MG[5];
+                hb[11] += Msf[8]; hb[12] += MG[6]; hb[13] += MG[7]; hb[14] += MG[8];
+                hb[15] += GtMG[0]; hb[16] += GtMG[1]; hb[17] += GtMG[2];
+                hb[18] += GtMG[4]; hb[19] += GtMG[5];
+                hb[20] += GtMG[8];
+                hb[21] -= ms[0]; hb[22] -= ms[1]; hb[23] -= ms[2]; hb[24] -= Gtm[0]; hb[25] -= Gtm[1]; hb[26] -= Gtm[2];
+            }
+            double *whg = v.wh + 6 * (size_t)gl;
+            double *ws = w + (size_t)l * ns * 6;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { whg[k] = wh[k]; ws[k] = wh[k]; }
+        }
+        // block reduction of the 27 host values: warp reduce-scatter, then one shared-memory atomic per warp and value
+        if (wid * 32 < nlm) {
+            const int base = reduce_scatter32(hb, lane);
+            if (base < 27) atomicAdd(&red[base], hb[0]);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1.9: assemble the direct (J^T W J) part of the group tile from the reduced vectors -------------
+    for (int idx = tid; idx < npairs * 36; idx += nt) {
+        const int p = idx / 36, k = idx % 36, r = k / 6, c = k % 6;
+        const int a = pair_a[p], b = pair_b[p];
+        double val = 0.0;
+        if (a == 0 && b == 0) {
+            val = red[sym6_index(r, c)];
+        } else if (a == 0) {
+            const double *R = red + 48 * (size_t)b;  // (0,s) = [[-A1, A2],[-A3, A4]]
+            if (r < 3 && c < 3) val = -R[sym3_index(r, c)];
+            else if (r < 3) val = R[6 + 3 * r + (c - 3)];
+            else if (c < 3) val = -R[15 + 3 * (r - 3) + c];
+            else val = R[24 + 3 * (r - 3) + (c - 3)];
+        } else if (a == b) {
+            const double *R = red + 48 * (size_t)a;  // (s,s) = [[A1, -A2],[-A2^T, A5]]
+            if (r < 3 && c < 3) val = R[sym3_index(r, c)];
+            else if (r < 3) val = -R[6 + 3 * r + (c - 3)];
+            else if (c < 3) val = -R[6 + 3 * c + (r - 3)];
+            else val = R[33 + sym3_index(r - 3, c - 3)];
+        }
+        T[idx] = val;
+    }
+    for (int idx = tid; idx < ns * 6; idx += nt) {
+        const int s = idx / 6, k = idx % 6;
+        double bp, hd;
+        if (s == 0) {
+            bp = red[21 + k];
+            hd = red[sym6_index(k, k)];
+        } else {
+            const double *R = red + 48 * (size_t)s;
+            bp = k < 3 ? R[39 + k] : -R[42 + (k - 3)];
+            hd = k < 3 ? R[sym3_index(k, k)] : R[33 + sym3_index(k - 3, k - 3)];
+        }
+        bvec[18 * s + k] = bp;
+        bvec[18 * s + 12 + k] = hd;
+        bvec[18 * s + 6 + k] = 0.0;
+    }
+    __syncthreads();
+
+    // ---- phase 2: Schur outer products, thread <-> (block pair, landmark subset) --------------------------------
+    if (WITH_SCHUR) {
+        const int nsub = max(1, nt / npairs);
+        for (int p0 = 0; p0 < npairs; p0 += nt) {  // one pass unless npairs > blockDim
+            const int item = tid;
+            const int p = p0 + (nsub > 1 ? item % npairs : item);
+            const int q = nsub > 1 ? item / npairs : 0;
+            const bool active = p < npairs && q < nsub;
+            double acc[36];
+#pragma unroll
+            for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+            if (active) {
+                const int a = pair_a[p], b = pair_b[p];
+                for (int l = q; l < nlm; l += nsub) {
+                    const double inv = hinv[l];
+                    const double *wa = w + ((size_t)l * ns + a) * 6;
+                    const double *wb = w + ((size_t)l * ns + b) * 6;
+                    double x[6], y[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { x[k] = wa[k] * inv; y[k] = wb[k]; }
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) acc[6 * r + c] += x[r] * y[c];
+                }
+            }
+            for (int qq = 0; qq < nsub; ++qq) {
+                if (active && q == qq) {
+                    double *t = T + 36 * (size_t)p;
+#pragma unroll
+                    for (int k = 0; k < 36; ++k) t[k] -= acc[k];
+                }
+                __syncthreads();
+            }
+        }
+        for (int idx = tid; idx < ns * 6; idx += nt) {
+            const int s = idx / 6, k = idx % 6;
+            double t = 0.0;
+            for (int l = 0; l < nlm; ++l) t += w[((size_t)l * ns + s) * 6 + k] * hinv[l] * blv[l];
+            bvec[18 * s + 6 + k] = t;
+        }
+        __syncthreads();
+    }
+
+    // ---- flush: one RED.F64 per touched element of the reduced system -------------------------------------------
+    for (int idx = tid; idx < npairs * 36; idx += nt) {
+        const int p = idx / 36, k = idx % 36, r = k / 6, c = k % 6;
+        const long long info = gv.pairinfo[h.pair0 + p];
+        const int flags = (int)(info & 3);
+        if (flags == 3) continue;
+        if (flags == 2 && r > c) continue;
+        const size_t off = (size_t)(info >> 2);
+        const size_t e = flags == 1 ? (size_t)c * gv.ld + r : (size_t)r * gv.ld + c;
+        const double val = T[idx];
+        if (val != 0.0) atomicAdd(v.S + off + e, val);
+    }
+    for (int idx = tid; idx < ns * 6; idx += nt) {
+        const int s = idx / 6, k = idx % 6;
+        if (pfix[s]) continue;
+        atomicAdd(v.bp + poff[s] + k, bvec[18 * s + k]);
+        atomicAdd(v.hdiag + poff[s] + k, bvec[18 * s + 12 + k]);
+        if (WITH_SCHUR) atomicAdd(v.bcorr + poff[s] + k, bvec[18 * s + 6 + k]);
+    }
+}

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <limits>
 #include <string>
 #include <vector>
 #include "../../include/vio_b200.h"
@@ -22,6 +23,15 @@ struct PackedGraph {
     std::vector<int> lm_global, lm_host, lm_eptr, e_pose_j;
     std::vector<double> pix, piy, piz, pjx, pjy, invd;
     std::vector<int> rowptr, col, tr, diag;
+    // landmark groups for the grouped linearise kernel (vio_grouped.cuh)
+    bool grouped_ok = false;
+    int n_groups = 0, group_threads = 0;
+    size_t group_smem_max = 0;
+    std::vector<int> g_hdr;        // 8 ints per group: host ns lm0 nlm ell0 pair0 slot0 pad
+    std::vector<int> g_slot_pose;  // per group ns entries (entry 0 = host)
+    std::vector<long long> g_pairinfo;
+    std::vector<double> ell_pjx, ell_pjy;
+    std::vector<int> ell_edge;
 };
 
 inline int pack_fail(std::string &err, int code, const char *fmt, ...) {
@@ -111,14 +121,21 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     lm_host.assign(L, 0); lm_eptr.assign(L + 1, 0); e_pose_j.assign(E, 0);
     pix.assign(L, 0.0); piy.assign(L, 0.0); piz.assign(L, 1.0); pjx.assign(E, 0.0); pjy.assign(E, 0.0); invd.assign(L, 0.0);
     K.lm_global.resize(L);
+    // local landmark order: sorted by host pose (stable) so that landmarks sharing a host are contiguous and
+    // can be grouped; landmarks without edges go last.
+    std::vector<int> lorder(L);
+    for (int ll = 0; ll < L; ++ll) lorder[ll] = l_begin + ll;
+    auto host_of = [&](int l) { return cnt[l] == cnt[l + 1] ? 0x7fffffff : g->rp_pose_i[eorder[cnt[l]]]; };
+    std::stable_sort(lorder.begin(), lorder.end(), [&](int a, int b) { return host_of(a) < host_of(b); });
+    int ecur = 0;
     for (int ll = 0; ll < L; ++ll) {
-        const int l = l_begin + ll;
+        const int l = lorder[ll];
         K.lm_global[ll] = l;
         invd[ll] = g->inv_depth[l];
-        lm_eptr[ll] = cnt[l] - cnt[l_begin];
+        lm_eptr[ll] = ecur;
         for (int k = cnt[l]; k < cnt[l + 1]; ++k) {
             const int e = eorder[k];
-            const int le = k - cnt[l_begin];
+            const int le = ecur++;
             if (k == cnt[l]) {
                 lm_host[ll] = g->rp_pose_i[e];
                 pix[ll] = g->rp_pts_i[3 * (size_t)e]; piy[ll] = g->rp_pts_i[3 * (size_t)e + 1]; piz[ll] = g->rp_pts_i[3 * (size_t)e + 2];
@@ -183,6 +200,101 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
                 if (col[k] == a) diag[a] = k;
             }
         s_count = (size_t)nnzb * 36;
+    }
+
+    // ---- landmark groups (same host, <= VIO_PACK_NS_MAX pose slots, shared-memory budget) ---------------------
+    {
+        const int NS_MAX = 22;
+        const size_t SMEM_BUDGET = 200 * 1024;
+        auto smem_bytes = [](int ns, int nlm) -> size_t {
+            const size_t npairs = (size_t)ns * (ns + 1) / 2;
+            const size_t dbl = (size_t)ns * 12 + (size_t)nlm * 16 + (size_t)nlm * ns * 6 + (size_t)nlm * (ns - 1) * 9 +
+                               2 * (size_t)nlm + (size_t)ns * 48 + npairs * 36 + (size_t)ns * 18;
+            return dbl * 8 + (3 * (size_t)ns + 2 * npairs) * 4;
+        };
+        auto block_off = [&](int pa, int pb, long long &off) -> bool {  // element offset of block (pa,pb) in S storage
+            if (storage == VIO_STORAGE_DENSE) { off = (long long)pose_off[pa] * P + pose_off[pb]; return true; }
+            const int ra = pose_blk[pa], cb = pose_blk[pb];
+            auto it = std::lower_bound(col.begin() + rowptr[ra], col.begin() + rowptr[ra + 1], cb);
+            if (it == col.begin() + rowptr[ra + 1] || *it != cb) return false;
+            off = 36LL * (it - col.begin());
+            return true;
+        };
+        K.grouped_ok = true;
+        K.n_groups = 0; K.group_smem_max = 0;
+        K.g_hdr.clear(); K.g_slot_pose.clear(); K.g_pairinfo.clear(); K.ell_pjx.clear(); K.ell_pjy.clear(); K.ell_edge.clear();
+        int max_obs_slots = 0;
+        int l0 = 0;
+        std::vector<int> slots;  // slot -> pose (slot 0 = host)
+        std::vector<int> slot_of_pose(C, -1);
+        while (l0 < L && K.grouped_ok) {
+            if (lm_eptr[l0] == lm_eptr[l0 + 1]) break;  // only edge-less landmarks remain
+            const int host = lm_host[l0];
+            slots.assign(1, host);
+            slot_of_pose[host] = 0;
+            int l1 = l0;
+            while (l1 < L && lm_eptr[l1] != lm_eptr[l1 + 1] && lm_host[l1] == host && (l1 - l0) < 128) {
+                // would this landmark fit?
+                int added = 0;
+                bool bad = false;
+                for (int e = lm_eptr[l1]; e < lm_eptr[l1 + 1]; ++e) {
+                    const int pj = e_pose_j[e];
+                    if (pj == host) { bad = true; break; }
+                    for (int e2 = lm_eptr[l1]; e2 < e; ++e2)
+                        if (e_pose_j[e2] == pj) { bad = true; break; }
+                    if (bad) break;
+                    if (slot_of_pose[pj] < 0) { slot_of_pose[pj] = (int)slots.size(); slots.push_back(pj); ++added; }
+                }
+                if (bad) { K.grouped_ok = false; break; }
+                const int ns_new = (int)slots.size();
+                if (ns_new > NS_MAX || smem_bytes(ns_new, l1 - l0 + 1) > SMEM_BUDGET) {
+                    // undo this landmark's slots and close the group (a single landmark that does not fit: irregular)
+                    for (int k = 0; k < added; ++k) { slot_of_pose[slots.back()] = -1; slots.pop_back(); }
+                    if (l1 == l0) K.grouped_ok = false;
+                    break;
+                }
+                ++l1;
+            }
+            if (!K.grouped_ok) { for (int p2 : slots) slot_of_pose[p2] = -1; break; }
+            const int ns = (int)slots.size(), nlm = l1 - l0;
+            const int ell0 = (int)K.ell_pjx.size(), pair0 = (int)K.g_pairinfo.size(), slot0 = (int)K.g_slot_pose.size();
+            const int hdr[8] = {host, ns, l0, nlm, ell0, pair0, slot0, 0};
+            K.g_hdr.insert(K.g_hdr.end(), hdr, hdr + 8);
+            K.g_slot_pose.insert(K.g_slot_pose.end(), slots.begin(), slots.end());
+            const double qnan = std::numeric_limits<double>::quiet_NaN();
+            K.ell_pjx.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, qnan);
+            K.ell_pjy.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, 0.0);
+            K.ell_edge.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, -1);
+            for (int l = l0; l < l1; ++l)
+                for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
+                    const int sl = slot_of_pose[e_pose_j[e]];
+                    const size_t idx = (size_t)ell0 + (size_t)(sl - 1) * nlm + (l - l0);
+                    K.ell_pjx[idx] = pjx[e]; K.ell_pjy[idx] = pjy[e]; K.ell_edge[idx] = e;
+                }
+            for (int a = 0; a < ns && K.grouped_ok; ++a)
+                for (int b = a; b < ns; ++b) {
+                    const int pa = slots[a], pb = slots[b];
+                    long long off = 0, info;
+                    if (K.pose_fixed.size() == 0) {}
+                    const bool fa = g->pose_fixed && g->pose_fixed[pa], fb = g->pose_fixed && g->pose_fixed[pb];
+                    if (fa || fb) info = 3;
+                    else if (a == b) { if (!block_off(pa, pa, off)) { K.grouped_ok = false; break; } info = (off << 2) | 2; }
+                    else if (pose_off[pa] < pose_off[pb]) { if (!block_off(pa, pb, off)) { K.grouped_ok = false; break; } info = (off << 2) | 0; }
+                    else { if (!block_off(pb, pa, off)) { K.grouped_ok = false; break; } info = (off << 2) | 1; }
+                    K.g_pairinfo.push_back(info);
+                }
+            K.group_smem_max = std::max(K.group_smem_max, smem_bytes(ns, nlm));
+            max_obs_slots = std::max(max_obs_slots, ns - 1);
+            for (int p2 : slots) slot_of_pose[p2] = -1;
+            K.n_groups++;
+            l0 = l1;
+        }
+        if (K.n_groups == 0) K.grouped_ok = false;
+        // one warp per observer slot, at most 10 warps; fewer slots per warp round when there are more
+        const int rounds = (max_obs_slots + 9) / 10;
+        int nwarp = rounds > 0 ? (max_obs_slots + rounds - 1) / rounds : 1;
+        if (nwarp < 4) nwarp = 4;
+        K.group_threads = 32 * nwarp;
     }
 
     K.C = C; K.NSB = NSB; K.NB = NB; K.P = P; K.L = L; K.Lglobal = Lg; K.E = E; K.storage = storage; K.nnzb = nnzb;
