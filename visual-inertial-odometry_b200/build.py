@@ -51,8 +51,35 @@ def build_scenes(force=False):
     return out
 
 
+REF_ASSIGN = "/root/reference/workspace/assignments"
+EIGEN_DIR = os.path.join(REF_ASSIGN, "02-kinematics-in-3D-space", "workspace", "Eigen")
+
+
+def build_backend(force=False):
+    """C++ drop-in layer (needs Eigen headers: here the copy vendored by the reference; any Eigen >= 3.3 works) and
+    the demo that links the reference's UNMODIFIED TestMonoBA.cpp against it.  Skipped (prebuilt files are used)
+    when no Eigen is available, e.g. on the GPU box."""
+    out = os.path.join(HERE, "libvio_backend.so")
+    demo = os.path.join(ROOT, "build", "test_mono_ba_b200")
+    eigen = os.environ.get("EIGEN3_INCLUDE_DIR", EIGEN_DIR)
+    if not os.path.isdir(eigen):
+        return out if os.path.exists(out) else None
+    src = os.path.join(HERE, "host", "backend_b200.cc")
+    hdrs = [os.path.join(ROOT, "include", "backend", "myslam_backend_b200.h"), os.path.join(ROOT, "include", "vio_b200.h")]
+    dyn = ["-Wl,--no-as-needed", "-l:libstdc++.so.6"]
+    if force or _newer(out, [src] + hdrs):
+        _run(["g++", "-std=c++14", "-O2", "-w", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + eigen, src,
+              "-o", out, "-L" + HERE, "-lvio_b200", "-Wl,-rpath,$ORIGIN"] + dyn)
+    driver = os.path.join(REF_ASSIGN, "15-vio-backend", "app", "TestMonoBA.cpp")
+    if os.path.exists(driver) and (force or _newer(demo, [out, driver])):
+        os.makedirs(os.path.dirname(demo), exist_ok=True)
+        _run(["g++", "-std=c++14", "-O2", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + eigen, driver, "-o", demo,
+              "-L" + HERE, "-lvio_backend", "-lvio_b200", "-Wl,-rpath,$ORIGIN/../visual-inertial-odometry_b200"] + dyn)
+    return out
+
+
 def build_all(force=False):
-    return build_cuda(force), build_scenes(force)
+    return build_cuda(force), build_scenes(force), build_backend(force)
 
 
 if __name__ == "__main__":

@@ -84,6 +84,9 @@ struct vio_problem {
     // solver workspaces
     DBuf<double> chol_work;
     DBuf<int> info;
+    DBuf<unsigned> bar;
+    bool coop_ok = false;
+    int num_sms = 148;
     DBuf<double> bpcg_minv, bpcg_x, bpcg_r, bpcg_z, bpcg_p, bpcg_w, bpcg_parta, bpcg_partb, bpcg_scal;
     // reductions
     DBuf<double> partial, partial2, scal;
@@ -336,11 +339,32 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         const int g_spmv = grid_for(6LL * nb, 192, BPCG_MAXPART);
         const int g_upd = grid_for(nb, 128, BPCG_MAXPART);
         const int g_dir = grid_for(6LL * nb, 256, BPCG_MAXPART);
+        double hs[8];
+        bool done_persistent = false;
+        if (p->coop_ok && !getenv("VIO_B200_PCG_MULTIKERNEL")) {
+            // one cooperative launch: grid sized to be co-resident (2 CTAs per SM at most)
+            int dev_sms = p->num_sms, occ = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bpcg_persistent, 256, 0));
+            int grid = std::min(dev_sms * std::min(occ, 2), (nb + 7) / 8);
+            grid = std::max(1, std::min(grid, BPCG_MAXPART));
+            if (p->bar.n < 2) CK(p->bar.alloc(2));
+            CK(cudaMemsetAsync(p->bar.p, 0, 2 * sizeof(unsigned), p->stream));
+            int mi = max_iter;
+            unsigned *barp = p->bar.p;
+            void *args[] = {(void *)&s, (void *)&mi, (void *)&barp};
+            cudaError_t ce = cudaLaunchCooperativeKernel((void *)k_bpcg_persistent, dim3(grid), dim3(256), args, 0, p->stream);
+            if (ce == cudaSuccess) {
+                p->launches++;
+                done_persistent = true;
+            } else {
+                (void)cudaGetLastError();  // fall back to the multi-kernel path below
+            }
+        }
+        if (!done_persistent) {
         k_bpcg_init<<<g_init, 256, 0, p->stream>>>(s);
         k_bpcg_init2<<<1, 256, 0, p->stream>>>(s, g_init);
         p->launches += 2;
         int par = 0;
-        double hs[8];
         const int batch = 32;
         for (int done_it = 0; done_it < max_iter;) {
             for (int k = 0; k < batch; ++k) {
@@ -355,6 +379,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             CK(cudaMemcpyAsync(hs, s.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
             CK(cudaStreamSynchronize(p->stream));
             if (hs[3] != 0.0) break;
+        }
         }
         CK(cudaMemcpyAsync(hs, s.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         CK(cudaStreamSynchronize(p->stream));
@@ -463,6 +488,13 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
     if (cudaMallocHost((void **)&p->h_scal, 64 * sizeof(double)) != cudaSuccess) {
         delete p;
         return VIO_ERR_CUDA;
+    }
+    {
+        int coop = 0, sms = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        p->coop_ok = coop != 0;
+        if (sms > 0) p->num_sms = sms;
     }
     p->ev_lin.resize(VIO_TRACE_MAX + 8);
     for (auto &e : p->ev_lin) {

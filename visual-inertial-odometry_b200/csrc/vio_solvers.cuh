@@ -314,3 +314,139 @@ __global__ void k_bpcg_commit(BpcgView s) {
     s.scal[4] = s.scal[6];
     s.scal[3] = s.scal[7];
 }
+
+// ------------------------------------------------------------------------------------------------
+// Persistent block-Jacobi PCG: ONE cooperative launch per reduced solve.  Every CTA owns a contiguous range
+// of block rows; three software grid barriers per iteration (after S p, after the r/z update, after the
+// direction update).  All CTAs re-sum the per-CTA partial dot products in the same fixed order, so alpha,
+// beta and the convergence decision are bitwise identical everywhere (and across ranks).  The reduced
+// system (60 MB at config 5) stays L2-resident between iterations.
+//   bar[0] = arrival counter, bar[1] = generation   (zeroed by the host before the launch)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned *vgen = bar + 1;
+        const unsigned gen = *vgen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == nblocks - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*vgen == gen) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double sum_partials_cg(const double *part, int n, double *red) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t += __ldcg(part + i);
+    return cta_sum(t, red);
+}
+
+__global__ void __launch_bounds__(256) k_bpcg_persistent(BpcgView s, int max_iter, unsigned *bar) {
+    __shared__ double red[32];
+    const int nblk = gridDim.x;
+    const int br = (s.nb + nblk - 1) / nblk;           // block rows per CTA
+    const int i0 = min(s.nb, blockIdx.x * br), i1 = min(s.nb, i0 + br);
+    const int r0 = 6 * i0, r1 = 6 * i1;
+    double *part_a = s.part_a, *part_b = s.part_b, *part_c = s.part_a + BPCG_MAXPART;
+    // ---- init: Minv = inv(S_ii + lambda I), x = 0, r = b, z = Minv r, p = z
+    double l_rz = 0.0, l_bb = 0.0;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        double A[36], Ai[36];
+        const double *d = s.val + 36 * (size_t)s.diag[i];
+        for (int k = 0; k < 36; ++k) A[k] = d[k];
+        for (int k = 0; k < 6; ++k) A[7 * k] += s.lambda;
+        inv6_spd(A, Ai);
+        double *mo = s.minv + 36 * (size_t)i;
+        for (int k = 0; k < 36; ++k) mo[k] = Ai[k];
+        double rb[6];
+        for (int k = 0; k < 6; ++k) rb[k] = s.b[6 * (size_t)i + k];
+        for (int r = 0; r < 6; ++r) {
+            double z = 0.0;
+            for (int c = 0; c < 6; ++c) z += Ai[6 * r + c] * rb[c];
+            const size_t o = 6 * (size_t)i + r;
+            s.x[o] = 0.0; s.r[o] = rb[r]; s.z[o] = z; s.p[o] = z;
+            l_rz += rb[r] * z;
+            l_bb += rb[r] * rb[r];
+        }
+    }
+    {
+        const double a = cta_sum(l_rz, red), b = cta_sum(l_bb, red);
+        if (threadIdx.x == 0) { part_a[blockIdx.x] = a; part_b[blockIdx.x] = b; }
+    }
+    grid_barrier(bar, nblk);
+    double rz = sum_partials_cg(part_a, nblk, red);
+    const double bb = sum_partials_cg(part_b, nblk, red);
+    double rr = bb;
+    int it = 0;
+    const double thr = s.tol * sqrt(bb);
+    grid_barrier(bar, nblk);  // partial buffers are reused below
+    if (bb > 0.0) {
+        while (it < max_iter) {
+            // ---- w = (S + lambda I) p on own rows; partial p.w
+            double l_pw = 0.0;
+            for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) {
+                const int i = t / 6, rw = t - 6 * i;
+                double acc = 0.0;
+                const int k0 = s.rowptr[i], k1 = s.rowptr[i + 1];
+                for (int k = k0; k < k1; ++k) {
+                    const double2 *a = reinterpret_cast<const double2 *>(s.val + 36 * (size_t)k + 6 * rw);
+                    const double2 *pp = reinterpret_cast<const double2 *>(s.p + 6 * (size_t)s.col[k]);
+                    const double2 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
+                    const double2 p0 = __ldcg(pp), p1 = __ldcg(pp + 1), p2 = __ldcg(pp + 2);
+                    acc += a0.x * p0.x + a0.y * p0.y + a1.x * p1.x + a1.y * p1.y + a2.x * p2.x + a2.y * p2.y;
+                }
+                const double pi = __ldcg(s.p + t);
+                acc += s.lambda * pi;
+                s.w[t] = acc;
+                l_pw += pi * acc;
+            }
+            {
+                const double a = cta_sum(l_pw, red);
+                if (threadIdx.x == 0) part_a[blockIdx.x] = a;
+            }
+            grid_barrier(bar, nblk);
+            const double alpha = rz / sum_partials_cg(part_a, nblk, red);
+            // ---- x += alpha p ; r -= alpha w (own rows) ; then z = Minv r ; partial r.z, r.r
+            for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) {
+                s.x[t] += alpha * __ldcg(s.p + t);
+                s.r[t] -= alpha * s.w[t];
+            }
+            __syncthreads();
+            double l_rz2 = 0.0, l_rr = 0.0;
+            for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) {
+                const int i = t / 6, rw = t - 6 * i;
+                const double *mi = s.minv + 36 * (size_t)i + 6 * rw;
+                const double *rb = s.r + 6 * (size_t)i;
+                const double z = mi[0] * rb[0] + mi[1] * rb[1] + mi[2] * rb[2] + mi[3] * rb[3] + mi[4] * rb[4] + mi[5] * rb[5];
+                s.z[t] = z;
+                l_rz2 += rb[rw] * z;
+                l_rr += rb[rw] * rb[rw];
+            }
+            {
+                const double a = cta_sum(l_rz2, red), b = cta_sum(l_rr, red);
+                if (threadIdx.x == 0) { part_b[blockIdx.x] = a; part_c[blockIdx.x] = b; }
+            }
+            grid_barrier(bar, nblk);
+            const double rz_new = sum_partials_cg(part_b, nblk, red);
+            rr = sum_partials_cg(part_c, nblk, red);
+            ++it;
+            if (!(sqrt(rr) > thr)) break;  // identical on every CTA
+            const double beta = rz_new / rz;
+            rz = rz_new;
+            for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) s.p[t] = s.z[t] + beta * __ldcg(s.p + t);
+            grid_barrier(bar, nblk);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        s.scal[4] = (double)it;
+        s.scal[5] = rr;
+        s.scal[3] = 1.0;
+        s.scal[2] = bb;
+    }
+}
