@@ -87,6 +87,8 @@ struct vio_problem {
     DBuf<unsigned> bar;
     bool coop_ok = false;
     int num_sms = 148;
+    DBuf<double> bpcg_p2;
+    DBuf<unsigned long long> prof;
     DBuf<double> bpcg_minv, bpcg_x, bpcg_r, bpcg_z, bpcg_p, bpcg_w, bpcg_parta, bpcg_partb, bpcg_scal;
     // reductions
     DBuf<double> partial, partial2, scal;
@@ -191,6 +193,11 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
         gv.n_groups = p->n_groups; gv.ld = p->storage == VIO_STORAGE_DENSE ? p->P : 6;
         gv.hdr = (const GroupHdr *)p->g_hdr.p; gv.slot_pose = p->g_slot_pose.p; gv.pairinfo = p->g_pairinfo.p;
         gv.ell_pjx = p->ell_pjx.p; gv.ell_pjy = p->ell_pjy.p; gv.ell_edge = p->ell_edge.p;
+        gv.prof = nullptr;
+        if (getenv("VIO_B200_PROFILE")) {
+            if (p->prof.n < 8) { CK(p->prof.alloc(8)); CK(cudaMemsetAsync(p->prof.p, 0, 8 * sizeof(unsigned long long), p->stream)); }
+            gv.prof = p->prof.p;
+        }
         if (with_schur) k_linearize_grouped<true><<<p->n_groups, p->group_threads, p->group_smem, p->stream>>>(v, gv);
         else k_linearize_grouped<false><<<p->n_groups, p->group_threads, p->group_smem, p->stream>>>(v, gv);
         p->launches++;
@@ -344,15 +351,20 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         if (p->coop_ok && !getenv("VIO_B200_PCG_MULTIKERNEL")) {
             // one cooperative launch: grid sized to be co-resident (2 CTAs per SM at most)
             int dev_sms = p->num_sms, occ = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bpcg_persistent, 256, 0));
-            int grid = std::min(dev_sms * std::min(occ, 2), (nb + 7) / 8);
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bpcg_persistent, BPCG_P_THREADS, 0));
+            int grid = std::min(dev_sms * std::max(1, std::min(occ, 1)), (nb + 15) / 16);
             grid = std::max(1, std::min(grid, BPCG_MAXPART));
             if (p->bar.n < 2) CK(p->bar.alloc(2));
+            if (p->bpcg_p2.n < (size_t)P) CK(p->bpcg_p2.alloc(P));
             CK(cudaMemsetAsync(p->bar.p, 0, 2 * sizeof(unsigned), p->stream));
             int mi = max_iter;
             unsigned *barp = p->bar.p;
-            void *args[] = {(void *)&s, (void *)&mi, (void *)&barp};
-            cudaError_t ce = cudaLaunchCooperativeKernel((void *)k_bpcg_persistent, dim3(grid), dim3(256), args, 0, p->stream);
+            double *p2 = p->bpcg_p2.p;
+            int n_init = g_init;
+            k_bpcg_init<<<g_init, 256, 0, p->stream>>>(s);
+            p->launches++;
+            void *args[] = {(void *)&s, (void *)&mi, (void *)&barp, (void *)&p2, (void *)&n_init};
+            cudaError_t ce = cudaLaunchCooperativeKernel((void *)k_bpcg_persistent, dim3(grid), dim3(BPCG_P_THREADS), args, 0, p->stream);
             if (ce == cudaSuccess) {
                 p->launches++;
                 done_persistent = true;
@@ -383,6 +395,13 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         }
         CK(cudaMemcpyAsync(hs, s.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         CK(cudaStreamSynchronize(p->stream));
+        if (done_persistent && getenv("VIO_B200_PROFILE")) {
+            double hc[4];
+            cudaMemcpy(hc, s.scal + 8, sizeof(hc), cudaMemcpyDeviceToHost);
+            const double it_ = std::max(1.0, hs[4]);
+            fprintf(stderr, "[vio_b200 profile] pcg CTA0 cycles/iter: spmv %.0f barrier1+sum %.0f update %.0f barrier2+sums %.0f (iters %.0f)\n",
+                    hc[0] / it_, hc[1] / it_, hc[2] / it_, hc[3] / it_, hs[4]);
+        }
         if (pcg_iters) *pcg_iters = (int64_t)hs[4];
     } else {
         return fail(p, VIO_ERR_INVALID, "unknown solver %d", solver);
@@ -865,6 +884,17 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
     p->last_lin_launches = (int64_t)p->ev_lin_used;
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    if (p->prof.n >= 8) {
+        unsigned long long hp[8];
+        cudaMemcpy(hp, p->prof.p, sizeof(hp), cudaMemcpyDeviceToHost);
+        double tot = 0;
+        for (int k = 0; k < 7; ++k) tot += (double)hp[k];
+        fprintf(stderr, "[vio_b200 profile] linearise phases (share of CTA cycles): setup %.1f%% host-chain %.1f%% edges %.1f%% "
+                        "landmark-sums %.1f%% assemble %.1f%% schur %.1f%% flush %.1f%%  (total %.3g cycles)\n",
+                100 * hp[0] / tot, 100 * hp[1] / tot, 100 * hp[2] / tot, 100 * hp[3] / tot, 100 * hp[4] / tot, 100 * hp[5] / tot,
+                100 * hp[6] / tot, tot);
+        cudaMemset(p->prof.p, 0, sizeof(hp));
+    }
     st->iterations = iter;
     st->n_trace = std::min(iter, VIO_TRACE_MAX);
     st->chi2_final = chi;

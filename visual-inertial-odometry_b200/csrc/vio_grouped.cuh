@@ -34,7 +34,16 @@ struct GroupView {
     const long long *pairinfo;   // [pair0 + p] = (offset << 2) | flags   (0 normal, 1 transposed, 2 diagonal, 3 skip)
     const double *ell_pjx, *ell_pjy;  // [ell0 + (s-1)*nlm + l], NaN = no observation
     const int *ell_edge;         // packed edge index (for H_lp observer rows), -1 = none
+    unsigned long long *prof;    // optional [8] per-phase cycle counters (VIO_B200_PROFILE=1), else nullptr
 };
+#define VIO_PROF_MARK(slot)                                                          \
+    do {                                                                             \
+        if (gv.prof && threadIdx.x == 0) {                                           \
+            const long long now_ = clock64();                                        \
+            atomicAdd(gv.prof + (slot), (unsigned long long)(now_ - prof_t_));       \
+            prof_t_ = now_;                                                          \
+        }                                                                            \
+    } while (0)
 
 __host__ __device__ inline size_t group_smem_doubles(int ns, int nlm) {
     const int npairs = ns * (ns + 1) / 2;
@@ -109,6 +118,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
     int *pair_a = poff + ns;                          // [npairs]
     int *pair_b = pair_a + npairs;
 
+    long long prof_t_ = gv.prof ? clock64() : 0;
     // ---- phase 0: slot table, pose cache, zero fills ---------------------------------------------------------
     for (int s = tid; s < ns; s += nt) {
         const int pid = s == 0 ? h.host : gv.slot_pose[h.slot0 + s];
@@ -123,8 +133,10 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         pair_a[p] = a;
         pair_b[p] = a + rem;
     }
-    for (size_t i = tid; i < (size_t)nlm * ns * 6; i += nt) w[i] = 0.0;
-    for (size_t i = tid; i < (size_t)nlm * (ns - 1) * 9; i += nt) lmM[i] = 0.0;
+    if (!h.pad) {  // pad = 1: every landmark of the group is observed from every slot -> all entries get written
+        for (size_t i = tid; i < (size_t)nlm * ns * 6; i += nt) w[i] = 0.0;
+        for (size_t i = tid; i < (size_t)nlm * (ns - 1) * 9; i += nt) lmM[i] = 0.0;
+    }
     for (int i = tid; i < ns * 48; i += nt) red[i] = 0.0;
     __syncthreads();
     for (int i = tid; i < ns * 12; i += nt) {
@@ -133,6 +145,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
     }
     __syncthreads();
     const bool hfix = pfix[0] != 0;
+    VIO_PROF_MARK(0);
 
     // ---- phase 0.5: per-landmark host chain ------------------------------------------------------------------
     for (int l = tid; l < nlm; l += nt) {
@@ -156,6 +169,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         for (int k = 0; k < 9; ++k) o[6 + k] = -G[k];
     }
     __syncthreads();
+    VIO_PROF_MARK(1);
 
     // ---- phase 1: edges, slot-major.  warp <-> slot, lanes <-> landmarks ----------------------------------------
     for (int s = 1 + wid; s < ns; s += nw) {
@@ -164,12 +178,16 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         double acc[48];
 #pragma unroll
         for (int k = 0; k < 48; ++k) acc[k] = 0.0;
+        // software pipeline: the next round's observation is in flight while this one is evaluated
+        const size_t ebase = (size_t)h.ell0 + (size_t)(s - 1) * nlm;
+        double n_pjx = 0.0, n_pjy = 0.0;
+        int n_edge = -1;
+        if (lane < nlm) { n_pjx = gv.ell_pjx[ebase + lane]; n_pjy = gv.ell_pjy[ebase + lane]; n_edge = gv.ell_edge[ebase + lane]; }
         for (int l = lane; l < nlm; l += 32) {
-            const size_t e = (size_t)h.ell0 + (size_t)(s - 1) * nlm + l;
-            const double pjx = gv.ell_pjx[e];
+            const double pjx = n_pjx, pjy = n_pjy;
+            const int edge = n_edge;
+            if (l + 32 < nlm) { n_pjx = gv.ell_pjx[ebase + l + 32]; n_pjy = gv.ell_pjy[ebase + l + 32]; n_edge = gv.ell_edge[ebase + l + 32]; }
             if (pjx != pjx) continue;  // NaN: this landmark is not observed from slot s
-            const double pjy = gv.ell_pjy[e];
-            const int edge = gv.ell_edge[e];
             const double *lh = lmh + 16 * (size_t)l;
             const double pw[3] = {lh[0], lh[1], lh[2]};
             double pcj[3], pbj[3], r[2];
@@ -206,8 +224,9 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
             lm9[6] = m[0]; lm9[7] = m[1]; lm9[8] = m[2];
             double *wog = v.wo + 6 * (size_t)edge;
             if (jfix) {
+                double *wz = w + ((size_t)l * ns + s) * 6;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) wog[k] = 0.0;
+                for (int k = 0; k < 6; ++k) { wog[k] = 0.0; wz[k] = 0.0; }
                 continue;
             }
             double N[9], MN[9], NMN[9], Ntm[3], Mg[3], NtMg[3];
@@ -242,6 +261,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         if (!(lane & 1)) red[48 * (size_t)s + base + 1] = acc[1];
     }
     __syncthreads();
+    VIO_PROF_MARK(2);
 
     // ---- phase 1.5: per-landmark sums -> H_ll, b_l, host row of H_lp, host blocks ------------------------------
     {
@@ -298,6 +318,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         }
     }
     __syncthreads();
+    VIO_PROF_MARK(3);
 
     // ---- phase 1.9: assemble the direct (J^T W J) part of the group tile from the reduced vectors -------------
     for (int idx = tid; idx < npairs * 36; idx += nt) {
@@ -337,19 +358,23 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         bvec[18 * s + 6 + k] = 0.0;
     }
     __syncthreads();
+    VIO_PROF_MARK(4);
 
     // ---- phase 2: Schur outer products, thread <-> (block pair, landmark subset) --------------------------------
+    int nsub = 1;
     if (WITH_SCHUR) {
-        const int nsub = max(1, nt / npairs);
+        // thread <-> (pair p, landmark subset q).  Lanes of a warp hold DIFFERENT pairs of the SAME subset, so the
+        // w_a / w_b reads of a warp hit few distinct shared-memory words (broadcast).  Subset q > 0 parks its
+        // partial tile in the (now dead) lmM region; the flush adds the copies up - no barrier rounds, no atomics.
+        nsub = max(1, min(nt / npairs, 1 + (int)(((size_t)nlm * (ns - 1) * 9) / ((size_t)npairs * 36))));
         for (int p0 = 0; p0 < npairs; p0 += nt) {  // one pass unless npairs > blockDim
-            const int item = tid;
-            const int p = p0 + (nsub > 1 ? item % npairs : item);
-            const int q = nsub > 1 ? item / npairs : 0;
+            const int p = p0 + (nsub > 1 ? tid % npairs : tid);
+            const int q = nsub > 1 ? tid / npairs : 0;
             const bool active = p < npairs && q < nsub;
-            double acc[36];
-#pragma unroll
-            for (int k = 0; k < 36; ++k) acc[k] = 0.0;
             if (active) {
+                double acc[36];
+#pragma unroll
+                for (int k = 0; k < 36; ++k) acc[k] = 0.0;
                 const int a = pair_a[p], b = pair_b[p];
                 for (int l = q; l < nlm; l += nsub) {
                     const double inv = hinv[l];
@@ -363,14 +388,15 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
 #pragma unroll
                         for (int c = 0; c < 6; ++c) acc[6 * r + c] += x[r] * y[c];
                 }
-            }
-            for (int qq = 0; qq < nsub; ++qq) {
-                if (active && q == qq) {
+                if (q == 0) {
                     double *t = T + 36 * (size_t)p;
 #pragma unroll
                     for (int k = 0; k < 36; ++k) t[k] -= acc[k];
+                } else {
+                    double *t = lmM + ((size_t)(q - 1) * npairs + p) * 36;
+#pragma unroll
+                    for (int k = 0; k < 36; ++k) t[k] = acc[k];
                 }
-                __syncthreads();
             }
         }
         for (int idx = tid; idx < ns * 6; idx += nt) {
@@ -382,6 +408,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         __syncthreads();
     }
 
+    VIO_PROF_MARK(5);
     // ---- flush: one RED.F64 per touched element of the reduced system -------------------------------------------
     for (int idx = tid; idx < npairs * 36; idx += nt) {
         const int p = idx / 36, k = idx % 36, r = k / 6, c = k % 6;
@@ -391,7 +418,9 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         if (flags == 2 && r > c) continue;
         const size_t off = (size_t)(info >> 2);
         const size_t e = flags == 1 ? (size_t)c * gv.ld + r : (size_t)r * gv.ld + c;
-        const double val = T[idx];
+        double val = T[idx];
+        if (WITH_SCHUR)
+            for (int q = 1; q < nsub; ++q) val -= lmM[((size_t)(q - 1) * npairs + p) * 36 + k];
         if (val != 0.0) atomicAdd(v.S + off + e, val);
     }
     for (int idx = tid; idx < ns * 6; idx += nt) {
@@ -401,4 +430,6 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         atomicAdd(v.hdiag + poff[s] + k, bvec[18 * s + 12 + k]);
         if (WITH_SCHUR) atomicAdd(v.bcorr + poff[s] + k, bvec[18 * s + 6 + k]);
     }
+    __syncthreads();
+    VIO_PROF_MARK(6);
 }

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <vector>
@@ -206,6 +207,8 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     {
         const int NS_MAX = 22;
         const size_t SMEM_BUDGET = 200 * 1024;
+        int target_lm = 50;  // landmarks per CTA (VIO_B200_GROUP_LM overrides; tuning knob)
+        if (const char *ev = getenv("VIO_B200_GROUP_LM")) target_lm = std::max(1, atoi(ev));
         auto smem_bytes = [](int ns, int nlm) -> size_t {
             const size_t npairs = (size_t)ns * (ns + 1) / 2;
             const size_t dbl = (size_t)ns * 12 + (size_t)nlm * 16 + (size_t)nlm * ns * 6 + (size_t)nlm * (ns - 1) * 9 +
@@ -255,45 +258,62 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
                 }
                 ++l1;
             }
-            if (!K.grouped_ok) { for (int p2 : slots) slot_of_pose[p2] = -1; break; }
-            const int ns = (int)slots.size(), nlm = l1 - l0;
-            const int ell0 = (int)K.ell_pjx.size(), pair0 = (int)K.g_pairinfo.size(), slot0 = (int)K.g_slot_pose.size();
-            const int hdr[8] = {host, ns, l0, nlm, ell0, pair0, slot0, 0};
-            K.g_hdr.insert(K.g_hdr.end(), hdr, hdr + 8);
-            K.g_slot_pose.insert(K.g_slot_pose.end(), slots.begin(), slots.end());
-            const double qnan = std::numeric_limits<double>::quiet_NaN();
-            K.ell_pjx.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, qnan);
-            K.ell_pjy.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, 0.0);
-            K.ell_edge.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, -1);
-            for (int l = l0; l < l1; ++l)
-                for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
-                    const int sl = slot_of_pose[e_pose_j[e]];
-                    const size_t idx = (size_t)ell0 + (size_t)(sl - 1) * nlm + (l - l0);
-                    K.ell_pjx[idx] = pjx[e]; K.ell_pjy[idx] = pjy[e]; K.ell_edge[idx] = e;
-                }
-            for (int a = 0; a < ns && K.grouped_ok; ++a)
-                for (int b = a; b < ns; ++b) {
-                    const int pa = slots[a], pb = slots[b];
-                    long long off = 0, info;
-                    if (K.pose_fixed.size() == 0) {}
-                    const bool fa = g->pose_fixed && g->pose_fixed[pa], fb = g->pose_fixed && g->pose_fixed[pb];
-                    if (fa || fb) info = 3;
-                    else if (a == b) { if (!block_off(pa, pa, off)) { K.grouped_ok = false; break; } info = (off << 2) | 2; }
-                    else if (pose_off[pa] < pose_off[pb]) { if (!block_off(pa, pb, off)) { K.grouped_ok = false; break; } info = (off << 2) | 0; }
-                    else { if (!block_off(pb, pa, off)) { K.grouped_ok = false; break; } info = (off << 2) | 1; }
-                    K.g_pairinfo.push_back(info);
-                }
-            K.group_smem_max = std::max(K.group_smem_max, smem_bytes(ns, nlm));
-            max_obs_slots = std::max(max_obs_slots, ns - 1);
             for (int p2 : slots) slot_of_pose[p2] = -1;
-            K.n_groups++;
+            if (!K.grouped_ok) break;
+            // split the feasible run [l0, l1) evenly into chunks of about `target` landmarks: smaller CTAs leave room
+            // for two resident CTAs per SM (shared memory and registers), which hides barrier and memory latency
+            const int nrun = l1 - l0;
+            const int nchunk = (nrun + target_lm - 1) / target_lm;
+            for (int ch = 0; ch < nchunk && K.grouped_ok; ++ch) {
+                const int la = l0 + (int)((long long)nrun * ch / nchunk), lb = l0 + (int)((long long)nrun * (ch + 1) / nchunk);
+                slots.assign(1, host);
+                slot_of_pose[host] = 0;
+                for (int l = la; l < lb; ++l)
+                    for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
+                        const int pj = e_pose_j[e];
+                        if (slot_of_pose[pj] < 0) { slot_of_pose[pj] = (int)slots.size(); slots.push_back(pj); }
+                    }
+                const int ns = (int)slots.size(), nlm = lb - la;
+                const int ell0 = (int)K.ell_pjx.size(), pair0 = (int)K.g_pairinfo.size(), slot0 = (int)K.g_slot_pose.size();
+                int full = 1;
+                for (int l = la; l < lb; ++l) if (lm_eptr[l + 1] - lm_eptr[l] != ns - 1) full = 0;
+                const int hdr[8] = {host, ns, la, nlm, ell0, pair0, slot0, full};
+                K.g_hdr.insert(K.g_hdr.end(), hdr, hdr + 8);
+                K.g_slot_pose.insert(K.g_slot_pose.end(), slots.begin(), slots.end());
+                const double qnan = std::numeric_limits<double>::quiet_NaN();
+                K.ell_pjx.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, qnan);
+                K.ell_pjy.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, 0.0);
+                K.ell_edge.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, -1);
+                for (int l = la; l < lb; ++l)
+                    for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
+                        const int sl = slot_of_pose[e_pose_j[e]];
+                        const size_t idx = (size_t)ell0 + (size_t)(sl - 1) * nlm + (l - la);
+                        K.ell_pjx[idx] = pjx[e]; K.ell_pjy[idx] = pjy[e]; K.ell_edge[idx] = e;
+                    }
+                for (int a = 0; a < ns && K.grouped_ok; ++a)
+                    for (int b = a; b < ns; ++b) {
+                        const int pa = slots[a], pb = slots[b];
+                        long long off = 0, info;
+                        const bool fa = g->pose_fixed && g->pose_fixed[pa], fb = g->pose_fixed && g->pose_fixed[pb];
+                        if (fa || fb) info = 3;
+                        else if (a == b) { if (!block_off(pa, pa, off)) { K.grouped_ok = false; break; } info = (off << 2) | 2; }
+                        else if (pose_off[pa] < pose_off[pb]) { if (!block_off(pa, pb, off)) { K.grouped_ok = false; break; } info = (off << 2) | 0; }
+                        else { if (!block_off(pb, pa, off)) { K.grouped_ok = false; break; } info = (off << 2) | 1; }
+                        K.g_pairinfo.push_back(info);
+                    }
+                K.group_smem_max = std::max(K.group_smem_max, smem_bytes(ns, nlm));
+                max_obs_slots = std::max(max_obs_slots, ns - 1);
+                for (int p2 : slots) slot_of_pose[p2] = -1;
+                K.n_groups++;
+            }
             l0 = l1;
         }
         if (K.n_groups == 0) K.grouped_ok = false;
-        // one warp per observer slot, at most 10 warps; fewer slots per warp round when there are more
-        const int rounds = (max_obs_slots + 9) / 10;
-        int nwarp = rounds > 0 ? (max_obs_slots + rounds - 1) / rounds : 1;
+        // two observer slots per warp, 4..10 warps (VIO_B200_GROUP_WARPS overrides; tuning knob)
+        int nwarp = (max_obs_slots + 1) / 2;
         if (nwarp < 4) nwarp = 4;
+        if (nwarp > 10) nwarp = 10;
+        if (const char *ev = getenv("VIO_B200_GROUP_WARPS")) nwarp = std::min(10, std::max(1, atoi(ev)));
         K.group_threads = 32 * nwarp;
     }
 

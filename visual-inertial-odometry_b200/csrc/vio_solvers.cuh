@@ -347,74 +347,75 @@ __device__ __forceinline__ double sum_partials_cg(const double *part, int n, dou
     return cta_sum(t, red);
 }
 
-__global__ void __launch_bounds__(256) k_bpcg_persistent(BpcgView s, int max_iter, unsigned *bar) {
+#define BPCG_P_THREADS 1024
+#define BPCG_P_GROUP 4  // lanes cooperating on one scalar row of S p
+
+__global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView s, int max_iter, unsigned *bar, double *pbuf2,
+                                                                       int n_init_parts) {
     __shared__ double red[32];
     const int nblk = gridDim.x;
     const int br = (s.nb + nblk - 1) / nblk;           // block rows per CTA
     const int i0 = min(s.nb, blockIdx.x * br), i1 = min(s.nb, i0 + br);
     const int r0 = 6 * i0, r1 = 6 * i1;
     double *part_a = s.part_a, *part_b = s.part_b, *part_c = s.part_a + BPCG_MAXPART;
-    // ---- init: Minv = inv(S_ii + lambda I), x = 0, r = b, z = Minv r, p = z
-    double l_rz = 0.0, l_bb = 0.0;
-    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        double A[36], Ai[36];
-        const double *d = s.val + 36 * (size_t)s.diag[i];
-        for (int k = 0; k < 36; ++k) A[k] = d[k];
-        for (int k = 0; k < 6; ++k) A[7 * k] += s.lambda;
-        inv6_spd(A, Ai);
-        double *mo = s.minv + 36 * (size_t)i;
-        for (int k = 0; k < 36; ++k) mo[k] = Ai[k];
-        double rb[6];
-        for (int k = 0; k < 6; ++k) rb[k] = s.b[6 * (size_t)i + k];
-        for (int r = 0; r < 6; ++r) {
-            double z = 0.0;
-            for (int c = 0; c < 6; ++c) z += Ai[6 * r + c] * rb[c];
-            const size_t o = 6 * (size_t)i + r;
-            s.x[o] = 0.0; s.r[o] = rb[r]; s.z[o] = z; s.p[o] = z;
-            l_rz += rb[r] * z;
-            l_bb += rb[r] * rb[r];
-        }
-    }
-    {
-        const double a = cta_sum(l_rz, red), b = cta_sum(l_bb, red);
-        if (threadIdx.x == 0) { part_a[blockIdx.x] = a; part_b[blockIdx.x] = b; }
-    }
-    grid_barrier(bar, nblk);
-    double rz = sum_partials_cg(part_a, nblk, red);
-    const double bb = sum_partials_cg(part_b, nblk, red);
-    double rr = bb;
-    int it = 0;
+    double *pb[2] = {s.p, pbuf2};  // direction vector, double buffered: p_new = z + beta p_old is formed on the fly
+    // init (Minv, x = 0, r = b, z = p = Minv r, partial r.z and b.b) was done by k_bpcg_init with n_init_parts CTAs;
+    // beta = 0 makes the first direction p_new = z + 0 * p_old = z.
+    double rz = sum_partials_cg(part_a, n_init_parts, red);
+    const double bb = sum_partials_cg(part_b, n_init_parts, red);
+    double rr = bb, beta = 0.0;
+    int it = 0, cur = 0;
     const double thr = s.tol * sqrt(bb);
     grid_barrier(bar, nblk);  // partial buffers are reused below
+    const int G = BPCG_P_GROUP;
+    const int sub = threadIdx.x % G;
+    long long tp0 = 0, c_spmv = 0, c_bar1 = 0, c_upd = 0, c_bar2 = 0;
+#define PCG_MARK(acc_) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); acc_ += n_ - tp0; tp0 = n_; } } while (0)
+    if (blockIdx.x == 0 && threadIdx.x == 0) tp0 = clock64();
     if (bb > 0.0) {
         while (it < max_iter) {
-            // ---- w = (S + lambda I) p on own rows; partial p.w
+            const double *pold = pb[cur];
+            double *pnew = pb[cur ^ 1];
+            // ---- w = (S + lambda I) p_new on own rows, p_new = z + beta p_old formed on the fly; partial p.w
             double l_pw = 0.0;
-            for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) {
-                const int i = t / 6, rw = t - 6 * i;
+            for (int t0 = r0; t0 < r1; t0 += blockDim.x / G) {
+                const int t = t0 + threadIdx.x / G;
                 double acc = 0.0;
-                const int k0 = s.rowptr[i], k1 = s.rowptr[i + 1];
-                for (int k = k0; k < k1; ++k) {
-                    const double2 *a = reinterpret_cast<const double2 *>(s.val + 36 * (size_t)k + 6 * rw);
-                    const double2 *pp = reinterpret_cast<const double2 *>(s.p + 6 * (size_t)s.col[k]);
-                    const double2 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
-                    const double2 p0 = __ldcg(pp), p1 = __ldcg(pp + 1), p2 = __ldcg(pp + 2);
-                    acc += a0.x * p0.x + a0.y * p0.y + a1.x * p1.x + a1.y * p1.y + a2.x * p2.x + a2.y * p2.y;
+                if (t < r1) {
+                    const int i = t / 6, rw = t - 6 * i;
+                    const int k0 = s.rowptr[i], k1 = s.rowptr[i + 1];
+                    for (int k = k0 + sub; k < k1; k += G) {
+                        const int cj = s.col[k];
+                        const double2 *a = reinterpret_cast<const double2 *>(s.val + 36 * (size_t)k + 6 * rw);
+                        const double2 *zz = reinterpret_cast<const double2 *>(s.z + 6 * (size_t)cj);
+                        const double2 *pp = reinterpret_cast<const double2 *>(pold + 6 * (size_t)cj);
+                        const double2 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
+                        const double2 z0 = __ldcg(zz), z1 = __ldcg(zz + 1), z2 = __ldcg(zz + 2);
+                        const double2 p0 = __ldcg(pp), p1 = __ldcg(pp + 1), p2 = __ldcg(pp + 2);
+                        acc += a0.x * (z0.x + beta * p0.x) + a0.y * (z0.y + beta * p0.y) + a1.x * (z1.x + beta * p1.x) +
+                               a1.y * (z1.y + beta * p1.y) + a2.x * (z2.x + beta * p2.x) + a2.y * (z2.y + beta * p2.y);
+                    }
                 }
-                const double pi = __ldcg(s.p + t);
-                acc += s.lambda * pi;
-                s.w[t] = acc;
-                l_pw += pi * acc;
+                for (int m = 1; m < G; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+                if (t < r1 && sub == 0) {
+                    const double pi = __ldcg(s.z + t) + beta * __ldcg(pold + t);
+                    acc += s.lambda * pi;
+                    pnew[t] = pi;
+                    s.w[t] = acc;
+                    l_pw += pi * acc;
+                }
             }
             {
                 const double a = cta_sum(l_pw, red);
                 if (threadIdx.x == 0) part_a[blockIdx.x] = a;
             }
+            PCG_MARK(c_spmv);
             grid_barrier(bar, nblk);
             const double alpha = rz / sum_partials_cg(part_a, nblk, red);
+            PCG_MARK(c_bar1);
             // ---- x += alpha p ; r -= alpha w (own rows) ; then z = Minv r ; partial r.z, r.r
             for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) {
-                s.x[t] += alpha * __ldcg(s.p + t);
+                s.x[t] += alpha * pnew[t];
                 s.r[t] -= alpha * s.w[t];
             }
             __syncthreads();
@@ -432,15 +433,16 @@ __global__ void __launch_bounds__(256) k_bpcg_persistent(BpcgView s, int max_ite
                 const double a = cta_sum(l_rz2, red), b = cta_sum(l_rr, red);
                 if (threadIdx.x == 0) { part_b[blockIdx.x] = a; part_c[blockIdx.x] = b; }
             }
+            PCG_MARK(c_upd);
             grid_barrier(bar, nblk);
             const double rz_new = sum_partials_cg(part_b, nblk, red);
             rr = sum_partials_cg(part_c, nblk, red);
+            PCG_MARK(c_bar2);
             ++it;
+            cur ^= 1;
             if (!(sqrt(rr) > thr)) break;  // identical on every CTA
-            const double beta = rz_new / rz;
+            beta = rz_new / rz;
             rz = rz_new;
-            for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) s.p[t] = s.z[t] + beta * __ldcg(s.p + t);
-            grid_barrier(bar, nblk);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -448,5 +450,7 @@ __global__ void __launch_bounds__(256) k_bpcg_persistent(BpcgView s, int max_ite
         s.scal[5] = rr;
         s.scal[3] = 1.0;
         s.scal[2] = bb;
+        s.scal[8] = (double)c_spmv; s.scal[9] = (double)c_bar1; s.scal[10] = (double)c_upd; s.scal[11] = (double)c_bar2;
     }
+#undef PCG_MARK
 }
