@@ -88,6 +88,9 @@ struct vio_problem {
     bool coop_ok = false;
     int num_sms = 148;
     DBuf<double> bpcg_p2;
+    DBuf<int> pcg_colptr, pcg_cols, pcg_lcol;
+    int pcg_grid = -1, pcg_br = 0, pcg_win = 0;
+    size_t pcg_smem = 0;
     DBuf<unsigned long long> prof;
     DBuf<double> bpcg_minv, bpcg_x, bpcg_r, bpcg_z, bpcg_p, bpcg_w, bpcg_parta, bpcg_partb, bpcg_scal;
     // reductions
@@ -350,21 +353,47 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         bool done_persistent = false;
         if (p->coop_ok && !getenv("VIO_B200_PCG_MULTIKERNEL")) {
             // one cooperative launch: grid sized to be co-resident (2 CTAs per SM at most)
-            int dev_sms = p->num_sms, occ = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bpcg_persistent, BPCG_P_THREADS, 0));
-            int grid = std::min(dev_sms * std::max(1, std::min(occ, 1)), (nb + 15) / 16);
-            grid = std::max(1, std::min(grid, BPCG_MAXPART));
+            const int grid = std::max(1, std::min(std::min(p->num_sms, BPCG_MAXPART), (nb + 15) / 16));
+            const int brc = (nb + grid - 1) / grid;
+            if (p->pcg_grid != grid) {
+                // per-CTA column windows + local block indices (host, once per graph)
+                std::vector<int> colptr(grid + 1, 0), cols, lcol(p->h_col.size(), 0), mark(nb, -1);
+                int win_max = 1;
+                for (int c = 0; c < grid; ++c) {
+                    const int a0 = std::min(nb, c * brc), a1 = std::min(nb, a0 + brc);
+                    const int start = (int)cols.size();
+                    for (int i = a0; i < a1; ++i)
+                        for (int k = p->h_rowptr[i]; k < p->h_rowptr[i + 1]; ++k) {
+                            const int j = p->h_col[k];
+                            if (mark[j] < start) { mark[j] = (int)cols.size(); cols.push_back(j); }
+                            lcol[k] = mark[j] - start;
+                        }
+                    colptr[c + 1] = (int)cols.size();
+                    win_max = std::max(win_max, (int)cols.size() - start);
+                }
+                CK(upload(p->pcg_colptr, colptr.data(), colptr.size(), p->stream));
+                CK(upload(p->pcg_cols, cols.data(), cols.size(), p->stream));
+                CK(upload(p->pcg_lcol, lcol.data(), lcol.size(), p->stream));
+                CK(cudaStreamSynchronize(p->stream));
+                p->pcg_grid = grid; p->pcg_br = brc; p->pcg_win = win_max;
+                p->pcg_smem = ((size_t)6 * win_max + (size_t)5 * 6 * brc + (size_t)36 * brc) * sizeof(double);
+                if (p->pcg_smem <= 200 * 1024)
+                    CK(cudaFuncSetAttribute(k_bpcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->pcg_smem));
+            }
             if (p->bar.n < 2) CK(p->bar.alloc(2));
             if (p->bpcg_p2.n < (size_t)P) CK(p->bpcg_p2.alloc(P));
             CK(cudaMemsetAsync(p->bar.p, 0, 2 * sizeof(unsigned), p->stream));
             int mi = max_iter;
             unsigned *barp = p->bar.p;
             double *p2 = p->bpcg_p2.p;
+            BpcgTables tb;
+            tb.br = p->pcg_br; tb.win_max = p->pcg_win; tb.cta_colptr = p->pcg_colptr.p; tb.cta_cols = p->pcg_cols.p; tb.lcol = p->pcg_lcol.p;
             int n_init = g_init;
             k_bpcg_init<<<g_init, 256, 0, p->stream>>>(s);
             p->launches++;
-            void *args[] = {(void *)&s, (void *)&mi, (void *)&barp, (void *)&p2, (void *)&n_init};
-            cudaError_t ce = cudaLaunchCooperativeKernel((void *)k_bpcg_persistent, dim3(grid), dim3(BPCG_P_THREADS), args, 0, p->stream);
+            void *args[] = {(void *)&s, (void *)&tb, (void *)&mi, (void *)&barp, (void *)&p2, (void *)&n_init};
+            cudaError_t ce = p->pcg_smem <= 200 * 1024 ? cudaSuccess : cudaErrorInvalidValue;
+            if (ce == cudaSuccess) ce = cudaLaunchCooperativeKernel((void *)k_bpcg_persistent, dim3(grid), dim3(BPCG_P_THREADS), args, p->pcg_smem, p->stream);
             if (ce == cudaSuccess) {
                 p->launches++;
                 done_persistent = true;
@@ -566,6 +595,7 @@ int vio_set_graph(vio_problem *p, const vio_graph *g) {
     p->has_graph = false;
     p->linearized = false;
     p->lm_valid = false;
+    p->pcg_grid = -1;
     PackedGraph K;
     {
         int rc = pack_graph(g, p->shard_rank, p->shard_world, K, p->err);

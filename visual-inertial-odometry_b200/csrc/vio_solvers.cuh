@@ -348,95 +348,150 @@ __device__ __forceinline__ double sum_partials_cg(const double *part, int n, dou
 }
 
 #define BPCG_P_THREADS 1024
-#define BPCG_P_GROUP 4  // lanes cooperating on one scalar row of S p
+#define BPCG_P_GROUP 8  // lanes cooperating on one scalar row of S p
 
-__global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView s, int max_iter, unsigned *bar, double *pbuf2,
-                                                                       int n_init_parts) {
+// per-CTA tables built once per graph by the host (do_solve_step): the block columns a CTA's rows touch
+// ("window") and, for every stored block, its index inside the owning CTA's window.
+struct BpcgTables {
+    int br;                 // block rows per CTA
+    int win_max;            // largest window (block columns)
+    const int *cta_colptr;  // [grid+1]
+    const int *cta_cols;    // window block columns, per CTA
+    const int *lcol;        // [nnzb] local window index of block k
+};
+
+// fixed-order sum of n partials by warp 0, broadcast to the CTA (identical bits on every CTA and rank)
+__device__ __forceinline__ double sum_partials_w0(const double *part, int n, double *bc) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+        for (int i = threadIdx.x; i < n; i += 32) t += __ldcg(part + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) *bc = t;
+    }
+    __syncthreads();
+    return *bc;
+}
+
+__global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView s, BpcgTables tb, int max_iter, unsigned *bar,
+                                                                       double *pbuf2, int n_init_parts) {
+    extern __shared__ double dsm[];
     __shared__ double red[32];
-    const int nblk = gridDim.x;
-    const int br = (s.nb + nblk - 1) / nblk;           // block rows per CTA
+    __shared__ double bc[2];
+    const int nblk = gridDim.x, tid = threadIdx.x, nt = blockDim.x;
+    const int br = tb.br;
     const int i0 = min(s.nb, blockIdx.x * br), i1 = min(s.nb, i0 + br);
-    const int r0 = 6 * i0, r1 = 6 * i1;
+    const int r0 = 6 * i0, nrow = 6 * (i1 - i0);
+    const int c0 = tb.cta_colptr[blockIdx.x], nwin = tb.cta_colptr[blockIdx.x + 1] - c0;
+    double *pw = dsm;                           // [win_max*6]  direction vector on the CTA's column window
+    double *w_s = pw + 6 * (size_t)tb.win_max;  // [br*6] each: S p, r, z, p, x of the CTA's own rows
+    double *r_s = w_s + 6 * (size_t)br;
+    double *z_s = r_s + 6 * (size_t)br;
+    double *p_s = z_s + 6 * (size_t)br;
+    double *x_s = p_s + 6 * (size_t)br;
+    double *mi_s = x_s + 6 * (size_t)br;        // [br*36] block-Jacobi preconditioner of the own rows
     double *part_a = s.part_a, *part_b = s.part_b, *part_c = s.part_a + BPCG_MAXPART;
-    double *pb[2] = {s.p, pbuf2};  // direction vector, double buffered: p_new = z + beta p_old is formed on the fly
-    // init (Minv, x = 0, r = b, z = p = Minv r, partial r.z and b.b) was done by k_bpcg_init with n_init_parts CTAs;
-    // beta = 0 makes the first direction p_new = z + 0 * p_old = z.
-    double rz = sum_partials_cg(part_a, n_init_parts, red);
-    const double bb = sum_partials_cg(part_b, n_init_parts, red);
+    double *pb[2] = {s.p, pbuf2};  // direction vector in HBM/L2, double buffered (neighbours read the previous one)
+    // init (Minv, r = b, z = p = Minv r, partial r.z and b.b) was done by k_bpcg_init with n_init_parts CTAs
+    for (int t = tid; t < nrow; t += nt) {
+        r_s[t] = s.r[r0 + t];
+        z_s[t] = s.z[r0 + t];
+        p_s[t] = 0.0;
+        x_s[t] = 0.0;
+    }
+    for (int t = tid; t < 36 * (i1 - i0); t += nt) mi_s[t] = s.minv[36 * (size_t)i0 + t];
+    double rz = sum_partials_w0(part_a, n_init_parts, bc);
+    const double bb = sum_partials_w0(part_b, n_init_parts, bc + 1);
     double rr = bb, beta = 0.0;
     int it = 0, cur = 0;
     const double thr = s.tol * sqrt(bb);
-    grid_barrier(bar, nblk);  // partial buffers are reused below
+    grid_barrier(bar, nblk);  // init partials consumed everywhere before the buffers are reused
     const int G = BPCG_P_GROUP;
-    const int sub = threadIdx.x % G;
+    const int sub = tid % G;
     long long tp0 = 0, c_spmv = 0, c_bar1 = 0, c_upd = 0, c_bar2 = 0;
-#define PCG_MARK(acc_) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); acc_ += n_ - tp0; tp0 = n_; } } while (0)
-    if (blockIdx.x == 0 && threadIdx.x == 0) tp0 = clock64();
+#define PCG_MARK(acc_) do { if (blockIdx.x == 0 && tid == 0) { const long long n_ = clock64(); acc_ += n_ - tp0; tp0 = n_; } } while (0)
+    if (blockIdx.x == 0 && tid == 0) tp0 = clock64();
     if (bb > 0.0) {
         while (it < max_iter) {
             const double *pold = pb[cur];
             double *pnew = pb[cur ^ 1];
-            // ---- w = (S + lambda I) p_new on own rows, p_new = z + beta p_old formed on the fly; partial p.w
-            double l_pw = 0.0;
-            for (int t0 = r0; t0 < r1; t0 += blockDim.x / G) {
-                const int t = t0 + threadIdx.x / G;
+            // ---- gather p_new = z + beta p_old on the column window (beta = 0 in the first iteration)
+            for (int t = tid; t < 6 * nwin; t += nt) {
+                const int j = tb.cta_cols[c0 + t / 6], c = t % 6;
+                pw[t] = __ldcg(s.z + 6 * (size_t)j + c) + beta * __ldcg(pold + 6 * (size_t)j + c);
+            }
+            for (int t = tid; t < nrow; t += nt) {
+                const double pi = z_s[t] + beta * p_s[t];
+                p_s[t] = pi;
+                pnew[r0 + t] = pi;
+            }
+            __syncthreads();
+            // ---- w = (S + lambda I) p on own rows: G lanes per scalar row, blocks strided over the lanes
+            for (int t0 = 0; t0 < nrow; t0 += nt / G) {
+                const int t = t0 + tid / G;
                 double acc = 0.0;
-                if (t < r1) {
-                    const int i = t / 6, rw = t - 6 * i;
-                    const int k0 = s.rowptr[i], k1 = s.rowptr[i + 1];
-                    for (int k = k0 + sub; k < k1; k += G) {
-                        const int cj = s.col[k];
-                        const double2 *a = reinterpret_cast<const double2 *>(s.val + 36 * (size_t)k + 6 * rw);
-                        const double2 *zz = reinterpret_cast<const double2 *>(s.z + 6 * (size_t)cj);
-                        const double2 *pp = reinterpret_cast<const double2 *>(pold + 6 * (size_t)cj);
-                        const double2 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
-                        const double2 z0 = __ldcg(zz), z1 = __ldcg(zz + 1), z2 = __ldcg(zz + 2);
-                        const double2 p0 = __ldcg(pp), p1 = __ldcg(pp + 1), p2 = __ldcg(pp + 2);
-                        acc += a0.x * (z0.x + beta * p0.x) + a0.y * (z0.y + beta * p0.y) + a1.x * (z1.x + beta * p1.x) +
-                               a1.y * (z1.y + beta * p1.y) + a2.x * (z2.x + beta * p2.x) + a2.y * (z2.y + beta * p2.y);
+                if (t < nrow) {
+                    const int i = i0 + t / 6, rw = t % 6;
+                    const int k1 = s.rowptr[i + 1];
+                    int k = s.rowptr[i] + sub;
+                    // up to three blocks per lane in flight (rows of <= 24 blocks are covered in one batch)
+                    for (; k < k1; k += 3 * G) {
+                        const int ka = k, kb = k + G, kc = k + 2 * G;
+                        const bool hb = kb < k1, hc = kc < k1;
+                        const double2 *A = reinterpret_cast<const double2 *>(s.val + 36 * (size_t)ka + 6 * rw);
+                        const double2 *B = reinterpret_cast<const double2 *>(s.val + 36 * (size_t)(hb ? kb : ka) + 6 * rw);
+                        const double2 *Cc = reinterpret_cast<const double2 *>(s.val + 36 * (size_t)(hc ? kc : ka) + 6 * rw);
+                        const double2 a0 = __ldg(A), a1 = __ldg(A + 1), a2 = __ldg(A + 2);
+                        const double2 b0 = __ldg(B), b1 = __ldg(B + 1), b2 = __ldg(B + 2);
+                        const double2 d0 = __ldg(Cc), d1 = __ldg(Cc + 1), d2 = __ldg(Cc + 2);
+                        const int la = __ldg(tb.lcol + ka), lb = __ldg(tb.lcol + (hb ? kb : ka)), lc = __ldg(tb.lcol + (hc ? kc : ka));
+                        const double *pa = pw + 6 * la, *pbb = pw + 6 * lb, *pc = pw + 6 * lc;
+                        acc += a0.x * pa[0] + a0.y * pa[1] + a1.x * pa[2] + a1.y * pa[3] + a2.x * pa[4] + a2.y * pa[5];
+                        if (hb) acc += b0.x * pbb[0] + b0.y * pbb[1] + b1.x * pbb[2] + b1.y * pbb[3] + b2.x * pbb[4] + b2.y * pbb[5];
+                        if (hc) acc += d0.x * pc[0] + d0.y * pc[1] + d1.x * pc[2] + d1.y * pc[3] + d2.x * pc[4] + d2.y * pc[5];
                     }
                 }
+#pragma unroll
                 for (int m = 1; m < G; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-                if (t < r1 && sub == 0) {
-                    const double pi = __ldcg(s.z + t) + beta * __ldcg(pold + t);
-                    acc += s.lambda * pi;
-                    pnew[t] = pi;
-                    s.w[t] = acc;
-                    l_pw += pi * acc;
-                }
+                if (t < nrow && sub == 0) w_s[t] = acc + s.lambda * p_s[t];
             }
+            __syncthreads();
+            double l_pw = 0.0;
+            for (int t = tid; t < nrow; t += nt) l_pw += p_s[t] * w_s[t];
             {
                 const double a = cta_sum(l_pw, red);
-                if (threadIdx.x == 0) part_a[blockIdx.x] = a;
+                if (tid == 0) part_a[blockIdx.x] = a;
             }
             PCG_MARK(c_spmv);
             grid_barrier(bar, nblk);
-            const double alpha = rz / sum_partials_cg(part_a, nblk, red);
+            const double alpha = rz / sum_partials_w0(part_a, nblk, bc);
             PCG_MARK(c_bar1);
-            // ---- x += alpha p ; r -= alpha w (own rows) ; then z = Minv r ; partial r.z, r.r
-            for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) {
-                s.x[t] += alpha * pnew[t];
-                s.r[t] -= alpha * s.w[t];
+            // ---- x += alpha p ; r -= alpha w ; z = Minv r ; partial r.z, r.r   (own rows, all in shared memory)
+            for (int t = tid; t < nrow; t += nt) {
+                x_s[t] += alpha * p_s[t];
+                r_s[t] -= alpha * w_s[t];
             }
             __syncthreads();
             double l_rz2 = 0.0, l_rr = 0.0;
-            for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) {
-                const int i = t / 6, rw = t - 6 * i;
-                const double *mi = s.minv + 36 * (size_t)i + 6 * rw;
-                const double *rb = s.r + 6 * (size_t)i;
+            for (int t = tid; t < nrow; t += nt) {
+                const int ib = t / 6, rw = t % 6;
+                const double *mi = mi_s + 36 * (size_t)ib + 6 * rw;
+                const double *rb = r_s + 6 * (size_t)ib;
                 const double z = mi[0] * rb[0] + mi[1] * rb[1] + mi[2] * rb[2] + mi[3] * rb[3] + mi[4] * rb[4] + mi[5] * rb[5];
-                s.z[t] = z;
+                z_s[t] = z;
+                s.z[r0 + t] = z;
                 l_rz2 += rb[rw] * z;
                 l_rr += rb[rw] * rb[rw];
             }
             {
                 const double a = cta_sum(l_rz2, red), b = cta_sum(l_rr, red);
-                if (threadIdx.x == 0) { part_b[blockIdx.x] = a; part_c[blockIdx.x] = b; }
+                if (tid == 0) { part_b[blockIdx.x] = a; part_c[blockIdx.x] = b; }
             }
             PCG_MARK(c_upd);
             grid_barrier(bar, nblk);
-            const double rz_new = sum_partials_cg(part_b, nblk, red);
-            rr = sum_partials_cg(part_c, nblk, red);
+            const double rz_new = sum_partials_w0(part_b, nblk, bc);
+            rr = sum_partials_w0(part_c, nblk, bc + 1);
             PCG_MARK(c_bar2);
             ++it;
             cur ^= 1;
@@ -445,7 +500,8 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
             rz = rz_new;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int t = tid; t < nrow; t += nt) s.x[r0 + t] = x_s[t];
+    if (blockIdx.x == 0 && tid == 0) {
         s.scal[4] = (double)it;
         s.scal[5] = rr;
         s.scal[3] = 1.0;
