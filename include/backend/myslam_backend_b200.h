@@ -267,7 +267,13 @@ class Problem {
 public:
     enum class ProblemType { SLAM_PROBLEM, GENERIC_PROBLEM };
     EIGEN_MAKE_ALIGNED_OPERATOR_NEW;
-    explicit Problem(ProblemType problemType);
+    // the flavour default is fixed by the DRIVER's translation unit (MYSLAM_B200_V17), not by how the library was built
+#ifdef MYSLAM_B200_V17
+    explicit Problem(ProblemType problemType) : Problem(problemType, true) {}
+#else
+    explicit Problem(ProblemType problemType) : Problem(problemType, false) {}
+#endif
+    Problem(ProblemType problemType, bool v17_flavour);
     ~Problem();
     bool AddVertex(std::shared_ptr<Vertex> vertex);
     bool RemoveVertex(std::shared_ptr<Vertex> vertex);
@@ -301,6 +307,7 @@ public:
     double LastMakeHessianMs() const { return last_hessian_ms_; }
 
 private:
+    bool SolveGenericB200(int iterations);
     bool IsPoseVertex(std::shared_ptr<Vertex> v);
     bool IsLandmarkVertex(std::shared_ptr<Vertex> v);
     void SetOrdering();

@@ -217,6 +217,33 @@ int vio_get_kernel_ms(vio_problem *p, double *ms_linearize_kernel, int64_t *laun
 /* total number of kernel launches issued by this handle since creation                      */
 int64_t vio_launch_count(const vio_problem *p);
 
+/* ---- GENERIC_PROBLEM lane: user-defined host edges --------------------------------------------------------------
+ * Problem(GENERIC_PROBLEM) lets callers subclass Vertex/Edge with their own virtual ComputeResidual /
+ * ComputeJacobians / Plus (A15/app/CurveFitting.cpp:14-48, A17/test/CurveFitting.cpp:8-45).  Those virtuals are host
+ * code by construction, so this lane takes the evaluated factors (stacked dense Jacobian, residuals, per-edge
+ * RobustInfo) and does the rest on the device: H = J^T W J, b = -J^T Wb r (MakeHessian, A17/src/backend/problem.cc:
+ * 319-358), (H + lambda I) dx = b (generic branch of SolveLinearSystem, :397-404), chi2, scale.                     */
+typedef struct vio_dense_system {
+    int32_t n;                 /* total local dimension                                                   */
+    int32_t rows;              /* stacked residual rows R = sum of the edges' residual dimensions          */
+    int32_t dmax;              /* largest residual dimension of an edge                                    */
+    int32_t reserved;
+    const double *J;           /* R x n row-major, zero where an edge does not touch a vertex              */
+    const double *r;           /* R                                                                        */
+    const int32_t *row_edge0;  /* R: first stacked row of the edge a row belongs to                        */
+    const int32_t *row_dim;    /* R: residual dimension of that edge                                       */
+    const double *W;           /* R x dmax: row i = row (i - row_edge0[i]) of the edge's RobustInfo        */
+    const double *Wb;          /* R x dmax: same rows of drho * Information (used for b)                   */
+} vio_dense_system;
+int vio_dense_accumulate(vio_problem *p, const vio_dense_system *s, double *max_abs_diag);
+/* chi2 = sum over edges of loss(r^T Information r); info rows like W above, loss per row's edge (VIO_LOSS_*) */
+int vio_dense_chi2(vio_problem *p, int32_t rows, int32_t dmax, const double *r, const int32_t *row_edge0,
+                   const int32_t *row_dim, const double *info, const int32_t *loss_kind, const double *loss_delta,
+                   double *chi2);
+/* (H + lambda I) dx = b by Cholesky; also returns dx^T (lambda dx + b) and |dx|^2 for IsGoodStepInLM       */
+int vio_dense_solve(vio_problem *p, double lambda, double *dx, double *scale_dot, double *dx_norm2);
+int vio_dense_get(vio_problem *p, double *H, double *b);
+
 /* FP64 FMA micro-benchmark (roofline denominator for the FP64-bound kernels): returns TFLOP/s */
 int vio_measure_fp64_peak(int device, double *tflops);
 

@@ -75,6 +75,13 @@ def build_backend(force=False):
         os.makedirs(os.path.dirname(demo), exist_ok=True)
         _run(["g++", "-std=c++14", "-O2", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + eigen, driver, "-o", demo,
               "-L" + HERE, "-lvio_backend", "-lvio_b200", "-Wl,-rpath,$ORIGIN/../visual-inertial-odometry_b200"] + dyn)
+    for src_rel, name, flags in (("15-vio-backend/app/CurveFitting.cpp", "curve_fitting15_b200", []),
+                                 ("17-vins-initialization/vins-mono/test/CurveFitting.cpp", "curve_fitting17_b200", ["-DMYSLAM_B200_V17"])):
+        drv = os.path.join(REF_ASSIGN, src_rel)
+        exe = os.path.join(ROOT, "build", name)
+        if os.path.exists(drv) and (force or _newer(exe, [out, drv])):
+            _run(["g++", "-std=c++14", "-O2", "-w"] + flags + ["-I" + os.path.join(ROOT, "include"), "-I" + eigen, drv, "-o", exe,
+                  "-L" + HERE, "-lvio_backend", "-lvio_b200", "-Wl,-rpath,$ORIGIN/../visual-inertial-odometry_b200"] + dyn)
     return out
 
 

@@ -77,7 +77,8 @@ EXPORTS = [
     "vio_set_allreduce", "vio_set_shard", "vio_set_prior", "vio_get_prior", "vio_set_vertices", "vio_get_vertices",
     "vio_solve", "vio_linearize", "vio_chi2", "vio_solve_step", "vio_apply_step", "vio_rollback_step",
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
-    "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak",
+    "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
+    "vio_dense_solve", "vio_dense_get",
 ]
 
 _lib = None

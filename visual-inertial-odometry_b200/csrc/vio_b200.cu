@@ -88,6 +88,10 @@ struct vio_problem {
     bool coop_ok = false;
     int num_sms = 148;
     DBuf<double> bpcg_p2;
+    // GENERIC_PROBLEM lane
+    int gen_n = 0;
+    DBuf<double> gen_J, gen_r, gen_W, gen_Wb, gen_H, gen_b, gen_dx, gen_work;
+    DBuf<int> gen_e0, gen_dim, gen_kind;
     DBuf<int> pcg_colptr, pcg_cols, pcg_lcol;
     int pcg_grid = -1, pcg_br = 0, pcg_win = 0;
     size_t pcg_smem = 0;
@@ -1066,6 +1070,79 @@ int vio_get_hessian(vio_problem *p, const vio_lm_opts *opts, double *H, double *
         for (int i = 0; i < P; ++i) b[i] = bp[i];
         for (int l = 0; l < M; ++l) b[P + p->lm_global[l]] = bl[l];
     }
+    return VIO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// GENERIC_PROBLEM lane
+// -------------------------------------------------------------------------------------------------
+int vio_dense_accumulate(vio_problem *p, const vio_dense_system *s, double *max_abs_diag) {
+    if (!p || !s || s->n <= 0 || s->rows <= 0 || s->dmax <= 0) return VIO_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    const int n = s->n, R = s->rows, dm = s->dmax;
+    cudaStream_t st = p->stream;
+    CK(upload(p->gen_J, s->J, (size_t)R * n, st)); CK(upload(p->gen_r, s->r, (size_t)R, st));
+    CK(upload(p->gen_W, s->W, (size_t)R * dm, st)); CK(upload(p->gen_Wb, s->Wb, (size_t)R * dm, st));
+    CK(upload(p->gen_e0, s->row_edge0, (size_t)R, st)); CK(upload(p->gen_dim, s->row_dim, (size_t)R, st));
+    if (p->gen_n != n) {
+        CK(p->gen_H.alloc((size_t)n * n)); CK(p->gen_b.alloc(n)); CK(p->gen_dx.alloc(n)); CK(p->gen_work.alloc((size_t)n * n));
+        p->gen_n = n;
+    }
+    DenseSysView v;
+    v.n = n; v.rows = R; v.dmax = dm; v.J = p->gen_J.p; v.r = p->gen_r.p; v.W = p->gen_W.p; v.Wb = p->gen_Wb.p;
+    v.row_edge0 = p->gen_e0.p; v.row_dim = p->gen_dim.p;
+    k_dense_accumulate<<<grid_for((long long)n * (n + 1), 128), 128, 0, st>>>(v, p->gen_H.p, p->gen_b.p);
+    k_absmax_diag<<<1, 256, 0, st>>>(p->gen_H.p, n, p->scal.p + 8);
+    p->launches += 2;
+    CK(cudaMemcpyAsync(p->h_scal + 8, p->scal.p + 8, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (max_abs_diag) *max_abs_diag = p->h_scal[8];
+    return VIO_OK;
+}
+
+int vio_dense_chi2(vio_problem *p, int32_t rows, int32_t dmax, const double *r, const int32_t *row_edge0,
+                   const int32_t *row_dim, const double *info, const int32_t *loss_kind, const double *loss_delta,
+                   double *chi2) {
+    if (!p || rows <= 0 || dmax <= 0 || !r || !row_edge0 || !row_dim || !info || !chi2) return VIO_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    DBuf<double> dr, dinfo, ddelta;
+    DBuf<int> de0, ddim, dkind;
+    CK(upload(dr, r, (size_t)rows, st)); CK(upload(dinfo, info, (size_t)rows * dmax, st));
+    CK(upload(de0, row_edge0, (size_t)rows, st)); CK(upload(ddim, row_dim, (size_t)rows, st));
+    if (loss_kind) { CK(upload(dkind, loss_kind, (size_t)rows, st)); CK(upload(ddelta, loss_delta, (size_t)rows, st)); }
+    k_dense_chi2<<<1, 256, 0, st>>>(rows, dmax, dr.p, de0.p, ddim.p, dinfo.p, loss_kind ? dkind.p : nullptr,
+                                    loss_kind ? ddelta.p : nullptr, p->scal.p + 9);
+    p->launches++;
+    CK(cudaMemcpyAsync(p->h_scal + 9, p->scal.p + 9, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *chi2 = p->h_scal[9];
+    return VIO_OK;
+}
+
+int vio_dense_solve(vio_problem *p, double lambda, double *dx, double *scale_dot, double *dx_norm2) {
+    if (!p || p->gen_n <= 0 || !dx) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    const int n = p->gen_n;
+    cudaStream_t st = p->stream;
+    k_dense_chol_solve<<<1, 1024, n * sizeof(double), st>>>(p->gen_H.p, p->gen_b.p, lambda, n, p->gen_work.p, p->gen_dx.p, p->info.p);
+    k_dense_scale<<<1, 256, 0, st>>>(p->gen_dx.p, p->gen_b.p, n, lambda, p->scal.p + 10);
+    p->launches += 2;
+    CK(cudaMemcpyAsync(dx, p->gen_dx.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p->h_scal + 10, p->scal.p + 10, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (scale_dot) *scale_dot = p->h_scal[10];
+    if (dx_norm2) *dx_norm2 = p->h_scal[11];
+    return VIO_OK;
+}
+
+int vio_dense_get(vio_problem *p, double *H, double *b) {
+    if (!p || p->gen_n <= 0) return VIO_ERR_STATE;
+    CK(cudaSetDevice(p->device));
+    const int n = p->gen_n;
+    if (H) CK(cudaMemcpyAsync(H, p->gen_H.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (b) CK(cudaMemcpyAsync(b, p->gen_b.p, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
     return VIO_OK;
 }
 

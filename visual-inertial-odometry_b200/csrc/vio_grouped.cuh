@@ -49,7 +49,7 @@ __host__ __device__ inline size_t group_smem_doubles(int ns, int nlm) {
     const int npairs = ns * (ns + 1) / 2;
     // pc[ns][12] lmh[nlm][16] w[nlm][ns][6] lmM[nlm][ns-1][9] hinv[nlm] blv[nlm] red[ns][48] T[npairs][36] bvec[ns][18]
     return (size_t)ns * 12 + (size_t)nlm * 16 + (size_t)nlm * ns * 6 + (size_t)nlm * (ns - 1) * 9 + 2 * (size_t)nlm +
-           (size_t)ns * 48 + (size_t)npairs * 36 + (size_t)ns * 18;
+           (size_t)ns * 48 + (size_t)npairs * 36 + (size_t)ns * 18 + (size_t)ns * 9;
 }
 __host__ __device__ inline size_t group_smem_bytes(int ns, int nlm) {
     const int npairs = ns * (ns + 1) / 2;
@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
     double *red = blv + nlm;                          // [ns][48]
     double *T = red + (size_t)ns * 48;                // [npairs][36]
     double *bvec = T + (size_t)npairs * 36;           // [ns][18]  bp(6) bcorr(6) hdiag(6)
-    int *pose_id = (int *)(bvec + (size_t)ns * 18);   // [ns]
+    double *rjric = bvec + (size_t)ns * 18;           // [ns][9]   Rj * Ric per slot (shared by all edges of the slot)
+    int *pose_id = (int *)(rjric + (size_t)ns * 9);   // [ns]
     int *pfix = pose_id + ns;
     int *poff = pfix + ns;
     int *pair_a = poff + ns;                          // [npairs]
@@ -143,6 +144,8 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         const int s = i / 12, k = i % 12;
         pc[i] = v.poseRT[16 * (size_t)pose_id[s] + k];
     }
+    __syncthreads();
+    for (int s = tid; s < ns; s += nt) mat3_mul(pc + 12 * (size_t)s, v.Ric, rjric + 9 * (size_t)s);
     __syncthreads();
     const bool hfix = pfix[0] != 0;
     VIO_PROF_MARK(0);
@@ -195,8 +198,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
             const double iz = 1.0 / pcj[2];
             const double rx = -pcj[0] * iz * iz, ry = -pcj[1] * iz * iz;
             // A = Ric^T Rj^T = (Rj Ric)^T ;  B = reduce * A
-            double RjRic[9];
-            mat3_mul(RTj, v.Ric, RjRic);
+            const double *RjRic = rjric + 9 * (size_t)s;
             double B[6];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {

@@ -510,3 +510,84 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
     }
 #undef PCG_MARK
 }
+
+// ------------------------------------------------------------------------------------------------
+// GENERIC_PROBLEM lane: dense H = J^T W J, b = -J^T Wb r from host-evaluated factors
+// ------------------------------------------------------------------------------------------------
+struct DenseSysView {
+    int n, rows, dmax;
+    const double *J, *r, *W, *Wb;
+    const int *row_edge0, *row_dim;
+};
+// one thread per (a, c) of H (and per a of b): fixed summation order over the stacked rows
+__global__ void k_dense_accumulate(DenseSysView s, double *H, double *b) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = s.n;
+    if (t >= n * (n + 1)) return;
+    const int a = t / (n + 1), c = t % (n + 1);
+    double acc = 0.0;
+    for (int i = 0; i < s.rows; ++i) {
+        const double ja = s.J[(size_t)i * n + a];
+        if (ja == 0.0) continue;
+        const int e0 = s.row_edge0[i], d = s.row_dim[i];
+        double wj = 0.0;
+        if (c < n) {
+            for (int k = 0; k < d; ++k) wj += s.W[(size_t)i * s.dmax + k] * s.J[(size_t)(e0 + k) * n + c];
+        } else {
+            for (int k = 0; k < d; ++k) wj += s.Wb[(size_t)i * s.dmax + k] * s.r[e0 + k];
+        }
+        acc += ja * wj;
+    }
+    if (c < n) H[(size_t)a * n + c] = acc;
+    else b[a] = -acc;
+}
+__global__ void k_dense_chi2(int rows, int dmax, const double *r, const int *row_edge0, const int *row_dim,
+                             const double *info, const int *loss_kind, const double *loss_delta, double *out) {
+    // single CTA; per-edge e2 = r^T Info r accumulated by the edge's first row, fixed order
+    __shared__ double sm[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+        if (row_edge0[i] != i) continue;
+        const int d = row_dim[i];
+        double e2 = 0.0;
+        for (int a = 0; a < d; ++a) {
+            double w = 0.0;
+            for (int k = 0; k < d; ++k) w += info[(size_t)(i + a) * dmax + k] * r[i + k];
+            e2 += r[i + a] * w;
+        }
+        double rho[3];
+        loss_compute(loss_kind ? loss_kind[i] : 0, loss_delta ? loss_delta[i] : 1.0, e2, rho);
+        t += (loss_kind && loss_kind[i] != 0) ? rho[0] : e2;
+    }
+    sm[threadIdx.x] = t;
+    __syncthreads();
+    for (int st = blockDim.x >> 1; st > 0; st >>= 1) {
+        if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sm[0];
+}
+__global__ void k_dense_scale(const double *dx, const double *b, int n, double lambda, double *out2) {
+    __shared__ double s1[256], s2[256];
+    double sc = 0.0, n2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { sc += dx[i] * (lambda * dx[i] + b[i]); n2 += dx[i] * dx[i]; }
+    s1[threadIdx.x] = sc; s2[threadIdx.x] = n2;
+    __syncthreads();
+    for (int st = blockDim.x >> 1; st > 0; st >>= 1) {
+        if (threadIdx.x < st) { s1[threadIdx.x] += s1[threadIdx.x + st]; s2[threadIdx.x] += s2[threadIdx.x + st]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out2[0] = s1[0]; out2[1] = s2[0]; }
+}
+__global__ void k_absmax_diag(const double *H, int n, double *out) {
+    __shared__ double sm[256];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(H[(size_t)i * n + i]));
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int st = blockDim.x >> 1; st > 0; st >>= 1) {
+        if (threadIdx.x < st) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + st]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sm[0];
+}

@@ -134,13 +134,7 @@ void EdgeImuB200::ComputeResidual() { device_only("EdgeImu::ComputeResidual"); }
 void EdgeImuB200::ComputeJacobians() { device_only("EdgeImu::ComputeJacobians"); }
 
 // ---- Problem ------------------------------------------------------------------------------------------------------
-Problem::Problem(ProblemType problemType) : problemType_(problemType) {
-#ifdef MYSLAM_B200_V17
-    v17_ = true;
-#else
-    v17_ = false;
-#endif
-}
+Problem::Problem(ProblemType problemType, bool v17_flavour) : problemType_(problemType), v17_(v17_flavour) {}
 Problem::~Problem() {
     if (handle_) vio_destroy(handle_);
     if (v17_) global_vertex_id = 0;  // the v17 destructor does this (vins-mono/src/backend/problem.cc:38-41)
@@ -225,10 +219,7 @@ bool Problem::Solve(int iterations) {
         return false;
     }
     const auto t0 = std::chrono::steady_clock::now();
-    if (problemType_ != ProblemType::SLAM_PROBLEM) {
-        std::cerr << "vio_b200: GENERIC_PROBLEM (user-defined host edges) is not on the device path yet" << std::endl;
-        return false;
-    }
+    if (problemType_ != ProblemType::SLAM_PROBLEM) return SolveGenericB200(iterations);
     SetOrdering();
     // ---- pack: pose-class vertices in id order, landmarks in id order ---------------------------------------------
     std::vector<double> pose, sb, invd;
@@ -389,6 +380,150 @@ bool Problem::Solve(int iterations) {
     for (size_t i = 0; i < lm_v.size(); ++i) lm_v[i]->Parameters()[0] = invd[i];
     if (have_prior && err_prior_.rows() > 0) vio_get_prior(handle_, b_prior_.data(), err_prior_.data());
     last_hessian_ms_ = st.ms_linearize;
+    last_solve_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::cout << "problem solve cost: " << last_solve_ms_ << " ms" << std::endl;
+    std::cout << "   makeHessian cost: " << last_hessian_ms_ << " ms" << std::endl;
+    return true;
+}
+
+// GENERIC_PROBLEM: vertices and edges are user subclasses whose ComputeResidual / ComputeJacobians / Plus are host
+// virtuals (A15/app/CurveFitting.cpp:14-48).  The host evaluates the factors through those virtuals exactly like the
+// reference's MakeHessian does (A17/src/backend/problem.cc:311-330) and hands them to the device, which builds H, b,
+// solves (H + lambda I) dx = b and reduces chi2 / scale (vio_dense_* in vio_b200.h).  The LM control below is the
+// reference's Solve loop (v15: 15-vio-backend/backend/problem.cc:155-222, v17: vins-mono/src/backend/problem.cc:169-250).
+// Deviation, on purpose: v15's generic branch solves with the UNDAMPED Hessian_ (problem.cc:347-352), a defect that
+// makes its own CurveFitting demo return 0 0 0; both flavours use the damped system here.
+bool Problem::SolveGenericB200(int iterations) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!handle_) {
+        int rc = vio_create(device_, nullptr, &handle_);
+        if (rc != VIO_OK) throw std::runtime_error("vio_b200: no CUDA device (the GPU backend has no CPU fallback)");
+    }
+    // ordering: vertices in id order at consecutive offsets (a single vertex in every reference driver)
+    int n = 0;
+    std::unordered_map<unsigned long, int> off;
+    std::vector<std::shared_ptr<Vertex>> verts;
+    for (auto &kv : verticies_) {
+        off[kv.first] = n;
+        kv.second->SetOrderingId(n);
+        n += kv.second->LocalDimension();
+        verts.push_back(kv.second);
+    }
+    ordering_generic_ = n;
+    std::vector<unsigned long> eids;
+    for (auto &kv : edges_) eids.push_back(kv.first);
+    std::sort(eids.begin(), eids.end());
+    int R = 0, dmax = 1;
+    for (auto id : eids) { const int d = (int)edges_[id]->Residual().rows(); R += d; dmax = std::max(dmax, d); }
+    std::vector<double> J((size_t)R * n), r(R), W((size_t)R * dmax), Wb((size_t)R * dmax), Om((size_t)R * dmax), delta(R);
+    std::vector<int32_t> e0(R), dim(R), kind(R);
+    bool user_loss = false;
+    auto evaluate = [&](bool jac) {
+        int row = 0;
+        for (auto id : eids) {
+            auto &e = edges_[id];
+            e->ComputeResidual();
+            const VecX res = e->Residual();
+            const int d = (int)res.rows();
+            const MatXX info = e->Information();
+            LossFunction *lf = e->GetLossFunction();
+            const int k = lf ? lf->KindB200() : 0;
+            if (k < 0) user_loss = true;
+            for (int a = 0; a < d; ++a) {
+                r[row + a] = res[a]; e0[row + a] = row; dim[row + a] = d; kind[row + a] = k < 0 ? 0 : k;
+                delta[row + a] = lf ? lf->DeltaB200() : 1.0;
+                for (int c = 0; c < d; ++c) Om[(size_t)(row + a) * dmax + c] = info(a, c);
+            }
+            if (jac) {
+                e->ComputeJacobians();
+                const auto jacs = e->Jacobians();
+                const auto vs = e->Verticies();
+                double drho;
+                MatXX rinfo(d, d);
+                e->RobustInfo(drho, rinfo);
+                for (int a = 0; a < d; ++a) {
+                    for (int c = 0; c < n; ++c) J[(size_t)(row + a) * n + c] = 0.0;
+                    for (int c = 0; c < d; ++c) { W[(size_t)(row + a) * dmax + c] = rinfo(a, c); Wb[(size_t)(row + a) * dmax + c] = drho * info(a, c); }
+                }
+                for (size_t vi = 0; vi < vs.size(); ++vi) {
+                    if (vs[vi]->IsFixed()) continue;
+                    const int o = off.at(vs[vi]->Id()), ld = vs[vi]->LocalDimension();
+                    for (int a = 0; a < d; ++a)
+                        for (int c = 0; c < ld; ++c) J[(size_t)(row + a) * n + o + c] += jacs[vi](a, c);
+                }
+            }
+            row += d;
+        }
+    };
+    auto chi2_now = [&](double &out) -> bool {
+        if (user_loss) { std::cerr << "vio_b200: user-defined loss functions are not supported" << std::endl; return false; }
+        int rc = vio_dense_chi2(handle_, R, dmax, r.data(), e0.data(), dim.data(), Om.data(), kind.data(), delta.data(), &out);
+        if (rc != VIO_OK) { std::cerr << "vio_b200: " << vio_last_error(handle_) << std::endl; return false; }
+        if (v17_) out *= 0.5;
+        return true;
+    };
+    double hess_ms = 0, maxdiag = 0;
+    auto make_hessian = [&]() -> bool {
+        const auto th = std::chrono::steady_clock::now();
+        evaluate(true);
+        vio_dense_system sys;
+        std::memset(&sys, 0, sizeof(sys));
+        sys.n = n; sys.rows = R; sys.dmax = dmax; sys.J = J.data(); sys.r = r.data(); sys.row_edge0 = e0.data();
+        sys.row_dim = dim.data(); sys.W = W.data(); sys.Wb = Wb.data();
+        int rc = vio_dense_accumulate(handle_, &sys, &maxdiag);
+        hess_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th).count();
+        if (rc != VIO_OK) { std::cerr << "vio_b200: " << vio_last_error(handle_) << std::endl; return false; }
+        return true;
+    };
+    if (!make_hessian()) return false;
+    double chi = 0;
+    if (!chi2_now(chi)) return false;
+    if (v17_) maxdiag = std::min(5e10, maxdiag);
+    double lambda = 1e-5 * maxdiag, ni = 2.0, last_chi = 1e20;
+    const double stop_thr = 1e-6 * chi;
+    bool stop = false;
+    int iter = 0;
+    std::vector<double> dx(n);
+    while (!stop && iter < iterations) {
+        std::cout << "iter: " << iter << " , chi= " << chi << " , Lambda= " << lambda << std::endl;
+        bool ok = false;
+        int false_cnt = 0;
+        while (!ok && (!v17_ || false_cnt < 10)) {
+            double dot = 0, dx2 = 0;
+            int rc = vio_dense_solve(handle_, lambda, dx.data(), &dot, &dx2);
+            if (rc != VIO_OK) { std::cerr << "vio_b200: " << vio_last_error(handle_) << std::endl; return false; }
+            if (!v17_ && (dx2 <= 1e-6 || false_cnt > 10)) { stop = true; break; }
+            for (auto &v : verts) {
+                v->BackUpParameters();
+                VecX d = Eigen::Map<VecX>(dx.data() + v->OrderingId(), v->LocalDimension());
+                v->Plus(d);
+            }
+            const double scale = v17_ ? 0.5 * dot + 1e-6 : dot + 1e-3;
+            evaluate(false);
+            double temp = 0;
+            if (!chi2_now(temp)) return false;
+            const double rho = (chi - temp) / scale;
+            if (rho > 0 && std::isfinite(temp)) {
+                double alpha = 1. - std::pow(2 * rho - 1, 3);
+                alpha = std::min(alpha, 2. / 3.);
+                lambda *= std::max(1. / 3., alpha);
+                ni = 2; chi = temp; ok = true;
+            } else { lambda *= ni; ni *= 2; ok = false; }
+            if (ok) { if (!make_hessian()) return false; false_cnt = 0; }
+            else {
+                false_cnt++;
+                for (auto &v : verts) {
+                    if (v17_) v->RollBackParameters();
+                    else { VecX d = Eigen::Map<VecX>(dx.data() + v->OrderingId(), v->LocalDimension()); v->Plus(-d); }
+                }
+            }
+        }
+        iter++;
+        if (v17_) { if (last_chi - chi < 1e-5) { std::cout << "sqrt(currentChi_) <= stopThresholdLM_" << std::endl; stop = true; } }
+        else if (std::sqrt(chi) <= stop_thr) stop = true;
+        last_chi = chi;
+    }
+    last_hessian_ms_ = hess_ms;
     last_solve_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     std::cout << "problem solve cost: " << last_solve_ms_ << " ms" << std::endl;
     std::cout << "   makeHessian cost: " << last_hessian_ms_ << " ms" << std::endl;
