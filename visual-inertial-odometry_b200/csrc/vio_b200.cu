@@ -452,8 +452,13 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         int rc = p->allreduce(p->scal.p + 4, 2, (void *)p->stream, p->allreduce_user);
         if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
     }
-    k_pose_scale<<<1, 256, 0, p->stream>>>(v, lambda, p->scal.p + 6, p->scal.p + 7);
-    p->launches++;
+    {
+        const int g = grid_for(p->P, 256, 64);
+        k_pose_scale<<<g, 256, 0, p->stream>>>(v, lambda, p->partial.p + 1024, p->partial2.p + 1024);
+        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p + 1024, g, p->scal.p + 6, 0);
+        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p + 1024, g, p->scal.p + 7, 0);
+        p->launches += 3;
+    }
     CK(cudaGetLastError());
     return VIO_OK;
 }

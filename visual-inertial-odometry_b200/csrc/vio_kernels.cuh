@@ -611,22 +611,15 @@ __global__ void __launch_bounds__(256) k_backsub(DevView v, double lambda, doubl
     block_sum_to(n2, partial_n2);
 }
 
-__global__ void k_pose_scale(DevView v, double lambda, double *out_scale, double *out_n2) {
-    // P is small relative to M; single block, fixed order
-    __shared__ double s1[256], s2[256];
+__global__ void __launch_bounds__(256) k_pose_scale(DevView v, double lambda, double *partial_scale, double *partial_n2) {
     double sc = 0.0, n2 = 0.0;
-    for (int i = threadIdx.x; i < v.P; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.P; i += gridDim.x * blockDim.x) {
         const double d = v.dxp[i];
         sc += d * (lambda * d + v.bp[i]);
         n2 += d * d;
     }
-    s1[threadIdx.x] = sc; s2[threadIdx.x] = n2;
-    __syncthreads();
-    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
-        if (threadIdx.x < s) { s1[threadIdx.x] += s1[threadIdx.x + s]; s2[threadIdx.x] += s2[threadIdx.x + s]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { *out_scale = s1[0]; *out_n2 = s2[0]; }
+    block_sum_to(sc, partial_scale);
+    block_sum_to(n2, partial_n2);
 }
 
 // UpdateStates: backup + Plus.  sign = +1 (update) ; v15 rollback calls it again with sign = -1, no backup.
