@@ -217,6 +217,22 @@ int vio_get_kernel_ms(vio_problem *p, double *ms_linearize_kernel, int64_t *laun
 /* total number of kernel launches issued by this handle since creation                      */
 int64_t vio_launch_count(const vio_problem *p);
 
+/* ---- batched solve: many independent small problems (BASELINE config 3: 4096 sliding windows) ----------------------
+ * n_workers host threads, each with its own handle + CUDA stream, pull items from a shared queue: pack -> H2D ->
+ * Solve(iterations) -> D2H.  Kernels of different problems overlap on the device.  Results are bitwise those of
+ * vio_set_graph + vio_set_prior + vio_solve + vio_get_vertices on one handle.                                     */
+typedef struct vio_batch_item {
+    const vio_graph *graph;
+    int32_t prior_dim, err_dim;                  /* 0 = no prior                                               */
+    const double *H_prior, *b_prior, *err_prior, *Jt_prior_inv;
+    double *pose_out, *speedbias_out, *inv_depth_out; /* sized like the graph's arrays; may be NULL            */
+    vio_stats *stats;                            /* may be NULL                                                */
+    int32_t rc;                                  /* out: VIO_OK or the error of this item                      */
+    int32_t reserved;
+} vio_batch_item;
+int vio_solve_batched(int device, int32_t n_workers, vio_batch_item *items, int64_t n_items, int32_t iterations,
+                      const vio_lm_opts *opts);
+
 /* ---- GENERIC_PROBLEM lane: user-defined host edges --------------------------------------------------------------
  * Problem(GENERIC_PROBLEM) lets callers subclass Vertex/Edge with their own virtual ComputeResidual /
  * ComputeJacobians / Plus (A15/app/CurveFitting.cpp:14-48, A17/test/CurveFitting.cpp:8-45).  Those virtuals are host

@@ -1,0 +1,53 @@
+"""BASELINE config 3 measurement (run on a GPU box): N perturbed copies of the config-2 window through
+vio_solve_batched; prints one JSON line with problems/s and summed edges/s, and the CPU oracle's rate beside it.
+
+    python tests/bench_batched.py --n 4096 --workers 16
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--workers", type=int, default=16)
+    ap.add_argument("--cpu-n", type=int, default=4)
+    args = ap.parse_args()
+    vio = importlib.import_module("visual-inertial-odometry_b200")
+    from tests import oraclelib as orc
+    base = vio.Scene.from_dict(dict(np.load(os.path.join(ROOT, "tests", "golden", "window_v17_scene.npz"))))
+    rng = np.random.default_rng(3)
+    distinct = []
+    for k in range(min(args.n, 64)):
+        s = vio.Scene.from_dict(base.export())
+        s.pose[1:, :3] += rng.normal(0, 0.01, (s.pose.shape[0] - 1, 3))
+        s.inv_depth *= 1.0 + rng.normal(0, 0.02, s.inv_depth.shape[0])
+        distinct.append(s)
+    scenes = [distinct[i % len(distinct)] for i in range(args.n)]
+    opts = vio.make_opts(flavour=vio.capi.LM_V17)
+    vio.capi.solve_batched(scenes[:args.workers], 10, opts, n_workers=args.workers)  # warm-up (contexts, allocations)
+    outs, dt = vio.capi.solve_batched(scenes, 10, opts, n_workers=args.workers)
+    E = int(base.rp_landmark.shape[0])
+    iters = sum(o["stats"].iterations for o in outs)
+    t0 = time.perf_counter()
+    for s in distinct[:args.cpu_n]:
+        orc.solve(s, 10, opts)
+    t_cpu = (time.perf_counter() - t0) / args.cpu_n
+    print(json.dumps({"metric": "batched_windows_per_sec", "value": args.n / dt, "unit": "problems/s", "n_problems": args.n,
+                      "workers": args.workers, "wall_s": dt, "lm_iterations_total": iters,
+                      "edges_per_sec": E * iters / dt, "edges_per_problem": E, "P": base.P,
+                      "cpu_oracle_port_problems_per_sec_1core": 1.0 / t_cpu,
+                      "note": "each problem: pack + H2D + Solve(10) + D2H through vio_solve_batched"}))
+
+
+if __name__ == "__main__":
+    main()

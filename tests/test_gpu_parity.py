@@ -286,3 +286,32 @@ def test_grouped_kernel_matches_generic_kernel(vio, scene_name):
     if a[4] is not None:
         assert rel_max(g[4], a[4]) <= 1e-12
         assert rel_l2(g[5], a[5]) <= 1e-12
+
+
+def test_batched_windows_match_single_solves(vio):
+    """BASELINE config 3 (batched sliding windows) at test size: vio_solve_batched over perturbed copies of the config-2
+    window gives, per problem, exactly what a single-handle solve gives, and agrees with the CPU oracle."""
+    from tests import oraclelib as orc
+    base = _window(vio)
+    rng = np.random.default_rng(5)
+    scenes = []
+    for k in range(6):
+        s = vio.Scene.from_dict(base.export())
+        s.pose[1:, :3] += rng.normal(0, 0.01, (s.pose.shape[0] - 1, 3))
+        s.inv_depth *= 1.0 + rng.normal(0, 0.02, s.inv_depth.shape[0])
+        scenes.append(s)
+    opts = vio.make_opts(flavour=vio.capi.LM_V17)
+    outs, dt = vio.capi.solve_batched(scenes, 10, opts, n_workers=3)
+    for s, o in zip(scenes[:3], outs[:3]):
+        p = vio.Problem()
+        p.set_graph(s)
+        st = p.solve(10, opts)
+        pose, sb, invd = p.get_vertices()
+        assert o["stats"].iterations == st.iterations
+        assert abs(o["stats"].chi2_final - st.chi2_final) <= 1e-9 * st.chi2_final
+        assert rel_max(o["pose"], pose) <= 1e-9 and rel_max(o["inv_depth"], invd) <= 1e-9
+    ref = orc.solve(scenes[5], 10, opts)
+    assert outs[5]["stats"].iterations == ref["iterations"]
+    assert abs(outs[5]["stats"].chi2_final - ref["chi2_final"]) <= FINAL_TOL * ref["chi2_final"]
+    assert rel_max(outs[5]["pose"], ref["pose"]) <= FINAL_TOL
+    assert rel_max(outs[5]["speedbias"], ref["speedbias"]) <= FINAL_TOL

@@ -69,6 +69,15 @@ class VioDims(C.Structure):
     ]
 
 
+class VioBatchItem(C.Structure):
+    _fields_ = [
+        ("graph", C.POINTER(VioGraph)), ("prior_dim", C.c_int32), ("err_dim", C.c_int32),
+        ("H_prior", _dp), ("b_prior", _dp), ("err_prior", _dp), ("Jt_prior_inv", _dp),
+        ("pose_out", _dp), ("speedbias_out", _dp), ("inv_depth_out", _dp),
+        ("stats", C.POINTER(VioStats)), ("rc", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 
 # every symbol include/vio_b200.h declares (tests check the library exports all of them)
@@ -78,7 +87,7 @@ EXPORTS = [
     "vio_solve", "vio_linearize", "vio_chi2", "vio_solve_step", "vio_apply_step", "vio_rollback_step",
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
     "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
-    "vio_dense_solve", "vio_dense_get",
+    "vio_dense_solve", "vio_dense_get", "vio_solve_batched",
 ]
 
 _lib = None
@@ -452,6 +461,50 @@ class Problem:
 
     def launch_count(self):
         return int(self._L.vio_launch_count(self._h))
+
+
+def solve_batched(scenes, iterations, opts=None, device=0, n_workers=16):
+    """BASELINE config 3: many independent problems through vio_solve_batched.
+
+    Returns (list of dicts with pose / speedbias / inv_depth / stats per scene, wall seconds of the call)."""
+    import time
+    n = len(scenes)
+    items = (VioBatchItem * n)()
+    keep, outs = [], []
+    for i, s in enumerate(scenes):
+        g, k = s.to_c()
+        gp = C.pointer(g)
+        st = VioStats()
+        pose = np.zeros_like(s.pose)
+        sb = np.zeros_like(s.speedbias)
+        invd = np.array(s.inv_depth, copy=True)
+        it = items[i]
+        it.graph = gp
+        if s.prior is not None:
+            H = np.ascontiguousarray(s.prior["H"], np.float64)
+            b = np.ascontiguousarray(s.prior["b"], np.float64)
+            it.prior_dim, it.H_prior, it.b_prior = b.shape[0], _d(H), _d(b)
+            keep += [H, b]
+            err = s.prior.get("err")
+            if err is not None and len(err):
+                err = np.ascontiguousarray(err, np.float64)
+                jt = np.ascontiguousarray(s.prior["jt_inv"], np.float64)
+                it.err_dim, it.err_prior, it.Jt_prior_inv = err.shape[0], _d(err), _d(jt)
+                keep += [err, jt]
+        it.pose_out = _d(pose)
+        it.speedbias_out = _d(sb) if sb.size else None
+        it.inv_depth_out = _d(invd) if invd.size else None
+        it.stats = C.pointer(st)
+        keep += [g, gp, k, s]
+        outs.append(dict(pose=pose, speedbias=sb, inv_depth=invd, stats=st))
+    L = lib()
+    L.vio_solve_batched.argtypes = [C.c_int, C.c_int32, C.POINTER(VioBatchItem), C.c_int64, C.c_int32, C.POINTER(VioLmOpts)]
+    t0 = time.perf_counter()
+    rc = L.vio_solve_batched(device, n_workers, items, n, iterations, C.byref(opts) if opts is not None else None)
+    dt = time.perf_counter() - t0
+    if rc != VIO_OK:
+        raise VioError(rc, "vio_solve_batched: item errors " + str([items[i].rc for i in range(n) if items[i].rc][:5]))
+    return outs, dt
 
 
 def measure_fp64_peak(device=0):

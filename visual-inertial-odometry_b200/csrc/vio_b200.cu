@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -553,7 +555,7 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
         p->coop_ok = coop != 0;
         if (sms > 0) p->num_sms = sms;
     }
-    p->ev_lin.resize(VIO_TRACE_MAX + 8);
+    p->ev_lin.resize(48);  // linearise-kernel timing events (first 48 linearisations of a solve are timed)
     for (auto &e : p->ev_lin) {
         cudaEventCreate(&e.a);
         cudaEventCreate(&e.b);
@@ -1076,6 +1078,43 @@ int vio_get_hessian(vio_problem *p, const vio_lm_opts *opts, double *H, double *
         for (int l = 0; l < M; ++l) b[P + p->lm_global[l]] = bl[l];
     }
     return VIO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// batched solve (config 3)
+// -------------------------------------------------------------------------------------------------
+int vio_solve_batched(int device, int32_t n_workers, vio_batch_item *items, int64_t n_items, int32_t iterations,
+                      const vio_lm_opts *opts) {
+    if (!items || n_items < 0) return VIO_ERR_INVALID;
+    if (n_items == 0) return VIO_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return VIO_ERR_NO_DEVICE;
+    if (n_workers <= 0) n_workers = 16;
+    if ((int64_t)n_workers > n_items) n_workers = (int32_t)n_items;
+    std::atomic<int64_t> next(0);
+    std::atomic<int> first_err(VIO_OK);
+    auto worker = [&]() {
+        vio_problem *h = nullptr;
+        int rc = vio_create(device, nullptr, &h);
+        if (rc != VIO_OK) { first_err.store(rc); return; }
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n_items) break;
+            vio_batch_item &it = items[i];
+            rc = it.graph ? vio_set_graph(h, it.graph) : VIO_ERR_INVALID;
+            if (rc == VIO_OK && it.prior_dim > 0)
+                rc = vio_set_prior(h, it.prior_dim, it.H_prior, it.b_prior, it.err_dim, it.err_prior, it.Jt_prior_inv);
+            if (rc == VIO_OK) rc = vio_solve(h, iterations, opts, it.stats);
+            if (rc == VIO_OK) rc = vio_get_vertices(h, it.pose_out, it.speedbias_out, it.inv_depth_out);
+            it.rc = rc;
+            if (rc != VIO_OK) { int exp = VIO_OK; first_err.compare_exchange_strong(exp, rc); }
+        }
+        vio_destroy(h);
+    };
+    std::vector<std::thread> pool;
+    for (int w = 0; w < n_workers; ++w) pool.emplace_back(worker);
+    for (auto &t : pool) t.join();
+    return first_err.load();
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -6,17 +6,25 @@
 template <typename T>
 struct DBuf {  // device buffer
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0;    // logical element count
+    size_t cap = 0;  // allocated element count: a handle that is re-used for many graphs (vio_solve_batched) only
+                     // re-allocates when a buffer has to grow
     cudaError_t alloc(size_t count) {
-        release();
         n = count;
-        if (count == 0) return cudaSuccess;
-        return cudaMalloc((void **)&p, count * sizeof(T));
+        if (count <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = count + count / 4 + 16;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want; else n = 0;
+        return e;
     }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
+        cap = 0;
     }
     DBuf() = default;
     DBuf(const DBuf &) = delete;
