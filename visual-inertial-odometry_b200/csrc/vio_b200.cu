@@ -931,9 +931,9 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
         double tot = 0;
         for (int k = 0; k < 7; ++k) tot += (double)hp[k];
         fprintf(stderr, "[vio_b200 profile] linearise phases (share of CTA cycles): setup %.1f%% host-chain %.1f%% edges %.1f%% "
-                        "landmark-sums %.1f%% assemble %.1f%% schur %.1f%% flush %.1f%%  (total %.3g cycles)\n",
+                        "landmark-sums %.1f%% assemble %.1f%% schur %.1f%% flush %.1f%%  (total %.3g cycles, %.3g ns => %.0f MHz)\n",
                 100 * hp[0] / tot, 100 * hp[1] / tot, 100 * hp[2] / tot, 100 * hp[3] / tot, 100 * hp[4] / tot, 100 * hp[5] / tot,
-                100 * hp[6] / tot, tot);
+                100 * hp[6] / tot, tot, (double)hp[7], 1e3 * tot / std::max(1.0, (double)hp[7]));
         cudaMemset(p->prof.p, 0, sizeof(hp));
     }
     st->iterations = iter;

@@ -49,7 +49,7 @@ __host__ __device__ inline size_t group_smem_doubles(int ns, int nlm) {
     const int npairs = ns * (ns + 1) / 2;
     // pc[ns][12] lmh[nlm][16] w[nlm][ns][6] lmM[nlm][ns-1][9] hinv[nlm] blv[nlm] red[ns][48] T[npairs][36] bvec[ns][18]
     return (size_t)ns * 12 + (size_t)nlm * 16 + (size_t)nlm * ns * 6 + (size_t)nlm * (ns - 1) * 9 + 2 * (size_t)nlm +
-           (size_t)ns * 48 + (size_t)npairs * 36 + (size_t)ns * 18 + (size_t)ns * 9;
+           (size_t)ns * 48 + (size_t)npairs * 36 + (size_t)ns * 18 + (size_t)ns * 9 + (size_t)npairs;
 }
 __host__ __device__ inline size_t group_smem_bytes(int ns, int nlm) {
     const int npairs = ns * (ns + 1) / 2;
@@ -113,13 +113,16 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
     double *T = red + (size_t)ns * 48;                // [npairs][36]
     double *bvec = T + (size_t)npairs * 36;           // [ns][18]  bp(6) bcorr(6) hdiag(6)
     double *rjric = bvec + (size_t)ns * 18;           // [ns][9]   Rj * Ric per slot (shared by all edges of the slot)
-    int *pose_id = (int *)(rjric + (size_t)ns * 9);   // [ns]
+    long long *pinfo_s = (long long *)(rjric + (size_t)ns * 9);  // [npairs] staged pair table
+    int *pose_id = (int *)(pinfo_s + npairs);         // [ns]
     int *pfix = pose_id + ns;
     int *poff = pfix + ns;
     int *pair_a = poff + ns;                          // [npairs]
     int *pair_b = pair_a + npairs;
 
     long long prof_t_ = gv.prof ? clock64() : 0;
+    unsigned long long prof_ns0_ = 0;
+    if (gv.prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ns0_));
     // ---- phase 0: slot table, pose cache, zero fills ---------------------------------------------------------
     for (int s = tid; s < ns; s += nt) {
         const int pid = s == 0 ? h.host : gv.slot_pose[h.slot0 + s];
@@ -322,28 +325,11 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
     __syncthreads();
     VIO_PROF_MARK(3);
 
-    // ---- phase 1.9: assemble the direct (J^T W J) part of the group tile from the reduced vectors -------------
-    for (int idx = tid; idx < npairs * 36; idx += nt) {
-        const int p = idx / 36, k = idx % 36, r = k / 6, c = k % 6;
-        const int a = pair_a[p], b = pair_b[p];
-        double val = 0.0;
-        if (a == 0 && b == 0) {
-            val = red[sym6_index(r, c)];
-        } else if (a == 0) {
-            const double *R = red + 48 * (size_t)b;  // (0,s) = [[-A1, A2],[-A3, A4]]
-            if (r < 3 && c < 3) val = -R[sym3_index(r, c)];
-            else if (r < 3) val = R[6 + 3 * r + (c - 3)];
-            else if (c < 3) val = -R[15 + 3 * (r - 3) + c];
-            else val = R[24 + 3 * (r - 3) + (c - 3)];
-        } else if (a == b) {
-            const double *R = red + 48 * (size_t)a;  // (s,s) = [[A1, -A2],[-A2^T, A5]]
-            if (r < 3 && c < 3) val = R[sym3_index(r, c)];
-            else if (r < 3) val = -R[6 + 3 * r + (c - 3)];
-            else if (c < 3) val = -R[6 + 3 * c + (r - 3)];
-            else val = R[33 + sym3_index(r - 3, c - 3)];
-        }
-        T[idx] = val;
-    }
+    // ---- phase 1.9: the direct (J^T W J) part of the group tile is read straight from the reduced vectors by the flush
+    // (direct_value below); T only receives the Schur part.  Stage the pair table while we are at it.
+    for (int p = tid; p < npairs; p += nt) pinfo_s[p] = gv.pairinfo[h.pair0 + p];
+    if (!WITH_SCHUR)
+        for (int idx = tid; idx < npairs * 36; idx += nt) T[idx] = 0.0;
     for (int idx = tid; idx < ns * 6; idx += nt) {
         const int s = idx / 6, k = idx % 6;
         double bp, hd;
@@ -378,13 +364,18 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
 #pragma unroll
                 for (int k = 0; k < 36; ++k) acc[k] = 0.0;
                 const int a = pair_a[p], b = pair_b[p];
-                for (int l = q; l < nlm; l += nsub) {
+                const int lstride = ns * 6;
+                const double *wa = w + (size_t)q * lstride + a * 6;
+                const double *wb = w + (size_t)q * lstride + b * 6;
+                for (int l = q; l < nlm; l += nsub, wa += (size_t)nsub * lstride, wb += (size_t)nsub * lstride) {
                     const double inv = hinv[l];
-                    const double *wa = w + ((size_t)l * ns + a) * 6;
-                    const double *wb = w + ((size_t)l * ns + b) * 6;
-                    double x[6], y[6];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) { x[k] = wa[k] * inv; y[k] = wb[k]; }
+                    // rows of w are 48 B: three 16-byte shared loads each
+                    const double2 a0 = *reinterpret_cast<const double2 *>(wa), a1 = *reinterpret_cast<const double2 *>(wa + 2),
+                                  a2 = *reinterpret_cast<const double2 *>(wa + 4);
+                    const double2 b0 = *reinterpret_cast<const double2 *>(wb), b1 = *reinterpret_cast<const double2 *>(wb + 2),
+                                  b2 = *reinterpret_cast<const double2 *>(wb + 4);
+                    const double x[6] = {a0.x * inv, a0.y * inv, a1.x * inv, a1.y * inv, a2.x * inv, a2.y * inv};
+                    const double y[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
 #pragma unroll
                     for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -393,7 +384,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
                 if (q == 0) {
                     double *t = T + 36 * (size_t)p;
 #pragma unroll
-                    for (int k = 0; k < 36; ++k) t[k] -= acc[k];
+                    for (int k = 0; k < 36; ++k) t[k] = -acc[k];
                 } else {
                     double *t = lmM + ((size_t)(q - 1) * npairs + p) * 36;
 #pragma unroll
@@ -413,14 +404,32 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
     VIO_PROF_MARK(5);
     // ---- flush: one RED.F64 per touched element of the reduced system -------------------------------------------
     for (int idx = tid; idx < npairs * 36; idx += nt) {
-        const int p = idx / 36, k = idx % 36, r = k / 6, c = k % 6;
-        const long long info = gv.pairinfo[h.pair0 + p];
+        const int p = idx / 36, k = idx - 36 * p, r = k / 6, c = k - 6 * r;
+        const long long info = pinfo_s[p];
         const int flags = (int)(info & 3);
         if (flags == 3) continue;
         if (flags == 2 && r > c) continue;
         const size_t off = (size_t)(info >> 2);
         const size_t e = flags == 1 ? (size_t)c * gv.ld + r : (size_t)r * gv.ld + c;
         double val = T[idx];
+        {
+            const int a = pair_a[p], b = pair_b[p];
+            if (a == 0 && b == 0) {
+                val += red[sym6_index(r, c)];
+            } else if (a == 0) {
+                const double *R = red + 48 * (size_t)b;  // (0,s) = [[-A1, A2],[-A3, A4]]
+                if (r < 3 && c < 3) val -= R[sym3_index(r, c)];
+                else if (r < 3) val += R[6 + 3 * r + (c - 3)];
+                else if (c < 3) val -= R[15 + 3 * (r - 3) + c];
+                else val += R[24 + 3 * (r - 3) + (c - 3)];
+            } else if (a == b) {
+                const double *R = red + 48 * (size_t)a;  // (s,s) = [[A1, -A2],[-A2^T, A5]]
+                if (r < 3 && c < 3) val += R[sym3_index(r, c)];
+                else if (r < 3) val -= R[6 + 3 * r + (c - 3)];
+                else if (c < 3) val -= R[6 + 3 * c + (r - 3)];
+                else val += R[33 + sym3_index(r - 3, c - 3)];
+            }
+        }
         if (WITH_SCHUR)
             for (int q = 1; q < nsub; ++q) val -= lmM[((size_t)(q - 1) * npairs + p) * 36 + k];
         if (val != 0.0) atomicAdd(v.S + off + e, val);
@@ -434,4 +443,9 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
     }
     __syncthreads();
     VIO_PROF_MARK(6);
+    if (gv.prof && threadIdx.x == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        atomicAdd(gv.prof + 7, ns1 - prof_ns0_);
+    }
 }

@@ -207,12 +207,12 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     {
         const int NS_MAX = 22;
         const size_t SMEM_BUDGET = 200 * 1024;
-        int target_lm = 50;  // landmarks per CTA (VIO_B200_GROUP_LM overrides; tuning knob)
+        int target_lm = 100;  // landmarks per CTA (VIO_B200_GROUP_LM overrides; tuning knob; 100 x 10 warps measured best)
         if (const char *ev = getenv("VIO_B200_GROUP_LM")) target_lm = std::max(1, atoi(ev));
         auto smem_bytes = [](int ns, int nlm) -> size_t {
             const size_t npairs = (size_t)ns * (ns + 1) / 2;
             const size_t dbl = (size_t)ns * 12 + (size_t)nlm * 16 + (size_t)nlm * ns * 6 + (size_t)nlm * (ns - 1) * 9 +
-                               2 * (size_t)nlm + (size_t)ns * 48 + npairs * 36 + (size_t)ns * 18 + (size_t)ns * 9;
+                               2 * (size_t)nlm + (size_t)ns * 48 + npairs * 36 + (size_t)ns * 18 + (size_t)ns * 9 + npairs;
             return dbl * 8 + (3 * (size_t)ns + 2 * npairs) * 4;
         };
         auto block_off = [&](int pa, int pb, long long &off) -> bool {  // element offset of block (pa,pb) in S storage
@@ -260,8 +260,7 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
             }
             for (int p2 : slots) slot_of_pose[p2] = -1;
             if (!K.grouped_ok) break;
-            // split the feasible run [l0, l1) evenly into chunks of about `target` landmarks: smaller CTAs leave room
-            // for two resident CTAs per SM (shared memory and registers), which hides barrier and memory latency
+            // split the feasible run [l0, l1) evenly into chunks of about `target_lm` landmarks
             const int nrun = l1 - l0;
             const int nchunk = (nrun + target_lm - 1) / target_lm;
             for (int ch = 0; ch < nchunk && K.grouped_ok; ++ch) {
@@ -309,8 +308,9 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
             l0 = l1;
         }
         if (K.n_groups == 0) K.grouped_ok = false;
-        // two observer slots per warp, 4..10 warps (VIO_B200_GROUP_WARPS overrides; tuning knob)
-        int nwarp = (max_obs_slots + 1) / 2;
+        // one observer slot per warp, 4..10 warps (VIO_B200_GROUP_WARPS overrides; tuning knob)
+        const int rounds = (max_obs_slots + 9) / 10;
+        int nwarp = rounds > 0 ? (max_obs_slots + rounds - 1) / rounds : 4;
         if (nwarp < 4) nwarp = 4;
         if (nwarp > 10) nwarp = 10;
         if (const char *ev = getenv("VIO_B200_GROUP_WARPS")) nwarp = std::min(10, std::max(1, atoi(ev)));
