@@ -47,8 +47,9 @@ struct GroupView {
 
 __host__ __device__ inline size_t group_smem_doubles(int ns, int nlm) {
     const int npairs = ns * (ns + 1) / 2;
-    // pc[ns][12] lmh[nlm][16] w[nlm][ns][6] lmM[nlm][ns-1][9] hinv[nlm] blv[nlm] red[ns][48] T[npairs][36] bvec[ns][18]
-    return (size_t)ns * 12 + (size_t)nlm * 16 + (size_t)nlm * ns * 6 + (size_t)nlm * (ns - 1) * 9 + 2 * (size_t)nlm +
+    // pc[ns][12] lmh[nlm][17] w[nlm][ns][6] lmM[nlm][LMS] hinv[nlm] blv[nlm] red[ns][48] T[npairs][36] bvec[ns][18]
+    // (lmh and lmM use ODD per-landmark strides so that lane = landmark accesses are bank-conflict free)
+    return (size_t)ns * 12 + (size_t)nlm * 17 + 1 + (size_t)nlm * ns * 6 + (size_t)nlm * (((ns - 1) * 9) | 1) + 2 * (size_t)nlm + 1 +
            (size_t)ns * 48 + (size_t)npairs * 36 + (size_t)ns * 18 + (size_t)ns * 9 + (size_t)npairs;
 }
 __host__ __device__ inline size_t group_smem_bytes(int ns, int nlm) {
@@ -104,12 +105,14 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
     const int ns = h.ns, nlm = h.nlm, npairs = ns * (ns + 1) / 2;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     double *pc = sm;                                  // [ns][12]
-    double *lmh = pc + (size_t)ns * 12;               // [nlm][16]  pw(3) g(3) G(9) lam-unused
-    double *w = lmh + (size_t)nlm * 16;               // [nlm][ns][6]
-    double *lmM = w + (size_t)nlm * ns * 6;           // [nlm][ns-1][9]
-    double *hinv = lmM + (size_t)nlm * (ns - 1) * 9;  // [nlm]
+    constexpr int LHS = 17;                           // odd strides: lane = landmark accesses hit 32 distinct banks
+    const int LMS = ((ns - 1) * 9) | 1;
+    double *lmh = pc + (size_t)ns * 12;               // [nlm][17]  pw(3) g(3) G(9)
+    double *w = lmh + (((size_t)nlm * LHS + 1) & ~(size_t)1);  // [nlm][ns][6]  (16-byte aligned for double2 loads)
+    double *lmM = w + (size_t)nlm * ns * 6;           // [nlm][LMS]  per (landmark, slot): M(6) m(3)
+    double *hinv = lmM + (size_t)nlm * LMS;           // [nlm]
     double *blv = hinv + nlm;                         // [nlm]
-    double *red = blv + nlm;                          // [ns][48]
+    double *red = blv + nlm + ((nlm * (LMS + 2)) & 1);  // [ns][48] (kept 16-byte aligned)
     double *T = red + (size_t)ns * 48;                // [npairs][36]
     double *bvec = T + (size_t)npairs * 36;           // [ns][18]  bp(6) bcorr(6) hdiag(6)
     double *rjric = bvec + (size_t)ns * 18;           // [ns][9]   Rj * Ric per slot (shared by all edges of the slot)
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
     }
     if (!h.pad) {  // pad = 1: every landmark of the group is observed from every slot -> all entries get written
         for (size_t i = tid; i < (size_t)nlm * ns * 6; i += nt) w[i] = 0.0;
-        for (size_t i = tid; i < (size_t)nlm * (ns - 1) * 9; i += nt) lmM[i] = 0.0;
+        for (size_t i = tid; i < (size_t)nlm * LMS; i += nt) lmM[i] = 0.0;
     }
     for (int i = tid; i < ns * 48; i += nt) red[i] = 0.0;
     __syncthreads();
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         mat3_mul_vec(pc, tmp, g);
         const double il2 = -1.0 / (lam * lam);
         mat3_mul_hat(pc, pbi, G);
-        double *o = lmh + 16 * (size_t)l;
+        double *o = lmh + LHS * (size_t)l;
         o[0] = pw[0]; o[1] = pw[1]; o[2] = pw[2];
         o[3] = g[0] * il2; o[4] = g[1] * il2; o[5] = g[2] * il2;
 #pragma unroll
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
             const int edge = n_edge;
             if (l + 32 < nlm) { n_pjx = gv.ell_pjx[ebase + l + 32]; n_pjy = gv.ell_pjy[ebase + l + 32]; n_edge = gv.ell_edge[ebase + l + 32]; }
             if (pjx != pjx) continue;  // NaN: this landmark is not observed from slot s
-            const double *lh = lmh + 16 * (size_t)l;
+            const double *lh = lmh + LHS * (size_t)l;
             const double pw[3] = {lh[0], lh[1], lh[2]};
             double pcj[3], pbj[3], r[2];
             reproj_residual(v.Ric, v.tic, RTj, pw, pjx, pjy, pcj, pbj, r);
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
             const double dc = drho * v.rp_info;
             const double m[3] = {dc * (B[0] * r[0] + B[3] * r[1]), dc * (B[1] * r[0] + B[4] * r[1]),
                                  dc * (B[2] * r[0] + B[5] * r[1])};
-            double *lm9 = lmM + ((size_t)l * (ns - 1) + (s - 1)) * 9;
+            double *lm9 = lmM + (size_t)l * LMS + (s - 1) * 9;
             lm9[0] = M[0]; lm9[1] = M[1]; lm9[2] = M[2]; lm9[3] = M[4]; lm9[4] = M[5]; lm9[5] = M[8];
             lm9[6] = m[0]; lm9[7] = m[1]; lm9[8] = m[2];
             double *wog = v.wo + 6 * (size_t)edge;
@@ -275,13 +278,13 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         for (int k = 0; k < 32; ++k) hb[k] = 0.0;
         for (int l = tid; l < nlm; l += nt) {
             double Ms[6] = {0, 0, 0, 0, 0, 0}, ms[3] = {0, 0, 0};
-            const double *q = lmM + (size_t)l * (ns - 1) * 9;
+            const double *q = lmM + (size_t)l * LMS;
             for (int s = 0; s < ns - 1; ++s) {
 #pragma unroll
                 for (int k = 0; k < 6; ++k) Ms[k] += q[9 * s + k];
                 ms[0] += q[9 * s + 6]; ms[1] += q[9 * s + 7]; ms[2] += q[9 * s + 8];
             }
-            const double *lh = lmh + 16 * (size_t)l;
+            const double *lh = lmh + LHS * (size_t)l;
             const double g[3] = {lh[3], lh[4], lh[5]};
             const double *G = lh + 6;
             const double Msf[9] = {Ms[0], Ms[1], Ms[2], Ms[1], Ms[3], Ms[4], Ms[2], Ms[4], Ms[5]};
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         // thread <-> (pair p, landmark subset q).  Lanes of a warp hold DIFFERENT pairs of the SAME subset, so the
         // w_a / w_b reads of a warp hit few distinct shared-memory words (broadcast).  Subset q > 0 parks its
         // partial tile in the (now dead) lmM region; the flush adds the copies up - no barrier rounds, no atomics.
-        nsub = max(1, min(nt / npairs, 1 + (int)(((size_t)nlm * (ns - 1) * 9) / ((size_t)npairs * 36))));
+        nsub = max(1, min(nt / npairs, 1 + (int)(((size_t)nlm * LMS) / ((size_t)npairs * 36))));
         for (int p0 = 0; p0 < npairs; p0 += nt) {  // one pass unless npairs > blockDim
             const int p = p0 + (nsub > 1 ? tid % npairs : tid);
             const int q = nsub > 1 ? tid / npairs : 0;
@@ -367,6 +370,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
                 const int lstride = ns * 6;
                 const double *wa = w + (size_t)q * lstride + a * 6;
                 const double *wb = w + (size_t)q * lstride + b * 6;
+#pragma unroll 2
                 for (int l = q; l < nlm; l += nsub, wa += (size_t)nsub * lstride, wb += (size_t)nsub * lstride) {
                     const double inv = hinv[l];
                     // rows of w are 48 B: three 16-byte shared loads each

@@ -211,8 +211,8 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         if (const char *ev = getenv("VIO_B200_GROUP_LM")) target_lm = std::max(1, atoi(ev));
         auto smem_bytes = [](int ns, int nlm) -> size_t {
             const size_t npairs = (size_t)ns * (ns + 1) / 2;
-            const size_t dbl = (size_t)ns * 12 + (size_t)nlm * 16 + (size_t)nlm * ns * 6 + (size_t)nlm * (ns - 1) * 9 +
-                               2 * (size_t)nlm + (size_t)ns * 48 + npairs * 36 + (size_t)ns * 18 + (size_t)ns * 9 + npairs;
+            const size_t dbl = (size_t)ns * 12 + (size_t)nlm * 17 + 1 + (size_t)nlm * ns * 6 + (size_t)nlm * (((ns - 1) * 9) | 1) +
+                               2 * (size_t)nlm + 1 + (size_t)ns * 48 + npairs * 36 + (size_t)ns * 18 + (size_t)ns * 9 + npairs;
             return dbl * 8 + (3 * (size_t)ns + 2 * npairs) * 4;
         };
         auto block_off = [&](int pa, int pb, long long &off) -> bool {  // element offset of block (pa,pb) in S storage
