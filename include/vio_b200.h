@@ -217,6 +217,16 @@ int vio_get_kernel_ms(vio_problem *p, double *ms_linearize_kernel, int64_t *laun
 /* total number of kernel launches issued by this handle since creation                      */
 int64_t vio_launch_count(const vio_problem *p);
 
+/* ---- Problem::Marginalize(margVertexs = {pose[marg_pose], speedbias[marg_sb]}, pose_dim = P)
+ * (A17/src/backend/problem.cc:617-795) on the handle's current graph, state and prior: edges connected to the frame
+ * are re-linearised (no vertex treated as fixed), their landmarks and then the frame's pose / speed-bias are
+ * eliminated (eigen pseudo-inverse, eps 1e-8), and the new prior of dimension *dim_out = P - 6 - (marg_sb >= 0 ? 9 : 0)
+ * is re-factored into H_prior, b_prior, err_prior, Jt_prior_inv (rows ordered by ascending eigenvalue like Eigen's
+ * SelfAdjointEigenSolver; eigenvector signs are not defined, so Jt_prior_inv / err_prior match the reference up to a
+ * sign per row).  Output arrays may be NULL.                                                                      */
+int vio_marginalize(vio_problem *p, int32_t marg_pose, int32_t marg_sb, int32_t *dim_out, double *H_prior,
+                    double *b_prior, double *err_prior, double *Jt_prior_inv);
+
 /* ---- batched solve: many independent small problems (BASELINE config 3: 4096 sliding windows) ----------------------
  * n_workers host threads, each with its own handle + CUDA stream, pull items from a shared queue: pack -> H2D ->
  * Solve(iterations) -> D2H.  Kernels of different problems overlap on the device.  Results are bitwise those of

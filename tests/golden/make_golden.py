@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 vio = importlib.import_module("visual-inertial-odometry_b200")
 from tests import refshim  # noqa: E402
-from tests.scenes_extra import window_scene  # noqa: E402
+from tests.scenes_extra import marginalize_ref, window_scene  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 capi = vio.capi
@@ -49,7 +49,12 @@ def main():
     sol(15, vio.scenes.monoba(20, 300), 10, "monoba_20x300_v15_solve10.npz")
     sol(15, vio.scenes.monoba(20, 300), 100, "monoba_20x300_v15_solve100.npz")
     sol(17, vio.scenes.monoba(20, 300, with_ext=True), 100, "monoba_20x300_v17_solve.npz")
-    w = window_scene(seed=2)
+    w, wA = window_scene(seed=2, return_marg_window=True)
+    # Problem::Marginalize: window A (frames 0..10, IMU edge 0->1, landmarks hosted in frame 0) -> 156-dim prior
+    np.savez_compressed(os.path.join(OUT, "windowA_v17_scene.npz"), **wA.export())
+    np.savez_compressed(os.path.join(OUT, "windowA_v17_marg.npz"), **marginalize_ref(wA))
+    # second step of the chain: window B WITH its prior, marginalise its oldest frame again
+    np.savez_compressed(os.path.join(OUT, "windowB_v17_marg.npz"), **marginalize_ref(w))
     lin(17, w, "window_v17_lin.npz")
     sol(17, w, 10, "window_v17_solve10.npz")
     np.savez_compressed(os.path.join(OUT, "window_v17_scene.npz"), **w.export())

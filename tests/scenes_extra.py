@@ -159,7 +159,22 @@ def _make_features(n, hosts, lens, frames_gt, rng):
     return feats
 
 
-def window_scene(seed=2, n_feat=1000):
+def marginalize_ref(A, marg_pose=1, marg_sb=0):
+    """Problem::Marginalize of the unmodified v17 backend on scene A -> dict(H, b, err, jt_inv) of dimension P - 15."""
+    Lr = C.CDLL(refshim.os.path.join(refshim.REF_DIR, "libref17.so"))
+    gA, keep = A.to_c()
+    pr0, k2 = refshim._prior(A)
+    P = A.P
+    dim = C.c_int32()
+    Hm, bm, em, jm = np.zeros((P, P)), np.zeros(P), np.zeros(P), np.zeros((P, P))
+    rc = Lr.ref17_marginalize(C.byref(gA), C.byref(pr0), marg_pose, marg_sb, P, C.byref(dim), _d(Hm), _d(bm), _d(em), _d(jm))
+    assert rc == 0, rc
+    n = dim.value
+    return dict(H=Hm.ravel()[:n * n].reshape(n, n).copy(), b=bm[:n].copy(), err=em[:n].copy(),
+                jt_inv=jm.ravel()[:n * n].reshape(n, n).copy())
+
+
+def window_scene(seed=2, n_feat=1000, return_marg_window=False):
     if not refshim.available(17):
         raise RuntimeError("window_scene needs oracle/_ref/libref17.so (IntegrationBase + Marginalize of the reference)")
     rng = np.random.default_rng(seed)
@@ -206,4 +221,6 @@ def window_scene(seed=2, n_feat=1000):
     H = np.zeros((P, P)); H[:n, :n] = Hp
     b = np.zeros(P); b[:n] = bp
     B.prior = dict(H=H, b=b, err=ep.copy(), jt_inv=Jp.copy())
+    if return_marg_window:
+        return B, A
     return B

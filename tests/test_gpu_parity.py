@@ -315,3 +315,30 @@ def test_batched_windows_match_single_solves(vio):
     assert abs(outs[5]["stats"].chi2_final - ref["chi2_final"]) <= FINAL_TOL * ref["chi2_final"]
     assert rel_max(outs[5]["pose"], ref["pose"]) <= FINAL_TOL
     assert rel_max(outs[5]["speedbias"], ref["speedbias"]) <= FINAL_TOL
+
+
+@pytest.mark.parametrize("scene_file,marg_file", [("windowA_v17_scene.npz", "windowA_v17_marg.npz"),
+                                                   ("window_v17_scene.npz", "windowB_v17_marg.npz")])
+def test_marginalize_vs_golden(vio, scene_file, marg_file):
+    """Problem::Marginalize (SURVEY §8f rank 1) against the unmodified v17 backend: the oldest frame's pose + speed-bias
+    and the landmarks it hosts are eliminated into a 156-dim prior.  Eigenvector signs are not defined, so
+    Jt_prior_inv / err_prior are compared through sign-free quantities."""
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    s = vio.Scene.from_dict(dict(np.load(os.path.join(gdir, scene_file))))
+    g = np.load(os.path.join(gdir, marg_file))
+    p = vio.Problem()
+    p.set_graph(s)
+    m = p.marginalize(1, 0)
+    assert m["dim"] == 156
+    assert rel_max(m["H"], g["H"]) <= 1e-8
+    assert rel_l2(m["b"], g["b"]) <= 1e-8
+    assert abs(np.linalg.norm(m["err"]) - np.linalg.norm(g["err"])) <= 1e-7 * np.linalg.norm(g["err"])
+    JJ, JJr = m["jt_inv"].T @ m["jt_inv"], g["jt_inv"].T @ g["jt_inv"]   # = pinv(H_prior), sign/order free
+    assert rel_max(JJ, JJr) <= 1e-6
+    # rows are ordered by ascending eigenvalue like Eigen: |rows| agree wherever the spectrum is not degenerate
+    rn, rnr = np.linalg.norm(m["jt_inv"], axis=1), np.linalg.norm(g["jt_inv"], axis=1)
+    assert np.allclose(rn, rnr, rtol=1e-6, atol=1e-12)
+    assert np.allclose(np.abs(m["err"]), np.abs(g["err"]), rtol=1e-5, atol=1e-7 * np.abs(g["err"]).max())
+    # H_prior is what the next window adds to its Hessian: symmetric, PSD up to rounding
+    assert np.abs(m["H"] - m["H"].T).max() <= 1e-9 * np.abs(m["H"]).max()

@@ -87,7 +87,7 @@ EXPORTS = [
     "vio_solve", "vio_linearize", "vio_chi2", "vio_solve_step", "vio_apply_step", "vio_rollback_step",
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
     "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
-    "vio_dense_solve", "vio_dense_get", "vio_solve_batched",
+    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_marginalize",
 ]
 
 _lib = None
@@ -452,6 +452,20 @@ class Problem:
         bl = np.zeros(d.M)
         self._ck(self._L.vio_get_b(self._h, _d(bp), _d(bl) if d.M else None))
         return bp, bl
+
+    def marginalize(self, marg_pose, marg_sb):
+        d = self.dims()
+        n = d.P
+        H = np.zeros((n, n))
+        b = np.zeros(n)
+        err = np.zeros(n)
+        Jt = np.zeros((n, n))
+        dim = C.c_int32()
+        self._L.vio_marginalize.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _dp, _dp, _dp, _dp]
+        self._ck(self._L.vio_marginalize(self._h, marg_pose, marg_sb, C.byref(dim), _d(H), _d(b), _d(err), _d(Jt)))
+        k = dim.value
+        return dict(dim=k, H=H.ravel()[:k * k].reshape(k, k).copy(), b=b[:k].copy(), err=err[:k].copy(),
+                    jt_inv=Jt.ravel()[:k * k].reshape(k, k).copy())
 
     def kernel_ms(self):
         ms = C.c_double()

@@ -22,6 +22,7 @@
 #include "vio_solvers.cuh"
 #include "vio_imu.cuh"
 #include "vio_grouped.cuh"
+#include "vio_marg.cuh"
 
 #define VIO_VERSION_STR "vio_b200 0.1 (sm_100a)"
 
@@ -54,6 +55,9 @@ struct vio_problem {
     int Lglobal = 0;
     std::vector<int> lm_global;  // local landmark -> caller's landmark index
     std::vector<int> h_pose_off, h_sb_off;
+    // host copies of the (small-graph) structure for Marginalize
+    std::vector<int> h_lm_host, h_lm_eptr, h_e_pose_j, h_imu_pose_i, h_imu_pose_j, h_sp_pose;
+    int h_ext_pose = -1;
 
     // device buffers
     DBuf<double> pose, pose_bak, sb, sb_bak, invdep, invdep_bak, poseRT;
@@ -618,6 +622,12 @@ int vio_set_graph(vio_problem *p, const vio_graph *g) {
     p->Lglobal = K.Lglobal; p->s_count = K.s_count; p->n_se3 = g->n_se3prior; p->n_imu = g->n_imu;
     p->h_pose_off = K.pose_off; p->h_sb_off = K.sb_off; p->h_rowptr = K.rowptr; p->h_col = K.col;
     p->lm_global = K.lm_global;
+    if (E <= (4 << 20)) { p->h_lm_host = K.lm_host; p->h_lm_eptr = K.lm_eptr; p->h_e_pose_j = K.e_pose_j; }
+    else { p->h_lm_host.clear(); p->h_lm_eptr.clear(); p->h_e_pose_j.clear(); }
+    p->h_imu_pose_i.assign(g->imu_pose_i, g->imu_pose_i + (g->n_imu > 0 ? g->n_imu : 0));
+    p->h_imu_pose_j.assign(g->imu_pose_j, g->imu_pose_j + (g->n_imu > 0 ? g->n_imu : 0));
+    p->h_sp_pose.assign(g->sp_pose, g->sp_pose + (g->n_se3prior > 0 ? g->n_se3prior : 0));
+    p->h_ext_pose = g->ext_pose;
     cudaStream_t s = p->stream;
     CK(upload(p->pose, g->pose, 7 * (size_t)C, s)); CK(p->pose_bak.alloc(7 * (size_t)C));
     CK(upload(p->sb, g->speedbias, 9 * (size_t)NSB, s)); CK(p->sb_bak.alloc(9 * (size_t)NSB));
@@ -1077,6 +1087,101 @@ int vio_get_hessian(vio_problem *p, const vio_lm_opts *opts, double *H, double *
         for (int i = 0; i < P; ++i) b[i] = bp[i];
         for (int l = 0; l < M; ++l) b[P + p->lm_global[l]] = bl[l];
     }
+    return VIO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Problem::Marginalize (A17/src/backend/problem.cc:617-795) on the handle's current graph, state and prior
+// -------------------------------------------------------------------------------------------------
+int vio_marginalize(vio_problem *p, int32_t marg_pose, int32_t marg_sb, int32_t *dim_out, double *H_prior, double *b_prior,
+                    double *err_prior, double *Jt_prior_inv) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    if (p->storage != VIO_STORAGE_DENSE || p->shard_world != 1) return fail(p, VIO_ERR_UNSUPPORTED, "Marginalize needs a dense, unsharded window");
+    if (marg_pose < 0 || marg_pose >= p->C || marg_sb >= p->NSB) return fail(p, VIO_ERR_INVALID, "bad vertex to marginalise");
+    if (p->L > 0 && p->h_lm_eptr.empty()) return fail(p, VIO_ERR_UNSUPPORTED, "graph too large for Marginalize");
+    for (int sp : p->h_sp_pose)
+        if (sp == marg_pose) return fail(p, VIO_ERR_UNSUPPORTED, "SE3-prior edge on the marginalised pose");
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    const int P = p->P;
+    // connected reprojection edges (host or observer is the frame) and their landmarks
+    std::vector<int> m_edge, m_lm, m_slot, slot_of(p->L, -1);
+    int Mm = 0;
+    for (int l = 0; l < p->L; ++l)
+        for (int e = p->h_lm_eptr[l]; e < p->h_lm_eptr[l + 1]; ++e)
+            if (p->h_lm_host[l] == marg_pose || p->h_e_pose_j[e] == marg_pose) {
+                if (slot_of[l] < 0) slot_of[l] = Mm++;
+                m_edge.push_back(e); m_lm.push_back(l); m_slot.push_back(slot_of[l]);
+            }
+    std::vector<int> m_imu;
+    for (int i = 0; i < (int)p->h_imu_pose_i.size(); ++i)
+        if (p->h_imu_pose_i[i] == marg_pose || p->h_imu_pose_j[i] == marg_pose) m_imu.push_back(i);
+    const int n_tot = P + Mm;
+    // permutation: the reference moves the marginalised vertices to the end, last one first (:724-748)
+    std::vector<int> perm(P);
+    for (int i = 0; i < P; ++i) perm[i] = i;
+    struct MV { int idx, dim; };
+    std::vector<MV> mv;
+    mv.push_back({p->h_pose_off[marg_pose], 6});
+    if (marg_sb >= 0) mv.push_back({p->h_sb_off[marg_sb], 9});
+    int m2 = 0;
+    for (int k = (int)mv.size() - 1; k >= 0; --k) {
+        // positions are given in the ORIGINAL ordering; earlier moves only affected larger offsets when idx is smaller
+        const int idx = mv[k].idx, dim = mv[k].dim;
+        // locate the current position of original index idx
+        int pos = (int)(std::find(perm.begin(), perm.end(), idx) - perm.begin());
+        std::vector<int> blk(perm.begin() + pos, perm.begin() + pos + dim);
+        perm.erase(perm.begin() + pos, perm.begin() + pos + dim);
+        perm.insert(perm.end(), blk.begin(), blk.end());
+        m2 += dim;
+    }
+    const int n2 = P - m2;
+    DBuf<double> H, b, Hpp, bpp, Hq, bq, U, V, lam, Ainv, Hn, bn, U2, V2, lam2, Jt, err, Hout;
+    DBuf<int> d_edge, d_lm, d_slot, d_imu, d_perm, ord, ord2;
+    CK(H.alloc((size_t)n_tot * n_tot)); CK(b.alloc(n_tot));
+    CK(cudaMemsetAsync(H.p, 0, (size_t)n_tot * n_tot * sizeof(double), st)); CK(cudaMemsetAsync(b.p, 0, n_tot * sizeof(double), st));
+    do_pose_prep(p);
+    if (!m_edge.empty()) {
+        CK(upload(d_edge, m_edge.data(), m_edge.size(), st)); CK(upload(d_lm, m_lm.data(), m_lm.size(), st));
+        CK(upload(d_slot, m_slot.data(), m_slot.size(), st));
+        MargEdgeView mvw;
+        mvw.n = (int)m_edge.size(); mvw.edge = d_edge.p; mvw.lm = d_lm.p; mvw.mslot = d_slot.p;
+        mvw.ext_off = p->h_ext_pose >= 0 ? p->h_pose_off[p->h_ext_pose] : -1;
+        k_marg_reproj<<<grid_for(mvw.n, 64), 64, 0, st>>>(p->view, mvw, H.p, b.p, n_tot, P);
+        p->launches++;
+    }
+    if (!m_imu.empty()) {
+        CK(upload(d_imu, m_imu.data(), m_imu.size(), st));
+        k_marg_imu<<<(int)m_imu.size(), 256, 0, st>>>(imu_view(p->imu, p->gravity), p->view, d_imu.p, H.p, b.p, n_tot);
+        p->launches++;
+    }
+    {
+        dim3 bb(32, 8), gg((n_tot + 31) / 32, (n_tot + 7) / 8);
+        k_mirror_dense<<<gg, bb, 0, st>>>(H.p, n_tot);
+    }
+    CK(Hpp.alloc((size_t)P * P)); CK(bpp.alloc(P)); CK(Hq.alloc((size_t)P * P)); CK(bq.alloc(P));
+    const bool have_prior = p->prior_dim == P;
+    k_marg_schur<<<grid_for((long long)P * (P + 1), 128), 128, 0, st>>>(H.p, b.p, n_tot, P, Mm, have_prior ? p->Hprior.p : nullptr,
+                                                                       have_prior ? p->bprior.p : nullptr, Hpp.p, bpp.p);
+    CK(upload(d_perm, perm.data(), perm.size(), st));
+    k_marg_permute<<<grid_for((long long)P * (P + 1), 128), 128, 0, st>>>(Hpp.p, bpp.p, d_perm.p, P, Hq.p, bq.p);
+    // eigen pseudo-inverse of the marginalised block, Schur, then the re-factorisation of the new prior
+    CK(U.alloc((size_t)m2 * m2)); CK(V.alloc((size_t)m2 * m2)); CK(lam.alloc(2 * (size_t)m2)); CK(ord.alloc(m2));
+    k_jacobi_eigh<<<1, 1024, 0, st>>>(Hq.p + (size_t)n2 * P + n2, P, m2, U.p, V.p, lam.p, ord.p);
+    CK(Ainv.alloc((size_t)m2 * m2)); CK(Hn.alloc((size_t)n2 * n2)); CK(bn.alloc(n2));
+    k_marg_eliminate<<<1, 1024, 0, st>>>(Hq.p, bq.p, P, n2, m2, V.p, lam.p, ord.p, 1e-8, Ainv.p, Hn.p, bn.p);
+    CK(U2.alloc((size_t)n2 * n2)); CK(V2.alloc((size_t)n2 * n2)); CK(lam2.alloc(2 * (size_t)n2)); CK(ord2.alloc(n2));
+    k_jacobi_eigh<<<1, 1024, 0, st>>>(Hn.p, n2, n2, U2.p, V2.p, lam2.p, ord2.p);
+    CK(Jt.alloc((size_t)n2 * n2)); CK(err.alloc(n2)); CK(Hout.alloc((size_t)n2 * n2));
+    k_marg_refactor<<<1, 1024, 0, st>>>(V2.p, lam2.p, ord2.p, n2, 1e-8, bn.p, Jt.p, err.p, Hout.p);
+    p->launches += 7;
+    CK(cudaGetLastError());
+    if (dim_out) *dim_out = n2;
+    if (H_prior) CK(cudaMemcpyAsync(H_prior, Hout.p, (size_t)n2 * n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (b_prior) CK(cudaMemcpyAsync(b_prior, bn.p, n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (err_prior) CK(cudaMemcpyAsync(err_prior, err.p, n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (Jt_prior_inv) CK(cudaMemcpyAsync(Jt_prior_inv, Jt.p, (size_t)n2 * n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return VIO_OK;
 }
 
