@@ -54,6 +54,7 @@ struct vio_problem;
 namespace myslam {
 namespace backend {
 
+struct PackB200;
 extern unsigned long global_vertex_id;
 extern unsigned long global_edge_id;
 
@@ -308,6 +309,7 @@ public:
 
 private:
     bool SolveGenericB200(int iterations);
+    bool PackGraphB200(PackB200 &K);
     bool IsPoseVertex(std::shared_ptr<Vertex> v);
     bool IsLandmarkVertex(std::shared_ptr<Vertex> v);
     void SetOrdering();

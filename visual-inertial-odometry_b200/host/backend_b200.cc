@@ -213,20 +213,30 @@ void Problem::SetOrdering() {
     for (auto &kv : idx_landmark_vertices_) kv.second->SetOrderingId(kv.second->OrderingId() + ordering_poses_);
 }
 
-bool Problem::Solve(int iterations) {
-    if (edges_.size() == 0 || verticies_.size() == 0) {
-        std::cerr << "\nCannot solve problem without edges or verticies" << std::endl;
-        return false;
-    }
-    const auto t0 = std::chrono::steady_clock::now();
-    if (problemType_ != ProblemType::SLAM_PROBLEM) return SolveGenericB200(iterations);
-    SetOrdering();
-    // ---- pack: pose-class vertices in id order, landmarks in id order ---------------------------------------------
+// everything Problem::Solve / Marginalize hand to the C-ABI: flat arrays + the vertex objects to write back into
+struct PackB200 {
     std::vector<double> pose, sb, invd;
     std::vector<uint8_t> pose_fixed, sb_fixed;
     std::vector<int32_t> pclass;
     std::unordered_map<unsigned long, int> pose_idx, sb_idx, lm_idx;
     std::vector<std::shared_ptr<Vertex>> pose_v, sb_v, lm_v;
+    std::vector<int32_t> rp_lm, rp_i, rp_j, sp_pose, imu_pi, imu_si, imu_pj, imu_sj;
+    std::vector<double> rp_pti, rp_ptj, sp_p, sp_q, sp_info, imu_dt, imu_dp, imu_dq, imu_dv, imu_ba, imu_bg, imu_jac, imu_cov;
+    vio_graph g;
+};
+
+bool Problem::PackGraphB200(PackB200 &K) {
+    auto &pose = K.pose; auto &sb = K.sb; auto &invd = K.invd; auto &pose_fixed = K.pose_fixed; auto &sb_fixed = K.sb_fixed;
+    auto &pclass = K.pclass; auto &pose_idx = K.pose_idx; auto &sb_idx = K.sb_idx; auto &lm_idx = K.lm_idx;
+    auto &pose_v = K.pose_v; auto &sb_v = K.sb_v; auto &lm_v = K.lm_v;
+    auto &rp_lm = K.rp_lm; auto &rp_i = K.rp_i; auto &rp_j = K.rp_j; auto &sp_pose = K.sp_pose;
+    auto &imu_pi = K.imu_pi; auto &imu_si = K.imu_si; auto &imu_pj = K.imu_pj; auto &imu_sj = K.imu_sj;
+    auto &rp_pti = K.rp_pti; auto &rp_ptj = K.rp_ptj; auto &sp_p = K.sp_p; auto &sp_q = K.sp_q; auto &sp_info = K.sp_info;
+    auto &imu_dt = K.imu_dt; auto &imu_dp = K.imu_dp; auto &imu_dq = K.imu_dq; auto &imu_dv = K.imu_dv;
+    auto &imu_ba = K.imu_ba; auto &imu_bg = K.imu_bg; auto &imu_jac = K.imu_jac; auto &imu_cov = K.imu_cov;
+    vio_graph &g = K.g;
+    SetOrdering();
+    // ---- pack: pose-class vertices in id order, landmarks in id order ---------------------------------------------
     for (auto &kv : verticies_) {
         auto &v = kv.second;
         const std::string t = v->TypeInfo();
@@ -257,9 +267,6 @@ bool Problem::Solve(int iterations) {
     eids.reserve(edges_.size());
     for (auto &kv : edges_) eids.push_back(kv.first);
     std::sort(eids.begin(), eids.end());  // deterministic packing order (the reference walks an unordered_map)
-    std::vector<int32_t> rp_lm, rp_i, rp_j, sp_pose, imu_pi, imu_si, imu_pj, imu_sj;
-    std::vector<double> rp_pti, rp_ptj, sp_p, sp_q, sp_info, imu_dt, imu_dp, imu_dq, imu_dv, imu_ba, imu_bg, imu_jac, imu_cov;
-    vio_graph g;
     std::memset(&g, 0, sizeof(g));
     g.ext_pose = -1;
     g.q_ic[3] = 1.0;
@@ -338,6 +345,21 @@ bool Problem::Solve(int iterations) {
     g.gravity[0] = 0; g.gravity[1] = 0; g.gravity[2] = 9.81;
     g.storage = VIO_STORAGE_AUTO;
 
+    return true;
+}
+
+bool Problem::Solve(int iterations) {
+    if (edges_.size() == 0 || verticies_.size() == 0) {
+        std::cerr << "\nCannot solve problem without edges or verticies" << std::endl;
+        return false;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    if (problemType_ != ProblemType::SLAM_PROBLEM) return SolveGenericB200(iterations);
+    PackB200 K;
+    if (!PackGraphB200(K)) return false;
+    vio_graph &g = K.g;
+    auto &pose = K.pose; auto &sb = K.sb; auto &invd = K.invd;
+    auto &pose_v = K.pose_v; auto &sb_v = K.sb_v; auto &lm_v = K.lm_v;
     if (!handle_) {
         int rc = vio_create(device_, nullptr, &handle_);
         if (rc != VIO_OK) throw std::runtime_error("vio_b200: no CUDA device (the GPU backend has no CPU fallback)");
@@ -530,10 +552,52 @@ bool Problem::SolveGenericB200(int iterations) {
     return true;
 }
 
-// Not on the device path yet; the declared-but-undefined overloads of the reference stay declared.
-bool Problem::Marginalize(const std::vector<std::shared_ptr<Vertex>>, int) {
-    std::cerr << "vio_b200: Problem::Marginalize is not implemented on the device path yet" << std::endl;
-    return false;
+// Problem::Marginalize(margVertexs, pose_dim): vins-mono/src/backend/problem.cc:617-795.  margVertexs[0] is the frame
+// pose, margVertexs[1] (optional) its speed-bias.  The elimination runs on the device (vio_marginalize); afterwards the
+// marginalised vertices and the landmarks that were eliminated with them are removed from the graph, like upstream.
+bool Problem::Marginalize(const std::vector<std::shared_ptr<Vertex>> margVertexs, int pose_dim) {
+    if (margVertexs.empty() || !v17_) { std::cerr << "vio_b200: Marginalize needs the v17 flavour and a frame vertex" << std::endl; return false; }
+    PackB200 K;
+    if (!PackGraphB200(K)) return false;
+    if ((int)ordering_poses_ != pose_dim) { std::cerr << "vio_b200: pose_dim does not match the pose-class dimension" << std::endl; return false; }
+    if (!handle_) {
+        int rc = vio_create(device_, nullptr, &handle_);
+        if (rc != VIO_OK) throw std::runtime_error("vio_b200: no CUDA device (the GPU backend has no CPU fallback)");
+    }
+    int rc = vio_set_graph(handle_, &K.g);
+    if (rc != VIO_OK) { std::cerr << "vio_b200: " << vio_last_error(handle_) << std::endl; return false; }
+    const int P = pose_dim;
+    if (H_prior_.rows() == P) {
+        std::vector<double> Hp((size_t)P * P);
+        for (int r = 0; r < P; ++r)
+            for (int c = 0; c < P; ++c) Hp[(size_t)r * P + c] = H_prior_(r, c);
+        rc = vio_set_prior(handle_, P, Hp.data(), b_prior_.data(), 0, nullptr, nullptr);
+        if (rc != VIO_OK) { std::cerr << "vio_b200: " << vio_last_error(handle_) << std::endl; return false; }
+    }
+    auto ip = K.pose_idx.find(margVertexs[0]->Id());
+    if (ip == K.pose_idx.end()) { std::cerr << "vio_b200: margVertexs[0] must be a VertexPose of this problem" << std::endl; return false; }
+    int msb = -1;
+    if (margVertexs.size() > 1) {
+        auto is = K.sb_idx.find(margVertexs[1]->Id());
+        if (is == K.sb_idx.end()) { std::cerr << "vio_b200: margVertexs[1] must be a VertexSpeedBias of this problem" << std::endl; return false; }
+        msb = is->second;
+    }
+    std::vector<double> H((size_t)P * P), b(P), e(P), J((size_t)P * P);
+    int32_t n = 0;
+    rc = vio_marginalize(handle_, ip->second, msb, &n, H.data(), b.data(), e.data(), J.data());
+    if (rc != VIO_OK) { std::cerr << "vio_b200: " << vio_last_error(handle_) << std::endl; return false; }
+    H_prior_ = Eigen::Map<Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>>(H.data(), n, n);
+    Jt_prior_inv_ = Eigen::Map<Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>>(J.data(), n, n);
+    b_prior_ = Eigen::Map<VecX>(b.data(), n);
+    err_prior_ = Eigen::Map<VecX>(e.data(), n);
+    // remove the marginalised vertices and the landmarks connected to the frame (problem.cc:786-793)
+    std::vector<std::shared_ptr<Vertex>> lms;
+    for (auto &ed : GetConnectedEdges(margVertexs[0]))
+        for (auto &vv : ed->Verticies())
+            if (IsLandmarkVertex(vv) && std::find(lms.begin(), lms.end(), vv) == lms.end()) lms.push_back(vv);
+    for (auto &mvx : margVertexs) RemoveVertex(mvx);
+    for (auto &lv : lms) RemoveVertex(lv);
+    return true;
 }
 bool Problem::Marginalize(const std::shared_ptr<Vertex>) { return true; }  // the v15 stub returns true as well
 
