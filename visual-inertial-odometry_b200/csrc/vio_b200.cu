@@ -89,6 +89,7 @@ struct vio_problem {
     DBuf<double> Hprior, bprior, bprior_bak, errprior, errprior_bak, Jtinv;
     // solver workspaces
     DBuf<double> chol_work;
+    bool chol_smem_set = false;
     DBuf<int> info;
     DBuf<unsigned> bar;
     bool coop_ok = false;
@@ -324,8 +325,17 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
     if (pcg_iters) *pcg_iters = 0;
     if (solver == VIO_SOLVER_DENSE_CHOL) {
         if (p->storage != VIO_STORAGE_DENSE) return fail(p, VIO_ERR_INVALID, "dense Cholesky needs dense storage");
-        if (p->chol_work.n < (size_t)P * P) CK(p->chol_work.alloc((size_t)P * P));
-        k_dense_chol_solve<<<1, 1024, P * sizeof(double), p->stream>>>(v.S, v.bS, lambda, P, p->chol_work.p, v.dxp, p->info.p);
+        const size_t tri_bytes = ((size_t)P * (P + 1) / 2 + P) * sizeof(double);
+        if (tri_bytes <= 220 * 1024) {
+            if (!p->chol_smem_set) {
+                CK(cudaFuncSetAttribute(k_dense_chol_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                p->chol_smem_set = true;
+            }
+            k_dense_chol_smem<<<1, 512, tri_bytes, p->stream>>>(v.S, v.bS, lambda, P, v.dxp, p->info.p);
+        } else {
+            if (p->chol_work.n < (size_t)P * P) CK(p->chol_work.alloc((size_t)P * P));
+            k_dense_chol_solve<<<1, 1024, P * sizeof(double), p->stream>>>(v.S, v.bS, lambda, P, p->chol_work.p, v.dxp, p->info.p);
+        }
         p->launches++;
     } else if (solver == VIO_SOLVER_REF_PCG) {
         if (p->storage != VIO_STORAGE_DENSE) return fail(p, VIO_ERR_INVALID, "reference PCG needs dense storage");
@@ -477,7 +487,7 @@ int do_apply(vio_problem *p, const vio_lm_opts &o) {
     p->launches += 1 + (p->NSB > 0) + (p->L > 0);
     if (p->prior_dim > 0 && p->err_dim > 0 && o.flavour == VIO_LM_V17) {
         // b_prior -= H_prior dx_p ; err_prior = -Jt_prior_inv b_prior.head(P-15)   (A17/src/backend/problem.cc:465-474)
-        k_prior_update<<<1, 256, 0, p->stream>>>(p->Hprior.p, p->bprior.p, p->bprior_bak.p, p->errprior.p,
+        k_prior_update<<<1, 1024, 0, p->stream>>>(p->Hprior.p, p->bprior.p, p->bprior_bak.p, p->errprior.p,
                                                 p->errprior_bak.p, p->Jtinv.p, v.dxp, p->P, p->err_dim);
         p->launches++;
     }

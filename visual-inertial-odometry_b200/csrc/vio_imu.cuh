@@ -224,20 +224,30 @@ __global__ void __launch_bounds__(256) k_imu_linearize(ImuView s, DevView v) {
     }
 }
 
-__global__ void k_imu_chi2(ImuView s, DevView v, double *out /* accumulates */) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    double chi = 0.0;
-    for (int e = 0; e < s.n; ++e) {
-        double r[15];
-        imu_edge_eval(s, v, e, r, nullptr);
-        const double *Om = s.info + 225 * (size_t)e;
-        for (int a = 0; a < 15; ++a) {
-            double t = 0.0;
-            for (int b = 0; b < 15; ++b) t += Om[15 * a + b] * r[b];
-            chi += r[a] * t;
+// one warp per IMU edge (lane 0 evaluates the residual, the lanes share the 15x15 quadratic form); per-edge values
+// are summed by thread 0 in edge order, so the result does not depend on scheduling
+__global__ void __launch_bounds__(1024) k_imu_chi2(ImuView s, DevView v, double *out /* accumulates */) {
+    __shared__ double r_s[32][15];
+    __shared__ double chi_s[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double total = 0.0;
+    for (int e0 = 0; e0 < s.n; e0 += nw) {
+        const int e = e0 + warp;
+        if (e < s.n) {
+            if (lane == 0) imu_edge_eval(s, v, e, r_s[warp], nullptr);
+            __syncwarp();
+            const double *Om = s.info + 225 * (size_t)e;
+            double part = 0.0;
+            for (int t = lane; t < 225; t += 32) part += r_s[warp][t / 15] * Om[t] * r_s[warp][t % 15];
+            part = warp_sum(part);
+            if (lane == 0) chi_s[warp] = part;
         }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int k = 0; k < nw && e0 + k < s.n; ++k) total += chi_s[k];
+        __syncthreads();
     }
-    *out += chi;
+    if (threadIdx.x == 0) *out += total;
 }
 
 inline ImuView imu_view(const ImuBuffers &b, const double G[3]) {
@@ -280,7 +290,7 @@ inline void imu_linearize(const ImuBuffers &b, const DevView &v, const double G[
     k_imu_linearize<<<b.n, 256, 0, st>>>(imu_view(b, G), v);
 }
 inline void imu_chi2(const ImuBuffers &b, const DevView &v, const double G[3], double *out, cudaStream_t st) {
-    k_imu_chi2<<<1, 32, 0, st>>>(imu_view(b, G), v, out);
+    k_imu_chi2<<<1, 32 * (b.n < 32 ? (b.n > 0 ? b.n : 1) : 32), 0, st>>>(imu_view(b, G), v, out);
 }
 
 // ---- dense marginalisation prior ------------------------------------------------------------------
@@ -300,7 +310,7 @@ __global__ void k_add_dense_prior(DevView v, const double *Hp, const double *bp,
 }
 
 // UpdateStates prior part: backup, b_prior -= H_prior dx_p, err_prior = -Jt_prior_inv b_prior.head(err_dim)
-__global__ void __launch_bounds__(256) k_prior_update(const double *Hp, double *bp, double *bp_bak, double *err,
+__global__ void __launch_bounds__(1024) k_prior_update(const double *Hp, double *bp, double *bp_bak, double *err,
                                                        double *err_bak, const double *Jt, const double *dx, int P,
                                                        int err_dim) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
