@@ -242,6 +242,19 @@ typedef struct vio_batch_item {
 } vio_batch_item;
 int vio_solve_batched(int device, int32_t n_workers, vio_batch_item *items, int64_t n_items, int32_t iterations,
                       const vio_lm_opts *opts);
+/* Lock-step variant for windows that share their pose-class structure (same number / order / fixed flags of poses and
+ * speed-biases, same IMU-edge count, same reprojection information / loss, same extrinsics, same prior dimensions - what
+ * consecutive Estimator::backendOptimization calls of one rig produce, A17/src/estimator.cpp:885-1030); landmark and edge
+ * counts may differ per item.  The batch is packed as ONE graph with `batch` stacked P x P reduced systems: every kernel
+ * launch covers all items, one CTA per item factorises its reduced system, and the v17 LM control runs per item between
+ * launches (items that converge early stop taking steps).  Results agree with vio_solve_batched to rounding (the
+ * reductions use a different, still deterministic, order).  v17 flavour + exact reduced solve only; max_chunk <= 0:
+ * 2048 items per packed graph.                                                                                        */
+int vio_solve_batched_lockstep(int device, vio_batch_item *items, int64_t n_items, int32_t iterations,
+                               const vio_lm_opts *opts, int32_t max_chunk);
+/* The lock-step entry keeps one device handle and its host staging alive between calls (a caller that submits batch
+ * after batch pays allocations once); this frees them.                                                                */
+int vio_lockstep_release(void);
 
 /* ---- GENERIC_PROBLEM lane: user-defined host edges --------------------------------------------------------------
  * Problem(GENERIC_PROBLEM) lets callers subclass Vertex/Edge with their own virtual ComputeResidual /

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--n", type=int, default=4096)
     ap.add_argument("--workers", type=int, default=16)
     ap.add_argument("--cpu-n", type=int, default=4)
+    ap.add_argument("--lockstep", action="store_true", help="vio_solve_batched_lockstep instead of the thread pool")
+    ap.add_argument("--chunk", type=int, default=0)
     args = ap.parse_args()
     vio = importlib.import_module("visual-inertial-odometry_b200")
     from tests import oraclelib as orc
@@ -34,8 +36,10 @@ def main():
         distinct.append(s)
     scenes = [distinct[i % len(distinct)] for i in range(args.n)]
     opts = vio.make_opts(flavour=vio.capi.LM_V17)
-    vio.capi.solve_batched(scenes[:args.workers], 10, opts, n_workers=args.workers)  # warm-up (contexts, allocations)
-    outs, dt = vio.capi.solve_batched(scenes, 10, opts, n_workers=args.workers)
+    kw = dict(n_workers=args.workers, lockstep=args.lockstep, max_chunk=args.chunk)
+    # warm-up (contexts, allocations); the lock-step entry keeps its handle + staging, so warm it at the measured size
+    vio.capi.solve_batched(scenes if args.lockstep else scenes[:args.workers], 10, opts, **kw)
+    outs, dt = vio.capi.solve_batched(scenes, 10, opts, **kw)
     E = int(base.rp_landmark.shape[0])
     iters = sum(o["stats"].iterations for o in outs)
     t0 = time.perf_counter()
@@ -43,10 +47,10 @@ def main():
         orc.solve(s, 10, opts)
     t_cpu = (time.perf_counter() - t0) / args.cpu_n
     print(json.dumps({"metric": "batched_windows_per_sec", "value": args.n / dt, "unit": "problems/s", "n_problems": args.n,
-                      "workers": args.workers, "wall_s": dt, "lm_iterations_total": iters,
+                      "workers": args.workers, "lockstep": bool(args.lockstep), "chunk": args.chunk, "wall_s": dt, "lm_iterations_total": iters,
                       "edges_per_sec": E * iters / dt, "edges_per_problem": E, "P": base.P,
                       "cpu_oracle_port_problems_per_sec_1core": 1.0 / t_cpu,
-                      "note": "each problem: pack + H2D + Solve(10) + D2H through vio_solve_batched"}))
+                      "note": "each problem: pack + H2D + Solve(10) + D2H through vio_solve_batched" + ("_lockstep" if args.lockstep else "")}))
 
 
 if __name__ == "__main__":

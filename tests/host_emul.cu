@@ -32,6 +32,7 @@ int setup(const vio_graph *g, HostProblem &H, std::string &err) {
     DevView &v = H.v;
     memset(&v, 0, sizeof(v));
     v.C = K.C; v.NSB = K.NSB; v.L = K.L; v.P = K.P; v.NB = K.NB; v.E = K.E; v.storage = K.storage; v.nnzb = K.nnzb;
+    v.batch = 1; v.Pper = K.P; v.Cper = K.C > 0 ? K.C : 1; v.NSBper = K.NSB > 0 ? K.NSB : 1;
     v.pose = H.pose.data(); v.pose_bak = H.pose_bak.data(); v.sb = H.sb.data(); v.invdep = K.invd.data();
     v.invdep_bak = H.invd_bak.data();
     v.pose_fixed = K.pose_fixed.data(); v.sb_fixed = K.sb_fixed.data();

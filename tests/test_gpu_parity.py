@@ -317,6 +317,54 @@ def test_batched_windows_match_single_solves(vio):
     assert rel_max(outs[5]["speedbias"], ref["speedbias"]) <= FINAL_TOL
 
 
+def test_lockstep_batch_matches_single_solves(vio):
+    """vio_solve_batched_lockstep: the batch packed as one graph (stacked reduced systems, per-problem LM control) gives
+    per problem what a single-handle solve gives - including problems that reject steps or stop early while others
+    continue, and windows with different landmark counts."""
+    from tests import oraclelib as orc
+    base = _window(vio)
+    rng = np.random.default_rng(11)
+    scenes = []
+    for k in range(7):
+        d = base.export()
+        if k in (2, 5):  # drop the last landmarks (and their edges) of this window: ragged batch
+            keep_l = d["inv_depth"].shape[0] - 7 * k
+            m = d["rp_landmark"] < keep_l
+            for key in ("rp_landmark", "rp_pose_i", "rp_pose_j", "rp_pts_i", "rp_pts_j"):
+                d[key] = d[key][m]
+            d["inv_depth"] = d["inv_depth"][:keep_l]
+        s = vio.Scene.from_dict(d)
+        amp = 0.01 if k != 3 else 0.2  # one badly perturbed window: rejected steps / more iterations
+        s.pose[1:-1, :3] += rng.normal(0, amp, (s.pose.shape[0] - 2, 3))
+        s.inv_depth *= 1.0 + rng.normal(0, 0.02, s.inv_depth.shape[0])
+        scenes.append(s)
+    opts = vio.make_opts(flavour=vio.capi.LM_V17)
+    outs, dt = vio.capi.solve_batched(scenes, 10, opts, lockstep=True)
+    iters = set()
+    for s, o in zip(scenes, outs):
+        p = vio.Problem()
+        p.set_graph(s)
+        st = p.solve(10, opts)
+        pose, sb, invd = p.get_vertices()
+        iters.add(st.iterations)
+        assert o["stats"].iterations == st.iterations
+        assert o["stats"].trial_steps == st.trial_steps
+        n = st.iterations
+        assert rel_max(np.array(o["stats"].chi2_trace[:n]), np.array(st.chi2_trace[:n])) <= 1e-8
+        assert abs(o["stats"].chi2_final - st.chi2_final) <= 1e-8 * st.chi2_final
+        assert rel_max(o["pose"], pose) <= 1e-8 and rel_max(o["speedbias"], sb) <= 1e-8
+        assert rel_max(o["inv_depth"], invd) <= 1e-7
+    # chunked (3 + 3 + 1) gives the same answers
+    outs2, _ = vio.capi.solve_batched(scenes, 10, opts, lockstep=True, max_chunk=3)
+    for a, b in zip(outs, outs2):
+        assert a["stats"].iterations == b["stats"].iterations
+        assert rel_max(a["pose"], b["pose"]) <= 1e-9
+    ref = orc.solve(scenes[6], 10, opts)
+    assert outs[6]["stats"].iterations == ref["iterations"]
+    assert abs(outs[6]["stats"].chi2_final - ref["chi2_final"]) <= FINAL_TOL * ref["chi2_final"]
+    assert rel_max(outs[6]["pose"], ref["pose"]) <= FINAL_TOL
+
+
 @pytest.mark.parametrize("scene_file,marg_file", [("windowA_v17_scene.npz", "windowA_v17_marg.npz"),
                                                    ("window_v17_scene.npz", "windowB_v17_marg.npz")])
 def test_marginalize_vs_golden(vio, scene_file, marg_file):

@@ -87,7 +87,7 @@ EXPORTS = [
     "vio_solve", "vio_linearize", "vio_chi2", "vio_solve_step", "vio_apply_step", "vio_rollback_step",
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
     "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
-    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_marginalize",
+    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_marginalize",
 ]
 
 _lib = None
@@ -477,8 +477,9 @@ class Problem:
         return int(self._L.vio_launch_count(self._h))
 
 
-def solve_batched(scenes, iterations, opts=None, device=0, n_workers=16):
-    """BASELINE config 3: many independent problems through vio_solve_batched.
+def solve_batched(scenes, iterations, opts=None, device=0, n_workers=16, lockstep=False, max_chunk=0):
+    """BASELINE config 3: many independent problems through vio_solve_batched (one handle per worker thread) or, with
+    lockstep=True, vio_solve_batched_lockstep (the whole batch as one packed graph).
 
     Returns (list of dicts with pose / speedbias / inv_depth / stats per scene, wall seconds of the call)."""
     import time
@@ -513,8 +514,12 @@ def solve_batched(scenes, iterations, opts=None, device=0, n_workers=16):
         outs.append(dict(pose=pose, speedbias=sb, inv_depth=invd, stats=st))
     L = lib()
     L.vio_solve_batched.argtypes = [C.c_int, C.c_int32, C.POINTER(VioBatchItem), C.c_int64, C.c_int32, C.POINTER(VioLmOpts)]
+    L.vio_solve_batched_lockstep.argtypes = [C.c_int, C.POINTER(VioBatchItem), C.c_int64, C.c_int32, C.POINTER(VioLmOpts), C.c_int32]
     t0 = time.perf_counter()
-    rc = L.vio_solve_batched(device, n_workers, items, n, iterations, C.byref(opts) if opts is not None else None)
+    if lockstep:
+        rc = L.vio_solve_batched_lockstep(device, items, n, iterations, C.byref(opts) if opts is not None else None, max_chunk)
+    else:
+        rc = L.vio_solve_batched(device, n_workers, items, n, iterations, C.byref(opts) if opts is not None else None)
     dt = time.perf_counter() - t0
     if rc != VIO_OK:
         raise VioError(rc, "vio_solve_batched: item errors " + str([items[i].rc for i in range(n) if items[i].rc][:5]))

@@ -7,7 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -23,6 +26,7 @@
 #include "vio_imu.cuh"
 #include "vio_grouped.cuh"
 #include "vio_marg.cuh"
+#include "vio_batch.cuh"
 
 #define VIO_VERSION_STR "vio_b200 0.1 (sm_100a)"
 
@@ -53,6 +57,11 @@ struct vio_problem {
     long long E = 0, nnzb = 0;
     int n_se3 = 0, n_imu = 0;
     int Lglobal = 0;
+    // lock-step batch (vio_solve_batched_lockstep): `batch` stacked problems of Pper rows each
+    int batch = 1, Pper = 0;
+    DBuf<int> lm_prob, lm_rng, imu_rng;
+    DBuf<uint8_t> b_act;
+    DBuf<double> b_lambda, b_out;
     std::vector<int> lm_global;  // local landmark -> caller's landmark index
     std::vector<int> h_pose_off, h_sb_off;
     // host copies of the (small-graph) structure for Marginalize
@@ -148,6 +157,9 @@ void fill_view(vio_problem *p) {
     DevView &v = p->view;
     v.C = p->C; v.NSB = p->NSB; v.L = p->L; v.P = p->P; v.NB = p->NB; v.E = p->E;
     v.storage = p->storage; v.nnzb = p->nnzb;
+    v.batch = p->batch; v.Pper = p->Pper;
+    v.Cper = std::max(1, p->C / p->batch); v.NSBper = std::max(1, p->NSB / p->batch);
+    v.lm_prob = p->lm_prob.p; v.act = nullptr;
     v.pose = p->pose.p; v.pose_bak = p->pose_bak.p; v.sb = p->sb.p; v.sb_bak = p->sb_bak.p;
     v.invdep = p->invdep.p; v.invdep_bak = p->invdep_bak.p;
     v.pose_fixed = p->pose_fixed.p; v.sb_fixed = p->sb_fixed.p;
@@ -204,7 +216,7 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
     if (ev) CK(cudaEventRecord(ev->a, p->stream));
     if (p->L > 0 && p->use_grouped) {
         GroupView gv;
-        gv.n_groups = p->n_groups; gv.ld = p->storage == VIO_STORAGE_DENSE ? p->P : 6;
+        gv.n_groups = p->n_groups; gv.ld = p->storage == VIO_STORAGE_DENSE ? p->Pper : 6;
         gv.hdr = (const GroupHdr *)p->g_hdr.p; gv.slot_pose = p->g_slot_pose.p; gv.pairinfo = p->g_pairinfo.p;
         gv.ell_pjx = p->ell_pjx.p; gv.ell_pjy = p->ell_pjy.p; gv.ell_edge = p->ell_edge.p;
         gv.prof = nullptr;
@@ -232,7 +244,7 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
             p->launches++;
         }
         if (p->prior_dim > 0 && o.flavour == VIO_LM_V17) {
-            k_add_dense_prior<<<grid_for((long long)p->P * p->P, 256), 256, 0, p->stream>>>(v, p->Hprior.p, p->bprior.p,
+            k_add_dense_prior<<<grid_for((long long)p->P * p->Pper, 256), 256, 0, p->stream>>>(v, p->Hprior.p, p->bprior.p,
                                                                                          p->imu.row_fixed.p);
             p->launches++;
         }
@@ -242,8 +254,8 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
         if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
     }
     if (p->storage == VIO_STORAGE_DENSE) {
-        dim3 b(32, 8), g((p->P + 31) / 32, (p->P + 7) / 8);
-        k_mirror_dense<<<g, b, 0, p->stream>>>(p->sys.p, p->P);
+        dim3 b(32, 8), g((p->Pper + 31) / 32, (p->Pper + 7) / 8, p->batch);
+        k_mirror_dense<<<g, b, 0, p->stream>>>(p->sys.p, p->Pper);
     } else {
         k_mirror_bsr<<<grid_for(p->nnzb * 36, 256), 256, 0, p->stream>>>(v);
     }
@@ -614,7 +626,10 @@ int vio_set_shard(vio_problem *p, int rank, int world) {
     return VIO_OK;
 }
 
-int vio_set_graph(vio_problem *p, const vio_graph *g) {
+static int set_graph_impl(vio_problem *p, const vio_graph *g, int batch);
+static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &K);
+int vio_set_graph(vio_problem *p, const vio_graph *g) { return set_graph_impl(p, g, 1); }
+static int set_graph_impl(vio_problem *p, const vio_graph *g, int batch) {
     if (!p || !g) return VIO_ERR_INVALID;
     CK(cudaSetDevice(p->device));
     p->has_graph = false;
@@ -623,11 +638,28 @@ int vio_set_graph(vio_problem *p, const vio_graph *g) {
     p->pcg_grid = -1;
     PackedGraph K;
     {
-        int rc = pack_graph(g, p->shard_rank, p->shard_world, K, p->err);
+        if (batch > 1 && p->shard_world > 1) return fail(p, VIO_ERR_UNSUPPORTED, "lock-step batches are not sharded");
+        int rc = pack_graph(g, p->shard_rank, p->shard_world, K, p->err, batch);
         if (rc) return rc;
     }
+    return upload_packed(p, g, K);
+}
+// device upload of a packed graph; `g` supplies the vertex values and the pose-only factors (its reprojection arrays
+// are not read any more)
+static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &K) {
+    p->batch = K.batch; p->Pper = K.Pper;
     const int C = K.C, NSB = K.NSB, L = K.L, P = K.P, NB = K.NB;
     const long long E = K.E;
+    const bool prof_up = K.batch > 1 && getenv("VIO_B200_PROFILE");
+    auto tick = [&](const char *what) {
+        if (!prof_up) return;
+        static double last = 0;
+        cudaStreamSynchronize(p->stream);
+        const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        if (what) fprintf(stderr, "[vio_b200 profile]   upload %-14s %.1f ms\n", what, t - last);
+        last = t;
+    };
+    tick(nullptr);
     p->C = C; p->NSB = NSB; p->L = L; p->P = P; p->NB = NB; p->E = E; p->storage = K.storage; p->nnzb = K.nnzb;
     p->Lglobal = K.Lglobal; p->s_count = K.s_count; p->n_se3 = g->n_se3prior; p->n_imu = g->n_imu;
     p->h_pose_off = K.pose_off; p->h_sb_off = K.sb_off; p->h_rowptr = K.rowptr; p->h_col = K.col;
@@ -639,6 +671,7 @@ int vio_set_graph(vio_problem *p, const vio_graph *g) {
     p->h_sp_pose.assign(g->sp_pose, g->sp_pose + (g->n_se3prior > 0 ? g->n_se3prior : 0));
     p->h_ext_pose = g->ext_pose;
     cudaStream_t s = p->stream;
+    tick("host copies");
     CK(upload(p->pose, g->pose, 7 * (size_t)C, s)); CK(p->pose_bak.alloc(7 * (size_t)C));
     CK(upload(p->sb, g->speedbias, 9 * (size_t)NSB, s)); CK(p->sb_bak.alloc(9 * (size_t)NSB));
     CK(upload(p->invdep, K.invd.data(), (size_t)L, s)); CK(p->invdep_bak.alloc(L));
@@ -651,10 +684,12 @@ int vio_set_graph(vio_problem *p, const vio_graph *g) {
     CK(upload(p->lm_piz, K.piz.data(), (size_t)L, s));
     CK(upload(p->e_pose_j, K.e_pose_j.data(), (size_t)E, s));
     CK(upload(p->e_pjx, K.pjx.data(), (size_t)E, s)); CK(upload(p->e_pjy, K.pjy.data(), (size_t)E, s));
+    tick("lm+edges");
     CK(p->Hll.alloc(L)); CK(p->bl.alloc(L)); CK(p->wh.alloc(6 * (size_t)L)); CK(p->wo.alloc(6 * (size_t)E));
     CK(p->sys.alloc(K.s_count + 3 * (size_t)P)); CK(p->bS.alloc(P)); CK(p->dxp.alloc(P)); CK(p->dxl.alloc(L));
     CK(cudaMemsetAsync(p->dxp.p, 0, P * sizeof(double), s));
     if (L > 0) CK(cudaMemsetAsync(p->dxl.p, 0, L * sizeof(double), s));
+    tick("out allocs");
     if (K.storage == VIO_STORAGE_BSR) {
         CK(upload(p->bsr_rowptr, K.rowptr.data(), K.rowptr.size(), s)); CK(upload(p->bsr_col, K.col.data(), K.col.size(), s));
         CK(upload(p->bsr_tr, K.tr.data(), K.tr.size(), s)); CK(upload(p->bsr_diag, K.diag.data(), K.diag.size(), s));
@@ -679,6 +714,7 @@ int vio_set_graph(vio_problem *p, const vio_graph *g) {
             CK(cudaMemsetAsync(p->wh.p, 0, 6 * (size_t)L * sizeof(double), s));
         }
     }
+    tick("groups");
     if (g->n_se3prior > 0) {
         CK(upload(p->sp_pose, g->sp_pose, (size_t)g->n_se3prior, s)); CK(upload(p->sp_p, g->sp_p, 3 * (size_t)g->n_se3prior, s));
         CK(upload(p->sp_q, g->sp_q, 4 * (size_t)g->n_se3prior, s)); CK(upload(p->sp_info, g->sp_info, 36 * (size_t)g->n_se3prior, s));
@@ -700,6 +736,7 @@ int vio_set_graph(vio_problem *p, const vio_graph *g) {
     quat_to_R(K.qic, v.Ric);
     v.tic[0] = K.tic[0]; v.tic[1] = K.tic[1]; v.tic[2] = K.tic[2];
     v.rp_info = g->rp_info; v.rp_loss = g->rp_loss; v.rp_delta = g->rp_loss_delta;
+    tick("imu+rest");
     CK(cudaStreamSynchronize(s));  // host staging vectors go out of scope
     p->has_graph = true;
     return VIO_OK;
@@ -1230,6 +1267,378 @@ int vio_solve_batched(int device, int32_t n_workers, vio_batch_item *items, int6
     for (int w = 0; w < n_workers; ++w) pool.emplace_back(worker);
     for (auto &t : pool) t.join();
     return first_err.load();
+}
+
+// -------------------------------------------------------------------------------------------------
+// lock-step batched solve: the batch is ONE packed graph (see vio_batch.cuh); every launch covers all problems and the
+// v17 LM control (A17/src/backend/problem.cc:169-250) runs per problem on the host between launches.
+// -------------------------------------------------------------------------------------------------
+// Host staging that survives between calls (per-item packs, the merged pack, the concatenated vertex / IMU arrays) and the
+// device handle with its buffers: a caller that submits batch after batch pays the allocations and page faults once.
+struct LockstepCache {
+    std::mutex mu;
+    vio_problem *handle = nullptr;
+    int device = -1;
+    std::vector<PackedGraph> Ks;
+    PackedGraph K;
+    std::vector<double> pose, sb, idt, idp, idq, idv, iba, ibg, ijac, icov;
+    std::vector<int32_t> ipi, isi, ipj, isj;
+};
+static LockstepCache g_lockstep;
+
+static int lockstep_chunk(vio_problem *p, LockstepCache &cache, vio_batch_item *items, int B, int32_t iterations, const vio_lm_opts &o) {
+    CK(cudaSetDevice(p->device));
+    const vio_graph *g0 = items[0].graph;
+    if (!g0) return fail(p, VIO_ERR_INVALID, "item 0: graph missing");
+    const bool prof = getenv("VIO_B200_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
+    const int C = g0->n_pose, NSB = g0->n_speedbias, NI = g0->n_imu, NBper = C + NSB;
+    // ---- structural identity of the pose-class part ------------------------------------------------------------
+    auto same_bytes = [](const void *a, const void *b, size_t n) { return (!a && !b) || (a && b && memcmp(a, b, n) == 0); };
+    for (int k = 0; k < B; ++k) {
+        const vio_graph *g = items[k].graph;
+        if (!g) return fail(p, VIO_ERR_INVALID, "item %d: graph missing", k);
+        if (g->n_pose != C || g->n_speedbias != NSB || g->n_imu != NI || g->n_se3prior != 0 || g->ext_pose != g0->ext_pose ||
+            g->rp_info != g0->rp_info || g->rp_loss != g0->rp_loss || g->rp_loss_delta != g0->rp_loss_delta ||
+            !same_bytes(g->pclass_order, g0->pclass_order, sizeof(int32_t) * NBper) || !same_bytes(g->pose_fixed, g0->pose_fixed, C) ||
+            !same_bytes(g->speedbias_fixed, g0->speedbias_fixed, NSB) || memcmp(g->gravity, g0->gravity, sizeof(g->gravity)) != 0 ||
+            items[k].prior_dim != items[0].prior_dim || items[k].err_dim != items[0].err_dim)
+            return fail(p, VIO_ERR_UNSUPPORTED, "item %d: lock-step batches need identical pose-class structure, factors kinds and options", k);
+        if (g->storage == VIO_STORAGE_BSR) return fail(p, VIO_ERR_UNSUPPORTED, "lock-step batches use dense storage");
+        const bool same_ext = g->ext_pose >= 0 ? memcmp(g->pose + 7 * (size_t)g->ext_pose, g0->pose + 7 * (size_t)g0->ext_pose, 56) == 0
+                                               : (memcmp(g->q_ic, g0->q_ic, 32) == 0 && memcmp(g->t_ic, g0->t_ic, 24) == 0);
+        if (!same_ext) return fail(p, VIO_ERR_UNSUPPORTED, "item %d: camera extrinsics differ inside a lock-step batch", k);
+        if (g->n_landmark < 0 || g->n_reproj < 0) return fail(p, VIO_ERR_INVALID, "item %d: negative size", k);
+    }
+    // ---- pack every item on its own (worker threads), merge, concatenate the small per-vertex arrays ------------------
+    const int n_thr = std::max(1, std::min(std::min(B, 16), (int)std::thread::hardware_concurrency()));
+    auto parallel_items = [&](const std::function<void(int, int)> &fn) {
+        if (n_thr == 1) { fn(0, B); return; }
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_thr; ++t) {
+            const int k0 = (int)((long long)B * t / n_thr), k1 = (int)((long long)B * (t + 1) / n_thr);
+            pool.emplace_back(fn, k0, k1);
+        }
+        for (auto &th : pool) th.join();
+    };
+    std::vector<PackedGraph> &Ks = cache.Ks;
+    Ks.resize(B);
+    std::vector<int> pack_rc(B, VIO_OK);
+    std::vector<std::string> pack_err(n_thr);
+    parallel_items([&](int k0, int k1) {
+        std::string e;
+        for (int k = k0; k < k1; ++k) {
+            vio_graph gk = *items[k].graph;
+            gk.storage = VIO_STORAGE_DENSE;
+            gk.n_se3prior = 0;
+            pack_rc[k] = pack_graph(&gk, 0, 1, Ks[k], e);
+            if (pack_rc[k] != VIO_OK) { pack_err[(size_t)((long long)k0 * n_thr / std::max(B, 1)) % n_thr] = e; break; }
+        }
+    });
+    for (int k = 0; k < B; ++k)
+        if (pack_rc[k] != VIO_OK) {
+            std::string msg;
+            for (auto &e : pack_err) if (!e.empty()) { msg = e; break; }
+            return fail(p, pack_rc[k], "item %d: %s", k, msg.c_str());
+        }
+    PackedGraph &K = cache.K;
+    PackedMerge mg;
+    {
+        int rc = mg.prepare(Ks, K, p->err);
+        if (rc) return rc;
+    }
+    const std::vector<long long> &Loff = mg.Lb;
+    const long long Lt = Loff[B];
+    std::vector<double> &pose = cache.pose, &sb = cache.sb, &idt = cache.idt, &idp = cache.idp, &idq = cache.idq, &idv = cache.idv,
+                        &iba = cache.iba, &ibg = cache.ibg, &ijac = cache.ijac, &icov = cache.icov;
+    std::vector<int32_t> &ipi = cache.ipi, &isi = cache.isi, &ipj = cache.ipj, &isj = cache.isj;
+    pose.resize(7 * (size_t)B * C); sb.resize(9 * (size_t)B * NSB);
+    ipi.resize((size_t)B * NI); isi.resize((size_t)B * NI); ipj.resize((size_t)B * NI); isj.resize((size_t)B * NI);
+    idt.resize((size_t)B * NI); idp.resize(3 * (size_t)B * NI); idq.resize(4 * (size_t)B * NI); idv.resize(3 * (size_t)B * NI);
+    iba.resize(3 * (size_t)B * NI); ibg.resize(3 * (size_t)B * NI); ijac.resize(225 * (size_t)B * NI); icov.resize(225 * (size_t)B * NI);
+    parallel_items([&](int k0, int k1) {
+        mg.fill(k0, k1);
+        for (int k = k0; k < k1; ++k) {
+            const vio_graph *g = items[k].graph;
+            if (C) memcpy(&pose[7 * (size_t)k * C], g->pose, 56 * (size_t)C);
+            if (NSB) memcpy(&sb[9 * (size_t)k * NSB], g->speedbias, 72 * (size_t)NSB);
+            for (int i = 0; i < NI; ++i) {
+                const size_t d = (size_t)k * NI + i;
+                ipi[d] = g->imu_pose_i[i] + k * C; ipj[d] = g->imu_pose_j[i] + k * C;
+                isi[d] = g->imu_sb_i[i] + k * NSB; isj[d] = g->imu_sb_j[i] + k * NSB;
+                idt[d] = g->imu_sum_dt[i];
+                memcpy(&idp[3 * d], g->imu_delta_p + 3 * i, 24); memcpy(&idq[4 * d], g->imu_delta_q + 4 * i, 32);
+                memcpy(&idv[3 * d], g->imu_delta_v + 3 * i, 24); memcpy(&iba[3 * d], g->imu_lin_ba + 3 * i, 24);
+                memcpy(&ibg[3 * d], g->imu_lin_bg + 3 * i, 24);
+                memcpy(&ijac[225 * d], g->imu_jacobian + 225 * i, 1800); memcpy(&icov[225 * d], g->imu_covariance + 225 * i, 1800);
+            }
+        }
+    });
+    for (int k = 0; k < B; ++k)
+        for (int i = 0; i < NI; ++i) {
+            const vio_graph *g = items[k].graph;
+            if (g->imu_pose_i[i] < 0 || g->imu_pose_i[i] >= C || g->imu_pose_j[i] < 0 || g->imu_pose_j[i] >= C || g->imu_sb_i[i] < 0 ||
+                g->imu_sb_i[i] >= NSB || g->imu_sb_j[i] < 0 || g->imu_sb_j[i] >= NSB)
+                return fail(p, VIO_ERR_INVALID, "item %d: bad IMU edge description", k);
+        }
+    vio_graph G = *g0;
+    G.n_pose = B * C; G.pose = pose.data(); G.pose_fixed = nullptr;
+    G.n_speedbias = B * NSB; G.speedbias = sb.data(); G.speedbias_fixed = nullptr; G.pclass_order = nullptr;
+    G.n_landmark = (int32_t)Lt; G.inv_depth = nullptr;
+    G.n_reproj = K.E; G.rp_landmark = nullptr; G.rp_pose_i = nullptr; G.rp_pose_j = nullptr; G.rp_pts_i = nullptr; G.rp_pts_j = nullptr;
+    G.n_se3prior = 0;
+    G.n_imu = B * NI; G.imu_pose_i = ipi.data(); G.imu_sb_i = isi.data(); G.imu_pose_j = ipj.data(); G.imu_sb_j = isj.data();
+    G.imu_sum_dt = idt.data(); G.imu_delta_p = idp.data(); G.imu_delta_q = idq.data(); G.imu_delta_v = idv.data();
+    G.imu_lin_ba = iba.data(); G.imu_lin_bg = ibg.data(); G.imu_jacobian = ijac.data(); G.imu_covariance = icov.data();
+    G.storage = VIO_STORAGE_DENSE;
+    const double t_concat = now();
+    p->has_graph = false; p->linearized = false; p->lm_valid = false; p->pcg_grid = -1;
+    {
+        int rc = upload_packed(p, &G, K);
+        if (rc) return rc;
+    }
+    const double t_pack = now();
+    const int Pper = p->Pper, L = p->L;
+    const size_t tri_bytes = ((size_t)Pper * (Pper + 1) / 2 + Pper) * sizeof(double);
+    if (tri_bytes > 220 * 1024) return fail(p, VIO_ERR_UNSUPPORTED, "lock-step batch: P=%d per problem does not fit the shared-memory Cholesky", Pper);
+    CK(cudaFuncSetAttribute(k_chol_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    // ---- per-problem landmark / IMU-edge ranges (items are contiguous in the merged pack) ---------------------------
+    std::vector<int> lm_prob(std::max(L, 1), 0), lm_rng(B + 1, 0), imu_rng(B + 1, 0);
+    for (int k = 0; k <= B; ++k) { lm_rng[k] = (int)Loff[k]; imu_rng[k] = k * NI; }
+    for (int k = 0; k < B; ++k) std::fill(lm_prob.begin() + lm_rng[k], lm_prob.begin() + lm_rng[k + 1], k);
+    cudaStream_t st = p->stream;
+    CK(upload(p->lm_prob, lm_prob.data(), lm_prob.size(), st)); CK(upload(p->lm_rng, lm_rng.data(), lm_rng.size(), st));
+    CK(upload(p->imu_rng, imu_rng.data(), imu_rng.size(), st));
+    CK(p->b_act.alloc(B)); CK(p->b_lambda.alloc(B)); CK(p->b_out.alloc(8 * (size_t)B));
+    // ---- priors: straight from the items' arrays into the stacked device buffers ----------------------------------
+    const int prior_dim = items[0].prior_dim, err_dim = items[0].err_dim;
+    if (prior_dim != 0 && prior_dim != Pper) return fail(p, VIO_ERR_INVALID, "prior dim %d != P %d", prior_dim, Pper);
+    if (err_dim < 0 || err_dim > prior_dim) return fail(p, VIO_ERR_INVALID, "bad err_dim");
+    if (prior_dim > 0) {
+        const size_t pp = (size_t)Pper * Pper, ee = (size_t)err_dim * err_dim;
+        CK(p->Hprior.alloc(B * pp)); CK(p->bprior.alloc((size_t)B * Pper)); CK(p->bprior_bak.alloc((size_t)B * Pper));
+        if (err_dim > 0) { CK(p->errprior.alloc((size_t)B * err_dim)); CK(p->errprior_bak.alloc((size_t)B * err_dim)); CK(p->Jtinv.alloc(B * ee)); }
+        for (int k = 0; k < B; ++k) {
+            if (!items[k].H_prior || !items[k].b_prior || (err_dim > 0 && (!items[k].err_prior || !items[k].Jt_prior_inv)))
+                return fail(p, VIO_ERR_INVALID, "item %d: prior arrays missing", k);
+            CK(cudaMemcpyAsync(p->Hprior.p + k * pp, items[k].H_prior, pp * sizeof(double), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(p->bprior.p + (size_t)k * Pper, items[k].b_prior, Pper * sizeof(double), cudaMemcpyHostToDevice, st));
+            if (err_dim > 0) {
+                CK(cudaMemcpyAsync(p->errprior.p + (size_t)k * err_dim, items[k].err_prior, err_dim * sizeof(double), cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(p->Jtinv.p + k * ee, items[k].Jt_prior_inv, ee * sizeof(double), cudaMemcpyHostToDevice, st));
+            }
+        }
+        CK(cudaStreamSynchronize(st));
+    }
+    p->prior_dim = prior_dim; p->err_dim = err_dim;
+    fill_view(p);  // lm_prob pointer
+    // ---- LM, per problem (A17/src/backend/problem.cc:169-250) ----------------------------------------------------
+    struct LmState {
+        double chi = 0, lambda = 0, ni = 2, last_chi = 1e20;
+        int iter = 0, false_cnt = 0;
+        bool done = false, in_iter = false;
+    };
+    std::vector<LmState> S(B);
+    std::vector<vio_stats> stats(B);
+    for (auto &t : stats) memset(&t, 0, sizeof(t));
+    std::vector<double> h_out(8 * (size_t)B), h_lambda(B);
+    std::vector<uint8_t> h_act(B), h_rej(B);
+    const ImuView iv = imu_view(p->imu, p->gravity);
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, st));
+    auto chi2_all = [&]() -> int {  // -> h_out[8k+0] + h_out[8k+1]
+        do_pose_prep(p);
+        k_chi2_batch<<<B, 256, 0, st>>>(p->view, p->lm_rng.p, p->b_out.p);
+        k_other_chi2_batch<<<B, 320, 0, st>>>(iv, p->view, p->imu_rng.p, p->errprior.p, p->prior_dim > 0 ? p->err_dim : 0, p->b_out.p);
+        p->launches += 2;
+        return VIO_OK;
+    };
+    auto fetch_out = [&]() -> int {
+        CK(cudaMemcpyAsync(h_out.data(), p->b_out.p, h_out.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return VIO_OK;
+    };
+    int rc;
+#define RC(x)                       \
+    do {                            \
+        rc = (x);                   \
+        if (rc) return rc;          \
+    } while (0)
+    RC(do_linearize(p, o, true));
+    RC(chi2_all());
+    k_maxdiag_batch<<<B, 256, 0, st>>>(p->view, p->lm_rng.p, p->b_out.p);
+    p->launches++;
+    RC(fetch_out());
+    int linearizations = 1;
+    for (int k = 0; k < B; ++k) {
+        S[k].chi = 0.5 * (h_out[8 * k] + h_out[8 * k + 1]);
+        S[k].lambda = 1e-5 * std::min(5e10, h_out[8 * k + 6]);
+        stats[k].chi2_initial = S[k].chi; stats[k].lambda_initial = S[k].lambda;
+        S[k].done = iterations <= 0;
+    }
+    for (;;) {
+        int n_act = 0;
+        for (int k = 0; k < B; ++k) {
+            LmState &s = S[k];
+            h_act[k] = !s.done;
+            h_lambda[k] = s.lambda;
+            if (s.done) continue;
+            ++n_act;
+            if (!s.in_iter) {  // top of the reference's outer loop
+                if (o.verbose) printf("[%d] iter: %d , chi= %g , Lambda= %g\n", k, s.iter, s.chi, s.lambda);
+                if (s.iter < VIO_TRACE_MAX) { stats[k].chi2_trace[s.iter] = s.chi; stats[k].lambda_trace[s.iter] = s.lambda; }
+                s.in_iter = true; s.false_cnt = 0;
+            }
+        }
+        if (n_act == 0) break;
+        CK(cudaMemcpyAsync(p->b_act.p, h_act.data(), B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(p->b_lambda.p, h_lambda.data(), B * sizeof(double), cudaMemcpyHostToDevice, st));
+        // SolveLinearSystem for every active problem
+        k_chol_batch<<<B, 512, tri_bytes, st>>>(p->view.S, p->view.bS, p->b_lambda.p, p->b_act.p, Pper, p->view.dxp);
+        k_backsub_batch<<<B, 256, 0, st>>>(p->view, p->lm_rng.p, p->b_lambda.p, p->b_out.p);
+        p->launches += 2;
+        // UpdateStates (masked)
+        {
+            DevView v = p->view;
+            v.act = p->b_act.p;
+            k_update_pose<<<grid_for(p->C, 128), 128, 0, st>>>(v, 1.0, 1);
+            if (p->NSB > 0) k_update_sb<<<grid_for(p->NSB, 128), 128, 0, st>>>(v, 1.0, 1);
+            if (p->L > 0) k_update_lm<<<grid_for(p->L, 256), 256, 0, st>>>(v, 1.0, 1);
+            p->launches += 1 + (p->NSB > 0) + (p->L > 0);
+            if (p->prior_dim > 0 && p->err_dim > 0) {
+                k_prior_update_batch<<<B, 512, 0, st>>>(p->Hprior.p, p->bprior.p, p->bprior_bak.p, p->errprior.p, p->errprior_bak.p,
+                                                       p->Jtinv.p, v.dxp, p->b_act.p, Pper, p->err_dim);
+                p->launches++;
+            }
+        }
+        RC(chi2_all());
+        RC(fetch_out());
+        // IsGoodStepInLM per problem
+        int n_ok = 0, n_rej = 0;
+        for (int k = 0; k < B; ++k) {
+            LmState &s = S[k];
+            h_rej[k] = 0;
+            if (s.done) continue;
+            stats[k].trial_steps++;
+            const double dot = h_out[8 * k + 2] + h_out[8 * k + 4];
+            const double scale = 0.5 * dot + 1e-6;
+            const double temp_chi = 0.5 * (h_out[8 * k] + h_out[8 * k + 1]);
+            const double rho = (s.chi - temp_chi) / scale;
+            bool ok;
+            if (rho > 0 && std::isfinite(temp_chi)) {
+                double alpha = 1.0 - std::pow(2 * rho - 1, 3);
+                alpha = std::min(alpha, 2.0 / 3.0);
+                s.lambda *= std::max(1.0 / 3.0, alpha);
+                s.ni = 2; s.chi = temp_chi; ok = true;
+            } else {
+                s.lambda *= s.ni; s.ni *= 2; ok = false;
+            }
+            if (ok) { ++n_ok; stats[k].accepted_steps++; stats[k].linearizations++; s.false_cnt = 0; }
+            else { ++n_rej; h_rej[k] = 1; s.false_cnt++; }
+            if (ok || s.false_cnt >= 10) {  // the reference's inner while ends
+                s.iter++; s.in_iter = false;
+                if (!o.fixed_iterations && s.last_chi - s.chi < 1e-5) s.done = true;
+                s.last_chi = s.chi;
+                if (s.iter >= iterations) s.done = true;
+            }
+        }
+        if (n_rej > 0) {  // RollbackStates for the rejected problems
+            CK(cudaMemcpyAsync(p->b_act.p, h_rej.data(), B, cudaMemcpyHostToDevice, st));
+            DevView v = p->view;
+            v.act = p->b_act.p;
+            long long n = std::max<long long>(std::max<long long>(7LL * p->C, 9LL * p->NSB), p->L);
+            k_restore<<<grid_for(n, 256), 256, 0, st>>>(v);
+            p->launches++;
+            if (p->prior_dim > 0 && p->err_dim > 0) {
+                k_prior_restore_batch<<<B, 256, 0, st>>>(p->bprior.p, p->bprior_bak.p, p->errprior.p, p->errprior_bak.p, p->b_act.p, Pper, p->err_dim);
+                p->launches++;
+            }
+        }
+        if (n_ok > 0) {  // MakeHessian at the new states (unchanged problems reproduce their system)
+            RC(do_linearize(p, o, true));
+            ++linearizations;
+        }
+    }
+#undef RC
+    CK(cudaEventRecord(ev1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    const double t_loop_end = now();
+    // ---- results --------------------------------------------------------------------------------------------------
+    std::vector<double> h_pose(7 * (size_t)B * C), h_sb(9 * (size_t)B * NSB), h_inv(Lt);
+    {
+        int rc2 = vio_get_vertices(p, h_pose.data(), NSB ? h_sb.data() : nullptr, Lt ? h_inv.data() : nullptr);
+        if (rc2) return rc2;
+    }
+    for (int k = 0; k < B; ++k) {
+        vio_batch_item &it = items[k];
+        if (it.pose_out && C) memcpy(it.pose_out, &h_pose[7 * (size_t)k * C], 56 * (size_t)C);
+        if (it.speedbias_out && NSB) memcpy(it.speedbias_out, &h_sb[9 * (size_t)k * NSB], 72 * (size_t)NSB);
+        if (it.inv_depth_out && it.graph->n_landmark) memcpy(it.inv_depth_out, &h_inv[Loff[k]], 8 * (size_t)it.graph->n_landmark);
+        if (it.stats) {
+            vio_stats &t = stats[k];
+            t.iterations = S[k].iter; t.n_trace = std::min(S[k].iter, VIO_TRACE_MAX);
+            t.linearizations += 1; t.chi2_final = S[k].chi; t.lambda_final = S[k].lambda; t.ms_total = ms;
+            *it.stats = t;
+        }
+        it.rc = VIO_OK;
+    }
+    if (prof)
+        fprintf(stderr, "[vio_b200 profile] lockstep B=%d: pack+merge %.1f ms, upload %.1f ms, priors+LM loop %.1f ms (%d linearisations, device %.1f ms), "
+                        "total %.1f ms\n", B, t_concat - t_start, t_pack - t_concat, t_loop_end - t_pack, linearizations, (double)ms, now() - t_start);
+    return VIO_OK;
+}
+
+int vio_solve_batched_lockstep(int device, vio_batch_item *items, int64_t n_items, int32_t iterations, const vio_lm_opts *opts,
+                               int32_t max_chunk) {
+    if (!items || n_items < 0) return VIO_ERR_INVALID;
+    if (n_items == 0) return VIO_OK;
+    vio_lm_opts o = opts ? *opts : default_opts();
+    if (o.flavour != VIO_LM_V17 || (o.solver != VIO_SOLVER_AUTO && o.solver != VIO_SOLVER_DENSE_CHOL))
+        return VIO_ERR_UNSUPPORTED;  // the lock-step loop is the v17 LM with the exact reduced solve
+    LockstepCache &cache = g_lockstep;
+    std::lock_guard<std::mutex> lock(cache.mu);  // one lock-step batch at a time per process
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    if (cache.handle && cache.device != device) { vio_destroy(cache.handle); cache.handle = nullptr; }
+    if (!cache.handle) {
+        int rc = vio_create(device, nullptr, &cache.handle);
+        if (rc != VIO_OK) return rc;
+        cache.device = device;
+    }
+    vio_problem *p = cache.handle;
+    const double t1 = now();
+    if (max_chunk <= 0) max_chunk = 2048;
+    int rc = VIO_OK;
+    for (int64_t i0 = 0; i0 < n_items && rc == VIO_OK; i0 += max_chunk) {
+        const int B = (int)std::min<int64_t>(max_chunk, n_items - i0);
+        rc = lockstep_chunk(p, cache, items + i0, B, iterations, o);
+        if (rc != VIO_OK) {
+            fprintf(stderr, "vio_solve_batched_lockstep: %s\n", p->err.c_str());
+            for (int k = 0; k < B; ++k) items[i0 + k].rc = rc;
+        }
+    }
+    if (getenv("VIO_B200_PROFILE"))
+        fprintf(stderr, "[vio_b200 profile] lockstep call: handle %.1f ms, chunks %.1f ms\n", t1 - t0, now() - t1);
+    return rc;
+}
+/* frees the cached lock-step handle and its host staging (optional; the process exit does it too) */
+int vio_lockstep_release(void) {
+    LockstepCache &cache = g_lockstep;
+    std::lock_guard<std::mutex> lock(cache.mu);
+    if (cache.handle) vio_destroy(cache.handle);
+    cache.handle = nullptr;
+    cache.device = -1;
+    std::vector<PackedGraph>().swap(cache.Ks);
+    cache.K = PackedGraph();
+    for (auto *v : {&cache.pose, &cache.sb, &cache.idt, &cache.idp, &cache.idq, &cache.idv, &cache.iba, &cache.ibg, &cache.ijac, &cache.icov})
+        std::vector<double>().swap(*v);
+    for (auto *v : {&cache.ipi, &cache.isi, &cache.ipj, &cache.isj}) std::vector<int32_t>().swap(*v);
+    return VIO_OK;
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -11,7 +11,12 @@
 
 struct DevView {
     // sizes
-    int C, NSB, L, P, NB;  // poses, speed-biases, landmarks, pose-class dim, pose-class blocks
+    int C, NSB, L, P, NB;  // poses, speed-biases, landmarks, pose-class dim (TOTAL over a lock-step batch), pose-class blocks
+    // lock-step batch of structurally identical problems (vio_solve_batched_lockstep): the reduced system is a "tall"
+    // dense matrix of `batch` stacked Pper x Pper blocks; pose_off / sb_off are GLOBAL row offsets.  batch = 1, Pper = P otherwise.
+    int batch, Pper, Cper, NSBper;
+    const int *lm_prob;      // [L] problem of each landmark (batch only)
+    const uint8_t *act;      // [batch] per-problem mask for the update / restore kernels, or nullptr
     long long E;           // reprojection edges (local shard)
     int storage;           // 1 dense, 2 bsr
     long long nnzb;

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) k_imu_linearize(ImuView s, DevView v) {
         if (ga < 0 || gc < 0 || ga > gc) continue;
         double acc = 0.0;
         for (int k = 0; k < 15; ++k) acc += J[30 * k + a] * OJ[30 * k + c];
-        atomicAdd(v.S + (size_t)ga * v.P + gc, acc);
+        atomicAdd(v.S + (size_t)ga * v.Pper + (gc % v.Pper), acc);
         if (ga == gc) atomicAdd(v.hdiag + ga, acc);
     }
     if (threadIdx.x < 30 && gidx[threadIdx.x] >= 0) {
@@ -297,9 +297,10 @@ inline void imu_chi2(const ImuBuffers &b, const DevView &v, const double G[3], d
 // Hessian_.topLeft += H_prior with rows/cols of fixed pose-class vertices zeroed; b_.head += b_prior (masked)
 __global__ void k_add_dense_prior(DevView v, const double *Hp, const double *bp, const uint8_t *row_fixed) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n = (long long)v.P * v.P;
+    const long long n = (long long)v.P * v.Pper;  // tall: P (total rows) x Pper
     if (t >= n) return;
-    const int r = (int)(t / v.P), c = (int)(t % v.P);
+    const int r = (int)(t / v.Pper), cl = (int)(t % v.Pper);
+    const int c = (r / v.Pper) * v.Pper + cl;  // global index of the column inside the row's problem
     if (r > c || row_fixed[r] || row_fixed[c]) return;
     const double h = Hp[t];
     v.S[t] += h;  // exclusive element ownership within this kernel; edge kernels ran earlier on the stream

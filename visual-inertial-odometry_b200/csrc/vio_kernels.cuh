@@ -108,8 +108,8 @@ __global__ void k_pose_prep(DevView v) {
 // Pointer to element (0,0) of the 6x6 block (pose a, pose b) with ordering offset(a) <= offset(b).
 VIO_HD double *s_block(const DevView &v, int a, int b, int &ld) {
     if (v.storage == 1) {
-        ld = v.P;
-        return v.S + (size_t)v.pose_off[a] * v.P + v.pose_off[b];
+        ld = v.Pper;
+        return v.S + (size_t)v.pose_off[a] * v.Pper + (v.pose_off[b] % v.Pper);
     }
     ld = 6;
     const int ra = v.pose_blk[a], cb = v.pose_blk[b];
@@ -542,9 +542,10 @@ __global__ void __launch_bounds__(256) k_chi2_lm(DevView v, double *partial) {
 // ------------------------------------------------------------------------------------------------
 // finalize reduced system after (all-reduced) accumulation: mirror the upper triangle, bS = bp - bcorr
 // ------------------------------------------------------------------------------------------------
-__global__ void k_mirror_dense(double *S, int P) {
+__global__ void k_mirror_dense(double *S, int P) {  // gridDim.z = number of stacked P x P problems
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    S += (size_t)blockIdx.z * P * P;
     if (r < P && c < P && r > c) S[(size_t)r * P + c] = S[(size_t)c * P + r];
 }
 __global__ void k_mirror_bsr(DevView v) {
@@ -624,6 +625,7 @@ __global__ void __launch_bounds__(256) k_pose_scale(DevView v, double lambda, do
 
 // UpdateStates: backup + Plus.  sign = +1 (update) ; v15 rollback calls it again with sign = -1, no backup.
 VIO_HD void update_pose(const DevView &v, int i, double sign, int backup) {
+    if (v.act && !v.act[i / v.Cper]) return;  // lock-step batch: this problem is not taking a step
     double *p = v.pose + 7 * (size_t)i;
     if (backup) {
         double *b = v.pose_bak + 7 * (size_t)i;
@@ -645,6 +647,7 @@ __global__ void k_update_pose(DevView v, double sign, int backup) {
 __global__ void k_update_sb(DevView v, double sign, int backup) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= v.NSB) return;
+    if (v.act && !v.act[i / v.NSBper]) return;
     double *p = v.sb + 9 * (size_t)i;
     const double *d = v.dxp + v.sb_off[i];
 #pragma unroll
@@ -656,12 +659,13 @@ __global__ void k_update_sb(DevView v, double sign, int backup) {
 __global__ void k_update_lm(DevView v, double sign, int backup) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= v.L) return;
+    if (v.act && !v.act[v.lm_prob[l]]) return;
     if (backup) v.invdep_bak[l] = v.invdep[l];
     v.invdep[l] += sign * v.dxl[l];
 }
-__global__ void k_restore(DevView v) {
+__global__ void k_restore(DevView v) {  // v.act (batch): restore only the problems whose step was rejected
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < (long long)v.C * 7) v.pose[t] = v.pose_bak[t];
-    if (t < (long long)v.NSB * 9) v.sb[t] = v.sb_bak[t];
-    if (t < v.L) v.invdep[t] = v.invdep_bak[t];
+    if (t < (long long)v.C * 7 && (!v.act || v.act[(t / 7) / v.Cper])) v.pose[t] = v.pose_bak[t];
+    if (t < (long long)v.NSB * 9 && (!v.act || v.act[(t / 9) / v.NSBper])) v.sb[t] = v.sb_bak[t];
+    if (t < v.L && (!v.act || v.act[v.lm_prob[t]])) v.invdep[t] = v.invdep_bak[t];
 }

@@ -16,6 +16,7 @@
 
 struct PackedGraph {
     int C = 0, NSB = 0, NB = 0, P = 0, L = 0, Lglobal = 0, storage = 1;
+    int batch = 1, Pper = 0;  // lock-step batch: `batch` stacked Pper x Pper reduced systems (dense), P = batch * Pper
     long long E = 0, nnzb = 0;
     size_t s_count = 0;
     std::vector<int> pose_off, sb_off, pose_blk, blk_off, blk_dim;
@@ -45,7 +46,7 @@ inline int pack_fail(std::string &err, int code, const char *fmt, ...) {
     return code;
 }
 
-inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, PackedGraph &K, std::string &err) {
+inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, PackedGraph &K, std::string &err, int batch = 1) {
     const int C = g->n_pose, NSB = g->n_speedbias, Lg = g->n_landmark;
     const long long Eg = g->n_reproj;
     if (C < 0 || NSB < 0 || Lg < 0 || Eg < 0) return pack_fail(err, VIO_ERR_INVALID, "negative size");
@@ -161,9 +162,12 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     long long nnzb = 0;
     std::vector<int> &rowptr = K.rowptr, &col = K.col, &tr = K.tr, &diag = K.diag;
     rowptr.clear(); col.clear(); tr.clear(); diag.clear();
+    if (batch < 1 || P % batch != 0) return pack_fail(err, VIO_ERR_INVALID, "batch %d does not divide P=%d", batch, P);
+    const int Pper = P / batch;
+    if (batch > 1 && storage != VIO_STORAGE_DENSE) return pack_fail(err, VIO_ERR_UNSUPPORTED, "lock-step batches use dense storage");
     if (storage == VIO_STORAGE_DENSE) {
-        if ((size_t)P * P * sizeof(double) > (size_t)16 << 30) return pack_fail(err, VIO_ERR_UNSUPPORTED, "dense S too large");
-        s_count = (size_t)P * P;
+        if ((size_t)P * Pper * sizeof(double) > (size_t)16 << 30) return pack_fail(err, VIO_ERR_UNSUPPORTED, "dense S too large");
+        s_count = (size_t)P * Pper;
     } else {
         // global pattern (all shards must agree): co-visibility of every landmark + diagonal
         std::vector<std::vector<int>> rows(NB);
@@ -216,7 +220,11 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
             return dbl * 8 + (3 * (size_t)ns + 2 * npairs) * 4;
         };
         auto block_off = [&](int pa, int pb, long long &off) -> bool {  // element offset of block (pa,pb) in S storage
-            if (storage == VIO_STORAGE_DENSE) { off = (long long)pose_off[pa] * P + pose_off[pb]; return true; }
+            if (storage == VIO_STORAGE_DENSE) {
+                if (pose_off[pa] / Pper != pose_off[pb] / Pper) return false;  // blocks never couple two problems of a batch
+                off = (long long)pose_off[pa] * Pper + pose_off[pb] % Pper;
+                return true;
+            }
             const int ra = pose_blk[pa], cb = pose_blk[pb];
             auto it = std::lower_bound(col.begin() + rowptr[ra], col.begin() + rowptr[ra + 1], cb);
             if (it == col.begin() + rowptr[ra + 1] || *it != cb) return false;
@@ -318,7 +326,7 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     }
 
     K.C = C; K.NSB = NSB; K.NB = NB; K.P = P; K.L = L; K.Lglobal = Lg; K.E = E; K.storage = storage; K.nnzb = nnzb;
-    K.s_count = s_count;
+    K.s_count = s_count; K.batch = batch; K.Pper = Pper;
     K.pose_fixed.assign(C, 0); K.sb_fixed.assign(NSB, 0);
     if (g->pose_fixed) K.pose_fixed.assign(g->pose_fixed, g->pose_fixed + C);
     if (g->speedbias_fixed) K.sb_fixed.assign(g->speedbias_fixed, g->speedbias_fixed + NSB);
@@ -329,3 +337,102 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         if (g->sp_pose[i] < 0 || g->sp_pose[i] >= C) return pack_fail(err, VIO_ERR_INVALID, "se3 prior %d: pose out of range", i);
     return VIO_OK;
 }
+
+// ---- lock-step batches -------------------------------------------------------------------------------------------
+// Merge per-item packs (same C / NSB / pose-class order, dense storage, unsharded) into ONE packed graph whose reduced
+// system is `B` stacked Pper x Pper blocks: pose-class offsets of item k are shifted by k*Pper, pose / speed-bias /
+// landmark / edge indices by the item prefix sums.  `fill(k0, k1)` may be called from several threads on disjoint item
+// ranges after `prepare`.
+struct PackedMerge {
+    const std::vector<PackedGraph> *Ks = nullptr;
+    PackedGraph *M = nullptr;
+    std::vector<long long> Lb, Eb, Gb, Sb, Pb, Xb;  // prefix sums: landmarks, edges, groups, slots, pairs, ELL entries
+    int C = 0, NSB = 0, NBper = 0, Pper = 0;
+
+    int prepare(const std::vector<PackedGraph> &ks, PackedGraph &m, std::string &err) {
+        Ks = &ks; M = &m;
+        const int B = (int)ks.size();
+        C = ks[0].C; NSB = ks[0].NSB; NBper = ks[0].NB; Pper = ks[0].P;
+        Lb.assign(B + 1, 0); Eb.assign(B + 1, 0); Gb.assign(B + 1, 0); Sb.assign(B + 1, 0); Pb.assign(B + 1, 0); Xb.assign(B + 1, 0);
+        bool grouped = true;
+        int threads = 0;
+        size_t smem = 0;
+        for (int k = 0; k < B; ++k) {
+            const PackedGraph &K = ks[k];
+            if (K.C != C || K.NSB != NSB || K.P != Pper || K.storage != VIO_STORAGE_DENSE || K.L != K.Lglobal)
+                return pack_fail(err, VIO_ERR_UNSUPPORTED, "item %d: pose-class structure differs inside a lock-step batch", k);
+            Lb[k + 1] = Lb[k] + K.L; Eb[k + 1] = Eb[k] + K.E;
+            const bool gk = K.grouped_ok || K.E == 0;
+            grouped = grouped && gk;
+            const long long ng = K.grouped_ok ? K.n_groups : 0;
+            Gb[k + 1] = Gb[k] + ng; Sb[k + 1] = Sb[k] + (K.grouped_ok ? (long long)K.g_slot_pose.size() : 0);
+            Pb[k + 1] = Pb[k] + (K.grouped_ok ? (long long)K.g_pairinfo.size() : 0);
+            Xb[k + 1] = Xb[k] + (K.grouped_ok ? (long long)K.ell_pjx.size() : 0);
+            if (K.grouped_ok) { threads = std::max(threads, K.group_threads); smem = std::max(smem, K.group_smem_max); }
+        }
+        if (Lb[B] > 0x7fffffffLL || Eb[B] > 0x7fffffffLL || Xb[B] > 0x7fffffffLL || (long long)B * Pper > 0x7fffffffLL ||
+            (long long)B * Pper * Pper > (1LL << 40))
+            return pack_fail(err, VIO_ERR_UNSUPPORTED, "lock-step batch too large");
+        m.C = B * C; m.NSB = B * NSB; m.NB = B * NBper; m.P = B * Pper; m.L = (int)Lb[B]; m.Lglobal = m.L; m.E = Eb[B];
+        m.storage = VIO_STORAGE_DENSE; m.nnzb = 0; m.batch = B; m.Pper = Pper; m.s_count = (size_t)m.P * Pper;
+        for (int q = 0; q < 4; ++q) m.qic[q] = ks[0].qic[q];
+        for (int q = 0; q < 3; ++q) m.tic[q] = ks[0].tic[q];
+        m.pose_off.resize(m.C); m.sb_off.resize(m.NSB); m.pose_blk.resize(m.C); m.blk_off.resize(m.NB); m.blk_dim.resize(m.NB);
+        m.blk_fixed.resize(m.NB); m.pose_fixed.resize(m.C); m.sb_fixed.resize(m.NSB); m.row_fixed.resize(m.P);
+        m.lm_global.resize(m.L); m.lm_host.resize(m.L); m.lm_eptr.resize((size_t)m.L + 1); m.e_pose_j.resize(m.E);
+        m.pix.resize(m.L); m.piy.resize(m.L); m.piz.resize(m.L); m.invd.resize(m.L); m.pjx.resize(m.E); m.pjy.resize(m.E);
+        m.lm_eptr[m.L] = (int)m.E;
+        m.rowptr.clear(); m.col.clear(); m.tr.clear(); m.diag.clear();
+        m.grouped_ok = grouped && Gb[B] > 0;
+        m.n_groups = m.grouped_ok ? (int)Gb[B] : 0; m.group_threads = threads; m.group_smem_max = smem;
+        if (m.grouped_ok) {
+            m.g_hdr.resize(8 * (size_t)Gb[B]); m.g_slot_pose.resize(Sb[B]); m.g_pairinfo.resize(Pb[B]);
+            m.ell_pjx.resize(Xb[B]); m.ell_pjy.resize(Xb[B]); m.ell_edge.resize(Xb[B]);
+        } else {
+            m.g_hdr.clear(); m.g_slot_pose.clear(); m.g_pairinfo.clear(); m.ell_pjx.clear(); m.ell_pjy.clear(); m.ell_edge.clear();
+        }
+        return VIO_OK;
+    }
+
+    void fill(int k0, int k1) const {
+        PackedGraph &m = *M;
+        for (int k = k0; k < k1; ++k) {
+            const PackedGraph &K = (*Ks)[k];
+            const int c0 = k * C, s0 = k * NSB, b0 = k * NBper, r0 = k * Pper;
+            const int l0 = (int)Lb[k], e0 = (int)Eb[k];
+            for (int i = 0; i < C; ++i) {
+                m.pose_off[c0 + i] = K.pose_off[i] + r0; m.pose_blk[c0 + i] = K.pose_blk[i] + b0; m.pose_fixed[c0 + i] = K.pose_fixed[i];
+            }
+            for (int i = 0; i < NSB; ++i) { m.sb_off[s0 + i] = K.sb_off[i] + r0; m.sb_fixed[s0 + i] = K.sb_fixed[i]; }
+            for (int i = 0; i < NBper; ++i) {
+                m.blk_off[b0 + i] = K.blk_off[i] + r0; m.blk_dim[b0 + i] = K.blk_dim[i]; m.blk_fixed[b0 + i] = K.blk_fixed[i];
+            }
+            for (int i = 0; i < Pper; ++i) m.row_fixed[r0 + i] = K.row_fixed[i];
+            for (int l = 0; l < K.L; ++l) {
+                m.lm_global[l0 + l] = K.lm_global[l] + l0; m.lm_host[l0 + l] = K.lm_host[l] + c0; m.lm_eptr[l0 + l] = K.lm_eptr[l] + e0;
+            }
+            if (K.L) {
+                std::copy(K.pix.begin(), K.pix.end(), m.pix.begin() + l0); std::copy(K.piy.begin(), K.piy.end(), m.piy.begin() + l0);
+                std::copy(K.piz.begin(), K.piz.end(), m.piz.begin() + l0); std::copy(K.invd.begin(), K.invd.end(), m.invd.begin() + l0);
+            }
+            for (long long e = 0; e < K.E; ++e) m.e_pose_j[e0 + e] = K.e_pose_j[e] + c0;
+            if (K.E) { std::copy(K.pjx.begin(), K.pjx.end(), m.pjx.begin() + e0); std::copy(K.pjy.begin(), K.pjy.end(), m.pjy.begin() + e0); }
+            if (!m.grouped_ok || !K.grouped_ok) continue;
+            const int gb = (int)Gb[k], sb = (int)Sb[k], pb = (int)Pb[k], xb = (int)Xb[k];
+            for (int gi = 0; gi < K.n_groups; ++gi) {
+                const int *h = &K.g_hdr[8 * (size_t)gi];
+                int *o = &m.g_hdr[8 * (size_t)(gb + gi)];
+                o[0] = h[0] + c0; o[1] = h[1]; o[2] = h[2] + l0; o[3] = h[3]; o[4] = h[4] + xb; o[5] = h[5] + pb; o[6] = h[6] + sb; o[7] = h[7];
+            }
+            for (size_t i = 0; i < K.g_slot_pose.size(); ++i) m.g_slot_pose[sb + i] = K.g_slot_pose[i] + c0;
+            const long long blk_shift = (long long)r0 * Pper;  // (pose_off + k Pper) * Pper + col  =  off + k Pper^2
+            for (size_t i = 0; i < K.g_pairinfo.size(); ++i) {
+                const long long info = K.g_pairinfo[i];
+                m.g_pairinfo[pb + i] = (info & 3) == 3 ? info : (((info >> 2) + blk_shift) << 2) | (info & 3);
+            }
+            std::copy(K.ell_pjx.begin(), K.ell_pjx.end(), m.ell_pjx.begin() + xb);
+            std::copy(K.ell_pjy.begin(), K.ell_pjy.end(), m.ell_pjy.begin() + xb);
+            for (size_t i = 0; i < K.ell_edge.size(); ++i) m.ell_edge[xb + i] = K.ell_edge[i] < 0 ? -1 : K.ell_edge[i] + e0;
+        }
+    }
+};
