@@ -50,7 +50,10 @@ enum {
     VIO_SOLVER_DENSE_CHOL = 1, /* v17: S.ldlt().solve  (A17/src/backend/problem.cc:439)      */
     VIO_SOLVER_REF_PCG = 2,    /* v15: PCGSolver incl. its missing first x update
                                   (A15/backend/problem.cc:530-560)                          */
-    VIO_SOLVER_BLOCK_PCG = 3   /* large BA: 6x6 block-Jacobi PCG on block-sparse S           */
+    VIO_SOLVER_BLOCK_PCG = 3,  /* large BA: 6x6 block-Jacobi PCG on block-sparse S           */
+    VIO_SOLVER_BLOCK_PCG_2L = 4 /* the same PCG with a two-level preconditioner: block-Jacobi + Galerkin coarse
+                                  correction over aggregates of consecutive pose blocks (camera chains).
+                                  AUTO picks it for block-sparse S with >= 256 pose blocks.              */
 };
 enum { VIO_LOSS_TRIVIAL = 0, VIO_LOSS_HUBER = 1, VIO_LOSS_CAUCHY = 2, VIO_LOSS_TUKEY = 3 };
 enum { VIO_STORAGE_AUTO = 0, VIO_STORAGE_DENSE = 1, VIO_STORAGE_BSR = 2 };
@@ -208,6 +211,9 @@ int vio_get_hessian(vio_problem *p, const vio_lm_opts *opts, double *H /* (P+M)^
 int vio_get_schur(vio_problem *p, double *S /* P*P row-major */, double *bS /* P */);
 /* block-sparse view of the same (BSR storage only)                                          */
 int vio_get_schur_bsr(vio_problem *p, int32_t *rowptr /* nb+1 */, int32_t *col /* nnzb */, double *val /* nnzb*36 */, double *bS);
+/* debug tap on the two-level PCG preconditioner of the last solve: coarse dimension, block rows per aggregate, the
+ * explicit coarse inverse (nc x nc) and the basis Z ([pose block][6][7]); VIO_ERR_STATE if the last solve did not use it. */
+int vio_get_coarse(vio_problem *p, int32_t *nc, int32_t *rows_per_aggregate, double *Ainv, double *Z);
 int vio_get_delta(vio_problem *p, double *dx_pose /* P */, double *dx_landmark /* M */);
 int vio_get_b(vio_problem *p, double *b_pose /* P */, double *b_landmark /* M */);
 int vio_get_landmark_diag(vio_problem *p, double *Hmm /* M */);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libvio_b200.so")
 VIO_OK = 0
 ERR_NAMES = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "UNSUPPORTED", 4: "EMPTY", 5: "NO_DEVICE", 6: "STATE"}
 LM_V15, LM_V17 = 0, 1
-SOLVER_AUTO, SOLVER_DENSE_CHOL, SOLVER_REF_PCG, SOLVER_BLOCK_PCG = 0, 1, 2, 3
+SOLVER_AUTO, SOLVER_DENSE_CHOL, SOLVER_REF_PCG, SOLVER_BLOCK_PCG, SOLVER_BLOCK_PCG_2L = 0, 1, 2, 3, 4
 LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY, LOSS_TUKEY = 0, 1, 2, 3
 STORAGE_AUTO, STORAGE_DENSE, STORAGE_BSR = 0, 1, 2
 TRACE_MAX = 256
@@ -87,7 +87,7 @@ EXPORTS = [
     "vio_solve", "vio_linearize", "vio_chi2", "vio_solve_step", "vio_apply_step", "vio_rollback_step",
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
     "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
-    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_marginalize",
+    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_get_coarse", "vio_marginalize",
 ]
 
 _lib = None
@@ -445,6 +445,15 @@ class Problem:
         dl = np.zeros(d.M)
         self._ck(self._L.vio_get_delta(self._h, _d(dp), _d(dl) if d.M else None))
         return dp, dl
+
+    def get_coarse(self):
+        nc, ma = C.c_int32(), C.c_int32()
+        self._ck(self._L.vio_get_coarse(self._h, C.byref(nc), C.byref(ma), None, None))
+        nb = self.dims().n_pose_blocks
+        A = np.zeros((nc.value, nc.value))
+        Z = np.zeros((nb, 6, 7))
+        self._ck(self._L.vio_get_coarse(self._h, None, None, _d(A), _d(Z)))
+        return ma.value, A, Z
 
     def get_b(self):
         d = self.dims()

@@ -109,6 +109,11 @@ struct vio_problem {
     DBuf<double> gen_J, gen_r, gen_W, gen_Wb, gen_H, gen_b, gen_dx, gen_work;
     DBuf<int> gen_e0, gen_dim, gen_kind;
     DBuf<int> pcg_colptr, pcg_cols, pcg_lcol;
+    // two-level preconditioner (CoarseView)
+    int cz_apc = 0, cz_ma = 0, cz_nc = 0, cz_ncb = 0, cz_rp = 0, cz_grid = 0, cz_na = 0;
+    size_t cz_smem = 0;
+    DBuf<int> cz_ptr, cz_fine, cz_frow, cz_row, cz_col, cz_aggptr, cz_blkpose;
+    DBuf<double> cz_A, cz_rowbuf, cz_rc, cz_Z;
     int pcg_grid = -1, pcg_br = 0, pcg_win = 0;
     size_t pcg_smem = 0;
     DBuf<unsigned long long> prof;
@@ -193,7 +198,8 @@ vio_lm_opts default_opts() {
 
 int resolve_solver(const vio_problem *p, const vio_lm_opts &o) {
     if (o.solver != VIO_SOLVER_AUTO) return o.solver;
-    if (p->storage == VIO_STORAGE_BSR) return VIO_SOLVER_BLOCK_PCG;
+    if (p->storage == VIO_STORAGE_BSR)
+        return (p->NB >= 256 && p->coop_ok && !getenv("VIO_B200_PCG_PLAIN")) ? VIO_SOLVER_BLOCK_PCG_2L : VIO_SOLVER_BLOCK_PCG;
     return o.flavour == VIO_LM_V15 ? VIO_SOLVER_REF_PCG : VIO_SOLVER_DENSE_CHOL;
 }
 
@@ -362,7 +368,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             CK(cudaStreamSynchronize(p->stream));
             *pcg_iters = it;
         }
-    } else if (solver == VIO_SOLVER_BLOCK_PCG) {
+    } else if (solver == VIO_SOLVER_BLOCK_PCG || solver == VIO_SOLVER_BLOCK_PCG_2L) {
         if (p->storage != VIO_STORAGE_BSR) return fail(p, VIO_ERR_INVALID, "block PCG needs BSR storage");
         const int nb = p->NB;
         if (p->bpcg_x.n < (size_t)P) {
@@ -385,7 +391,19 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         bool done_persistent = false;
         if (p->coop_ok && !getenv("VIO_B200_PCG_MULTIKERNEL")) {
             // one cooperative launch: grid sized to be co-resident (2 CTAs per SM at most)
-            const int grid = std::max(1, std::min(std::min(p->num_sms, BPCG_MAXPART), (nb + 15) / 16));
+            int grid = std::max(1, std::min(std::min(p->num_sms, BPCG_MAXPART), (nb + 15) / 16));
+            // two-level preconditioner: apc aggregates per CTA of >= 16 block rows; the coarse inversion keeps 7*apc rows of
+            // the (7*grid*apc)^2 coarse matrix per CTA in shared memory, which caps grid * apc^2 (a slightly smaller grid
+            // is accepted for that)
+            int apc_sel = 0;
+            {
+                const size_t budget = 224 * 1024;
+                for (int apc = std::max(1, std::min(4, ((nb + grid - 1) / grid) / 16)); apc >= 1; --apc) {
+                    const int cap = (int)(budget / (8 * CZ_KD * CZ_KD * (size_t)apc * apc));
+                    if (cap >= grid) { apc_sel = apc; break; }
+                    if (cap * 10 >= grid * 9) { apc_sel = apc; grid = cap; break; }
+                }
+            }
             const int brc = (nb + grid - 1) / grid;
             if (p->pcg_grid != grid) {
                 // per-CTA column windows + local block indices (host, once per graph)
@@ -411,6 +429,59 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                 p->pcg_smem = ((size_t)6 * win_max + (size_t)5 * 6 * brc + (size_t)36 * brc) * sizeof(double);
                 if (p->pcg_smem <= 200 * 1024)
                     CK(cudaFuncSetAttribute(k_bpcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->pcg_smem));
+                // ---- aggregates of the two-level preconditioner: each CTA's rows split into apc chunks of ma rows
+                {
+                    const int apc = std::max(1, apc_sel);
+                    const int nc_ = CZ_KD * grid * apc, ma = (brc + apc - 1) / apc, na = grid * apc;
+                    const size_t smem2 = p->pcg_smem + (size_t)6 * CZ_KD * brc * sizeof(double);
+                    const size_t inv_smem = (size_t)CZ_KD * apc * nc_ * sizeof(double);
+                    p->cz_apc = (apc_sel > 0 && inv_smem <= 224 * 1024 && smem2 <= 200 * 1024 && (int)p->h_pose_off.size() >= nb) ? apc : 0;
+                    if (p->cz_apc > 0) {
+                        auto agg_of = [&](int i) { const int c = i / brc, ib = i - c * brc; return c * apc + std::min(apc - 1, ib / ma); };
+                        std::vector<int> aptr(na + 1, 0), blk_pose(nb, 0);
+                        for (int i = 0; i < nb; ++i) aptr[agg_of(i) + 1]++;
+                        for (int a2 = 0; a2 < na; ++a2) aptr[a2 + 1] += aptr[a2];
+                        for (size_t pi = 0; pi < p->h_pose_off.size(); ++pi) blk_pose[p->h_pose_off[pi] / 6] = (int)pi;
+                        // coarse pattern + the fine blocks behind every coarse block, in CSR order of the fine matrix
+                        typedef std::pair<int, std::vector<std::pair<int, int>>> CEntry;  // coarse column, (fine block, fine row)
+                        std::vector<std::vector<CEntry>> crow(na);
+                        for (int i = 0; i < nb; ++i) {
+                            auto &row = crow[agg_of(i)];
+                            for (int k = p->h_rowptr[i]; k < p->h_rowptr[i + 1]; ++k) {
+                                const int b2 = agg_of(p->h_col[k]);
+                                auto it = std::find_if(row.begin(), row.end(), [&](const CEntry &e) { return e.first == b2; });
+                                if (it == row.end()) { row.emplace_back(b2, std::vector<std::pair<int, int>>()); it = row.end() - 1; }
+                                it->second.emplace_back(k, i);
+                            }
+                        }
+                        std::vector<int> cptr(1, 0), cfine, cfrow, crw, ccl;
+                        for (int a2 = 0; a2 < na; ++a2) {
+                            auto &row = crow[a2];
+                            if (std::find_if(row.begin(), row.end(), [&](const CEntry &e) { return e.first == a2; }) == row.end())
+                                row.emplace_back(a2, std::vector<std::pair<int, int>>());  // diagonal of an empty aggregate
+                            std::sort(row.begin(), row.end(), [](const CEntry &x, const CEntry &y) { return x.first < y.first; });
+                            for (auto &e : row) {
+                                crw.push_back(a2); ccl.push_back(e.first);
+                                for (auto &fk : e.second) { cfine.push_back(fk.first); cfrow.push_back(fk.second); }
+                                cptr.push_back((int)cfine.size());
+                            }
+                        }
+                        if (cfine.empty()) { cfine.push_back(0); cfrow.push_back(0); }
+                        CK(upload(p->cz_ptr, cptr.data(), cptr.size(), p->stream)); CK(upload(p->cz_fine, cfine.data(), cfine.size(), p->stream));
+                        CK(upload(p->cz_frow, cfrow.data(), cfrow.size(), p->stream));
+                        CK(upload(p->cz_row, crw.data(), crw.size(), p->stream)); CK(upload(p->cz_col, ccl.data(), ccl.size(), p->stream));
+                        CK(upload(p->cz_aggptr, aptr.data(), aptr.size(), p->stream)); CK(upload(p->cz_blkpose, blk_pose.data(), blk_pose.size(), p->stream));
+                        CK(cudaStreamSynchronize(p->stream));
+                        p->cz_ma = ma; p->cz_nc = nc_; p->cz_ncb = (int)crw.size(); p->cz_na = na;
+                        p->cz_rp = apc;  // coarse block rows per CTA of the inversion kernel
+                        p->cz_grid = grid;
+                        p->cz_smem = inv_smem;
+                        CK(p->cz_A.alloc((size_t)nc_ * nc_)); CK(p->cz_rowbuf.alloc(2 * (size_t)CZ_KD * nc_)); CK(p->cz_rc.alloc(nc_));
+                        CK(p->cz_Z.alloc((size_t)6 * CZ_KD * nb));
+                        CK(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->cz_smem));
+                        CK(cudaFuncSetAttribute(k_bpcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                    }
+                }
             }
             if (p->bar.n < 2) CK(p->bar.alloc(2));
             if (p->bpcg_p2.n < (size_t)P) CK(p->bpcg_p2.alloc(P));
@@ -423,9 +494,32 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             int n_init = g_init;
             k_bpcg_init<<<g_init, 256, 0, p->stream>>>(s);
             p->launches++;
-            void *args[] = {(void *)&s, (void *)&tb, (void *)&mi, (void *)&barp, (void *)&p2, (void *)&n_init};
+            CoarseView cv;
+            memset(&cv, 0, sizeof(cv));
             cudaError_t ce = p->pcg_smem <= 200 * 1024 ? cudaSuccess : cudaErrorInvalidValue;
-            if (ce == cudaSuccess) ce = cudaLaunchCooperativeKernel((void *)k_bpcg_persistent, dim3(grid), dim3(BPCG_P_THREADS), args, p->pcg_smem, p->stream);
+            if (solver == VIO_SOLVER_BLOCK_PCG_2L && p->cz_apc > 0 && ce == cudaSuccess) {
+                // Z at the linearisation state ; Ac = Z^T (S + lambda I) Z, inverted in place
+                const int nc_ = p->cz_nc;
+                k_coarse_basis<<<p->cz_na, 64, 0, p->stream>>>(v.pose, v.pose_fixed, p->cz_blkpose.p, p->cz_aggptr.p, p->cz_Z.p);
+                CK(cudaMemsetAsync(p->cz_A.p, 0, (size_t)nc_ * nc_ * sizeof(double), p->stream));
+                k_coarse_assemble<<<p->cz_ncb, 784, 0, p->stream>>>(v.S, v.bsr_col, p->cz_ptr.p, p->cz_fine.p, p->cz_frow.p, p->cz_row.p,
+                                                                    p->cz_col.p, p->cz_aggptr.p, p->cz_Z.p, lambda, nc_, p->cz_A.p);
+                double *Ap = p->cz_A.p, *rbuf = p->cz_rowbuf.p;
+                int ncv = nc_, rpv = p->cz_rp;
+                void *iargs[] = {(void *)&Ap, (void *)&ncv, (void *)&rpv, (void *)&rbuf, (void *)&barp};
+                ce = cudaLaunchCooperativeKernel((void *)k_coarse_invert, dim3(p->cz_grid), dim3(1024), iargs, p->cz_smem, p->stream);
+                if (ce == cudaSuccess) {
+                    p->launches += 3;
+                    CK(cudaMemsetAsync(p->bar.p, 0, 2 * sizeof(unsigned), p->stream));
+                    cv.apc = p->cz_apc; cv.ma = p->cz_ma; cv.nc = nc_; cv.Ainv = p->cz_A.p; cv.rc = p->cz_rc.p; cv.Z = p->cz_Z.p;
+                } else {
+                    (void)cudaGetLastError();
+                    ce = cudaSuccess;  // plain block-Jacobi below
+                }
+            }
+            void *args[] = {(void *)&s, (void *)&tb, (void *)&mi, (void *)&barp, (void *)&p2, (void *)&n_init, (void *)&cv};
+            if (ce == cudaSuccess) ce = cudaLaunchCooperativeKernel((void *)k_bpcg_persistent, dim3(grid), dim3(BPCG_P_THREADS), args,
+                                                                        p->pcg_smem + (cv.apc > 0 ? (size_t)6 * CZ_KD * p->pcg_br * sizeof(double) : 0), p->stream);
             if (ce == cudaSuccess) {
                 p->launches++;
                 done_persistent = true;
@@ -1043,6 +1137,17 @@ int vio_get_schur_bsr(vio_problem *p, int32_t *rowptr, int32_t *col, double *val
     if (col) memcpy(col, p->h_col.data(), p->h_col.size() * sizeof(int));
     if (val) CK(cudaMemcpyAsync(val, p->sys.p, p->s_count * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (bS) CK(cudaMemcpyAsync(bS, p->bS.p, p->P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
+/* debug tap: the two-level preconditioner of the last block-PCG solve (coarse inverse nc x nc, basis Z [nb][6][7]) */
+int vio_get_coarse(vio_problem *p, int32_t *nc, int32_t *rows_per_aggregate, double *Ainv, double *Z) {
+    if (!p || !p->has_graph || p->cz_apc == 0 || p->cz_A.n == 0) return VIO_ERR_STATE;
+    if (nc) *nc = p->cz_nc;
+    if (rows_per_aggregate) *rows_per_aggregate = p->cz_ma;
+    if (Ainv) CK(cudaMemcpyAsync(Ainv, p->cz_A.p, (size_t)p->cz_nc * p->cz_nc * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (Z) CK(cudaMemcpyAsync(Z, p->cz_Z.p, p->cz_Z.n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return VIO_OK;
 }

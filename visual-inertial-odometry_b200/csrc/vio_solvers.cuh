@@ -397,6 +397,206 @@ __device__ __forceinline__ double sum_partials_cg(const double *part, int n, dou
     return cta_sum(t, red);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Two-level preconditioner for the block PCG:  M^-1 = blockdiag(S + lambda I)^-1  +  Z Ac^-1 Z^T.
+// The coarse space is built from AGGREGATES of consecutive pose blocks (each CTA of the persistent PCG kernel splits its
+// own block rows into `apc` aggregates, so restriction and prolongation are CTA-local).  On every aggregate Z holds the
+// seven infinitesimal similarity motions of the world frame restricted to the aggregate's cameras (translation, rotation
+// and scale about the aggregate's centroid - the gauge freedoms of bundle adjustment, i.e. the near-null space of S):
+//     d t_i = tau + omega x (p_i - c) + sigma (p_i - c),     d theta_i = R_i^T omega     (Plus is q <- q * Exp(d theta))
+// Ac = Z^T (S + lambda I) Z is the (7 na)^2 Galerkin coarse matrix, inverted explicitly once per trial step.
+// Block-Jacobi alone leaves the long-wavelength drift modes of a camera CHAIN (~25k iterations at 10k cameras); the
+// coarse space removes them.  Everything is summed in a fixed order: ranks that solve the same reduced system
+// redundantly stay bitwise equal.
+// ------------------------------------------------------------------------------------------------
+#define CZ_KD 7  // coarse degrees of freedom per aggregate
+struct CoarseView {
+    int apc;              // aggregates per PCG CTA; 0 = plain block-Jacobi
+    int ma;               // block rows per aggregate (last aggregate of a CTA may hold fewer)
+    int nc;               // coarse dimension = CZ_KD * grid * apc
+    const double *Ainv;   // nc x nc
+    const double *Z;      // [nb][6][CZ_KD]
+    double *rc;           // [nc] restricted residual
+};
+
+// Z_i of every pose block: one CTA per aggregate (blocks agg_ptr[a] .. agg_ptr[a+1])
+__global__ void __launch_bounds__(64) k_coarse_basis(const double *__restrict__ pose, const uint8_t *__restrict__ pose_fixed,
+                                                      const int *__restrict__ blk_pose, const int *__restrict__ agg_ptr,
+                                                      double *__restrict__ Z) {
+    __shared__ double c_s[3];
+    const int a = blockIdx.x, i0 = agg_ptr[a], i1 = agg_ptr[a + 1];
+    if (threadIdx.x == 0) {
+        double c[3] = {0, 0, 0};
+        int n = 0;
+        for (int i = i0; i < i1; ++i) {
+            const int pi = blk_pose[i];
+            if (pose_fixed[pi]) continue;
+            c[0] += pose[7 * (size_t)pi]; c[1] += pose[7 * (size_t)pi + 1]; c[2] += pose[7 * (size_t)pi + 2];
+            ++n;
+        }
+        const double inv = n > 0 ? 1.0 / n : 0.0;
+        c_s[0] = c[0] * inv; c_s[1] = c[1] * inv; c_s[2] = c[2] * inv;
+    }
+    __syncthreads();
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const int pi = blk_pose[i];
+        double *z = Z + 6 * CZ_KD * (size_t)i;
+        for (int k = 0; k < 6 * CZ_KD; ++k) z[k] = 0.0;
+        if (pose_fixed[pi]) continue;
+        const double *pp = pose + 7 * (size_t)pi;
+        const double d[3] = {pp[0] - c_s[0], pp[1] - c_s[1], pp[2] - c_s[2]};
+        double R[9];
+        quat_to_R(pp + 3, R);
+        // rows 0..2: [ I | -[d]x | d ]
+        z[0 * CZ_KD + 0] = 1.0; z[1 * CZ_KD + 1] = 1.0; z[2 * CZ_KD + 2] = 1.0;
+        z[0 * CZ_KD + 4] = d[2];  z[0 * CZ_KD + 5] = -d[1];
+        z[1 * CZ_KD + 3] = -d[2]; z[1 * CZ_KD + 5] = d[0];
+        z[2 * CZ_KD + 3] = d[1];  z[2 * CZ_KD + 4] = -d[0];
+        z[0 * CZ_KD + 6] = d[0]; z[1 * CZ_KD + 6] = d[1]; z[2 * CZ_KD + 6] = d[2];
+        // rows 3..5: [ 0 | R^T | 0 ]
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) z[(3 + r) * CZ_KD + 3 + c] = R[3 * c + r];
+    }
+}
+
+// Galerkin assembly, one CTA per coarse block (a, b): Ac_ab = sum over the fine blocks (i, j) listed by the host (fixed
+// order) of Z_i^T S_ij Z_j, plus lambda * sum_i Z_i^T Z_i on the diagonal blocks.  784 threads = 49 outputs x 16 lanes.
+__global__ void __launch_bounds__(784) k_coarse_assemble(const double *__restrict__ val, const int *__restrict__ bsr_col,
+                                                          const int *__restrict__ cb_ptr, const int *__restrict__ cb_fine,
+                                                          const int *__restrict__ cb_frow, const int *__restrict__ cb_row,
+                                                          const int *__restrict__ cb_col, const int *__restrict__ agg_ptr,
+                                                          const double *__restrict__ Z, double lambda, int nc, double *__restrict__ Ac) {
+    __shared__ double part[16][CZ_KD * CZ_KD];
+    const int cb = blockIdx.x, e = threadIdx.x % (CZ_KD * CZ_KD), g = threadIdx.x / (CZ_KD * CZ_KD);
+    const int r = e / CZ_KD, c = e % CZ_KD;
+    double acc = 0.0;
+    for (int q = cb_ptr[cb] + g; q < cb_ptr[cb + 1]; q += 16) {
+        const int k = cb_fine[q], i = cb_frow[q], j = bsr_col[k];
+        const double *V = val + 36 * (size_t)k, *Zi = Z + 6 * CZ_KD * (size_t)i, *Zj = Z + 6 * CZ_KD * (size_t)j;
+        double t = 0.0;
+#pragma unroll
+        for (int x = 0; x < 6; ++x) {
+            double u = 0.0;
+#pragma unroll
+            for (int y = 0; y < 6; ++y) u += __ldg(V + 6 * x + y) * __ldg(Zj + y * CZ_KD + c);
+            t += __ldg(Zi + x * CZ_KD + r) * u;
+        }
+        acc += t;
+    }
+    part[g][e] = acc;
+    __syncthreads();
+    if (g == 0) {
+        const int a = cb_row[cb], b = cb_col[cb];
+        double t = 0.0;
+        for (int q = 0; q < 16; ++q) t += part[q][e];
+        if (a == b) {
+            double zz = 0.0;
+            for (int i = agg_ptr[a]; i < agg_ptr[a + 1]; ++i) {
+                const double *Zi = Z + 6 * CZ_KD * (size_t)i;
+                for (int x = 0; x < 6; ++x) zz += Zi[x * CZ_KD + r] * Zi[x * CZ_KD + c];
+            }
+            t += lambda * zz;
+            if (r == c && !(t > 0.0)) t = 1.0;  // aggregate without free cameras: identity
+        }
+        Ac[(size_t)(CZ_KD * a + r) * nc + CZ_KD * b + c] = t;
+    }
+}
+
+// In-place BLOCK Gauss-Jordan inverse of the SPD coarse matrix (7x7 pivot blocks, no pivoting: every pivot block is a
+// Schur complement of an SPD matrix), cooperative launch.  CTA c keeps its `bpc` block rows (7*bpc scalar rows, all nc
+// columns) in shared memory.  Step k: the owner inverts the pivot block, scales its block row and publishes it (7 x nc
+// doubles, double buffered); one grid barrier; every CTA eliminates block column k from its rows, each thread taking
+// whole columns (7 pivot values from L2, reused for all own rows).  na barriers instead of nc.
+__device__ inline void inv7_spd(const double *A /* 7x7 row-major, ld */, int ld, double *Ai /* 7x7 dense */) {
+    double L[49], Li[49];
+    for (int i = 0; i < 49; ++i) { L[i] = 0.0; Li[i] = 0.0; }
+    for (int j = 0; j < 7; ++j) {
+        double d = A[j * ld + j];
+        for (int k = 0; k < j; ++k) d -= L[7 * j + k] * L[7 * j + k];
+        d = sqrt(d);
+        L[7 * j + j] = d;
+        for (int i = j + 1; i < 7; ++i) {
+            double t = A[i * ld + j];
+            for (int k = 0; k < j; ++k) t -= L[7 * i + k] * L[7 * j + k];
+            L[7 * i + j] = t / d;
+        }
+    }
+    for (int j = 0; j < 7; ++j) {  // Li = L^-1 (lower)
+        Li[7 * j + j] = 1.0 / L[7 * j + j];
+        for (int i = j + 1; i < 7; ++i) {
+            double t = 0.0;
+            for (int k = j; k < i; ++k) t -= L[7 * i + k] * Li[7 * k + j];
+            Li[7 * i + j] = t / L[7 * i + i];
+        }
+    }
+    for (int r = 0; r < 7; ++r)
+        for (int c = 0; c < 7; ++c) {
+            double t = 0.0;
+            for (int k = (r > c ? r : c); k < 7; ++k) t += Li[7 * k + r] * Li[7 * k + c];
+            Ai[7 * r + c] = t;
+        }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_coarse_invert(double *A, int nc, int bpc, double *rowbuf /* [2][7][nc] */, unsigned *bar) {
+    extern __shared__ double csm[];
+    double *rows = csm;  // [7*bpc][nc]
+    __shared__ double F[4 * CZ_KD][CZ_KD];  // own rows' block column k before the update (bpc <= 4)
+    __shared__ double Pm[CZ_KD * CZ_KD];
+    const int tid = threadIdx.x, nt = blockDim.x, nblk = gridDim.x;
+    const int na = nc / CZ_KD;
+    const int a0 = min(na, blockIdx.x * bpc), a1 = min(na, a0 + bpc);
+    const int r0 = CZ_KD * a0, nr = CZ_KD * (a1 - a0);
+    for (int t = tid; t < nr * nc; t += nt) rows[t] = A[(size_t)r0 * nc + t];
+    __syncthreads();
+    for (int k = 0; k < na; ++k) {
+        double *pub = rowbuf + (size_t)(k & 1) * CZ_KD * nc;
+        const int kc = CZ_KD * k;
+        if (k >= a0 && k < a1) {
+            double *rk = rows + (size_t)(CZ_KD * (k - a0)) * nc;  // the pivot block row (7 x nc)
+            if (tid == 0) inv7_spd(rk + kc, nc, Pm);
+            __syncthreads();
+            // row block <- P * row block (columns outside the pivot block), pivot block <- P
+            for (int j = tid; j < nc; j += nt) {
+                double v[CZ_KD], o[CZ_KD];
+#pragma unroll
+                for (int m = 0; m < CZ_KD; ++m) v[m] = rk[(size_t)m * nc + j];
+                const bool inpiv = j >= kc && j < kc + CZ_KD;
+#pragma unroll
+                for (int r = 0; r < CZ_KD; ++r) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int m = 0; m < CZ_KD; ++m) t += Pm[CZ_KD * r + m] * v[m];
+                    o[r] = inpiv ? Pm[CZ_KD * r + (j - kc)] : t;
+                }
+#pragma unroll
+                for (int r = 0; r < CZ_KD; ++r) { rk[(size_t)r * nc + j] = o[r]; __stcg(pub + (size_t)r * nc + j, o[r]); }
+            }
+        }
+        grid_barrier(bar, nblk);
+        // multipliers: own rows' block column k (the pivot block row itself is skipped below)
+        for (int t = tid; t < nr * CZ_KD; t += nt) F[t / CZ_KD][t % CZ_KD] = rows[(size_t)(t / CZ_KD) * nc + kc + t % CZ_KD];
+        __syncthreads();
+        for (int j = tid; j < nc; j += nt) {
+            double pv[CZ_KD];
+#pragma unroll
+            for (int m = 0; m < CZ_KD; ++m) pv[m] = __ldcg(pub + (size_t)m * nc + j);
+            const bool inpiv = j >= kc && j < kc + CZ_KD;
+            for (int i = 0; i < nr; ++i) {
+                if ((r0 + i) / CZ_KD == k) continue;
+                double t = 0.0;
+#pragma unroll
+                for (int m = 0; m < CZ_KD; ++m) t += F[i][m] * pv[m];
+                // column inside the pivot block: A_ik <- -F P  (pv holds P there) ; elsewhere A_ij -= F * pivotrow_j
+                double *e = rows + (size_t)i * nc + j;
+                *e = inpiv ? -t : *e - t;
+            }
+        }
+        __syncthreads();
+    }
+    for (int t = tid; t < nr * nc; t += nt) A[(size_t)r0 * nc + t] = rows[t];
+}
+
 #define BPCG_P_THREADS 1024
 #define BPCG_P_GROUP 8  // lanes cooperating on one scalar row of S p
 
@@ -425,7 +625,7 @@ __device__ __forceinline__ double sum_partials_w0(const double *part, int n, dou
 }
 
 __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView s, BpcgTables tb, int max_iter, unsigned *bar,
-                                                                       double *pbuf2, int n_init_parts) {
+                                                                       double *pbuf2, int n_init_parts, CoarseView cv) {
     extern __shared__ double dsm[];
     __shared__ double red[32];
     __shared__ double bc[2];
@@ -457,6 +657,67 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
     int it = 0, cur = 0;
     const double thr = s.tol * sqrt(bb);
     grid_barrier(bar, nblk);  // init partials consumed everywhere before the buffers are reused
+    // ---- coarse correction z += Z Ac^-1 Z^T r on the CTA's own rows (one grid barrier); see CoarseView
+    __shared__ double zc_s[32][4];  // [coarse row of this CTA][warp partial]
+    __shared__ double zc_f[32];
+    const int crow_n = CZ_KD * cv.apc;  // coarse rows owned by this CTA (<= 32)
+    double *Z_s = mi_s + 36 * (size_t)br;  // [br][6][CZ_KD] (only allocated when cv.apc > 0)
+    if (cv.apc > 0)
+        for (int t = tid; t < 6 * CZ_KD * (i1 - i0); t += nt) Z_s[t] = cv.Z[6 * CZ_KD * (size_t)i0 + t];
+    auto coarse_correct = [&]() {
+        const int nbl = i1 - i0;
+        if (tid < crow_n) {
+            const int al = tid / CZ_KD, m = tid % CZ_KD;
+            const int b0 = min(nbl, al * cv.ma), b1 = min(nbl, b0 + cv.ma);
+            double t = 0.0;
+            for (int ib = b0; ib < b1; ++ib) {
+                const double *zi = Z_s + 6 * CZ_KD * ib + m, *rb = r_s + 6 * ib;
+                t += zi[0] * rb[0] + zi[CZ_KD] * rb[1] + zi[2 * CZ_KD] * rb[2] + zi[3 * CZ_KD] * rb[3] + zi[4 * CZ_KD] * rb[4] +
+                     zi[5 * CZ_KD] * rb[5];
+            }
+            __stcg(cv.rc + (size_t)crow_n * blockIdx.x + tid, t);
+        }
+        grid_barrier(bar, nblk);
+        const int nwarp = nt >> 5, wpr = max(1, min(4, nwarp / crow_n));  // warps per coarse row
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < crow_n * wpr) {
+            const int row = warp / wpr, wl = warp % wpr;
+            const double *Ar = cv.Ainv + (size_t)(crow_n * blockIdx.x + row) * cv.nc;
+            double t = 0.0;
+            for (int j = wl * 32 + lane; j < cv.nc; j += 32 * wpr) t += __ldg(Ar + j) * __ldcg(cv.rc + j);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) zc_s[row][wl] = t;
+        }
+        __syncthreads();
+        if (tid < crow_n) {
+            double t = 0.0;
+            for (int q = 0; q < wpr; ++q) t += zc_s[tid][q];
+            zc_f[tid] = t;
+        }
+        __syncthreads();
+        for (int t = tid; t < nrow; t += nt) {
+            const int ib = t / 6, x = t % 6;
+            const double *zi = Z_s + 6 * CZ_KD * ib + x * CZ_KD, *zc = zc_f + CZ_KD * min(cv.apc - 1, ib / cv.ma);
+            double u = 0.0;
+#pragma unroll
+            for (int m = 0; m < CZ_KD; ++m) u += zi[m] * zc[m];
+            z_s[t] += u;
+        }
+        __syncthreads();
+    };
+    if (cv.apc > 0 && bb > 0.0) {
+        // the init kernel applied block-Jacobi only: add the coarse term to z and recompute r.z
+        __syncthreads();
+        coarse_correct();
+        double l = 0.0;
+        for (int t = tid; t < nrow; t += nt) { l += r_s[t] * z_s[t]; s.z[r0 + t] = z_s[t]; }
+        const double a = cta_sum(l, red);
+        if (tid == 0) part_b[blockIdx.x] = a;
+        grid_barrier(bar, nblk);
+        rz = sum_partials_w0(part_b, nblk, bc);
+        grid_barrier(bar, nblk);  // part_b is rewritten in the first iteration
+    }
     const int G = BPCG_P_GROUP;
     const int sub = tid % G;
     long long tp0 = 0, c_spmv = 0, c_bar1 = 0, c_upd = 0, c_bar2 = 0;
@@ -524,15 +785,32 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
             }
             __syncthreads();
             double l_rz2 = 0.0, l_rr = 0.0;
-            for (int t = tid; t < nrow; t += nt) {
-                const int ib = t / 6, rw = t % 6;
-                const double *mi = mi_s + 36 * (size_t)ib + 6 * rw;
-                const double *rb = r_s + 6 * (size_t)ib;
-                const double z = mi[0] * rb[0] + mi[1] * rb[1] + mi[2] * rb[2] + mi[3] * rb[3] + mi[4] * rb[4] + mi[5] * rb[5];
-                z_s[t] = z;
-                s.z[r0 + t] = z;
-                l_rz2 += rb[rw] * z;
-                l_rr += rb[rw] * rb[rw];
+            if (cv.apc == 0) {
+                for (int t = tid; t < nrow; t += nt) {
+                    const int ib = t / 6, rw = t % 6;
+                    const double *mi = mi_s + 36 * (size_t)ib + 6 * rw;
+                    const double *rb = r_s + 6 * (size_t)ib;
+                    const double z = mi[0] * rb[0] + mi[1] * rb[1] + mi[2] * rb[2] + mi[3] * rb[3] + mi[4] * rb[4] + mi[5] * rb[5];
+                    z_s[t] = z;
+                    s.z[r0 + t] = z;
+                    l_rz2 += rb[rw] * z;
+                    l_rr += rb[rw] * rb[rw];
+                }
+            } else {
+                for (int t = tid; t < nrow; t += nt) {
+                    const int ib = t / 6, rw = t % 6;
+                    const double *mi = mi_s + 36 * (size_t)ib + 6 * rw;
+                    const double *rb = r_s + 6 * (size_t)ib;
+                    z_s[t] = mi[0] * rb[0] + mi[1] * rb[1] + mi[2] * rb[2] + mi[3] * rb[3] + mi[4] * rb[4] + mi[5] * rb[5];
+                }
+                __syncthreads();
+                coarse_correct();
+                for (int t = tid; t < nrow; t += nt) {
+                    const double z = z_s[t], r = r_s[t];
+                    s.z[r0 + t] = z;
+                    l_rz2 += r * z;
+                    l_rr += r * r;
+                }
             }
             {
                 const double a = cta_sum(l_rz2, red), b = cta_sum(l_rr, red);
