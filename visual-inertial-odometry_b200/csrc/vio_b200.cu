@@ -114,6 +114,8 @@ struct vio_problem {
     size_t cz_smem = 0;
     DBuf<int> cz_ptr, cz_fine, cz_frow, cz_row, cz_col, cz_aggptr, cz_blkpose;
     DBuf<double> cz_A, cz_rowbuf, cz_rc, cz_Z;
+    DBuf<unsigned> cz_flags;
+    unsigned cz_epoch = 0;
     int pcg_grid = -1, pcg_br = 0, pcg_win = 0;
     size_t pcg_smem = 0;
     DBuf<unsigned long long> prof;
@@ -433,7 +435,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                 {
                     const int apc = std::max(1, apc_sel);
                     const int nc_ = CZ_KD * grid * apc, ma = (brc + apc - 1) / apc, na = grid * apc;
-                    const size_t smem2 = p->pcg_smem + (size_t)6 * CZ_KD * brc * sizeof(double);
+                    const size_t smem2 = p->pcg_smem + ((size_t)6 * CZ_KD * brc + nc_) * sizeof(double);
                     const size_t inv_smem = (size_t)CZ_KD * apc * nc_ * sizeof(double);
                     p->cz_apc = (apc_sel > 0 && inv_smem <= 224 * 1024 && smem2 <= 200 * 1024 && (int)p->h_pose_off.size() >= nb) ? apc : 0;
                     if (p->cz_apc > 0) {
@@ -476,7 +478,8 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                         p->cz_rp = apc;  // coarse block rows per CTA of the inversion kernel
                         p->cz_grid = grid;
                         p->cz_smem = inv_smem;
-                        CK(p->cz_A.alloc((size_t)nc_ * nc_)); CK(p->cz_rowbuf.alloc(2 * (size_t)CZ_KD * nc_)); CK(p->cz_rc.alloc(nc_));
+                        CK(p->cz_A.alloc((size_t)nc_ * nc_)); CK(p->cz_rowbuf.alloc((size_t)na * CZ_KD * nc_)); CK(p->cz_flags.alloc(na));
+                        CK(cudaMemsetAsync(p->cz_flags.p, 0, na * sizeof(unsigned), p->stream)); p->cz_epoch = 0; CK(p->cz_rc.alloc(nc_));
                         CK(p->cz_Z.alloc((size_t)6 * CZ_KD * nb));
                         CK(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->cz_smem));
                         CK(cudaFuncSetAttribute(k_bpcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -505,9 +508,11 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                 k_coarse_assemble<<<p->cz_ncb, 784, 0, p->stream>>>(v.S, v.bsr_col, p->cz_ptr.p, p->cz_fine.p, p->cz_frow.p, p->cz_row.p,
                                                                     p->cz_col.p, p->cz_aggptr.p, p->cz_Z.p, lambda, nc_, p->cz_A.p);
                 double *Ap = p->cz_A.p, *rbuf = p->cz_rowbuf.p;
+                unsigned *flg = p->cz_flags.p;
+                unsigned epoch = ++p->cz_epoch;  // flags of earlier launches hold smaller epochs: no reset needed
                 int ncv = nc_, rpv = p->cz_rp;
-                void *iargs[] = {(void *)&Ap, (void *)&ncv, (void *)&rpv, (void *)&rbuf, (void *)&barp};
-                ce = cudaLaunchCooperativeKernel((void *)k_coarse_invert, dim3(p->cz_grid), dim3(1024), iargs, p->cz_smem, p->stream);
+                void *iargs[] = {(void *)&Ap, (void *)&ncv, (void *)&rpv, (void *)&rbuf, (void *)&flg, (void *)&epoch};
+                ce = cudaLaunchCooperativeKernel((void *)k_coarse_invert, dim3(p->cz_grid), dim3(CZ_INV_THREADS), iargs, p->cz_smem, p->stream);
                 if (ce == cudaSuccess) {
                     p->launches += 3;
                     CK(cudaMemsetAsync(p->bar.p, 0, 2 * sizeof(unsigned), p->stream));
@@ -519,7 +524,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             }
             void *args[] = {(void *)&s, (void *)&tb, (void *)&mi, (void *)&barp, (void *)&p2, (void *)&n_init, (void *)&cv};
             if (ce == cudaSuccess) ce = cudaLaunchCooperativeKernel((void *)k_bpcg_persistent, dim3(grid), dim3(BPCG_P_THREADS), args,
-                                                                        p->pcg_smem + (cv.apc > 0 ? (size_t)6 * CZ_KD * p->pcg_br * sizeof(double) : 0), p->stream);
+                                                                        p->pcg_smem + (cv.apc > 0 ? ((size_t)6 * CZ_KD * p->pcg_br + cv.nc) * sizeof(double) : 0), p->stream);
             if (ce == cudaSuccess) {
                 p->launches++;
                 done_persistent = true;

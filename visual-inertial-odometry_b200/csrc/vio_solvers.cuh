@@ -538,59 +538,134 @@ __device__ inline void inv7_spd(const double *A /* 7x7 row-major, ld */, int ld,
         }
 }
 
-__global__ void __launch_bounds__(1024, 1) k_coarse_invert(double *A, int nc, int bpc, double *rowbuf /* [2][7][nc] */, unsigned *bar) {
+// 7x7 SPD inverse by Gauss-Jordan in shared memory, all threads of the CTA call it (49 of them work)
+__device__ __forceinline__ void inv7_cta(const double *A, int ld, double *M /* shared [49] out */) {
+    const int tid = threadIdx.x, r = tid / CZ_KD, c = tid % CZ_KD;
+    if (tid < CZ_KD * CZ_KD) M[tid] = A[(size_t)r * ld + c];
+    __syncthreads();
+    for (int k = 0; k < CZ_KD; ++k) {
+        double d = 0.0, f = 0.0, pk = 0.0, cur = 0.0;
+        if (tid < CZ_KD * CZ_KD) { d = 1.0 / M[CZ_KD * k + k]; f = M[CZ_KD * r + k]; pk = M[CZ_KD * k + c]; cur = M[tid]; }
+        __syncthreads();
+        if (tid < CZ_KD * CZ_KD) {
+            double v;
+            if (r == k) v = (c == k) ? d : pk * d;
+            else v = (c == k) ? -f * d : cur - f * (pk * d);
+            M[tid] = v;
+        }
+        __syncthreads();
+    }
+}
+
+#define CZ_INV_THREADS 512
+#define CZ_NCOL 4
+// Flags instead of grid barriers: pivot block row k is published into its OWN slot of `pivbuf` ([na][7][nc], never
+// reused within a launch, so there is no write-after-read hazard) and flag[k] = epoch is set with release semantics;
+// consumers spin on flag[k].  The critical path is the owner chain (eliminate block row k+1 with pivot k, invert the
+// 7x7 pivot, scale, publish); everybody else runs behind it without any all-to-all synchronisation.  Cooperative launch
+// (co-residency) makes the spinning safe.
+__device__ __forceinline__ void flag_wait(const unsigned *flag, unsigned epoch) {
+    if (threadIdx.x == 0) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        } while (v != epoch);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void flag_set(unsigned *flag, unsigned epoch) {
+    __syncthreads();  // every thread's stores are done ...
+    if (threadIdx.x == 0) {
+        __threadfence();  // ... and visible device-wide before the flag
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(CZ_INV_THREADS, 1) k_coarse_invert(double *A, int nc, int bpc, double *pivbuf /* [na][7][nc] */,
+                                                                     unsigned *flags /* [na] */, unsigned epoch) {
     extern __shared__ double csm[];
     double *rows = csm;  // [7*bpc][nc]
-    __shared__ double F[4 * CZ_KD][CZ_KD];  // own rows' block column k before the update (bpc <= 4)
+    __shared__ __align__(16) double F[4 * CZ_KD][CZ_KD + 1];  // own rows' block column k before the update (bpc <= 4)
     __shared__ double Pm[CZ_KD * CZ_KD];
-    const int tid = threadIdx.x, nt = blockDim.x, nblk = gridDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
     const int na = nc / CZ_KD;
     const int a0 = min(na, blockIdx.x * bpc), a1 = min(na, a0 + bpc);
     const int r0 = CZ_KD * a0, nr = CZ_KD * (a1 - a0);
     for (int t = tid; t < nr * nc; t += nt) rows[t] = A[(size_t)r0 * nc + t];
     __syncthreads();
-    for (int k = 0; k < na; ++k) {
-        double *pub = rowbuf + (size_t)(k & 1) * CZ_KD * nc;
+    // pivot block row k <- [P A_k,: with P = A_kk^-1 | P inside the pivot block], written to shared memory and published
+    auto publish_pivot = [&](int k) {
+        double *pub = pivbuf + (size_t)k * CZ_KD * nc;
         const int kc = CZ_KD * k;
-        if (k >= a0 && k < a1) {
-            double *rk = rows + (size_t)(CZ_KD * (k - a0)) * nc;  // the pivot block row (7 x nc)
-            if (tid == 0) inv7_spd(rk + kc, nc, Pm);
-            __syncthreads();
-            // row block <- P * row block (columns outside the pivot block), pivot block <- P
-            for (int j = tid; j < nc; j += nt) {
-                double v[CZ_KD], o[CZ_KD];
-#pragma unroll
-                for (int m = 0; m < CZ_KD; ++m) v[m] = rk[(size_t)m * nc + j];
-                const bool inpiv = j >= kc && j < kc + CZ_KD;
-#pragma unroll
-                for (int r = 0; r < CZ_KD; ++r) {
-                    double t = 0.0;
-#pragma unroll
-                    for (int m = 0; m < CZ_KD; ++m) t += Pm[CZ_KD * r + m] * v[m];
-                    o[r] = inpiv ? Pm[CZ_KD * r + (j - kc)] : t;
-                }
-#pragma unroll
-                for (int r = 0; r < CZ_KD; ++r) { rk[(size_t)r * nc + j] = o[r]; __stcg(pub + (size_t)r * nc + j, o[r]); }
-            }
-        }
-        grid_barrier(bar, nblk);
-        // multipliers: own rows' block column k (the pivot block row itself is skipped below)
-        for (int t = tid; t < nr * CZ_KD; t += nt) F[t / CZ_KD][t % CZ_KD] = rows[(size_t)(t / CZ_KD) * nc + kc + t % CZ_KD];
-        __syncthreads();
+        double *rk = rows + (size_t)(CZ_KD * (k - a0)) * nc;
+        inv7_cta(rk + kc, nc, Pm);
         for (int j = tid; j < nc; j += nt) {
-            double pv[CZ_KD];
+            double v[CZ_KD], o[CZ_KD];
 #pragma unroll
-            for (int m = 0; m < CZ_KD; ++m) pv[m] = __ldcg(pub + (size_t)m * nc + j);
+            for (int m = 0; m < CZ_KD; ++m) v[m] = rk[(size_t)m * nc + j];
             const bool inpiv = j >= kc && j < kc + CZ_KD;
-            for (int i = 0; i < nr; ++i) {
-                if ((r0 + i) / CZ_KD == k) continue;
+#pragma unroll
+            for (int r = 0; r < CZ_KD; ++r) {
                 double t = 0.0;
 #pragma unroll
-                for (int m = 0; m < CZ_KD; ++m) t += F[i][m] * pv[m];
-                // column inside the pivot block: A_ik <- -F P  (pv holds P there) ; elsewhere A_ij -= F * pivotrow_j
-                double *e = rows + (size_t)i * nc + j;
-                *e = inpiv ? -t : *e - t;
+                for (int m = 0; m < CZ_KD; ++m) t += Pm[CZ_KD * r + m] * v[m];
+                o[r] = inpiv ? Pm[CZ_KD * r + (j - kc)] : t;
             }
+#pragma unroll
+            for (int r = 0; r < CZ_KD; ++r) { rk[(size_t)r * nc + j] = o[r]; __stcg(pub + (size_t)r * nc + j, o[r]); }
+        }
+        flag_set(flags + k, epoch);
+    };
+    // elimination of block column k from own scalar rows [i_lo, i_hi) (the pivot block row itself is skipped).  Each
+    // thread takes CZ_NCOL columns at a time: the 7 multipliers of a row (three 16-byte shared loads + one) are reused
+    // for all of them, which keeps the shared-memory traffic below the FP64 work.
+    auto eliminate = [&](int k, int i_lo, int i_hi) {
+        const double *pub = pivbuf + (size_t)k * CZ_KD * nc;
+        const int kc = CZ_KD * k;
+        for (int jb = 0; jb < nc; jb += CZ_NCOL * nt) {
+            double pv[CZ_NCOL][CZ_KD];
+            int jj[CZ_NCOL];
+#pragma unroll
+            for (int c = 0; c < CZ_NCOL; ++c) {
+                jj[c] = jb + c * nt + tid;
+#pragma unroll
+                for (int m = 0; m < CZ_KD; ++m) pv[c][m] = jj[c] < nc ? __ldcg(pub + (size_t)m * nc + jj[c]) : 0.0;
+            }
+            for (int i = i_lo; i < i_hi; ++i) {
+                if ((r0 + i) / CZ_KD == k) continue;
+                const double2 f01 = *reinterpret_cast<const double2 *>(&F[i][0]), f23 = *reinterpret_cast<const double2 *>(&F[i][2]),
+                              f45 = *reinterpret_cast<const double2 *>(&F[i][4]);
+                const double f6 = F[i][6];
+#pragma unroll
+                for (int c = 0; c < CZ_NCOL; ++c) {
+                    if (jj[c] >= nc) continue;
+                    const double t = f01.x * pv[c][0] + f01.y * pv[c][1] + f23.x * pv[c][2] + f23.y * pv[c][3] + f45.x * pv[c][4] +
+                                     f45.y * pv[c][5] + f6 * pv[c][6];
+                    double *e = rows + (size_t)i * nc + jj[c];
+                    const bool inpiv = jj[c] >= kc && jj[c] < kc + CZ_KD;
+                    *e = inpiv ? -t : *e - t;  // inside the pivot block pv holds P:  A_ik <- -F P
+                }
+            }
+        }
+    };
+    if (a0 == 0 && a1 > 0) publish_pivot(0);
+    for (int k = 0; k < na; ++k) {
+        const int kc = CZ_KD * k;
+        const bool own_k = k >= a0 && k < a1;
+        if (!own_k) flag_wait(flags + k, epoch);  // pivot block row k is published (the owner has it already)
+        for (int t = tid; t < nr * CZ_KD; t += nt) F[t / CZ_KD][t % CZ_KD] = rows[(size_t)(t / CZ_KD) * nc + kc + t % CZ_KD];
+        __syncthreads();
+        const bool own_next = (k + 1 < na) && (k + 1 >= a0) && (k + 1 < a1);
+        if (own_next) {
+            // the owner chain: bring block row k+1 up to date first and publish the next pivot, then the other rows
+            const int lo = CZ_KD * (k + 1 - a0);
+            eliminate(k, lo, lo + CZ_KD);
+            __syncthreads();
+            publish_pivot(k + 1);
+            eliminate(k, 0, lo);
+            eliminate(k, lo + CZ_KD, nr);
+        } else {
+            eliminate(k, 0, nr);
         }
         __syncthreads();
     }
@@ -657,42 +732,57 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
     int it = 0, cur = 0;
     const double thr = s.tol * sqrt(bb);
     grid_barrier(bar, nblk);  // init partials consumed everywhere before the buffers are reused
-    // ---- coarse correction z += Z Ac^-1 Z^T r on the CTA's own rows (one grid barrier); see CoarseView
-    __shared__ double zc_s[32][4];  // [coarse row of this CTA][warp partial]
+    // ---- coarse correction z += Z Ac^-1 Z^T r on the CTA's own rows; see CoarseView.  Every CTA keeps the whole restricted
+    // residual rc = Z^T r in shared memory and updates it by the CG recurrence rc -= alpha Z^T (S p), whose pieces are
+    // exchanged on the iteration's first barrier: the coarse term costs no barrier of its own.
+    __shared__ double zc_w[32][28];  // [warp][coarse row of this CTA] partial sums
     __shared__ double zc_f[32];
     const int crow_n = CZ_KD * cv.apc;  // coarse rows owned by this CTA (<= 32)
     double *Z_s = mi_s + 36 * (size_t)br;  // [br][6][CZ_KD] (only allocated when cv.apc > 0)
     if (cv.apc > 0)
         for (int t = tid; t < 6 * CZ_KD * (i1 - i0); t += nt) Z_s[t] = cv.Z[6 * CZ_KD * (size_t)i0 + t];
-    auto coarse_correct = [&]() {
+    double *rc_s = Z_s + 6 * CZ_KD * (size_t)br;  // [nc] the whole restricted residual Z^T r, kept by every CTA
+    // own aggregates' part of Z^T v (v = r at the start, S p inside the iteration) -> global exchange buffer
+    auto restrict_publish = [&](const double *v_s) {
         const int nbl = i1 - i0;
         if (tid < crow_n) {
             const int al = tid / CZ_KD, m = tid % CZ_KD;
             const int b0 = min(nbl, al * cv.ma), b1 = min(nbl, b0 + cv.ma);
             double t = 0.0;
             for (int ib = b0; ib < b1; ++ib) {
-                const double *zi = Z_s + 6 * CZ_KD * ib + m, *rb = r_s + 6 * ib;
-                t += zi[0] * rb[0] + zi[CZ_KD] * rb[1] + zi[2 * CZ_KD] * rb[2] + zi[3 * CZ_KD] * rb[3] + zi[4 * CZ_KD] * rb[4] +
-                     zi[5 * CZ_KD] * rb[5];
+                const double *zi = Z_s + 6 * CZ_KD * ib + m, *vb = v_s + 6 * ib;
+                t += zi[0] * vb[0] + zi[CZ_KD] * vb[1] + zi[2 * CZ_KD] * vb[2] + zi[3 * CZ_KD] * vb[3] + zi[4 * CZ_KD] * vb[4] +
+                     zi[5 * CZ_KD] * vb[5];
             }
             __stcg(cv.rc + (size_t)crow_n * blockIdx.x + tid, t);
         }
-        grid_barrier(bar, nblk);
-        const int nwarp = nt >> 5, wpr = max(1, min(4, nwarp / crow_n));  // warps per coarse row
-        const int warp = tid >> 5, lane = tid & 31;
-        if (warp < crow_n * wpr) {
-            const int row = warp / wpr, wl = warp % wpr;
-            const double *Ar = cv.Ainv + (size_t)(crow_n * blockIdx.x + row) * cv.nc;
-            double t = 0.0;
-            for (int j = wl * 32 + lane; j < cv.nc; j += 32 * wpr) t += __ldg(Ar + j) * __ldcg(cv.rc + j);
+    };
+    // z_s += Z (Ainv[own rows, :] rc_s): every thread takes whole columns (one Ainv element per own coarse row, all loads
+    // independent), then a fixed-order reduction over lanes and warps
+    auto coarse_apply = [&]() {
+        const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
+        for (int al = 0; al < cv.apc; ++al) {  // one aggregate (CZ_KD coarse rows) at a time: 7 accumulators in registers
+            double acc[CZ_KD];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0) zc_s[row][wl] = t;
+            for (int q = 0; q < CZ_KD; ++q) acc[q] = 0.0;
+            const double *Ar = cv.Ainv + (size_t)(crow_n * blockIdx.x + CZ_KD * al) * cv.nc;
+            for (int j = tid; j < cv.nc; j += nt) {
+                const double rj = rc_s[j];
+#pragma unroll
+                for (int q = 0; q < CZ_KD; ++q) acc[q] += __ldg(Ar + (size_t)q * cv.nc + j) * rj;
+            }
+#pragma unroll
+            for (int q = 0; q < CZ_KD; ++q) {
+                double t = acc[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) zc_w[warp][CZ_KD * al + q] = t;
+            }
         }
         __syncthreads();
         if (tid < crow_n) {
             double t = 0.0;
-            for (int q = 0; q < wpr; ++q) t += zc_s[tid][q];
+            for (int w = 0; w < nwarp; ++w) t += zc_w[w][tid];
             zc_f[tid] = t;
         }
         __syncthreads();
@@ -707,16 +797,20 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
         __syncthreads();
     };
     if (cv.apc > 0 && bb > 0.0) {
-        // the init kernel applied block-Jacobi only: add the coarse term to z and recompute r.z
+        // the init kernel applied block-Jacobi only: rc = Z^T r, add the coarse term to z and recompute r.z
         __syncthreads();
-        coarse_correct();
+        restrict_publish(r_s);
+        grid_barrier(bar, nblk);
+        for (int j = tid; j < cv.nc; j += nt) rc_s[j] = __ldcg(cv.rc + j);
+        __syncthreads();
+        coarse_apply();
         double l = 0.0;
         for (int t = tid; t < nrow; t += nt) { l += r_s[t] * z_s[t]; s.z[r0 + t] = z_s[t]; }
         const double a = cta_sum(l, red);
         if (tid == 0) part_b[blockIdx.x] = a;
         grid_barrier(bar, nblk);
         rz = sum_partials_w0(part_b, nblk, bc);
-        grid_barrier(bar, nblk);  // part_b is rewritten in the first iteration
+        grid_barrier(bar, nblk);  // part_b and the exchange buffer are rewritten in the first iteration
     }
     const int G = BPCG_P_GROUP;
     const int sub = tid % G;
@@ -774,10 +868,13 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
                 const double a = cta_sum(l_pw, red);
                 if (tid == 0) part_a[blockIdx.x] = a;
             }
+            if (cv.apc > 0) restrict_publish(w_s);  // Z^T (S p) rides on the same barrier: rc -= alpha Z^T S p below
             PCG_MARK(c_spmv);
             grid_barrier(bar, nblk);
             const double alpha = rz / sum_partials_w0(part_a, nblk, bc);
             PCG_MARK(c_bar1);
+            if (cv.apc > 0)
+                for (int j = tid; j < cv.nc; j += nt) rc_s[j] -= alpha * __ldcg(cv.rc + j);
             // ---- x += alpha p ; r -= alpha w ; z = Minv r ; partial r.z, r.r   (own rows, all in shared memory)
             for (int t = tid; t < nrow; t += nt) {
                 x_s[t] += alpha * p_s[t];
@@ -804,7 +901,7 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
                     z_s[t] = mi[0] * rb[0] + mi[1] * rb[1] + mi[2] * rb[2] + mi[3] * rb[3] + mi[4] * rb[4] + mi[5] * rb[5];
                 }
                 __syncthreads();
-                coarse_correct();
+                coarse_apply();
                 for (int t = tid; t < nrow; t += nt) {
                     const double z = z_s[t], r = r_s[t];
                     s.z[r0 + t] = z;
