@@ -24,7 +24,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     s = vio.scenes.ring(n_cam=300, n_landmark=30000, k_obs=11, seed=21)
     s.storage = vio.capi.STORAGE_BSR
-    opts = vio.make_opts(flavour=vio.capi.LM_V17, solver=vio.capi.SOLVER_BLOCK_PCG, pcg_tol=1e-10, fixed_iterations=1)
+    opts = vio.make_opts(flavour=vio.capi.LM_V17, solver=vio.capi.SOLVER_BLOCK_PCG_2L, pcg_tol=1e-10, fixed_iterations=1)
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         p = vio.Problem(device=local, stream=stream.cuda_stream)

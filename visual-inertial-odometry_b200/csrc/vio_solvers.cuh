@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
             for (int j = tid; j < cv.nc; j += nt) {
                 const double rj = rc_s[j];
 #pragma unroll
-                for (int q = 0; q < CZ_KD; ++q) acc[q] += __ldg(Ar + (size_t)q * cv.nc + j) * rj;
+                for (int q = 0; q < CZ_KD; ++q) acc[q] += __ldcs(Ar + (size_t)q * cv.nc + j) * rj;  // evict-first: keep S in L2
             }
 #pragma unroll
             for (int q = 0; q < CZ_KD; ++q) {
