@@ -18,11 +18,17 @@ struct HostProblem {
     DevView v;
 };
 
+void setup_packed(const vio_graph *g, const double *pose, HostProblem &H);
 int setup(const vio_graph *g, HostProblem &H, std::string &err) {
     int rc = pack_graph(g, 0, 1, H.K, err);
     if (rc) return rc;
+    setup_packed(g, g->pose, H);
+    return VIO_OK;
+}
+// host view over an already packed graph (H.K); g supplies the factor constants, pose the C x 7 vertex values
+void setup_packed(const vio_graph *g, const double *pose, HostProblem &H) {
     PackedGraph &K = H.K;
-    H.pose.assign(g->pose, g->pose + 7 * (size_t)K.C);
+    H.pose.assign(pose, pose + 7 * (size_t)K.C);
     H.pose_bak = H.pose;
     H.sb.assign(9 * (size_t)K.NSB, 0.0);
     H.poseRT.assign(16 * (size_t)K.C, 0.0);
@@ -32,7 +38,8 @@ int setup(const vio_graph *g, HostProblem &H, std::string &err) {
     DevView &v = H.v;
     memset(&v, 0, sizeof(v));
     v.C = K.C; v.NSB = K.NSB; v.L = K.L; v.P = K.P; v.NB = K.NB; v.E = K.E; v.storage = K.storage; v.nnzb = K.nnzb;
-    v.batch = 1; v.Pper = K.P; v.Cper = K.C > 0 ? K.C : 1; v.NSBper = K.NSB > 0 ? K.NSB : 1;
+    v.batch = K.batch; v.Pper = K.Pper > 0 ? K.Pper : K.P;
+    v.Cper = K.C > 0 ? K.C / K.batch : 1; v.NSBper = K.NSB > 0 ? K.NSB / K.batch : 1;
     v.pose = H.pose.data(); v.pose_bak = H.pose_bak.data(); v.sb = H.sb.data(); v.invdep = K.invd.data();
     v.invdep_bak = H.invd_bak.data();
     v.pose_fixed = K.pose_fixed.data(); v.sb_fixed = K.sb_fixed.data();
@@ -48,7 +55,6 @@ int setup(const vio_graph *g, HostProblem &H, std::string &err) {
     v.S = H.sys.data(); v.bcorr = v.S + K.s_count; v.bp = v.bcorr + K.P; v.hdiag = v.bp + K.P; v.bS = H.bS.data();
     v.bsr_rowptr = K.rowptr.data(); v.bsr_col = K.col.data(); v.bsr_tr = K.tr.data();
     v.dxp = H.dxp.data(); v.dxl = H.dxl.data();
-    return VIO_OK;
 }
 }  // namespace
 
@@ -180,6 +186,67 @@ int emul_chi2(const vio_graph *g, double *out) {
             for (int b = 0; b < 6; ++b) chi += r[a] * Om[6 * a + b] * r[b];
     }
     *out = chi;
+    return VIO_OK;
+}
+
+// Lock-step batches (vio_solve_batched_lockstep): pack every item on its own and merge (PackedMerge, the production
+// path), pack the caller-concatenated graph with batch = B (pack_graph's own batch mode), and
+//  (1) compare every table of the two packs (n_diff = number of differing arrays; landmark-order dependent arrays are
+//      only compared when no item has an edge-less landmark, where the two orders coincide),
+//  (2) run MakeHessian + Schur with the device bodies over the MERGED pack: S_out = B stacked Pper x Pper systems
+//      (upper triangles mirrored), bS_out = B x Pper.
+int emul_merge_check(const vio_graph *const *items, int B, const vio_graph *concat, int *n_diff, double *S_out, double *bS_out) {
+    std::string err;
+    std::vector<PackedGraph> Ks(B);
+    for (int k = 0; k < B; ++k) {
+        vio_graph gk = *items[k];
+        gk.storage = VIO_STORAGE_DENSE;
+        gk.n_se3prior = 0;
+        int rc = pack_graph(&gk, 0, 1, Ks[k], err);
+        if (rc) { fprintf(stderr, "emul: item %d: %s\n", k, err.c_str()); return rc; }
+    }
+    HostProblem H;
+    PackedMerge mg;
+    int rc = mg.prepare(Ks, H.K, err);
+    if (rc) { fprintf(stderr, "emul: merge: %s\n", err.c_str()); return rc; }
+    mg.fill(0, B);
+    PackedGraph K2;
+    vio_graph gc = *concat;
+    gc.storage = VIO_STORAGE_DENSE;
+    rc = pack_graph(&gc, 0, 1, K2, err, B);
+    if (rc) { fprintf(stderr, "emul: concat: %s\n", err.c_str()); return rc; }
+    const PackedGraph &M = H.K;
+    int nd = 0;
+    bool edgeless = false;
+    for (int l = 0; l < M.L; ++l) edgeless = edgeless || M.lm_eptr[l] == M.lm_eptr[l + 1];
+#define CMP(field) do { if (!(M.field == K2.field)) { ++nd; fprintf(stderr, "emul: merged pack differs in %s\n", #field); } } while (0)
+    CMP(C); CMP(NSB); CMP(NB); CMP(P); CMP(L); CMP(E); CMP(storage); CMP(batch); CMP(Pper); CMP(s_count);
+    CMP(pose_off); CMP(sb_off); CMP(pose_blk); CMP(blk_off); CMP(blk_dim); CMP(blk_fixed); CMP(pose_fixed); CMP(sb_fixed); CMP(row_fixed);
+    if (!edgeless) {
+        CMP(lm_global); CMP(lm_host); CMP(lm_eptr); CMP(e_pose_j); CMP(pix); CMP(piy); CMP(piz); CMP(pjx); CMP(pjy); CMP(invd);
+        CMP(grouped_ok); CMP(n_groups); CMP(group_threads); CMP(group_smem_max);
+        CMP(g_hdr); CMP(g_slot_pose); CMP(g_pairinfo); CMP(ell_edge); CMP(ell_pjy);
+        // ell_pjx marks missing entries with NaN: compare bit patterns
+        if (M.ell_pjx.size() != K2.ell_pjx.size() ||
+            memcmp(M.ell_pjx.data(), K2.ell_pjx.data(), M.ell_pjx.size() * sizeof(double)) != 0) { ++nd; fprintf(stderr, "emul: merged pack differs in ell_pjx\n"); }
+    }
+#undef CMP
+    if (n_diff) *n_diff = nd;
+    setup_packed(concat, concat->pose, H);
+    DevView &v = H.v;
+    for (int i = 0; i < M.C; ++i) pose_prep(v, i);
+    for (int l = 0; l < M.L; ++l) linearize_landmark<true>(v, l);
+    const int P = M.P, Pper = M.Pper;
+    if (S_out) {
+        memcpy(S_out, v.S, (size_t)P * Pper * sizeof(double));
+        for (int k = 0; k < B; ++k) {
+            double *Sk = S_out + (size_t)k * Pper * Pper;
+            for (int r = 0; r < Pper; ++r)
+                for (int c = 0; c < r; ++c) Sk[(size_t)r * Pper + c] = Sk[(size_t)c * Pper + r];
+        }
+    }
+    if (bS_out)
+        for (int i = 0; i < P; ++i) bS_out[i] = v.bp[i] - v.bcorr[i];
     return VIO_OK;
 }
 }

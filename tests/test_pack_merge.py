@@ -1,0 +1,95 @@
+"""Host logic of the lock-step batch (vio_solve_batched_lockstep) without a GPU: the per-item packs merged by
+PackedMerge must equal pack_graph's own batch mode on the caller-concatenated graph, and MakeHessian + Schur run with
+the device bodies over the merged pack (tests/host_emul.cu) must give every window's reduced system bit for bit."""
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests import emul  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not emul.available(), reason="tests/libhost_emul.so not built (__graft_entry__.build())")
+
+
+def _window(vio):
+    path = os.path.join(ROOT, "tests", "golden", "window_v17_scene.npz")
+    return vio.Scene.from_dict(dict(np.load(path)))
+
+
+def _items(vio, ragged):
+    base = _window(vio)
+    rng = np.random.default_rng(2)
+    out = []
+    for k in range(4):
+        d = base.export()
+        d.pop("imu_pose_i", None)  # the emulation covers the reprojection factors; drop IMU edges and the prior
+        for key in [x for x in d if x.startswith("imu_") or x.startswith("prior_")]:
+            d.pop(key)
+        if ragged and k in (1, 3):
+            keep_l = d["inv_depth"].shape[0] - 11 * k
+            m = d["rp_landmark"] < keep_l
+            for key in ("rp_landmark", "rp_pose_i", "rp_pose_j", "rp_pts_i", "rp_pts_j"):
+                d[key] = d[key][m]
+            d["inv_depth"] = d["inv_depth"][:keep_l]
+        s = vio.Scene.from_dict(d)
+        s.pose[1:, :3] += rng.normal(0, 0.01, (s.pose.shape[0] - 1, 3))
+        s.inv_depth *= 1.0 + rng.normal(0, 0.02, s.inv_depth.shape[0])
+        out.append(s)
+    return out
+
+
+def _concat(vio, items):
+    s0 = items[0]
+    Cn, NSB = s0.pose.shape[0], s0.speedbias.shape[0]
+    for s in items:
+        s._norm()
+    d = s0.export()
+    d["pose"] = np.vstack([s.pose for s in items])
+    d["pose_fixed"] = np.concatenate([s.pose_fixed for s in items])
+    d["speedbias"] = np.vstack([s.speedbias for s in items])
+    d["speedbias_fixed"] = np.concatenate([np.atleast_1d(s.speedbias_fixed) if s.speedbias_fixed is not None
+                                           else np.zeros(NSB, np.uint8) for s in items])
+    order = []
+    for k, s in enumerate(items):
+        o = np.asarray(s.pclass_order, np.int64)
+        order.append(np.where(o >= 0, o + k * Cn, ~((~o) + k * NSB)))
+    d["pclass_order"] = np.concatenate(order).astype(np.int32)
+    loff = np.cumsum([0] + [s.inv_depth.shape[0] for s in items])
+    d["inv_depth"] = np.concatenate([s.inv_depth for s in items])
+    d["rp_landmark"] = np.concatenate([s.rp_landmark + loff[k] for k, s in enumerate(items)]).astype(np.int32)
+    d["rp_pose_i"] = np.concatenate([s.rp_pose_i + k * Cn for k, s in enumerate(items)]).astype(np.int32)
+    d["rp_pose_j"] = np.concatenate([s.rp_pose_j + k * Cn for k, s in enumerate(items)]).astype(np.int32)
+    d["rp_pts_i"] = np.vstack([s.rp_pts_i for s in items])
+    d["rp_pts_j"] = np.vstack([s.rp_pts_j for s in items])
+    return vio.Scene.from_dict(d)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_merged_pack_equals_batch_pack_and_linearises_per_window(ragged):
+    vio = importlib.import_module("visual-inertial-odometry_b200")
+    items = _items(vio, ragged)
+    cat = _concat(vio, items)
+    B = len(items)
+    P = items[0].P
+    gs = [s.to_c() for s in items]
+    arr = (C.POINTER(vio.capi.VioGraph) * B)(*[C.pointer(g) for g, _ in gs])
+    gc, keep = cat.to_c()
+    nd = C.c_int(-1)
+    S = np.zeros((B, P, P))
+    bS = np.zeros((B, P))
+    L = emul.lib()
+    L.emul_merge_check.argtypes = [C.POINTER(C.POINTER(vio.capi.VioGraph)), C.c_int, C.POINTER(vio.capi.VioGraph),
+                                   C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    rc = L.emul_merge_check(arr, B, C.byref(gc), C.byref(nd), S.ctypes.data_as(C.POINTER(C.c_double)),
+                            bS.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0
+    assert nd.value == 0
+    for k, s in enumerate(items):
+        Sk, bk = emul.schur(s)
+        assert np.array_equal(S[k], Sk)
+        assert np.array_equal(bS[k], bk)
