@@ -262,6 +262,27 @@ int vio_solve_batched_lockstep(int device, vio_batch_item *items, int64_t n_item
  * after batch pays allocations once); this frees them.                                                                */
 int vio_lockstep_release(void);
 
+/* ---- IMU pre-integration -------------------------------------------------------------------------
+ * IntegrationBase(acc_0, gyr_0, ba, bg) followed by push_back(dt, acc, gyr) for every further sample
+ * (A17/include/factor/integration_base.h:13-158: midpoint integration, jacobian = F jacobian,
+ * covariance = F covariance F^T + V noise V^T), for a batch of segments at once - what processIMU accumulates
+ * between two keyframes (A17/src/estimator.cpp:75-110), and what repropagate() redoes when the bias estimate moved.
+ * Segment k owns samples [seg_ptr[k], seg_ptr[k+1]); its first sample is (acc_0, gyr_0) and that sample's dt is not
+ * read.  Outputs use the layout of the EdgeImu constants in vio_graph (imu_sum_dt ... imu_covariance).           */
+typedef struct vio_imu_segments {
+    int32_t n_segments;
+    int32_t reserved;
+    const int32_t *seg_ptr;  /* n_segments + 1                                                      */
+    const double *dt;        /* per sample                                                          */
+    const double *acc;       /* per sample x 3                                                      */
+    const double *gyr;       /* per sample x 3                                                      */
+    const double *ba;        /* per segment x 3: linearized_ba                                      */
+    const double *bg;        /* per segment x 3: linearized_bg                                      */
+    double acc_n, acc_w, gyr_n, gyr_w; /* ACC_N, ACC_W, GYR_N, GYR_W (A17/include/parameters.h)       */
+} vio_imu_segments;
+int vio_preintegrate(int device, const vio_imu_segments *in, double *sum_dt, double *delta_p, double *delta_q,
+                     double *delta_v, double *jacobian, double *covariance);
+
 /* ---- GENERIC_PROBLEM lane: user-defined host edges --------------------------------------------------------------
  * Problem(GENERIC_PROBLEM) lets callers subclass Vertex/Edge with their own virtual ComputeResidual /
  * ComputeJacobians / Plus (A15/app/CurveFitting.cpp:14-48, A17/test/CurveFitting.cpp:8-45).  Those virtuals are host

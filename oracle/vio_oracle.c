@@ -925,3 +925,89 @@ int orc_linearize_bsr(const vio_graph *g, const int32_t *rowptr, const int32_t *
 int orc_linearize_sample(const vio_graph *g, int64_t lm_begin, int64_t lm_end, double *checksum) {
     return linearize_range(g, NULL, NULL, NULL, NULL, NULL, NULL, lm_begin, lm_end, checksum);
 }
+
+/* ================================================================================================
+ * IntegrationBase (A17/include/factor/integration_base.h)
+ *   ctor :13-30  jacobian = I, covariance = 0, noise = diag(ACC_N^2, GYR_N^2, ACC_N^2, GYR_N^2, ACC_W^2, GYR_W^2) x I3
+ *   midPointIntegration :55-130, propagate :132-158 (delta_q.normalize() after every sample)
+ * ================================================================================================ */
+int orc_preintegrate(int32_t n, const double *dt, const double *acc, const double *gyr, const double *ba, const double *bg,
+                     const double *noise, double *sum_dt, double *delta_p, double *delta_q_xyzw, double *delta_v,
+                     double *jac225, double *cov225) {
+    double J[225], P[225], F[225], V[270], T[225], Q[18];
+    double p[3] = {0, 0, 0}, v[3] = {0, 0, 0}, q[4] = {0, 0, 0, 1}, a0[3], g0[3], sdt = 0.0;
+    if (n < 1) return VIO_ERR_INVALID;
+    for (int i = 0; i < 225; ++i) { J[i] = (i / 15 == i % 15) ? 1.0 : 0.0; P[i] = 0.0; }
+    for (int k = 0; k < 3; ++k) {
+        Q[k] = noise[0] * noise[0]; Q[3 + k] = noise[2] * noise[2]; Q[6 + k] = noise[0] * noise[0];
+        Q[9 + k] = noise[2] * noise[2]; Q[12 + k] = noise[1] * noise[1]; Q[15 + k] = noise[3] * noise[3];
+        a0[k] = acc[k]; g0[k] = gyr[k];
+    }
+    for (int i = 1; i < n; ++i) {
+        const double h = dt[i];
+        const double *a1 = acc + 3 * i, *g1 = gyr + 3 * i;
+        double a0x[3], a1x[3], w[3], ua0[3], ua1[3], q1[4], dqh[4], R0[9], R1[9], A0[9], A1[9], W[9], M0[9], M1[9], IW[9], M1w[9];
+        for (int k = 0; k < 3; ++k) { a0x[k] = a0[k] - ba[k]; a1x[k] = a1[k] - ba[k]; w[k] = 0.5 * (g0[k] + g1[k]) - bg[k]; }
+        q_rot(q, a0x, ua0);
+        dqh[0] = w[0] * h / 2; dqh[1] = w[1] * h / 2; dqh[2] = w[2] * h / 2; dqh[3] = 1.0;
+        q_mul(q, dqh, q1);
+        q_rot(q1, a1x, ua1);
+        q_toR(q, R0); q_toR(q1, R1);
+        hat3(a0x, A0); hat3(a1x, A1); hat3(w, W);
+        m3_mul(R0, A0, M0); m3_mul(R1, A1, M1);
+        for (int k = 0; k < 9; ++k) IW[k] = ((k % 4 == 0) ? 1.0 : 0.0) - W[k] * h;
+        m3_mul(M1, IW, M1w);
+        memset(F, 0, sizeof(F)); memset(V, 0, sizeof(V));
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                const double id = r == c ? 1.0 : 0.0, m0 = M0[3 * r + c], m1 = M1[3 * r + c], m1w = M1w[3 * r + c];
+                const double r0 = R0[3 * r + c], r1 = R1[3 * r + c];
+#define FB(br, bc) F[(3 * (br) + r) * 15 + 3 * (bc) + c]
+#define VB(br, bc) V[(3 * (br) + r) * 18 + 3 * (bc) + c]
+                FB(0, 0) = id; FB(0, 1) = -0.25 * m0 * h * h + -0.25 * m1w * h * h; FB(0, 2) = id * h;
+                FB(0, 3) = -0.25 * (r0 + r1) * h * h; FB(0, 4) = -0.25 * m1 * h * h * -h;
+                FB(1, 1) = IW[3 * r + c]; FB(1, 4) = -1.0 * id * h;
+                FB(2, 1) = -0.5 * m0 * h + -0.5 * m1w * h; FB(2, 2) = id; FB(2, 3) = -0.5 * (r0 + r1) * h;
+                FB(2, 4) = -0.5 * m1 * h * -h; FB(3, 3) = id; FB(4, 4) = id;
+                VB(0, 0) = 0.25 * r0 * h * h; VB(0, 1) = 0.25 * -m1 * h * h * 0.5 * h; VB(0, 2) = 0.25 * r1 * h * h;
+                VB(0, 3) = VB(0, 1); VB(1, 1) = 0.5 * id * h; VB(1, 3) = 0.5 * id * h;
+                VB(2, 0) = 0.5 * r0 * h; VB(2, 1) = 0.5 * -m1 * h * 0.5 * h; VB(2, 2) = 0.5 * r1 * h; VB(2, 3) = VB(2, 1);
+                VB(3, 4) = id * h; VB(4, 5) = id * h;
+#undef FB
+#undef VB
+            }
+        /* jacobian = F jacobian ; covariance = F covariance F^T + V noise V^T */
+        for (int r = 0; r < 15; ++r)
+            for (int c = 0; c < 15; ++c) {
+                double a = 0.0, b = 0.0;
+                for (int k = 0; k < 15; ++k) { a += F[15 * r + k] * J[15 * k + c]; b += F[15 * r + k] * P[15 * k + c]; }
+                T[15 * r + c] = b;
+                cov225[15 * r + c] = a; /* scratch: new jacobian */
+            }
+        memcpy(J, cov225, sizeof(J));
+        for (int r = 0; r < 15; ++r)
+            for (int c = 0; c < 15; ++c) {
+                double a = 0.0;
+                for (int k = 0; k < 15; ++k) a += T[15 * r + k] * F[15 * c + k];
+                for (int k = 0; k < 18; ++k) a += V[18 * r + k] * Q[k] * V[18 * c + k];
+                P[15 * r + c] = a;
+            }
+        for (int k = 0; k < 3; ++k) {
+            const double ua = 0.5 * (ua0[k] + ua1[k]);
+            p[k] = p[k] + v[k] * h + 0.5 * ua * h * h;
+            v[k] = v[k] + ua * h;
+        }
+        {
+            const double nq = sqrt(q1[0] * q1[0] + q1[1] * q1[1] + q1[2] * q1[2] + q1[3] * q1[3]);
+            for (int k = 0; k < 4; ++k) q[k] = q1[k] / nq;
+        }
+        sdt += h;
+        for (int k = 0; k < 3; ++k) { a0[k] = a1[k]; g0[k] = g1[k]; }
+    }
+    *sum_dt = sdt;
+    for (int k = 0; k < 3; ++k) { delta_p[k] = p[k]; delta_v[k] = v[k]; }
+    for (int k = 0; k < 4; ++k) delta_q_xyzw[k] = q[k];
+    memcpy(jac225, J, sizeof(J));
+    memcpy(cov225, P, sizeof(P));
+    return VIO_OK;
+}

@@ -70,6 +70,12 @@ int orc_linearize_bsr(const vio_graph *g, const int32_t *rowptr, const int32_t *
  * work cannot be optimised away; used to time the reference dataflow per edge on a bounded sample */
 int orc_linearize_sample(const vio_graph *g, int64_t lm_begin, int64_t lm_end, double *checksum);
 
+/* --- IMU pre-integration: IntegrationBase::push_back over samples 1..n-1 after construction with sample 0
+ * (A17/include/factor/integration_base.h:13-158).  noise = {ACC_N, ACC_W, GYR_N, GYR_W}. ------------------------ */
+int orc_preintegrate(int32_t n, const double *dt, const double *acc, const double *gyr, const double *ba, const double *bg,
+                     const double *noise, double *sum_dt, double *delta_p, double *delta_q_xyzw, double *delta_v,
+                     double *jac225, double *cov225);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,3 +136,17 @@ def linearize_sample(scene, lm_begin, lm_end):
     rc = lib().orc_linearize_sample(C.byref(g), lm_begin, lm_end, C.byref(cs))
     assert rc == 0, rc
     return cs.value
+
+
+def preintegrate(dt, acc, gyr, ba, bg, noise):
+    """orc_preintegrate on one segment -> (sum_dt, dp, dq, dv, jac[225], cov[225])."""
+    L = lib()
+    dt, acc, gyr = (np.ascontiguousarray(x, np.float64) for x in (dt, acc, gyr))
+    ba, bg, noise = (np.ascontiguousarray(x, np.float64) for x in (ba, bg, noise))
+    sd = C.c_double()
+    dp, dq, dv, jac, cov = np.zeros(3), np.zeros(4), np.zeros(3), np.zeros(225), np.zeros(225)
+    L.orc_preintegrate.argtypes = [C.c_int32, _dp, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_double), _dp, _dp, _dp, _dp, _dp]
+    rc = L.orc_preintegrate(dt.shape[0], _d(dt), _d(acc), _d(gyr), _d(ba), _d(bg), _d(noise), C.byref(sd), _d(dp), _d(dq), _d(dv),
+                            _d(jac), _d(cov))
+    assert rc == 0, rc
+    return sd.value, dp, dq, dv, jac, cov

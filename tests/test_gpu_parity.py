@@ -435,3 +435,32 @@ def test_marginalize_vs_golden(vio, scene_file, marg_file):
     assert np.abs(JHJ - np.eye(well.sum())).max() <= 1e-6
     # chi2 only sees |err_prior| (A17/src/backend/problem.cc:505-506); the noise rows move it by < 1 %
     assert abs(np.linalg.norm(m["err"]) - np.linalg.norm(g["err"])) <= 1e-2 * np.linalg.norm(g["err"])
+
+
+def test_preintegration_vs_golden(vio):
+    """vio_preintegrate (IntegrationBase::push_back for a batch of segments, SURVEY 8f-3) against vectors from the
+    unmodified reference and against the C oracle; ragged segments incl. a one-sample and an empty one."""
+    from tests import oraclelib as orc
+    g = _gold("preint_v17.npz")
+    out = vio.capi.preintegrate(g["seg_ptr"], g["dt"], g["acc"], g["gyr"], g["ba"], g["bg"], g["noise"])
+    for key in ("sum_dt", "delta_p", "delta_q", "delta_v", "jacobian", "covariance"):
+        for k in range(len(g["seg_ptr"]) - 1):
+            ref = np.atleast_1d(g[key][k])
+            scale = max(np.abs(ref).max(), 1e-300)
+            assert np.abs(np.atleast_1d(out[key][k]) - ref).max() <= 1e-9 * scale, (key, k)
+    # the one-sample segment is the identity pre-integration
+    assert out["sum_dt"][0] == 0.0 and np.array_equal(out["delta_q"][0], [0, 0, 0, 1])
+    assert np.array_equal(out["jacobian"][0].reshape(15, 15), np.eye(15)) and not out["covariance"][0].any()
+    # a batch with an empty segment in the middle, against the oracle
+    sp = np.array([0, 21, 21, 61], np.int32)
+    o2 = vio.capi.preintegrate(sp, g["dt"][:61], g["acc"][:61], g["gyr"][:61], g["ba"][:3], g["bg"][:3], g["noise"])
+    for k, (a, b) in enumerate([(0, 21), (21, 21), (21, 61)]):
+        if a == b:
+            assert o2["sum_dt"][k] == 0.0 and not o2["covariance"][k].any()
+            continue
+        sd, dp, dq, dv, jac, cov = orc.preintegrate(g["dt"][a:b], g["acc"][a:b], g["gyr"][a:b], g["ba"][k], g["bg"][k], g["noise"])
+        assert abs(o2["sum_dt"][k] - sd) <= 1e-14
+        assert rel_max(o2["delta_p"][k], dp) <= 1e-9 and rel_max(o2["delta_v"][k], dv) <= 1e-9
+        assert rel_max(o2["jacobian"][k], jac) <= 1e-9 and rel_max(o2["covariance"][k], cov) <= 1e-9
+    # the outputs feed EdgeImu unchanged: same layout as the vio_graph IMU arrays
+    assert out["jacobian"].shape == (6, 225) and out["delta_q"].shape == (6, 4)

@@ -186,3 +186,18 @@ def test_pose_plus_matches_oracle(vio):
         orc.lib().orc_pose_plus(pi.ctypes.data_as(C.POINTER(C.c_double)), np.ascontiguousarray(dx[i]).ctypes.data_as(C.POINTER(C.c_double)))
         exp[i] = pi
     assert np.abs(out - exp).max() <= 1e-15
+
+
+def test_oracle_preintegration_vs_golden():
+    """IntegrationBase::push_back (SURVEY 8f-3): the C restatement against vectors from the unmodified reference -
+    ragged segments (1 .. 200 samples), jittered dt, non-zero linearisation biases."""
+    g = np.load(os.path.join(GOLD, "preint_v17.npz"))
+    sp = g["seg_ptr"]
+    for k in range(len(sp) - 1):
+        a, b = sp[k], sp[k + 1]
+        sd, dp, dq, dv, jac, cov = orc.preintegrate(g["dt"][a:b], g["acc"][a:b], g["gyr"][a:b], g["ba"][k], g["bg"][k], g["noise"])
+        assert abs(sd - g["sum_dt"][k]) <= 1e-15 * max(1.0, g["sum_dt"][k])
+        for mine, ref in ((dp, g["delta_p"][k]), (dq, g["delta_q"][k]), (dv, g["delta_v"][k]), (jac, g["jacobian"][k]),
+                          (cov, g["covariance"][k])):
+            scale = max(np.abs(ref).max(), 1e-300)
+            assert np.abs(mine - ref).max() <= 1e-12 * scale

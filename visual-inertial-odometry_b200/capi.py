@@ -87,7 +87,7 @@ EXPORTS = [
     "vio_solve", "vio_linearize", "vio_chi2", "vio_solve_step", "vio_apply_step", "vio_rollback_step",
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
     "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
-    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_get_coarse", "vio_marginalize",
+    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_get_coarse", "vio_preintegrate", "vio_marginalize",
 ]
 
 _lib = None
@@ -533,6 +533,35 @@ def solve_batched(scenes, iterations, opts=None, device=0, n_workers=16, lockste
     if rc != VIO_OK:
         raise VioError(rc, "vio_solve_batched: item errors " + str([items[i].rc for i in range(n) if items[i].rc][:5]))
     return outs, dt
+
+
+class VioImuSegments(C.Structure):
+    _fields_ = [("n_segments", C.c_int32), ("reserved", C.c_int32), ("seg_ptr", C.POINTER(C.c_int32)),
+                ("dt", _dp), ("acc", _dp), ("gyr", _dp), ("ba", _dp), ("bg", _dp),
+                ("acc_n", C.c_double), ("acc_w", C.c_double), ("gyr_n", C.c_double), ("gyr_w", C.c_double)]
+
+
+def preintegrate(seg_ptr, dt, acc, gyr, ba, bg, noise, device=0):
+    """IntegrationBase::push_back over a batch of IMU segments on the device (vio_preintegrate).
+    noise = (ACC_N, ACC_W, GYR_N, GYR_W).  -> dict with the EdgeImu constants per segment."""
+    seg_ptr = np.ascontiguousarray(seg_ptr, np.int32)
+    n = seg_ptr.shape[0] - 1
+    dt, acc, gyr = (np.ascontiguousarray(x, np.float64) for x in (dt, acc, gyr))
+    ba, bg = np.ascontiguousarray(ba, np.float64), np.ascontiguousarray(bg, np.float64)
+    s = VioImuSegments()
+    s.n_segments = n
+    s.seg_ptr = seg_ptr.ctypes.data_as(C.POINTER(C.c_int32))
+    s.dt, s.acc, s.gyr, s.ba, s.bg = _d(dt), _d(acc), _d(gyr), _d(ba), _d(bg)
+    s.acc_n, s.acc_w, s.gyr_n, s.gyr_w = (float(x) for x in noise)
+    out = dict(sum_dt=np.zeros(n), delta_p=np.zeros((n, 3)), delta_q=np.zeros((n, 4)), delta_v=np.zeros((n, 3)),
+               jacobian=np.zeros((n, 225)), covariance=np.zeros((n, 225)))
+    L = lib()
+    L.vio_preintegrate.argtypes = [C.c_int, C.POINTER(VioImuSegments), _dp, _dp, _dp, _dp, _dp, _dp]
+    rc = L.vio_preintegrate(device, C.byref(s), _d(out["sum_dt"]), _d(out["delta_p"]), _d(out["delta_q"]), _d(out["delta_v"]),
+                            _d(out["jacobian"]), _d(out["covariance"]))
+    if rc != VIO_OK:
+        raise VioError(rc, "vio_preintegrate")
+    return out
 
 
 def measure_fp64_peak(device=0):

@@ -27,6 +27,7 @@
 #include "vio_grouped.cuh"
 #include "vio_marg.cuh"
 #include "vio_batch.cuh"
+#include "vio_preint.cuh"
 
 #define VIO_VERSION_STR "vio_b200 0.1 (sm_100a)"
 
@@ -1748,6 +1749,45 @@ int vio_lockstep_release(void) {
     for (auto *v : {&cache.pose, &cache.sb, &cache.idt, &cache.idp, &cache.idq, &cache.idv, &cache.iba, &cache.ibg, &cache.ijac, &cache.icov})
         std::vector<double>().swap(*v);
     for (auto *v : {&cache.ipi, &cache.isi, &cache.ipj, &cache.isj}) std::vector<int32_t>().swap(*v);
+    return VIO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// IMU pre-integration
+// -------------------------------------------------------------------------------------------------
+int vio_preintegrate(int device, const vio_imu_segments *in, double *sum_dt, double *delta_p, double *delta_q, double *delta_v,
+                     double *jacobian, double *covariance) {
+    if (!in || in->n_segments < 0 || !sum_dt || !delta_p || !delta_q || !delta_v || !jacobian || !covariance) return VIO_ERR_INVALID;
+    if (in->n_segments == 0) return VIO_OK;
+    if (!in->seg_ptr || !in->dt || !in->acc || !in->gyr || !in->ba || !in->bg) return VIO_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return VIO_ERR_NO_DEVICE;
+    vio_problem *p = nullptr;  // CK() wants a handle for the message; none here
+    CK(cudaSetDevice(device));
+    const int n = in->n_segments;
+    for (int k = 0; k < n; ++k)
+        if (in->seg_ptr[k + 1] < in->seg_ptr[k] || in->seg_ptr[k] < 0) return VIO_ERR_INVALID;
+    const size_t ns = (size_t)in->seg_ptr[n];
+    DBuf<int> d_ptr;
+    DBuf<double> d_dt, d_acc, d_gyr, d_ba, d_bg, d_out;
+    cudaStream_t st = nullptr;
+    CK(upload(d_ptr, in->seg_ptr, (size_t)n + 1, st)); CK(upload(d_dt, in->dt, ns, st)); CK(upload(d_acc, in->acc, 3 * ns, st));
+    CK(upload(d_gyr, in->gyr, 3 * ns, st)); CK(upload(d_ba, in->ba, 3 * (size_t)n, st)); CK(upload(d_bg, in->bg, 3 * (size_t)n, st));
+    CK(d_out.alloc((size_t)n * (1 + 3 + 4 + 3 + 225 + 225)));
+    PreintView v;
+    v.n_seg = n; v.seg_ptr = d_ptr.p; v.dt = d_dt.p; v.acc = d_acc.p; v.gyr = d_gyr.p; v.ba = d_ba.p; v.bg = d_bg.p;
+    v.acc_n = in->acc_n; v.acc_w = in->acc_w; v.gyr_n = in->gyr_n; v.gyr_w = in->gyr_w;
+    v.sum_dt = d_out.p; v.dp = v.sum_dt + n; v.dq = v.dp + 3 * (size_t)n; v.dv = v.dq + 4 * (size_t)n;
+    v.jac = v.dv + 3 * (size_t)n; v.cov = v.jac + 225 * (size_t)n;
+    k_preintegrate<<<n, 256, 0, st>>>(v);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(sum_dt, v.sum_dt, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(delta_p, v.dp, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(delta_q, v.dq, 4 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(delta_v, v.dv, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(jacobian, v.jac, 225 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(covariance, v.cov, 225 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return VIO_OK;
 }
 

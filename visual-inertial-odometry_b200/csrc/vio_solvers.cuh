@@ -796,7 +796,8 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
         }
         __syncthreads();
     };
-    if (cv.apc > 0 && bb > 0.0) {
+    bool use_coarse = cv.apc > 0;
+    if (use_coarse && bb > 0.0) {
         // the init kernel applied block-Jacobi only: rc = Z^T r, add the coarse term to z and recompute r.z
         __syncthreads();
         restrict_publish(r_s);
@@ -811,6 +812,26 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
         grid_barrier(bar, nblk);
         rz = sum_partials_w0(part_b, nblk, bc);
         grid_barrier(bar, nblk);  // part_b and the exchange buffer are rewritten in the first iteration
+        if (!(rz > 0.0) || !(rz < 1e300)) {
+            // the coarse inverse broke down (a pivot block lost definiteness to rounding): this solve falls back to
+            // block-Jacobi.  rz is bitwise the same on every CTA, so the decision is uniform.
+            use_coarse = false;
+            double l2 = 0.0;
+            for (int t = tid; t < nrow; t += nt) {
+                const int ib = t / 6, rw = t % 6;
+                const double *mi = mi_s + 36 * (size_t)ib + 6 * rw;
+                const double *rb = r_s + 6 * (size_t)ib;
+                const double z = mi[0] * rb[0] + mi[1] * rb[1] + mi[2] * rb[2] + mi[3] * rb[3] + mi[4] * rb[4] + mi[5] * rb[5];
+                z_s[t] = z;
+                s.z[r0 + t] = z;
+                l2 += rb[rw] * z;
+            }
+            const double a2 = cta_sum(l2, red);
+            if (tid == 0) part_b[blockIdx.x] = a2;
+            grid_barrier(bar, nblk);
+            rz = sum_partials_w0(part_b, nblk, bc);
+            grid_barrier(bar, nblk);
+        }
     }
     const int G = BPCG_P_GROUP;
     const int sub = tid % G;
@@ -868,12 +889,12 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
                 const double a = cta_sum(l_pw, red);
                 if (tid == 0) part_a[blockIdx.x] = a;
             }
-            if (cv.apc > 0) restrict_publish(w_s);  // Z^T (S p) rides on the same barrier: rc -= alpha Z^T S p below
+            if (use_coarse) restrict_publish(w_s);  // Z^T (S p) rides on the same barrier: rc -= alpha Z^T S p below
             PCG_MARK(c_spmv);
             grid_barrier(bar, nblk);
             const double alpha = rz / sum_partials_w0(part_a, nblk, bc);
             PCG_MARK(c_bar1);
-            if (cv.apc > 0)
+            if (use_coarse)
                 for (int j = tid; j < cv.nc; j += nt) rc_s[j] -= alpha * __ldcg(cv.rc + j);
             // ---- x += alpha p ; r -= alpha w ; z = Minv r ; partial r.z, r.r   (own rows, all in shared memory)
             for (int t = tid; t < nrow; t += nt) {
@@ -882,7 +903,7 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
             }
             __syncthreads();
             double l_rz2 = 0.0, l_rr = 0.0;
-            if (cv.apc == 0) {
+            if (!use_coarse) {
                 for (int t = tid; t < nrow; t += nt) {
                     const int ib = t / 6, rw = t % 6;
                     const double *mi = mi_s + 36 * (size_t)ib + 6 * rw;
