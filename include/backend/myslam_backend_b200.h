@@ -224,6 +224,24 @@ private:
     Vec3 pts_i_, pts_j_;
 };
 
+// 2-vertex [VertexPointXYZ, VertexPose] factor (15-vio-backend/backend/edge_reprojection.h:56-83)
+class EdgeReprojectionXYZ : public Edge {
+public:
+    EIGEN_MAKE_ALIGNED_OPERATOR_NEW;
+    explicit EdgeReprojectionXYZ(const Vec3 &pts_i);
+    std::string TypeInfo() const override { return "EdgeReprojectionXYZ"; }
+    void ComputeResidual() override;
+    void ComputeJacobians() override;
+    void SetTranslationImuFromCamera(Eigen::Quaterniond &qic_, Vec3 &tic_);
+    const Vec3 &Obs() const { return obs_; }
+    const Qd &Qic() const { return qic; }
+    const Vec3 &Tic() const { return tic; }
+private:
+    Qd qic = Qd::Identity();
+    Vec3 tic = Vec3::Zero();
+    Vec3 obs_;
+};
+
 class EdgeSE3Prior : public Edge {
 public:
     EIGEN_MAKE_ALIGNED_OPERATOR_NEW;

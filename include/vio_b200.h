@@ -117,6 +117,20 @@ typedef struct vio_graph {
     double gravity[3];           /* global G (A17/include/parameters.h:49)                 */
 
     int32_t storage;             /* VIO_STORAGE_* for the reduced camera system            */
+
+    /* VertexPointXYZ (A15/backend/vertex_point_xyz.h:12-18) + EdgeReprojectionXYZ, the 2-vertex factor [X_w, T_i]
+     * (A15/backend/edge_reprojection.cc:113-163; same code in A17/src/backend/edge_reprojection.cc:130-180).  Points
+     * are landmark-class vertices of local dimension 3, ordered after the inverse-depth landmarks:
+     * Hessian_ = [P | n_landmark | 3 n_point].  Information = rp_info*I2, loss rp_loss (shared with EdgeReprojection);
+     * extrinsics q_ic/t_ic (or the fixed ext_pose vertex).  May be mixed with inverse-depth landmarks.
+     * Not supported together with vio_set_shard, vio_marginalize or the lock-step batch.              */
+    int32_t n_point;
+    int32_t reserved_xyz;
+    const double *point_xyz;     /* n_point x 3 world coordinates                          */
+    int64_t n_reproj_xyz;
+    const int32_t *rx_point;     /* n_reproj_xyz                                           */
+    const int32_t *rx_pose;      /* observing pose index                                   */
+    const double *rx_obs;        /* n_reproj_xyz x 2 (obs_.head<2>())                      */
 } vio_graph;
 
 /* ---- LM options / statistics -------------------------------------------------------------- */
@@ -193,6 +207,12 @@ int vio_get_prior(vio_problem *p, double *b_prior /* P */, double *err_prior /* 
 /* overwrite the current estimates (used by per-iteration re-synchronised parity tests)       */
 int vio_set_vertices(vio_problem *p, const double *pose, const double *speedbias, const double *inv_depth);
 int vio_get_vertices(vio_problem *p, double *pose, double *speedbias, double *inv_depth);
+/* VertexPointXYZ estimates (n_point x 3) */
+int vio_set_points(vio_problem *p, const double *point_xyz);
+int vio_get_points(vio_problem *p, double *point_xyz);
+/* debug tap on the point blocks of the last linearisation / step: Hmm 3x3 blocks (n_point x 9 row-major), b (n_point x 3),
+ * delta_x (n_point x 3); any pointer may be NULL */
+int vio_get_point_system(vio_problem *p, double *Hmm, double *b, double *dx);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_stats *stats);

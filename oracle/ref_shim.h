@@ -39,6 +39,9 @@ int REF_FN(step)(const vio_graph *g, const ref_prior *prior, double lambda, doub
 /* Problem::Solve(iterations); final vertex parameters written to pose/speedbias/inv_depth; prior b/err read back */
 int REF_FN(solve)(const vio_graph *g, const ref_prior *prior, int32_t iterations, double *pose, double *speedbias,
                   double *inv_depth, double *b_prior_out, double *err_prior_out, ref_result *res);
+/* the same with the VertexPointXYZ estimates (n_point x 3) read back as well */
+int REF_FN(solve_points)(const vio_graph *g, const ref_prior *prior, int32_t iterations, double *pose, double *speedbias,
+                         double *inv_depth, double *point_xyz, double *b_prior_out, double *err_prior_out, ref_result *res);
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@
 #include "backend/problem.h"
 #include "backend/vertex_pose.h"
 #include "backend/vertex_inverse_depth.h"
+#include "backend/vertex_point_xyz.h"
 #include "backend/edge_reprojection.h"
 #include "backend/edge_prior.h"
 #undef private
@@ -36,6 +37,7 @@ struct Built {
     std::unique_ptr<Problem> problem;
     std::vector<std::shared_ptr<VertexPose>> poses;
     std::vector<std::shared_ptr<VertexInverseDepth>> landmarks;
+    std::vector<std::shared_ptr<VertexPointXYZ>> points;
 };
 
 struct CoutCapture {
@@ -90,6 +92,27 @@ bool build(const vio_graph *g, Built &B) {
         e->SetTranslationImuFromCamera(qic, tic);
         std::vector<std::shared_ptr<Vertex>> vs{B.landmarks[g->rp_landmark[i]], B.poses[g->rp_pose_i[i]],
                                                 B.poses[g->rp_pose_j[i]]};
+        e->SetVertex(vs);
+        if (g->rp_info != 1.0) {
+            MatXX info = MatXX::Identity(2, 2) * g->rp_info;
+            e->SetInformation(info);
+        }
+        B.problem->AddEdge(e);
+    }
+    // VertexPointXYZ + EdgeReprojectionXYZ, created after the inverse-depth landmarks: Hessian_ = [P | M1 | 3 Mx]
+    for (int i = 0; i < g->n_point; ++i) {
+        std::shared_ptr<VertexPointXYZ> v(new VertexPointXYZ());
+        VecX x(3);
+        for (int k = 0; k < 3; ++k) x[k] = g->point_xyz[3 * i + k];
+        v->SetParameters(x);
+        B.problem->AddVertex(v);
+        B.points.push_back(v);
+    }
+    for (int64_t i = 0; i < g->n_reproj_xyz; ++i) {
+        Vec3 obs(g->rx_obs[2 * i], g->rx_obs[2 * i + 1], 1.0);
+        std::shared_ptr<EdgeReprojectionXYZ> e(new EdgeReprojectionXYZ(obs));
+        e->SetTranslationImuFromCamera(qic, tic);
+        std::vector<std::shared_ptr<Vertex>> vs{B.points[g->rx_point[i]], B.poses[g->rx_pose[i]]};
         e->SetVertex(vs);
         if (g->rp_info != 1.0) {
             MatXX info = MatXX::Identity(2, 2) * g->rp_info;
@@ -153,8 +176,14 @@ int ref15_step(const vio_graph *g, const ref_prior *, double lambda, double *S, 
     return VIO_OK;
 }
 
-int ref15_solve(const vio_graph *g, const ref_prior *, int32_t iterations, double *pose, double *, double *inv_depth,
-                double *, double *, ref_result *res) {
+int ref15_solve_points(const vio_graph *g, const ref_prior *, int32_t iterations, double *pose, double *, double *inv_depth,
+                       double *point_xyz, double *, double *, ref_result *res);
+int ref15_solve(const vio_graph *g, const ref_prior *pr, int32_t iterations, double *pose, double *sb, double *inv_depth,
+                double *bp, double *ep, ref_result *res) {
+    return ref15_solve_points(g, pr, iterations, pose, sb, inv_depth, nullptr, bp, ep, res);
+}
+int ref15_solve_points(const vio_graph *g, const ref_prior *, int32_t iterations, double *pose, double *, double *inv_depth,
+                       double *point_xyz, double *, double *, ref_result *res) {
     Built B;
     if (!build(g, B)) return VIO_ERR_UNSUPPORTED;
     std::string log;
@@ -188,6 +217,9 @@ int ref15_solve(const vio_graph *g, const ref_prior *, int32_t iterations, doubl
     for (int i = 0; i < g->n_pose; ++i)
         for (int k = 0; k < 7; ++k) pose[7 * i + k] = B.poses[i]->Parameters()[k];
     for (int i = 0; i < g->n_landmark; ++i) inv_depth[i] = B.landmarks[i]->Parameters()[0];
+    if (point_xyz)
+        for (int i = 0; i < g->n_point; ++i)
+            for (int k = 0; k < 3; ++k) point_xyz[3 * i + k] = B.points[i]->Parameters()[k];
     return VIO_OK;
 }
 }

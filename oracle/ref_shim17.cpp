@@ -20,6 +20,7 @@
 #include "backend/vertex_pose.h"
 #include "backend/vertex_speedbias.h"
 #include "backend/vertex_inverse_depth.h"
+#include "backend/vertex_point_xyz.h"
 #include "backend/edge_reprojection.h"
 #include "backend/edge_prior.h"
 #include "backend/edge_imu.h"
@@ -44,6 +45,7 @@ struct Built {
     std::vector<std::shared_ptr<VertexPose>> poses;
     std::vector<std::shared_ptr<VertexSpeedBias>> sbs;
     std::vector<std::shared_ptr<VertexInverseDepth>> landmarks;
+    std::vector<std::shared_ptr<VertexPointXYZ>> points;
     std::vector<std::unique_ptr<IntegrationBase>> preint;
     std::unique_ptr<LossFunction> loss;
     ~Built() { problem.reset(); }
@@ -148,6 +150,32 @@ bool build(const vio_graph *g, const ref_prior *prior, Built &B) {
         if (B.loss) e->SetLossFunction(B.loss.get());
         B.problem->AddEdge(e);
     }
+    // VertexPointXYZ + EdgeReprojectionXYZ, created after the inverse-depth landmarks: Hessian_ = [P | M1 | 3 Mx]
+    for (int i = 0; i < g->n_point; ++i) {
+        std::shared_ptr<VertexPointXYZ> v(new VertexPointXYZ());
+        VecX x(3);
+        for (int k = 0; k < 3; ++k) x[k] = g->point_xyz[3 * i + k];
+        v->SetParameters(x);
+        B.problem->AddVertex(v);
+        B.points.push_back(v);
+    }
+    if (g->n_reproj_xyz > 0) {
+        const double *ex = g->ext_pose >= 0 ? g->pose + 7 * g->ext_pose : nullptr;
+        Eigen::Quaterniond qic = ex ? Eigen::Quaterniond(ex[6], ex[3], ex[4], ex[5])
+                                    : Eigen::Quaterniond(g->q_ic[3], g->q_ic[0], g->q_ic[1], g->q_ic[2]);
+        Vec3 tic = ex ? Vec3(ex[0], ex[1], ex[2]) : Vec3(g->t_ic[0], g->t_ic[1], g->t_ic[2]);
+        for (int64_t i = 0; i < g->n_reproj_xyz; ++i) {
+            Vec3 obs(g->rx_obs[2 * i], g->rx_obs[2 * i + 1], 1.0);
+            std::shared_ptr<EdgeReprojectionXYZ> e(new EdgeReprojectionXYZ(obs));
+            e->SetTranslationImuFromCamera(qic, tic);
+            std::vector<std::shared_ptr<Vertex>> vs{B.points[g->rx_point[i]], B.poses[g->rx_pose[i]]};
+            e->SetVertex(vs);
+            MatXX info = MatXX::Identity(2, 2) * g->rp_info;
+            e->SetInformation(info);
+            if (B.loss) e->SetLossFunction(B.loss.get());
+            B.problem->AddEdge(e);
+        }
+    }
     if (prior && prior->dim > 0) {
         MatXX H(prior->dim, prior->dim);
         VecX b(prior->dim);
@@ -224,8 +252,14 @@ int ref17_step(const vio_graph *g, const ref_prior *prior, double lambda, double
     return VIO_OK;
 }
 
+int ref17_solve_points(const vio_graph *g, const ref_prior *prior, int32_t iterations, double *pose, double *speedbias,
+                       double *inv_depth, double *point_xyz, double *b_prior_out, double *err_prior_out, ref_result *res);
 int ref17_solve(const vio_graph *g, const ref_prior *prior, int32_t iterations, double *pose, double *speedbias,
                 double *inv_depth, double *b_prior_out, double *err_prior_out, ref_result *res) {
+    return ref17_solve_points(g, prior, iterations, pose, speedbias, inv_depth, nullptr, b_prior_out, err_prior_out, res);
+}
+int ref17_solve_points(const vio_graph *g, const ref_prior *prior, int32_t iterations, double *pose, double *speedbias,
+                       double *inv_depth, double *point_xyz, double *b_prior_out, double *err_prior_out, ref_result *res) {
     Built B;
     if (!build(g, prior, B)) return VIO_ERR_UNSUPPORTED;
     std::string log;
@@ -261,6 +295,9 @@ int ref17_solve(const vio_graph *g, const ref_prior *prior, int32_t iterations, 
     for (int i = 0; i < g->n_speedbias; ++i)
         for (int k = 0; k < 9; ++k) speedbias[9 * i + k] = B.sbs[i]->Parameters()[k];
     for (int i = 0; i < g->n_landmark; ++i) inv_depth[i] = B.landmarks[i]->Parameters()[0];
+    if (point_xyz)
+        for (int i = 0; i < g->n_point; ++i)
+            for (int k = 0; k < 3; ++k) point_xyz[3 * i + k] = B.points[i]->Parameters()[k];
     if (b_prior_out) copy_out(B.problem->b_prior_, b_prior_out);
     if (err_prior_out) copy_out(B.problem->err_prior_, err_prior_out);
     return VIO_OK;

@@ -405,7 +405,7 @@ static int make_ordering(const vio_graph *g, ordering *o) {
         if (ent >= 0) { if (ent >= C || o->pose_off[ent] >= 0) return VIO_ERR_INVALID; o->pose_off[ent] = P; P += 6; }
         else { int i = ~ent; if (i >= NSB || o->sb_off[i] >= 0) return VIO_ERR_INVALID; o->sb_off[i] = P; P += 9; }
     }
-    o->P = P; o->M = g->n_landmark; o->NB = NB;
+    o->P = P; o->M = g->n_landmark + 3 * g->n_point; o->NB = NB; /* [inverse depths | 3 per VertexPointXYZ] */
     o->row_fixed = (unsigned char *)calloc(P > 0 ? P : 1, 1);
     for (int i = 0; i < C; ++i)
         if (g->pose_fixed && g->pose_fixed[i]) for (int d = 0; d < 6; ++d) o->row_fixed[o->pose_off[i] + d] = 1;
@@ -489,6 +489,39 @@ static void add_edge_dense(double *H, double *b, int n, int d, int nv, const dou
     }
 }
 
+/* EdgeReprojectionXYZ — A15/backend/edge_reprojection.cc:113-163 (A17/src/backend/edge_reprojection.cc:130-180):
+ * vertices [X_w(3), T_i]; r (2), JX (2x3 row-major), JT (2x6 row-major, translation columns first). */
+void orc_reproj_xyz(const double *X, const double *pose_i, const double qic[4], const double tic[3], const double *obs,
+                    double r[2], double *JX, double *JT) {
+    const double *Pi = pose_i, *Qi = pose_i + 3;
+    double qinv[4], qicinv[4], d[3] = {X[0] - Pi[0], X[1] - Pi[1], X[2] - Pi[2]}, pb[3], e[3], pc[3];
+    q_inv(Qi, qinv); q_inv(qic, qicinv);
+    q_rot(qinv, d, pb);
+    e[0] = pb[0] - tic[0]; e[1] = pb[1] - tic[1]; e[2] = pb[2] - tic[2];
+    q_rot(qicinv, e, pc);
+    const double dep = pc[2];
+    r[0] = pc[0] / dep - obs[0];
+    r[1] = pc[1] / dep - obs[1];
+    if (!JX && !JT) return;
+    double Ri[9], ric[9], ricT[9], RiT[9], A[9], H3[9], Hh[9];
+    q_toR(Qi, Ri); q_toR(qic, ric);
+    m3_T(ric, ricT); m3_T(Ri, RiT);
+    const double red[6] = {1.0 / dep, 0, -pc[0] / (dep * dep), 0, 1.0 / dep, -pc[1] / (dep * dep)};
+    m3_mul(ricT, RiT, A);      /* ric^T Ri^T */
+    hat3(pb, H3);
+    m3_mul(ricT, H3, Hh);      /* ric^T hat(p_b) */
+    for (int c = 0; c < 3; ++c) {
+        const double jx0 = red[0] * A[c] + red[1] * A[3 + c] + red[2] * A[6 + c];
+        const double jx1 = red[3] * A[c] + red[4] * A[3 + c] + red[5] * A[6 + c];
+        if (JX) { JX[c] = jx0; JX[3 + c] = jx1; }
+        if (JT) {
+            JT[c] = -jx0; JT[6 + c] = -jx1;
+            JT[3 + c] = red[0] * Hh[c] + red[1] * Hh[3 + c] + red[2] * Hh[6 + c];
+            JT[9 + c] = red[3] * Hh[c] + red[4] * Hh[3 + c] + red[5] * Hh[6 + c];
+        }
+    }
+}
+
 int orc_make_hessian(const vio_graph *g, const orc_prior *prior, int flavour, double *H, double *b) {
     ordering o;
     int rc = make_ordering(g, &o);
@@ -512,6 +545,18 @@ int orc_make_hessian(const vio_graph *g, const orc_prior *prior, int flavour, do
                       (g->pose_fixed && g->pose_fixed[j]) ? -1 : o.pose_off[j]};
         /* v15: b -= JtW r with W = information; v17: b -= drho * J^T * information * r */
         add_edge_dense(H, b, n, 2, 3, Jv, ldj, dim, off, W, flavour == VIO_LM_V17 ? Om : W, drho, r);
+    }
+    for (int64_t e = 0; e < g->n_reproj_xyz; ++e) {
+        int l = g->rx_point[e], i = g->rx_pose[e];
+        double r[2], JX[6], JT[12];
+        orc_reproj_xyz(g->point_xyz + 3 * (size_t)l, g->pose + 7 * (size_t)i, qic, tic, g->rx_obs + 2 * e, r, JX, JT);
+        double W[4], Om[4] = {g->rp_info, 0, 0, g->rp_info}, drho = 1.0, rho0;
+        if (flavour == VIO_LM_V17) robust_info2(g->rp_loss, g->rp_loss_delta, g->rp_info, r, &drho, W, &rho0);
+        else memcpy(W, Om, sizeof(W));
+        const double *Jv[2] = {JX, JT};
+        int ldj[2] = {3, 6}, dim[2] = {3, 6};
+        int off[2] = {P + g->n_landmark + 3 * l, (g->pose_fixed && g->pose_fixed[i]) ? -1 : o.pose_off[i]};
+        add_edge_dense(H, b, n, 2, 2, Jv, ldj, dim, off, W, flavour == VIO_LM_V17 ? Om : W, drho, r);
     }
     for (int k = 0; k < g->n_se3prior; ++k) {
         int i = g->sp_pose[k];
@@ -572,6 +617,18 @@ int orc_chi2(const vio_graph *g, const orc_prior *prior, int flavour, double *ch
         }
         chi += e2;
     }
+    for (int64_t e = 0; e < g->n_reproj_xyz; ++e) {
+        double r[2];
+        orc_reproj_xyz(g->point_xyz + 3 * (size_t)g->rx_point[e], g->pose + 7 * (size_t)g->rx_pose[e], qic, tic, g->rx_obs + 2 * e,
+                       r, NULL, NULL);
+        double e2 = g->rp_info * (r[0] * r[0] + r[1] * r[1]);
+        if (flavour == VIO_LM_V17 && g->rp_loss != VIO_LOSS_TRIVIAL) {
+            double rho[3];
+            orc_loss(g->rp_loss, g->rp_loss_delta, e2, rho);
+            e2 = rho[0];
+        }
+        chi += e2;
+    }
     for (int k = 0; k < g->n_se3prior; ++k) {
         double r[6];
         orc_se3prior(g->pose + 7 * (size_t)g->sp_pose[k], g->sp_p + 3 * k, g->sp_q + 4 * k, r, NULL);
@@ -596,23 +653,44 @@ int orc_chi2(const vio_graph *g, const orc_prior *prior, int flavour, double *ch
 
 /* Problem::SolveLinearSystem (SLAM branch) — A15/backend/problem.cc:353-421, A17/src/backend/problem.cc:406-449.
  * Hmm is diagonal for inverse-depth landmarks, so Hpm*Hmm_inv is a column scaling. */
-int orc_solve_linear(const double *H, const double *b, int P, int M, double lambda, int solver, double *S, double *bS,
-                     double *dx, int64_t *pcg_iters) {
-    const int n = P + M;
+/* Landmark block structure [M1 scalars | Mx blocks of 3]: Hmm_inv = per-landmark block inverse
+ * (A15/backend/problem.cc:383-388: Hmm.block(idx, idx, size, size).inverse()). */
+int orc_solve_linear_blocks(const double *H, const double *b, int P, int M1, int Mx, double lambda, int solver, double *S,
+                            double *bS, double *dx, int64_t *pcg_iters) {
+    const int M = M1 + 3 * Mx, n = P + M;
     double *Sl = S ? S : (double *)malloc(sizeof(double) * (size_t)P * P);
     double *bl = bS ? bS : (double *)malloc(sizeof(double) * P);
-    double *hinv = (double *)malloc(sizeof(double) * (M > 0 ? M : 1));
-    for (int l = 0; l < M; ++l) hinv[l] = 1.0 / H[(size_t)(P + l) * n + P + l];
+    /* tempH = Hpm * Hmm_inv (P x M), built block by block */
+    double *T = (double *)malloc(sizeof(double) * (size_t)P * (M > 0 ? M : 1));
+    double *hinv = (double *)malloc(sizeof(double) * (M1 + 9 * (size_t)Mx + 1));
+    for (int l = 0; l < M1; ++l) hinv[l] = 1.0 / H[(size_t)(P + l) * n + P + l];
+    for (int l = 0; l < Mx; ++l) {
+        double A[9], Ai[9];
+        const int g0 = P + M1 + 3 * l;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) A[3 * r + c] = H[(size_t)(g0 + r) * n + g0 + c];
+        mat_inverse(3, A, Ai);
+        memcpy(hinv + M1 + 9 * (size_t)l, Ai, sizeof(Ai));
+    }
     for (int r = 0; r < P; ++r) {
         const double *hr = H + (size_t)r * n;
+        double *tr = T + (size_t)r * M;
+        for (int l = 0; l < M1; ++l) tr[l] = hr[P + l] * hinv[l];
+        for (int l = 0; l < Mx; ++l) {
+            const double *Ai = hinv + M1 + 9 * (size_t)l, *h3 = hr + P + M1 + 3 * l;
+            for (int c = 0; c < 3; ++c) tr[M1 + 3 * l + c] = h3[0] * Ai[c] + h3[1] * Ai[3 + c] + h3[2] * Ai[6 + c];
+        }
+    }
+    for (int r = 0; r < P; ++r) {
+        const double *tr = T + (size_t)r * M;
         for (int c = 0; c < P; ++c) {
             double t = 0;
-            const double *hc = H + (size_t)c * n;
-            for (int l = 0; l < M; ++l) t += (hr[P + l] * hinv[l]) * hc[P + l]; /* tempH * Hmp, Hmp = Hpm^T */
-            Sl[(size_t)r * P + c] = hr[c] - t;
+            const double *hc = H + (size_t)c * n + P; /* Hmp = Hpm^T */
+            for (int l = 0; l < M; ++l) t += tr[l] * hc[l];
+            Sl[(size_t)r * P + c] = H[(size_t)r * n + c] - t;
         }
         double t = 0;
-        for (int l = 0; l < M; ++l) t += (hr[P + l] * hinv[l]) * b[P + l];
+        for (int l = 0; l < M; ++l) t += tr[l] * b[P + l];
         bl[r] = b[r] - t;
     }
     for (int i = 0; i < P; ++i) Sl[(size_t)i * P + i] += lambda;
@@ -620,22 +698,38 @@ int orc_solve_linear(const double *H, const double *b, int P, int M, double lamb
     if (solver == VIO_SOLVER_REF_PCG) it = ref_pcg(P, Sl, bl, 2 * P, dx);
     else chol_solve(P, Sl, bl, dx);
     if (pcg_iters) *pcg_iters = it;
-    for (int l = 0; l < M; ++l) {
+    /* delta_x_ll = Hmm_inv * (bmm - Hmp * delta_x_pp) */
+    for (int l = 0; l < M1; ++l) {
         double t = b[P + l];
         const double *hl = H + (size_t)(P + l) * n;
         for (int c = 0; c < P; ++c) t -= hl[c] * dx[c];
         dx[P + l] = hinv[l] * t;
     }
+    for (int l = 0; l < Mx; ++l) {
+        const int g0 = P + M1 + 3 * l;
+        double t[3];
+        for (int a = 0; a < 3; ++a) {
+            t[a] = b[g0 + a];
+            const double *hl = H + (size_t)(g0 + a) * n;
+            for (int c = 0; c < P; ++c) t[a] -= hl[c] * dx[c];
+        }
+        const double *Ai = hinv + M1 + 9 * (size_t)l;
+        for (int a = 0; a < 3; ++a) dx[g0 + a] = Ai[3 * a] * t[0] + Ai[3 * a + 1] * t[1] + Ai[3 * a + 2] * t[2];
+    }
     if (!S) free(Sl);
     if (!bS) free(bl);
-    free(hinv);
+    free(T); free(hinv);
     return VIO_OK;
+}
+int orc_solve_linear(const double *H, const double *b, int P, int M, double lambda, int solver, double *S, double *bS,
+                     double *dx, int64_t *pcg_iters) {
+    return orc_solve_linear_blocks(H, b, P, M, 0, lambda, solver, S, bS, dx, pcg_iters);
 }
 
 /* ---- Problem::Solve — A15/backend/problem.cc:155-222 (v15), A17/src/backend/problem.cc:169-250 (v17) ---- */
 typedef struct {
     vio_graph g; /* shallow copy whose state arrays point at the buffers below */
-    double *pose, *sb, *invd, *pose_bak, *sb_bak, *invd_bak;
+    double *pose, *sb, *invd, *pose_bak, *sb_bak, *invd_bak, *pts, *pts_bak;
     orc_prior prior;
     double *bprior, *err, *bprior_bak, *err_bak;
 } lm_state;
@@ -646,6 +740,7 @@ static void update_states(lm_state *s, const ordering *o, const double *dx, int 
         memcpy(s->pose_bak, s->pose, sizeof(double) * 7 * (size_t)g->n_pose);
         memcpy(s->sb_bak, s->sb, sizeof(double) * 9 * (size_t)g->n_speedbias);
         memcpy(s->invd_bak, s->invd, sizeof(double) * (size_t)g->n_landmark);
+        memcpy(s->pts_bak, s->pts, sizeof(double) * 3 * (size_t)g->n_point);
     }
     for (int i = 0; i < g->n_pose; ++i) {
         double d[6];
@@ -655,6 +750,7 @@ static void update_states(lm_state *s, const ordering *o, const double *dx, int 
     for (int i = 0; i < g->n_speedbias; ++i)
         for (int k = 0; k < 9; ++k) s->sb[9 * (size_t)i + k] += sign * dx[o->sb_off[i] + k];
     for (int l = 0; l < g->n_landmark; ++l) s->invd[l] += sign * dx[o->P + l];
+    for (int l = 0; l < 3 * g->n_point; ++l) s->pts[l] += sign * dx[o->P + g->n_landmark + l]; /* Vertex::Plus */
     /* prior update: A17/src/backend/problem.cc:465-474 */
     if (flavour == VIO_LM_V17 && s->prior.dim > 0 && s->prior.err_dim > 0 && backup) {
         const int P = o->P, ed = s->prior.err_dim;
@@ -675,6 +771,11 @@ static void update_states(lm_state *s, const ordering *o, const double *dx, int 
 
 int orc_solve(const vio_graph *g0, const orc_prior *prior, int iterations, const vio_lm_opts *opts, double *pose,
               double *speedbias, double *inv_depth, double *b_prior_out, double *err_prior_out, orc_result *res) {
+    return orc_solve_points(g0, prior, iterations, opts, pose, speedbias, inv_depth, NULL, b_prior_out, err_prior_out, res);
+}
+int orc_solve_points(const vio_graph *g0, const orc_prior *prior, int iterations, const vio_lm_opts *opts, double *pose,
+                     double *speedbias, double *inv_depth, double *point_xyz, double *b_prior_out, double *err_prior_out,
+                     orc_result *res) {
     const int flavour = opts ? opts->flavour : VIO_LM_V17;
     int solver = opts ? opts->solver : VIO_SOLVER_AUTO;
     const int fixed_it = opts ? opts->fixed_iterations : 0;
@@ -687,14 +788,16 @@ int orc_solve(const vio_graph *g0, const orc_prior *prior, int iterations, const
     lm_state s;
     memset(&s, 0, sizeof(s));
     s.g = *g0;
-    size_t np = 7 * (size_t)g0->n_pose, ns = 9 * (size_t)g0->n_speedbias, nl = (size_t)g0->n_landmark;
+    size_t np = 7 * (size_t)g0->n_pose, ns = 9 * (size_t)g0->n_speedbias, nl = (size_t)g0->n_landmark, nx = 3 * (size_t)g0->n_point;
     s.pose = malloc(sizeof(double) * (np + 1)); s.pose_bak = malloc(sizeof(double) * (np + 1));
     s.sb = malloc(sizeof(double) * (ns + 1)); s.sb_bak = malloc(sizeof(double) * (ns + 1));
     s.invd = malloc(sizeof(double) * (nl + 1)); s.invd_bak = malloc(sizeof(double) * (nl + 1));
     memcpy(s.pose, g0->pose, sizeof(double) * np);
     if (ns) memcpy(s.sb, g0->speedbias, sizeof(double) * ns);
     if (nl) memcpy(s.invd, g0->inv_depth, sizeof(double) * nl);
-    s.g.pose = s.pose; s.g.speedbias = s.sb; s.g.inv_depth = s.invd;
+    s.pts = malloc(sizeof(double) * (nx + 1)); s.pts_bak = malloc(sizeof(double) * (nx + 1));
+    if (nx) memcpy(s.pts, g0->point_xyz, sizeof(double) * nx);
+    s.g.pose = s.pose; s.g.speedbias = s.sb; s.g.inv_depth = s.invd; s.g.point_xyz = s.pts;
     if (prior && prior->dim > 0 && !v15) {
         s.prior = *prior;
         s.bprior = malloc(sizeof(double) * P); s.bprior_bak = malloc(sizeof(double) * P);
@@ -730,7 +833,7 @@ int orc_solve(const vio_graph *g0, const orc_prior *prior, int iterations, const
         int ok = 0, false_cnt = 0;
         while (!ok && (v15 || false_cnt < 10)) {
             int64_t pit = 0;
-            orc_solve_linear(H, b, P, M, lambda, solver, NULL, NULL, dx, &pit);
+            orc_solve_linear_blocks(H, b, P, g0->n_landmark, g0->n_point, lambda, solver, NULL, NULL, dx, &pit);
             if (res) { res->trial_steps++; res->pcg_iterations += pit; }
             double dx2 = 0, dot = 0;
             for (int i = 0; i < n; ++i) { dx2 += dx[i] * dx[i]; dot += dx[i] * (lambda * dx[i] + b[i]); }
@@ -754,6 +857,7 @@ int orc_solve(const vio_graph *g0, const orc_prior *prior, int iterations, const
                     memcpy(s.pose, s.pose_bak, sizeof(double) * np);
                     memcpy(s.sb, s.sb_bak, sizeof(double) * ns);
                     memcpy(s.invd, s.invd_bak, sizeof(double) * nl);
+                    memcpy(s.pts, s.pts_bak, sizeof(double) * nx);
                     if (s.prior.dim > 0 && s.prior.err_dim > 0) {
                         memcpy(s.bprior, s.bprior_bak, sizeof(double) * P);
                         memcpy(s.err, s.err_bak, sizeof(double) * s.prior.err_dim);
@@ -776,10 +880,11 @@ int orc_solve(const vio_graph *g0, const orc_prior *prior, int iterations, const
     if (pose) memcpy(pose, s.pose, sizeof(double) * np);
     if (speedbias && ns) memcpy(speedbias, s.sb, sizeof(double) * ns);
     if (inv_depth && nl) memcpy(inv_depth, s.invd, sizeof(double) * nl);
+    if (point_xyz && nx) memcpy(point_xyz, s.pts, sizeof(double) * nx);
     if (b_prior_out && s.bprior) memcpy(b_prior_out, s.bprior, sizeof(double) * P);
     if (err_prior_out && s.err) memcpy(err_prior_out, s.err, sizeof(double) * s.prior.err_dim);
     free(H); free(b); free(dx);
-    free(s.pose); free(s.pose_bak); free(s.sb); free(s.sb_bak); free(s.invd); free(s.invd_bak);
+    free(s.pose); free(s.pose_bak); free(s.sb); free(s.sb_bak); free(s.invd); free(s.invd_bak); free(s.pts); free(s.pts_bak);
     free(s.bprior); free(s.bprior_bak); free(s.err); free(s.err_bak);
     free_ordering(&o);
     return VIO_OK;

@@ -61,6 +61,16 @@ int orc_solve_linear(const double *H, const double *b, int P, int M, double lamb
 int orc_solve(const vio_graph *g, const orc_prior *prior, int iterations, const vio_lm_opts *opts, double *pose,
               double *speedbias, double *inv_depth, double *b_prior_out, double *err_prior_out, orc_result *res);
 
+/* VertexPointXYZ / EdgeReprojectionXYZ (A15/backend/edge_reprojection.cc:113-163): landmark dims are ordered
+ * [n_landmark inverse depths | 3 per point]; orc_dims' M counts both. */
+void orc_reproj_xyz(const double *X, const double *pose_i, const double qic[4], const double tic[3], const double *obs,
+                    double r[2], double *JX /* 2x3 or NULL */, double *JT /* 2x6 or NULL */);
+int orc_solve_linear_blocks(const double *H, const double *b, int P, int M1, int Mx, double lambda, int solver, double *S,
+                            double *bS, double *dx, int64_t *pcg_iters);
+int orc_solve_points(const vio_graph *g, const orc_prior *prior, int iterations, const vio_lm_opts *opts, double *pose,
+                     double *speedbias, double *inv_depth, double *point_xyz, double *b_prior_out, double *err_prior_out,
+                     orc_result *res);
+
 /* --- block-sparse path for the large synthetic BA (configs 4/5): same per-edge arithmetic, dense
  * containers replaced by 6x6 block storage.  pattern: rowptr (C+1), col (nnzb) as returned by
  * vio_get_schur_bsr; val (nnzb*36) receives the undamped reduced system, bS (6C). ----------------- */

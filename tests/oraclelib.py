@@ -68,7 +68,7 @@ def _prior(scene):
 def hessian(scene, flavour):
     g, keep = scene.to_c()
     pr, k2 = _prior(scene)
-    n = scene.P + scene.inv_depth.shape[0]
+    n = scene.P + scene.inv_depth.shape[0] + 3 * scene.point_xyz.shape[0]
     H, b = np.zeros((n, n)), np.zeros(n)
     rc = lib().orc_make_hessian(C.byref(g), C.byref(pr), flavour, _d(H), _d(b))
     assert rc == 0, rc
@@ -84,14 +84,17 @@ def chi2(scene, flavour):
     return out.value
 
 
-def solve_linear(H, b, P, lam, solver):
+def solve_linear(H, b, P, lam, solver, n_point=0):
+    """n_point: number of VertexPointXYZ landmarks (3x3 blocks) at the end of the landmark range"""
     n = H.shape[0]
-    M = n - P
+    M1 = n - P - 3 * n_point
     S, bS, dx = np.zeros((P, P)), np.zeros(P), np.zeros(n)
     it = C.c_int64()
     H = np.ascontiguousarray(H)
     b = np.ascontiguousarray(b)
-    rc = lib().orc_solve_linear(_d(H), _d(b), P, M, lam, solver, _d(S), _d(bS), _d(dx), C.byref(it))
+    lib().orc_solve_linear_blocks.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _dp, _dp, _dp,
+                                              C.POINTER(C.c_int64)]
+    rc = lib().orc_solve_linear_blocks(_d(H), _d(b), P, M1, n_point, lam, solver, _d(S), _d(bS), _d(dx), C.byref(it))
     assert rc == 0, rc
     return S, bS, dx, it.value
 
@@ -102,14 +105,15 @@ def solve(scene, iterations, opts):
     pose = np.zeros_like(scene.pose)
     sb = np.zeros_like(scene.speedbias)
     invd = np.zeros_like(scene.inv_depth)
+    pts = np.zeros_like(scene.point_xyz)
     bpo = np.zeros(max(scene.P, 1))
     epo = np.zeros(max(scene.P, 1))
     res = OrcResult()
-    rc = lib().orc_solve(C.byref(g), C.byref(pr), iterations, C.byref(opts), _d(pose), _d(sb) if sb.size else None, _d(invd),
-                         _d(bpo), _d(epo), C.byref(res))
+    rc = lib().orc_solve_points(C.byref(g), C.byref(pr), iterations, C.byref(opts), _d(pose), _d(sb) if sb.size else None,
+                                _d(invd), _d(pts), _d(bpo), _d(epo), C.byref(res))
     assert rc == 0, rc
     n = min(res.iterations, capi.TRACE_MAX)
-    return dict(pose=pose, speedbias=sb, inv_depth=invd, iterations=res.iterations, chi2_trace=np.array(res.chi2_trace[:n]),
+    return dict(pose=pose, speedbias=sb, inv_depth=invd, point_xyz=pts, iterations=res.iterations, chi2_trace=np.array(res.chi2_trace[:n]),
                 lambda_trace=np.array(res.lambda_trace[:n]), chi2_final=res.chi2_final, lambda_final=res.lambda_final,
                 ms_total=res.ms_total, ms_hessian=res.ms_hessian, linearizations=res.linearizations,
                 pcg_iterations=res.pcg_iterations, b_prior=bpo, err_prior=epo)

@@ -58,15 +58,21 @@ def _prior(scene):
     return pr, keep
 
 
+def _m(scene):
+    """landmark dimension: inverse depths + 3 per VertexPointXYZ"""
+    scene._norm()
+    return scene.inv_depth.shape[0] + 3 * scene.point_xyz.shape[0]
+
+
 def hessian(ver, scene):
     g, keep = scene.to_c()
     pr, k2 = _prior(scene)
-    n = scene.P + scene.inv_depth.shape[0]
+    n = scene.P + _m(scene)
     H, b = np.zeros((n, n)), np.zeros(n)
     P, M = C.c_int32(), C.c_int32()
     rc = getattr(_lib(ver), f"ref{ver}_hessian")(C.byref(g), C.byref(pr), _d(H), _d(b), C.byref(P), C.byref(M))
     assert rc == 0, rc
-    assert P.value == scene.P and M.value == scene.inv_depth.shape[0]
+    assert P.value == scene.P and M.value == _m(scene)
     return H, b
 
 
@@ -83,7 +89,7 @@ def step(ver, scene, lam):
     g, keep = scene.to_c()
     pr, k2 = _prior(scene)
     P = scene.P
-    n = P + scene.inv_depth.shape[0]
+    n = P + _m(scene)
     S, bS, dx = np.zeros((P, P)), np.zeros(P), np.zeros(n)
     rc = getattr(_lib(ver), f"ref{ver}_step")(C.byref(g), C.byref(pr), C.c_double(lam), _d(S), _d(bS), _d(dx))
     assert rc == 0, rc
@@ -96,13 +102,14 @@ def solve(ver, scene, iterations):
     pose = np.zeros_like(scene.pose)
     sb = np.zeros_like(scene.speedbias)
     invd = np.zeros_like(scene.inv_depth)
+    pts = np.zeros_like(scene.point_xyz)
     res = RefResult()
     bpo = np.zeros(max(scene.P, 1))
     epo = np.zeros(max(scene.P, 1))
-    rc = getattr(_lib(ver), f"ref{ver}_solve")(C.byref(g), C.byref(pr), iterations, _d(pose), _d(sb) if sb.size else None,
-                                               _d(invd), _d(bpo), _d(epo), C.byref(res))
+    rc = getattr(_lib(ver), f"ref{ver}_solve_points")(C.byref(g), C.byref(pr), iterations, _d(pose), _d(sb) if sb.size else None,
+                                                      _d(invd), _d(pts), _d(bpo), _d(epo), C.byref(res))
     assert rc == 0, rc
-    out = dict(pose=pose, speedbias=sb, inv_depth=invd, iterations=res.iterations,
+    out = dict(pose=pose, speedbias=sb, inv_depth=invd, point_xyz=pts, iterations=res.iterations,
                chi2_trace=np.array(res.chi2_trace[:res.iterations]), lambda_trace=np.array(res.lambda_trace[:res.iterations]),
                chi2_final=res.chi2_final, lambda_final=res.lambda_final, ms_solve=res.ms_solve, ms_hessian=res.ms_hessian,
                b_prior=bpo, err_prior=epo)

@@ -224,3 +224,31 @@ def window_scene(seed=2, n_feat=1000, return_marg_window=False):
     if return_marg_window:
         return B, A
     return B
+
+
+def xyz_scene(kind):
+    """Deterministic VertexPointXYZ / EdgeReprojectionXYZ scenes behind tests/golden/*xyz*.npz and mixed_*.npz: the
+    TestMonoBA scene with (some of) its landmarks re-parameterised as world points (scenes.to_xyz)."""
+    vio = importlib.import_module("visual-inertial-odometry_b200")
+    sc = vio.scenes
+    if kind == "xyz_v15":
+        return sc.to_xyz(sc.monoba(6, 40), noise=0.01, seed=1)
+    if kind == "xyz_v17_cauchy":
+        s = sc.to_xyz(sc.monoba(6, 40, with_ext=True), noise=0.01, seed=1)
+        s.rp_loss, s.rp_loss_delta, s.rp_info = capi.LOSS_CAUCHY, 1.0, 100.0
+        return s
+    if kind == "mixed_v17":
+        m = np.zeros(40, bool)
+        m[::2] = True
+        s = sc.to_xyz(sc.monoba(6, 40, with_ext=True), mask=m, noise=0.01, seed=2)
+        s.rp_loss, s.rp_loss_delta, s.rp_info = capi.LOSS_CAUCHY, 1.0, 100.0
+        return s
+    if kind == "xyz_v17_solve":
+        return sc.to_xyz(sc.monoba(20, 300, with_ext=True), noise=0.02, seed=3)
+    if kind == "mixed_v17_solve":
+        m = np.zeros(300, bool)
+        m[100:250] = True
+        return sc.to_xyz(sc.monoba(20, 300, with_ext=True), mask=m, noise=0.02, seed=4)
+    if kind == "xyz_v15_solve":
+        return sc.to_xyz(sc.monoba(20, 300), noise=0.02, seed=5)
+    raise ValueError(kind)

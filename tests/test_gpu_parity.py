@@ -464,3 +464,68 @@ def test_preintegration_vs_golden(vio):
         assert rel_max(o2["jacobian"][k], jac) <= 1e-9 and rel_max(o2["covariance"][k], cov) <= 1e-9
     # the outputs feed EdgeImu unchanged: same layout as the vio_graph IMU arrays
     assert out["jacobian"].shape == (6, 225) and out["delta_q"].shape == (6, 4)
+
+
+XYZ_LIN = [("xyz_6x40_v15_lin.npz", 15, "xyz_v15"), ("xyz_6x40_v17_cauchy_lin.npz", 17, "xyz_v17_cauchy"),
+           ("mixed_6x40_v17_lin.npz", 17, "mixed_v17")]
+
+
+@pytest.mark.parametrize("name,ver,kind", XYZ_LIN, ids=[c[0] for c in XYZ_LIN])
+def test_xyz_linearisation_vs_golden(vio, name, ver, kind):
+    """VertexPointXYZ / EdgeReprojectionXYZ on the device against the unmodified reference: Hessian_ with its
+    3x3 landmark blocks, b_, chi2, lambda0, the Schur complement and the step (poses, inverse depths, points)."""
+    from tests.scenes_extra import xyz_scene
+    g = _gold(name)
+    s = xyz_scene(kind)
+    fl = vio.capi.LM_V15 if ver == 15 else vio.capi.LM_V17
+    solver = vio.capi.SOLVER_DENSE_CHOL
+    opts = vio.make_opts(flavour=fl, solver=solver)
+    p = vio.Problem()
+    p.set_graph(s)
+    H, b = p.get_hessian(opts)
+    assert rel_max(H, g["H"]) <= H_TOL and rel_l2(b, g["b"]) <= H_TOL
+    assert abs(p.chi2(opts) - float(g["chi2"])) <= H_TOL * float(g["chi2"])
+    p.linearize(opts)
+    S, bS = p.get_schur()
+    lam = float(g["lam"])
+    Sg = g["S"] - lam * np.eye(S.shape[0])  # the reference stores the damped H_pp_schur_
+    assert rel_max(S, Sg) <= H_TOL and rel_l2(bS, g["bS"]) <= H_TOL
+    if ver == 17:  # v15 golden dx comes from the inexact reference PCG; the exact-solve step is pinned for v17
+        p.solve_step(lam, opts)
+        dxp, dxl = p.get_delta()
+        _, _, dxx = p.get_point_system()
+        dx = np.concatenate([dxp, dxl, dxx.ravel()])
+        assert rel_l2(dx, g["dx"]) <= 1e-8
+    Hmm, bx, _ = p.get_point_system()
+    n0 = s.P + s.inv_depth.shape[0]
+    for l in range(0, s.point_xyz.shape[0], 7):
+        blk = g["H"][n0 + 3 * l:n0 + 3 * l + 3, n0 + 3 * l:n0 + 3 * l + 3]
+        assert rel_max(Hmm[l], blk) <= H_TOL
+
+
+@pytest.mark.parametrize("name,kind,ver,iters", [("xyz_20x300_v17_solve.npz", "xyz_v17_solve", 17, 20),
+                                                 ("mixed_20x300_v17_solve.npz", "mixed_v17_solve", 17, 20),
+                                                 ("xyz_20x300_v15_solve10.npz", "xyz_v15_solve", 15, 10)])
+def test_xyz_solve_vs_golden(vio, name, kind, ver, iters):
+    """Problem::Solve on graphs with VertexPointXYZ landmarks (pure and mixed with inverse depths): iteration count,
+    chi2 trace and final estimates against the unmodified reference."""
+    from tests.scenes_extra import xyz_scene
+    g = _gold(name)
+    s = xyz_scene(kind)
+    fl = vio.capi.LM_V15 if ver == 15 else vio.capi.LM_V17
+    p = vio.Problem()
+    p.set_graph(s)
+    st = p.solve(iters, vio.make_opts(flavour=fl))
+    pose, _, invd = p.get_vertices()
+    pts = p.get_points()
+    if ver == 17:
+        assert st.iterations == int(g["iterations"])
+        assert np.allclose(st.chi2_trace[:st.n_trace], g["chi2_trace"], rtol=1e-7, atol=0)
+        assert rel_max(pose, g["pose"]) <= FINAL_TOL and rel_max(pts, g["point_xyz"]) <= FINAL_TOL
+        if invd.size:
+            assert rel_max(invd, g["inv_depth"]) <= FINAL_TOL
+    else:
+        # v15: inexact reference PCG (DESIGN 6): cost trace to 2e-6, estimates to 1e-3
+        n = min(st.n_trace, len(g["chi2_trace"]))
+        assert np.allclose(st.chi2_trace[:n], g["chi2_trace"][:n], rtol=2e-5, atol=0)
+        assert rel_max(pts, g["point_xyz"]) <= 1e-3

@@ -201,3 +201,39 @@ def test_oracle_preintegration_vs_golden():
                           (cov, g["covariance"][k])):
             scale = max(np.abs(ref).max(), 1e-300)
             assert np.abs(mine - ref).max() <= 1e-12 * scale
+
+
+XYZ_LIN = [("xyz_6x40_v15_lin.npz", 15, "xyz_v15"), ("xyz_6x40_v17_cauchy_lin.npz", 17, "xyz_v17_cauchy"),
+           ("mixed_6x40_v17_lin.npz", 17, "mixed_v17")]
+
+
+@pytest.mark.parametrize("name,ver,kind", XYZ_LIN, ids=[c[0] for c in XYZ_LIN])
+def test_oracle_xyz_linearisation_vs_golden(vio, name, ver, kind):
+    """VertexPointXYZ / EdgeReprojectionXYZ: oracle vs the unmodified reference - full Hessian_ with 3x3
+    landmark blocks ordered [P | inverse depths | points], b_, chi2, lambda0, Schur complement and the step."""
+    from tests.scenes_extra import xyz_scene
+    g = gold(name)
+    s = xyz_scene(kind)
+    fl = vio.capi.LM_V15 if ver == 15 else vio.capi.LM_V17
+    H, b = orc.hessian(s, fl)
+    assert H.shape[0] == s.P + s.inv_depth.shape[0] + 3 * s.point_xyz.shape[0]
+    assert rel_max(H, g["H"]) <= 1e-12 and rel_l2(b, g["b"]) <= 1e-12
+    assert abs(orc.chi2(s, fl) - float(g["chi2"])) <= 1e-12 * float(g["chi2"])
+    solver = vio.capi.SOLVER_REF_PCG if ver == 15 else vio.capi.SOLVER_DENSE_CHOL
+    S, bS, dx, it = orc.solve_linear(H, b, s.P, float(g["lam"]), solver, n_point=s.point_xyz.shape[0])
+    assert rel_max(S, g["S"]) <= 1e-12 and rel_l2(bS, g["bS"]) <= 1e-11
+    assert rel_l2(dx, g["dx"]) <= (1e-4 if ver == 15 else 1e-8)
+
+
+@pytest.mark.parametrize("name,kind,iters", [("xyz_20x300_v17_solve.npz", "xyz_v17_solve", 20),
+                                             ("mixed_20x300_v17_solve.npz", "mixed_v17_solve", 20)])
+def test_oracle_xyz_solve_vs_golden(vio, name, kind, iters):
+    from tests.scenes_extra import xyz_scene
+    g = gold(name)
+    s = xyz_scene(kind)
+    r = orc.solve(s, iters, vio.make_opts(flavour=vio.capi.LM_V17))
+    assert r["iterations"] == int(g["iterations"])
+    assert np.allclose(r["chi2_trace"], g["chi2_trace"], rtol=1e-8, atol=0)
+    assert rel_max(r["pose"], g["pose"]) <= 1e-8 and rel_max(r["point_xyz"], g["point_xyz"]) <= 1e-8
+    if s.inv_depth.shape[0]:
+        assert rel_max(r["inv_depth"], g["inv_depth"]) <= 1e-8

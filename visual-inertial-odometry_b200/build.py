@@ -82,6 +82,14 @@ def build_backend(force=False):
         if os.path.exists(drv) and (force or _newer(exe, [out, drv])):
             _run(["g++", "-std=c++14", "-O2", "-w"] + flags + ["-I" + os.path.join(ROOT, "include"), "-I" + eigen, drv, "-o", exe,
                   "-L" + HERE, "-lvio_backend", "-lvio_b200", "-Wl,-rpath,$ORIGIN/../visual-inertial-odometry_b200"] + dyn)
+    # this repository's own VertexPointXYZ / EdgeReprojectionXYZ driver (tests/xyz_ba_driver.cc): the same source is
+    # also compiled against the unmodified reference by oracle/Makefile (oracle/_ref/xyz_ba_ref15)
+    drv = os.path.join(ROOT, "tests", "xyz_ba_driver.cc")
+    exe = os.path.join(ROOT, "build", "xyz_ba_b200")
+    if os.path.exists(drv) and (force or _newer(exe, [out, drv])):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        _run(["g++", "-std=c++14", "-O2", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + eigen, drv, "-o", exe,
+              "-L" + HERE, "-lvio_backend", "-lvio_b200", "-Wl,-rpath,$ORIGIN/../visual-inertial-odometry_b200"] + dyn)
     return out
 
 

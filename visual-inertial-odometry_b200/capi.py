@@ -39,6 +39,8 @@ class VioGraph(C.Structure):
         ("imu_lin_ba", _dp), ("imu_lin_bg", _dp), ("imu_jacobian", _dp), ("imu_covariance", _dp),
         ("gravity", C.c_double * 3),
         ("storage", C.c_int32),
+        ("n_point", C.c_int32), ("reserved_xyz", C.c_int32), ("point_xyz", _dp),
+        ("n_reproj_xyz", C.c_int64), ("rx_point", _ip), ("rx_pose", _ip), ("rx_obs", _dp),
     ]
 
 
@@ -87,7 +89,7 @@ EXPORTS = [
     "vio_solve", "vio_linearize", "vio_chi2", "vio_solve_step", "vio_apply_step", "vio_rollback_step",
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
     "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
-    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_get_coarse", "vio_preintegrate", "vio_marginalize",
+    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_get_coarse", "vio_preintegrate", "vio_set_points", "vio_get_points", "vio_get_point_system", "vio_marginalize",
 ]
 
 _lib = None
@@ -178,6 +180,11 @@ class Scene:
         self.sp_q = np.zeros((0, 4))
         self.sp_info = np.zeros((0, 36))
         self.imu = None  # dict of arrays, see to_c
+        # VertexPointXYZ landmarks + EdgeReprojectionXYZ observations
+        self.point_xyz = np.zeros((0, 3))
+        self.rx_point = np.zeros(0, np.int32)
+        self.rx_pose = np.zeros(0, np.int32)
+        self.rx_obs = np.zeros((0, 2))
         self.gravity = np.array([0.0, 0.0, 9.81])
         self.storage = STORAGE_AUTO
         # generator extras (not part of the graph)
@@ -197,6 +204,10 @@ class Scene:
         self.sp_p = c(self.sp_p, np.float64).reshape(-1, 3)
         self.sp_q = c(self.sp_q, np.float64).reshape(-1, 4)
         self.sp_info = c(self.sp_info, np.float64).reshape(-1, 36)
+        self.point_xyz = c(self.point_xyz, np.float64).reshape(-1, 3)
+        self.rx_point = c(self.rx_point, np.int32)
+        self.rx_pose = c(self.rx_pose, np.int32)
+        self.rx_obs = c(self.rx_obs, np.float64).reshape(-1, 2)
         if self.pose_fixed is not None:
             self.pose_fixed = c(self.pose_fixed, np.uint8)
         if self.speedbias_fixed is not None:
@@ -251,6 +262,10 @@ class Scene:
             g.imu_jacobian, g.imu_covariance = _d(m["jacobian"]), _d(m["covariance"])
             keep.append(m)
         g.storage = int(self.storage)
+        g.n_point = self.point_xyz.shape[0]
+        g.point_xyz = _d(self.point_xyz)
+        g.n_reproj_xyz = self.rx_point.shape[0]
+        g.rx_point, g.rx_pose, g.rx_obs = _i(self.rx_point), _i(self.rx_pose), _d(self.rx_obs)
         return g, keep
 
     @property
@@ -259,7 +274,7 @@ class Scene:
 
     _ARRAYS = ("pose", "pose_fixed", "speedbias", "speedbias_fixed", "pclass_order", "inv_depth", "rp_landmark",
                "rp_pose_i", "rp_pose_j", "rp_pts_i", "rp_pts_j", "q_ic", "t_ic", "sp_pose", "sp_p", "sp_q", "sp_info",
-               "gravity", "pose_gt", "inv_depth_gt")
+               "gravity", "pose_gt", "inv_depth_gt", "point_xyz", "rx_point", "rx_pose", "rx_obs")
     _SCALARS = ("rp_info", "rp_loss", "rp_loss_delta", "ext_pose", "storage")
 
     def export(self):
@@ -415,9 +430,26 @@ class Problem:
         self._ck(self._L.vio_get_vertices(self._h, _d(pose), _d(sb) if sb.size else None, _d(invd) if invd.size else None))
         return pose, sb, invd
 
+    def get_points(self):
+        xyz = np.zeros_like(self.scene.point_xyz)
+        if xyz.size:
+            self._ck(self._L.vio_get_points(self._h, _d(xyz)))
+        return xyz
+
+    def set_points(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        self._ck(self._L.vio_set_points(self._h, _d(xyz)))
+
+    def get_point_system(self):
+        n = self.scene.point_xyz.shape[0]
+        H, b, dx = np.zeros((n, 3, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+        if n:
+            self._ck(self._L.vio_get_point_system(self._h, _d(H), _d(b), _d(dx)))
+        return H, b, dx
+
     def get_hessian(self, opts=None):
         d = self.dims()
-        n = d.P + d.M
+        n = d.P + d.M + 3 * self.scene.point_xyz.shape[0]
         H = np.zeros((n, n))
         b = np.zeros(n)
         self._ck(self._L.vio_get_hessian(self._h, C.byref(opts) if opts is not None else None, _d(H), _d(b)))

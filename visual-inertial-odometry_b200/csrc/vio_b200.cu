@@ -28,6 +28,7 @@
 #include "vio_marg.cuh"
 #include "vio_batch.cuh"
 #include "vio_preint.cuh"
+#include "vio_xyz.cuh"
 
 #define VIO_VERSION_STR "vio_b200 0.1 (sm_100a)"
 
@@ -88,6 +89,12 @@ struct vio_problem {
     DBuf<int> g_hdr, g_slot_pose, ell_edge;
     DBuf<long long> g_pairinfo;
     DBuf<double> ell_pjx, ell_pjy;
+    // VertexPointXYZ landmarks (vio_xyz.cuh)
+    int Lx = 0;
+    long long Ex = 0;
+    DBuf<double> pt, pt_bak, ex_ox, ex_oy, Hxx, bx, wx, dxx;
+    DBuf<int> px_eptr, ex_pose;
+    std::vector<int> h_px_eptr, h_ex_pose;
     // se3 priors
     DBuf<int> sp_pose;
     DBuf<double> sp_p, sp_q, sp_info;
@@ -184,6 +191,8 @@ void fill_view(vio_problem *p) {
     v.bS = p->bS.p;
     v.bsr_rowptr = p->bsr_rowptr.p; v.bsr_col = p->bsr_col.p; v.bsr_tr = p->bsr_tr.p;
     v.dxp = p->dxp.p; v.dxl = p->dxl.p;
+    v.Lx = p->Lx; v.Ex = p->Ex; v.pt = p->pt.p; v.pt_bak = p->pt_bak.p; v.px_eptr = p->px_eptr.p; v.ex_pose = p->ex_pose.p;
+    v.ex_ox = p->ex_ox.p; v.ex_oy = p->ex_oy.p; v.Hxx = p->Hxx.p; v.bx = p->bx.p; v.wx = p->wx.p; v.dxx = p->dxx.p;
 }
 
 Se3PriorView se3_view(vio_problem *p) {
@@ -241,6 +250,11 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
         else k_linearize_lm<false><<<grid_for(p->L, 128), 128, 0, p->stream>>>(v);
         p->launches++;
     }
+    if (p->Lx > 0) {
+        if (with_schur) k_linearize_xyz<true><<<grid_for(p->Lx, 128), 128, 0, p->stream>>>(v);
+        else k_linearize_xyz<false><<<grid_for(p->Lx, 128), 128, 0, p->stream>>>(v);
+        p->launches++;
+    }
     if (ev) CK(cudaEventRecord(ev->b, p->stream));
     // pose-only factors are owned by shard 0 so the all-reduce counts them once
     if (p->shard_rank == 0) {
@@ -289,6 +303,11 @@ int do_chi2(vio_problem *p, const vio_lm_opts &o, double *out) {
     }
     double *other = p->scal.p + 1;
     CK(cudaMemsetAsync(other, 0, sizeof(double), p->stream));
+    if (p->Lx > 0) {
+        k_chi2_xyz<<<256, 256, 0, p->stream>>>(v, p->partial.p + 1280);
+        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p + 1280, 256, other, 1);
+        p->launches += 2;
+    }
     if (p->shard_rank == 0) {
         if (p->n_se3 > 0) {
             k_se3prior_chi2<<<1, 32, 0, p->stream>>>(v, se3_view(p), other);
@@ -318,7 +337,13 @@ int do_chi2(vio_problem *p, const vio_lm_opts &o, double *out) {
 
 int do_maxdiag(vio_problem *p, double *out) {
     k_maxdiag<<<RED_BLOCKS, 256, 0, p->stream>>>(p->view, p->partial.p);
-    k_max_partials<<<1, 256, 0, p->stream>>>(p->partial.p, RED_BLOCKS, p->scal.p + 2);
+    int n_part = RED_BLOCKS;
+    if (p->Lx > 0) {
+        k_maxdiag_xyz<<<256, 256, 0, p->stream>>>(p->view, p->partial.p + RED_BLOCKS);
+        n_part += 256;
+        p->launches++;
+    }
+    k_max_partials<<<1, 256, 0, p->stream>>>(p->partial.p, n_part, p->scal.p + 2);
     p->launches += 2;
     CK(cudaMemcpyAsync(p->h_scal + 2, p->scal.p + 2, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
@@ -576,6 +601,12 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
     } else {
         CK(cudaMemsetAsync(p->scal.p + 4, 0, 2 * sizeof(double), p->stream));
     }
+    if (p->Lx > 0) {
+        k_backsub_xyz<<<256, 256, 0, p->stream>>>(v, lambda, p->partial.p + 1280, p->partial2.p + 1280);
+        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p + 1280, 256, p->scal.p + 4, 1);
+        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p + 1280, 256, p->scal.p + 5, 1);
+        p->launches += 3;
+    }
     if (p->allreduce && p->shard_world > 1) {
         int rc = p->allreduce(p->scal.p + 4, 2, (void *)p->stream, p->allreduce_user);
         if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
@@ -597,6 +628,10 @@ int do_apply(vio_problem *p, const vio_lm_opts &o) {
     if (p->NSB > 0) k_update_sb<<<grid_for(p->NSB, 128), 128, 0, p->stream>>>(v, 1.0, 1);
     if (p->L > 0) k_update_lm<<<grid_for(p->L, 256), 256, 0, p->stream>>>(v, 1.0, 1);
     p->launches += 1 + (p->NSB > 0) + (p->L > 0);
+    if (p->Lx > 0) {
+        k_update_xyz<<<grid_for(3LL * p->Lx, 256), 256, 0, p->stream>>>(v, 1.0, 1);
+        p->launches++;
+    }
     if (p->prior_dim > 0 && p->err_dim > 0 && o.flavour == VIO_LM_V17) {
         // b_prior -= H_prior dx_p ; err_prior = -Jt_prior_inv b_prior.head(P-15)   (A17/src/backend/problem.cc:465-474)
         k_prior_update<<<1, 1024, 0, p->stream>>>(p->Hprior.p, p->bprior.p, p->bprior_bak.p, p->errprior.p,
@@ -615,10 +650,18 @@ int do_rollback(vio_problem *p, const vio_lm_opts &o) {
         if (p->NSB > 0) k_update_sb<<<grid_for(p->NSB, 128), 128, 0, p->stream>>>(v, -1.0, 0);
         if (p->L > 0) k_update_lm<<<grid_for(p->L, 256), 256, 0, p->stream>>>(v, -1.0, 0);
         p->launches += 1 + (p->NSB > 0) + (p->L > 0);
+        if (p->Lx > 0) {
+            k_update_xyz<<<grid_for(3LL * p->Lx, 256), 256, 0, p->stream>>>(v, -1.0, 0);
+            p->launches++;
+        }
     } else {
         long long n = std::max<long long>(std::max<long long>(7LL * p->C, 9LL * p->NSB), p->L);
         k_restore<<<grid_for(n, 256), 256, 0, p->stream>>>(v);
         p->launches++;
+        if (p->Lx > 0) {
+            k_restore_xyz<<<grid_for(3LL * p->Lx, 256), 256, 0, p->stream>>>(v);
+            p->launches++;
+        }
         if (p->prior_dim > 0 && p->err_dim > 0) {
             CK(cudaMemcpyAsync(p->bprior.p, p->bprior_bak.p, p->P * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
             CK(cudaMemcpyAsync(p->errprior.p, p->errprior_bak.p, p->err_dim * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
@@ -815,6 +858,16 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
         }
     }
     tick("groups");
+    p->Lx = K.Lx; p->Ex = K.Ex;
+    p->h_px_eptr = K.px_eptr; p->h_ex_pose = K.ex_pose;
+    if (K.Lx > 0) {
+        CK(upload(p->pt, g->point_xyz, 3 * (size_t)K.Lx, s)); CK(p->pt_bak.alloc(3 * (size_t)K.Lx));
+        CK(upload(p->px_eptr, K.px_eptr.data(), (size_t)K.Lx + 1, s)); CK(upload(p->ex_pose, K.ex_pose.data(), (size_t)K.Ex, s));
+        CK(upload(p->ex_ox, K.ex_ox.data(), (size_t)K.Ex, s)); CK(upload(p->ex_oy, K.ex_oy.data(), (size_t)K.Ex, s));
+        CK(p->Hxx.alloc(6 * (size_t)K.Lx)); CK(p->bx.alloc(3 * (size_t)K.Lx)); CK(p->wx.alloc(18 * (size_t)std::max<long long>(K.Ex, 1)));
+        CK(p->dxx.alloc(3 * (size_t)K.Lx));
+        CK(cudaMemsetAsync(p->dxx.p, 0, 3 * (size_t)K.Lx * sizeof(double), s));
+    }
     if (g->n_se3prior > 0) {
         CK(upload(p->sp_pose, g->sp_pose, (size_t)g->n_se3prior, s)); CK(upload(p->sp_p, g->sp_p, 3 * (size_t)g->n_se3prior, s));
         CK(upload(p->sp_q, g->sp_q, 4 * (size_t)g->n_se3prior, s)); CK(upload(p->sp_info, g->sp_info, 36 * (size_t)g->n_se3prior, s));
@@ -910,6 +963,47 @@ int vio_get_vertices(vio_problem *p, double *pose, double *sb, double *invd) {
     return VIO_OK;
 }
 
+int vio_set_points(vio_problem *p, const double *xyz) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    if (p->Lx == 0) return VIO_OK;
+    if (!xyz) return VIO_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(p->pt.p, xyz, 3 * (size_t)p->Lx * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->linearized = false;
+    p->lm_valid = false;
+    return VIO_OK;
+}
+int vio_get_points(vio_problem *p, double *xyz) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    if (p->Lx == 0) return VIO_OK;
+    if (!xyz) return VIO_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(xyz, p->pt.p, 3 * (size_t)p->Lx * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+int vio_get_point_system(vio_problem *p, double *Hmm, double *b, double *dx) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    if (p->Lx == 0) return VIO_OK;
+    CK(cudaSetDevice(p->device));
+    const size_t n = (size_t)p->Lx;
+    if (Hmm) {
+        std::vector<double> h(6 * n);
+        CK(cudaMemcpyAsync(h.data(), p->Hxx.p, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        for (size_t l = 0; l < n; ++l) {
+            const double *s6 = &h[6 * l];
+            double *o = Hmm + 9 * l;
+            o[0] = s6[0]; o[1] = s6[1]; o[2] = s6[2]; o[3] = s6[1]; o[4] = s6[3]; o[5] = s6[4]; o[6] = s6[2]; o[7] = s6[4]; o[8] = s6[5];
+        }
+    }
+    if (b) CK(cudaMemcpyAsync(b, p->bx.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (dx) CK(cudaMemcpyAsync(dx, p->dxx.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return VIO_OK;
+}
+
 int vio_linearize(vio_problem *p, const vio_lm_opts *opts) {
     if (!p || !p->has_graph) return VIO_ERR_STATE;
     CK(cudaSetDevice(p->device));
@@ -968,7 +1062,8 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
     vio_stats local;
     if (!st) st = &local;
     memset(st, 0, sizeof(*st));
-    if ((p->Lglobal == 0 && p->C + p->NSB == 0) || (p->E == 0 && p->n_se3 == 0 && p->n_imu == 0 && p->shard_world == 1))
+    if ((p->Lglobal == 0 && p->Lx == 0 && p->C + p->NSB == 0) ||
+        (p->E == 0 && p->Ex == 0 && p->n_se3 == 0 && p->n_imu == 0 && p->shard_world == 1))
         return fail(p, VIO_ERR_EMPTY, "Cannot solve problem without edges or verticies");
     const bool v15 = o.flavour == VIO_LM_V15;
     cudaEvent_t ev0, ev1;
@@ -1196,7 +1291,7 @@ int vio_get_hessian(vio_problem *p, const vio_lm_opts *opts, double *H, double *
     if (p->shard_world != 1) return fail(p, VIO_ERR_UNSUPPORTED, "full Hessian tap is single-shard");
     CK(cudaSetDevice(p->device));
     vio_lm_opts o = opts ? *opts : default_opts();
-    const int P = p->P, M = p->L, n = P + M;
+    const int P = p->P, M = p->L, Mx = p->Lx, n = P + M + 3 * Mx;
     if (n > 8192) return fail(p, VIO_ERR_UNSUPPORTED, "full Hessian tap limited to P+M <= 8192");
     p->ev_lin_used = 0;
     int rc = do_linearize(p, o, false);  // S buffer = Hpp (no Schur), bp = b_ pose part
@@ -1245,6 +1340,32 @@ int vio_get_hessian(vio_problem *p, const vio_lm_opts *opts, double *H, double *
         for (int i = 0; i < P; ++i) b[i] = bp[i];
         for (int l = 0; l < M; ++l) b[P + p->lm_global[l]] = bl[l];
     }
+    if (Mx > 0) {
+        // VertexPointXYZ blocks: ordered after the inverse-depth landmarks
+        std::vector<double> Hx(6 * (size_t)Mx), bxv(3 * (size_t)Mx), wx(18 * (size_t)std::max<long long>(p->Ex, 1));
+        CK(cudaMemcpyAsync(Hx.data(), p->Hxx.p, Hx.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaMemcpyAsync(bxv.data(), p->bx.p, bxv.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (p->Ex) CK(cudaMemcpyAsync(wx.data(), p->wx.p, 18 * (size_t)p->Ex * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        for (int l = 0; l < Mx; ++l) {
+            const int g0 = P + M + 3 * l;
+            const double *s6 = &Hx[6 * (size_t)l];
+            const double full[9] = {s6[0], s6[1], s6[2], s6[1], s6[3], s6[4], s6[2], s6[4], s6[5]};
+            if (H) {
+                for (int a = 0; a < 3; ++a)
+                    for (int c = 0; c < 3; ++c) H[(size_t)(g0 + a) * n + g0 + c] = full[3 * a + c];
+                for (int e = p->h_px_eptr[l]; e < p->h_px_eptr[l + 1]; ++e) {
+                    const int off = p->h_pose_off[p->h_ex_pose[e]];
+                    for (int a = 0; a < 3; ++a)
+                        for (int c = 0; c < 6; ++c) {
+                            H[(size_t)(g0 + a) * n + off + c] += wx[18 * (size_t)e + 6 * a + c];
+                            H[(size_t)(off + c) * n + g0 + a] += wx[18 * (size_t)e + 6 * a + c];
+                        }
+                }
+            }
+            if (b) for (int a = 0; a < 3; ++a) b[g0 + a] = bxv[3 * (size_t)l + a];
+        }
+    }
     return VIO_OK;
 }
 
@@ -1257,6 +1378,7 @@ int vio_marginalize(vio_problem *p, int32_t marg_pose, int32_t marg_sb, int32_t 
     if (p->storage != VIO_STORAGE_DENSE || p->shard_world != 1) return fail(p, VIO_ERR_UNSUPPORTED, "Marginalize needs a dense, unsharded window");
     if (marg_pose < 0 || marg_pose >= p->C || marg_sb >= p->NSB) return fail(p, VIO_ERR_INVALID, "bad vertex to marginalise");
     if (p->L > 0 && p->h_lm_eptr.empty()) return fail(p, VIO_ERR_UNSUPPORTED, "graph too large for Marginalize");
+    if (p->Lx > 0) return fail(p, VIO_ERR_UNSUPPORTED, "Marginalize does not handle VertexPointXYZ landmarks");
     for (int sp : p->h_sp_pose)
         if (sp == marg_pose) return fail(p, VIO_ERR_UNSUPPORTED, "SE3-prior edge on the marginalised pose");
     CK(cudaSetDevice(p->device));
@@ -1417,6 +1539,7 @@ static int lockstep_chunk(vio_problem *p, LockstepCache &cache, vio_batch_item *
             items[k].prior_dim != items[0].prior_dim || items[k].err_dim != items[0].err_dim)
             return fail(p, VIO_ERR_UNSUPPORTED, "item %d: lock-step batches need identical pose-class structure, factors kinds and options", k);
         if (g->storage == VIO_STORAGE_BSR) return fail(p, VIO_ERR_UNSUPPORTED, "lock-step batches use dense storage");
+        if (g->n_point != 0 || g->n_reproj_xyz != 0) return fail(p, VIO_ERR_UNSUPPORTED, "lock-step batches do not take VertexPointXYZ landmarks");
         const bool same_ext = g->ext_pose >= 0 ? memcmp(g->pose + 7 * (size_t)g->ext_pose, g0->pose + 7 * (size_t)g0->ext_pose, 56) == 0
                                                : (memcmp(g->q_ic, g0->q_ic, 32) == 0 && memcmp(g->t_ic, g0->t_ic, 24) == 0);
         if (!same_ext) return fail(p, VIO_ERR_UNSUPPORTED, "item %d: camera extrinsics differ inside a lock-step batch", k);

@@ -42,4 +42,11 @@ struct DevView {
     const int *bsr_rowptr, *bsr_col, *bsr_tr;  // tr: id of the transposed block
     // solve outputs
     double *dxp, *dxl;
+    // VertexPointXYZ landmarks + EdgeReprojectionXYZ observations (vio_xyz.cuh): CSR by point, caller order
+    int Lx;
+    long long Ex;
+    double *pt, *pt_bak;                 // [Lx][3]
+    const int *px_eptr, *ex_pose;        // [Lx+1], [Ex]
+    const double *ex_ox, *ex_oy;         // [Ex]
+    double *Hxx, *bx, *wx, *dxx;         // [Lx][6] sym 3x3 (xx xy xz yy yz zz), [Lx][3], [Ex][18] H_lp rows 3x6, [Lx][3]
 };

@@ -25,6 +25,11 @@ struct PackedGraph {
     std::vector<int> lm_global, lm_host, lm_eptr, e_pose_j;
     std::vector<double> pix, piy, piz, pjx, pjy, invd;
     std::vector<int> rowptr, col, tr, diag;
+    // VertexPointXYZ landmarks (caller order) and their EdgeReprojectionXYZ observations, CSR by point
+    int Lx = 0;
+    long long Ex = 0;
+    std::vector<int> px_eptr, ex_pose;
+    std::vector<double> ex_ox, ex_oy;
     // landmark groups for the grouped linearise kernel (vio_grouped.cuh)
     bool grouped_ok = false;
     int n_groups = 0, group_threads = 0;
@@ -153,6 +158,32 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     }
     lm_eptr[L] = (int)E;
 
+    // ---- VertexPointXYZ observations, CSR by point ---------------------------------------------------
+    const int Lx = g->n_point;
+    const long long Ex = g->n_reproj_xyz;
+    if (Lx < 0 || Ex < 0) return pack_fail(err, VIO_ERR_INVALID, "negative size");
+    if (Ex > 0 && (!g->rx_point || !g->rx_pose || !g->rx_obs)) return pack_fail(err, VIO_ERR_INVALID, "EdgeReprojectionXYZ arrays missing");
+    if (Lx > 0 && !g->point_xyz) return pack_fail(err, VIO_ERR_INVALID, "point_xyz missing");
+    if ((Lx > 0 || Ex > 0) && (shard_world > 1 || batch > 1))
+        return pack_fail(err, VIO_ERR_UNSUPPORTED, "VertexPointXYZ landmarks are not supported with sharding / lock-step batches");
+    if (Ex > 0x7fffffffLL) return pack_fail(err, VIO_ERR_UNSUPPORTED, "more than 2^31 EdgeReprojectionXYZ edges");
+    K.Lx = Lx; K.Ex = Ex;
+    K.px_eptr.assign((size_t)Lx + 1, 0); K.ex_pose.assign(Ex, 0); K.ex_ox.assign(Ex, 0.0); K.ex_oy.assign(Ex, 0.0);
+    {
+        for (long long e = 0; e < Ex; ++e) {
+            const int l = g->rx_point[e], a = g->rx_pose[e];
+            if (l < 0 || l >= Lx) return pack_fail(err, VIO_ERR_INVALID, "xyz edge %lld: point out of range", e);
+            if (a < 0 || a >= C) return pack_fail(err, VIO_ERR_INVALID, "xyz edge %lld: pose out of range", e);
+            K.px_eptr[l + 1]++;
+        }
+        for (int l = 0; l < Lx; ++l) K.px_eptr[l + 1] += K.px_eptr[l];
+        std::vector<int> cur(K.px_eptr.begin(), K.px_eptr.end() - 1);
+        for (long long e = 0; e < Ex; ++e) {
+            const int k = cur[g->rx_point[e]]++;
+            K.ex_pose[k] = g->rx_pose[e]; K.ex_ox[k] = g->rx_obs[2 * (size_t)e]; K.ex_oy[k] = g->rx_obs[2 * (size_t)e + 1];
+        }
+    }
+
     // ---- storage of the reduced system ----------------------------------------------------------
     int storage = g->storage;
     if (storage == VIO_STORAGE_AUTO) storage = (NSB == 0 && P > 2048) ? VIO_STORAGE_BSR : VIO_STORAGE_DENSE;
@@ -186,6 +217,12 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
             for (size_t a = 0; a < set.size(); ++a)
                 for (size_t b = 0; b < set.size(); ++b) add(set[a], set[b]);
             last = set;
+        }
+        for (int l = 0; l < Lx; ++l) {
+            set.clear();
+            for (int k = K.px_eptr[l]; k < K.px_eptr[l + 1]; ++k) set.push_back(pose_blk[K.ex_pose[k]]);
+            for (size_t a = 0; a < set.size(); ++a)
+                for (size_t b = 0; b < set.size(); ++b) add(set[a], set[b]);
         }
         rowptr.assign(NB + 1, 0);
         for (int k = 0; k < NB; ++k) {
@@ -375,6 +412,7 @@ struct PackedMerge {
             return pack_fail(err, VIO_ERR_UNSUPPORTED, "lock-step batch too large");
         m.C = B * C; m.NSB = B * NSB; m.NB = B * NBper; m.P = B * Pper; m.L = (int)Lb[B]; m.Lglobal = m.L; m.E = Eb[B];
         m.storage = VIO_STORAGE_DENSE; m.nnzb = 0; m.batch = B; m.Pper = Pper; m.s_count = (size_t)m.P * Pper;
+        m.Lx = 0; m.Ex = 0; m.px_eptr.assign(1, 0); m.ex_pose.clear(); m.ex_ox.clear(); m.ex_oy.clear();
         for (int q = 0; q < 4; ++q) m.qic[q] = ks[0].qic[q];
         for (int q = 0; q < 3; ++q) m.tic[q] = ks[0].tic[q];
         m.pose_off.resize(m.C); m.sb_off.resize(m.NSB); m.pose_blk.resize(m.C); m.blk_off.resize(m.NB); m.blk_dim.resize(m.NB);

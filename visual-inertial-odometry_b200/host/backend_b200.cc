@@ -125,6 +125,11 @@ EdgeReprojection::EdgeReprojection(const Vec3 &pts_i, const Vec3 &pts_j)
 void EdgeReprojection::SetTranslationImuFromCamera(Eigen::Quaterniond &qic_, Vec3 &tic_) { qic = qic_; tic = tic_; }
 void EdgeReprojection::ComputeResidual() { device_only("EdgeReprojection::ComputeResidual"); }
 void EdgeReprojection::ComputeJacobians() { device_only("EdgeReprojection::ComputeJacobians"); }
+EdgeReprojectionXYZ::EdgeReprojectionXYZ(const Vec3 &pts_i)
+    : Edge(2, 2, std::vector<std::string>{"VertexXYZ", "VertexPose"}), obs_(pts_i) {}
+void EdgeReprojectionXYZ::SetTranslationImuFromCamera(Eigen::Quaterniond &qic_, Vec3 &tic_) { qic = qic_; tic = tic_; }
+void EdgeReprojectionXYZ::ComputeResidual() { device_only("EdgeReprojectionXYZ::ComputeResidual"); }
+void EdgeReprojectionXYZ::ComputeJacobians() { device_only("EdgeReprojectionXYZ::ComputeJacobians"); }
 EdgeSE3Prior::EdgeSE3Prior(const Vec3 &p, const Qd &q) : Edge(6, 1, std::vector<std::string>{"VertexPose"}), Pp_(p), Qp_(q) {}
 void EdgeSE3Prior::ComputeResidual() { device_only("EdgeSE3Prior::ComputeResidual"); }
 void EdgeSE3Prior::ComputeJacobians() { device_only("EdgeSE3Prior::ComputeJacobians"); }
@@ -222,6 +227,11 @@ struct PackB200 {
     std::vector<std::shared_ptr<Vertex>> pose_v, sb_v, lm_v;
     std::vector<int32_t> rp_lm, rp_i, rp_j, sp_pose, imu_pi, imu_si, imu_pj, imu_sj;
     std::vector<double> rp_pti, rp_ptj, sp_p, sp_q, sp_info, imu_dt, imu_dp, imu_dq, imu_dv, imu_ba, imu_bg, imu_jac, imu_cov;
+    // VertexPointXYZ landmarks + EdgeReprojectionXYZ observations
+    std::unordered_map<unsigned long, int> pt_idx;
+    std::vector<std::shared_ptr<Vertex>> pt_v;
+    std::vector<double> pt, rx_obs;
+    std::vector<int32_t> rx_point, rx_pose;
     vio_graph g;
 };
 
@@ -258,6 +268,11 @@ bool Problem::PackGraphB200(PackB200 &K) {
             lm_idx[v->Id()] = (int)lm_v.size();
             lm_v.push_back(v);
             invd.push_back(x[0]);
+        } else if (t == "VertexPointXYZ") {
+            if (v->IsFixed()) { std::cerr << "vio_b200: fixed landmarks are not supported" << std::endl; return false; }
+            K.pt_idx[v->Id()] = (int)K.pt_v.size();
+            K.pt_v.push_back(v);
+            for (int k = 0; k < 3; ++k) K.pt.push_back(x[k]);
         } else {
             std::cerr << "vio_b200: vertex type " << t << " is not on the device path" << std::endl;
             return false;
@@ -307,6 +322,33 @@ bool Problem::PackGraphB200(PackB200 &K) {
             for (int k = 0; k < 3; ++k) rp_pti.push_back(er->PtsI()[k]);
             rp_ptj.push_back(er->PtsJ()[0]);
             rp_ptj.push_back(er->PtsJ()[1]);
+        } else if (t == "EdgeReprojectionXYZ") {
+            auto *ex = dynamic_cast<EdgeReprojectionXYZ *>(e.get());
+            if (!ex || vs.size() < 2) { std::cerr << "vio_b200: foreign EdgeReprojectionXYZ type" << std::endl; return false; }
+            const MatXX info = e->Information();
+            const double c = info(0, 0);
+            if (info.rows() != 2 || info(1, 1) != c || info(0, 1) != 0.0 || info(1, 0) != 0.0) {
+                std::cerr << "vio_b200: reprojection information must be c*I2" << std::endl;
+                return false;
+            }
+            LossFunction *lf = e->GetLossFunction();
+            const int kind = lf ? lf->KindB200() : 0;
+            const double delta = lf ? lf->DeltaB200() : 1.0;
+            if (kind < 0) { std::cerr << "vio_b200: user-defined loss functions are not supported" << std::endl; return false; }
+            if (!have_rp) {
+                g.rp_info = c; g.rp_loss = kind; g.rp_loss_delta = delta; g.ext_pose = -1;
+                g.q_ic[0] = ex->Qic().x(); g.q_ic[1] = ex->Qic().y(); g.q_ic[2] = ex->Qic().z(); g.q_ic[3] = ex->Qic().w();
+                g.t_ic[0] = ex->Tic().x(); g.t_ic[1] = ex->Tic().y(); g.t_ic[2] = ex->Tic().z();
+                have_rp = true;
+            } else if (g.rp_info != c || g.rp_loss != kind || g.rp_loss_delta != delta ||
+                       (g.ext_pose < 0 && (g.q_ic[3] != ex->Qic().w() || g.q_ic[0] != ex->Qic().x() || g.t_ic[0] != ex->Tic().x()))) {
+                std::cerr << "vio_b200: reprojection edges must share information, loss and extrinsics" << std::endl;
+                return false;
+            }
+            K.rx_point.push_back(K.pt_idx.at(vs[0]->Id()));
+            K.rx_pose.push_back(pose_idx.at(vs[1]->Id()));
+            K.rx_obs.push_back(ex->Obs()[0]);
+            K.rx_obs.push_back(ex->Obs()[1]);
         } else if (t == "EdgeSE3Prior") {
             auto *ep = dynamic_cast<EdgeSE3Prior *>(e.get());
             if (!ep) return false;
@@ -344,6 +386,8 @@ bool Problem::PackGraphB200(PackB200 &K) {
     g.imu_lin_ba = imu_ba.data(); g.imu_lin_bg = imu_bg.data(); g.imu_jacobian = imu_jac.data(); g.imu_covariance = imu_cov.data();
     g.gravity[0] = 0; g.gravity[1] = 0; g.gravity[2] = 9.81;
     g.storage = VIO_STORAGE_AUTO;
+    g.n_point = (int32_t)K.pt_v.size(); g.point_xyz = K.pt.data();
+    g.n_reproj_xyz = (int64_t)K.rx_point.size(); g.rx_point = K.rx_point.data(); g.rx_pose = K.rx_pose.data(); g.rx_obs = K.rx_obs.data();
 
     return true;
 }
@@ -400,6 +444,11 @@ bool Problem::Solve(int iterations) {
         for (int k = 0; k < 9; ++k) x[k] = sb[9 * i + k];
     }
     for (size_t i = 0; i < lm_v.size(); ++i) lm_v[i]->Parameters()[0] = invd[i];
+    if (!K.pt_v.empty()) {
+        if (vio_get_points(handle_, K.pt.data()) != VIO_OK) return false;
+        for (size_t i = 0; i < K.pt_v.size(); ++i)
+            for (int k = 0; k < 3; ++k) K.pt_v[i]->Parameters()[k] = K.pt[3 * i + k];
+    }
     if (have_prior && err_prior_.rows() > 0) vio_get_prior(handle_, b_prior_.data(), err_prior_.data());
     last_hessian_ms_ = st.ms_linearize;
     last_solve_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

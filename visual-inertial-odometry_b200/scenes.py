@@ -86,3 +86,58 @@ CONFIGS = {
     "config4_ba_1k_100k": (ring, dict(n_cam=1000, n_landmark=100000, k_obs=11, seed=4)),
     "config5_ba_10k_1m": (ring, dict(n_cam=10000, n_landmark=1000000, k_obs=11, seed=5)),
 }
+
+
+def _quat_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def to_xyz(scene, mask=None, noise=0.0, seed=0):
+    """Re-parameterise inverse-depth landmarks as VertexPointXYZ world points observed through EdgeReprojectionXYZ
+    (A15/backend/edge_reprojection.cc:113-163): every observation of a converted landmark - the host's included -
+    becomes a 2-vertex [X_w, T_i] factor.  mask selects the landmarks to convert (default all); the others stay
+    inverse-depth landmarks, so mixed graphs can be built.  noise perturbs the points (metres, Gaussian)."""
+    from .capi import Scene
+    scene._norm()
+    L = scene.inv_depth.shape[0]
+    mask = np.ones(L, bool) if mask is None else np.asarray(mask, bool)
+    d = scene.export()
+    if scene.ext_pose >= 0:
+        ex = scene.pose[scene.ext_pose]
+        tic, Ric = ex[:3], _quat_R(ex[3:7])
+    else:
+        tic, Ric = np.asarray(scene.t_ic, float), _quat_R(scene.q_ic)
+    lm, pi, pj = scene.rp_landmark, scene.rp_pose_i, scene.rp_pose_j
+    conv = mask[lm]
+    new_id = -np.ones(L, np.int64)
+    new_id[mask] = np.arange(mask.sum())
+    keep_id = -np.ones(L, np.int64)
+    keep_id[~mask] = np.arange((~mask).sum())
+    pts = np.zeros((int(mask.sum()), 3))
+    rx_point, rx_pose, rx_obs = [], [], []
+    seen = set()
+    for e in np.nonzero(conv)[0]:
+        l, h = int(lm[e]), int(pi[e])
+        if l not in seen:
+            seen.add(l)
+            pc = scene.rp_pts_i[e] / scene.inv_depth[l]
+            pb = Ric @ pc + tic
+            pts[new_id[l]] = _quat_R(scene.pose[h, 3:7]) @ pb + scene.pose[h, :3]
+            rx_point.append(new_id[l]); rx_pose.append(h); rx_obs.append(scene.rp_pts_i[e, :2] / scene.rp_pts_i[e, 2])
+        rx_point.append(new_id[l]); rx_pose.append(int(pj[e])); rx_obs.append(scene.rp_pts_j[e, :2])
+    if noise > 0:
+        pts += np.random.default_rng(seed).normal(0, noise, pts.shape)
+    k = ~conv
+    d["inv_depth"] = scene.inv_depth[~mask]
+    d["rp_landmark"] = keep_id[lm[k]].astype(np.int32)
+    for key in ("rp_pose_i", "rp_pose_j", "rp_pts_i", "rp_pts_j"):
+        d[key] = getattr(scene, key)[k]
+    d["point_xyz"] = pts
+    d["rx_point"] = np.asarray(rx_point, np.int32)
+    d["rx_pose"] = np.asarray(rx_pose, np.int32)
+    d["rx_obs"] = np.asarray(rx_obs, np.float64).reshape(-1, 2)
+    d.pop("inv_depth_gt", None)
+    return Scene.from_dict(d)
