@@ -82,8 +82,8 @@ def build_backend(force=False):
         if os.path.exists(drv) and (force or _newer(exe, [out, drv])):
             _run(["g++", "-std=c++14", "-O2", "-w"] + flags + ["-I" + os.path.join(ROOT, "include"), "-I" + eigen, drv, "-o", exe,
                   "-L" + HERE, "-lvio_backend", "-lvio_b200", "-Wl,-rpath,$ORIGIN/../visual-inertial-odometry_b200"] + dyn)
-    # this repository's own VertexPointXYZ / EdgeReprojectionXYZ driver (tests/xyz_ba_driver.cc): the same source is
-    # also compiled against the unmodified reference by oracle/Makefile (oracle/_ref/xyz_ba_ref15)
+    # this repository's own VertexPointXYZ / EdgeReprojectionXYZ driver (tests/xyz_ba_driver.cc): the test suite also
+    # builds the same source against the unmodified reference backend and compares the two binaries
     drv = os.path.join(ROOT, "tests", "xyz_ba_driver.cc")
     exe = os.path.join(ROOT, "build", "xyz_ba_b200")
     if os.path.exists(drv) and (force or _newer(exe, [out, drv])):
