@@ -124,6 +124,8 @@ struct vio_problem {
     DBuf<double> cz_A, cz_rowbuf, cz_rc, cz_Z;
     DBuf<unsigned> cz_flags;
     unsigned cz_epoch = 0;
+    bool cz_have_inverse = false, cz_refreshed = false, cz_reuse_policy = false;
+    double cz_last_iters = 0, cz_ref_iters = 0;
     int pcg_grid = -1, pcg_br = 0, pcg_win = 0;
     size_t pcg_smem = 0;
     DBuf<unsigned long long> prof;
@@ -239,7 +241,7 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
         gv.ell_pjx = p->ell_pjx.p; gv.ell_pjy = p->ell_pjy.p; gv.ell_edge = p->ell_edge.p;
         gv.prof = nullptr;
         if (getenv("VIO_B200_PROFILE")) {
-            if (p->prof.n < 8) { CK(p->prof.alloc(8)); CK(cudaMemsetAsync(p->prof.p, 0, 8 * sizeof(unsigned long long), p->stream)); }
+            if (p->prof.n < 16) { CK(p->prof.alloc(16)); CK(cudaMemsetAsync(p->prof.p, 0, 16 * sizeof(unsigned long long), p->stream)); }
             gv.prof = p->prof.p;
         }
         if (with_schur) k_linearize_grouped<true><<<p->n_groups, p->group_threads, p->group_smem, p->stream>>>(v, gv);
@@ -526,7 +528,17 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             CoarseView cv;
             memset(&cv, 0, sizeof(cv));
             cudaError_t ce = p->pcg_smem <= 200 * 1024 ? cudaSuccess : cudaErrorInvalidValue;
-            if (solver == VIO_SOLVER_BLOCK_PCG_2L && p->cz_apc > 0 && ce == cudaSuccess) {
+            // Lagged coarse inverse (default; VIO_B200_COARSE_REUSE=0 re-inverts every trial step): any SPD approximation of Z Ac^-1 Z^T keeps PCG exact, only its
+            // rate depends on it, so the inverse of an earlier trial step may be kept while it still works: refresh when
+            // the last solve needed more than 1.5x (+10) the iterations of the solve right after the previous refresh.
+            bool reuse = false;
+            if (solver == VIO_SOLVER_BLOCK_PCG_2L && p->cz_apc > 0 && ce == cudaSuccess && p->cz_have_inverse && p->cz_reuse_policy &&
+                p->cz_last_iters <= 1.5 * p->cz_ref_iters + 10) {
+                reuse = true;
+                cv.apc = p->cz_apc; cv.ma = p->cz_ma; cv.nc = p->cz_nc; cv.Ainv = p->cz_A.p; cv.rc = p->cz_rc.p; cv.Z = p->cz_Z.p;
+            }
+            p->cz_refreshed = false;
+            if (!reuse && solver == VIO_SOLVER_BLOCK_PCG_2L && p->cz_apc > 0 && ce == cudaSuccess) {
                 // Z at the linearisation state ; Ac = Z^T (S + lambda I) Z, inverted in place
                 const int nc_ = p->cz_nc;
                 k_coarse_basis<<<p->cz_na, 64, 0, p->stream>>>(v.pose, v.pose_fixed, p->cz_blkpose.p, p->cz_aggptr.p, p->cz_Z.p);
@@ -537,15 +549,22 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                 unsigned *flg = p->cz_flags.p;
                 unsigned epoch = ++p->cz_epoch;  // flags of earlier launches hold smaller epochs: no reset needed
                 int ncv = nc_, rpv = p->cz_rp;
-                void *iargs[] = {(void *)&Ap, (void *)&ncv, (void *)&rpv, (void *)&rbuf, (void *)&flg, (void *)&epoch};
+                unsigned long long *gjprof = nullptr;
+                if (getenv("VIO_B200_PROFILE")) {
+                    if (p->prof.n < 16) { CK(p->prof.alloc(16)); CK(cudaMemsetAsync(p->prof.p, 0, 16 * sizeof(unsigned long long), p->stream)); }
+                    gjprof = p->prof.p + 8;
+                }
+                void *iargs[] = {(void *)&Ap, (void *)&ncv, (void *)&rpv, (void *)&rbuf, (void *)&flg, (void *)&epoch, (void *)&gjprof};
                 ce = cudaLaunchCooperativeKernel((void *)k_coarse_invert, dim3(p->cz_grid), dim3(CZ_INV_THREADS), iargs, p->cz_smem, p->stream);
                 if (ce == cudaSuccess) {
                     p->launches += 3;
                     CK(cudaMemsetAsync(p->bar.p, 0, 2 * sizeof(unsigned), p->stream));
                     cv.apc = p->cz_apc; cv.ma = p->cz_ma; cv.nc = nc_; cv.Ainv = p->cz_A.p; cv.rc = p->cz_rc.p; cv.Z = p->cz_Z.p;
+                    p->cz_have_inverse = true; p->cz_refreshed = true;
                 } else {
                     (void)cudaGetLastError();
                     ce = cudaSuccess;  // plain block-Jacobi below
+                    p->cz_have_inverse = false;
                 }
             }
             void *args[] = {(void *)&s, (void *)&tb, (void *)&mi, (void *)&barp, (void *)&p2, (void *)&n_init, (void *)&cv};
@@ -589,6 +608,8 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                     hc[0] / it_, hc[1] / it_, hc[2] / it_, hc[3] / it_, hs[4]);
         }
         if (pcg_iters) *pcg_iters = (int64_t)hs[4];
+        p->cz_last_iters = hs[4];
+        if (p->cz_refreshed) p->cz_ref_iters = hs[4];
     } else {
         return fail(p, VIO_ERR_INVALID, "unknown solver %d", solver);
     }
@@ -791,6 +812,8 @@ static int set_graph_impl(vio_problem *p, const vio_graph *g, int batch) {
 // are not read any more)
 static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &K) {
     p->batch = K.batch; p->Pper = K.Pper;
+    p->cz_have_inverse = false;
+    { const char *ev = getenv("VIO_B200_COARSE_REUSE"); p->cz_reuse_policy = !ev || atoi(ev) != 0; }  // default on
     const int C = K.C, NSB = K.NSB, L = K.L, P = K.P, NB = K.NB;
     const long long E = K.E;
     const bool prof_up = K.batch > 1 && getenv("VIO_B200_PROFILE");
@@ -944,6 +967,7 @@ int vio_set_vertices(vio_problem *p, const double *pose, const double *sb, const
     CK(cudaStreamSynchronize(p->stream));
     p->linearized = false;
     p->lm_valid = false;
+    p->cz_have_inverse = false;  // the state jumped: a lagged coarse inverse would belong to another linearisation
     return VIO_OK;
 }
 
@@ -972,6 +996,7 @@ int vio_set_points(vio_problem *p, const double *xyz) {
     CK(cudaStreamSynchronize(p->stream));
     p->linearized = false;
     p->lm_valid = false;
+    p->cz_have_inverse = false;  // the state jumped: a lagged coarse inverse would belong to another linearisation
     return VIO_OK;
 }
 int vio_get_points(vio_problem *p, double *xyz) {
@@ -1187,6 +1212,14 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
                 100 * hp[0] / tot, 100 * hp[1] / tot, 100 * hp[2] / tot, 100 * hp[3] / tot, 100 * hp[4] / tot, 100 * hp[5] / tot,
                 100 * hp[6] / tot, tot, (double)hp[7], 1e3 * tot / std::max(1.0, (double)hp[7]));
         cudaMemset(p->prof.p, 0, sizeof(hp));
+        if (p->prof.n >= 16) {
+            unsigned long long gq[8];
+            cudaMemcpy(gq, p->prof.p + 8, sizeof(gq), cudaMemcpyDeviceToHost);
+            if (gq[0] + gq[1] + gq[2] > 0)
+                fprintf(stderr, "[vio_b200 profile] coarse inverse owner chain (cycles, summed over pivots): wait %llu eliminate-own %llu "
+                                "inv7 %llu scale+publish %llu flag-set %llu\n", gq[0], gq[1], gq[2], gq[3], gq[4]);
+            cudaMemset(p->prof.p + 8, 0, sizeof(gq));
+        }
     }
     st->iterations = iter;
     st->n_trace = std::min(iter, VIO_TRACE_MAX);

@@ -582,23 +582,34 @@ __device__ __forceinline__ void flag_set(unsigned *flag, unsigned epoch) {
 }
 
 __global__ void __launch_bounds__(CZ_INV_THREADS, 1) k_coarse_invert(double *A, int nc, int bpc, double *pivbuf /* [na][7][nc] */,
-                                                                     unsigned *flags /* [na] */, unsigned epoch) {
+                                                                     unsigned *flags /* [na] */, unsigned epoch,
+                                                                     unsigned long long *prof /* [8] or nullptr */) {
     extern __shared__ double csm[];
     double *rows = csm;  // [7*bpc][nc]
+    long long pt0 = 0;
+#define GJ_MARK(slot_) do { if (prof && tid == 0) { const long long n_ = clock64(); atomicAdd(prof + (slot_), (unsigned long long)(n_ - pt0)); pt0 = n_; } } while (0)
     __shared__ __align__(16) double F[4 * CZ_KD][CZ_KD + 1];  // own rows' block column k before the update (bpc <= 4)
     __shared__ double Pm[CZ_KD * CZ_KD];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int na = nc / CZ_KD;
-    const int a0 = min(na, blockIdx.x * bpc), a1 = min(na, a0 + bpc);
-    const int r0 = CZ_KD * a0, nr = CZ_KD * (a1 - a0);
-    for (int t = tid; t < nr * nc; t += nt) rows[t] = A[(size_t)r0 * nc + t];
+    // cyclic ownership: coarse block row k lives in CTA (k mod gridDim.x), local slot k / gridDim.x, so consecutive pivots
+    // always sit on different CTAs and a CTA's own elimination work never delays the pivot it has to publish next
+    const int nblk = gridDim.x, cta = blockIdx.x;
+    const int nslot = cta < na ? (na - cta + nblk - 1) / nblk : 0;  // <= bpc
+    const int nr = CZ_KD * nslot;
+    (void)bpc;
+    for (int t = tid; t < nr * nc; t += nt) {
+        const int i = t / nc, j = t - i * nc;
+        rows[t] = A[(size_t)(CZ_KD * (cta + (i / CZ_KD) * nblk) + i % CZ_KD) * nc + j];
+    }
     __syncthreads();
     // pivot block row k <- [P A_k,: with P = A_kk^-1 | P inside the pivot block], written to shared memory and published
     auto publish_pivot = [&](int k) {
         double *pub = pivbuf + (size_t)k * CZ_KD * nc;
         const int kc = CZ_KD * k;
-        double *rk = rows + (size_t)(CZ_KD * (k - a0)) * nc;
+        double *rk = rows + (size_t)(CZ_KD * (k / nblk)) * nc;
         inv7_cta(rk + kc, nc, Pm);
+        GJ_MARK(2);
         for (int j = tid; j < nc; j += nt) {
             double v[CZ_KD], o[CZ_KD];
 #pragma unroll
@@ -614,6 +625,8 @@ __global__ void __launch_bounds__(CZ_INV_THREADS, 1) k_coarse_invert(double *A, 
 #pragma unroll
             for (int r = 0; r < CZ_KD; ++r) { rk[(size_t)r * nc + j] = o[r]; __stcg(pub + (size_t)r * nc + j, o[r]); }
         }
+        __syncthreads();
+        GJ_MARK(3);
         flag_set(flags + k, epoch);
     };
     // elimination of block column k from own scalar rows [i_lo, i_hi) (the pivot block row itself is skipped).  Each
@@ -632,7 +645,7 @@ __global__ void __launch_bounds__(CZ_INV_THREADS, 1) k_coarse_invert(double *A, 
                 for (int m = 0; m < CZ_KD; ++m) pv[c][m] = jj[c] < nc ? __ldcg(pub + (size_t)m * nc + jj[c]) : 0.0;
             }
             for (int i = i_lo; i < i_hi; ++i) {
-                if ((r0 + i) / CZ_KD == k) continue;
+                if (cta + (i / CZ_KD) * nblk == k) continue;
                 const double2 f01 = *reinterpret_cast<const double2 *>(&F[i][0]), f23 = *reinterpret_cast<const double2 *>(&F[i][2]),
                               f45 = *reinterpret_cast<const double2 *>(&F[i][4]);
                 const double f6 = F[i][6];
@@ -648,20 +661,25 @@ __global__ void __launch_bounds__(CZ_INV_THREADS, 1) k_coarse_invert(double *A, 
             }
         }
     };
-    if (a0 == 0 && a1 > 0) publish_pivot(0);
+    if (prof && tid == 0) pt0 = clock64();
+    if (cta == 0 && nslot > 0) publish_pivot(0);
     for (int k = 0; k < na; ++k) {
         const int kc = CZ_KD * k;
-        const bool own_k = k >= a0 && k < a1;
+        const bool own_k = (k % nblk) == cta;
+        const bool own_next = (k + 1 < na) && ((k + 1) % nblk) == cta;
+        if (own_next && prof && tid == 0) pt0 = clock64();
         if (!own_k) flag_wait(flags + k, epoch);  // pivot block row k is published (the owner has it already)
+        if (own_next) GJ_MARK(0);
         for (int t = tid; t < nr * CZ_KD; t += nt) F[t / CZ_KD][t % CZ_KD] = rows[(size_t)(t / CZ_KD) * nc + kc + t % CZ_KD];
         __syncthreads();
-        const bool own_next = (k + 1 < na) && (k + 1 >= a0) && (k + 1 < a1);
         if (own_next) {
             // the owner chain: bring block row k+1 up to date first and publish the next pivot, then the other rows
-            const int lo = CZ_KD * (k + 1 - a0);
+            const int lo = CZ_KD * ((k + 1) / nblk);
             eliminate(k, lo, lo + CZ_KD);
             __syncthreads();
+            GJ_MARK(1);
             publish_pivot(k + 1);
+            GJ_MARK(4);
             eliminate(k, 0, lo);
             eliminate(k, lo + CZ_KD, nr);
         } else {
@@ -669,7 +687,10 @@ __global__ void __launch_bounds__(CZ_INV_THREADS, 1) k_coarse_invert(double *A, 
         }
         __syncthreads();
     }
-    for (int t = tid; t < nr * nc; t += nt) A[(size_t)r0 * nc + t] = rows[t];
+    for (int t = tid; t < nr * nc; t += nt) {
+        const int i = t / nc, j = t - i * nc;
+        A[(size_t)(CZ_KD * (cta + (i / CZ_KD) * nblk) + i % CZ_KD) * nc + j] = rows[t];
+    }
 }
 
 #define BPCG_P_THREADS 1024
