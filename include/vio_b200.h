@@ -240,6 +240,11 @@ int vio_get_landmark_diag(vio_problem *p, double *Hmm /* M */);
 
 /* last-kernel timing tap for bench.py: average ms of the linearise kernel over the last solve */
 int vio_get_kernel_ms(vio_problem *p, double *ms_linearize_kernel, int64_t *launches);
+/* the same for the block-PCG of the last solve: average ms of one k_bpcg_persistent launch (CUDA events on the handle's
+ * stream), launches timed, PCG iterations summed over them, average ms of one coarse-preconditioner refresh (basis +
+ * Galerkin assembly + inversion) and how many refreshes the lagged-inverse policy made */
+int vio_get_solver_ms(vio_problem *p, double *ms_pcg_kernel, int64_t *pcg_launches, double *pcg_iterations,
+                      double *ms_coarse_setup, int64_t *coarse_refreshes);
 /* total number of kernel launches issued by this handle since creation                      */
 int64_t vio_launch_count(const vio_problem *p);
 

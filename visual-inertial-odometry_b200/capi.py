@@ -89,7 +89,7 @@ EXPORTS = [
     "vio_solve", "vio_linearize", "vio_chi2", "vio_solve_step", "vio_apply_step", "vio_rollback_step",
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
     "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
-    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_get_coarse", "vio_preintegrate", "vio_set_points", "vio_get_points", "vio_get_point_system", "vio_marginalize",
+    "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_get_coarse", "vio_preintegrate", "vio_get_solver_ms", "vio_set_points", "vio_get_points", "vio_get_point_system", "vio_marginalize",
 ]
 
 _lib = None
@@ -513,6 +513,13 @@ class Problem:
         n = C.c_int64()
         self._ck(self._L.vio_get_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def solver_ms(self):
+        """-> dict: PCG kernel ms per launch, launches, iterations, coarse refresh ms and count (last solve)"""
+        a, c, it = C.c_double(), C.c_double(), C.c_double()
+        na, nc = C.c_int64(), C.c_int64()
+        self._ck(self._L.vio_get_solver_ms(self._h, C.byref(a), C.byref(na), C.byref(it), C.byref(c), C.byref(nc)))
+        return dict(pcg_ms=a.value, pcg_launches=na.value, pcg_iterations=it.value, coarse_ms=c.value, coarse_refreshes=nc.value)
 
     def launch_count(self):
         return int(self._L.vio_launch_count(self._h))

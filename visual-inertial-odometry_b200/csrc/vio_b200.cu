@@ -134,8 +134,11 @@ struct vio_problem {
     DBuf<double> partial, partial2, scal;
     double *h_scal = nullptr;  // pinned
     // timing
-    std::vector<EvPair> ev_lin;
-    size_t ev_lin_used = 0;
+    std::vector<EvPair> ev_lin, ev_pcg, ev_coarse;
+    size_t ev_lin_used = 0, ev_pcg_used = 0, ev_coarse_used = 0;
+    double last_pcg_ms = 0.0, last_coarse_ms = 0.0, last_pcg_iters = 0.0, pcg_iters_acc = 0.0;
+    int64_t last_pcg_launches = 0, last_coarse_launches = 0;
+    bool pcg_timed_this = false;
     double last_lin_ms = 0.0;
     int64_t last_lin_launches = 0;
 
@@ -541,6 +544,8 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             if (!reuse && solver == VIO_SOLVER_BLOCK_PCG_2L && p->cz_apc > 0 && ce == cudaSuccess) {
                 // Z at the linearisation state ; Ac = Z^T (S + lambda I) Z, inverted in place
                 const int nc_ = p->cz_nc;
+                EvPair *evc = p->ev_coarse_used < p->ev_coarse.size() ? &p->ev_coarse[p->ev_coarse_used++] : nullptr;
+                if (evc) CK(cudaEventRecord(evc->a, p->stream));
                 k_coarse_basis<<<p->cz_na, 64, 0, p->stream>>>(v.pose, v.pose_fixed, p->cz_blkpose.p, p->cz_aggptr.p, p->cz_Z.p);
                 CK(cudaMemsetAsync(p->cz_A.p, 0, (size_t)nc_ * nc_ * sizeof(double), p->stream));
                 k_coarse_assemble<<<p->cz_ncb, 784, 0, p->stream>>>(v.S, v.bsr_col, p->cz_ptr.p, p->cz_fine.p, p->cz_frow.p, p->cz_row.p,
@@ -556,6 +561,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                 }
                 void *iargs[] = {(void *)&Ap, (void *)&ncv, (void *)&rpv, (void *)&rbuf, (void *)&flg, (void *)&epoch, (void *)&gjprof};
                 ce = cudaLaunchCooperativeKernel((void *)k_coarse_invert, dim3(p->cz_grid), dim3(CZ_INV_THREADS), iargs, p->cz_smem, p->stream);
+                if (evc) CK(cudaEventRecord(evc->b, p->stream));
                 if (ce == cudaSuccess) {
                     p->launches += 3;
                     CK(cudaMemsetAsync(p->bar.p, 0, 2 * sizeof(unsigned), p->stream));
@@ -568,8 +574,12 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                 }
             }
             void *args[] = {(void *)&s, (void *)&tb, (void *)&mi, (void *)&barp, (void *)&p2, (void *)&n_init, (void *)&cv};
+            EvPair *evp = p->ev_pcg_used < p->ev_pcg.size() ? &p->ev_pcg[p->ev_pcg_used++] : nullptr;
+            p->pcg_timed_this = evp != nullptr;
+            if (evp) CK(cudaEventRecord(evp->a, p->stream));
             if (ce == cudaSuccess) ce = cudaLaunchCooperativeKernel((void *)k_bpcg_persistent, dim3(grid), dim3(BPCG_P_THREADS), args,
                                                                         p->pcg_smem + (cv.apc > 0 ? ((size_t)6 * CZ_KD * p->pcg_br + cv.nc) * sizeof(double) : 0), p->stream);
+            if (evp) CK(cudaEventRecord(evp->b, p->stream));
             if (ce == cudaSuccess) {
                 p->launches++;
                 done_persistent = true;
@@ -609,6 +619,8 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         }
         if (pcg_iters) *pcg_iters = (int64_t)hs[4];
         p->cz_last_iters = hs[4];
+        if (p->pcg_timed_this) p->pcg_iters_acc += hs[4];
+        p->pcg_timed_this = false;
         if (p->cz_refreshed) p->cz_ref_iters = hs[4];
     } else {
         return fail(p, VIO_ERR_INVALID, "unknown solver %d", solver);
@@ -745,11 +757,14 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
         p->coop_ok = coop != 0;
         if (sms > 0) p->num_sms = sms;
     }
-    p->ev_lin.resize(48);  // linearise-kernel timing events (first 48 linearisations of a solve are timed)
-    for (auto &e : p->ev_lin) {
-        cudaEventCreate(&e.a);
-        cudaEventCreate(&e.b);
-    }
+    p->ev_lin.resize(48);  // kernel timing events (the first 48 launches of a solve are timed)
+    p->ev_pcg.resize(48);
+    p->ev_coarse.resize(48);
+    for (auto *vec : {&p->ev_lin, &p->ev_pcg, &p->ev_coarse})
+        for (auto &e : *vec) {
+            cudaEventCreate(&e.a);
+            cudaEventCreate(&e.b);
+        }
     if (p->partial.alloc(2048) != cudaSuccess || p->partial2.alloc(2048) != cudaSuccess ||
         p->scal.alloc(64) != cudaSuccess || p->info.alloc(4) != cudaSuccess) {
         delete p;
@@ -763,10 +778,11 @@ void vio_destroy(vio_problem *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
-    for (auto &e : p->ev_lin) {
-        cudaEventDestroy(e.a);
-        cudaEventDestroy(e.b);
-    }
+    for (auto *vec : {&p->ev_lin, &p->ev_pcg, &p->ev_coarse})
+        for (auto &e : *vec) {
+            cudaEventDestroy(e.a);
+            cudaEventDestroy(e.b);
+        }
     if (p->h_scal) cudaFreeHost(p->h_scal);
     if (p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -1095,7 +1111,7 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(cudaEventRecord(ev0, p->stream));
-    p->ev_lin_used = 0;
+    p->ev_lin_used = 0; p->ev_pcg_used = 0; p->ev_coarse_used = 0; p->pcg_iters_acc = 0.0;
     int rc;
 #define RC(x)                       \
     do {                            \
@@ -1200,6 +1216,14 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
     st->ms_linearize = lin;
     p->last_lin_ms = p->ev_lin_used ? lin / p->ev_lin_used : 0.0;
     p->last_lin_launches = (int64_t)p->ev_lin_used;
+    {
+        double tp = 0, tc = 0;
+        for (size_t i = 0; i < p->ev_pcg_used; ++i) { float t = 0; cudaEventElapsedTime(&t, p->ev_pcg[i].a, p->ev_pcg[i].b); tp += t; }
+        for (size_t i = 0; i < p->ev_coarse_used; ++i) { float t = 0; cudaEventElapsedTime(&t, p->ev_coarse[i].a, p->ev_coarse[i].b); tc += t; }
+        p->last_pcg_ms = p->ev_pcg_used ? tp / p->ev_pcg_used : 0.0; p->last_pcg_launches = (int64_t)p->ev_pcg_used;
+        p->last_coarse_ms = p->ev_coarse_used ? tc / p->ev_coarse_used : 0.0; p->last_coarse_launches = (int64_t)p->ev_coarse_used;
+        p->last_pcg_iters = p->pcg_iters_acc;
+    }
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
     if (p->prof.n >= 8) {
@@ -1229,6 +1253,16 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
     return VIO_OK;
 }
 
+int vio_get_solver_ms(vio_problem *p, double *ms_pcg_kernel, int64_t *pcg_launches, double *pcg_iterations,
+                      double *ms_coarse_setup, int64_t *coarse_refreshes) {
+    if (!p) return VIO_ERR_INVALID;
+    if (ms_pcg_kernel) *ms_pcg_kernel = p->last_pcg_ms;
+    if (pcg_launches) *pcg_launches = p->last_pcg_launches;
+    if (pcg_iterations) *pcg_iterations = p->last_pcg_iters;
+    if (ms_coarse_setup) *ms_coarse_setup = p->last_coarse_ms;
+    if (coarse_refreshes) *coarse_refreshes = p->last_coarse_launches;
+    return VIO_OK;
+}
 int vio_get_kernel_ms(vio_problem *p, double *ms, int64_t *launches) {
     if (!p) return VIO_ERR_INVALID;
     if (ms) *ms = p->last_lin_ms;
