@@ -275,7 +275,8 @@ def run_ours(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
-        solver = {"two_level": capi.SOLVER_BLOCK_PCG_2L, "block_jacobi": capi.SOLVER_BLOCK_PCG}[args.pcg]
+        solver = {"two_level": capi.SOLVER_BLOCK_PCG_2L, "block_jacobi": capi.SOLVER_BLOCK_PCG,
+                  "block_cholesky": capi.SOLVER_BLOCK_CHOL}[args.pcg]
         cold = vio.make_opts(flavour=capi.LM_V17, solver=solver, fixed_iterations=1, pcg_max_iter=args.pcg_max_iter)
         # ---- HBM-resident timing: the reference's Solve(K) from the perturbed initial state, K LM iterations on the
         # natural damping schedule (lambda0 = 1e-5 max diag, shrinking with every accepted step).  Warm-up = the same
@@ -417,8 +418,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--pcg", default="two_level", choices=["two_level", "block_jacobi"],
-                    help="preconditioner of the block PCG (two_level = block-Jacobi + coarse correction)")
+    ap.add_argument("--pcg", default="two_level", choices=["two_level", "block_jacobi", "block_cholesky"],
+                    help="reduced solver on the block-sparse S: block PCG with the two-level (block-Jacobi + coarse correction) or "
+                         "the plain block-Jacobi preconditioner, or the exact block-sparse Cholesky")
     ap.add_argument("--pcg-max-iter", type=int, default=0, help="cap PCG iterations (profiling runs only; 0 = 2P like the reference)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -51,6 +51,10 @@ enum {
     VIO_SOLVER_REF_PCG = 2,    /* v15: PCGSolver incl. its missing first x update
                                   (A15/backend/problem.cc:530-560)                          */
     VIO_SOLVER_BLOCK_PCG = 3,  /* large BA: 6x6 block-Jacobi PCG on block-sparse S           */
+    VIO_SOLVER_BLOCK_CHOL = 5,  /* block-sparse Cholesky on the 6x6 BSR pattern in the natural pose order (symbolic
+                                  factorisation on the host once per graph, numeric right-looking factorisation and the
+                                  two triangular solves on the device): the exact "block-Cholesky reduced solve" of
+                                  BASELINE config 4                                                    */
     VIO_SOLVER_BLOCK_PCG_2L = 4 /* the same PCG with a two-level preconditioner: block-Jacobi + Galerkin coarse
                                   correction over aggregates of consecutive pose blocks (camera chains).
                                   AUTO picks it for block-sparse S with >= 256 pose blocks.              */

@@ -248,6 +248,54 @@ def test_two_level_pcg_matches_block_jacobi_pcg(vio):
     assert it2 * 5 < it1, (it1, it2)
 
 
+def test_block_cholesky_is_exact(vio):
+    """VIO_SOLVER_BLOCK_CHOL (block-sparse Cholesky on the BSR pattern, "block-Cholesky reduced solve" of config 4):
+    the step equals the dense Cholesky step on a small ring to rounding, solves the tapped reduced system to 1e-12 at
+    1000 cameras (band + wrap-around border pattern), and a full Solve follows the dense-storage solve."""
+    s = vio.scenes.ring(n_cam=40, n_landmark=800, k_obs=6, seed=7)
+    s.storage = vio.capi.STORAGE_DENSE
+    p1 = vio.Problem()
+    p1.set_graph(s)
+    o1 = vio.make_opts(flavour=vio.capi.LM_V17, solver=vio.capi.SOLVER_DENSE_CHOL)
+    p1.linearize(o1)
+    S1, _ = p1.get_schur()
+    lam = 1e-6 * np.abs(np.diag(S1)).max()
+    p1.solve_step(lam, o1)
+    d1, l1 = p1.get_delta()
+    s.storage = vio.capi.STORAGE_BSR
+    p2 = vio.Problem()
+    p2.set_graph(s)
+    o2 = vio.make_opts(flavour=vio.capi.LM_V17, solver=vio.capi.SOLVER_BLOCK_CHOL)
+    p2.linearize(o2)
+    p2.solve_step(lam, o2)
+    d2, l2 = p2.get_delta()
+    assert rel_max(d2, d1) <= 1e-9 and rel_max(l2, l1) <= 1e-9
+    st1 = p1.solve(6, o1)
+    st2 = p2.solve(6, o2)
+    assert st1.iterations == st2.iterations
+    assert np.allclose(st2.chi2_trace[:st2.n_trace], st1.chi2_trace[:st1.n_trace], rtol=1e-9, atol=0)
+    # 1000 cameras: residual of the tapped block-sparse system
+    s = vio.scenes.ring(n_cam=1000, n_landmark=20000, k_obs=8, seed=9)
+    s.storage = vio.capi.STORAGE_BSR
+    p = vio.Problem()
+    p.set_graph(s)
+    p.linearize(o2)
+    rowptr, col, val, bS = p.get_schur_bsr()
+    lam = 1e-9 * np.abs(val).max()
+    p.solve_step(lam, o2)
+    d, _ = p.get_delta()
+    nb = len(rowptr) - 1
+    r = bS - lam * d
+    rows = np.repeat(np.arange(nb), np.diff(rowptr))
+    np.subtract.at(r.reshape(nb, 6), rows, np.einsum("kij,kj->ki", val, d.reshape(nb, 6)[col]))
+    assert np.linalg.norm(r) / np.linalg.norm(bS) <= 1e-9
+    # and the two-level PCG at tight tolerance lands on the same step
+    o3 = vio.make_opts(flavour=vio.capi.LM_V17, solver=vio.capi.SOLVER_BLOCK_PCG_2L, pcg_tol=1e-13)
+    p.solve_step(lam, o3)
+    d3, _ = p.get_delta()
+    assert rel_max(d3, d) <= 1e-5
+
+
 def test_large_scene_properties(vio):
     """Size-independent properties at BASELINE config-4 size (1k cameras x 100k landmarks x 1M observations):
     S symmetric, chi2 decreases monotonically over accepted steps, BSR S equals the oracle's block-sparse S on a

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libvio_b200.so")
 VIO_OK = 0
 ERR_NAMES = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "UNSUPPORTED", 4: "EMPTY", 5: "NO_DEVICE", 6: "STATE"}
 LM_V15, LM_V17 = 0, 1
-SOLVER_AUTO, SOLVER_DENSE_CHOL, SOLVER_REF_PCG, SOLVER_BLOCK_PCG, SOLVER_BLOCK_PCG_2L = 0, 1, 2, 3, 4
+SOLVER_AUTO, SOLVER_DENSE_CHOL, SOLVER_REF_PCG, SOLVER_BLOCK_PCG, SOLVER_BLOCK_PCG_2L, SOLVER_BLOCK_CHOL = 0, 1, 2, 3, 4, 5
 LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY, LOSS_TUKEY = 0, 1, 2, 3
 STORAGE_AUTO, STORAGE_DENSE, STORAGE_BSR = 0, 1, 2
 TRACE_MAX = 256

@@ -29,6 +29,8 @@
 #include "vio_batch.cuh"
 #include "vio_preint.cuh"
 #include "vio_xyz.cuh"
+#include "vio_bchol.h"
+#include "vio_bchol.cuh"
 
 #define VIO_VERSION_STR "vio_b200 0.1 (sm_100a)"
 
@@ -124,6 +126,12 @@ struct vio_problem {
     DBuf<double> cz_A, cz_rowbuf, cz_rc, cz_Z;
     DBuf<unsigned> cz_flags;
     unsigned cz_epoch = 0;
+    // block-sparse Cholesky (vio_bchol.*)
+    BcholSymbolic bchol_sym;
+    bool bchol_ready = false;
+    DBuf<int> bc_colptr, bc_rowidx, bc_upd_a, bc_upd_b;
+    DBuf<long long> bc_a_to_l, bc_upd_ptr, bc_upd_dst;
+    DBuf<double> bc_L;
     bool cz_have_inverse = false, cz_refreshed = false, cz_reuse_policy = false;
     double cz_last_iters = 0, cz_ref_iters = 0;
     int pcg_grid = -1, pcg_br = 0, pcg_win = 0;
@@ -622,6 +630,32 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         if (p->pcg_timed_this) p->pcg_iters_acc += hs[4];
         p->pcg_timed_this = false;
         if (p->cz_refreshed) p->cz_ref_iters = hs[4];
+    } else if (solver == VIO_SOLVER_BLOCK_CHOL) {
+        if (p->storage != VIO_STORAGE_BSR) return fail(p, VIO_ERR_INVALID, "block Cholesky needs BSR storage");
+        const int nb = p->NB;
+        if (!p->bchol_ready) {
+            // symbolic factorisation in the natural order, once per graph (host)
+            if (!bchol_symbolic(nb, p->h_rowptr, p->h_col, 8LL * 1000 * 1000, p->bchol_sym))
+                return fail(p, VIO_ERR_UNSUPPORTED, "block Cholesky: fill of the natural ordering exceeds the cap");
+            const BcholSymbolic &Y = p->bchol_sym;
+            CK(upload(p->bc_colptr, Y.colptr.data(), Y.colptr.size(), p->stream)); CK(upload(p->bc_rowidx, Y.rowidx.data(), Y.rowidx.size(), p->stream));
+            CK(upload(p->bc_a_to_l, Y.a_to_l.data(), Y.a_to_l.size(), p->stream)); CK(upload(p->bc_upd_ptr, Y.upd_ptr.data(), Y.upd_ptr.size(), p->stream));
+            CK(upload(p->bc_upd_a, Y.upd_a.data(), Y.upd_a.size(), p->stream)); CK(upload(p->bc_upd_b, Y.upd_b.data(), Y.upd_b.size(), p->stream));
+            CK(upload(p->bc_upd_dst, Y.upd_dst.data(), Y.upd_dst.size(), p->stream));
+            CK(p->bc_L.alloc(36 * (size_t)Y.nnzL));
+            CK(cudaStreamSynchronize(p->stream));
+            p->bchol_ready = true;
+        }
+        const BcholSymbolic &Y = p->bchol_sym;
+        BcholView bv;
+        bv.nb = nb; bv.colptr = p->bc_colptr.p; bv.rowidx = p->bc_rowidx.p; bv.L = p->bc_L.p;
+        bv.upd_ptr = p->bc_upd_ptr.p; bv.upd_dst = p->bc_upd_dst.p; bv.upd_a = p->bc_upd_a.p; bv.upd_b = p->bc_upd_b.p;
+        CK(cudaMemsetAsync(p->bc_L.p, 0, 36 * (size_t)Y.nnzL * sizeof(double), p->stream));
+        k_bchol_init<<<grid_for(p->nnzb * 36, 256), 256, 0, p->stream>>>(v.S, p->bc_a_to_l.p, p->bsr_col.p, p->bsr_rowptr.p, nb, p->nnzb,
+                                                                          lambda, p->bc_L.p);
+        k_bchol_factor<<<1, 1024, 0, p->stream>>>(bv, p->info.p);
+        k_bchol_solve<<<1, 256, 0, p->stream>>>(bv, v.bS, v.dxp);
+        p->launches += 3;
     } else {
         return fail(p, VIO_ERR_INVALID, "unknown solver %d", solver);
     }
@@ -829,6 +863,7 @@ static int set_graph_impl(vio_problem *p, const vio_graph *g, int batch) {
 static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &K) {
     p->batch = K.batch; p->Pper = K.Pper;
     p->cz_have_inverse = false;
+    p->bchol_ready = false;
     { const char *ev = getenv("VIO_B200_COARSE_REUSE"); p->cz_reuse_policy = !ev || atoi(ev) != 0; }  // default on
     const int C = K.C, NSB = K.NSB, L = K.L, P = K.P, NB = K.NB;
     const long long E = K.E;
@@ -1147,7 +1182,7 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
         int false_cnt = 0;
         while (!ok && (v15 || false_cnt < 10)) {
             int64_t pit = 0;
-            RC(do_solve_step(p, o, lambda, resolve_solver(p, o) == VIO_SOLVER_DENSE_CHOL ? nullptr : &pit));
+            RC(do_solve_step(p, o, lambda, (resolve_solver(p, o) == VIO_SOLVER_DENSE_CHOL || resolve_solver(p, o) == VIO_SOLVER_BLOCK_CHOL) ? nullptr : &pit));
             st->trial_steps++;
             st->pcg_iterations += pit;
             // scalars of this trial step: scale and |dx|^2
