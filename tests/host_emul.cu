@@ -10,6 +10,7 @@
 #include "../include/vio_b200.h"
 #include "../visual-inertial-odometry_b200/csrc/vio_pack.h"
 #include "../visual-inertial-odometry_b200/csrc/vio_kernels.cuh"
+#include "../visual-inertial-odometry_b200/csrc/vio_bchol.h"
 
 namespace {
 struct HostProblem {
@@ -247,6 +248,95 @@ int emul_merge_check(const vio_graph *const *items, int B, const vio_graph *conc
     }
     if (bS_out)
         for (int i = 0; i < P; ++i) bS_out[i] = v.bp[i] - v.bcorr[i];
+    return VIO_OK;
+}
+
+// Block-sparse Cholesky: the host symbolic factorisation of the product (vio_bchol.h) driven by a plain CPU restatement of
+// the device numeric loops (k_bchol_init / k_bchol_factor / k_bchol_solve walk the same colptr / rowidx / update map).
+// val: BSR values (nnzb x 36) of a symmetric positive definite block matrix; returns x = (A + lambda I)^-1 b, nnz(L).
+int emul_bchol_solve(int nb, const int *rowptr_, const int *col_, const double *val, double lambda, const double *b, double *x,
+                     long long *nnzL) {
+    std::vector<int> rowptr(rowptr_, rowptr_ + nb + 1), col(col_, col_ + rowptr_[nb]);
+    BcholSymbolic Y;
+    if (!bchol_symbolic(nb, rowptr, col, 8LL * 1000 * 1000, Y)) return VIO_ERR_UNSUPPORTED;
+    if (nnzL) *nnzL = Y.nnzL;
+    std::vector<double> L(36 * (size_t)Y.nnzL, 0.0);
+    for (int i = 0; i < nb; ++i)
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (Y.a_to_l[k] < 0) continue;
+            for (int e = 0; e < 36; ++e) L[36 * (size_t)Y.a_to_l[k] + e] = val[36 * (size_t)k + e] + ((col[k] == i && e % 7 == 0) ? lambda : 0.0);
+        }
+    for (int j = 0; j < nb; ++j) {
+        const int base = Y.colptr[j], cnt = Y.colptr[j + 1] - base - 1;
+        double *D = &L[36 * (size_t)base];
+        for (int c = 0; c < 6; ++c) {
+            double d = D[7 * c];
+            for (int k = 0; k < c; ++k) d -= D[6 * c + k] * D[6 * c + k];
+            if (!(d > 0.0)) return VIO_ERR_INVALID;
+            d = sqrt(d);
+            D[7 * c] = d;
+            for (int r = c + 1; r < 6; ++r) {
+                double t = D[6 * r + c];
+                for (int k = 0; k < c; ++k) t -= D[6 * r + k] * D[6 * c + k];
+                D[6 * r + c] = t / d;
+            }
+            for (int r = 0; r < c; ++r) D[6 * r + c] = 0.0;
+        }
+        for (int t = 0; t < 6 * cnt; ++t) {
+            double *row = &L[36 * (size_t)(base + 1 + t / 6) + 6 * (t % 6)], xr[6];
+            for (int c = 0; c < 6; ++c) {
+                double a = row[c];
+                for (int k = 0; k < c; ++k) a -= xr[k] * D[6 * c + k];
+                xr[c] = a / D[7 * c];
+            }
+            for (int c = 0; c < 6; ++c) row[c] = xr[c];
+        }
+        for (long long q = Y.upd_ptr[j]; q < Y.upd_ptr[j + 1]; ++q)
+            for (int e = 0; e < 36; ++e) {
+                const double *La = &L[36 * (size_t)(base + Y.upd_a[q]) + 6 * (e / 6)], *Lb = &L[36 * (size_t)(base + Y.upd_b[q]) + 6 * (e % 6)];
+                double sacc = 0.0;
+                for (int k = 0; k < 6; ++k) sacc += La[k] * Lb[k];
+                L[36 * (size_t)Y.upd_dst[q] + e] -= sacc;
+            }
+    }
+    for (int t = 0; t < 6 * nb; ++t) x[t] = b[t];
+    for (int j = 0; j < nb; ++j) {
+        const int base = Y.colptr[j], cnt = Y.colptr[j + 1] - base - 1;
+        const double *D = &L[36 * (size_t)base];
+        double y[6];
+        for (int c = 0; c < 6; ++c) {
+            double a = x[6 * (size_t)j + c];
+            for (int k = 0; k < c; ++k) a -= D[6 * c + k] * y[k];
+            y[c] = a / D[7 * c];
+        }
+        for (int c = 0; c < 6; ++c) x[6 * (size_t)j + c] = y[c];
+        for (int sb = 0; sb < cnt; ++sb)
+            for (int r = 0; r < 6; ++r) {
+                const double *Lr = &L[36 * (size_t)(base + 1 + sb) + 6 * r];
+                double a = 0.0;
+                for (int c = 0; c < 6; ++c) a += Lr[c] * y[c];
+                x[6 * (size_t)Y.rowidx[base + 1 + sb] + r] -= a;
+            }
+    }
+    for (int j = nb - 1; j >= 0; --j) {
+        const int base = Y.colptr[j], cnt = Y.colptr[j + 1] - base - 1;
+        const double *D = &L[36 * (size_t)base];
+        for (int sb = 0; sb < cnt; ++sb) {
+            const double *Ls = &L[36 * (size_t)(base + 1 + sb)], *xs = &x[6 * (size_t)Y.rowidx[base + 1 + sb]];
+            for (int c = 0; c < 6; ++c) {
+                double a = 0.0;
+                for (int r = 0; r < 6; ++r) a += Ls[6 * r + c] * xs[r];
+                x[6 * (size_t)j + c] -= a;
+            }
+        }
+        double y[6];
+        for (int c = 5; c >= 0; --c) {
+            double a = x[6 * (size_t)j + c];
+            for (int k = c + 1; k < 6; ++k) a -= D[6 * k + c] * y[k];
+            y[c] = a / D[7 * c];
+        }
+        for (int c = 0; c < 6; ++c) x[6 * (size_t)j + c] = y[c];
+    }
     return VIO_OK;
 }
 }

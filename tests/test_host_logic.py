@@ -1,4 +1,4 @@
-"""Host logic of the lock-step batch (vio_solve_batched_lockstep) without a GPU: the per-item packs merged by
+"""Host-side logic without a GPU.  Lock-step batch (vio_solve_batched_lockstep): the per-item packs merged by
 PackedMerge must equal pack_graph's own batch mode on the caller-concatenated graph, and MakeHessian + Schur run with
 the device bodies over the merged pack (tests/host_emul.cu) must give every window's reduced system bit for bit."""
 import ctypes as C
@@ -93,3 +93,50 @@ def test_merged_pack_equals_batch_pack_and_linearises_per_window(ragged):
         Sk, bk = emul.schur(s)
         assert np.array_equal(S[k], Sk)
         assert np.array_equal(bS[k], bk)
+
+
+@pytest.mark.parametrize("nb,kind", [(40, "ring"), (60, "random")])
+def test_block_cholesky_symbolic_factorisation(nb, kind):
+    """Host logic of VIO_SOLVER_BLOCK_CHOL: the symbolic factorisation (fill pattern + update map, csrc/vio_bchol.h)
+    driven by a CPU restatement of the device loops solves random SPD block-sparse systems - a band with wrap-around
+    border (camera ring) and an irregular pattern - to rounding."""
+    rng = np.random.default_rng(nb)
+    pat = [set([i]) for i in range(nb)]
+    if kind == "ring":
+        for i in range(nb):
+            for d in range(1, 5):
+                j = (i + d) % nb
+                pat[i].add(j); pat[j].add(i)
+    else:
+        for _ in range(3 * nb):
+            i, j = rng.integers(0, nb, 2)
+            pat[i].add(int(j)); pat[j].add(int(i))
+    A = np.zeros((6 * nb, 6 * nb))
+    for i in range(nb):
+        for j in pat[i]:
+            if j > i:
+                B = rng.normal(size=(6, 6))
+                A[6 * i:6 * i + 6, 6 * j:6 * j + 6] = B
+                A[6 * j:6 * j + 6, 6 * i:6 * i + 6] = B.T
+    A += np.diag(np.abs(A).sum(1) + 1.0)  # diagonally dominant => SPD
+    rowptr, col, val = [0], [], []
+    for i in range(nb):
+        for j in sorted(pat[i]):
+            col.append(j)
+            val.append(A[6 * i:6 * i + 6, 6 * j:6 * j + 6].copy())
+        rowptr.append(len(col))
+    rowptr, col = np.array(rowptr, np.int32), np.array(col, np.int32)
+    val = np.ascontiguousarray(np.array(val))
+    b = rng.normal(size=6 * nb)
+    x = np.zeros(6 * nb)
+    nnzL = C.c_longlong()
+    L = emul.lib()
+    ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    L.emul_bchol_solve.argtypes = [C.c_int, ip, ip, dp, C.c_double, dp, dp, C.POINTER(C.c_longlong)]
+    lam = 0.37
+    rc = L.emul_bchol_solve(nb, rowptr.ctypes.data_as(ip), col.ctypes.data_as(ip), val.ctypes.data_as(dp), lam,
+                            b.ctypes.data_as(dp), x.ctypes.data_as(dp), C.byref(nnzL))
+    assert rc == 0
+    ref = np.linalg.solve(A + lam * np.eye(6 * nb), b)
+    assert np.abs(x - ref).max() <= 1e-11 * np.abs(ref).max()
+    assert nnzL.value >= (len(col) + nb) // 2  # at least the lower triangle of A
