@@ -577,3 +577,30 @@ def test_xyz_solve_vs_golden(vio, name, kind, ver, iters):
         n = min(st.n_trace, len(g["chi2_trace"]))
         assert np.allclose(st.chi2_trace[:n], g["chi2_trace"][:n], rtol=2e-5, atol=0)
         assert rel_max(pts, g["point_xyz"]) <= 1e-3
+
+
+def test_window_stream_marginalize_feeds_next_solve(vio):
+    """One step of the VINS window stream entirely on the device (Estimator::backendOptimization, A17/src/estimator.cpp:
+    885-1140): Marginalize the oldest frame of window A, extend the prior by the new frame's 15 dims, Solve window B
+    with it.  Reference = the same chain through the unmodified backend (window_v17_solve10.npz was produced with the
+    reference's own Marginalize output).  The hand-off is as accurate as Marginalize's conditioning allows:
+    cost trace 1e-4, estimates 1e-5."""
+    A = vio.Scene.from_dict(dict(_gold("windowA_v17_scene.npz")))
+    B = _window(vio)
+    g = _gold("window_v17_solve10.npz")
+    pa = vio.Problem()
+    pa.set_graph(A)
+    m = pa.marginalize(1, 0)
+    n, P = m["dim"], B.P
+    assert n == 156 and P == 171
+    H = np.zeros((P, P)); H[:n, :n] = m["H"]
+    b = np.zeros(P); b[:n] = m["b"]
+    B.prior = dict(H=H, b=b, err=m["err"].copy(), jt_inv=m["jt_inv"].copy())
+    pb = vio.Problem()
+    pb.set_graph(B)
+    st = pb.solve(10, vio.make_opts(flavour=vio.capi.LM_V17))
+    pose, sb, invd = pb.get_vertices()
+    assert st.iterations == int(g["iterations"])
+    assert np.allclose(st.chi2_trace[:st.n_trace], g["chi2_trace"], rtol=1e-3, atol=0)
+    assert rel_max(pose, g["pose"]) <= 1e-5 and rel_max(invd, g["inv_depth"]) <= 1e-4
+    assert rel_max(sb[:, :3], g["speedbias"][:, :3]) <= 1e-4
