@@ -867,16 +867,6 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     { const char *ev = getenv("VIO_B200_COARSE_REUSE"); p->cz_reuse_policy = !ev || atoi(ev) != 0; }  // default on
     const int C = K.C, NSB = K.NSB, L = K.L, P = K.P, NB = K.NB;
     const long long E = K.E;
-    const bool prof_up = K.batch > 1 && getenv("VIO_B200_PROFILE");
-    auto tick = [&](const char *what) {
-        if (!prof_up) return;
-        static double last = 0;
-        cudaStreamSynchronize(p->stream);
-        const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-        if (what) fprintf(stderr, "[vio_b200 profile]   upload %-14s %.1f ms\n", what, t - last);
-        last = t;
-    };
-    tick(nullptr);
     p->C = C; p->NSB = NSB; p->L = L; p->P = P; p->NB = NB; p->E = E; p->storage = K.storage; p->nnzb = K.nnzb;
     p->Lglobal = K.Lglobal; p->s_count = K.s_count; p->n_se3 = g->n_se3prior; p->n_imu = g->n_imu;
     p->h_pose_off = K.pose_off; p->h_sb_off = K.sb_off; p->h_rowptr = K.rowptr; p->h_col = K.col;
@@ -888,7 +878,6 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     p->h_sp_pose.assign(g->sp_pose, g->sp_pose + (g->n_se3prior > 0 ? g->n_se3prior : 0));
     p->h_ext_pose = g->ext_pose;
     cudaStream_t s = p->stream;
-    tick("host copies");
     CK(upload(p->pose, g->pose, 7 * (size_t)C, s)); CK(p->pose_bak.alloc(7 * (size_t)C));
     CK(upload(p->sb, g->speedbias, 9 * (size_t)NSB, s)); CK(p->sb_bak.alloc(9 * (size_t)NSB));
     CK(upload(p->invdep, K.invd.data(), (size_t)L, s)); CK(p->invdep_bak.alloc(L));
@@ -901,12 +890,10 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     CK(upload(p->lm_piz, K.piz.data(), (size_t)L, s));
     CK(upload(p->e_pose_j, K.e_pose_j.data(), (size_t)E, s));
     CK(upload(p->e_pjx, K.pjx.data(), (size_t)E, s)); CK(upload(p->e_pjy, K.pjy.data(), (size_t)E, s));
-    tick("lm+edges");
     CK(p->Hll.alloc(L)); CK(p->bl.alloc(L)); CK(p->wh.alloc(6 * (size_t)L)); CK(p->wo.alloc(6 * (size_t)E));
     CK(p->sys.alloc(K.s_count + 3 * (size_t)P)); CK(p->bS.alloc(P)); CK(p->dxp.alloc(P)); CK(p->dxl.alloc(L));
     CK(cudaMemsetAsync(p->dxp.p, 0, P * sizeof(double), s));
     if (L > 0) CK(cudaMemsetAsync(p->dxl.p, 0, L * sizeof(double), s));
-    tick("out allocs");
     if (K.storage == VIO_STORAGE_BSR) {
         CK(upload(p->bsr_rowptr, K.rowptr.data(), K.rowptr.size(), s)); CK(upload(p->bsr_col, K.col.data(), K.col.size(), s));
         CK(upload(p->bsr_tr, K.tr.data(), K.tr.size(), s)); CK(upload(p->bsr_diag, K.diag.data(), K.diag.size(), s));
@@ -931,7 +918,6 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
             CK(cudaMemsetAsync(p->wh.p, 0, 6 * (size_t)L * sizeof(double), s));
         }
     }
-    tick("groups");
     p->Lx = K.Lx; p->Ex = K.Ex;
     p->h_px_eptr = K.px_eptr; p->h_ex_pose = K.ex_pose;
     if (K.Lx > 0) {
@@ -963,7 +949,6 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     quat_to_R(K.qic, v.Ric);
     v.tic[0] = K.tic[0]; v.tic[1] = K.tic[1]; v.tic[2] = K.tic[2];
     v.rp_info = g->rp_info; v.rp_loss = g->rp_loss; v.rp_delta = g->rp_loss_delta;
-    tick("imu+rest");
     CK(cudaStreamSynchronize(s));  // host staging vectors go out of scope
     p->has_graph = true;
     return VIO_OK;
