@@ -362,7 +362,7 @@ def run_ours(args):
                    "linearizations": int(st.linearizations), "pcg_iterations": int(st.pcg_iterations),
                    "chi2_start": st.chi2_trace[0] if st.n_trace else None, "chi2_final": st.chi2_final,
                    "warmup_chi2_initial": st_w.chi2_initial},
-            "roofline": {"bound": "hbm", "kernel": "k_linearize_grouped (linearise + JtWJ + Schur)",
+            "roofline_linearize": {"bound": "hbm", "kernel": "k_linearize_grouped (linearise + JtWJ + Schur)",
                          "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (ach_gbs / hbm_peak) if ach_gbs else None,
                          "traffic": measured_traffic(args.workload, "k_linearize_grouped") if world == 1 else None,
@@ -374,16 +374,21 @@ def run_ours(args):
                                   "algorithmic_flops_per_launch": flops_alg,
                                   "peak_source": "measured DFMA micro-benchmark (vio_measure_fp64_peak) in this run"},
                          "binding": "fp64" if (ach_tf and fp64_peak and ach_gbs and ach_tf / fp64_peak > ach_gbs / hbm_peak) else "hbm"},
-            "roofline_pcg": {"bound": "hbm", "kernel": "k_bpcg_persistent (6x6 block PCG, %s preconditioner, one cooperative launch per solve)" % args.pcg,
+            # the dominant kernel of the step (about two thirds of it, see kernel_share_of_step): the block PCG
+            "roofline": {"bound": "hbm", "kernel": "k_bpcg_persistent (6x6 block PCG, %s preconditioner, one cooperative launch per solve)" % args.pcg,
                              "achieved": pcg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (pcg_gbs / hbm_peak) if pcg_gbs else None,
-                             "traffic": None,
+                             "traffic": measured_traffic(args.workload, "k_bpcg_persistent") if (world == 1 and args.pcg == "two_level") else None,
+                             "traffic_source": "profiles/traffic.json: DRAM bytes of ONE ncu --set full launch (a late LM iteration, ~170 PCG "
+                                               "iterations); below the algorithmic bytes because part of S stays in L2 between iterations",
+                             "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": (8.0 * 36 * nnzb * sol["pcg_iterations"] / sol["pcg_launches"]) if sol["pcg_launches"] else None,
                              "algorithmic_bytes_per_iteration": 8.0 * 36 * nnzb, "iterations": sol["pcg_iterations"],
                              "kernel_ms": sol["pcg_ms"], "kernel_launches_timed": sol["pcg_launches"],
                              "us_per_iteration": (1e3 * sol["pcg_ms"] * sol["pcg_launches"] / sol["pcg_iterations"]) if sol["pcg_iterations"] else None,
                              "coarse_refresh_ms": sol["coarse_ms"], "coarse_refreshes": sol["coarse_refreshes"],
                              "note": "algorithmic bytes = S streamed once per PCG iteration (8*nnz(S)); the two-level preconditioner "
-                                     "also reads its dense coarse inverse (8*nc^2 = 33 MB) per iteration, so S does not stay "
-                                     "L2-resident (ncu: 1.4 TB/s DRAM, 43 % L2 hit; profiles/r01_pcg2l_c5_ncu_details.txt). "
+                                     "also reads its dense coarse inverse (8*nc^2 = 33 MB) per iteration, so S only partly stays "
+                                     "L2-resident (ncu: 0.86 TB/s DRAM, 61 % L2 hit; profiles/r01_pcg2l_c5_ncu_details.txt). "
                                      "Timed with CUDA events around each launch; shares of one LM iteration: see "
                                      "kernel_share_of_step"},
             "kernel_share_of_step": {
