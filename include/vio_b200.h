@@ -94,7 +94,8 @@ typedef struct vio_graph {
     double rp_loss_delta;
     /* camera->body extrinsics.  ext_pose < 0: constants q_ic/t_ic (v15 SetTranslationImuFromCamera,
      * A15/backend/edge_reprojection.cc:42-45).  ext_pose >= 0: index of the extrinsic VertexPose
-     * (v17 4-vertex edge); it must be fixed (ESTIMATE_EXTRINSIC=0 path, A17/src/estimator.cpp:915-932). */
+     * (v17 4-vertex edge).  Fixed (ESTIMATE_EXTRINSIC=0, A17/src/estimator.cpp:915-932): any handle.  Free (the edge's
+     * 4th Jacobian, A17/src/backend/edge_reprojection.cc:97-103): dense storage, unsharded, single problem.          */
     int32_t ext_pose;
     double q_ic[4];              /* xyzw                                                   */
     double t_ic[3];

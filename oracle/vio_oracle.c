@@ -179,6 +179,47 @@ void orc_reproj(double inv_dep, const double *pi7, const double *pj7, const doub
         Jl[a] = (red[3 * a] * v3[0] + red[3 * a + 1] * v3[1] + red[3 * a + 2] * v3[2]) * -1.0 / (inv_dep * inv_dep);
 }
 
+/* Fourth Jacobian of the v17 4-vertex EdgeReprojection, w.r.t. the extrinsic VertexPose
+ * (A17/src/backend/edge_reprojection.cc:97-103).  Jex: 2x6 row-major, translation columns first. */
+void orc_reproj_jext(double inv_dep, const double *pi7, const double *pj7, const double *qic, const double *tic,
+                     const double *pts_i, double Jex[12]) {
+    const double Qi[4] = {pi7[3], pi7[4], pi7[5], pi7[6]}, Qj[4] = {pj7[3], pj7[4], pj7[5], pj7[6]};
+    double pci[3] = {pts_i[0] / inv_dep, pts_i[1] / inv_dep, pts_i[2] / inv_dep};
+    double pbi[3], pw[3], pbj[3], pcj[3], t[3], Qji[4], qici[4];
+    q_rot(qic, pci, pbi);
+    for (int k = 0; k < 3; ++k) pbi[k] += tic[k];
+    q_rot(Qi, pbi, pw);
+    for (int k = 0; k < 3; ++k) pw[k] += pi7[k];
+    for (int k = 0; k < 3; ++k) t[k] = pw[k] - pj7[k];
+    q_inv(Qj, Qji);
+    q_rot(Qji, t, pbj);
+    for (int k = 0; k < 3; ++k) t[k] = pbj[k] - tic[k];
+    q_inv(qic, qici);
+    q_rot(qici, t, pcj);
+    const double dep = pcj[2];
+    const double red[6] = {1.0 / dep, 0, -pcj[0] / (dep * dep), 0, 1.0 / dep, -pcj[1] / (dep * dep)};
+    double Ri[9], Rj[9], ric[9], ricT[9], RjT[9], RjTRi[9], M1[9], L[9], tmp_r[9], T1[9], S1[9], S2[9], S3[9], Rr[9], v[3], w[3], u[3];
+    q_toR(Qi, Ri); q_toR(Qj, Rj); q_toR(qic, ric);
+    m3_T(ric, ricT); m3_T(Rj, RjT);
+    m3_mul(RjT, Ri, RjTRi);
+    for (int k = 0; k < 9; ++k) M1[k] = RjTRi[k] - ((k % 4 == 0) ? 1.0 : 0.0);
+    m3_mul(ricT, M1, L);                       /* ric^T (Rj^T Ri - I) */
+    m3_mul(ricT, RjTRi, T1); m3_mul(T1, ric, tmp_r); /* tmp_r = ric^T Rj^T Ri ric */
+    hat3(pci, S1);
+    m3_mul(tmp_r, S1, Rr);                     /* tmp_r skew(p_ci) */
+    m3_vec(tmp_r, pci, v); hat3(v, S2);        /* skew(tmp_r p_ci) */
+    m3_vec(Ri, tic, w);
+    for (int k = 0; k < 3; ++k) w[k] += pi7[k] - pj7[k];
+    m3_vec(RjT, w, u);
+    for (int k = 0; k < 3; ++k) u[k] -= tic[k];
+    m3_vec(ricT, u, v); hat3(v, S3);           /* skew(ric^T (Rj^T (Ri tic + Pi - Pj) - tic)) */
+    double je[18];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) { je[6 * a + b] = L[3 * a + b]; je[6 * a + 3 + b] = -Rr[3 * a + b] + S2[3 * a + b] + S3[3 * a + b]; }
+    for (int a = 0; a < 2; ++a)
+        for (int c = 0; c < 6; ++c) Jex[6 * a + c] = red[3 * a] * je[c] + red[3 * a + 1] * je[6 + c] + red[3 * a + 2] * je[12 + c];
+}
+
 /* ---- EdgeSE3Prior: A15/backend/edge_prior.cpp:39-80 (USE_SO3_JACOBIAN) ------------------------------ */
 void orc_se3prior(const double *pose, const double *pp, const double *qp, double r[6], double J[36]) {
     double qi[4] = {pose[3], pose[4], pose[5], pose[6]}, qn[4] = {qp[0], qp[1], qp[2], qp[3]};
@@ -539,12 +580,15 @@ int orc_make_hessian(const vio_graph *g, const orc_prior *prior, int flavour, do
         double W[4], Om[4] = {g->rp_info, 0, 0, g->rp_info}, drho = 1.0, rho0;
         if (flavour == VIO_LM_V17) robust_info2(g->rp_loss, g->rp_loss_delta, g->rp_info, r, &drho, W, &rho0);
         else memcpy(W, Om, sizeof(W));
-        const double *Jv[3] = {Jl, Ji, Jj};
-        int ldj[3] = {1, 6, 6}, dim[3] = {1, 6, 6};
-        int off[3] = {P + l, (g->pose_fixed && g->pose_fixed[i]) ? -1 : o.pose_off[i],
-                      (g->pose_fixed && g->pose_fixed[j]) ? -1 : o.pose_off[j]};
+        const int ext_free = g->ext_pose >= 0 && !(g->pose_fixed && g->pose_fixed[g->ext_pose]);
+        double Jex[12];
+        if (ext_free) orc_reproj_jext(g->inv_depth[l], g->pose + 7 * (size_t)i, g->pose + 7 * (size_t)j, qic, tic, g->rp_pts_i + 3 * e, Jex);
+        const double *Jv[4] = {Jl, Ji, Jj, Jex};
+        int ldj[4] = {1, 6, 6, 6}, dim[4] = {1, 6, 6, 6};
+        int off[4] = {P + l, (g->pose_fixed && g->pose_fixed[i]) ? -1 : o.pose_off[i],
+                      (g->pose_fixed && g->pose_fixed[j]) ? -1 : o.pose_off[j], ext_free ? o.pose_off[g->ext_pose] : -1};
         /* v15: b -= JtW r with W = information; v17: b -= drho * J^T * information * r */
-        add_edge_dense(H, b, n, 2, 3, Jv, ldj, dim, off, W, flavour == VIO_LM_V17 ? Om : W, drho, r);
+        add_edge_dense(H, b, n, 2, ext_free ? 4 : 3, Jv, ldj, dim, off, W, flavour == VIO_LM_V17 ? Om : W, drho, r);
     }
     for (int64_t e = 0; e < g->n_reproj_xyz; ++e) {
         int l = g->rx_point[e], i = g->rx_pose[e];

@@ -61,6 +61,9 @@ int orc_solve_linear(const double *H, const double *b, int P, int M, double lamb
 int orc_solve(const vio_graph *g, const orc_prior *prior, int iterations, const vio_lm_opts *opts, double *pose,
               double *speedbias, double *inv_depth, double *b_prior_out, double *err_prior_out, orc_result *res);
 
+/* 4th Jacobian of the v17 4-vertex EdgeReprojection (extrinsic vertex not fixed), A17/src/backend/edge_reprojection.cc:97-103 */
+void orc_reproj_jext(double inv_dep, const double *pose_i, const double *pose_j, const double *qic, const double *tic,
+                     const double *pts_i, double Jex[12]);
 /* VertexPointXYZ / EdgeReprojectionXYZ (A15/backend/edge_reprojection.cc:113-163): landmark dims are ordered
  * [n_landmark inverse depths | 3 per point]; orc_dims' M counts both. */
 void orc_reproj_xyz(const double *X, const double *pose_i, const double qic[4], const double tic[3], const double *obs,

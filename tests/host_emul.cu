@@ -15,7 +15,7 @@
 namespace {
 struct HostProblem {
     PackedGraph K;
-    std::vector<double> pose, pose_bak, sb, poseRT, Hll, bl, wh, wo, sys, bS, dxp, dxl, invd_bak;
+    std::vector<double> pose, pose_bak, sb, poseRT, Hll, bl, wh, wo, we, sys, bS, dxp, dxl, invd_bak;
     DevView v;
 };
 
@@ -53,6 +53,8 @@ void setup_packed(const vio_graph *g, const double *pose, HostProblem &H) {
     v.e_pose_j = K.e_pose_j.data(); v.e_pjx = K.pjx.data(); v.e_pjy = K.pjy.data();
     v.rp_info = g->rp_info; v.rp_loss = g->rp_loss; v.rp_delta = g->rp_loss_delta;
     v.Hll = H.Hll.data(); v.bl = H.bl.data(); v.wh = H.wh.data(); v.wo = H.wo.data();
+    H.we.assign(6 * (size_t)(K.L > 0 ? K.L : 1), 0.0);
+    v.we = H.we.data(); v.ext_pose = K.ext_free ? g->ext_pose : -1;
     v.S = H.sys.data(); v.bcorr = v.S + K.s_count; v.bp = v.bcorr + K.P; v.hdiag = v.bp + K.P; v.bS = H.bS.data();
     v.bsr_rowptr = K.rowptr.data(); v.bsr_col = K.col.data(); v.bsr_tr = K.tr.data();
     v.dxp = H.dxp.data(); v.dxl = H.dxl.data();

@@ -252,3 +252,16 @@ def xyz_scene(kind):
     if kind == "xyz_v15_solve":
         return sc.to_xyz(sc.monoba(20, 300), noise=0.02, seed=5)
     raise ValueError(kind)
+
+
+def extfree_scene(n_pose=6, n_feat=40):
+    """TestMonoBA scene in the v17 4-vertex form with the extrinsic VertexPose NOT fixed (ESTIMATE_EXTRINSIC=1): every
+    EdgeReprojection contributes its 4th Jacobian (A17/src/backend/edge_reprojection.cc:97-103)."""
+    vio = importlib.import_module("visual-inertial-odometry_b200")
+    s = vio.scenes.monoba(n_pose, n_feat, with_ext=True)
+    s.pose_fixed = np.zeros(s.pose.shape[0], np.uint8)
+    q = np.array([0.01, -0.02, 0.015, 1.0])
+    s.pose[0, :3] = [0.05, -0.02, 0.01]
+    s.pose[0, 3:] = q / np.linalg.norm(q)
+    s.rp_loss, s.rp_loss_delta, s.rp_info = capi.LOSS_CAUCHY, 1.0, 100.0
+    return s

@@ -604,3 +604,35 @@ def test_window_stream_marginalize_feeds_next_solve(vio):
     assert np.allclose(st.chi2_trace[:st.n_trace], g["chi2_trace"], rtol=1e-3, atol=0)
     assert rel_max(pose, g["pose"]) <= 1e-5 and rel_max(invd, g["inv_depth"]) <= 1e-4
     assert rel_max(sb[:, :3], g["speedbias"][:, :3]) <= 1e-4
+
+
+def test_free_extrinsic_vertex_vs_golden(vio):
+    """v17 4-vertex EdgeReprojection with the extrinsic VertexPose being estimated (ESTIMATE_EXTRINSIC=1): Hessian_ incl.
+    the extrinsic row/column and its coupling with every landmark, Schur complement, step and a full Solve against the
+    unmodified reference."""
+    from tests.scenes_extra import extfree_scene
+    g = _gold("extfree_6x40_v17_lin.npz")
+    s = extfree_scene(6, 40)
+    opts = vio.make_opts(flavour=vio.capi.LM_V17, solver=vio.capi.SOLVER_DENSE_CHOL)
+    p = vio.Problem()
+    p.set_graph(s)
+    H, b = p.get_hessian(opts)
+    assert rel_max(H, g["H"]) <= H_TOL and rel_l2(b, g["b"]) <= H_TOL
+    assert abs(p.chi2(opts) - float(g["chi2"])) <= H_TOL * float(g["chi2"])
+    p.linearize(opts)
+    S, bS = p.get_schur()
+    lam = float(g["lam"])
+    assert rel_max(S, g["S"] - lam * np.eye(S.shape[0])) <= H_TOL and rel_l2(bS, g["bS"]) <= H_TOL
+    p.solve_step(lam, opts)
+    dxp, dxl = p.get_delta()
+    assert rel_l2(np.concatenate([dxp, dxl]), g["dx"]) <= 1e-7
+    gs = _gold("extfree_20x300_v17_solve.npz")
+    s2 = extfree_scene(20, 300)
+    p2 = vio.Problem()
+    p2.set_graph(s2)
+    st = p2.solve(20, vio.make_opts(flavour=vio.capi.LM_V17))
+    pose, _, invd = p2.get_vertices()
+    assert st.iterations == int(gs["iterations"])
+    assert np.allclose(st.chi2_trace[:st.n_trace], gs["chi2_trace"], rtol=1e-6, atol=0)
+    assert rel_max(pose, gs["pose"]) <= FINAL_TOL and rel_max(invd, gs["inv_depth"]) <= FINAL_TOL
+    assert np.abs(pose[0] - s2.pose[0]).max() > 1e-6  # the extrinsic estimate moved

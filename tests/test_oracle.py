@@ -237,3 +237,27 @@ def test_oracle_xyz_solve_vs_golden(vio, name, kind, iters):
     assert rel_max(r["pose"], g["pose"]) <= 1e-8 and rel_max(r["point_xyz"], g["point_xyz"]) <= 1e-8
     if s.inv_depth.shape[0]:
         assert rel_max(r["inv_depth"], g["inv_depth"]) <= 1e-8
+
+
+def test_oracle_free_extrinsic_vs_golden(vio):
+    """v17 4-vertex EdgeReprojection with the extrinsic vertex being estimated: oracle (4th Jacobian, orc_reproj_jext)
+    and the device per-landmark body run on the CPU (tests/host_emul.cu) against the unmodified reference."""
+    from tests.scenes_extra import extfree_scene
+    from tests import emul
+    g = gold("extfree_6x40_v17_lin.npz")
+    s = extfree_scene(6, 40)
+    H, b = orc.hessian(s, vio.capi.LM_V17)
+    assert rel_max(H, g["H"]) <= 1e-12 and rel_l2(b, g["b"]) <= 1e-12
+    assert np.abs(H[:6, s.P:]).max() > 0  # the extrinsic vertex couples with the landmarks
+    S, bS, dx, _ = orc.solve_linear(H, b, s.P, float(g["lam"]), vio.capi.SOLVER_DENSE_CHOL)
+    assert rel_max(S, g["S"]) <= 1e-11 and rel_l2(dx, g["dx"]) <= 1e-7
+    if emul.available():
+        Se, bSe = emul.schur(s)
+        lam = float(g["lam"])
+        assert rel_max(Se, g["S"] - lam * np.eye(s.P)) <= 1e-9 and rel_l2(bSe, g["bS"]) <= 1e-9
+    gs = gold("extfree_20x300_v17_solve.npz")
+    s2 = extfree_scene(20, 300)
+    r = orc.solve(s2, 20, vio.make_opts(flavour=vio.capi.LM_V17))
+    assert r["iterations"] == int(gs["iterations"])
+    assert np.allclose(r["chi2_trace"], gs["chi2_trace"], rtol=1e-7, atol=0)
+    assert rel_max(r["pose"], gs["pose"]) <= 1e-7

@@ -78,7 +78,8 @@ struct vio_problem {
     DBuf<int> pose_off, sb_off, pose_blk;
     DBuf<int> lm_host, lm_eptr, e_pose_j;
     DBuf<double> lm_pix, lm_piy, lm_piz, e_pjx, e_pjy;
-    DBuf<double> Hll, bl, wh, wo;
+    DBuf<double> Hll, bl, wh, wo, we;
+    bool ext_free = false;
     DBuf<double> sys;  // [S | bcorr | bp | hdiag]
     DBuf<double> bS, dxp, dxl;
     DBuf<int> bsr_rowptr, bsr_col, bsr_tr, bsr_diag;
@@ -197,6 +198,7 @@ void fill_view(vio_problem *p) {
     v.lm_pix = p->lm_pix.p; v.lm_piy = p->lm_piy.p; v.lm_piz = p->lm_piz.p;
     v.e_pose_j = p->e_pose_j.p; v.e_pjx = p->e_pjx.p; v.e_pjy = p->e_pjy.p;
     v.Hll = p->Hll.p; v.bl = p->bl.p; v.wh = p->wh.p; v.wo = p->wo.p;
+    v.ext_pose = p->ext_free ? p->h_ext_pose : -1; v.we = p->we.p;
     v.S = p->sys.p;
     v.bcorr = p->sys.p + p->s_count;
     v.bp = v.bcorr + p->P;
@@ -232,6 +234,14 @@ int resolve_solver(const vio_problem *p, const vio_lm_opts &o) {
 // linearise: MakeHessian + Schur (+ all-reduce of the reduced system when sharded)
 // ---------------------------------------------------------------------------------------------
 int do_pose_prep(vio_problem *p) {
+    if (p->ext_free) {
+        // the extrinsic vertex is being estimated: the kernels take R_ic / t_ic by value, refresh them from its current pose
+        double e[7];
+        CK(cudaMemcpyAsync(e, p->pose.p + 7 * (size_t)p->h_ext_pose, sizeof(e), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        quat_to_R(e + 3, p->view.Ric);
+        p->view.tic[0] = e[0]; p->view.tic[1] = e[1]; p->view.tic[2] = e[2];
+    }
     k_pose_prep<<<grid_for(p->C, 128), 128, 0, p->stream>>>(p->view);
     p->launches++;
     return VIO_OK;
@@ -891,6 +901,8 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     CK(upload(p->e_pose_j, K.e_pose_j.data(), (size_t)E, s));
     CK(upload(p->e_pjx, K.pjx.data(), (size_t)E, s)); CK(upload(p->e_pjy, K.pjy.data(), (size_t)E, s));
     CK(p->Hll.alloc(L)); CK(p->bl.alloc(L)); CK(p->wh.alloc(6 * (size_t)L)); CK(p->wo.alloc(6 * (size_t)E));
+    p->ext_free = K.ext_free;
+    if (K.ext_free) { CK(p->we.alloc(6 * (size_t)std::max(L, 1))); CK(cudaMemsetAsync(p->we.p, 0, 6 * (size_t)std::max(L, 1) * sizeof(double), s)); }
     CK(p->sys.alloc(K.s_count + 3 * (size_t)P)); CK(p->bS.alloc(P)); CK(p->dxp.alloc(P)); CK(p->dxl.alloc(L));
     CK(cudaMemsetAsync(p->dxp.p, 0, P * sizeof(double), s));
     if (L > 0) CK(cudaMemsetAsync(p->dxl.p, 0, L * sizeof(double), s));
@@ -1405,6 +1417,11 @@ int vio_get_hessian(vio_problem *p, const vio_lm_opts *opts, double *H, double *
         CK(cudaMemcpyAsync(wo.data(), p->wo.p, wo.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         CK(cudaMemcpyAsync(ej.data(), p->e_pose_j.p, p->E * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     }
+    std::vector<double> wev;
+    if (p->ext_free && M) {
+        wev.resize(6 * (size_t)M);
+        CK(cudaMemcpyAsync(wev.data(), p->we.p, wev.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    }
     CK(cudaStreamSynchronize(p->stream));
     if (H) {
         memset(H, 0, (size_t)n * n * sizeof(double));
@@ -1421,6 +1438,7 @@ int vio_get_hessian(vio_problem *p, const vio_lm_opts *opts, double *H, double *
             };
             if (eptr[l] != eptr[l + 1]) put(host[l], &wh[6 * (size_t)l]);
             for (int e = eptr[l]; e < eptr[l + 1]; ++e) put(ej[e], &wo[6 * (size_t)e]);
+            if (p->ext_free && eptr[l] != eptr[l + 1]) put(p->h_ext_pose, &wev[6 * (size_t)l]);
         }
     }
     if (b) {

@@ -35,6 +35,9 @@ struct DevView {
     double rp_info;
     int rp_loss;
     double rp_delta;
+    // free extrinsic vertex (4-vertex EdgeReprojection with ESTIMATE_EXTRINSIC=1): pose index or -1; its H_lp rows [L][6]
+    int ext_pose;
+    double *we;
     // linearisation outputs
     double *Hll, *bl, *wh, *wo;
     double *S;         // dense P*P or bsr values

@@ -240,6 +240,9 @@ VIO_HD void linearize_landmark(const DevView &v, int l) {
 
     double Ms[6] = {0, 0, 0, 0, 0, 0};  // Σ M_e, symmetric 3x3: 00 01 02 11 12 22
     double ms[3] = {0, 0, 0};           // Σ drho c B^T r
+    // free extrinsic vertex (v17 4-vertex edge, A17/src/backend/edge_reprojection.cc:97-103): its H_lp row Σ J_ex^T W J_lambda
+    const int xe = v.ext_pose;
+    double wes[6] = {0, 0, 0, 0, 0, 0};
 
     for (int e = e0; e < e1; ++e) {
         const int j = v.e_pose_j[e];
@@ -284,6 +287,83 @@ VIO_HD void linearize_landmark(const DevView &v, int l) {
                              dc * (B[2] * r[0] + B[5] * r[1])};
         Ms[0] += M[0]; Ms[1] += M[1]; Ms[2] += M[2]; Ms[3] += M[4]; Ms[4] += M[5]; Ms[5] += M[8];
         ms[0] += m[0]; ms[1] += m[1]; ms[2] += m[2];
+
+        if (xe >= 0) {
+            // J_ex = red * [ Ric^T (Rj^T Ri - I) | -T skew(p_ci) + skew(T p_ci) + skew(Ric^T (Rj^T (Ri tic + Pi - Pj) - tic)) ],
+            // T = Ric^T Rj^T Ri Ric
+            double RjtRi[9], M1[9], Lm[9], T1[9], Tm[9], S1[9], TS[9], tv[3], wv[3], uv[3], qv[3];
+            mat3t_mul(RTj, RTh, RjtRi);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) M1[k] = RjtRi[k] - ((k % 4 == 0) ? 1.0 : 0.0);
+            mat3t_mul(v.Ric, M1, Lm);
+            mat3t_mul(v.Ric, RjtRi, T1);
+            mat3_mul(T1, v.Ric, Tm);
+            mat3_mul_hat(Tm, pci, TS);                       // T skew(p_ci)
+            mat3_mul_vec(Tm, pci, tv);                       // T p_ci
+            mat3_mul_vec(RTh, v.tic, wv);
+            wv[0] += RTh[9] - RTj[9]; wv[1] += RTh[10] - RTj[10]; wv[2] += RTh[11] - RTj[11];
+            mat3t_mul_vec(RTj, wv, uv);
+            uv[0] -= v.tic[0]; uv[1] -= v.tic[1]; uv[2] -= v.tic[2];
+            mat3t_mul_vec(v.Ric, uv, qv);
+            const double h1[9] = {0.0, -tv[2], tv[1], tv[2], 0.0, -tv[0], -tv[1], tv[0], 0.0};
+            const double h2[9] = {0.0, -qv[2], qv[1], qv[2], 0.0, -qv[0], -qv[1], qv[0], 0.0};
+#pragma unroll
+            for (int k = 0; k < 9; ++k) S1[k] = -TS[k] + h1[k] + h2[k];
+            double Je[12], WJe[12];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                Je[c] = red[0] * Lm[c] + red[2] * Lm[6 + c];
+                Je[6 + c] = red[4] * Lm[3 + c] + red[5] * Lm[6 + c];
+                Je[3 + c] = red[0] * S1[c] + red[2] * S1[6 + c];
+                Je[9 + c] = red[4] * S1[3 + c] + red[5] * S1[6 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { WJe[c] = W[0] * Je[c] + W[1] * Je[6 + c]; WJe[6 + c] = W[1] * Je[c] + W[2] * Je[6 + c]; }
+            double Xe[36];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) Xe[6 * a + c] = Je[a] * WJe[c] + Je[6 + a] * WJe[6 + c];
+            s_add_diag(v, xe, Xe, 1.0);
+            double *hd = v.hdiag + v.pose_off[xe], *be = v.bp + v.pose_off[xe];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                vio_add(hd + k, Xe[7 * k]);
+                vio_add(be + k, -dc * (Je[k] * r[0] + Je[6 + k] * r[1]));
+            }
+            // H_lp row of the extrinsic vertex: J_ex^T W J_lambda, J_lambda = B g
+            const double jl0 = B[0] * g[0] + B[1] * g[1] + B[2] * g[2], jl1 = B[3] * g[0] + B[4] * g[1] + B[5] * g[2];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) wes[k] += WJe[k] * jl0 + WJe[6 + k] * jl1;
+            // (ext, host) = J_ex^T W B [I G] ; (ext, j) = J_ex^T W B [-I N]
+            double JeWB[18];  // 6x3 = J_ex^T (W B)
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) JeWB[3 * a + c] = Je[a] * WB[c] + Je[6 + a] * WB[3 + c];
+            if (!hfix) {
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        Xe[6 * a + c] = JeWB[3 * a + c];
+                        Xe[6 * a + 3 + c] = JeWB[3 * a] * G[c] + JeWB[3 * a + 1] * G[3 + c] + JeWB[3 * a + 2] * G[6 + c];
+                    }
+                s_add_block(v, xe, h, Xe, 1.0);
+            }
+            if (!v.pose_fixed[j]) {
+                double Nn[9];
+                mat3_mul_hat(RTj, pbj, Nn);
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        Xe[6 * a + c] = -JeWB[3 * a + c];
+                        Xe[6 * a + 3 + c] = JeWB[3 * a] * Nn[c] + JeWB[3 * a + 1] * Nn[3 + c] + JeWB[3 * a + 2] * Nn[6 + c];
+                    }
+                s_add_block(v, xe, j, Xe, 1.0);
+            }
+        }
 
         double *wj = v.wo + 6 * (size_t)e;
         if (v.pose_fixed[j]) {
@@ -384,24 +464,32 @@ VIO_HD void linearize_landmark(const DevView &v, int l) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) whp[k] = wh[k];
 
+    double *wep = nullptr;
+    if (xe >= 0) {
+        wep = v.we + 6 * (size_t)l;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) wep[k] = wes[k];
+    }
     if (!WITH_SCHUR) return;
     // Schur complement: S -= Hpl Hll^-1 Hlp ; bS -= Hpl Hll^-1 bl     (landmark diagonal is never damped)
+    // vertex list: host (a = -1), observers (0 .. n_obs-1) and, when it is being estimated, the extrinsic vertex (a = n_obs)
     const double inv = 1.0 / Hll;
-    const int n = e1 - e0;
+    const int n_obs = e1 - e0;
+    const int n = n_obs + (xe >= 0 ? 1 : 0);
     for (int a = -1; a < n; ++a) {
-        const int pa = a < 0 ? h : v.e_pose_j[e0 + a];
+        const int pa = a < 0 ? h : (a < n_obs ? v.e_pose_j[e0 + a] : xe);
         if (v.pose_fixed[pa]) continue;
         double wa[6];
-        const double *wap = a < 0 ? whp : v.wo + 6 * (size_t)(e0 + a);
+        const double *wap = a < 0 ? whp : (a < n_obs ? v.wo + 6 * (size_t)(e0 + a) : wep);
 #pragma unroll
         for (int k = 0; k < 6; ++k) wa[k] = wap[k] * inv;
         double *bc = v.bcorr + v.pose_off[pa];
 #pragma unroll
         for (int k = 0; k < 6; ++k) vio_add(bc + k, wa[k] * bl);
         for (int b = a; b < n; ++b) {
-            const int pb = b < 0 ? h : v.e_pose_j[e0 + b];
+            const int pb = b < 0 ? h : (b < n_obs ? v.e_pose_j[e0 + b] : xe);
             if (v.pose_fixed[pb]) continue;
-            const double *wbp = b < 0 ? whp : v.wo + 6 * (size_t)(e0 + b);
+            const double *wbp = b < 0 ? whp : (b < n_obs ? v.wo + 6 * (size_t)(e0 + b) : wep);
             double X[36];
 #pragma unroll
             for (int r = 0; r < 6; ++r)
@@ -602,6 +690,12 @@ __global__ void __launch_bounds__(256) k_backsub(DevView v, double lambda, doubl
             const double *dj = v.dxp + v.pose_off[v.e_pose_j[e]];
 #pragma unroll
             for (int k = 0; k < 6; ++k) t -= w[k] * dj[k];
+        }
+        if (v.ext_pose >= 0) {  // free extrinsic vertex
+            const double *w = v.we + 6 * (size_t)l;
+            const double *dx = v.dxp + v.pose_off[v.ext_pose];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) t -= w[k] * dx[k];
         }
         const double d = t / v.Hll[l];
         v.dxl[l] = d;

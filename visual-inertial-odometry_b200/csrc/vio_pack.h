@@ -16,6 +16,7 @@
 
 struct PackedGraph {
     int C = 0, NSB = 0, NB = 0, P = 0, L = 0, Lglobal = 0, storage = 1;
+    bool ext_free = false;    // the extrinsic VertexPose is being estimated (4-vertex EdgeReprojection, 4th Jacobian)
     int batch = 1, Pper = 0;  // lock-step batch: `batch` stacked Pper x Pper reduced systems (dense), P = batch * Pper
     long long E = 0, nnzb = 0;
     size_t s_count = 0;
@@ -81,11 +82,17 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         }
     }
     // ---- extrinsics -----------------------------------------------------------------------------
+    K.ext_free = false;
     double *qic = K.qic, *tic = K.tic;
     if (g->ext_pose >= 0) {
         if (g->ext_pose >= C) return pack_fail(err, VIO_ERR_INVALID, "ext_pose out of range");
-        if (!(g->pose_fixed && g->pose_fixed[g->ext_pose]))
-            return pack_fail(err, VIO_ERR_UNSUPPORTED, "extrinsic vertex must be fixed (ESTIMATE_EXTRINSIC=0 path)");
+        // a FREE extrinsic vertex (ESTIMATE_EXTRINSIC=1) contributes the 4th Jacobian of every EdgeReprojection and couples
+        // with every landmark: handled by the per-landmark kernel on unsharded, single-problem, dense handles
+        K.ext_free = !(g->pose_fixed && g->pose_fixed[g->ext_pose]);
+        if (K.ext_free && (shard_world > 1 || batch > 1))
+            return pack_fail(err, VIO_ERR_UNSUPPORTED, "a free extrinsic vertex is not supported with sharding / lock-step batches");
+        if (K.ext_free && (g->n_point > 0 || g->n_reproj_xyz > 0))
+            return pack_fail(err, VIO_ERR_UNSUPPORTED, "a free extrinsic vertex cannot be combined with EdgeReprojectionXYZ (constant extrinsics)");
         const double *e = g->pose + 7 * (size_t)g->ext_pose;
         tic[0] = e[0]; tic[1] = e[1]; tic[2] = e[2];
         qic[0] = e[3]; qic[1] = e[4]; qic[2] = e[5]; qic[3] = e[6];
@@ -186,7 +193,8 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
 
     // ---- storage of the reduced system ----------------------------------------------------------
     int storage = g->storage;
-    if (storage == VIO_STORAGE_AUTO) storage = (NSB == 0 && P > 2048) ? VIO_STORAGE_BSR : VIO_STORAGE_DENSE;
+    if (storage == VIO_STORAGE_AUTO) storage = (NSB == 0 && P > 2048 && !K.ext_free) ? VIO_STORAGE_BSR : VIO_STORAGE_DENSE;
+    if (K.ext_free && storage != VIO_STORAGE_DENSE) return pack_fail(err, VIO_ERR_UNSUPPORTED, "a free extrinsic vertex needs dense storage");
     if (storage == VIO_STORAGE_BSR && (NSB != 0 || g->n_imu != 0))
         return pack_fail(err, VIO_ERR_UNSUPPORTED, "BSR storage supports 6-dof pose vertices only");
     size_t s_count;
@@ -352,7 +360,7 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
             }
             l0 = l1;
         }
-        if (K.n_groups == 0) K.grouped_ok = false;
+        if (K.n_groups == 0 || K.ext_free) K.grouped_ok = false;
         // one observer slot per warp, 4..10 warps (VIO_B200_GROUP_WARPS overrides; tuning knob)
         const int rounds = (max_obs_slots + 9) / 10;
         int nwarp = rounds > 0 ? (max_obs_slots + rounds - 1) / rounds : 4;
