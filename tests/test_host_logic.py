@@ -140,3 +140,42 @@ def test_block_cholesky_symbolic_factorisation(nb, kind):
     ref = np.linalg.solve(A + lam * np.eye(6 * nb), b)
     assert np.abs(x - ref).max() <= 1e-11 * np.abs(ref).max()
     assert nnzL.value >= (len(col) + nb) // 2  # at least the lower triangle of A
+
+
+def test_packer_rejects_what_the_device_path_does_not_cover():
+    """vio_set_graph's checks (csrc/vio_pack.h), exercised through the CPU harness: bad indices are VIO_ERR_INVALID,
+    graphs outside the documented preconditions are VIO_ERR_UNSUPPORTED - never a silent wrong answer."""
+    vio = importlib.import_module("visual-inertial-odometry_b200")
+    capi = vio.capi
+    INVALID, UNSUPPORTED = capi.VIO_ERR_INVALID, capi.VIO_ERR_UNSUPPORTED
+
+    def rc_of(scene):
+        g, keep = scene.to_c()
+        P = scene.P
+        S, bS = np.zeros((max(P, 1), max(P, 1))), np.zeros(max(P, 1))
+        dp = C.POINTER(C.c_double)
+        return emul.lib().emul_linearize(C.byref(g), 1, S.ctypes.data_as(dp), None, bS.ctypes.data_as(dp), None, None, None, None, None)
+
+    ok = vio.scenes.monoba(4, 30)
+    assert rc_of(ok) == 0
+    s = vio.scenes.monoba(4, 30)
+    s.rp_pose_j[3] = 99                                   # pose index out of range
+    assert rc_of(s) == INVALID
+    s = vio.scenes.monoba(4, 30)
+    s.rp_landmark[0] = -1
+    assert rc_of(s) == INVALID
+    s = vio.scenes.monoba(4, 30)
+    k = int(np.nonzero(s.rp_landmark == s.rp_landmark[5])[0][-1])
+    s.rp_pose_i[k] = (s.rp_pose_i[k] + 1) % 4              # edges of one landmark disagree on the host pose
+    assert rc_of(s) == UNSUPPORTED
+    s = _window(vio)
+    s.storage = capi.STORAGE_BSR                          # block-sparse storage with speed-bias vertices
+    assert rc_of(s) == UNSUPPORTED
+    s = vio.scenes.monoba(4, 30, with_ext=True)
+    s.pose_fixed[0] = 0                                   # free extrinsic vertex: fine on a dense single problem ...
+    assert rc_of(s) == 0
+    s.storage = capi.STORAGE_BSR                          # ... but not with block-sparse storage
+    assert rc_of(s) == UNSUPPORTED
+    s = vio.scenes.to_xyz(vio.scenes.monoba(4, 30))
+    s.rx_point[2] = 10 ** 6
+    assert rc_of(s) == INVALID

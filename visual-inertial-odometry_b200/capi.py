@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvio_b200.so")
 
 VIO_OK = 0
+VIO_ERR_INVALID, VIO_ERR_CUDA, VIO_ERR_UNSUPPORTED, VIO_ERR_EMPTY, VIO_ERR_NO_DEVICE, VIO_ERR_STATE = 1, 2, 3, 4, 5, 6
 ERR_NAMES = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "UNSUPPORTED", 4: "EMPTY", 5: "NO_DEVICE", 6: "STATE"}
 LM_V15, LM_V17 = 0, 1
 SOLVER_AUTO, SOLVER_DENSE_CHOL, SOLVER_REF_PCG, SOLVER_BLOCK_PCG, SOLVER_BLOCK_PCG_2L, SOLVER_BLOCK_CHOL = 0, 1, 2, 3, 4, 5
