@@ -113,6 +113,8 @@ struct vio_problem {
     DBuf<int> info;
     DBuf<unsigned> bar;
     bool coop_ok = false;
+    // debugging / A-B switches read from the environment once, at vio_create
+    bool env_profile = false, env_multikernel = false, env_pcg_plain = false;
     int num_sms = 148;
     DBuf<double> bpcg_p2;
     // GENERIC_PROBLEM lane
@@ -226,7 +228,7 @@ vio_lm_opts default_opts() {
 int resolve_solver(const vio_problem *p, const vio_lm_opts &o) {
     if (o.solver != VIO_SOLVER_AUTO) return o.solver;
     if (p->storage == VIO_STORAGE_BSR)
-        return (p->NB >= 256 && p->coop_ok && !getenv("VIO_B200_PCG_PLAIN")) ? VIO_SOLVER_BLOCK_PCG_2L : VIO_SOLVER_BLOCK_PCG;
+        return (p->NB >= 256 && p->coop_ok && !p->env_pcg_plain) ? VIO_SOLVER_BLOCK_PCG_2L : VIO_SOLVER_BLOCK_PCG;
     return o.flavour == VIO_LM_V15 ? VIO_SOLVER_REF_PCG : VIO_SOLVER_DENSE_CHOL;
 }
 
@@ -261,7 +263,7 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
         gv.hdr = (const GroupHdr *)p->g_hdr.p; gv.slot_pose = p->g_slot_pose.p; gv.pairinfo = p->g_pairinfo.p;
         gv.ell_pjx = p->ell_pjx.p; gv.ell_pjy = p->ell_pjy.p; gv.ell_edge = p->ell_edge.p;
         gv.prof = nullptr;
-        if (getenv("VIO_B200_PROFILE")) {
+        if (p->env_profile) {
             if (p->prof.n < 16) { CK(p->prof.alloc(16)); CK(cudaMemsetAsync(p->prof.p, 0, 16 * sizeof(unsigned long long), p->stream)); }
             gv.prof = p->prof.p;
         }
@@ -440,7 +442,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         const int g_dir = grid_for(6LL * nb, 256, BPCG_MAXPART);
         double hs[8];
         bool done_persistent = false;
-        if (p->coop_ok && !getenv("VIO_B200_PCG_MULTIKERNEL")) {
+        if (p->coop_ok && !p->env_multikernel) {
             // one cooperative launch: grid sized to be co-resident (2 CTAs per SM at most)
             int grid = std::max(1, std::min(std::min(p->num_sms, BPCG_MAXPART), (nb + 15) / 16));
             // two-level preconditioner: apc aggregates per CTA of >= 16 block rows; the coarse inversion keeps 7*apc rows of
@@ -573,7 +575,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                 unsigned epoch = ++p->cz_epoch;  // flags of earlier launches hold smaller epochs: no reset needed
                 int ncv = nc_, rpv = p->cz_rp;
                 unsigned long long *gjprof = nullptr;
-                if (getenv("VIO_B200_PROFILE")) {
+                if (p->env_profile) {
                     if (p->prof.n < 16) { CK(p->prof.alloc(16)); CK(cudaMemsetAsync(p->prof.p, 0, 16 * sizeof(unsigned long long), p->stream)); }
                     gjprof = p->prof.p + 8;
                 }
@@ -628,7 +630,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         }
         CK(cudaMemcpyAsync(hs, s.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         CK(cudaStreamSynchronize(p->stream));
-        if (done_persistent && getenv("VIO_B200_PROFILE")) {
+        if (done_persistent && p->env_profile) {
             double hc[4];
             cudaMemcpy(hc, s.scal + 8, sizeof(hc), cudaMemcpyDeviceToHost);
             const double it_ = std::max(1.0, hs[4]);
@@ -799,6 +801,9 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         p->coop_ok = coop != 0;
+        p->env_profile = getenv("VIO_B200_PROFILE") != nullptr;
+        p->env_multikernel = getenv("VIO_B200_PCG_MULTIKERNEL") != nullptr;
+        p->env_pcg_plain = getenv("VIO_B200_PCG_PLAIN") != nullptr;
         if (sms > 0) p->num_sms = sms;
     }
     p->ev_lin.resize(48);  // kernel timing events (the first 48 launches of a solve are timed)
