@@ -284,8 +284,9 @@ int vio_solve_batched(int device, int32_t n_workers, vio_batch_item *items, int6
  * counts may differ per item.  The batch is packed as ONE graph with `batch` stacked P x P reduced systems: every kernel
  * launch covers all items, one CTA per item factorises its reduced system, and the v17 LM control runs per item between
  * launches (items that converge early stop taking steps).  Results agree with vio_solve_batched to rounding (the
- * reductions use a different, still deterministic, order).  v17 flavour + exact reduced solve only; max_chunk <= 0:
- * 2048 items per packed graph.                                                                                        */
+ * reductions use a different, still deterministic, order).  v17 flavour + exact reduced solve only.  Batches larger than
+ * max_chunk (<= 0: 1024 items) are processed as a two-slot software pipeline: while the LM loop of one chunk runs on the
+ * device, the next chunk is packed and uploaded into a second handle.                                                  */
 int vio_solve_batched_lockstep(int device, vio_batch_item *items, int64_t n_items, int32_t iterations,
                                const vio_lm_opts *opts, int32_t max_chunk);
 /* The lock-step entry keeps one device handle and its host staging alive between calls (a caller that submits batch

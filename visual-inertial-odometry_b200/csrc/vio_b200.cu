@@ -1619,17 +1619,25 @@ int vio_solve_batched(int device, int32_t n_workers, vio_batch_item *items, int6
 // Host staging that survives between calls (per-item packs, the merged pack, the concatenated vertex / IMU arrays) and the
 // device handle with its buffers: a caller that submits batch after batch pays the allocations and page faults once.
 struct LockstepCache {
-    std::mutex mu;
     vio_problem *handle = nullptr;
     int device = -1;
     std::vector<PackedGraph> Ks;
     PackedGraph K;
     std::vector<double> pose, sb, idt, idp, idq, idv, iba, ibg, ijac, icov;
     std::vector<int32_t> ipi, isi, ipj, isj;
+    // what lockstep_prepare leaves for lockstep_run
+    int B = 0, C = 0, NSB = 0, Pper = 0;
+    long long Lt = 0;
+    size_t tri_bytes = 0;
+    std::vector<long long> Loff;
+    double ms_pack = 0.0, ms_upload = 0.0;
 };
-static LockstepCache g_lockstep;
+// two slots: while the LM loop of one chunk runs on the device, the next chunk is packed and uploaded into the other
+static LockstepCache g_lockstep[2];
+static std::mutex g_lockstep_mu;
 
-static int lockstep_chunk(vio_problem *p, LockstepCache &cache, vio_batch_item *items, int B, int32_t iterations, const vio_lm_opts &o) {
+// phase 1 (host-heavy): validate, pack every item, merge, upload graph and priors into the slot's handle
+static int lockstep_prepare(vio_problem *p, LockstepCache &cache, vio_batch_item *items, int B) {
     CK(cudaSetDevice(p->device));
     const vio_graph *g0 = items[0].graph;
     if (!g0) return fail(p, VIO_ERR_INVALID, "item 0: graph missing");
@@ -1777,6 +1785,23 @@ static int lockstep_chunk(vio_problem *p, LockstepCache &cache, vio_batch_item *
     }
     p->prior_dim = prior_dim; p->err_dim = err_dim;
     fill_view(p);  // lm_prob pointer
+    cache.B = B; cache.C = C; cache.NSB = NSB; cache.Pper = Pper; cache.Lt = Lt; cache.tri_bytes = tri_bytes; cache.Loff = Loff;
+    cache.ms_pack = t_concat - t_start; cache.ms_upload = now() - t_concat;
+    (void)prof;
+    return VIO_OK;
+}
+
+// phase 2 (device-heavy): the per-problem LM loop over the prepared chunk, then the results
+static int lockstep_run(vio_problem *p, LockstepCache &cache, vio_batch_item *items, int32_t iterations, const vio_lm_opts &o) {
+    CK(cudaSetDevice(p->device));
+    const bool prof = getenv("VIO_B200_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
+    const int B = cache.B, C = cache.C, NSB = cache.NSB, Pper = cache.Pper;
+    const long long Lt = cache.Lt;
+    const size_t tri_bytes = cache.tri_bytes;
+    const std::vector<long long> &Loff = cache.Loff;
+    cudaStream_t st = p->stream;
     // ---- LM, per problem (A17/src/backend/problem.cc:169-250) ----------------------------------------------------
     struct LmState {
         double chi = 0, lambda = 0, ni = 2, last_chi = 1e20;
@@ -1932,8 +1957,9 @@ static int lockstep_chunk(vio_problem *p, LockstepCache &cache, vio_batch_item *
         it.rc = VIO_OK;
     }
     if (prof)
-        fprintf(stderr, "[vio_b200 profile] lockstep B=%d: pack+merge %.1f ms, upload %.1f ms, priors+LM loop %.1f ms (%d linearisations, device %.1f ms), "
-                        "total %.1f ms\n", B, t_concat - t_start, t_pack - t_concat, t_loop_end - t_pack, linearizations, (double)ms, now() - t_start);
+        fprintf(stderr, "[vio_b200 profile] lockstep B=%d: pack+merge %.1f ms, upload (graph + priors) %.1f ms | LM loop %.1f ms (%d linearisations, "
+                        "device %.1f ms), results %.1f ms\n", B, cache.ms_pack, cache.ms_upload, t_loop_end - t_start, linearizations, (double)ms,
+                now() - t_loop_end);
     return VIO_OK;
 }
 
@@ -1944,44 +1970,71 @@ int vio_solve_batched_lockstep(int device, vio_batch_item *items, int64_t n_item
     vio_lm_opts o = opts ? *opts : default_opts();
     if (o.flavour != VIO_LM_V17 || (o.solver != VIO_SOLVER_AUTO && o.solver != VIO_SOLVER_DENSE_CHOL))
         return VIO_ERR_UNSUPPORTED;  // the lock-step loop is the v17 LM with the exact reduced solve
-    LockstepCache &cache = g_lockstep;
-    std::lock_guard<std::mutex> lock(cache.mu);  // one lock-step batch at a time per process
+    std::lock_guard<std::mutex> lock(g_lockstep_mu);  // one lock-step batch at a time per process
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
-    if (cache.handle && cache.device != device) { vio_destroy(cache.handle); cache.handle = nullptr; }
-    if (!cache.handle) {
-        int rc = vio_create(device, nullptr, &cache.handle);
-        if (rc != VIO_OK) return rc;
-        cache.device = device;
-    }
-    vio_problem *p = cache.handle;
-    const double t1 = now();
-    if (max_chunk <= 0) max_chunk = 2048;
-    int rc = VIO_OK;
-    for (int64_t i0 = 0; i0 < n_items && rc == VIO_OK; i0 += max_chunk) {
-        const int B = (int)std::min<int64_t>(max_chunk, n_items - i0);
-        rc = lockstep_chunk(p, cache, items + i0, B, iterations, o);
-        if (rc != VIO_OK) {
-            fprintf(stderr, "vio_solve_batched_lockstep: %s\n", p->err.c_str());
-            for (int k = 0; k < B; ++k) items[i0 + k].rc = rc;
+    if (max_chunk <= 0) max_chunk = 1024;
+    const int64_t n_chunks = (n_items + max_chunk - 1) / max_chunk;
+    for (int sl = 0; sl < (n_chunks > 1 ? 2 : 1); ++sl) {
+        LockstepCache &c = g_lockstep[sl];
+        if (c.handle && c.device != device) { vio_destroy(c.handle); c.handle = nullptr; }
+        if (!c.handle) {
+            int rc = vio_create(device, nullptr, &c.handle);
+            if (rc != VIO_OK) return rc;
+            c.device = device;
         }
     }
+    const double t1 = now();
+    auto chunk_of = [&](int64_t k, vio_batch_item *&first, int &B) {
+        const int64_t i0 = k * max_chunk;
+        first = items + i0;
+        B = (int)std::min<int64_t>(max_chunk, n_items - i0);
+    };
+    auto report = [&](int rc, LockstepCache &c, vio_batch_item *first, int B) {
+        fprintf(stderr, "vio_solve_batched_lockstep: %s\n", c.handle->err.c_str());
+        for (int k = 0; k < B; ++k) first[k].rc = rc;
+    };
+    // software pipeline over the chunks: prepare(k+1) (host packing + H2D into the other slot) overlaps run(k) (device LM loop)
+    int rc = VIO_OK;
+    vio_batch_item *first = nullptr;
+    int B = 0;
+    chunk_of(0, first, B);
+    rc = lockstep_prepare(g_lockstep[0].handle, g_lockstep[0], first, B);
+    if (rc != VIO_OK) report(rc, g_lockstep[0], first, B);
+    for (int64_t k = 0; k < n_chunks && rc == VIO_OK; ++k) {
+        LockstepCache &cur = g_lockstep[k & 1];
+        chunk_of(k, first, B);
+        std::thread next;
+        int rc_next = VIO_OK;
+        vio_batch_item *nfirst = nullptr;
+        int nB = 0;
+        if (k + 1 < n_chunks) {
+            chunk_of(k + 1, nfirst, nB);
+            LockstepCache *nc = &g_lockstep[(k + 1) & 1];
+            next = std::thread([&rc_next, nc, nfirst, nB] { rc_next = lockstep_prepare(nc->handle, *nc, nfirst, nB); });
+        }
+        rc = lockstep_run(cur.handle, cur, first, iterations, o);
+        if (next.joinable()) next.join();
+        if (rc != VIO_OK) report(rc, cur, first, B);
+        else if (rc_next != VIO_OK) { rc = rc_next; report(rc, g_lockstep[(k + 1) & 1], nfirst, nB); }
+    }
     if (getenv("VIO_B200_PROFILE"))
-        fprintf(stderr, "[vio_b200 profile] lockstep call: handle %.1f ms, chunks %.1f ms\n", t1 - t0, now() - t1);
+        fprintf(stderr, "[vio_b200 profile] lockstep call: handles %.1f ms, %lld chunk(s) %.1f ms\n", t1 - t0, (long long)n_chunks, now() - t1);
     return rc;
 }
-/* frees the cached lock-step handle and its host staging (optional; the process exit does it too) */
+/* frees the cached lock-step handles and their host staging (optional; the process exit does it too) */
 int vio_lockstep_release(void) {
-    LockstepCache &cache = g_lockstep;
-    std::lock_guard<std::mutex> lock(cache.mu);
-    if (cache.handle) vio_destroy(cache.handle);
-    cache.handle = nullptr;
-    cache.device = -1;
-    std::vector<PackedGraph>().swap(cache.Ks);
-    cache.K = PackedGraph();
-    for (auto *v : {&cache.pose, &cache.sb, &cache.idt, &cache.idp, &cache.idq, &cache.idv, &cache.iba, &cache.ibg, &cache.ijac, &cache.icov})
-        std::vector<double>().swap(*v);
-    for (auto *v : {&cache.ipi, &cache.isi, &cache.ipj, &cache.isj}) std::vector<int32_t>().swap(*v);
+    std::lock_guard<std::mutex> lock(g_lockstep_mu);
+    for (LockstepCache &cache : g_lockstep) {
+        if (cache.handle) vio_destroy(cache.handle);
+        cache.handle = nullptr;
+        cache.device = -1;
+        std::vector<PackedGraph>().swap(cache.Ks);
+        cache.K = PackedGraph();
+        for (auto *v : {&cache.pose, &cache.sb, &cache.idt, &cache.idp, &cache.idq, &cache.idv, &cache.iba, &cache.ibg, &cache.ijac, &cache.icov})
+            std::vector<double>().swap(*v);
+        for (auto *v : {&cache.ipi, &cache.isi, &cache.ipj, &cache.isj}) std::vector<int32_t>().swap(*v);
+    }
     return VIO_OK;
 }
 
