@@ -140,7 +140,13 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     std::vector<int> lorder(L);
     for (int ll = 0; ll < L; ++ll) lorder[ll] = l_begin + ll;
     auto host_of = [&](int l) { return cnt[l] == cnt[l + 1] ? 0x7fffffff : g->rp_pose_i[eorder[cnt[l]]]; };
-    std::stable_sort(lorder.begin(), lorder.end(), [&](int a, int b) { return host_of(a) < host_of(b); });
+    {
+        // scenes are usually generated host by host: skip the sort when the order is already non-decreasing
+        std::vector<int> hkey(L);
+        for (int ll = 0; ll < L; ++ll) hkey[ll] = host_of(l_begin + ll);
+        if (!std::is_sorted(hkey.begin(), hkey.end()))
+            std::stable_sort(lorder.begin(), lorder.end(), [&](int a, int b) { return hkey[a - l_begin] < hkey[b - l_begin]; });
+    }
     int ecur = 0;
     for (int ll = 0; ll < L; ++ll) {
         const int l = lorder[ll];
@@ -279,10 +285,18 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         K.grouped_ok = true;
         K.n_groups = 0; K.group_smem_max = 0;
         K.g_hdr.clear(); K.g_slot_pose.clear(); K.g_pairinfo.clear(); K.ell_pjx.clear(); K.ell_pjy.clear(); K.ell_edge.clear();
+        {
+            // the ELL arrays hold every edge once plus padding: reserve up front instead of growing group by group
+            const size_t cap = (size_t)E + (size_t)E / 4 + 1024;
+            K.ell_pjx.reserve(cap); K.ell_pjy.reserve(cap); K.ell_edge.reserve(cap);
+            const size_t ng = (size_t)L / (size_t)std::max(1, target_lm / 2) + 16;
+            K.g_hdr.reserve(8 * ng); K.g_slot_pose.reserve(NS_MAX * ng / 2); K.g_pairinfo.reserve(ng * 70);
+        }
         int max_obs_slots = 0;
         int l0 = 0;
         std::vector<int> slots;  // slot -> pose (slot 0 = host)
         std::vector<int> slot_of_pose(C, -1);
+        std::vector<int> seen_stamp(C, 0);  // landmark (index + 1) that last listed this pose as an observer
         while (l0 < L && K.grouped_ok) {
             if (lm_eptr[l0] == lm_eptr[l0 + 1]) break;  // only edge-less landmarks remain
             const int host = lm_host[l0];
@@ -295,10 +309,8 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
                 bool bad = false;
                 for (int e = lm_eptr[l1]; e < lm_eptr[l1 + 1]; ++e) {
                     const int pj = e_pose_j[e];
-                    if (pj == host) { bad = true; break; }
-                    for (int e2 = lm_eptr[l1]; e2 < e; ++e2)
-                        if (e_pose_j[e2] == pj) { bad = true; break; }
-                    if (bad) break;
+                    if (pj == host || seen_stamp[pj] == l1 + 1) { bad = true; break; }  // observer == host, or seen twice
+                    seen_stamp[pj] = l1 + 1;
                     if (slot_of_pose[pj] < 0) { slot_of_pose[pj] = (int)slots.size(); slots.push_back(pj); ++added; }
                 }
                 if (bad) { K.grouped_ok = false; break; }
