@@ -341,4 +341,17 @@ int emul_bchol_solve(int nb, const int *rowptr_, const int *col_, const double *
     }
     return VIO_OK;
 }
+
+// packer facts for host-side tests: were all landmarks grouped for the shared-memory linearise kernel, how many groups
+int emul_pack_info(const vio_graph *g, int *grouped_ok, int *n_groups, int *group_threads, long long *smem_max) {
+    PackedGraph K;
+    std::string err;
+    int rc = pack_graph(g, 0, 1, K, err);
+    if (rc) { fprintf(stderr, "emul: %s\n", err.c_str()); return rc; }
+    if (grouped_ok) *grouped_ok = K.grouped_ok ? 1 : 0;
+    if (n_groups) *n_groups = K.n_groups;
+    if (group_threads) *group_threads = K.group_threads;
+    if (smem_max) *smem_max = (long long)K.group_smem_max;
+    return VIO_OK;
+}
 }

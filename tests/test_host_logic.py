@@ -179,3 +179,26 @@ def test_packer_rejects_what_the_device_path_does_not_cover():
     s = vio.scenes.to_xyz(vio.scenes.monoba(4, 30))
     s.rx_point[2] = 10 ** 6
     assert rc_of(s) == INVALID
+
+
+def test_reference_scenes_are_grouped_for_the_shared_memory_kernel():
+    """The production linearise kernel needs every landmark in a group (same host, <= 22 pose slots, shared-memory
+    budget); the packer must manage that for the reference-shaped scenes, otherwise the slow generic kernel would run."""
+    vio = importlib.import_module("visual-inertial-odometry_b200")
+
+    def info(scene):
+        g, keep = scene.to_c()
+        ok, ng, nt, sm = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        assert emul.lib().emul_pack_info(C.byref(g), C.byref(ok), C.byref(ng), C.byref(nt), C.byref(sm)) == 0
+        return ok.value, ng.value, nt.value, sm.value
+
+    for s, min_groups in ((vio.scenes.monoba(20, 300), 3), (vio.scenes.monoba(20, 300, with_ext=True), 3), (_window(vio), 8),
+                          (vio.scenes.ring(n_cam=200, n_landmark=4000, k_obs=11, seed=1), 40)):
+        ok, ng, nt, sm = info(s)
+        assert ok == 1 and ng >= min_groups, (ok, ng)
+        assert 128 <= nt <= 320 and sm <= 200 * 1024
+    # a landmark observed twice by the same pose cannot be grouped: falls back to the generic kernel, still packs
+    s = vio.scenes.monoba(6, 40)
+    k = int(np.nonzero(s.rp_landmark == 3)[0][1])
+    s.rp_pose_j[k] = s.rp_pose_j[int(np.nonzero(s.rp_landmark == 3)[0][0])]
+    assert info(s)[0] == 0

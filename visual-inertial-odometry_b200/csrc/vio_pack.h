@@ -296,7 +296,8 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         int l0 = 0;
         std::vector<int> slots;  // slot -> pose (slot 0 = host)
         std::vector<int> slot_of_pose(C, -1);
-        std::vector<int> seen_stamp(C, 0);  // landmark (index + 1) that last listed this pose as an observer
+        std::vector<int> seen_stamp(C, 0);  // evaluation (a landmark may be tried twice: last of a run, first of the next) that last listed this pose
+        int stamp = 0;
         while (l0 < L && K.grouped_ok) {
             if (lm_eptr[l0] == lm_eptr[l0 + 1]) break;  // only edge-less landmarks remain
             const int host = lm_host[l0];
@@ -305,12 +306,13 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
             int l1 = l0;
             while (l1 < L && lm_eptr[l1] != lm_eptr[l1 + 1] && lm_host[l1] == host && (l1 - l0) < 128) {
                 // would this landmark fit?
+                ++stamp;
                 int added = 0;
                 bool bad = false;
                 for (int e = lm_eptr[l1]; e < lm_eptr[l1 + 1]; ++e) {
                     const int pj = e_pose_j[e];
-                    if (pj == host || seen_stamp[pj] == l1 + 1) { bad = true; break; }  // observer == host, or seen twice
-                    seen_stamp[pj] = l1 + 1;
+                    if (pj == host || seen_stamp[pj] == stamp) { bad = true; break; }  // observer == host, or seen twice
+                    seen_stamp[pj] = stamp;
                     if (slot_of_pose[pj] < 0) { slot_of_pose[pj] = (int)slots.size(); slots.push_back(pj); ++added; }
                 }
                 if (bad) { K.grouped_ok = false; break; }
