@@ -1160,3 +1160,195 @@ int orc_preintegrate(int32_t n, const double *dt, const double *acc, const doubl
     memcpy(cov225, P, sizeof(P));
     return VIO_OK;
 }
+
+/* ================================================================================================
+ * Problem::Marginalize(margVertexs = {pose[marg_pose], speedbias[marg_sb]}, pose_dim)
+ * A17/src/backend/problem.cc:617-795.  Eigen's SelfAdjointEigenSolver is restated as a cyclic Jacobi eigen-solver
+ * (ascending eigenvalues, eigenvector signs arbitrary - as with Eigen); see DESIGN 6 for what is and is not
+ * reproducible across backward-stable eigen-solvers.
+ * ================================================================================================ */
+static void jacobi_eigh(int n, double *A /* in: symmetric, destroyed */, double *w /* n ascending */, double *V /* n x n, columns */) {
+    for (int i = 0; i < n * n; ++i) V[i] = 0.0;
+    for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int p = 0; p < n; ++p) { diag += A[p * n + p] * A[p * n + p]; for (int q = p + 1; q < n; ++q) off += A[p * n + q] * A[p * n + q]; }
+        if (off <= 1e-32 * (diag + off)) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[p * n + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) {
+                    const double akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - s * akq; A[k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - s * aqk; A[q * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = c * vkp - s * vkq; V[k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
+    for (int i = 0; i < n - 1; ++i) {  /* selection sort, ascending, columns of V follow */
+        int m = i;
+        for (int j = i + 1; j < n; ++j) if (w[j] < w[m]) m = j;
+        if (m != i) {
+            double t = w[i]; w[i] = w[m]; w[m] = t;
+            for (int k = 0; k < n; ++k) { t = V[k * n + i]; V[k * n + i] = V[k * n + m]; V[k * n + m] = t; }
+        }
+    }
+}
+
+int orc_marginalize(const vio_graph *g, const orc_prior *prior, int32_t marg_pose, int32_t marg_sb, int32_t *dim_out,
+                    double *H_out, double *b_out, double *err_out, double *jt_inv_out) {
+    ordering o;
+    int rc = make_ordering(g, &o);
+    if (rc) return rc;
+    const int P = o.P; /* pose_dim */
+    if (marg_pose < 0 || marg_pose >= g->n_pose || marg_sb < 0 || marg_sb >= g->n_speedbias || g->n_point > 0) { free_ordering(&o); return VIO_ERR_INVALID; }
+    double qic[4], tic[3];
+    get_ext(g, qic, tic);
+    /* landmarks of the frame's edges get ordering ids pose_dim, pose_dim+1, ... (:626-639; here in landmark-index order) */
+    int *lm_slot = (int *)malloc(sizeof(int) * (g->n_landmark > 0 ? g->n_landmark : 1));
+    for (int l = 0; l < g->n_landmark; ++l) lm_slot[l] = -1;
+    int nl = 0;
+    for (int64_t e = 0; e < g->n_reproj; ++e)
+        if (g->rp_pose_i[e] == marg_pose || g->rp_pose_j[e] == marg_pose) lm_slot[g->rp_landmark[e]] = 0;
+    for (int l = 0; l < g->n_landmark; ++l) if (lm_slot[l] == 0) lm_slot[l] = nl++;
+    const int cols = P + nl;
+    double *H = (double *)calloc((size_t)cols * cols, sizeof(double)), *b = (double *)calloc(cols, sizeof(double));
+    /* H_marg, b_marg over the frame's edges: NO fixed-vertex test here, the extrinsic vertex contributes too (:645-680) */
+    for (int64_t e = 0; e < g->n_reproj; ++e) {
+        const int l = g->rp_landmark[e], i = g->rp_pose_i[e], j = g->rp_pose_j[e];
+        if (i != marg_pose && j != marg_pose) continue;
+        double r[2], Jl[2], Ji[12], Jj[12], Jex[12], W[4], Om[4] = {g->rp_info, 0, 0, g->rp_info}, drho = 1.0, rho0;
+        orc_reproj(g->inv_depth[l], g->pose + 7 * (size_t)i, g->pose + 7 * (size_t)j, qic, tic, g->rp_pts_i + 3 * e, g->rp_pts_j + 2 * e, r, Jl, Ji, Jj);
+        robust_info2(g->rp_loss, g->rp_loss_delta, g->rp_info, r, &drho, W, &rho0);
+        const double *Jv[4] = {Jl, Ji, Jj, Jex};
+        int ldj[4] = {1, 6, 6, 6}, dim[4] = {1, 6, 6, 6}, off[4] = {P + lm_slot[l], o.pose_off[i], o.pose_off[j], -1};
+        int nv = 3;
+        if (g->ext_pose >= 0) {
+            orc_reproj_jext(g->inv_depth[l], g->pose + 7 * (size_t)i, g->pose + 7 * (size_t)j, qic, tic, g->rp_pts_i + 3 * e, Jex);
+            off[3] = o.pose_off[g->ext_pose];
+            nv = 4;
+        }
+        add_edge_dense(H, b, cols, 2, nv, Jv, ldj, dim, off, W, Om, drho, r);
+    }
+    for (int k = 0; k < g->n_imu; ++k) {
+        const int pi = g->imu_pose_i[k], si = g->imu_sb_i[k], pj = g->imu_pose_j[k], sj = g->imu_sb_j[k];
+        if (pi != marg_pose && pj != marg_pose) continue;
+        double r[15], J[450], info[225];
+        orc_imu(g->pose + 7 * (size_t)pi, g->speedbias + 9 * (size_t)si, g->pose + 7 * (size_t)pj, g->speedbias + 9 * (size_t)sj,
+                g->imu_sum_dt[k], g->imu_delta_p + 3 * k, g->imu_delta_q + 4 * k, g->imu_delta_v + 3 * k, g->imu_lin_ba + 3 * k,
+                g->imu_lin_bg + 3 * k, g->imu_jacobian + 225 * k, g->gravity, r, J);
+        mat_inverse(15, g->imu_covariance + 225 * k, info);
+        const double *Jv[4] = {J, J + 6, J + 15, J + 21};
+        int ldj[4] = {30, 30, 30, 30}, dim[4] = {6, 9, 6, 9}, off[4] = {o.pose_off[pi], o.sb_off[si], o.pose_off[pj], o.sb_off[sj]};
+        add_edge_dense(H, b, cols, 15, 4, Jv, ldj, dim, off, info, info, 1.0, r);
+    }
+    for (int k = 0; k < g->n_se3prior; ++k) {
+        const int i = g->sp_pose[k];
+        if (i != marg_pose) continue;
+        double r[6], J[36];
+        orc_se3prior(g->pose + 7 * (size_t)i, g->sp_p + 3 * k, g->sp_q + 4 * k, r, J);
+        const double *Jv[1] = {J};
+        int ldj[1] = {6}, dim[1] = {6}, off[1] = {o.pose_off[i]};
+        add_edge_dense(H, b, cols, 6, 1, Jv, ldj, dim, off, g->sp_info + 36 * k, g->sp_info + 36 * k, 1.0, r);
+    }
+    /* marg landmarks (:686-708) */
+    double *Hm = (double *)calloc((size_t)P * P, sizeof(double)), *bm = (double *)calloc(P, sizeof(double));
+    for (int r = 0; r < P; ++r) {
+        for (int c = 0; c < P; ++c) {
+            double t = 0.0;
+            for (int l = 0; l < nl; ++l) t += (H[(size_t)r * cols + P + l] / H[(size_t)(P + l) * cols + P + l]) * H[(size_t)(P + l) * cols + c];
+            Hm[(size_t)r * P + c] = H[(size_t)r * cols + c] - t;
+        }
+        double t = 0.0;
+        for (int l = 0; l < nl; ++l) t += (H[(size_t)r * cols + P + l] / H[(size_t)(P + l) * cols + P + l]) * b[P + l];
+        bm[r] = b[r] - t;
+    }
+    /* + prior (:710-715) */
+    if (prior && prior->dim > 0) {
+        if (prior->dim != P) { free(H); free(b); free(Hm); free(bm); free(lm_slot); free_ordering(&o); return VIO_ERR_INVALID; }
+        for (int i = 0; i < P * P; ++i) Hm[i] += prior->H[i];
+        for (int i = 0; i < P; ++i) bm[i] += prior->b[i];
+    }
+    /* move the marginalised blocks to the bottom right, larger index first (:720-745): a stable permutation */
+    int *perm = (int *)malloc(sizeof(int) * P), n_keep = 0;
+    const int off_p = o.pose_off[marg_pose], off_s = o.sb_off[marg_sb];
+    int first_off = off_p < off_s ? off_p : off_s, first_dim = off_p < off_s ? 6 : 9;
+    int second_off = off_p < off_s ? off_s : off_p, second_dim = off_p < off_s ? 9 : 6;
+    /* the loop moves margVertexs[1] (speed-bias) first, then margVertexs[0] (pose): final tail order = [speed-bias | pose] */
+    for (int r = 0; r < P; ++r) {
+        const int in_first = r >= first_off && r < first_off + first_dim, in_second = r >= second_off && r < second_off + second_dim;
+        if (!in_first && !in_second) perm[n_keep++] = r;
+    }
+    const int m2 = 15, n2 = P - m2;
+    for (int d = 0; d < 9; ++d) perm[n2 + d] = off_s + d;
+    for (int d = 0; d < 6; ++d) perm[n2 + 9 + d] = off_p + d;
+    double *Hp = (double *)malloc(sizeof(double) * (size_t)P * P), *bp = (double *)malloc(sizeof(double) * P);
+    for (int r = 0; r < P; ++r) { bp[r] = bm[perm[r]]; for (int c = 0; c < P; ++c) Hp[(size_t)r * P + c] = Hm[(size_t)perm[r] * P + perm[c]]; }
+    /* Amm pseudo-inverse and Schur (:747-766) */
+    const double eps = 1e-8;
+    double Amm[225], wv[15], Vv[225], Ainv[225];
+    for (int r = 0; r < m2; ++r)
+        for (int c = 0; c < m2; ++c) Amm[r * m2 + c] = 0.5 * (Hp[(size_t)(n2 + r) * P + n2 + c] + Hp[(size_t)(n2 + c) * P + n2 + r]);
+    jacobi_eigh(m2, Amm, wv, Vv);
+    for (int r = 0; r < m2; ++r)
+        for (int c = 0; c < m2; ++c) {
+            double t = 0.0;
+            for (int k = 0; k < m2; ++k) t += Vv[r * m2 + k] * (wv[k] > eps ? 1.0 / wv[k] : 0.0) * Vv[c * m2 + k];
+            Ainv[r * m2 + c] = t;
+        }
+    double *Hpr = (double *)malloc(sizeof(double) * (size_t)n2 * n2), *bpr = (double *)malloc(sizeof(double) * n2);
+    double *tB = (double *)malloc(sizeof(double) * (size_t)n2 * m2);
+    for (int r = 0; r < n2; ++r)
+        for (int c = 0; c < m2; ++c) {
+            double t = 0.0;
+            for (int k = 0; k < m2; ++k) t += Hp[(size_t)r * P + n2 + k] * Ainv[k * m2 + c];
+            tB[(size_t)r * m2 + c] = t;
+        }
+    for (int r = 0; r < n2; ++r) {
+        for (int c = 0; c < n2; ++c) {
+            double t = 0.0;
+            for (int k = 0; k < m2; ++k) t += tB[(size_t)r * m2 + k] * Hp[(size_t)(n2 + k) * P + c];
+            Hpr[(size_t)r * n2 + c] = Hp[(size_t)r * P + c] - t;
+        }
+        double t = 0.0;
+        for (int k = 0; k < m2; ++k) t += tB[(size_t)r * m2 + k] * bp[n2 + k];
+        bpr[r] = bp[r] - t;
+    }
+    /* eigen-decomposition of H_prior: Jt_prior_inv, err_prior, H_prior = J^T J, |.| < 1e-9 -> 0 (:768-782) */
+    double *Acopy = (double *)malloc(sizeof(double) * (size_t)n2 * n2), *w2 = (double *)malloc(sizeof(double) * n2);
+    double *V2 = (double *)malloc(sizeof(double) * (size_t)n2 * n2);
+    memcpy(Acopy, Hpr, sizeof(double) * (size_t)n2 * n2);
+    jacobi_eigh(n2, Acopy, w2, V2);
+    for (int r = 0; r < n2; ++r) {
+        const double sis = w2[r] > eps ? sqrt(1.0 / w2[r]) : 0.0;
+        for (int c = 0; c < n2; ++c) jt_inv_out[(size_t)r * n2 + c] = sis * V2[(size_t)c * n2 + r];
+    }
+    for (int r = 0; r < n2; ++r) {
+        double t = 0.0;
+        for (int c = 0; c < n2; ++c) t += jt_inv_out[(size_t)r * n2 + c] * bpr[c];
+        err_out[r] = -t;
+    }
+    for (int r = 0; r < n2; ++r)
+        for (int c = 0; c < n2; ++c) {
+            double t = 0.0;
+            for (int k = 0; k < n2; ++k) t += V2[(size_t)r * n2 + k] * (w2[k] > eps ? w2[k] : 0.0) * V2[(size_t)c * n2 + k];
+            H_out[(size_t)r * n2 + c] = fabs(t) > 1e-9 ? t : 0.0;
+        }
+    memcpy(b_out, bpr, sizeof(double) * n2);
+    *dim_out = n2;
+    free(H); free(b); free(Hm); free(bm); free(lm_slot); free(perm); free(Hp); free(bp); free(Hpr); free(bpr); free(tB);
+    free(Acopy); free(w2); free(V2);
+    free_ordering(&o);
+    return VIO_OK;
+}

@@ -89,6 +89,11 @@ int orc_preintegrate(int32_t n, const double *dt, const double *acc, const doubl
                      const double *noise, double *sum_dt, double *delta_p, double *delta_q_xyzw, double *delta_v,
                      double *jac225, double *cov225);
 
+/* --- Problem::Marginalize({pose[marg_pose], speedbias[marg_sb]}, pose_dim = P) - A17/src/backend/problem.cc:617-795.
+ * Outputs sized for P-15: H (dim x dim), b, err (dim), Jt_prior_inv (dim x dim). ----------------------------------- */
+int orc_marginalize(const vio_graph *g, const orc_prior *prior, int32_t marg_pose, int32_t marg_sb, int32_t *dim_out,
+                    double *H_out, double *b_out, double *err_out, double *jt_inv_out);
+
 #ifdef __cplusplus
 }
 #endif

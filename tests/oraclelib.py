@@ -154,3 +154,19 @@ def preintegrate(dt, acc, gyr, ba, bg, noise):
                             _d(jac), _d(cov))
     assert rc == 0, rc
     return sd.value, dp, dq, dv, jac, cov
+
+
+def marginalize(scene, marg_pose, marg_sb):
+    """orc_marginalize -> dict(dim, H, b, err, jt_inv) like Problem.marginalize"""
+    g, keep = scene.to_c()
+    pr, k2 = _prior(scene)
+    n = scene.P
+    H, b, err, Jt = np.zeros((n, n)), np.zeros(n), np.zeros(n), np.zeros((n, n))
+    dim = C.c_int32()
+    L = lib()
+    L.orc_marginalize.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _dp, _dp, _dp, _dp]
+    rc = L.orc_marginalize(C.byref(g), C.byref(pr), marg_pose, marg_sb, C.byref(dim), _d(H), _d(b), _d(err), _d(Jt))
+    assert rc == 0, rc
+    k = dim.value
+    return dict(dim=k, H=H.ravel()[:k * k].reshape(k, k).copy(), b=b[:k].copy(), err=err[:k].copy(),
+                jt_inv=Jt.ravel()[:k * k].reshape(k, k).copy())

@@ -483,6 +483,10 @@ def test_marginalize_vs_golden(vio, scene_file, marg_file):
     assert np.abs(JHJ - np.eye(well.sum())).max() <= 1e-6
     # chi2 only sees |err_prior| (A17/src/backend/problem.cc:505-506); the noise rows move it by < 1 %
     assert abs(np.linalg.norm(m["err"]) - np.linalg.norm(g["err"])) <= 1e-2 * np.linalg.norm(g["err"])
+    # and against the C oracle's restatement (orc_marginalize), same conditioning-limited tolerances
+    from tests import oraclelib as orc
+    mo = orc.marginalize(s, 1, 0)
+    assert mo["dim"] == m["dim"] and rel_max(m["H"], mo["H"]) <= 2e-5 and rel_l2(m["b"], mo["b"]) <= 2e-4
 
 
 def test_preintegration_vs_golden(vio):

@@ -261,3 +261,23 @@ def test_oracle_free_extrinsic_vs_golden(vio):
     assert r["iterations"] == int(gs["iterations"])
     assert np.allclose(r["chi2_trace"], gs["chi2_trace"], rtol=1e-7, atol=0)
     assert rel_max(r["pose"], gs["pose"]) <= 1e-7
+
+
+@pytest.mark.parametrize("scene_file,marg_file", [("windowA_v17_scene.npz", "windowA_v17_marg.npz"),
+                                                   ("window_v17_scene.npz", "windowB_v17_marg.npz")])
+def test_oracle_marginalize_vs_golden(vio, scene_file, marg_file):
+    """Problem::Marginalize restated in C (orc_marginalize, Jacobi eigen-solver in place of Eigen's) against the unmodified
+    backend, with the tolerances the algorithm's own conditioning allows: H_prior / b_prior to kappa * eps,
+    Jt_prior_inv / err_prior only on the well-conditioned rows and up to the eigenvector sign."""
+    s = vio.Scene.from_dict(dict(np.load(os.path.join(GOLD, scene_file))))
+    g = np.load(os.path.join(GOLD, marg_file))
+    m = orc.marginalize(s, 1, 0)
+    assert m["dim"] == 156
+    assert rel_max(m["H"], g["H"]) <= 2e-5 and rel_l2(m["b"], g["b"]) <= 2e-4
+    rn, rnr = np.linalg.norm(m["jt_inv"], axis=1), np.linalg.norm(g["jt_inv"], axis=1)
+    k = int(((rnr > 0) & (rnr < 0.1)).sum())
+    well = np.zeros(156, bool)
+    well[156 - k:] = True
+    assert k >= 10 and np.allclose(rn[well], rnr[well], rtol=1e-3)
+    assert np.allclose(np.abs(m["err"][well]), np.abs(g["err"][well]), rtol=1e-2, atol=1e-3 * np.abs(g["err"][well]).max())
+    assert abs(np.linalg.norm(m["err"]) - np.linalg.norm(g["err"])) <= 1e-2 * np.linalg.norm(g["err"])
