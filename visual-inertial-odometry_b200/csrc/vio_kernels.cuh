@@ -18,8 +18,20 @@
 // ------------------------------------------------------------------------------------------------
 // FP64 accumulate into global memory: RED.E.ADD.F64 on the device.  The host branch exists only so
 // tests/host_emul.cu can run the same per-landmark bodies on the CPU as a debugging/unit-test aid.
+// Warp aggregation: in the per-landmark kernels consecutive landmarks usually share their host and observers, so all 32
+// lanes of a warp tend to add to the SAME element; when they do, one shuffle reduction + one RED replaces 32 REDs.
 VIO_HD void vio_add(double *p, double x) {
 #ifdef __CUDA_ARCH__
+    const unsigned active = __activemask();
+    if (active == 0xffffffffu) {
+        const unsigned long long a0 = __shfl_sync(0xffffffffu, (unsigned long long)p, 0);
+        if (__all_sync(0xffffffffu, a0 == (unsigned long long)p)) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(p, x);
+            return;
+        }
+    }
     atomicAdd(p, x);
 #else
     *p += x;
