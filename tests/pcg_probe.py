@@ -33,7 +33,7 @@ cands = [(g, na // g) for g in range(1, 149) if na % g == 0]
 agg = None
 for g, apc in cands:
     brc = (nb + g - 1) // g
-    if (brc + apc - 1) // apc == ma and g == min(g, (nb + 15) // 16):
+    if (brc + apc - 1) // apc == ma and g == min(g, (nb + 7) // 8):
         agg = np.array([(i // brc) * apc + min(apc - 1, (i % brc) // ma) for i in range(nb)])
 print("layout grid", g, "apc", apc)
 rows, cols, vals = [], [], []

@@ -444,7 +444,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         bool done_persistent = false;
         if (p->coop_ok && !p->env_multikernel) {
             // one cooperative launch: grid sized to be co-resident (2 CTAs per SM at most)
-            int grid = std::max(1, std::min(std::min(p->num_sms, BPCG_MAXPART), (nb + 15) / 16));
+            int grid = std::max(1, std::min(std::min(p->num_sms, BPCG_MAXPART), (nb + 7) / 8));
             // two-level preconditioner: apc aggregates per CTA of >= 16 block rows; the coarse inversion keeps 7*apc rows of
             // the (7*grid*apc)^2 coarse matrix per CTA in shared memory, which caps grid * apc^2 (a slightly smaller grid
             // is accepted for that)
