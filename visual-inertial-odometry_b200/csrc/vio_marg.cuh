@@ -35,7 +35,7 @@ __global__ void k_marg_reproj(DevView v, MargEdgeView m, double *H, double *b, i
     const double lam = v.invdep[l];
     const double pts_i[3] = {v.lm_pix[l], v.lm_piy[l], v.lm_piz[l]};
     const double pci[3] = {pts_i[0] / lam, pts_i[1] / lam, pts_i[2] / lam};
-    double pbi[3], pw[3], tmp[3];
+    double pbi[3], pw[3];
     mat3_mul_vec(v.Ric, pci, pbi);
     for (int k = 0; k < 3; ++k) pbi[k] += v.tic[k];
     mat3_mul_vec(RTh, pbi, pw);
