@@ -58,36 +58,7 @@ __host__ __device__ inline size_t group_smem_bytes(int ns, int nlm) {
     return group_smem_doubles(ns, nlm) * sizeof(double) + (3 * (size_t)ns + 2 * (size_t)npairs) * sizeof(int);
 }
 
-template <int N>
-__device__ __forceinline__ void rs_step(double *v, bool up, int mask) {
-    constexpr int H = N / 2;
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        const double send = up ? v[i] : v[i + H];
-        const double keep = up ? v[i + H] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-    }
-}
-// warp sum of a 48-vector, scattered: afterwards lane holds element `base` in v[0] and (if !(lane&1)) base+1 in v[1]
-__device__ __forceinline__ int reduce_scatter48(double *v, int lane) {
-    int base = 0;
-    rs_step<48>(v, lane & 16, 16); base += (lane & 16) ? 24 : 0;
-    rs_step<24>(v, lane & 8, 8);   base += (lane & 8) ? 12 : 0;
-    rs_step<12>(v, lane & 4, 4);   base += (lane & 4) ? 6 : 0;
-    rs_step<6>(v, lane & 2, 2);    base += (lane & 2) ? 3 : 0;
-    v[3] = 0.0;
-    rs_step<4>(v, lane & 1, 1);    base += (lane & 1) ? 2 : 0;
-    return base;
-}
-__device__ __forceinline__ int reduce_scatter32(double *v, int lane) {
-    int base = 0;
-    rs_step<32>(v, lane & 16, 16); base += (lane & 16) ? 16 : 0;
-    rs_step<16>(v, lane & 8, 8);   base += (lane & 8) ? 8 : 0;
-    rs_step<8>(v, lane & 4, 4);    base += (lane & 4) ? 4 : 0;
-    rs_step<4>(v, lane & 2, 2);    base += (lane & 2) ? 2 : 0;
-    rs_step<2>(v, lane & 1, 1);    base += (lane & 1) ? 1 : 0;
-    return base;  // v[0] holds element `base`
-}
+// rs_step / reduce_scatter48 / reduce_scatter32 (warp reduce-scatter by recursive halving) live in vio_kernels.cuh
 
 __device__ __forceinline__ int sym6_index(int r, int c) {  // upper triangle, row-major
     if (r > c) { const int t = r; r = c; c = t; }

@@ -48,6 +48,39 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// ---- warp reduce-scatter by recursive halving (47 shuffles for a 48-vector instead of 240 for 48 butterflies) ----
+template <int N>
+__device__ __forceinline__ void rs_step(double *v, bool up, int mask) {
+    constexpr int H = N / 2;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const double send = up ? v[i] : v[i + H];
+        const double keep = up ? v[i + H] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+}
+// warp sum of a 48-vector, scattered: afterwards lane holds element `base` in v[0] and (if !(lane&1)) base+1 in v[1]
+__device__ __forceinline__ int reduce_scatter48(double *v, int lane) {
+    int base = 0;
+    rs_step<48>(v, lane & 16, 16); base += (lane & 16) ? 24 : 0;
+    rs_step<24>(v, lane & 8, 8);   base += (lane & 8) ? 12 : 0;
+    rs_step<12>(v, lane & 4, 4);   base += (lane & 4) ? 6 : 0;
+    rs_step<6>(v, lane & 2, 2);    base += (lane & 2) ? 3 : 0;
+    v[3] = 0.0;
+    rs_step<4>(v, lane & 1, 1);    base += (lane & 1) ? 2 : 0;
+    return base;
+}
+__device__ __forceinline__ int reduce_scatter32(double *v, int lane) {
+    int base = 0;
+    rs_step<32>(v, lane & 16, 16); base += (lane & 16) ? 16 : 0;
+    rs_step<16>(v, lane & 8, 8);   base += (lane & 8) ? 8 : 0;
+    rs_step<8>(v, lane & 4, 4);    base += (lane & 4) ? 4 : 0;
+    rs_step<4>(v, lane & 2, 2);    base += (lane & 2) ? 2 : 0;
+    rs_step<2>(v, lane & 1, 1);    base += (lane & 1) ? 1 : 0;
+    return base;  // v[0] holds element `base`
+}
+
+
 // block-level deterministic sum -> partial[blockIdx.x]   (blockDim.x multiple of 32, <= 1024)
 __device__ __forceinline__ void block_sum_to(double v, double *partial) {
     __shared__ double sm[32];
@@ -133,41 +166,84 @@ VIO_HD double *s_block(const DevView &v, int a, int b, int &ld) {
     return v.S + 36 * (size_t)lo;
 }
 
+#ifdef __CUDA_ARCH__
+// Warp-uniform 6x6 block add: when all 32 lanes add a block to the SAME place (consecutive landmarks of the per-landmark
+// kernels share their observers), the 36 values are summed over the warp by one reduce-scatter (47 shuffles) and every
+// lane issues at most two REDs, instead of 36 shuffle-reduced adds (180 shuffles) or 36 x 32 plain REDs.
+// Y[e] is the value for element e = 6 r + c of the block at p (leading dimension ld); upper_only skips r > c.
+__device__ __forceinline__ bool warp_block_add(double *p, int ld, const double Y[36], bool upper_only) {
+    if (__activemask() != 0xffffffffu) return false;
+    const unsigned long long p0 = __shfl_sync(0xffffffffu, (unsigned long long)p, 0);
+    const int u0 = __shfl_sync(0xffffffffu, (int)upper_only, 0);
+    if (!__all_sync(0xffffffffu, p0 == (unsigned long long)p && u0 == (int)upper_only)) return false;
+    double v[48];
+#pragma unroll
+    for (int e = 0; e < 36; ++e) v[e] = Y[e];
+#pragma unroll
+    for (int e = 36; e < 48; ++e) v[e] = 0.0;
+    const int lane = threadIdx.x & 31;
+    const int base = reduce_scatter48(v, lane);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int e = base + q;
+        if (q == 1 && (lane & 1)) break;
+        if (e < 36) {
+            const int r = e / 6, c = e % 6;
+            if (!upper_only || c >= r) atomicAdd(p + (size_t)r * ld + c, v[q]);
+        }
+    }
+    return true;
+}
+#endif
+
 // S(block a,b) += sgn * X (6x6, row-major X) where X is the (a,b) block; handles orientation so that
 // only the upper block-triangle (and upper element-triangle of diagonal blocks) is touched.
 VIO_HD void s_add_block(const DevView &v, int a, int b, const double X[36], double sgn) {
     int ld;
+    double Y[36];
+    double *p;
+    bool upper = false;
     if (a == b) {
         // X + X^T contribution when both ends of an edge hit the same vertex
-        double *p = s_block(v, a, a, ld);
+        p = s_block(v, a, a, ld);
+        upper = true;
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
-            for (int c = r; c < 6; ++c) vio_add(p + (size_t)r * ld + c, sgn * (X[6 * r + c] + X[6 * c + r]));
-        return;
-    }
-    if (v.pose_off[a] < v.pose_off[b]) {
-        double *p = s_block(v, a, b, ld);
+            for (int c = 0; c < 6; ++c) Y[6 * r + c] = sgn * (X[6 * r + c] + X[6 * c + r]);
+    } else if (v.pose_off[a] < v.pose_off[b]) {
+        p = s_block(v, a, b, ld);
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) vio_add(p + (size_t)r * ld + c, sgn * X[6 * r + c]);
+        for (int e = 0; e < 36; ++e) Y[e] = sgn * X[e];
     } else {
-        double *p = s_block(v, b, a, ld);
+        p = s_block(v, b, a, ld);
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
-            for (int c = 0; c < 6; ++c) vio_add(p + (size_t)r * ld + c, sgn * X[6 * c + r]);
+            for (int c = 0; c < 6; ++c) Y[6 * r + c] = sgn * X[6 * c + r];
     }
+#ifdef __CUDA_ARCH__
+    if (warp_block_add(p, ld, Y, upper)) return;
+#endif
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = upper ? r : 0; c < 6; ++c) vio_add(p + (size_t)r * ld + c, Y[6 * r + c]);
 }
 // diagonal block (a,a) += sgn * X, X symmetric: only the upper element-triangle is stored
 VIO_HD void s_add_diag(const DevView &v, int a, const double X[36], double sgn) {
     int ld;
     double *p = s_block(v, a, a, ld);
+    double Y[36];
+#pragma unroll
+    for (int e = 0; e < 36; ++e) Y[e] = sgn * X[e];
+#ifdef __CUDA_ARCH__
+    if (warp_block_add(p, ld, Y, true)) return;
+#endif
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
-        for (int c = r; c < 6; ++c) vio_add(p + (size_t)r * ld + c, sgn * X[6 * r + c]);
+        for (int c = r; c < 6; ++c) vio_add(p + (size_t)r * ld + c, Y[6 * r + c]);
 }
 
 // ------------------------------------------------------------------------------------------------
