@@ -136,7 +136,7 @@ struct vio_problem {
     DBuf<long long> bc_a_to_l, bc_upd_ptr, bc_upd_dst;
     DBuf<double> bc_L;
     bool cz_have_inverse = false, cz_refreshed = false, cz_reuse_policy = false;
-    double cz_last_iters = 0, cz_ref_iters = 0;
+    double cz_last_iters = 0, cz_ref_iters = 0, cz_reuse_factor = 1.5;
     int pcg_grid = -1, pcg_br = 0, pcg_win = 0;
     size_t pcg_smem = 0;
     DBuf<unsigned long long> prof;
@@ -556,7 +556,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             // the last solve needed more than 1.5x (+10) the iterations of the solve right after the previous refresh.
             bool reuse = false;
             if (solver == VIO_SOLVER_BLOCK_PCG_2L && p->cz_apc > 0 && ce == cudaSuccess && p->cz_have_inverse && p->cz_reuse_policy &&
-                p->cz_last_iters <= 1.5 * p->cz_ref_iters + 10) {
+                p->cz_last_iters <= p->cz_reuse_factor * p->cz_ref_iters + 10) {
                 reuse = true;
                 cv.apc = p->cz_apc; cv.ma = p->cz_ma; cv.nc = p->cz_nc; cv.Ainv = p->cz_A.p; cv.rc = p->cz_rc.p; cv.Z = p->cz_Z.p;
             }
@@ -880,6 +880,7 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     p->cz_have_inverse = false;
     p->bchol_ready = false;
     { const char *ev = getenv("VIO_B200_COARSE_REUSE"); p->cz_reuse_policy = !ev || atoi(ev) != 0; }  // default on
+    { const char *ev = getenv("VIO_B200_COARSE_REUSE_FACTOR"); if (ev && atof(ev) >= 1.0) p->cz_reuse_factor = atof(ev); }
     const int C = K.C, NSB = K.NSB, L = K.L, P = K.P, NB = K.NB;
     const long long E = K.E;
     p->C = C; p->NSB = NSB; p->L = L; p->P = P; p->NB = NB; p->E = E; p->storage = K.storage; p->nnzb = K.nnzb;
