@@ -766,16 +766,22 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
     // own aggregates' part of Z^T v (v = r at the start, S p inside the iteration) -> global exchange buffer
     auto restrict_publish = [&](const double *v_s) {
         const int nbl = i1 - i0;
-        if (tid < crow_n) {
-            const int al = tid / CZ_KD, m = tid % CZ_KD;
+        // 8 lanes per coarse row (block rows strided over them), combined by a fixed-order shuffle tree
+        if (tid < 8 * crow_n) {  // crow_n <= 28: at most 7 warps, every warp fully populated or tail-guarded below
+            const int cr = tid >> 3, g8 = tid & 7;
+            const int al = cr / CZ_KD, m = cr % CZ_KD;
             const int b0 = min(nbl, al * cv.ma), b1 = min(nbl, b0 + cv.ma);
             double t = 0.0;
-            for (int ib = b0; ib < b1; ++ib) {
+            for (int ib = b0 + g8; ib < b1; ib += 8) {
                 const double *zi = Z_s + 6 * CZ_KD * ib + m, *vb = v_s + 6 * ib;
                 t += zi[0] * vb[0] + zi[CZ_KD] * vb[1] + zi[2 * CZ_KD] * vb[2] + zi[3 * CZ_KD] * vb[3] + zi[4 * CZ_KD] * vb[4] +
                      zi[5 * CZ_KD] * vb[5];
             }
-            __stcg(cv.rc + (size_t)crow_n * blockIdx.x + tid, t);
+            const unsigned grp = 0xffu << ((tid & 31) & ~7);
+            t += __shfl_xor_sync(grp, t, 1);
+            t += __shfl_xor_sync(grp, t, 2);
+            t += __shfl_xor_sync(grp, t, 4);
+            if (g8 == 0) __stcg(cv.rc + (size_t)crow_n * blockIdx.x + cr, t);
         }
     };
     // z_s += Z (Ainv[own rows, :] rc_s): every thread takes whole columns (one Ainv element per own coarse row, all loads
@@ -801,10 +807,12 @@ __global__ void __launch_bounds__(BPCG_P_THREADS, 1) k_bpcg_persistent(BpcgView 
             }
         }
         __syncthreads();
-        if (tid < crow_n) {
-            double t = 0.0;
-            for (int w = 0; w < nwarp; ++w) t += zc_w[w][tid];
-            zc_f[tid] = t;
+        // combine the per-warp partials: warp cr sums the nwarp (<= 32) partials of coarse row cr in a fixed shuffle order
+        if (warp < crow_n) {
+            double t = lane < nwarp ? zc_w[lane][warp] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) zc_f[warp] = t;
         }
         __syncthreads();
         for (int t = tid; t < nrow; t += nt) {
