@@ -170,3 +170,33 @@ def marginalize(scene, marg_pose, marg_sb):
     k = dim.value
     return dict(dim=k, H=H.ravel()[:k * k].reshape(k, k).copy(), b=b[:k].copy(), err=err[:k].copy(),
                 jt_inv=Jt.ravel()[:k * k].reshape(k, k).copy())
+
+
+def nullspace_hessian(scene):
+    """numpy restatement of hessian_nullspace_test.cpp:95-140 (14-sliding-window/src): H = J^T J over pose(6) + XYZ(3)
+    reprojection blocks of the `scenes.nullspace()` graph, in the reference's own parameterisation
+    (jacobian_Ci = [J_uv Rcw | J_uv hat(Pc)], jacobian_Pj = J_uv Rcw, fx = fy = 1)."""
+    qR = importlib.import_module("visual-inertial-odometry_b200").scenes._quat_R
+    N, M = scene.pose.shape[0], scene.point_xyz.shape[0]
+    H = np.zeros((6 * N + 3 * M, 6 * N + 3 * M))
+    for m in range(M):
+        Pw = scene.point_xyz[m]
+        for n in range(N):
+            Rcw = qR(scene.pose[n, 3:7]).T
+            x, y, z = Rcw @ (Pw - scene.pose[n, :3])
+            Juv = np.array([[1 / z, 0, -x / z ** 2], [0, 1 / z, -y / z ** 2]])
+            JP = Juv @ Rcw
+            JC = np.hstack([Juv @ Rcw, Juv @ np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]])])
+            a, b = slice(6 * n, 6 * n + 6), slice(6 * N + 3 * m, 6 * N + 3 * m + 3)
+            H[a, a] += JC.T @ JC
+            H[a, b] += JC.T @ JP
+            H[b, a] += JP.T @ JC
+            H[b, b] += JP.T @ JP
+    return H
+
+
+def nullspace_golden():
+    """The 120 singular values printed by the unmodified reference binary (6 digits), tests/golden/."""
+    path = os.path.join(ROOT, "tests", "golden", "hessian_nullspace_singular_values.txt")
+    with open(path) as f:
+        return np.array([float(ln.split(":")[1]) for ln in f if ":" in ln and ln.strip()[0].isdigit()])

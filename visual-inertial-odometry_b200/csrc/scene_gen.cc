@@ -234,4 +234,32 @@ int vio_scene_ring_fill(int n_cam, int n_landmark, int k_obs, int with_ext, uint
     }
     return 0;
 }
+// hessian_nullspace_test scene (/root/reference/workspace/assignments/14-sliding-window/src/hessian_nullspace_test.cpp:
+// 45-93): N = 10 cameras on the quarter arc, M = 20 world points drawn x, y ~ U(-4,4), z ~ U(8,10) from ONE
+// default-seeded std::default_random_engine in the order x, y, z per point; every camera sees every point.
+int vio_scene_nullspace_fill(int draw_order, double *pose /* 10 x 7 */, double *points /* 20 x 3 */) {
+    const int N = 10, M = 20;
+    const double radius = 8;
+    for (int n = 0; n < N; ++n) {
+        const double theta = n * 2 * M_PI / (N * 4);
+        double R[9], q[4];
+        rotz(theta, R);
+        mat_to_quat(R, q);
+        double *o = pose + 7 * n;
+        o[0] = radius * std::cos(theta) - radius; o[1] = radius * std::sin(theta); o[2] = 1 * std::sin(2 * theta);
+        o[3] = q[0]; o[4] = q[1]; o[5] = q[2]; o[6] = q[3];
+    }
+    std::default_random_engine generator;
+    std::uniform_real_distribution<double> xy_uniform(-4.0, 4.0), z_uniform(8.0, 10.0);
+    for (int m = 0; m < M; ++m) {
+        // The reference draws inside a constructor call, Eigen::Vector3d(xy(gen), xy(gen), z(gen)), whose argument
+        // evaluation order is unspecified: draw_order 0 = left to right (x, y, z), 1 = right to left (z, y, x; what g++
+        // does).  tests/test_oracle.py pins the order against the singular values the reference publishes.
+        double x, y, z;
+        if (draw_order == 0) { x = xy_uniform(generator); y = xy_uniform(generator); z = z_uniform(generator); }
+        else { z = z_uniform(generator); y = xy_uniform(generator); x = xy_uniform(generator); }
+        points[3 * m] = x; points[3 * m + 1] = y; points[3 * m + 2] = z;
+    }
+    return 0;
+}
 }

@@ -145,6 +145,7 @@ struct vio_problem {
     DBuf<double> partial, partial2, scal;
     double *h_scal = nullptr;  // pinned
     // timing
+    cudaEvent_t ev_solve0 = nullptr, ev_solve1 = nullptr;  // created once per handle (error paths of vio_solve cannot leak them)
     std::vector<EvPair> ev_lin, ev_pcg, ev_coarse;
     size_t ev_lin_used = 0, ev_pcg_used = 0, ev_coarse_used = 0;
     double last_pcg_ms = 0.0, last_coarse_ms = 0.0, last_pcg_iters = 0.0, pcg_iters_acc = 0.0;
@@ -181,6 +182,27 @@ inline int grid_for(long long n, int block, int cap = 1 << 30) {
     if (g > cap) g = cap;
     return (int)g;
 }
+
+// The dynamic shared-memory cap of a kernel is context-wide state: several handles (worker threads of vio_solve_batched, the
+// two slots of the lock-step pipeline) launch the same kernels with different sizes, so the cap is raised ONCE per
+// (device, kernel) to the device's opt-in maximum and never lowered.  Launches still request only what they need.
+cudaError_t raise_smem_cap(const void *func) {
+    static std::mutex mu;
+    static std::vector<std::pair<int, const void *>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto &d : done)
+        if (d.first == dev && d.second == func) return cudaSuccess;
+    int optin = 0;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) done.emplace_back(dev, func);
+    return e;
+}
+#define RAISE_SMEM(kernel) raise_smem_cap((const void *)(kernel))
 
 const int RED_BLOCKS = 592;  // 4 CTAs per SM x 148 SMs for the grid-stride reduction kernels
 
@@ -253,7 +275,7 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
     const DevView &v = p->view;
     const size_t sys_n = p->s_count + 3 * (size_t)p->P;
     CK(cudaMemsetAsync(p->sys.p, 0, sys_n * sizeof(double), p->stream));
-    do_pose_prep(p);
+    { const int rc_pp = do_pose_prep(p); if (rc_pp) return rc_pp; }
     EvPair *ev = nullptr;
     if (p->ev_lin_used < p->ev_lin.size()) ev = &p->ev_lin[p->ev_lin_used++];
     if (ev) CK(cudaEventRecord(ev->a, p->stream));
@@ -317,7 +339,7 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
 // chi2 at the current state -> host double (synchronises)
 int do_chi2(vio_problem *p, const vio_lm_opts &o, double *out) {
     const DevView &v = p->view;
-    do_pose_prep(p);
+    { const int rc_pp = do_pose_prep(p); if (rc_pp) return rc_pp; }
     double *acc = p->scal.p + 0;
     if (p->L > 0) {
         k_chi2_lm<<<RED_BLOCKS, 256, 0, p->stream>>>(v, p->partial.p);
@@ -399,7 +421,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         const size_t tri_bytes = ((size_t)P * (P + 1) / 2 + P) * sizeof(double);
         if (tri_bytes <= 220 * 1024) {
             if (!p->chol_smem_set) {
-                CK(cudaFuncSetAttribute(k_dense_chol_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                CK(RAISE_SMEM(k_dense_chol_smem));
                 p->chol_smem_set = true;
             }
             k_dense_chol_smem<<<1, 512, tri_bytes, p->stream>>>(v.S, v.bS, lambda, P, v.dxp, p->info.p);
@@ -412,7 +434,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         if (p->storage != VIO_STORAGE_DENSE) return fail(p, VIO_ERR_INVALID, "reference PCG needs dense storage");
         const size_t smem = 5 * (size_t)P * sizeof(double);
         if (smem > 200 * 1024) return fail(p, VIO_ERR_UNSUPPORTED, "reference PCG: P=%d too large for one CTA", P);
-        CK(cudaFuncSetAttribute(k_ref_pcg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(RAISE_SMEM(k_ref_pcg));
         k_ref_pcg<<<1, 1024, smem, p->stream>>>(v.S, v.bS, lambda, P, 2 * P, v.dxp, p->info.p);
         p->launches++;
         if (pcg_iters) {
@@ -481,7 +503,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                 p->pcg_grid = grid; p->pcg_br = brc; p->pcg_win = win_max;
                 p->pcg_smem = ((size_t)6 * win_max + (size_t)5 * 6 * brc + (size_t)36 * brc) * sizeof(double);
                 if (p->pcg_smem <= 200 * 1024)
-                    CK(cudaFuncSetAttribute(k_bpcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->pcg_smem));
+                    CK(RAISE_SMEM(k_bpcg_persistent));
                 // ---- aggregates of the two-level preconditioner: each CTA's rows split into apc chunks of ma rows
                 {
                     const int apc = std::max(1, apc_sel);
@@ -532,8 +554,8 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                         CK(p->cz_A.alloc((size_t)nc_ * nc_)); CK(p->cz_rowbuf.alloc((size_t)na * CZ_KD * nc_)); CK(p->cz_flags.alloc(na));
                         CK(cudaMemsetAsync(p->cz_flags.p, 0, na * sizeof(unsigned), p->stream)); p->cz_epoch = 0; CK(p->cz_rc.alloc(nc_));
                         CK(p->cz_Z.alloc((size_t)6 * CZ_KD * nb));
-                        CK(cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->cz_smem));
-                        CK(cudaFuncSetAttribute(k_bpcg_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                        CK(RAISE_SMEM(k_coarse_invert));
+                        CK(RAISE_SMEM(k_bpcg_persistent));
                     }
                 }
             }
@@ -806,6 +828,10 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
         p->env_pcg_plain = getenv("VIO_B200_PCG_PLAIN") != nullptr;
         if (sms > 0) p->num_sms = sms;
     }
+    if (cudaEventCreate(&p->ev_solve0) != cudaSuccess || cudaEventCreate(&p->ev_solve1) != cudaSuccess) {
+        delete p;
+        return VIO_ERR_CUDA;
+    }
     p->ev_lin.resize(48);  // kernel timing events (the first 48 launches of a solve are timed)
     p->ev_pcg.resize(48);
     p->ev_coarse.resize(48);
@@ -832,6 +858,8 @@ void vio_destroy(vio_problem *p) {
             cudaEventDestroy(e.a);
             cudaEventDestroy(e.b);
         }
+    if (p->ev_solve0) cudaEventDestroy(p->ev_solve0);
+    if (p->ev_solve1) cudaEventDestroy(p->ev_solve1);
     if (p->h_scal) cudaFreeHost(p->h_scal);
     if (p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -928,8 +956,8 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
         CK(upload(p->g_pairinfo, K.g_pairinfo.data(), K.g_pairinfo.size(), s));
         CK(upload(p->ell_pjx, K.ell_pjx.data(), K.ell_pjx.size(), s)); CK(upload(p->ell_pjy, K.ell_pjy.data(), K.ell_pjy.size(), s));
         CK(upload(p->ell_edge, K.ell_edge.data(), K.ell_edge.size(), s));
-        CK(cudaFuncSetAttribute(k_linearize_grouped<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->group_smem));
-        CK(cudaFuncSetAttribute(k_linearize_grouped<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->group_smem));
+        CK(RAISE_SMEM(k_linearize_grouped<true>));
+        CK(RAISE_SMEM(k_linearize_grouped<false>));
         // landmarks without edges are outside every group: their outputs stay zero
         if (L > 0) {
             CK(cudaMemsetAsync(p->Hll.p, 0, L * sizeof(double), s)); CK(cudaMemsetAsync(p->bl.p, 0, L * sizeof(double), s));
@@ -982,7 +1010,11 @@ int vio_get_dims(const vio_problem *p, vio_dims *out) {
 int vio_set_prior(vio_problem *p, int32_t dim, const double *H, const double *b, int32_t err_dim, const double *err,
                   const double *jt) {
     if (!p || !p->has_graph) return VIO_ERR_STATE;
-    if (dim == 0) { p->prior_dim = 0; p->err_dim = 0; return VIO_OK; }
+    if (dim == 0) {
+        p->prior_dim = 0; p->err_dim = 0;
+        p->linearized = false; p->lm_valid = false; p->cz_have_inverse = false;
+        return VIO_OK;
+    }
     if (dim != p->P || !H || !b) return fail(p, VIO_ERR_INVALID, "prior dim %d != P %d", dim, p->P);
     if (p->storage != VIO_STORAGE_DENSE) return fail(p, VIO_ERR_UNSUPPORTED, "dense prior needs dense storage");
     if (err_dim < 0 || err_dim > dim) return fail(p, VIO_ERR_INVALID, "bad err_dim");
@@ -996,6 +1028,8 @@ int vio_set_prior(vio_problem *p, int32_t dim, const double *H, const double *b,
     }
     CK(cudaStreamSynchronize(p->stream));
     p->prior_dim = dim; p->err_dim = err_dim;
+    // the linear system changed: a warm-started solve must not reuse the old linearisation or a lagged coarse inverse
+    p->linearized = false; p->lm_valid = false; p->cz_have_inverse = false;
     return VIO_OK;
 }
 
@@ -1145,9 +1179,7 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
         (p->E == 0 && p->Ex == 0 && p->n_se3 == 0 && p->n_imu == 0 && p->shard_world == 1))
         return fail(p, VIO_ERR_EMPTY, "Cannot solve problem without edges or verticies");
     const bool v15 = o.flavour == VIO_LM_V15;
-    cudaEvent_t ev0, ev1;
-    CK(cudaEventCreate(&ev0));
-    CK(cudaEventCreate(&ev1));
+    const cudaEvent_t ev0 = p->ev_solve0, ev1 = p->ev_solve1;
     CK(cudaEventRecord(ev0, p->stream));
     p->ev_lin_used = 0; p->ev_pcg_used = 0; p->ev_coarse_used = 0; p->pcg_iters_acc = 0.0;
     int rc;
@@ -1262,8 +1294,6 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
         p->last_coarse_ms = p->ev_coarse_used ? tc / p->ev_coarse_used : 0.0; p->last_coarse_launches = (int64_t)p->ev_coarse_used;
         p->last_pcg_iters = p->pcg_iters_acc;
     }
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     if (p->prof.n >= 8) {
         unsigned long long hp[8];
         cudaMemcpy(hp, p->prof.p, sizeof(hp), cudaMemcpyDeviceToHost);
@@ -1531,7 +1561,7 @@ int vio_marginalize(vio_problem *p, int32_t marg_pose, int32_t marg_sb, int32_t 
     DBuf<int> d_edge, d_lm, d_slot, d_imu, d_perm, ord, ord2;
     CK(H.alloc((size_t)n_tot * n_tot)); CK(b.alloc(n_tot));
     CK(cudaMemsetAsync(H.p, 0, (size_t)n_tot * n_tot * sizeof(double), st)); CK(cudaMemsetAsync(b.p, 0, n_tot * sizeof(double), st));
-    do_pose_prep(p);
+    { const int rc_pp = do_pose_prep(p); if (rc_pp) return rc_pp; }
     if (!m_edge.empty()) {
         CK(upload(d_edge, m_edge.data(), m_edge.size(), st)); CK(upload(d_lm, m_lm.data(), m_lm.size(), st));
         CK(upload(d_slot, m_slot.data(), m_slot.size(), st));
@@ -1757,7 +1787,7 @@ static int lockstep_prepare(vio_problem *p, LockstepCache &cache, vio_batch_item
     const int Pper = p->Pper, L = p->L;
     const size_t tri_bytes = ((size_t)Pper * (Pper + 1) / 2 + Pper) * sizeof(double);
     if (tri_bytes > 220 * 1024) return fail(p, VIO_ERR_UNSUPPORTED, "lock-step batch: P=%d per problem does not fit the shared-memory Cholesky", Pper);
-    CK(cudaFuncSetAttribute(k_chol_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CK(RAISE_SMEM(k_chol_batch));
     // ---- per-problem landmark / IMU-edge ranges (items are contiguous in the merged pack) ---------------------------
     std::vector<int> lm_prob(std::max(L, 1), 0), lm_rng(B + 1, 0), imu_rng(B + 1, 0);
     for (int k = 0; k <= B; ++k) { lm_rng[k] = (int)Loff[k]; imu_rng[k] = k * NI; }
@@ -1848,11 +1878,10 @@ static int lockstep_run(vio_problem *p, LockstepCache &cache, vio_batch_item *it
     std::vector<double> h_out(8 * (size_t)B), h_lambda(B);
     std::vector<uint8_t> h_act(B), h_rej(B);
     const ImuView iv = imu_view(p->imu, p->gravity);
-    cudaEvent_t ev0, ev1;
-    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    const cudaEvent_t ev0 = p->ev_solve0, ev1 = p->ev_solve1;
     CK(cudaEventRecord(ev0, st));
     auto chi2_all = [&]() -> int {  // -> h_out[8k+0] + h_out[8k+1]
-        do_pose_prep(p);
+        { const int rc_pp = do_pose_prep(p); if (rc_pp) return rc_pp; }
         k_chi2_batch<<<B, 256, 0, st>>>(p->view, p->lm_rng.p, p->b_out.p);
         k_other_chi2_batch<<<B, 320, 0, st>>>(iv, p->view, p->imu_rng.p, p->errprior.p, p->prior_dim > 0 ? p->err_dim : 0, p->b_out.p);
         p->launches += 2;
@@ -1969,7 +1998,6 @@ static int lockstep_run(vio_problem *p, LockstepCache &cache, vio_batch_item *it
     CK(cudaStreamSynchronize(st));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     const double t_loop_end = now();
     // ---- results --------------------------------------------------------------------------------------------------
     std::vector<double> h_pose(7 * (size_t)B * C), h_sb(9 * (size_t)B * NSB), h_inv(Lt);

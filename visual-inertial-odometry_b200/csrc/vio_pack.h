@@ -60,6 +60,18 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     if (Eg > 0 && (!g->rp_landmark || !g->rp_pose_i || !g->rp_pose_j || !g->rp_pts_i || !g->rp_pts_j))
         return pack_fail(err, VIO_ERR_INVALID, "reprojection arrays missing");
     if (Eg > 0x7fffffffLL) return pack_fail(err, VIO_ERR_UNSUPPORTED, "more than 2^31 edges per shard");
+    if (Lg > 0 && !g->inv_depth) return pack_fail(err, VIO_ERR_INVALID, "inv_depth array missing");
+    if (NSB > 0 && !g->speedbias) return pack_fail(err, VIO_ERR_INVALID, "speedbias array missing");
+    if (g->n_se3prior < 0 || g->n_imu < 0) return pack_fail(err, VIO_ERR_INVALID, "negative size");
+    if (g->n_se3prior > 0) {
+        if (!g->sp_pose || !g->sp_p || !g->sp_q || !g->sp_info) return pack_fail(err, VIO_ERR_INVALID, "EdgeSE3Prior arrays missing");
+        for (int k = 0; k < g->n_se3prior; ++k)
+            if (g->sp_pose[k] < 0 || g->sp_pose[k] >= C) return pack_fail(err, VIO_ERR_INVALID, "se3 prior %d: pose out of range", k);
+    }
+    if (g->n_imu > 0 && (!g->imu_pose_i || !g->imu_pose_j || !g->imu_sb_i || !g->imu_sb_j || !g->imu_sum_dt || !g->imu_delta_p ||
+                         !g->imu_delta_q || !g->imu_delta_v || !g->imu_lin_ba || !g->imu_lin_bg || !g->imu_jacobian ||
+                         !g->imu_covariance))
+        return pack_fail(err, VIO_ERR_INVALID, "EdgeImu arrays missing");
     // ---- ordering of the pose-class vertices (reference SetOrdering) -------------------------
     const int NB = C + NSB;
     std::vector<int> &pose_off = K.pose_off, &sb_off = K.sb_off, &pose_blk = K.pose_blk, &blk_off = K.blk_off, &blk_dim = K.blk_dim;

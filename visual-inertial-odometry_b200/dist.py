@@ -22,8 +22,14 @@ def make_allreduce_hook():
     import torch.distributed as dist
 
     def hook(ptr, n, stream):
+        # the C side orders its kernels on `stream` (the handle's stream, possibly one torch has never seen): run the
+        # collective on that stream so NCCL waits for the linearise kernels and the mirror/finalise kernels wait for NCCL
         t = torch.as_tensor(_CudaPtr(ptr, n), device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if stream:
+            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return 0
 
     return hook

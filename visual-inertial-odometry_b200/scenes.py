@@ -80,6 +80,28 @@ def ring(n_cam=1000, n_landmark=100000, k_obs=11, with_ext=False, seed=4, prior_
     return s
 
 
+def nullspace(draw_order=1):
+    """The reference's hessian_nullspace_test scene (A14 = 14-sliding-window/src/hessian_nullspace_test.cpp:45-93) as a
+    graph of VertexPose + VertexPointXYZ + EdgeReprojectionXYZ: 10 cameras, 20 world points, every camera sees every
+    point, exact observations (zero residual), identity extrinsics, no priors.  J^T J of this graph has the singular
+    values the reference publishes (A14/README.md:125-149), nullspace dimension 7."""
+    L = _L()
+    s = capi.Scene()
+    s.pose = np.zeros((10, 7))
+    pts = np.zeros((20, 3))
+    L.vio_scene_nullspace_fill(int(draw_order), _p(s.pose, C.c_double), _p(pts, C.c_double))
+    s.point_xyz = pts
+    rx_point, rx_pose, rx_obs = [], [], []
+    for m in range(20):
+        for n in range(10):
+            pc = _quat_R(s.pose[n, 3:7]).T @ (pts[m] - s.pose[n, :3])
+            rx_point.append(m); rx_pose.append(n); rx_obs.append(pc[:2] / pc[2])
+    s.rx_point = np.asarray(rx_point, np.int32)
+    s.rx_pose = np.asarray(rx_pose, np.int32)
+    s.rx_obs = np.asarray(rx_obs, np.float64)
+    return s
+
+
 CONFIGS = {
     # name: (factory, kwargs)
     "config1_monoba_20x300": (monoba, dict(pose_nums=20, feature_nums=300)),
