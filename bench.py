@@ -6,8 +6,10 @@
 
 A "step" is one Levenberg-Marquardt iteration of backend::Problem::Solve over the whole scene: reduced solve +
 back-substitution + state update + chi2 pass + (accepted) re-linearisation with MakeHessian + Schur.
-`value` = E x K / t with all inputs resident in HBM; `e2e` = the same through the C-ABI with HOST state buffers
-(vio_set_vertices H2D -> vio_solve(1) -> vio_get_vertices D2H per step, pinned host memory).
+`value` = E x K / t for one vio_solve(K) with all inputs resident in HBM (CUDA events, max over ranks);
+`e2e` = the same call with HOST state buffers: vio_set_vertices (pinned H2D) -> vio_solve(K) -> vio_get_vertices (D2H),
+graph resident; `dropin` = a complete Problem::Solve(K) on a fresh problem: vio_set_graph (pack + upload of the edge
+records) -> vio_solve(K) -> vio_get_vertices.  At N > 1 rank 0 also re-solves unsharded and reports `parity_vs_n1`.
 """
 import argparse
 import importlib
@@ -232,6 +234,40 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+SOLVERS = {"auto": "SOLVER_AUTO", "bcr": "SOLVER_BCR", "two_level": "SOLVER_BLOCK_PCG_2L", "block_jacobi": "SOLVER_BLOCK_PCG",
+           "block_cholesky": "SOLVER_BLOCK_CHOL"}
+SOLVER_NAMES = {0: "auto", 1: "dense_cholesky", 2: "reference_pcg", 3: "block_pcg_6x6_block_jacobi", 4: "block_pcg_6x6_two_level",
+                5: "block_sparse_cholesky", 6: "block_cyclic_reduction"}
+
+
+def parity_vs_unsharded(vio, capi, scene, opts, steps, sharded, stream):
+    """Rank 0 only: the same Solve(K) on ONE GPU, unsharded, compared with what the N-rank run produced."""
+    import torch
+    with torch.cuda.stream(stream):
+        q = vio.Problem(device=torch.cuda.current_device(), stream=stream.cuda_stream)
+        q.set_graph(scene)
+        q.linearize(opts)
+        _, _, val1, bS1 = q.get_schur_bsr()
+        st1 = q.solve(steps, opts)
+        pose1, _, invd1 = q.get_vertices()
+    n = min(st1.n_trace, len(sharded["trace"]))
+    tr1, trN = np.array(st1.chi2_trace[:n]), np.array(sharded["trace"][:n])
+    out = {
+        "S_rel": float(np.abs(sharded["val"] - val1).max() / np.abs(val1).max()),
+        "bS_rel": float(np.linalg.norm(sharded["bS"] - bS1) / np.linalg.norm(bS1)),
+        "chi2_trace_rel": float(np.abs(trN / tr1 - 1.0).max()) if n else None,
+        "chi2_final_rel": float(abs(sharded["chi2_final"] / st1.chi2_final - 1.0)),
+        "pose_abs": float(np.abs(sharded["pose"] - pose1).max()),
+        "inv_depth_abs_owned": float(np.abs(sharded["invd"][sharded["owned"]] - invd1[sharded["owned"]]).max()),
+        "iterations_equal": bool(st1.iterations == sharded["iterations"]),
+        "tolerances": {"S_rel": 1e-9, "chi2": 1e-6, "pose_abs": 1e-6},
+    }
+    out["ok"] = bool(out["S_rel"] <= 1e-9 and out["bS_rel"] <= 1e-9 and out["chi2_final_rel"] <= 1e-6 and
+                     (out["chi2_trace_rel"] is None or out["chi2_trace_rel"] <= 1e-6) and out["pose_abs"] <= 1e-6 and
+                     out["inv_depth_abs_owned"] <= 1e-6 and out["iterations_equal"])
+    return out
+
+
 def run_ours(args):
     import torch
     vio = importlib.import_module(PKG)
@@ -275,8 +311,14 @@ def run_ours(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
-        solver = {"two_level": capi.SOLVER_BLOCK_PCG_2L, "block_jacobi": capi.SOLVER_BLOCK_PCG,
-                  "block_cholesky": capi.SOLVER_BLOCK_CHOL}[args.pcg]
+        def max_over_ranks(x):
+            if dist is None:
+                return x
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        solver = getattr(capi, SOLVERS[args.solver])
         cold = vio.make_opts(flavour=capi.LM_V17, solver=solver, fixed_iterations=1, pcg_max_iter=args.pcg_max_iter)
         # ---- HBM-resident timing: the reference's Solve(K) from the perturbed initial state, K LM iterations on the
         # natural damping schedule (lambda0 = 1e-5 max diag, shrinking with every accepted step).  Warm-up = the same
@@ -294,26 +336,28 @@ def run_ours(args):
         ev1.record(stream)
         barrier()
         launches = p.launch_count() - launches0
-        ms = ev0.elapsed_time(ev1)
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
         lin_ms, lin_n = p.kernel_ms()  # CUDA events around the linearise kernel on the handle's stream
-        sol = p.solver_ms()      # the same around every PCG launch and coarse-preconditioner refresh
-        if dist is not None:
-            t = torch.tensor([lin_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            lin_ms = float(t.item())
+        sol = p.solver_ms()      # the same around every reduced-solve launch (and coarse-preconditioner refresh)
+        lin_ms = max_over_ranks(lin_ms)
+        sharded = None
+        if world > 1 and not args.no_parity:
+            pose_n, _, invd_n = p.get_vertices()
+            # landmarks this rank owns (the others keep their initial values in get_vertices): the packer's edge-balanced cut
+            edge_ptr = np.searchsorted(scene.rp_landmark, np.arange(L + 1), side="left")
+            cuts = importlib.import_module(PKG + ".dist").shard_ranges(edge_ptr, world)
+            owned = np.zeros(L, bool)
+            owned[cuts[rank]:cuts[rank + 1]] = True
+            sharded = {"pose": pose_n, "invd": invd_n, "owned": owned, "trace": list(st.chi2_trace[:st.n_trace]),
+                       "chi2_final": st.chi2_final, "iterations": st.iterations}
         # ---- end to end through the C-ABI with host state buffers -------------------------------------------
         pose_h = torch.empty((C, 7), dtype=torch.float64).pin_memory()
         invd_h = torch.empty((L,), dtype=torch.float64).pin_memory()
         pose_np, invd_np = pose_h.numpy(), invd_h.numpy()
         pose_np[:] = scene.pose
         invd_np[:] = scene.inv_depth
-        # the user-facing call: state from pinned host memory -> Solve(K) -> state back to the host, twice
+        # the user-facing call on a resident graph: state from pinned host memory -> Solve(K) -> state back, twice
         e2e_calls = 2
-        e2e_steps = e2e_calls * args.steps
         p.set_vertices(pose=pose_np, inv_depth=invd_np)
         p.solve(1, cold)
         p.get_vertices()
@@ -326,15 +370,28 @@ def run_ours(args):
             e2e_iters += st_e.iterations
             po, _, iv = p.get_vertices()
         barrier()
-        t_e2e = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e = float(t.item())
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        # ---- the drop-in call: what one Problem::Solve(K) on a fresh Problem costs - graph packing + upload of the edge
+        # records from host arrays (vio_set_graph), Solve(K), read-back of the estimates
+        barrier()
+        t0 = time.perf_counter()
+        p.set_graph(scene)
+        t_sg = time.perf_counter() - t0
+        st_d = p.solve(args.steps, cold)
+        p.get_vertices()
+        barrier()
+        t_dropin = max_over_ranks(time.perf_counter() - t0)
+        if sharded is not None:
+            p.set_vertices(pose=scene.pose, inv_depth=scene.inv_depth)
+            p.linearize(cold)
+            _, _, sharded["val"], sharded["bS"] = p.get_schur_bsr()
         if sampler:
             sampler.stop_flag = True
             sampler.join(timeout=2)
         fp64_peak = capi.measure_fp64_peak(local_rank) if rank == 0 else None
+        parity = None
+        if rank == 0 and sharded is not None:
+            parity = parity_vs_unsharded(vio, capi, scene, cold, args.steps, sharded, stream)
 
     if rank == 0:
         value = E * st.iterations / (ms * 1e-3)
@@ -344,8 +401,54 @@ def run_ours(args):
         flops_alg = alg_flops_linearize(E_k, wl["k_obs"])
         ach_gbs = bytes_alg / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else None
         ach_tf = flops_alg / (lin_ms * 1e-3) / 1e12 if lin_ms > 0 else None
-        pcg_t = sol["pcg_ms"] * sol["pcg_launches"] * 1e-3
-        pcg_gbs = (8.0 * 36 * nnzb * sol["pcg_iterations"] / pcg_t / 1e9) if pcg_t > 0 else None
+        solver_used = SOLVER_NAMES.get(int(st.solver_used), str(st.solver_used))
+        red_t = sol["pcg_ms"] * sol["pcg_launches"] * 1e-3   # seconds inside the timed reduced-solve launches
+        hbm_frac = (ach_gbs / hbm_peak) if ach_gbs else None
+        fp64_frac = (ach_tf / fp64_peak) if (ach_tf and fp64_peak) else None
+        roof_lin = {"kernel": "k_linearize_grouped (linearise + JtWJ + Schur, one CTA per landmark group)",
+                    "bound": "fp64" if (fp64_frac and hbm_frac and fp64_frac > hbm_frac) else "hbm",
+                    "achieved": ach_tf if (fp64_frac and hbm_frac and fp64_frac > hbm_frac) else ach_gbs,
+                    "peak": fp64_peak if (fp64_frac and hbm_frac and fp64_frac > hbm_frac) else hbm_peak,
+                    "unit": "TFLOP/s" if (fp64_frac and hbm_frac and fp64_frac > hbm_frac) else "GB/s",
+                    "frac": max(x for x in (hbm_frac, fp64_frac) if x is not None) if (hbm_frac or fp64_frac) else None,
+                    "hbm_frac": hbm_frac, "fp64_frac": fp64_frac,
+                    "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": bytes_alg},
+                    "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "algorithmic_flops_per_launch": flops_alg,
+                             "peak_source": "measured DFMA micro-benchmark (vio_measure_fp64_peak) in this run"},
+                    "traffic": measured_traffic(args.workload, "k_linearize_grouped") if world == 1 else None,
+                    "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                    "kernel_ms": lin_ms, "kernel_launches_timed": int(lin_n),
+                    "note": "SURVEY 8(d): achieved := max(bytes_alg/t/BW_peak, flops_alg/t/FP64_peak); the fused kernel is "
+                            "FP64-pipe bound (21 FLOP/B against a ridge of ~5.5)"}
+        if int(st.solver_used) == capi.SOLVER_BCR:
+            w = wl["k_obs"] - 1
+            n_nodes, M = C // w, 6 * (w + (w & 1))
+            flops_exec = n_nodes * 15.0 * M ** 3
+            flops_min = 6.0 * C * (6 * (w + 1)) ** 2
+            roof_red = {"kernel": "k_bcr_run (block cyclic reduction, persistent work-queue kernel; + k_bcr_load / k_bcr_finish)",
+                        "bound": "fp64", "achieved": flops_exec / red_t * sol["pcg_launches"] / 1e12 if red_t > 0 else None,
+                        "peak": fp64_peak, "unit": "TFLOP/s",
+                        "frac": (flops_exec / red_t * sol["pcg_launches"] / 1e12 / fp64_peak) if (red_t > 0 and fp64_peak) else None,
+                        "executed_flops_per_solve": flops_exec, "banded_cholesky_flops_per_solve": flops_min,
+                        "nodes": n_nodes, "node_dim": M, "levels": int(np.ceil(np.log2(max(n_nodes, 2)))) + 1,
+                        "kernel_ms": sol["pcg_ms"], "kernel_launches_timed": sol["pcg_launches"],
+                        "note": "exact solve; the dependency chain of log2(nodes) levels (one M x M Cholesky + 6 dense M^3 products "
+                                "each) bounds it, not the FP64 pipe: the upper levels keep only a few SMs busy"}
+        else:
+            pcg_gbs = (8.0 * 36 * nnzb * sol["pcg_iterations"] / red_t / 1e9) if red_t > 0 else None
+            roof_red = {"kernel": "k_bpcg_persistent (6x6 block PCG, one cooperative launch per solve)", "bound": "hbm",
+                        "achieved": pcg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (pcg_gbs / hbm_peak) if pcg_gbs else None,
+                        "traffic": measured_traffic(args.workload, "k_bpcg_persistent") if (world == 1 and args.solver == "two_level") else None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_iteration": 8.0 * 36 * nnzb, "iterations": sol["pcg_iterations"],
+                        "kernel_ms": sol["pcg_ms"], "kernel_launches_timed": sol["pcg_launches"],
+                        "us_per_iteration": (1e3 * sol["pcg_ms"] * sol["pcg_launches"] / sol["pcg_iterations"]) if sol["pcg_iterations"] else None,
+                        "coarse_refresh_ms": sol["coarse_ms"], "coarse_refreshes": sol["coarse_refreshes"]}
+        share = {"k_linearize_grouped": lin_ms * lin_n / ms if ms > 0 else None,
+                 "reduced_solve": sol["pcg_ms"] * sol["pcg_launches"] / ms if ms > 0 else None,
+                 "coarse_refresh": sol["coarse_ms"] * sol["coarse_refreshes"] / ms if ms > 0 else None}
+        dominant_is_lin = (share["k_linearize_grouped"] or 0) >= (share["reduced_solve"] or 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": int(st.iterations),
             "warmup": int(args.warmup), "ms_per_step": ms / max(st.iterations, 1), "higher_is_better": True,
@@ -354,7 +457,7 @@ def run_ours(args):
             # SURVEY 8(d) metric (i): E x linearisations / time inside the linearise + JtWJ + Schur kernel alone
             "linearise_edges_per_sec": (E_local * world) / (lin_ms * 1e-3) if lin_ms > 0 else None,
             "config": {"workload": args.workload, **wl, "edges": E, "landmarks": L, "cameras": C,
-                       "lm_flavour": "v17", "reduced_solver": "block_pcg_6x6_" + args.pcg, "pcg_tol": 1e-6,
+                       "lm_flavour": "v17", "reduced_solver": solver_used, "reduced_solver_requested": args.solver,
                        "schedule": "Solve(K) from the perturbed initial state (natural LM damping schedule)",
                        "parallelism": f"landmark_shard{world}", "l2": "inputs (>=520 MB of edge records) larger than L2",
                        "scene_gen_s": round(t_gen, 2), "pack_upload_s": round(t_pack, 2)},
@@ -362,54 +465,39 @@ def run_ours(args):
                    "linearizations": int(st.linearizations), "pcg_iterations": int(st.pcg_iterations),
                    "chi2_start": st.chi2_trace[0] if st.n_trace else None, "chi2_final": st.chi2_final,
                    "warmup_chi2_initial": st_w.chi2_initial},
-            "roofline_linearize": {"bound": "hbm", "kernel": "k_linearize_grouped (linearise + JtWJ + Schur)",
-                         "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": (ach_gbs / hbm_peak) if ach_gbs else None,
-                         "traffic": measured_traffic(args.workload, "k_linearize_grouped") if world == 1 else None,
-                         "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_alg, "kernel_ms": lin_ms, "kernel_launches_timed": int(lin_n),
-                         "fp64": {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                                  "frac": (ach_tf / fp64_peak) if (ach_tf and fp64_peak) else None,
-                                  "algorithmic_flops_per_launch": flops_alg,
-                                  "peak_source": "measured DFMA micro-benchmark (vio_measure_fp64_peak) in this run"},
-                         "binding": "fp64" if (ach_tf and fp64_peak and ach_gbs and ach_tf / fp64_peak > ach_gbs / hbm_peak) else "hbm"},
-            # the dominant kernel of the step (about two thirds of it, see kernel_share_of_step): the block PCG
-            "roofline": {"bound": "hbm", "kernel": "k_bpcg_persistent (6x6 block PCG, %s preconditioner, one cooperative launch per solve)" % args.pcg,
-                             "achieved": pcg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (pcg_gbs / hbm_peak) if pcg_gbs else None,
-                             "traffic": measured_traffic(args.workload, "k_bpcg_persistent") if (world == 1 and args.pcg == "two_level") else None,
-                             "traffic_source": "profiles/traffic.json: DRAM bytes of ONE ncu --set full launch (a late LM iteration, ~170 PCG "
-                                               "iterations); below the algorithmic bytes because part of S stays in L2 between iterations",
-                             "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": (8.0 * 36 * nnzb * sol["pcg_iterations"] / sol["pcg_launches"]) if sol["pcg_launches"] else None,
-                             "algorithmic_bytes_per_iteration": 8.0 * 36 * nnzb, "iterations": sol["pcg_iterations"],
-                             "kernel_ms": sol["pcg_ms"], "kernel_launches_timed": sol["pcg_launches"],
-                             "us_per_iteration": (1e3 * sol["pcg_ms"] * sol["pcg_launches"] / sol["pcg_iterations"]) if sol["pcg_iterations"] else None,
-                             "coarse_refresh_ms": sol["coarse_ms"], "coarse_refreshes": sol["coarse_refreshes"],
-                             "note": "algorithmic bytes = S streamed once per PCG iteration (8*nnz(S)); the two-level preconditioner "
-                                     "also reads its dense coarse inverse (8*nc^2 = 33 MB) per iteration, so S only partly stays "
-                                     "L2-resident (ncu: 0.86 TB/s DRAM, 61 % L2 hit; profiles/r01_pcg2l_c5_ncu_details.txt). "
-                                     "Timed with CUDA events around each launch; shares of one LM iteration: see "
-                                     "kernel_share_of_step"},
-            "kernel_share_of_step": {
-                "k_bpcg_persistent": sol["pcg_ms"] * sol["pcg_launches"] / ms if ms > 0 else None,
-                "coarse_refresh (k_coarse_basis + k_coarse_assemble + k_coarse_invert)": sol["coarse_ms"] * sol["coarse_refreshes"] / ms if ms > 0 else None,
-                "k_linearize_grouped": lin_ms * lin_n / ms if ms > 0 else None},
+            # the kernel that dominates the step (kernel_share_of_step)
+            "roofline": roof_lin if dominant_is_lin else roof_red,
+            "roofline_linearize": roof_lin,
+            "roofline_reduced_solve": roof_red,
+            "kernel_share_of_step": share,
             "e2e": {"value": E * e2e_iters / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int((pose_np.nbytes + invd_np.nbytes) // max(1, args.steps)),
                     "d2h_bytes_per_step": int((pose_np.nbytes + invd_np.nbytes) // max(1, args.steps)), "steps": int(e2e_iters),
                     "calls": e2e_calls, "h2d_bytes_per_call": int(pose_np.nbytes + invd_np.nbytes),
                     "d2h_bytes_per_call": int(pose_np.nbytes + invd_np.nbytes),
-                    "call": "vio_set_vertices(pinned host state) -> vio_solve(K) -> vio_get_vertices(host): one Solve call moves "
-                            "the state once each way and runs K LM iterations (steps); bytes_per_step = bytes_per_call / K"},
+                    "call": "graph resident; per call: vio_set_vertices(pinned host state) -> vio_solve(K) -> vio_get_vertices(host); "
+                            "bytes_per_step = bytes_per_call / K"},
+            # one complete Problem::Solve(K) on a FRESH problem: edge records from host arrays every call
+            "dropin": {"value": E * st_d.iterations / t_dropin, "unit": UNIT, "seconds_per_call": t_dropin,
+                       "set_graph_s": t_sg, "steps": int(st_d.iterations),
+                       "h2d_bytes_per_call": int(52 * E + 24 * L + 56 * C),
+                       "call": "vio_set_graph(host edge arrays: pack + upload) -> vio_solve(K) -> vio_get_vertices(host)"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary() if sampler else None,
         }
+        if parity is not None:
+            line["parity_vs_n1"] = parity
         if world == 1 and not args.no_cpu:
             cb = cpu_reference_rate(vio, scene, steps=3, warmup=1, target_s=12.0)
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
                                     "sample": cb["sample"]}
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            sys.stderr.write("parity_vs_n1 FAILED: %s\n" % json.dumps(parity))
+            if dist is not None:
+                dist.barrier()
+                dist.destroy_process_group()
+            sys.exit(3)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -423,9 +511,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--pcg", default="two_level", choices=["two_level", "block_jacobi", "block_cholesky"],
-                    help="reduced solver on the block-sparse S: block PCG with the two-level (block-Jacobi + coarse correction) or "
-                         "the plain block-Jacobi preconditioner, or the exact block-sparse Cholesky")
+    ap.add_argument("--solver", "--pcg", dest="solver", default="auto", choices=list(SOLVERS),
+                    help="reduced solver on the block-sparse S: auto (= block cyclic reduction on a camera ring), bcr, block PCG "
+                         "with the two-level or the plain block-Jacobi preconditioner, or the block-sparse Cholesky")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the unsharded re-solve on rank 0 (parity_vs_n1)")
     ap.add_argument("--pcg-max-iter", type=int, default=0, help="cap PCG iterations (profiling runs only; 0 = 2P like the reference)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

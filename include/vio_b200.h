@@ -55,9 +55,16 @@ enum {
                                   factorisation on the host once per graph, numeric right-looking factorisation and the
                                   two triangular solves on the device): the exact "block-Cholesky reduced solve" of
                                   BASELINE config 4                                                    */
-    VIO_SOLVER_BLOCK_PCG_2L = 4 /* the same PCG with a two-level preconditioner: block-Jacobi + Galerkin coarse
+    VIO_SOLVER_BLOCK_PCG_2L = 4, /* the same PCG with a two-level preconditioner: block-Jacobi + Galerkin coarse
                                   correction over aggregates of consecutive pose blocks (camera chains).
-                                  AUTO picks it for block-sparse S with >= 256 pose blocks.              */
+                                  AUTO picks it for block-sparse S with >= 256 pose blocks whose pattern VIO_SOLVER_BCR
+                                  does not cover.                                                       */
+    VIO_SOLVER_BCR = 6          /* block cyclic reduction: EXACT solve (like S.ldlt().solve, A17/src/backend/problem.cc:439)
+                                  for a camera chain / ring, i.e. a block-sparse S that is a cyclic block band of half
+                                  bandwidth <= 12 pose blocks in creation order (fixed, uncoupled pose blocks allowed
+                                  anywhere).  Nested-dissection Cholesky over dense super-blocks, log2(#cameras / bandwidth)
+                                  levels, one persistent kernel.  AUTO picks it whenever the pattern qualifies;
+                                  VIO_ERR_UNSUPPORTED when requested explicitly on another pattern.        */
 };
 enum { VIO_LOSS_TRIVIAL = 0, VIO_LOSS_HUBER = 1, VIO_LOSS_CAUCHY = 2, VIO_LOSS_TUKEY = 3 };
 enum { VIO_STORAGE_AUTO = 0, VIO_STORAGE_DENSE = 1, VIO_STORAGE_BSR = 2 };
@@ -161,10 +168,11 @@ typedef struct vio_stats {
     double lambda_initial, lambda_final;
     double ms_total;          /* CUDA-event time of the whole solve on the handle's stream  */
     double ms_linearize;      /* Σ linearise+accumulate+Schur kernels                       */
-    double ms_reduced_solve;
+    double ms_reduced_solve;  /* Σ reduced-solve kernels (timed launches: PCG / coarse refresh / cyclic reduction) */
     double ms_backsub_update;
     double ms_chi2;
     int32_t n_trace;          /* min(iterations, VIO_TRACE_MAX)                             */
+    int32_t solver_used;      /* the VIO_SOLVER_* that VIO_SOLVER_AUTO resolved to            */
     double chi2_trace[VIO_TRACE_MAX];   /* currentChi_ printed at the top of each iteration */
     double lambda_trace[VIO_TRACE_MAX];
 } vio_stats;

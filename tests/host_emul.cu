@@ -11,6 +11,7 @@
 #include "../visual-inertial-odometry_b200/csrc/vio_pack.h"
 #include "../visual-inertial-odometry_b200/csrc/vio_kernels.cuh"
 #include "../visual-inertial-odometry_b200/csrc/vio_bchol.h"
+#include "../visual-inertial-odometry_b200/csrc/vio_bcr.h"
 
 namespace {
 struct HostProblem {
@@ -338,6 +339,148 @@ int emul_bchol_solve(int nb, const int *rowptr_, const int *col_, const double *
             y[c] = a / D[7 * c];
         }
         for (int c = 0; c < 6; ++c) x[6 * (size_t)j + c] = y[c];
+    }
+    return VIO_OK;
+}
+
+// Block cyclic reduction (vio_bcr.h): the host plan of the product interpreted sequentially on the CPU with plain dense
+// loops - the same items, slots, couplings and update rules the persistent device kernel (vio_bcr.cuh) executes.
+// val: BSR values (nnzb x 36); returns x = (A + lambda I)^-1 b.  info[0..5] = n, w, M, levels, items, slots.
+int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *val, double lambda, const double *b, double *x,
+                   int *info) {
+    std::vector<int> rowptr(rowptr_, rowptr_ + nb + 1), col(col_, col_ + rowptr_[nb]);
+    BcrPlan Y;
+    bcr_plan(nb, rowptr, col, Y);
+    if (!Y.ok) return VIO_ERR_UNSUPPORTED;
+    const int n = Y.n, M = Y.M;
+    const size_t MM = (size_t)M * M;
+    if (info) { info[0] = n; info[1] = Y.w; info[2] = M; info[3] = Y.n_levels; info[4] = (int)Y.items.size(); info[5] = Y.n_slots; }
+    std::vector<double> pool(MM * Y.n_slots, 0.0), bv((size_t)n * M, 0.0), xv((size_t)n * M, 0.0);
+    // loader: BSR blocks -> node tiles, lambda and identity padding on the diagonal
+    for (int i = 0; i < nb; ++i)
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (Y.dst[k] < 0) continue;
+            const bool dg = (Y.dst[k] & BCR_DST_DIAG) != 0;
+            const size_t off = (size_t)(Y.dst[k] & ~BCR_DST_DIAG);
+            for (int e = 0; e < 36; ++e)
+                pool[off + (size_t)(e / 6) * M + e % 6] = val[36 * (size_t)k + e] + ((dg && e % 7 == 0) ? lambda : 0.0);
+        }
+    for (int a = 0; a < n; ++a)
+        for (int q = 6 * Y.node_size[a]; q < M; ++q) pool[(size_t)a * MM + (size_t)q * M + q] = 1.0;
+    for (int i = 0; i < nb; ++i)
+        if (Y.blk_node[i] >= 0)
+            for (int c = 0; c < 6; ++c) bv[(size_t)Y.blk_node[i] * M + 6 * Y.blk_loc[i] + c] = b[6 * (size_t)i + c];
+    std::vector<char> done(Y.items.size(), 0);
+    std::vector<double> Dm(MM), X(MM), Z(MM), U(MM), T(MM), t(M);
+    auto tn = [&](const double *A, const double *B, double *C, double sign, bool accumulate) {  // C (+)= sign * A^T B
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) {
+                double acc = 0.0;
+                for (int r = 0; r < M; ++r) acc += A[(size_t)r * M + i] * B[(size_t)r * M + j];
+                C[(size_t)i * M + j] = (accumulate ? C[(size_t)i * M + j] : 0.0) + sign * acc;
+            }
+    };
+    for (size_t q = 0; q < Y.items.size(); ++q) {
+        const BcrItem &it = Y.items[q];
+        for (int d : it.dep)
+            if (d >= 0 && !done[d]) return VIO_ERR_STATE;  // the order must satisfy every dependency
+        double *bk = &bv[(size_t)it.node * M];
+        if (it.kind & BCR_BACKSUB) {
+            const double *Uk = &pool[(size_t)it.node * MM];
+            for (int i = 0; i < M; ++i) {
+                double a = bk[i];
+                if (it.left >= 0) for (int c = 0; c < M; ++c) a -= pool[(size_t)it.cl_slot * MM + (size_t)i * M + c] * xv[(size_t)it.left * M + c];
+                if (it.right >= 0) for (int c = 0; c < M; ++c) a -= pool[(size_t)it.cr_slot * MM + (size_t)i * M + c] * xv[(size_t)it.right * M + c];
+                t[i] = a;
+            }
+            for (int i = 0; i < M; ++i) {
+                double a = 0.0;
+                for (int r = i; r < M; ++r) a += Uk[(size_t)i * M + r] * t[r];
+                xv[(size_t)it.node * M + i] = a;
+            }
+            done[q] = 1;
+            continue;
+        }
+        std::copy(pool.begin() + (size_t)it.node * MM, pool.begin() + (size_t)(it.node + 1) * MM, Dm.begin());
+        for (int u = 0; u < 2; ++u) {
+            if (it.upd_slot[u] < 0) continue;
+            const double *W = &pool[(size_t)it.upd_slot[u] * MM], *ye = &bv[(size_t)it.upd_node[u] * M];
+            tn(W, W, Dm.data(), -1.0, true);
+            for (int i = 0; i < M; ++i) {
+                double a = 0.0;
+                for (int r = 0; r < M; ++r) a += W[(size_t)r * M + i] * ye[r];
+                bk[i] -= a;
+            }
+        }
+        if (!(it.kind & BCR_ELIM)) {
+            std::copy(Dm.begin(), Dm.end(), pool.begin() + (size_t)it.node * MM);
+            done[q] = 1;
+            continue;
+        }
+        auto coupling = [&](int mode, int a, int bb, double *out) {
+            if (mode == 0) { std::fill(out, out + MM, 0.0); return; }
+            if (mode == 1) {
+                const double *src = &pool[(size_t)a * MM];
+                for (int i = 0; i < M; ++i)
+                    for (int j = 0; j < M; ++j) out[(size_t)i * M + j] = bb ? src[(size_t)j * M + i] : src[(size_t)i * M + j];
+                return;
+            }
+            tn(&pool[(size_t)a * MM], &pool[(size_t)bb * MM], out, -1.0, false);
+        };
+        coupling(it.cl_mode, it.cl_a, it.cl_b, X.data());
+        coupling(it.cr_mode, it.cr_a, it.cr_b, Z.data());
+        if (it.kind & BCR_MERGE)
+            for (size_t e = 0; e < MM; ++e) Z[e] += X[e];
+        // D = L L^T ; U = L^-T by forward elimination on [D | I]
+        std::fill(U.begin(), U.end(), 0.0);
+        for (int i = 0; i < M; ++i) U[(size_t)i * M + i] = 1.0;
+        for (int j = 0; j < M; ++j) {
+            const double d = Dm[(size_t)j * M + j];
+            if (!(d > 0.0)) return VIO_ERR_INVALID;
+            const double pinv = 1.0 / sqrt(d);
+            std::vector<double> v(M, 0.0);
+            for (int k = j; k < M; ++k) v[k] = Dm[(size_t)j * M + k] * pinv;
+            for (int c = 0; c <= j; ++c) U[(size_t)c * M + j] *= pinv;
+            for (int i = j + 1; i < M; ++i) {
+                for (int k = j + 1; k < M; ++k) Dm[(size_t)i * M + k] -= v[i] * v[k];
+                for (int c = 0; c <= j; ++c) U[(size_t)c * M + i] -= v[i] * U[(size_t)c * M + j];
+            }
+        }
+        if (it.cl_slot >= 0) tn(U.data(), X.data(), &pool[(size_t)it.cl_slot * MM], 1.0, false);
+        if (it.cr_slot >= 0) tn(U.data(), Z.data(), &pool[(size_t)it.cr_slot * MM], 1.0, false);
+        for (int i = 0; i < M; ++i) {
+            double a = 0.0;
+            for (int r = 0; r <= i; ++r) a += U[(size_t)r * M + i] * bk[r];
+            t[i] = a;
+        }
+        for (int i = 0; i < M; ++i) bk[i] = t[i];
+        std::copy(U.begin(), U.end(), pool.begin() + (size_t)it.node * MM);
+        done[q] = 1;
+    }
+    for (int i = 0; i < nb; ++i) {
+        if (Y.blk_node[i] >= 0) {
+            for (int c = 0; c < 6; ++c) x[6 * (size_t)i + c] = xv[(size_t)Y.blk_node[i] * M + 6 * Y.blk_loc[i] + c];
+        } else {
+            // isolated pose block: 6x6 solve of (S_ii + lambda I) x = b_i
+            double A[36], y[6];
+            int kd = -1;
+            for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) if (col[k] == i) kd = k;
+            for (int e = 0; e < 36; ++e) A[e] = (kd >= 0 ? val[36 * (size_t)kd + e] : 0.0) + (e % 7 == 0 ? lambda : 0.0);
+            for (int c = 0; c < 6; ++c) y[c] = b[6 * (size_t)i + c];
+            for (int c = 0; c < 6; ++c) {  // Gaussian elimination without pivoting (SPD)
+                if (!(A[7 * c] > 0.0)) return VIO_ERR_INVALID;
+                for (int r = c + 1; r < 6; ++r) {
+                    const double f = A[6 * r + c] / A[7 * c];
+                    for (int k = c; k < 6; ++k) A[6 * r + k] -= f * A[6 * c + k];
+                    y[r] -= f * y[c];
+                }
+            }
+            for (int c = 5; c >= 0; --c) {
+                double a = y[c];
+                for (int k = c + 1; k < 6; ++k) a -= A[6 * c + k] * x[6 * (size_t)i + k];
+                x[6 * (size_t)i + c] = a / A[7 * c];
+            }
+        }
     }
     return VIO_OK;
 }

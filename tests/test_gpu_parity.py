@@ -681,3 +681,103 @@ def test_xyz_hessian_nullspace_known_answer(vio):
     for n in range(10):
         T[6 * n:6 * n + 3] = -1.0
     assert rel_max(H, T[:, None] * Ho * T[None, :]) <= H_TOL
+
+
+def _bsr_residual(rowptr, col, val, bS, lam, d):
+    nb = len(rowptr) - 1
+    r = bS - lam * d
+    rows = np.repeat(np.arange(nb), np.diff(rowptr))
+    np.subtract.at(r.reshape(nb, 6), rows, np.einsum("kij,kj->ki", val, d.reshape(nb, 6)[col]))
+    return np.linalg.norm(r) / np.linalg.norm(bS)
+
+
+@pytest.mark.parametrize("n_cam,n_lm,k_obs,ext", [(1000, 20000, 8, False), (1000, 20000, 11, True), (333, 6000, 5, False),
+                                                  (64, 1500, 11, False), (97, 2000, 4, True)])
+def test_block_cyclic_reduction_is_exact(vio, n_cam, n_lm, k_obs, ext):
+    """VIO_SOLVER_BCR (block cyclic reduction over dense super-blocks of the camera ring): the step solves the tapped
+    block-sparse reduced system to rounding, equals the block-sparse Cholesky step (an independent exact solver), is
+    bitwise reproducible, is what VIO_SOLVER_AUTO picks for a camera ring, and a full Solve follows the block-Cholesky
+    solve.  Cases: even / odd / ragged node counts, a fixed extrinsic vertex (isolated pose block 0)."""
+    capi = vio.capi
+    s = vio.scenes.ring(n_cam=n_cam, n_landmark=n_lm, k_obs=k_obs, seed=9, with_ext=ext)
+    s.storage = capi.STORAGE_BSR
+    p = vio.Problem()
+    p.set_graph(s)
+    ob = vio.make_opts(flavour=capi.LM_V17, solver=capi.SOLVER_BCR)
+    oc = vio.make_opts(flavour=capi.LM_V17, solver=capi.SOLVER_BLOCK_CHOL)
+    p.linearize(ob)
+    rowptr, col, val, bS = p.get_schur_bsr()
+    for scale in (1e-9, 1e-4):
+        lam = scale * np.abs(val).max()
+        p.solve_step(lam, ob)
+        d1, l1 = p.get_delta()
+        assert _bsr_residual(rowptr, col, val, bS, lam, d1) <= 1e-9
+        p.solve_step(lam, ob)
+        d1b, _ = p.get_delta()
+        assert np.array_equal(d1, d1b)
+        p.solve_step(lam, oc)
+        d2, l2 = p.get_delta()
+        assert rel_max(d1, d2) <= 1e-8 and rel_max(l1, l2) <= 1e-8
+    st1 = p.solve(6, vio.make_opts(flavour=capi.LM_V17))
+    assert st1.solver_used == capi.SOLVER_BCR
+    pose1, _, invd1 = p.get_vertices()
+    p2 = vio.Problem()
+    p2.set_graph(s)
+    st2 = p2.solve(6, oc)
+    pose2, _, invd2 = p2.get_vertices()
+    assert st1.iterations == st2.iterations
+    assert np.allclose(st1.chi2_trace[:st1.n_trace], st2.chi2_trace[:st2.n_trace], rtol=1e-8, atol=0)
+    assert np.abs(pose1 - pose2).max() <= FINAL_TOL * np.abs(pose2).max()
+    assert np.abs(invd1 - invd2).max() <= FINAL_TOL * np.abs(invd2).max()
+
+
+def test_block_cyclic_reduction_refuses_other_patterns(vio):
+    """A graph whose reduced system is not a narrow cyclic band (every camera sees every landmark: dense S in BSR
+    storage) makes VIO_SOLVER_BCR return VIO_ERR_UNSUPPORTED, and VIO_SOLVER_AUTO keeps the block PCG."""
+    capi = vio.capi
+    s = vio.scenes.monoba(20, 300)
+    s.storage = capi.STORAGE_BSR
+    p = vio.Problem()
+    p.set_graph(s)
+    p.linearize(vio.make_opts(flavour=capi.LM_V17))
+    with pytest.raises(Exception):
+        p.solve_step(1.0, vio.make_opts(flavour=capi.LM_V17, solver=capi.SOLVER_BCR))
+    st = p.solve(3, vio.make_opts(flavour=capi.LM_V17))
+    assert st.solver_used in (capi.SOLVER_BLOCK_PCG, capi.SOLVER_BLOCK_PCG_2L)
+
+
+def test_config5_size_parity(vio):
+    """What bench.py runs, at BASELINE config-5 size (10k cameras x 1M landmarks x 10M observations, block-sparse S):
+    (1) S and b_S of the grouped linearise kernel vs the C oracle over ALL landmarks, rel <= 1e-9;
+    (2) Solve(6) with the default reduced solver (VIO_SOLVER_AUTO -> block cyclic reduction) vs the block-sparse
+        Cholesky and vs the two-level PCG at tight tolerance: cost trace, final cost, poses and inverse depths within
+        north_star's 1e-6."""
+    from tests import oraclelib as orc
+    capi = vio.capi
+    s = vio.scenes.ring(n_cam=10000, n_landmark=1000000, k_obs=11, seed=5)
+    s.storage = capi.STORAGE_BSR
+    p = vio.Problem()
+    p.set_graph(s)
+    auto = vio.make_opts(flavour=capi.LM_V17, fixed_iterations=1)
+    p.linearize(auto)
+    rowptr, col, val, bS = p.get_schur_bsr()
+    vo, bo, Hll, bl = orc.linearize_bsr(s, rowptr, col)
+    assert np.abs(val - vo).max() <= H_TOL * np.abs(vo).max()
+    assert rel_l2(bS, bo) <= H_TOL
+    del vo
+    st = p.solve(6, auto)
+    assert st.solver_used == capi.SOLVER_BCR
+    pose, _, invd = p.get_vertices()
+    tr = np.array(st.chi2_trace[:st.n_trace])
+    assert st.chi2_final < 1e-3 * st.chi2_initial
+    for solver, tol in ((capi.SOLVER_BLOCK_CHOL, 0.0), (capi.SOLVER_BLOCK_PCG_2L, 1e-11)):
+        q = vio.Problem()
+        q.set_graph(s)
+        st2 = q.solve(6, vio.make_opts(flavour=capi.LM_V17, solver=solver, fixed_iterations=1, pcg_tol=tol))
+        pose2, _, invd2 = q.get_vertices()
+        assert st2.iterations == st.iterations and st2.trial_steps == st.trial_steps
+        assert np.allclose(tr, st2.chi2_trace[:st2.n_trace], rtol=FINAL_TOL, atol=0)
+        assert abs(st2.chi2_final - st.chi2_final) <= FINAL_TOL * st.chi2_final
+        assert np.abs(pose - pose2).max() <= FINAL_TOL * np.abs(pose2).max()
+        assert np.abs(invd - invd2).max() <= FINAL_TOL * np.abs(invd2).max()
+        del q

@@ -202,3 +202,83 @@ def test_reference_scenes_are_grouped_for_the_shared_memory_kernel():
     k = int(np.nonzero(s.rp_landmark == 3)[0][1])
     s.rp_pose_j[k] = s.rp_pose_j[int(np.nonzero(s.rp_landmark == 3)[0][0])]
     assert info(s)[0] == 0
+
+
+def _band_system(nb, w, closed, iso, rng):
+    """Random SPD block matrix: pose blocks `iso` are isolated (diagonal only), the others form a chain (closed: ring)
+    with half bandwidth w in chain order."""
+    chain = [i for i in range(nb) if i not in iso]
+    nc = len(chain)
+    pat = [set([i]) for i in range(nb)]
+    for a in range(nc):
+        for d in range(1, w + 1):
+            c = a + d
+            if c >= nc:
+                if not closed:
+                    continue
+                c -= nc
+            i, j = chain[a], chain[c]
+            if i != j:
+                pat[i].add(j); pat[j].add(i)
+    A = np.zeros((6 * nb, 6 * nb))
+    for i in range(nb):
+        for j in pat[i]:
+            if j > i:
+                B = rng.normal(size=(6, 6))
+                A[6 * i:6 * i + 6, 6 * j:6 * j + 6] = B
+                A[6 * j:6 * j + 6, 6 * i:6 * i + 6] = B.T
+    A += np.diag(np.abs(A).sum(1) + 1.0)
+    rowptr, col, val = [0], [], []
+    for i in range(nb):
+        for j in sorted(pat[i]):
+            col.append(j)
+            val.append(A[6 * i:6 * i + 6, 6 * j:6 * j + 6].copy())
+        rowptr.append(len(col))
+    return A, np.array(rowptr, np.int32), np.array(col, np.int32), np.ascontiguousarray(np.array(val))
+
+
+@pytest.mark.parametrize("nb,w,closed,iso", [(40, 4, True, ()), (41, 4, True, (0,)), (37, 3, True, (5, 20)), (36, 4, False, ()),
+                                             (130, 10, True, (0,)), (24, 8, True, ()), (12, 4, True, ()), (101, 10, True, (0,)),
+                                             (64, 2, True, ()), (65, 2, False, (64,)), (250, 5, True, ()), (30, 11, True, ())])
+def test_block_cyclic_reduction_plan_solves_band_systems(nb, w, closed, iso):
+    """Host logic of VIO_SOLVER_BCR (csrc/vio_bcr.h): the node partition, level schedule, coupling bookkeeping and item
+    dependencies, interpreted on the CPU with dense loops (tests/host_emul.cu::emul_bcr_solve), solve random SPD block
+    band systems - rings and open chains, odd and even node counts at every level, ragged last nodes, isolated (fixed)
+    pose blocks - to rounding."""
+    rng = np.random.default_rng(1000 * nb + w)
+    A, rowptr, col, val = _band_system(nb, w, closed, set(iso), rng)
+    b = rng.normal(size=6 * nb)
+    x = np.zeros(6 * nb)
+    L = emul.lib()
+    ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    L.emul_bcr_solve.argtypes = [C.c_int, ip, ip, dp, C.c_double, dp, dp, ip]
+    info = np.zeros(8, np.int32)
+    lam = 0.21
+    rc = L.emul_bcr_solve(nb, rowptr.ctypes.data_as(ip), col.ctypes.data_as(ip), val.ctypes.data_as(dp), lam,
+                          b.ctypes.data_as(dp), x.ctypes.data_as(dp), info.ctypes.data_as(ip))
+    nc = nb - len(iso)
+    if (nc // w) < 3 or 6 * (-(-nc // (nc // w)) + (-(-nc // (nc // w))) % 2) > 72:
+        assert rc == importlib.import_module("visual-inertial-odometry_b200").capi.VIO_ERR_UNSUPPORTED
+        return
+    assert rc == 0, rc
+    ref = np.linalg.solve(A + lam * np.eye(6 * nb), b)
+    assert np.abs(x - ref).max() <= 1e-11 * np.abs(ref).max()
+    n, wq, M, levels, items, slots = info[:6]
+    assert wq == w and n == nc // w and M % 12 == 0
+    assert levels == int(np.ceil(np.log2(n))) + 1
+
+
+def test_block_cyclic_reduction_rejects_other_patterns():
+    """Patterns that are not a narrow cyclic block band (random long-range couplings, a band wider than the shared-memory
+    tile) are refused, so VIO_SOLVER_AUTO keeps the PCG for them."""
+    rng = np.random.default_rng(7)
+    capi = importlib.import_module("visual-inertial-odometry_b200").capi
+    L = emul.lib()
+    ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    L.emul_bcr_solve.argtypes = [C.c_int, ip, ip, dp, C.c_double, dp, dp, ip]
+    for nb, w in ((60, 13), (200, 40)):
+        A, rowptr, col, val = _band_system(nb, w, True, set(), rng)
+        b, x = rng.normal(size=6 * nb), np.zeros(6 * nb)
+        rc = L.emul_bcr_solve(nb, rowptr.ctypes.data_as(ip), col.ctypes.data_as(ip), val.ctypes.data_as(dp), 0.1,
+                              b.ctypes.data_as(dp), x.ctypes.data_as(dp), None)
+        assert rc == capi.VIO_ERR_UNSUPPORTED

@@ -16,6 +16,7 @@ VIO_ERR_INVALID, VIO_ERR_CUDA, VIO_ERR_UNSUPPORTED, VIO_ERR_EMPTY, VIO_ERR_NO_DE
 ERR_NAMES = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "UNSUPPORTED", 4: "EMPTY", 5: "NO_DEVICE", 6: "STATE"}
 LM_V15, LM_V17 = 0, 1
 SOLVER_AUTO, SOLVER_DENSE_CHOL, SOLVER_REF_PCG, SOLVER_BLOCK_PCG, SOLVER_BLOCK_PCG_2L, SOLVER_BLOCK_CHOL = 0, 1, 2, 3, 4, 5
+SOLVER_BCR = 6
 LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY, LOSS_TUKEY = 0, 1, 2, 3
 STORAGE_AUTO, STORAGE_DENSE, STORAGE_BSR = 0, 1, 2
 TRACE_MAX = 256
@@ -60,7 +61,7 @@ class VioStats(C.Structure):
         ("lambda_initial", C.c_double), ("lambda_final", C.c_double),
         ("ms_total", C.c_double), ("ms_linearize", C.c_double), ("ms_reduced_solve", C.c_double),
         ("ms_backsub_update", C.c_double), ("ms_chi2", C.c_double),
-        ("n_trace", C.c_int32),
+        ("n_trace", C.c_int32), ("solver_used", C.c_int32),
         ("chi2_trace", C.c_double * TRACE_MAX), ("lambda_trace", C.c_double * TRACE_MAX),
     ]
 

@@ -31,6 +31,8 @@
 #include "vio_xyz.cuh"
 #include "vio_bchol.h"
 #include "vio_bchol.cuh"
+#include "vio_bcr.h"
+#include "vio_bcr.cuh"
 
 #define VIO_VERSION_STR "vio_b200 0.1 (sm_100a)"
 
@@ -135,6 +137,17 @@ struct vio_problem {
     DBuf<int> bc_colptr, bc_rowidx, bc_upd_a, bc_upd_b;
     DBuf<long long> bc_a_to_l, bc_upd_ptr, bc_upd_dst;
     DBuf<double> bc_L;
+    // block cyclic reduction (vio_bcr.*): plan built lazily per graph; bcr_state 0 = not tried, 1 = usable, -1 = pattern refused
+    BcrPlan bcr;
+    int bcr_state = 0;
+    bool env_no_bcr = false;
+    unsigned bcr_epoch = 0;
+    size_t bcr_smem = 0;
+    DBuf<BcrItem> bcr_items;
+    DBuf<long long> bcr_dst;
+    DBuf<int> bcr_blk_node, bcr_blk_loc, bcr_node_size;
+    DBuf<double> bcr_pool, bcr_bv, bcr_xv;
+    DBuf<unsigned> bcr_flags;
     bool cz_have_inverse = false, cz_refreshed = false, cz_reuse_policy = false;
     double cz_last_iters = 0, cz_ref_iters = 0, cz_reuse_factor = 1.5;
     int pcg_grid = -1, pcg_br = 0, pcg_win = 0;
@@ -198,7 +211,11 @@ cudaError_t raise_smem_cap(const void *func) {
     int optin = 0;
     e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, func);
+    if (e != cudaSuccess) return e;
+    // static + dynamic shared memory together must fit the opt-in limit
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
     if (e == cudaSuccess) done.emplace_back(dev, func);
     return e;
 }
@@ -247,10 +264,42 @@ vio_lm_opts default_opts() {
     return o;
 }
 
-int resolve_solver(const vio_problem *p, const vio_lm_opts &o) {
+// host plan + device tables of the block cyclic reduction, once per graph.  Returns true when the pattern qualifies.
+bool bcr_prepare(vio_problem *p) {
+    if (p->bcr_state != 0) return p->bcr_state > 0;
+    p->bcr_state = -1;
+    if (p->storage != VIO_STORAGE_BSR || p->batch != 1) return false;
+    bcr_plan(p->NB, p->h_rowptr, p->h_col, p->bcr);
+    const BcrPlan &Y = p->bcr;
+    if (!Y.ok) return false;
+    const size_t MM = (size_t)Y.M * Y.M;
+    cudaStream_t s = p->stream;
+    bool ok = true;
+    ok &= upload(p->bcr_items, Y.items.data(), Y.items.size(), s) == cudaSuccess;
+    ok &= upload(p->bcr_dst, Y.dst.data(), Y.dst.size(), s) == cudaSuccess;
+    ok &= upload(p->bcr_blk_node, Y.blk_node.data(), Y.blk_node.size(), s) == cudaSuccess;
+    ok &= upload(p->bcr_blk_loc, Y.blk_loc.data(), Y.blk_loc.size(), s) == cudaSuccess;
+    ok &= upload(p->bcr_node_size, Y.node_size.data(), Y.node_size.size(), s) == cudaSuccess;
+    ok &= p->bcr_pool.alloc(MM * Y.n_slots) == cudaSuccess;
+    ok &= p->bcr_bv.alloc((size_t)Y.n * Y.M) == cudaSuccess && p->bcr_xv.alloc((size_t)Y.n * Y.M) == cudaSuccess;
+    ok &= p->bcr_flags.alloc(Y.items.size() + 1) == cudaSuccess;  // [n_items] = the work-queue head
+    ok = ok && cudaMemsetAsync(p->bcr_flags.p, 0, (Y.items.size() + 1) * sizeof(unsigned), s) == cudaSuccess;
+    p->bcr_smem = (5 * MM + 4 * (size_t)Y.M) * sizeof(double);
+    ok = ok && RAISE_SMEM(k_bcr_run) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+    if (!ok) { (void)cudaGetLastError(); return false; }
+    p->bcr_epoch = 0;
+    p->bcr_state = 1;
+    return true;
+}
+
+int resolve_solver(vio_problem *p, const vio_lm_opts &o) {
     if (o.solver != VIO_SOLVER_AUTO) return o.solver;
-    if (p->storage == VIO_STORAGE_BSR)
+    if (p->storage == VIO_STORAGE_BSR) {
+        // exact block cyclic reduction whenever S is a cyclic block band (camera chain / ring); the two-level PCG otherwise
+        if (!p->env_no_bcr && bcr_prepare(p)) return VIO_SOLVER_BCR;
         return (p->NB >= 256 && p->coop_ok && !p->env_pcg_plain) ? VIO_SOLVER_BLOCK_PCG_2L : VIO_SOLVER_BLOCK_PCG;
+    }
     return o.flavour == VIO_LM_V15 ? VIO_SOLVER_REF_PCG : VIO_SOLVER_DENSE_CHOL;
 }
 
@@ -664,6 +713,31 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         if (p->pcg_timed_this) p->pcg_iters_acc += hs[4];
         p->pcg_timed_this = false;
         if (p->cz_refreshed) p->cz_ref_iters = hs[4];
+    } else if (solver == VIO_SOLVER_BCR) {
+        if (p->storage != VIO_STORAGE_BSR) return fail(p, VIO_ERR_INVALID, "block cyclic reduction needs BSR storage");
+        if (!bcr_prepare(p))
+            return fail(p, VIO_ERR_UNSUPPORTED, "block cyclic reduction: S is not a cyclic block band of half bandwidth <= %d pose blocks",
+                        BCR_MAX_M / 6);
+        const BcrPlan &Y = p->bcr;
+        const size_t MM = (size_t)Y.M * Y.M;
+        EvPair *evp = p->ev_pcg_used < p->ev_pcg.size() ? &p->ev_pcg[p->ev_pcg_used++] : nullptr;
+        if (evp) CK(cudaEventRecord(evp->a, p->stream));
+        // node tiles D_i and level-0 couplings E_i are rebuilt from S + lambda I; the W tiles behind them are overwritten
+        CK(cudaMemsetAsync(p->bcr_pool.p, 0, 2 * (size_t)Y.n * MM * sizeof(double), p->stream));
+        CK(cudaMemsetAsync(p->bcr_bv.p, 0, (size_t)Y.n * Y.M * sizeof(double), p->stream));
+        CK(cudaMemsetAsync(p->bcr_flags.p + Y.items.size(), 0, sizeof(unsigned), p->stream));
+        CK(cudaMemsetAsync(p->info.p + 2, 0, sizeof(int), p->stream));
+        k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->bcr_dst.p, p->nnzb, v.bS, p->bcr_blk_node.p, p->bcr_blk_loc.p,
+                                                         p->bcr_node_size.p, p->NB, Y.n, Y.M, lambda, p->bcr_pool.p, p->bcr_bv.p);
+        BcrView bv;
+        bv.n = Y.n; bv.M = Y.M; bv.n_items = (int)Y.items.size(); bv.items = p->bcr_items.p; bv.pool = p->bcr_pool.p;
+        bv.bv = p->bcr_bv.p; bv.xv = p->bcr_xv.p; bv.flags = p->bcr_flags.p; bv.counter = p->bcr_flags.p + Y.items.size();
+        bv.epoch = ++p->bcr_epoch; bv.info = p->info.p + 2;
+        k_bcr_run<<<std::min(p->num_sms, bv.n_items), BCR_THREADS, p->bcr_smem, p->stream>>>(bv);
+        k_bcr_finish<<<grid_for(p->NB, 256), 256, 0, p->stream>>>(p->bcr_xv.p, p->bcr_blk_node.p, p->bcr_blk_loc.p, p->NB, Y.M, v.S,
+                                                                p->bsr_diag.p, v.bS, lambda, v.dxp, p->info.p + 2);
+        if (evp) CK(cudaEventRecord(evp->b, p->stream));
+        p->launches += 3;
     } else if (solver == VIO_SOLVER_BLOCK_CHOL) {
         if (p->storage != VIO_STORAGE_BSR) return fail(p, VIO_ERR_INVALID, "block Cholesky needs BSR storage");
         const int nb = p->NB;
@@ -826,6 +900,7 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
         p->env_profile = getenv("VIO_B200_PROFILE") != nullptr;
         p->env_multikernel = getenv("VIO_B200_PCG_MULTIKERNEL") != nullptr;
         p->env_pcg_plain = getenv("VIO_B200_PCG_PLAIN") != nullptr;
+        p->env_no_bcr = getenv("VIO_B200_NO_BCR") != nullptr;
         if (sms > 0) p->num_sms = sms;
     }
     if (cudaEventCreate(&p->ev_solve0) != cudaSuccess || cudaEventCreate(&p->ev_solve1) != cudaSuccess) {
@@ -907,6 +982,7 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     p->batch = K.batch; p->Pper = K.Pper;
     p->cz_have_inverse = false;
     p->bchol_ready = false;
+    p->bcr_state = 0;
     { const char *ev = getenv("VIO_B200_COARSE_REUSE"); p->cz_reuse_policy = !ev || atoi(ev) != 0; }  // default on
     { const char *ev = getenv("VIO_B200_COARSE_REUSE_FACTOR"); if (ev && atof(ev) >= 1.0) p->cz_reuse_factor = atof(ev); }
     const int C = K.C, NSB = K.NSB, L = K.L, P = K.P, NB = K.NB;
@@ -1217,7 +1293,8 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
         int false_cnt = 0;
         while (!ok && (v15 || false_cnt < 10)) {
             int64_t pit = 0;
-            RC(do_solve_step(p, o, lambda, (resolve_solver(p, o) == VIO_SOLVER_DENSE_CHOL || resolve_solver(p, o) == VIO_SOLVER_BLOCK_CHOL) ? nullptr : &pit));
+            const int solver_now = resolve_solver(p, o);
+            RC(do_solve_step(p, o, lambda, (solver_now == VIO_SOLVER_DENSE_CHOL || solver_now == VIO_SOLVER_BLOCK_CHOL || solver_now == VIO_SOLVER_BCR) ? nullptr : &pit));
             st->trial_steps++;
             st->pcg_iterations += pit;
             // scalars of this trial step: scale and |dx|^2
@@ -1293,7 +1370,9 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
         p->last_pcg_ms = p->ev_pcg_used ? tp / p->ev_pcg_used : 0.0; p->last_pcg_launches = (int64_t)p->ev_pcg_used;
         p->last_coarse_ms = p->ev_coarse_used ? tc / p->ev_coarse_used : 0.0; p->last_coarse_launches = (int64_t)p->ev_coarse_used;
         p->last_pcg_iters = p->pcg_iters_acc;
+        st->ms_reduced_solve = tp + tc;
     }
+    st->solver_used = resolve_solver(p, o);
     if (p->prof.n >= 8) {
         unsigned long long hp[8];
         cudaMemcpy(hp, p->prof.p, sizeof(hp), cudaMemcpyDeviceToHost);
