@@ -143,6 +143,7 @@ struct vio_problem {
     bool env_no_bcr = false;
     unsigned bcr_epoch = 0;
     size_t bcr_smem = 0;
+    int bcr_nbuf = 5;
     DBuf<BcrItem> bcr_items;
     DBuf<long long> bcr_dst;
     DBuf<int> bcr_blk_node, bcr_blk_loc, bcr_node_size;
@@ -284,7 +285,12 @@ bool bcr_prepare(vio_problem *p) {
     ok &= p->bcr_bv.alloc((size_t)Y.n * Y.M) == cudaSuccess && p->bcr_xv.alloc((size_t)Y.n * Y.M) == cudaSuccess;
     ok &= p->bcr_flags.alloc(Y.items.size() + 1) == cudaSuccess;  // [n_items] = the work-queue head
     ok = ok && cudaMemsetAsync(p->bcr_flags.p, 0, (Y.items.size() + 1) * sizeof(unsigned), s) == cudaSuccess;
-    p->bcr_smem = (5 * MM + 4 * (size_t)Y.M) * sizeof(double);
+    {
+        // seven operand tiles when they fit (both sides' operands prefetched at once), else five
+        const size_t vec = (12 * (size_t)Y.M + 32) * sizeof(double), lim = 225 * 1024;
+        p->bcr_nbuf = (7 * MM * sizeof(double) + vec <= lim) ? 7 : 5;
+        p->bcr_smem = p->bcr_nbuf * MM * sizeof(double) + vec;
+    }
     ok = ok && RAISE_SMEM(k_bcr_run) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
     if (!ok) { (void)cudaGetLastError(); return false; }
@@ -335,7 +341,7 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
         gv.ell_pjx = p->ell_pjx.p; gv.ell_pjy = p->ell_pjy.p; gv.ell_edge = p->ell_edge.p;
         gv.prof = nullptr;
         if (p->env_profile) {
-            if (p->prof.n < 16) { CK(p->prof.alloc(16)); CK(cudaMemsetAsync(p->prof.p, 0, 16 * sizeof(unsigned long long), p->stream)); }
+            if (p->prof.n < 32) { CK(p->prof.alloc(32)); CK(cudaMemsetAsync(p->prof.p, 0, 32 * sizeof(unsigned long long), p->stream)); }
             gv.prof = p->prof.p;
         }
         if (with_schur) k_linearize_grouped<true><<<p->n_groups, p->group_threads, p->group_smem, p->stream>>>(v, gv);
@@ -647,7 +653,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                 int ncv = nc_, rpv = p->cz_rp;
                 unsigned long long *gjprof = nullptr;
                 if (p->env_profile) {
-                    if (p->prof.n < 16) { CK(p->prof.alloc(16)); CK(cudaMemsetAsync(p->prof.p, 0, 16 * sizeof(unsigned long long), p->stream)); }
+                    if (p->prof.n < 32) { CK(p->prof.alloc(32)); CK(cudaMemsetAsync(p->prof.p, 0, 32 * sizeof(unsigned long long), p->stream)); }
                     gjprof = p->prof.p + 8;
                 }
                 void *iargs[] = {(void *)&Ap, (void *)&ncv, (void *)&rpv, (void *)&rbuf, (void *)&flg, (void *)&epoch, (void *)&gjprof};
@@ -730,9 +736,14 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->bcr_dst.p, p->nnzb, v.bS, p->bcr_blk_node.p, p->bcr_blk_loc.p,
                                                          p->bcr_node_size.p, p->NB, Y.n, Y.M, lambda, p->bcr_pool.p, p->bcr_bv.p);
         BcrView bv;
-        bv.n = Y.n; bv.M = Y.M; bv.n_items = (int)Y.items.size(); bv.items = p->bcr_items.p; bv.pool = p->bcr_pool.p;
+        bv.n = Y.n; bv.M = Y.M; bv.nbuf = p->bcr_nbuf; bv.n_items = (int)Y.items.size(); bv.items = p->bcr_items.p; bv.pool = p->bcr_pool.p;
         bv.bv = p->bcr_bv.p; bv.xv = p->bcr_xv.p; bv.flags = p->bcr_flags.p; bv.counter = p->bcr_flags.p + Y.items.size();
         bv.epoch = ++p->bcr_epoch; bv.info = p->info.p + 2;
+        bv.prof = nullptr;
+        if (p->env_profile) {
+            if (p->prof.n < 32) { CK(p->prof.alloc(32)); CK(cudaMemsetAsync(p->prof.p, 0, 32 * sizeof(unsigned long long), p->stream)); }
+            bv.prof = p->prof.p + 16;
+        }
         k_bcr_run<<<std::min(p->num_sms, bv.n_items), BCR_THREADS, p->bcr_smem, p->stream>>>(bv);
         k_bcr_finish<<<grid_for(p->NB, 256), 256, 0, p->stream>>>(p->bcr_xv.p, p->bcr_blk_node.p, p->bcr_blk_loc.p, p->NB, Y.M, v.S,
                                                                 p->bsr_diag.p, v.bS, lambda, v.dxp, p->info.p + 2);
@@ -1373,6 +1384,20 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
         st->ms_reduced_solve = tp + tc;
     }
     st->solver_used = resolve_solver(p, o);
+    if (p->prof.n >= 32) {
+        unsigned long long hq[16];
+        cudaMemcpy(hq, p->prof.p + 16, sizeof(hq), cudaMemcpyDeviceToHost);
+        if (hq[7] > 0)
+            fprintf(stderr, "[vio_b200 profile] cyclic reduction, cycles per ELIMINATION item: dependency wait (all items) %.0f, updates+couplings %.0f, "
+                            "Cholesky %.0f, W products+stores %.0f; per back-substitution item %.0f; per kept-node item %.0f  (%llu eliminations, %llu items)\n",
+                    (double)hq[0] / hq[7], (double)hq[1] / std::max(1ull, hq[6]), (double)hq[2] / std::max(1ull, hq[6]), (double)hq[3] / std::max(1ull, hq[6]),
+                    (double)hq[4] / std::max(1ull, hq[6]), (double)hq[5] / std::max(1ull, hq[7] - 2 * hq[6]), hq[6], hq[7]);
+        if (hq[7] > 0)
+            fprintf(stderr, "[vio_b200 profile] Cholesky panels, cycles per elimination: warp 0 (look-ahead factor) work %.0f + barrier wait %.0f ; "
+                            "warp 1 (trailing update) work %.0f + barrier wait %.0f\n", (double)hq[8] / std::max(1ull, hq[6]),
+                    (double)hq[9] / std::max(1ull, hq[6]), (double)hq[10] / std::max(1ull, hq[6]), (double)hq[11] / std::max(1ull, hq[6]));
+        cudaMemset(p->prof.p + 16, 0, sizeof(hq));
+    }
     if (p->prof.n >= 8) {
         unsigned long long hp[8];
         cudaMemcpy(hp, p->prof.p, sizeof(hp), cudaMemcpyDeviceToHost);
