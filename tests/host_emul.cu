@@ -352,8 +352,8 @@ int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *va
     BcrPlan Y;
     bcr_plan(nb, rowptr, col, Y);
     if (!Y.ok) return VIO_ERR_UNSUPPORTED;
-    const int n = Y.n, M = Y.M;
-    const size_t MM = (size_t)M * M;
+    const int n = Y.n, M = Y.M, LD = Y.ld;  // tiles are M x LD (row stride LD)
+    const size_t MM = (size_t)M * LD;
     if (info) { info[0] = n; info[1] = Y.w; info[2] = M; info[3] = Y.n_levels; info[4] = (int)Y.items.size(); info[5] = Y.n_slots; }
     std::vector<double> pool(MM * Y.n_slots, 0.0), bv((size_t)n * M, 0.0), xv((size_t)n * M, 0.0);
     // loader: BSR blocks -> node tiles, lambda and identity padding on the diagonal
@@ -363,10 +363,10 @@ int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *va
             const bool dg = (Y.dst[k] & BCR_DST_DIAG) != 0;
             const size_t off = (size_t)(Y.dst[k] & ~BCR_DST_DIAG);
             for (int e = 0; e < 36; ++e)
-                pool[off + (size_t)(e / 6) * M + e % 6] = val[36 * (size_t)k + e] + ((dg && e % 7 == 0) ? lambda : 0.0);
+                pool[off + (size_t)(e / 6) * LD + e % 6] = val[36 * (size_t)k + e] + ((dg && e % 7 == 0) ? lambda : 0.0);
         }
     for (int a = 0; a < n; ++a)
-        for (int q = 6 * Y.node_size[a]; q < M; ++q) pool[(size_t)a * MM + (size_t)q * M + q] = 1.0;
+        for (int q = 6 * Y.node_size[a]; q < M; ++q) pool[(size_t)a * MM + (size_t)q * LD + q] = 1.0;
     for (int i = 0; i < nb; ++i)
         if (Y.blk_node[i] >= 0)
             for (int c = 0; c < 6; ++c) bv[(size_t)Y.blk_node[i] * M + 6 * Y.blk_loc[i] + c] = b[6 * (size_t)i + c];
@@ -376,8 +376,8 @@ int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *va
         for (int i = 0; i < M; ++i)
             for (int j = 0; j < M; ++j) {
                 double acc = 0.0;
-                for (int r = 0; r < M; ++r) acc += A[(size_t)r * M + i] * B[(size_t)r * M + j];
-                C[(size_t)i * M + j] = (accumulate ? C[(size_t)i * M + j] : 0.0) + sign * acc;
+                for (int r = 0; r < M; ++r) acc += A[(size_t)r * LD + i] * B[(size_t)r * LD + j];
+                C[(size_t)i * LD + j] = (accumulate ? C[(size_t)i * LD + j] : 0.0) + sign * acc;
             }
     };
     for (size_t q = 0; q < Y.items.size(); ++q) {
@@ -389,13 +389,13 @@ int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *va
             const double *Uk = &pool[(size_t)it.node * MM];
             for (int i = 0; i < M; ++i) {
                 double a = bk[i];
-                if (it.left >= 0) for (int c = 0; c < M; ++c) a -= pool[(size_t)it.cl_slot * MM + (size_t)i * M + c] * xv[(size_t)it.left * M + c];
-                if (it.right >= 0) for (int c = 0; c < M; ++c) a -= pool[(size_t)it.cr_slot * MM + (size_t)i * M + c] * xv[(size_t)it.right * M + c];
+                if (it.left >= 0) for (int c = 0; c < M; ++c) a -= pool[(size_t)it.cl_slot * MM + (size_t)i * LD + c] * xv[(size_t)it.left * M + c];
+                if (it.right >= 0) for (int c = 0; c < M; ++c) a -= pool[(size_t)it.cr_slot * MM + (size_t)i * LD + c] * xv[(size_t)it.right * M + c];
                 t[i] = a;
             }
             for (int i = 0; i < M; ++i) {
                 double a = 0.0;
-                for (int r = i; r < M; ++r) a += Uk[(size_t)i * M + r] * t[r];
+                for (int r = i; r < M; ++r) a += Uk[(size_t)i * LD + r] * t[r];
                 xv[(size_t)it.node * M + i] = a;
             }
             done[q] = 1;
@@ -408,7 +408,7 @@ int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *va
             tn(W, W, Dm.data(), -1.0, true);
             for (int i = 0; i < M; ++i) {
                 double a = 0.0;
-                for (int r = 0; r < M; ++r) a += W[(size_t)r * M + i] * ye[r];
+                for (int r = 0; r < M; ++r) a += W[(size_t)r * LD + i] * ye[r];
                 bk[i] -= a;
             }
         }
@@ -422,7 +422,7 @@ int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *va
             if (mode == 1) {
                 const double *src = &pool[(size_t)a * MM];
                 for (int i = 0; i < M; ++i)
-                    for (int j = 0; j < M; ++j) out[(size_t)i * M + j] = bb ? src[(size_t)j * M + i] : src[(size_t)i * M + j];
+                    for (int j = 0; j < M; ++j) out[(size_t)i * LD + j] = bb ? src[(size_t)j * LD + i] : src[(size_t)i * LD + j];
                 return;
             }
             tn(&pool[(size_t)a * MM], &pool[(size_t)bb * MM], out, -1.0, false);
@@ -433,24 +433,24 @@ int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *va
             for (size_t e = 0; e < MM; ++e) Z[e] += X[e];
         // D = L L^T ; U = L^-T by forward elimination on [D | I]
         std::fill(U.begin(), U.end(), 0.0);
-        for (int i = 0; i < M; ++i) U[(size_t)i * M + i] = 1.0;
+        for (int i = 0; i < M; ++i) U[(size_t)i * LD + i] = 1.0;
         for (int j = 0; j < M; ++j) {
-            const double d = Dm[(size_t)j * M + j];
+            const double d = Dm[(size_t)j * LD + j];
             if (!(d > 0.0)) return VIO_ERR_INVALID;
             const double pinv = 1.0 / sqrt(d);
             std::vector<double> v(M, 0.0);
-            for (int k = j; k < M; ++k) v[k] = Dm[(size_t)j * M + k] * pinv;
-            for (int c = 0; c <= j; ++c) U[(size_t)c * M + j] *= pinv;
+            for (int k = j; k < M; ++k) v[k] = Dm[(size_t)j * LD + k] * pinv;
+            for (int c = 0; c <= j; ++c) U[(size_t)c * LD + j] *= pinv;
             for (int i = j + 1; i < M; ++i) {
-                for (int k = j + 1; k < M; ++k) Dm[(size_t)i * M + k] -= v[i] * v[k];
-                for (int c = 0; c <= j; ++c) U[(size_t)c * M + i] -= v[i] * U[(size_t)c * M + j];
+                for (int k = j + 1; k < M; ++k) Dm[(size_t)i * LD + k] -= v[i] * v[k];
+                for (int c = 0; c <= j; ++c) U[(size_t)c * LD + i] -= v[i] * U[(size_t)c * LD + j];
             }
         }
         if (it.cl_slot >= 0) tn(U.data(), X.data(), &pool[(size_t)it.cl_slot * MM], 1.0, false);
         if (it.cr_slot >= 0) tn(U.data(), Z.data(), &pool[(size_t)it.cr_slot * MM], 1.0, false);
         for (int i = 0; i < M; ++i) {
             double a = 0.0;
-            for (int r = 0; r <= i; ++r) a += U[(size_t)r * M + i] * bk[r];
+            for (int r = 0; r <= i; ++r) a += U[(size_t)r * LD + i] * bk[r];
             t[i] = a;
         }
         for (int i = 0; i < M; ++i) bk[i] = t[i];

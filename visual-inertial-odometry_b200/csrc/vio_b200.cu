@@ -273,7 +273,7 @@ bool bcr_prepare(vio_problem *p) {
     bcr_plan(p->NB, p->h_rowptr, p->h_col, p->bcr);
     const BcrPlan &Y = p->bcr;
     if (!Y.ok) return false;
-    const size_t MM = (size_t)Y.M * Y.M;
+    const size_t MM = (size_t)Y.M * Y.ld;  // elements of a tile
     cudaStream_t s = p->stream;
     bool ok = true;
     ok &= upload(p->bcr_items, Y.items.data(), Y.items.size(), s) == cudaSuccess;
@@ -725,7 +725,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             return fail(p, VIO_ERR_UNSUPPORTED, "block cyclic reduction: S is not a cyclic block band of half bandwidth <= %d pose blocks",
                         BCR_MAX_M / 6);
         const BcrPlan &Y = p->bcr;
-        const size_t MM = (size_t)Y.M * Y.M;
+        const size_t MM = (size_t)Y.M * Y.ld;
         EvPair *evp = p->ev_pcg_used < p->ev_pcg.size() ? &p->ev_pcg[p->ev_pcg_used++] : nullptr;
         if (evp) CK(cudaEventRecord(evp->a, p->stream));
         // node tiles D_i and level-0 couplings E_i are rebuilt from S + lambda I; the W tiles behind them are overwritten
@@ -734,9 +734,9 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         CK(cudaMemsetAsync(p->bcr_flags.p + Y.items.size(), 0, sizeof(unsigned), p->stream));
         CK(cudaMemsetAsync(p->info.p + 2, 0, sizeof(int), p->stream));
         k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->bcr_dst.p, p->nnzb, v.bS, p->bcr_blk_node.p, p->bcr_blk_loc.p,
-                                                         p->bcr_node_size.p, p->NB, Y.n, Y.M, lambda, p->bcr_pool.p, p->bcr_bv.p);
+                                                         p->bcr_node_size.p, p->NB, Y.n, Y.M, Y.ld, lambda, p->bcr_pool.p, p->bcr_bv.p);
         BcrView bv;
-        bv.n = Y.n; bv.M = Y.M; bv.nbuf = p->bcr_nbuf; bv.n_items = (int)Y.items.size(); bv.items = p->bcr_items.p; bv.pool = p->bcr_pool.p;
+        bv.n = Y.n; bv.M = Y.M; bv.ld = Y.ld; bv.nbuf = p->bcr_nbuf; bv.n_items = (int)Y.items.size(); bv.items = p->bcr_items.p; bv.pool = p->bcr_pool.p;
         bv.bv = p->bcr_bv.p; bv.xv = p->bcr_xv.p; bv.flags = p->bcr_flags.p; bv.counter = p->bcr_flags.p + Y.items.size();
         bv.epoch = ++p->bcr_epoch; bv.info = p->info.p + 2;
         bv.prof = nullptr;
@@ -1394,8 +1394,8 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
                     (double)hq[4] / std::max(1ull, hq[6]), (double)hq[5] / std::max(1ull, hq[7] - 2 * hq[6]), hq[6], hq[7]);
         if (hq[7] > 0)
             fprintf(stderr, "[vio_b200 profile] Cholesky panels, cycles per elimination: warp 0 (look-ahead factor) work %.0f + barrier wait %.0f ; "
-                            "warp 1 (trailing update) work %.0f + barrier wait %.0f\n", (double)hq[8] / std::max(1ull, hq[6]),
-                    (double)hq[9] / std::max(1ull, hq[6]), (double)hq[10] / std::max(1ull, hq[6]), (double)hq[11] / std::max(1ull, hq[6]));
+                            "warp 1 (trailing update) work %.0f + barrier wait %.0f ; bulk-load wait per elimination %.0f (not in updates+couplings); fused pair products %.0f, gemv %.0f, other %.0f\n", (double)hq[8] / std::max(1ull, hq[6]),
+                    (double)hq[9] / std::max(1ull, hq[6]), (double)hq[10] / std::max(1ull, hq[6]), (double)hq[11] / std::max(1ull, hq[6]), (double)hq[12] / std::max(1ull, hq[6]), (double)hq[13] / std::max(1ull, hq[6]), (double)hq[14] / std::max(1ull, hq[6]), (double)hq[15] / std::max(1ull, hq[6]));
         cudaMemset(p->prof.p + 16, 0, sizeof(hq));
     }
     if (p->prof.n >= 8) {

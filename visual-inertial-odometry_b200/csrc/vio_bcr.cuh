@@ -14,7 +14,7 @@
 #define BCR_THREADS 256
 
 struct BcrView {
-    int n, M, n_items;
+    int n, M, ld, n_items;  // ld: row stride of a tile (BcrPlan::ld)
     int nbuf;            // 7 or 5 operand tiles in shared memory (see k_bcr_run)
     const BcrItem *items;
     double *pool;        // [n_slots][M*M]
@@ -30,7 +30,7 @@ struct BcrView {
 // ---- loader ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bcr_load(const double *__restrict__ val, const long long *__restrict__ dst, long long nnzb,
                                                   const double *__restrict__ b, const int *__restrict__ blk_node,
-                                                  const int *__restrict__ blk_loc, const int *__restrict__ node_size, int nb, int n, int M,
+                                                  const int *__restrict__ blk_loc, const int *__restrict__ node_size, int nb, int n, int M, int LD,
                                                   double lambda, double *__restrict__ pool, double *__restrict__ bv) {
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (long long t = t0; t < nnzb * 36; t += stride) {
@@ -39,11 +39,11 @@ __global__ void __launch_bounds__(256) k_bcr_load(const double *__restrict__ val
         const long long d = dst[k];
         if (d < 0) continue;
         const bool dg = (d & BCR_DST_DIAG) != 0;
-        pool[(d & ~BCR_DST_DIAG) + (long long)(e / 6) * M + e % 6] = val[t] + ((dg && e % 7 == 0) ? lambda : 0.0);
+        pool[(d & ~BCR_DST_DIAG) + (long long)(e / 6) * LD + e % 6] = val[t] + ((dg && e % 7 == 0) ? lambda : 0.0);
     }
     for (long long t = t0; t < (long long)n * M; t += stride) {  // identity padding of ragged nodes
         const int a = (int)(t / M), q = (int)(t % M);
-        if (q >= 6 * node_size[a]) pool[(long long)a * M * M + (long long)q * M + q] = 1.0;
+        if (q >= 6 * node_size[a]) pool[(long long)a * M * LD + (long long)q * LD + q] = 1.0;
     }
     for (long long t = t0; t < 6LL * nb; t += stride) {
         const int i = (int)(t / 6), c = (int)(t % 6);
@@ -92,100 +92,105 @@ __global__ void __launch_bounds__(256) k_bcr_finish(const double *__restrict__ x
 }
 
 // ---- tile helpers (all threads of the CTA) ---------------------------------------------------------------------------
-__device__ __forceinline__ void bcr_load_tile(double *dst, const double *src, int M, bool transpose) {
-    const int MM = M * M;
+// A tile is M rows x LD doubles (row stride LD >= M, see BcrPlan::ld); TS = M * LD elements.
+__device__ __forceinline__ void bcr_load_tile(double *dst, const double *src, int M, int LD, bool transpose) {
+    const int TS = M * LD;
     if (!transpose) {
         const double2 *s2 = reinterpret_cast<const double2 *>(src);
         double2 *d2 = reinterpret_cast<double2 *>(dst);
-        for (int t = threadIdx.x; t < (MM >> 1); t += blockDim.x) d2[t] = __ldcg(s2 + t);
+        for (int t = threadIdx.x; t < (TS >> 1); t += blockDim.x) d2[t] = __ldcg(s2 + t);
     } else {
-        for (int t = threadIdx.x; t < MM; t += blockDim.x) {
-            const int r = t / M, c = t - r * M;
-            dst[c * M + r] = __ldcg(src + t);
+        for (int t = threadIdx.x; t < TS; t += blockDim.x) {
+            const int r = t / LD, c = t - r * LD;
+            if (c < M) dst[c * LD + r] = __ldcg(src + t);
         }
     }
 }
-__device__ __forceinline__ void bcr_store_tile(double *dst, const double *src, int M) {
+__device__ __forceinline__ void bcr_store_tile(double *dst, const double *src, int TS) {
     const double2 *s2 = reinterpret_cast<const double2 *>(src);
     double2 *d2 = reinterpret_cast<double2 *>(dst);
-    for (int t = threadIdx.x; t < ((M * M) >> 1); t += blockDim.x) __stcg(d2 + t, s2[t]);
+    for (int t = threadIdx.x; t < (TS >> 1); t += blockDim.x) __stcg(d2 + t, s2[t]);
 }
 
-// C = A^T B over 4x4 register tiles.  A thread's tile is NOT a contiguous 4x4 patch: it owns rows {2ti, 2ti+1, h+2ti,
-// h+2ti+1} and columns {2tj, 2tj+1, h+2tj, h+2tj+1} (h = M/2), so the 16-byte operand loads of consecutive threads are
-// contiguous in shared memory (conflict free; a contiguous 4-wide patch would put consecutive threads 32 bytes apart,
-// a 2-way bank conflict per quarter warp that makes the products shared-memory bound instead of FP64 bound).
-// epi(i, j, v0, v1) receives elements (i, j) and (i, j+1) of the product (j even: 16-byte aligned).  TRI: A is upper triangular (A[r][i] = 0 for r > i).
-template <bool TRI, class Epi>
-__device__ __forceinline__ void bcr_tn(const double *__restrict__ A, const double *__restrict__ B, int M, Epi epi) {
-    const int T = M >> 2, h = M >> 1;
-    for (int t = threadIdx.x; t < T * T; t += blockDim.x) {
-        const int ti = t / T, tj = t - ti * T;
-        double acc[4][4];
+// ---- FP64 tensor-core products -------------------------------------------------------------------------------------
+// mma.sync.m8n8k4.f64 (DMMA): C(8x8) += A(8x4) B(4x8) per warp instruction, i.e. 256 FMAs for three operand registers -
+// the dense M x M products run on the FP64 pipe at its full rate (37 TFLOP/s measured on B200 against 34 for DFMA) with
+// a quarter of the shared-memory traffic and a tenth of the instructions of a register-tiled DFMA loop.
+//   lane l = 4 g + q:  a = A[g][q],  b = B[q][g],  c0, c1 = C[g][2q], C[g][2q+1]
+__device__ __forceinline__ void bcr_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#define BCR_MAXTC ((BCR_MAX_M + 7) / 8)  // 8-wide tile columns of a node tile
+
+// C1 = A^T B1 [and C2 = A^T B2] for row-major M x M tiles in shared memory: both operands are read along rows, the
+// fragments are 4 rows x 8 consecutive columns (conflict free with the padded row stride LD).  A warp owns a band of 8
+// rows of the result and all its tile columns.  TRI: A is upper triangular (A[r][i] = 0 for r > i): the band stops at its
+// diagonal.  epi(i, j, v0, v1) receives elements (i, j), (i, j + 1) (j even).
+template <bool TRI, bool PAIR, int TC, class Epi1, class Epi2>
+__device__ __forceinline__ void bcr_mma_tn_tc(const double *__restrict__ A, const double *__restrict__ B1, const double *__restrict__ B2, int M, int LD,
+                                              Epi1 epi1, Epi2 epi2) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, g = lane >> 2, q = lane & 3;
+    // TC = ceil(M / 8) is a compile-time constant: the tile loop is fully unrolled WITHOUT branches, so the fragment loads
+    // of a k-step are all issued before its first DMMA (a guarded loop serialises load latency and DMMA per tile)
+    bool cv[TC];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+    for (int t = 0; t < TC; ++t) cv[t] = 8 * t + g < M;
+    for (int ti = warp; ti < TC; ti += nw) {
+        const int i0 = 8 * ti;
+        const bool rv = i0 + g < M;
+        double c1[TC][2], c2[PAIR ? TC : 1][2];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-        const int rend = TRI ? min(M, h + 2 * ti + 2) : M;
-        const double *ap = A + 2 * ti, *bp = B + 2 * tj;
-#pragma unroll 4
-        for (int r = 0; r < rend; ++r, ap += M, bp += M) {
-            const double2 a01 = *reinterpret_cast<const double2 *>(ap), a23 = *reinterpret_cast<const double2 *>(ap + h);
-            const double2 b01 = *reinterpret_cast<const double2 *>(bp), b23 = *reinterpret_cast<const double2 *>(bp + h);
-            const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bw[4] = {b01.x, b01.y, b23.x, b23.y};
+        for (int t = 0; t < TC; ++t) { c1[t][0] = c1[t][1] = 0.0; if (PAIR) { c2[t][0] = c2[t][1] = 0.0; } }
+        const int rend = TRI ? min(M, i0 + 8) : M;
+        const double *ap = A + q * LD + (rv ? i0 + g : 0), *b1p = B1 + q * LD + g, *b2p = B2 + q * LD + g;
+#pragma unroll 1
+        for (int r0 = 0; r0 < rend; r0 += 4, ap += 4 * LD, b1p += 4 * LD, b2p += 4 * LD) {
+            double a = *ap, b1[TC], b2[PAIR ? TC : 1];
+            if (!rv) a = 0.0;
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int t = 0; t < TC; ++t) {
+                // the last tile may hang over the edge of the row: the address is clamped, the value masked
+                b1[t] = b1p[cv[t] ? 8 * t : 0];
+                if (PAIR) b2[t] = b2p[cv[t] ? 8 * t : 0];
+            }
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bw[b];
+            for (int t = 0; t < TC; ++t) {
+                bcr_dmma(c1[t][0], c1[t][1], a, cv[t] ? b1[t] : 0.0);
+                if (PAIR) bcr_dmma(c2[t][0], c2[t][1], a, cv[t] ? b2[t] : 0.0);
+            }
         }
+        if (rv) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; b += 2) epi(2 * ti + (a & 1) + (a >> 1) * h, 2 * tj + (b >> 1) * h, acc[a][b], acc[a][b + 1]);
+            for (int t = 0; t < TC; ++t) {
+                const int j = 8 * t + 2 * q;
+                if (j < M) {
+                    epi1(i0 + g, j, c1[t][0], c1[t][1]);
+                    if (PAIR) epi2(i0 + g, j, c2[t][0], c2[t][1]);
+                }
+            }
+        }
     }
 }
-
-// fused pair sharing the A operand:  C1 = A^T A (symmetric update) and C2 = A^T B
-template <class Epi1, class Epi2>
-__device__ __forceinline__ void bcr_tn_pair(const double *__restrict__ A, const double *__restrict__ B, int M, Epi1 epi1, Epi2 epi2) {
-    const int T = M >> 2, h = M >> 1;
-    for (int t = threadIdx.x; t < T * T; t += blockDim.x) {
-        const int ti = t / T, tj = t - ti * T;
-        double c1[4][4], c2[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) { c1[a][b] = 0.0; c2[a][b] = 0.0; }
-        const double *ap = A + 2 * ti, *aq = A + 2 * tj, *bp = B + 2 * tj;
-#pragma unroll 2
-        for (int r = 0; r < M; ++r, ap += M, aq += M, bp += M) {
-            const double2 a01 = *reinterpret_cast<const double2 *>(ap), a23 = *reinterpret_cast<const double2 *>(ap + h);
-            const double2 q01 = *reinterpret_cast<const double2 *>(aq), q23 = *reinterpret_cast<const double2 *>(aq + h);
-            const double2 b01 = *reinterpret_cast<const double2 *>(bp), b23 = *reinterpret_cast<const double2 *>(bp + h);
-            const double av[4] = {a01.x, a01.y, a23.x, a23.y}, qv[4] = {q01.x, q01.y, q23.x, q23.y}, bw[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) { c1[a][b] += av[a] * qv[b]; c2[a][b] += av[a] * bw[b]; }
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; b += 2) {
-                const int i = 2 * ti + (a & 1) + (a >> 1) * h, j = 2 * tj + (b >> 1) * h;
-                epi1(i, j, c1[a][b], c1[a][b + 1]);
-                epi2(i, j, c2[a][b], c2[a][b + 1]);
-            }
+template <bool TRI, bool PAIR, class Epi1, class Epi2>
+__device__ __forceinline__ void bcr_mma_tn(const double *__restrict__ A, const double *__restrict__ B1, const double *__restrict__ B2, int M, int LD,
+                                           Epi1 epi1, Epi2 epi2) {
+    switch ((M + 7) >> 3) {  // M is a multiple of 12 up to BCR_MAX_M
+        case 2: bcr_mma_tn_tc<TRI, PAIR, 2>(A, B1, B2, M, LD, epi1, epi2); break;
+        case 3: bcr_mma_tn_tc<TRI, PAIR, 3>(A, B1, B2, M, LD, epi1, epi2); break;
+        case 5: bcr_mma_tn_tc<TRI, PAIR, 5>(A, B1, B2, M, LD, epi1, epi2); break;
+        case 6: bcr_mma_tn_tc<TRI, PAIR, 6>(A, B1, B2, M, LD, epi1, epi2); break;
+        case 8: bcr_mma_tn_tc<TRI, PAIR, 8>(A, B1, B2, M, LD, epi1, epi2); break;
+        default: bcr_mma_tn_tc<TRI, PAIR, 9>(A, B1, B2, M, LD, epi1, epi2); break;
     }
 }
 
 // v[i] -= sum_r A[r][i] * y[r]   (A: shared tile, y: shared vector).  Four threads per element (r = part mod 4), combined
 // through `scratch` ([4][M]); contains two barriers - every thread of the CTA must call it.
-__device__ __forceinline__ void bcr_gemv_t_sub(const double *A, const double *y, double *v, double *scratch, int M) {
+__device__ __forceinline__ void bcr_gemv_t_sub(const double *A, const double *y, double *v, double *scratch, int M, int LD) {
     for (int t = threadIdx.x; t < 4 * M; t += blockDim.x) {
         const int part = t / M, i = t - part * M;
         double a = 0.0;
-        for (int r = part; r < M; r += 4) a += A[r * M + i] * y[r];
+        for (int r = part; r < M; r += 4) a += A[r * LD + i] * y[r];
         scratch[part * M + i] = a;
     }
     __syncthreads();
@@ -199,35 +204,53 @@ __device__ __forceinline__ void bcr_gemv_t_sub(const double *A, const double *y,
 //   * warp 0 owns the critical path: it brings the NEXT panel's 4 rows up to date in registers (rank-4 update with the
 //     current panel), factorises them there (lanes = columns, pivots and multipliers by shuffle) and publishes the
 //     scaled rows V'[k][0..3], the reciprocal pivots and the panel's 4x4 triangle for the following iteration;
-//   * warps 1.. apply the current panel to everything else: rank-4 update of the trailing rows of D, and for the
-//     rows of U first the panel's 4x4 triangular transform of columns j0..j0+3, then the same rank-4 update.
+//   * the other warps apply the current panel to everything else as rank-4 DMMA updates on 8x8 tiles,
+//     C[rows][cols] -= F[rows][0..3] V[cols][0..3]^T: for the trailing rows of D the multipliers F are rows of V, for the
+//     rows of U they are columns j0..j0+3 of U after the panel's 4x4 triangular transform (done in registers by the
+//     lanes that need them, written back once).
 // One barrier per panel (M/4 panels); V and the panel scalars are double buffered.
 #define BCR_PANEL 4
-#define BCR_MAXPASS 3  // ceil(BCR_MAX_M / 32)
-static_assert(BCR_MAX_M <= 32 * BCR_MAXPASS, "panel rows are held by one warp");
+#define BCR_CHUNK 8  // column tiles of the trailing update in flight per band
 
-// factorise 4 panel rows held in registers (r[q][sp] = row j0+q, column j0 + lane + 32 sp); sc[0..3] = 1/sqrt(pivot),
-// sc[4..9] = v_a[j0+q] for a < q in the order (0,1) (0,2) (1,2) (0,3) (1,3) (2,3)
+// Factorise 4 panel rows held in registers (r[q][sp] = row j0+q, column j0 + lane + 32 sp).  blk = the panel's 4x4
+// leading block (lower triangle: 00 10 11 20 21 22 30 31 32 33), up to date and identical in every lane: each lane
+// factorises it redundantly in registers, so the critical path (4 dependent reciprocal square roots) has no shuffles and
+// no shared-memory round trips; the lane's own columns follow with independent FMAs.
+// Publishes V'[k][0..3] (scaled rows), sc[0..3] = 1/sqrt(pivot), sc[4..9] = L[j0+q][a] for a < q in the order
+// (0,1) (0,2) (1,2) (0,3) (1,3) (2,3).
 template <int NPASS>
-__device__ __forceinline__ void bcr_panel_factor(double (&r)[BCR_PANEL][NPASS], int j0, int lane, int M, double *__restrict__ Vn,
-                                                 double *__restrict__ sc, int *info) {
-    double pq[BCR_PANEL];
+__device__ __forceinline__ void bcr_panel_factor(double (&r)[BCR_PANEL][NPASS], const double (&blk)[10], int j0, int lane, int M,
+                                                 double *__restrict__ Vn, double *__restrict__ sc, int *info) {
+    // 4x4 Cholesky of the leading block
+    const bool bad0 = !(blk[0] > 0.0);
+    const double p0 = rsqrt(bad0 ? 1.0 : blk[0]);
+    const double l10 = blk[1] * p0, l20 = blk[3] * p0, l30 = blk[6] * p0;
+    const double d1 = blk[2] - l10 * l10;
+    const bool bad1 = !(d1 > 0.0);
+    const double p1 = rsqrt(bad1 ? 1.0 : d1);
+    const double l21 = (blk[4] - l20 * l10) * p1, l31 = (blk[7] - l30 * l10) * p1;
+    const double d2 = blk[5] - l20 * l20 - l21 * l21;
+    const bool bad2 = !(d2 > 0.0);
+    const double p2 = rsqrt(bad2 ? 1.0 : d2);
+    const double l32 = (blk[8] - l30 * l20 - l31 * l21) * p2;
+    const double d3 = blk[9] - l30 * l30 - l31 * l31 - l32 * l32;
+    const bool bad3 = !(d3 > 0.0);
+    const double p3 = rsqrt(bad3 ? 1.0 : d3);
+    if (lane == 0 && (bad0 || bad1 || bad2 || bad3)) *info = j0 + 1 + (bad0 ? 0 : (bad1 ? 1 : (bad2 ? 2 : 3)));
+    // own columns: v_0 = r_0 p0 ; v_1 = (r_1 - l10 v_0) p1 ; ...   (columns left of the diagonal come out as the zeros of L^T)
 #pragma unroll
-    for (int q = 0; q < BCR_PANEL; ++q) {
-        const double d = __shfl_sync(0xffffffffu, r[q][0], q);
-        if (lane == 0 && !(d > 0.0)) *info = j0 + q + 1;
-        const double p = rsqrt(d > 0.0 ? d : 1.0);
-        pq[q] = p;
-#pragma unroll
-        for (int sp = 0; sp < NPASS; ++sp) r[q][sp] *= p;
-        if (lane < q) r[q][0] = 0.0;  // left of the diagonal: already eliminated
-#pragma unroll
-        for (int i = q + 1; i < BCR_PANEL; ++i) {
-            const double f = __shfl_sync(0xffffffffu, r[q][0], i);  // v_q[j0 + i]
-#pragma unroll
-            for (int sp = 0; sp < NPASS; ++sp) r[i][sp] -= f * r[q][sp];
-        }
+    for (int sp = 0; sp < NPASS; ++sp) {
+        const double v0 = r[0][sp] * p0;
+        const double v1 = (r[1][sp] - l10 * v0) * p1;
+        const double v2 = (r[2][sp] - l20 * v0 - l21 * v1) * p2;
+        const double v3 = (r[3][sp] - l30 * v0 - l31 * v1 - l32 * v2) * p3;
+        r[0][sp] = v0; r[1][sp] = v1; r[2][sp] = v2; r[3][sp] = v3;
     }
+    // exact zeros left of the diagonal inside the panel (rounding leaves ~1e-17 there; they are never read as multipliers,
+    // but V feeds the DMMA updates as a whole)
+    if (lane < 1) r[1][0] = 0.0;
+    if (lane < 2) r[2][0] = 0.0;
+    if (lane < 3) r[3][0] = 0.0;
 #pragma unroll
     for (int sp = 0; sp < NPASS; ++sp) {
         const int k = j0 + lane + 32 * sp;
@@ -236,28 +259,36 @@ __device__ __forceinline__ void bcr_panel_factor(double (&r)[BCR_PANEL][NPASS], 
             *reinterpret_cast<double2 *>(Vn + 4 * k + 2) = make_double2(r[2][sp], r[3][sp]);
         }
     }
-    if (lane == 0) { sc[0] = pq[0]; sc[1] = pq[1]; sc[2] = pq[2]; sc[3] = pq[3]; }
-    if (lane == 1) sc[4] = r[0][0];
-    if (lane == 2) { sc[5] = r[0][0]; sc[6] = r[1][0]; }
-    if (lane == 3) { sc[7] = r[0][0]; sc[8] = r[1][0]; sc[9] = r[2][0]; }
+    if (lane == 0) {
+        sc[0] = p0; sc[1] = p1; sc[2] = p2; sc[3] = p3;
+        sc[4] = l10; sc[5] = l20; sc[6] = l21; sc[7] = l30; sc[8] = l31; sc[9] = l32;
+    }
 }
 
 template <int NPASS>  // ceil(M / 32)
 __device__ __forceinline__ void bcr_chol_inv(double *__restrict__ D, double *__restrict__ U, double *__restrict__ V /* [2][M][4] */,
-                                             double *__restrict__ sc /* [2][16] */, int M, int *info, unsigned long long *prof) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+                                             double *__restrict__ sc /* [2][16] */, int M, int LD, int *info, unsigned long long *prof) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5, g = lane >> 2, q = lane & 3;
     long long cw0 = 0, cw1 = 0, cb0 = 0, cb1 = 0;
-    for (int t = tid; t < M * M; t += nt) U[t] = (t / M == t % M) ? 1.0 : 0.0;
+    for (int t = tid; t < M * LD; t += nt) U[t] = (t / LD == t % LD) ? 1.0 : 0.0;
     if (warp == 0) {
         double r[BCR_PANEL][NPASS];
 #pragma unroll
-        for (int q = 0; q < BCR_PANEL; ++q)
+        for (int qq = 0; qq < BCR_PANEL; ++qq)
 #pragma unroll
             for (int sp = 0; sp < NPASS; ++sp) {
                 const int k = lane + 32 * sp;
-                r[q][sp] = k < M ? D[q * M + k] : 0.0;
+                r[qq][sp] = k < M ? D[qq * LD + k] : 0.0;
             }
-        bcr_panel_factor<NPASS>(r, 0, lane, M, V, sc, info);
+        double blk[10];
+        {
+            int e = 0;
+#pragma unroll
+            for (int a2 = 0; a2 < BCR_PANEL; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 <= a2; ++b2) blk[e++] = D[a2 * LD + b2];
+        }
+        bcr_panel_factor<NPASS>(r, blk, 0, lane, M, V, sc, info);
     }
     __syncthreads();
     const int np = M / BCR_PANEL;
@@ -265,94 +296,91 @@ __device__ __forceinline__ void bcr_chol_inv(double *__restrict__ D, double *__r
         const int j0 = BCR_PANEL * pnl, k0 = j0 + BCR_PANEL, cur = pnl & 1;
         const long long tA = prof ? clock64() : 0;
         const double *Vc = V + cur * 4 * M, *scc = sc + cur * 16;
-        double vk[NPASS][BCR_PANEL];
-#pragma unroll
-        for (int sp = 0; sp < NPASS; ++sp) {
-            const int k = k0 + lane + 32 * sp;
-            if (k < M) {
-                const double2 a = *reinterpret_cast<const double2 *>(Vc + 4 * k), b2 = *reinterpret_cast<const double2 *>(Vc + 4 * k + 2);
-                vk[sp][0] = a.x; vk[sp][1] = a.y; vk[sp][2] = b2.x; vk[sp][3] = b2.y;
-            } else {
-                vk[sp][0] = vk[sp][1] = vk[sp][2] = vk[sp][3] = 0.0;
-            }
-        }
         if (warp == 0) {
             if (k0 < M) {
-                double r[BCR_PANEL][NPASS];
+                double vk[NPASS][BCR_PANEL], r[BCR_PANEL][NPASS];
 #pragma unroll
-                for (int q = 0; q < BCR_PANEL; ++q) {
-                    const double *fp = Vc + 4 * (k0 + q);
+                for (int sp = 0; sp < NPASS; ++sp) {
+                    const int k = k0 + lane + 32 * sp;
+                    if (k < M) {
+                        const double2 a = *reinterpret_cast<const double2 *>(Vc + 4 * k), b2 = *reinterpret_cast<const double2 *>(Vc + 4 * k + 2);
+                        vk[sp][0] = a.x; vk[sp][1] = a.y; vk[sp][2] = b2.x; vk[sp][3] = b2.y;
+                    } else {
+                        vk[sp][0] = vk[sp][1] = vk[sp][2] = vk[sp][3] = 0.0;
+                    }
+                }
+                double fq[BCR_PANEL][BCR_PANEL];  // V[k0+a][q]: the panel rows' own multipliers (the same in every lane)
+#pragma unroll
+                for (int qq = 0; qq < BCR_PANEL; ++qq) {
+                    const double *fp = Vc + 4 * (k0 + qq);
                     const double2 f01 = *reinterpret_cast<const double2 *>(fp), f23 = *reinterpret_cast<const double2 *>(fp + 2);
+                    fq[qq][0] = f01.x; fq[qq][1] = f01.y; fq[qq][2] = f23.x; fq[qq][3] = f23.y;
 #pragma unroll
                     for (int sp = 0; sp < NPASS; ++sp) {
                         const int k = k0 + lane + 32 * sp;
-                        r[q][sp] = k < M ? D[(k0 + q) * M + k] - (f01.x * vk[sp][0] + f01.y * vk[sp][1] + f23.x * vk[sp][2] + f23.y * vk[sp][3]) : 0.0;
+                        r[qq][sp] = k < M ? D[(k0 + qq) * LD + k] - ((f01.x * vk[sp][0] + f01.y * vk[sp][1]) + (f23.x * vk[sp][2] + f23.y * vk[sp][3])) : 0.0;
                     }
                 }
-                bcr_panel_factor<NPASS>(r, k0, lane, M, V + (cur ^ 1) * 4 * M, sc + (cur ^ 1) * 16, info);
+                double blk[10];
+                {
+                    int e = 0;
+#pragma unroll
+                    for (int a2 = 0; a2 < BCR_PANEL; ++a2)
+#pragma unroll
+                        for (int b2 = 0; b2 <= a2; ++b2)
+                            blk[e++] = D[(k0 + a2) * LD + k0 + b2] -
+                                       ((fq[a2][0] * fq[b2][0] + fq[a2][1] * fq[b2][1]) + (fq[a2][2] * fq[b2][2] + fq[a2][3] * fq[b2][3]));
+                }
+                bcr_panel_factor<NPASS>(r, blk, k0, lane, M, V + (cur ^ 1) * 4 * M, sc + (cur ^ 1) * 16, info);
             }
         } else {
-            const int nD = max(0, M - k0 - BCR_PANEL);  // trailing rows of D below the next panel
-            const int nwk = nw - 1, w1 = warp - 1;
-            int kk[NPASS];
-            bool kv[NPASS];
-#pragma unroll
-            for (int sp = 0; sp < NPASS; ++sp) { kk[sp] = k0 + lane + 32 * sp; kv[sp] = kk[sp] < M; if (!kv[sp]) kk[sp] = M - 1; }
-            // (1) trailing rows of D, two at a time (loads grouped before the stores: the rows are independent but live in
-            //     the same array, the compiler would otherwise serialise them)
-            for (int rr = w1; rr < nD; rr += 2 * nwk) {
-                const int ia = k0 + BCR_PANEL + rr, ib = ia + nwk;
-                const bool hb = rr + nwk < nD;
-                double *ra = D + ia * M, *rb = D + (hb ? ib : ia) * M;
-                const double2 fa01 = *reinterpret_cast<const double2 *>(Vc + 4 * ia), fa23 = *reinterpret_cast<const double2 *>(Vc + 4 * ia + 2);
-                const double2 fb01 = *reinterpret_cast<const double2 *>(Vc + 4 * (hb ? ib : ia)), fb23 = *reinterpret_cast<const double2 *>(Vc + 4 * (hb ? ib : ia) + 2);
-                double va[NPASS], vb[NPASS];
-#pragma unroll
-                for (int sp = 0; sp < NPASS; ++sp) { va[sp] = ra[kk[sp]]; vb[sp] = rb[kk[sp]]; }
-#pragma unroll
-                for (int sp = 0; sp < NPASS; ++sp) {
-                    va[sp] -= fa01.x * vk[sp][0] + fa01.y * vk[sp][1] + fa23.x * vk[sp][2] + fa23.y * vk[sp][3];
-                    vb[sp] -= fb01.x * vk[sp][0] + fb01.y * vk[sp][1] + fb23.x * vk[sp][2] + fb23.y * vk[sp][3];
-                }
-#pragma unroll
-                for (int sp = 0; sp < NPASS; ++sp) {
-                    if (kv[sp]) ra[kk[sp]] = va[sp];
-                    if (kv[sp] && hb) rb[kk[sp]] = vb[sp];
-                }
-            }
-            // (2) rows 0 .. j0+3 of U: the panel's 4x4 triangular transform of columns j0..j0+3, then the same rank-4 update
+            const int wk = warp - 1, nwk = nw - 1;  // worker index / count
+            const int nD = max(0, M - k0 - BCR_PANEL);   // trailing rows of D below the next panel: rows k0+4 ..
+            const int nbD = (nD + 7) >> 3, nbU = (k0 + 7) >> 3;  // 8-row bands of D, and of rows 0 .. j0+3 of U
+            const int nct = (M - k0 + 7) >> 3;               // 8-column tiles from column k0
             const double p0 = scc[0], p1 = scc[1], p2 = scc[2], p3 = scc[3];
             const double s01 = scc[4], s02 = scc[5], s12 = scc[6], s03 = scc[7], s13 = scc[8], s23 = scc[9];
-            for (int rr = w1; rr < k0; rr += 2 * nwk) {
-                const bool hb = rr + nwk < k0;
-                double *ra = U + rr * M, *rb = U + (hb ? rr + nwk : rr) * M;
-                const double2 ua01 = *reinterpret_cast<const double2 *>(ra + j0), ua23 = *reinterpret_cast<const double2 *>(ra + j0 + 2);
-                const double2 ub01 = *reinterpret_cast<const double2 *>(rb + j0), ub23 = *reinterpret_cast<const double2 *>(rb + j0 + 2);
-                double va[NPASS], vb[NPASS];
+            for (int bnd = wk; bnd < nbD + nbU; bnd += nwk) {
+                double *C;
+                double a;  // this lane's multiplier F[g][q], negated
+                bool rv;
+                if (bnd < nbD) {
+                    const int i = k0 + BCR_PANEL + 8 * bnd + g;
+                    rv = i < M;
+                    C = D + (rv ? i : M - 1) * LD;
+                    a = rv ? -Vc[4 * i + q] : 0.0;
+                } else {
+                    const int c = 8 * (bnd - nbD) + g;
+                    rv = c < k0;
+                    C = U + (rv ? c : 0) * LD;
+                    const double2 u01 = *reinterpret_cast<const double2 *>(C + j0), u23 = *reinterpret_cast<const double2 *>(C + j0 + 2);
+                    const double g0 = u01.x * p0;
+                    const double g1 = (u01.y - s01 * g0) * p1;
+                    const double g2 = (u23.x - s02 * g0 - s12 * g1) * p2;
+                    const double g3 = (u23.y - s03 * g0 - s13 * g1 - s23 * g2) * p3;
+                    const double gq = q == 0 ? g0 : (q == 1 ? g1 : (q == 2 ? g2 : g3));
+                    __syncwarp();  // the four lanes of a row have read columns j0..j0+3 before they are overwritten
+                    if (rv) C[j0 + q] = gq;
+                    a = rv ? -gq : 0.0;
+                }
+                // column tiles BCR_CHUNK at a time, loads before the DMMAs before the stores (no branches in between)
+                for (int ct0 = 0; ct0 < nct; ct0 += BCR_CHUNK) {
+                    double b[BCR_CHUNK];
+                    double2 c[BCR_CHUNK];
+                    bool cv[BCR_CHUNK];
 #pragma unroll
-                for (int sp = 0; sp < NPASS; ++sp) { va[sp] = ra[kk[sp]]; vb[sp] = rb[kk[sp]]; }
-                const double a0 = ua01.x * p0, b0 = ub01.x * p0;
-                const double a1 = (ua01.y - s01 * a0) * p1, b1 = (ub01.y - s01 * b0) * p1;
-                const double a2 = (ua23.x - s02 * a0 - s12 * a1) * p2, b2 = (ub23.x - s02 * b0 - s12 * b1) * p2;
-                const double a3 = (ua23.y - s03 * a0 - s13 * a1 - s23 * a2) * p3, b3 = (ub23.y - s03 * b0 - s13 * b1 - s23 * b2) * p3;
-                __syncwarp();  // every lane has read columns j0..j0+3 before lane 0 overwrites them
-                if (lane == 0) {
-                    *reinterpret_cast<double2 *>(ra + j0) = make_double2(a0, a1);
-                    *reinterpret_cast<double2 *>(ra + j0 + 2) = make_double2(a2, a3);
-                    if (hb) {
-                        *reinterpret_cast<double2 *>(rb + j0) = make_double2(b0, b1);
-                        *reinterpret_cast<double2 *>(rb + j0 + 2) = make_double2(b2, b3);
+                    for (int u = 0; u < BCR_CHUNK; ++u) {
+                        const int kb = k0 + 8 * (ct0 + u) + g, kc = k0 + 8 * (ct0 + u) + 2 * q;
+                        cv[u] = rv && kc < M;
+                        b[u] = Vc[4 * min(kb, M - 1) + q];
+                        if (kb >= M) b[u] = 0.0;
+                        c[u] = *reinterpret_cast<const double2 *>(C + min(kc, M - 2));
                     }
-                }
 #pragma unroll
-                for (int sp = 0; sp < NPASS; ++sp) {
-                    va[sp] -= a0 * vk[sp][0] + a1 * vk[sp][1] + a2 * vk[sp][2] + a3 * vk[sp][3];
-                    vb[sp] -= b0 * vk[sp][0] + b1 * vk[sp][1] + b2 * vk[sp][2] + b3 * vk[sp][3];
-                }
+                    for (int u = 0; u < BCR_CHUNK; ++u) bcr_dmma(c[u].x, c[u].y, a, b[u]);
 #pragma unroll
-                for (int sp = 0; sp < NPASS; ++sp) {
-                    if (kv[sp]) ra[kk[sp]] = va[sp];
-                    if (kv[sp] && hb) rb[kk[sp]] = vb[sp];
+                    for (int u = 0; u < BCR_CHUNK; ++u)
+                        if (cv[u]) *reinterpret_cast<double2 *>(C + k0 + 8 * (ct0 + u) + 2 * q) = c[u];
                 }
             }
         }
@@ -414,7 +442,7 @@ __device__ __forceinline__ void bcr_fence_async() { asm volatile("fence.proxy.as
 // (nbuf = 7, M <= 60) both sides' operands are fetched with the first bulk batch; with five, side 1 reuses side 0's.
 __global__ void __launch_bounds__(BCR_THREADS, 1) k_bcr_run(BcrView s) {
     extern __shared__ __align__(128) double bsm[];
-    const int M = s.M, MM = M * M, tid = threadIdx.x, nt = blockDim.x;
+    const int M = s.M, LD = s.ld, MM = M * LD, tid = threadIdx.x, nt = blockDim.x;  // MM: elements of a tile (M rows x LD)
     const unsigned tile_bytes = (unsigned)MM * 8u;
     double *Dm = bsm, *X = Dm + MM, *Z = X + MM;
     // operand tiles as OFFSETS into bsm (a pointer array would make the compiler lose the shared address space and fall
@@ -466,8 +494,8 @@ __global__ void __launch_bounds__(BCR_THREADS, 1) k_bcr_run(BcrView s) {
             for (int i = warp; i < M; i += nw) {
                 double a = 0.0;
                 for (int c = lane; c < M; c += 32) {
-                    if (hl) a += Wl[i * M + c] * ye0[c];
-                    if (hr) a += Wr[i * M + c] * ye1[c];
+                    if (hl) a += Wl[i * LD + c] * ye0[c];
+                    if (hr) a += Wr[i * LD + c] * ye1[c];
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -476,7 +504,7 @@ __global__ void __launch_bounds__(BCR_THREADS, 1) k_bcr_run(BcrView s) {
             __syncthreads();
             for (int i = warp; i < M; i += nw) {
                 double a = 0.0;
-                for (int r = i + lane; r < M; r += 32) a += Dm[i * M + r] * vv[r];
+                for (int r = i + lane; r < M; r += 32) a += Dm[i * LD + r] * vv[r];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
                 if (lane == 0) __stcg(s.xv + (size_t)it.node * M + i, a);
@@ -523,6 +551,7 @@ __global__ void __launch_bounds__(BCR_THREADS, 1) k_bcr_run(BcrView s) {
             bcr_mbar_wait(&ldbar, ph);
             ph ^= 1u;
             __syncthreads();
+            if (elim) BCR_MARK(12);
 #pragma unroll 1
             for (int sd = 0; sd < 2; ++sd) {
                 if (!act[sd]) continue;
@@ -540,32 +569,36 @@ __global__ void __launch_bounds__(BCR_THREADS, 1) k_bcr_run(BcrView s) {
                         ph ^= 1u;
                     }
                 }
-                if (mode[sd] == 1 && cb[sd] != 0) bcr_load_tile(OUT, s.pool + (size_t)ca[sd] * MM, M, true);  // rare: transposed coupling
+                if (mode[sd] == 1 && cb[sd] != 0) bcr_load_tile(OUT, s.pool + (size_t)ca[sd] * MM, M, LD, true);  // rare: transposed coupling
                 auto upd = [&](int i, int j, double v0, double v1) {
-                    double2 *d = reinterpret_cast<double2 *>(Dm + i * M + j);
+                    double2 *d = reinterpret_cast<double2 *>(Dm + i * LD + j);
                     double2 c = *d;
                     c.x -= v0; c.y -= v1;
                     *d = c;
                 };
-                auto neg_out = [&](int i, int j, double v0, double v1) { *reinterpret_cast<double2 *>(OUT + i * M + j) = make_double2(-v0, -v1); };
+                auto neg_out = [&](int i, int j, double v0, double v1) { *reinterpret_cast<double2 *>(OUT + i * LD + j) = make_double2(-v0, -v1); };
                 if (fused[sd]) {
-                    bcr_tn_pair(A1, A2, M, upd, neg_out);
-                    bcr_gemv_t_sub(A1, ye, bk, vv, M);
+                    if (elim) BCR_MARK(15);
+                    bcr_mma_tn<false, true>(A1, A1, A2, M, LD, upd, neg_out);
+                    __syncthreads();
+                    if (elim) BCR_MARK(13);
+                    bcr_gemv_t_sub(A1, ye, bk, vv, M, LD);
+                    if (elim) BCR_MARK(14);
                 } else if (us[sd] >= 0) {
-                    bcr_tn<false>(A1, A1, M, upd);
-                    bcr_gemv_t_sub(A1, ye, bk, vv, M);
+                    bcr_mma_tn<false, false>(A1, A1, A1, M, LD, upd, upd);
+                    bcr_gemv_t_sub(A1, ye, bk, vv, M, LD);
                 }
                 if (mode[sd] == 2 && !fused[sd]) {  // rare: a coupling carried over a level, its factors are not this level's W
                     __syncthreads();
-                    bcr_load_tile(A1, s.pool + (size_t)ca[sd] * MM, M, false);
-                    bcr_load_tile(A2, s.pool + (size_t)cb[sd] * MM, M, false);
+                    bcr_load_tile(A1, s.pool + (size_t)ca[sd] * MM, M, LD, false);
+                    bcr_load_tile(A2, s.pool + (size_t)cb[sd] * MM, M, LD, false);
                     __syncthreads();
-                    bcr_tn<false>(A1, A2, M, neg_out);
+                    bcr_mma_tn<false, false>(A1, A2, A2, M, LD, neg_out, neg_out);
                 }
             }
             __syncthreads();
             if (!elim) {
-                bcr_store_tile(s.pool + node_off, Dm, M);
+                bcr_store_tile(s.pool + node_off, Dm, MM);
                 for (int i = tid; i < M; i += nt) __stcg(s.bv + (size_t)it.node * M + i, bk[i]);
                 __syncthreads();
                 BCR_MARK(5);
@@ -577,24 +610,24 @@ __global__ void __launch_bounds__(BCR_THREADS, 1) k_bcr_run(BcrView s) {
                     __syncthreads();
                 }
                 double *U = BCR_OPA(0);
-                if (M <= 64) bcr_chol_inv<2>(Dm, U, vv, vv + 8 * M, M, s.info, s.prof);
-                else bcr_chol_inv<3>(Dm, U, vv, vv + 8 * M, M, s.info, s.prof);
+                if (M <= 64) bcr_chol_inv<2>(Dm, U, vv, vv + 8 * M, M, LD, s.info, s.prof);
+                else bcr_chol_inv<3>(Dm, U, vv, vv + 8 * M, M, LD, s.info, s.prof);
                 BCR_MARK(2);
                 // W_l = U^T X, W_r = U^T Z -> their pool tiles; y = U^T b; U -> the node's tile
-                if (hasL) {
-                    double *out = s.pool + (size_t)it.cl_slot * MM;
-                    bcr_tn<true>(U, X, M, [&](int i, int j, double v0, double v1) { __stcg(reinterpret_cast<double2 *>(out + (size_t)i * M + j), make_double2(v0, v1)); });
-                }
-                if (hasR) {
-                    double *out = s.pool + (size_t)it.cr_slot * MM;
-                    bcr_tn<true>(U, Z, M, [&](int i, int j, double v0, double v1) { __stcg(reinterpret_cast<double2 *>(out + (size_t)i * M + j), make_double2(v0, v1)); });
+                {
+                    double *outL = s.pool + (size_t)(hasL ? it.cl_slot : 0) * MM, *outR = s.pool + (size_t)(hasR ? it.cr_slot : 0) * MM;
+                    auto stL = [&](int i, int j, double v0, double v1) { __stcg(reinterpret_cast<double2 *>(outL + (size_t)i * LD + j), make_double2(v0, v1)); };
+                    auto stR = [&](int i, int j, double v0, double v1) { __stcg(reinterpret_cast<double2 *>(outR + (size_t)i * LD + j), make_double2(v0, v1)); };
+                    if (hasL && hasR) bcr_mma_tn<true, true>(U, X, Z, M, LD, stL, stR);
+                    else if (hasL) bcr_mma_tn<true, false>(U, X, X, M, LD, stL, stL);
+                    else if (hasR) bcr_mma_tn<true, false>(U, Z, Z, M, LD, stR, stR);
                 }
                 for (int i = tid; i < M; i += nt) {
                     double a = 0.0;
-                    for (int r = 0; r <= i; ++r) a += U[r * M + i] * bk[r];
+                    for (int r = 0; r <= i; ++r) a += U[r * LD + i] * bk[r];
                     __stcg(s.bv + (size_t)it.node * M + i, a);
                 }
-                bcr_store_tile(s.pool + node_off, U, M);
+                bcr_store_tile(s.pool + node_off, U, MM);
                 __syncthreads();
                 BCR_MARK(3);
                 if (s.prof && tid == 0) atomicAdd(s.prof + 6, 1ull);

@@ -49,6 +49,8 @@ struct BcrPlan {
     int n = 0;           // nodes
     int w = 0;           // half bandwidth in pose blocks
     int mb = 0, M = 0;   // pose blocks per node (padded), node dimension 6 * mb
+    int ld = 0;          // row stride of a tile (doubles): M, or M + 4 where M would put the rows of a 4-row operand fragment on the
+                         // same shared-memory banks (the DMMA fragment loads read 4 rows x 8 columns); a tile is M x ld
     int n_slots = 0;     // M x M tiles in the pool: [0, n) = D / U of the nodes, then couplings / W tiles
     int n_elim_items = 0;
     std::vector<int> blk_node, blk_loc;   // [nb] node and position inside the node of every pose block (-1: isolated)
@@ -94,6 +96,7 @@ inline void bcr_plan(int nb, const std::vector<int> &rowptr, const std::vector<i
     mb += mb & 1;  // even: the tile dimension 6 mb is a multiple of 4 (4x4 register tiles, 16-byte shared loads)
     if (6 * mb > BCR_MAX_M) return;
     Y.n = n; Y.w = w; Y.mb = mb; Y.M = 6 * mb;
+    Y.ld = (Y.M % 16 == 4 || Y.M % 16 == 12) ? Y.M : Y.M + 4;
     Y.blk_node.assign(nb, -1); Y.blk_loc.assign(nb, -1); Y.node_size.assign(n, 0);
     {
         int c = 0;
@@ -112,8 +115,8 @@ inline void bcr_plan(int nb, const std::vector<int> &rowptr, const std::vector<i
             const int d = (b - a + n) % n;
             if (!(d == 0 || d == 1 || d == n - 1)) return;
         }
-    const int M = Y.M;
-    const long long MM = (long long)M * M;
+    const int M = Y.ld;  // row stride of the tiles (the loader map below only needs the stride)
+    const long long MM = (long long)Y.M * Y.ld;
     // ---- level schedule
     struct Coup { int mode, a, b, rows; };  // mode 1: materialised slot a (rows = node `rows`); mode 2: product of eliminated node a
     struct ElimInfo { int item = -1, wl = -1, wr = -1; };
