@@ -231,7 +231,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"nproc": os.cpu_count()},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 SOLVERS = {"auto": "SOLVER_AUTO", "bcr": "SOLVER_BCR", "two_level": "SOLVER_BLOCK_PCG_2L", "block_jacobi": "SOLVER_BLOCK_PCG",
@@ -296,8 +296,12 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         p = vio.Problem(device=local_rank, stream=stream.cuda_stream)
         if world > 1:
-            p.set_shard(rank, world)
-            p.set_allreduce(importlib.import_module(PKG + ".dist").make_allreduce_hook())
+            vdist = importlib.import_module(PKG + ".dist")
+            if args.collective == "native":
+                vdist.init_native_nccl(p, rank, world)  # NCCL communicator inside libvio_b200.so, no Python in the loop
+            else:
+                p.set_shard(rank, world)
+                p.set_allreduce(vdist.make_allreduce_hook())
         t0 = time.perf_counter()
         p.set_graph(scene)
         t_pack = time.perf_counter() - t0
@@ -459,7 +463,7 @@ def run_ours(args):
             "config": {"workload": args.workload, **wl, "edges": E, "landmarks": L, "cameras": C,
                        "lm_flavour": "v17", "reduced_solver": solver_used, "reduced_solver_requested": args.solver,
                        "schedule": "Solve(K) from the perturbed initial state (natural LM damping schedule)",
-                       "parallelism": f"landmark_shard{world}", "l2": "inputs (>=520 MB of edge records) larger than L2",
+                       "parallelism": f"landmark_shard{world}", "collective": (args.collective if world > 1 else None), "l2": "inputs (>=520 MB of edge records) larger than L2",
                        "scene_gen_s": round(t_gen, 2), "pack_upload_s": round(t_pack, 2)},
             "lm": {"trial_steps": int(st.trial_steps), "accepted": int(st.accepted_steps),
                    "linearizations": int(st.linearizations), "pcg_iterations": int(st.pcg_iterations),
@@ -491,7 +495,7 @@ def run_ours(args):
             cb = cpu_reference_rate(vio, scene, steps=3, warmup=1, target_s=12.0)
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
                                     "sample": cb["sample"]}
-        print(json.dumps(line))
+        emit(line)
         if parity is not None and not parity["ok"]:
             sys.stderr.write("parity_vs_n1 FAILED: %s\n" % json.dumps(parity))
             if dist is not None:
@@ -503,7 +507,26 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of this run, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: native libraries (NCCL prints its version banner with printf at communicator
+    # creation) get stderr as their fd 1 for the whole run, the JSON goes to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -514,6 +537,8 @@ def main():
     ap.add_argument("--solver", "--pcg", dest="solver", default="auto", choices=list(SOLVERS),
                     help="reduced solver on the block-sparse S: auto (= block cyclic reduction on a camera ring), bcr, block PCG "
                          "with the two-level or the plain block-Jacobi preconditioner, or the block-sparse Cholesky")
+    ap.add_argument("--collective", default="native", choices=["native", "hook"],
+                    help="N > 1: native = NCCL called from inside libvio_b200.so (vio_nccl_init); hook = torch.distributed callback")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the unsharded re-solve on rank 0 (parity_vs_n1)")
     ap.add_argument("--pcg-max-iter", type=int, default=0, help="cap PCG iterations (profiling runs only; 0 = 2P like the reference)")
     args = ap.parse_args()

@@ -207,6 +207,18 @@ int vio_device_count(void);
 int vio_set_graph(vio_problem *p, const vio_graph *g);
 int vio_get_dims(const vio_problem *p, vio_dims *out);
 int vio_set_allreduce(vio_problem *p, vio_allreduce_fn fn, void *user);
+/* Native multi-GPU path: one process (or thread) per GPU, NCCL over NVLink / NVSwitch, no callback into the host
+ * language.  The library loads libnccl.so.2 at run time (dlopen; VIO_ERR_UNSUPPORTED when it is absent) and issues its
+ * collectives (one all-reduce of the reduced system per linearisation, three scalar all-reduces per trial step) on the
+ * handle's stream.
+ *   vio_nccl_unique_id : rank 0 creates the 128-byte ncclUniqueId; the caller ships it to the other ranks (MPI, a file,
+ *                        torch.distributed.broadcast_object_list, ...)
+ *   vio_nccl_init      : collective over all ranks - creates the communicator (owned by the handle) and sets the
+ *                        landmark shard (rank, world); call before vio_set_graph
+ *   vio_set_nccl_comm  : adopt an existing ncclComm_t (passed as void*) created elsewhere with the same libnccl      */
+int vio_nccl_unique_id(void *id128);
+int vio_nccl_init(vio_problem *p, int rank, int world, const void *id128);
+int vio_set_nccl_comm(vio_problem *p, void *nccl_comm, int rank, int world);
 /* landmark sharding (call before vio_set_graph with the FULL graph on every rank): rank r keeps a
  * contiguous, edge-balanced range of landmarks and their observations; pose-class vertices, the
  * reduced-system sparsity pattern and the LM scalars are replicated. Pose-only factors (SE3 prior,

@@ -92,6 +92,7 @@ EXPORTS = [
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
     "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
     "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_get_coarse", "vio_preintegrate", "vio_get_solver_ms", "vio_set_points", "vio_get_points", "vio_get_point_system", "vio_marginalize",
+    "vio_nccl_unique_id", "vio_nccl_init", "vio_set_nccl_comm",
 ]
 
 _lib = None
@@ -122,6 +123,9 @@ def lib():
         L.vio_get_dims.argtypes = [C.c_void_p, C.POINTER(VioDims)]
         L.vio_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p]
         L.vio_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.vio_nccl_unique_id.argtypes = [C.c_void_p]
+        L.vio_nccl_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.vio_set_nccl_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.vio_set_prior.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, C.c_int32, _dp, _dp]
         L.vio_get_prior.argtypes = [C.c_void_p, _dp, _dp]
         L.vio_set_vertices.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -360,6 +364,12 @@ class Problem:
     def set_shard(self, rank, world):
         self._ck(self._L.vio_set_shard(self._h, rank, world))
 
+    def nccl_init(self, rank, world, unique_id):
+        """Native NCCL path: create the communicator inside libvio_b200.so (collective over all ranks) and set the shard.
+        unique_id: the 128 bytes of nccl_unique_id() made on rank 0 and shipped to every rank by the caller."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self._L.vio_nccl_init(self._h, rank, world, buf))
+
     def set_allreduce(self, pyfunc):
         """pyfunc(dev_ptr:int, count:int, stream:int) -> 0 on success."""
         self._cb = ALLREDUCE_FN(lambda ptr, n, st, user: int(pyfunc(ptr, n, st) or 0))
@@ -525,6 +535,15 @@ class Problem:
 
     def launch_count(self):
         return int(self._L.vio_launch_count(self._h))
+
+
+def nccl_unique_id():
+    """128-byte ncclUniqueId from the libnccl.so.2 the library loaded (call on rank 0, broadcast to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().vio_nccl_unique_id(buf)
+    if rc != VIO_OK:
+        raise VioError(rc, "vio_nccl_unique_id (libnccl.so.2 not loadable?)")
+    return buf.raw
 
 
 def solve_batched(scenes, iterations, opts=None, device=0, n_workers=16, lockstep=False, max_chunk=0):

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include "../../include/vio_b200.h"
 #include "vio_host.h"
@@ -38,6 +39,42 @@
 
 namespace {
 
+// ---- NCCL, loaded at run time (no link-time dependency: single-GPU users need no NCCL) ----------------------------
+struct VioNcclId { char internal[128]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(VioNcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, VioNcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+const int VIO_NCCL_FLOAT64 = 8, VIO_NCCL_SUM = 0;  // ncclDataType_t / ncclRedOp_t values of nccl.h
+NcclApi &nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // the soname first: inside a process that already loaded a libnccl.so.2 (e.g. PyTorch's bundled copy) this
+        // returns that very library
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.GetUniqueId = (int (*)(VioNcclId *))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void **, int, VioNcclId, int))dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (int (*)(void *))dlsym(api.lib, "ncclCommDestroy");
+        api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+        api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+        api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather;
+    });
+    return api;
+}
+
 struct EvPair {
     cudaEvent_t a, b;
 };
@@ -56,6 +93,8 @@ struct vio_problem {
     int64_t launches = 0;
     vio_allreduce_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
+    void *nccl_comm = nullptr;  // ncclComm_t (vio_nccl_init / vio_set_nccl_comm); takes precedence over the hook
+    bool nccl_owned = false;
     int shard_rank = 0, shard_world = 1;
 
     // sizes
@@ -309,6 +348,20 @@ int resolve_solver(vio_problem *p, const vio_lm_opts &o) {
     return o.flavour == VIO_LM_V15 ? VIO_SOLVER_REF_PCG : VIO_SOLVER_DENSE_CHOL;
 }
 
+// in-place sum over the ranks of `count` doubles at device pointer ptr, ordered on the handle's stream
+bool is_sharded(const vio_problem *p) { return p->shard_world > 1 && (p->nccl_comm || p->allreduce); }
+int dist_sum(vio_problem *p, double *ptr, int64_t count) {
+    if (p->nccl_comm) {
+        NcclApi &api = nccl_api();
+        const int rc = api.AllReduce(ptr, ptr, (size_t)count, VIO_NCCL_FLOAT64, VIO_NCCL_SUM, p->nccl_comm, p->stream);
+        if (rc != 0) return fail(p, VIO_ERR_CUDA, "ncclAllReduce failed: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
+        return VIO_OK;
+    }
+    const int rc = p->allreduce(ptr, count, (void *)p->stream, p->allreduce_user);
+    if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+    return VIO_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // linearise: MakeHessian + Schur (+ all-reduce of the reduced system when sharded)
 // ---------------------------------------------------------------------------------------------
@@ -374,9 +427,9 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
             p->launches++;
         }
     }
-    if (p->allreduce && p->shard_world > 1) {
-        int rc = p->allreduce(p->sys.p, (int64_t)sys_n, (void *)p->stream, p->allreduce_user);
-        if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+    if (is_sharded(p)) {
+        const int rc = dist_sum(p, p->sys.p, (int64_t)sys_n);
+        if (rc) return rc;
     }
     if (p->storage == VIO_STORAGE_DENSE) {
         dim3 b(32, 8), g((p->Pper + 31) / 32, (p->Pper + 7) / 8, p->batch);
@@ -424,10 +477,10 @@ int do_chi2(vio_problem *p, const vio_lm_opts &o, double *out) {
             p->launches++;
         }
     }
-    if (p->allreduce && p->shard_world > 1) {
+    if (is_sharded(p)) {
         // scal[0] + scal[1] are contiguous
-        int rc = p->allreduce(p->scal.p, 2, (void *)p->stream, p->allreduce_user);
-        if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+        const int rc = dist_sum(p, p->scal.p, 2);
+        if (rc) return rc;
     }
     CK(cudaMemcpyAsync(p->h_scal, p->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
@@ -450,13 +503,13 @@ int do_maxdiag(vio_problem *p, double *out) {
     CK(cudaMemcpyAsync(p->h_scal + 2, p->scal.p + 2, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     double m = p->h_scal[2];
-    if (p->allreduce && p->shard_world > 1) {
-        // max over ranks through the sum hook: one-hot slots
+    if (is_sharded(p)) {
+        // max over ranks through the sum: one-hot slots
         std::vector<double> slots(p->shard_world, 0.0);
         slots[p->shard_rank] = m;
         CK(cudaMemcpyAsync(p->partial.p, slots.data(), slots.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-        int rc = p->allreduce(p->partial.p, p->shard_world, (void *)p->stream, p->allreduce_user);
-        if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+        const int rc = dist_sum(p, p->partial.p, p->shard_world);
+        if (rc) return rc;
         CK(cudaMemcpyAsync(slots.data(), p->partial.p, slots.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         CK(cudaStreamSynchronize(p->stream));
         for (double s : slots) m = std::max(m, s);
@@ -793,9 +846,9 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p + 1280, 256, p->scal.p + 5, 1);
         p->launches += 3;
     }
-    if (p->allreduce && p->shard_world > 1) {
-        int rc = p->allreduce(p->scal.p + 4, 2, (void *)p->stream, p->allreduce_user);
-        if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+    if (is_sharded(p)) {
+        const int rc = dist_sum(p, p->scal.p + 4, 2);
+        if (rc) return rc;
     }
     {
         const int g = grid_for(p->P, 256, 64);
@@ -939,6 +992,7 @@ void vio_destroy(vio_problem *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
+    if (p->nccl_comm && p->nccl_owned) nccl_api().CommDestroy(p->nccl_comm);
     for (auto *vec : {&p->ev_lin, &p->ev_pcg, &p->ev_coarse})
         for (auto &e : *vec) {
             cudaEventDestroy(e.a);
@@ -959,6 +1013,47 @@ int vio_set_allreduce(vio_problem *p, vio_allreduce_fn fn, void *user) {
     if (!p) return VIO_ERR_INVALID;
     p->allreduce = fn;
     p->allreduce_user = user;
+    return VIO_OK;
+}
+
+int vio_nccl_unique_id(void *id128) {
+    if (!id128) return VIO_ERR_INVALID;
+    NcclApi &api = nccl_api();
+    if (!api.ok) return VIO_ERR_UNSUPPORTED;
+    VioNcclId id;
+    if (api.GetUniqueId(&id) != 0) return VIO_ERR_CUDA;
+    memcpy(id128, id.internal, sizeof(id.internal));
+    return VIO_OK;
+}
+
+int vio_nccl_init(vio_problem *p, int rank, int world, const void *id128) {
+    if (!p || !id128 || world < 1 || rank < 0 || rank >= world) return VIO_ERR_INVALID;
+    NcclApi &api = nccl_api();
+    if (!api.ok) return fail(p, VIO_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+    CK(cudaSetDevice(p->device));
+    if (p->nccl_comm && p->nccl_owned) api.CommDestroy(p->nccl_comm);
+    p->nccl_comm = nullptr;
+    VioNcclId id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    void *comm = nullptr;
+    const int rc = api.CommInitRank(&comm, world, id, rank);
+    if (rc != 0) return fail(p, VIO_ERR_CUDA, "ncclCommInitRank failed: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
+    p->nccl_comm = comm;
+    p->nccl_owned = true;
+    p->shard_rank = rank;
+    p->shard_world = world;
+    return VIO_OK;
+}
+
+int vio_set_nccl_comm(vio_problem *p, void *nccl_comm, int rank, int world) {
+    if (!p || world < 1 || rank < 0 || rank >= world) return VIO_ERR_INVALID;
+    NcclApi &api = nccl_api();
+    if (nccl_comm && !api.ok) return fail(p, VIO_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+    if (p->nccl_comm && p->nccl_owned) api.CommDestroy(p->nccl_comm);
+    p->nccl_comm = nccl_comm;
+    p->nccl_owned = false;
+    p->shard_rank = rank;
+    p->shard_world = world;
     return VIO_OK;
 }
 

@@ -35,6 +35,20 @@ def make_allreduce_hook():
     return hook
 
 
+def init_native_nccl(problem, rank=None, world=None):
+    """Native collectives: libvio_b200.so creates its own NCCL communicator (vio_nccl_init) and issues every all-reduce of
+    the solve itself on the handle's stream - no callback into Python.  torch.distributed (any backend) is only used once,
+    to ship rank 0's 128-byte ncclUniqueId to the other ranks.  Call on every rank before set_graph."""
+    import torch.distributed as dist
+    from . import capi
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    box = [capi.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    problem.nccl_init(rank, world, box[0])
+    return problem
+
+
 def shard_ranges(edge_ptr, world):
     """Landmark cut points used by vio_set_shard: contiguous ranges balanced by edge count.
 
