@@ -345,33 +345,12 @@ int emul_bchol_solve(int nb, const int *rowptr_, const int *col_, const double *
 
 // Block cyclic reduction (vio_bcr.h): the host plan of the product interpreted sequentially on the CPU with plain dense
 // loops - the same items, slots, couplings and update rules the persistent device kernel (vio_bcr.cuh) executes.
-// val: BSR values (nnzb x 36); returns x = (A + lambda I)^-1 b.  info[0..5] = n, w, M, levels, items, slots.
-int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *val, double lambda, const double *b, double *x,
-                   int *info) {
-    std::vector<int> rowptr(rowptr_, rowptr_ + nb + 1), col(col_, col_ + rowptr_[nb]);
-    BcrPlan Y;
-    bcr_plan(nb, rowptr, col, Y);
-    if (!Y.ok) return VIO_ERR_UNSUPPORTED;
-    const int n = Y.n, M = Y.M, LD = Y.ld;  // tiles are M x LD (row stride LD)
+namespace {
+// items [first, last) of a schedule over tiles of M rows x LD; xpool = export pool (open chains), done = per-item flags
+int bcr_run_items(const std::vector<BcrItem> &items, int first, int last, std::vector<char> &done, int M, int LD, std::vector<double> &pool,
+                  std::vector<double> &bv, std::vector<double> &xv, std::vector<double> *xpool) {
     const size_t MM = (size_t)M * LD;
-    if (info) { info[0] = n; info[1] = Y.w; info[2] = M; info[3] = Y.n_levels; info[4] = (int)Y.items.size(); info[5] = Y.n_slots; }
-    std::vector<double> pool(MM * Y.n_slots, 0.0), bv((size_t)n * M, 0.0), xv((size_t)n * M, 0.0);
-    // loader: BSR blocks -> node tiles, lambda and identity padding on the diagonal
-    for (int i = 0; i < nb; ++i)
-        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
-            if (Y.dst[k] < 0) continue;
-            const bool dg = (Y.dst[k] & BCR_DST_DIAG) != 0;
-            const size_t off = (size_t)(Y.dst[k] & ~BCR_DST_DIAG);
-            for (int e = 0; e < 36; ++e)
-                pool[off + (size_t)(e / 6) * LD + e % 6] = val[36 * (size_t)k + e] + ((dg && e % 7 == 0) ? lambda : 0.0);
-        }
-    for (int a = 0; a < n; ++a)
-        for (int q = 6 * Y.node_size[a]; q < M; ++q) pool[(size_t)a * MM + (size_t)q * LD + q] = 1.0;
-    for (int i = 0; i < nb; ++i)
-        if (Y.blk_node[i] >= 0)
-            for (int c = 0; c < 6; ++c) bv[(size_t)Y.blk_node[i] * M + 6 * Y.blk_loc[i] + c] = b[6 * (size_t)i + c];
-    std::vector<char> done(Y.items.size(), 0);
-    std::vector<double> Dm(MM), X(MM), Z(MM), U(MM), T(MM), t(M);
+    std::vector<double> Dm(MM), X(MM), Z(MM), U(MM), t(M);
     auto tn = [&](const double *A, const double *B, double *C, double sign, bool accumulate) {  // C (+)= sign * A^T B
         for (int i = 0; i < M; ++i)
             for (int j = 0; j < M; ++j) {
@@ -380,10 +359,16 @@ int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *va
                 C[(size_t)i * LD + j] = (accumulate ? C[(size_t)i * LD + j] : 0.0) + sign * acc;
             }
     };
-    for (size_t q = 0; q < Y.items.size(); ++q) {
-        const BcrItem &it = Y.items[q];
+    for (int q = first; q < last; ++q) {
+        const BcrItem &it = items[q];
         for (int d : it.dep)
             if (d >= 0 && !done[d]) return VIO_ERR_STATE;  // the order must satisfy every dependency
+        if (it.kind & BCR_EXPORT) {
+            if (!xpool) return VIO_ERR_STATE;
+            tn(&pool[(size_t)it.cl_a * MM], &pool[(size_t)it.cl_b * MM], &(*xpool)[(size_t)it.cl_slot * MM], -1.0, false);
+            done[q] = 1;
+            continue;
+        }
         double *bk = &bv[(size_t)it.node * M];
         if (it.kind & BCR_BACKSUB) {
             const double *Uk = &pool[(size_t)it.node * MM];
@@ -457,30 +442,155 @@ int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *va
         std::copy(U.begin(), U.end(), pool.begin() + (size_t)it.node * MM);
         done[q] = 1;
     }
+    return VIO_OK;
+}
+
+// isolated pose block i: 6x6 solve of (S_ii + lambda I) x = b_i
+int bcr_solve_iso(int i, const std::vector<int> &rowptr, const std::vector<int> &col, const double *val, double lambda, const double *b, double *x) {
+    double A[36], y[6];
+    int kd = -1;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) if (col[k] == i) kd = k;
+    for (int e = 0; e < 36; ++e) A[e] = (kd >= 0 ? val[36 * (size_t)kd + e] : 0.0) + (e % 7 == 0 ? lambda : 0.0);
+    for (int c = 0; c < 6; ++c) y[c] = b[6 * (size_t)i + c];
+    for (int c = 0; c < 6; ++c) {  // Gaussian elimination without pivoting (SPD)
+        if (!(A[7 * c] > 0.0)) return VIO_ERR_INVALID;
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = A[6 * r + c] / A[7 * c];
+            for (int k = c; k < 6; ++k) A[6 * r + k] -= f * A[6 * c + k];
+            y[r] -= f * y[c];
+        }
+    }
+    for (int c = 5; c >= 0; --c) {
+        double a = y[c];
+        for (int k = c + 1; k < 6; ++k) a -= A[6 * c + k] * x[6 * (size_t)i + k];
+        x[6 * (size_t)i + c] = a / A[7 * c];
+    }
+    return VIO_OK;
+}
+}  // namespace
+
+// val: BSR values (nnzb x 36); returns x = (A + lambda I)^-1 b.  info[0..5] = n, w, M, levels, items, slots.
+int emul_bcr_solve(int nb, const int *rowptr_, const int *col_, const double *val, double lambda, const double *b, double *x,
+                   int *info) {
+    std::vector<int> rowptr(rowptr_, rowptr_ + nb + 1), col(col_, col_ + rowptr_[nb]);
+    BcrPlan Y;
+    bcr_plan(nb, rowptr, col, Y);
+    if (!Y.ok) return VIO_ERR_UNSUPPORTED;
+    const int n = Y.n, M = Y.M, LD = Y.ld;  // tiles are M x LD (row stride LD)
+    const size_t MM = (size_t)M * LD;
+    if (info) { info[0] = n; info[1] = Y.w; info[2] = M; info[3] = Y.n_levels; info[4] = (int)Y.items.size(); info[5] = Y.n_slots; }
+    std::vector<double> pool(MM * Y.n_slots, 0.0), bv((size_t)n * M, 0.0), xv((size_t)n * M, 0.0);
+    // loader: BSR blocks -> node tiles, lambda and identity padding on the diagonal
+    for (int i = 0; i < nb; ++i)
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (Y.dst[k] < 0) continue;
+            const bool dg = (Y.dst[k] & BCR_DST_DIAG) != 0;
+            const size_t off = (size_t)(Y.dst[k] & ~BCR_DST_DIAG);
+            for (int e = 0; e < 36; ++e)
+                pool[off + (size_t)(e / 6) * LD + e % 6] = val[36 * (size_t)k + e] + ((dg && e % 7 == 0) ? lambda : 0.0);
+        }
+    for (int a = 0; a < n; ++a)
+        for (int q = 6 * Y.node_size[a]; q < M; ++q) pool[(size_t)a * MM + (size_t)q * LD + q] = 1.0;
+    for (int i = 0; i < nb; ++i)
+        if (Y.blk_node[i] >= 0)
+            for (int c = 0; c < 6; ++c) bv[(size_t)Y.blk_node[i] * M + 6 * Y.blk_loc[i] + c] = b[6 * (size_t)i + c];
+    std::vector<char> done(Y.items.size(), 0);
+    int rc = bcr_run_items(Y.items, 0, (int)Y.items.size(), done, M, LD, pool, bv, xv, nullptr);
+    if (rc) return rc;
     for (int i = 0; i < nb; ++i) {
         if (Y.blk_node[i] >= 0) {
             for (int c = 0; c < 6; ++c) x[6 * (size_t)i + c] = xv[(size_t)Y.blk_node[i] * M + 6 * Y.blk_loc[i] + c];
         } else {
-            // isolated pose block: 6x6 solve of (S_ii + lambda I) x = b_i
-            double A[36], y[6];
-            int kd = -1;
-            for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) if (col[k] == i) kd = k;
-            for (int e = 0; e < 36; ++e) A[e] = (kd >= 0 ? val[36 * (size_t)kd + e] : 0.0) + (e % 7 == 0 ? lambda : 0.0);
-            for (int c = 0; c < 6; ++c) y[c] = b[6 * (size_t)i + c];
-            for (int c = 0; c < 6; ++c) {  // Gaussian elimination without pivoting (SPD)
-                if (!(A[7 * c] > 0.0)) return VIO_ERR_INVALID;
-                for (int r = c + 1; r < 6; ++r) {
-                    const double f = A[6 * r + c] / A[7 * c];
-                    for (int k = c; k < 6; ++k) A[6 * r + k] -= f * A[6 * c + k];
-                    y[r] -= f * y[c];
-                }
-            }
-            for (int c = 5; c >= 0; --c) {
-                double a = y[c];
-                for (int k = c + 1; k < 6; ++k) a -= A[6 * c + k] * x[6 * (size_t)i + k];
-                x[6 * (size_t)i + c] = a / A[7 * c];
-            }
+            rc = bcr_solve_iso(i, rowptr, col, val, lambda, b, x);
+            if (rc) return rc;
         }
+    }
+    return VIO_OK;
+}
+
+// The multi-GPU variant (BcrDistPlan) with the `world` ranks played one after the other: every rank gets a SHARE of S and b
+// (blocks inside an interface node are split between its two neighbouring ranks, like the landmark shards split them),
+// eliminates its own open chain, exports its part of the interface system; the parts are summed (the all-reduce), the
+// interface system is solved, every rank back-substitutes its interior.
+int emul_bcr_dist_solve(int nb, const int *rowptr_, const int *col_, const double *val, double lambda, const double *b, int world, double *x) {
+    std::vector<int> rowptr(rowptr_, rowptr_ + nb + 1), col(col_, col_ + rowptr_[nb]);
+    BcrPlan P;
+    bcr_plan(nb, rowptr, col, P);
+    if (!P.ok) return VIO_ERR_UNSUPPORTED;
+    const int n = P.n, M = P.M, LD = P.ld;
+    const size_t MM = (size_t)M * LD;
+    std::vector<BcrDistPlan> D(world);
+    for (int r = 0; r < world; ++r) {
+        bcr_dist_plan(P, rowptr, col, r, world, D[r]);
+        if (!D[r].ok) return VIO_ERR_UNSUPPORTED;
+    }
+    const BcrSched &I = D[0].iface;
+    // interface pool: tiles [0, world) = D of the interface nodes, [world, 2 world) = their couplings, then W tiles
+    std::vector<double> ipool(MM * I.n_slots, 0.0), ibv((size_t)world * M, 0.0), ixv((size_t)world * M, 0.0);
+    struct RankState { std::vector<double> pool, bv, xv; std::vector<char> done; };
+    std::vector<RankState> R(world);
+    // which rank's share a block (or b entry) of an interface node goes to: 30 % to the rank that sees it as its LAST local node
+    for (int r = 0; r < world; ++r) {
+        const BcrDistPlan &d = D[r];
+        const int m = d.m;
+        RankState &S = R[r];
+        S.pool.assign(MM * d.local.n_slots, 0.0); S.bv.assign((size_t)(m + 1) * M, 0.0); S.xv.assign((size_t)(m + 1) * M, 0.0);
+        S.done.assign(d.local.items.size(), 0);
+        for (int i = 0; i < nb; ++i)
+            for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+                if (d.dst[k] < 0) continue;
+                const bool dg = (d.dst[k] & BCR_DST_DIAG) != 0;
+                const size_t off = (size_t)(d.dst[k] & ~BCR_DST_DIAG);
+                const int a = d.blk_lnode[i], bb = d.blk_lnode[col[k]];
+                double share = 1.0;
+                if (a == bb && a == 0) share = 0.7;
+                if (a == bb && a == m) share = 0.3;
+                for (int e = 0; e < 36; ++e)
+                    S.pool[off + (size_t)(e / 6) * LD + e % 6] = share * val[36 * (size_t)k + e] + ((dg && e % 7 == 0) ? lambda : 0.0);
+            }
+        for (int j = 0; j < m; ++j) {  // identity padding of ragged OWNED nodes
+            const int a = (d.lo + j) % n;
+            for (int q = 6 * P.node_size[a]; q < M; ++q) S.pool[(size_t)j * MM + (size_t)q * LD + q] = 1.0;
+        }
+        for (int i = 0; i < nb; ++i) {
+            const int j = d.blk_lnode[i];
+            if (j < 0) continue;
+            const double share = j == 0 ? 0.7 : (j == m ? 0.3 : 1.0);
+            for (int c = 0; c < 6; ++c) S.bv[(size_t)j * M + 6 * P.blk_loc[i] + c] = share * b[6 * (size_t)i + c];
+        }
+        std::vector<double> contrib(MM * 2 * world, 0.0);
+        int rc = bcr_run_items(d.local.items, 0, d.local.n_elim_items, S.done, M, LD, S.pool, S.bv, S.xv, &contrib);
+        if (rc) return rc;
+        // the two end nodes' D and b are this rank's share of interface nodes r and r+1
+        const int ia = r, ib = (r + 1) % world;
+        for (size_t e = 0; e < MM; ++e) { contrib[(size_t)ia * MM + e] += S.pool[e]; contrib[(size_t)ib * MM + e] += S.pool[(size_t)m * MM + e]; }
+        for (size_t e = 0; e < contrib.size(); ++e) ipool[e] += contrib[e];  // the all-reduce
+        for (int c = 0; c < M; ++c) { ibv[(size_t)ia * M + c] += S.bv[c]; ibv[(size_t)ib * M + c] += S.bv[(size_t)m * M + c]; }
+    }
+    {
+        std::vector<char> done(I.items.size(), 0);
+        int rc = bcr_run_items(I.items, 0, (int)I.items.size(), done, M, LD, ipool, ibv, ixv, nullptr);
+        if (rc) return rc;
+    }
+    std::vector<char> have(nb, 0);
+    for (int r = 0; r < world; ++r) {
+        const BcrDistPlan &d = D[r];
+        RankState &S = R[r];
+        const int m = d.m;
+        for (int c = 0; c < M; ++c) { S.xv[c] = ixv[(size_t)r * M + c]; S.xv[(size_t)m * M + c] = ixv[(size_t)((r + 1) % world) * M + c]; }
+        int rc = bcr_run_items(d.local.items, d.local.n_elim_items, (int)d.local.items.size(), S.done, M, LD, S.pool, S.bv, S.xv, nullptr);
+        if (rc) return rc;
+        for (int i = 0; i < nb; ++i) {
+            const int j = d.blk_lnode[i];
+            if (j < 0 || j >= m) continue;  // owned nodes only
+            for (int c = 0; c < 6; ++c) x[6 * (size_t)i + c] = S.xv[(size_t)j * M + 6 * P.blk_loc[i] + c];
+            have[i] = 1;
+        }
+    }
+    for (int i = 0; i < nb; ++i) {
+        if (P.blk_node[i] >= 0) { if (!have[i]) return VIO_ERR_STATE; continue; }
+        int rc = bcr_solve_iso(i, rowptr, col, val, lambda, b, x);
+        if (rc) return rc;
     }
     return VIO_OK;
 }

@@ -282,3 +282,30 @@ def test_block_cyclic_reduction_rejects_other_patterns():
         rc = L.emul_bcr_solve(nb, rowptr.ctypes.data_as(ip), col.ctypes.data_as(ip), val.ctypes.data_as(dp), 0.1,
                               b.ctypes.data_as(dp), x.ctypes.data_as(dp), None)
         assert rc == capi.VIO_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("nb,w,closed,iso,world", [(80, 4, True, (), 2), (81, 4, True, (0,), 2), (130, 10, True, (0,), 2), (160, 5, True, (), 4),
+                                                   (163, 5, True, (7,), 4), (240, 5, True, (), 8), (250, 5, True, (), 8), (96, 3, False, (), 4),
+                                                   (90, 3, True, (), 3), (64, 4, True, (), 8)])
+def test_block_cyclic_reduction_multi_rank_plan(nb, w, closed, iso, world):
+    """Host logic of the multi-GPU reduced solve (csrc/vio_bcr.h: BcrDistPlan): every rank eliminates the open chain of its
+    own nodes between two pinned interface nodes, the interface system is summed over the ranks and solved, the interiors
+    are back-substituted.  Played rank after rank on the CPU (tests/host_emul.cu::emul_bcr_dist_solve) it solves the same
+    random SPD band systems as the single-rank plan, with the interface nodes' blocks split between neighbouring ranks."""
+    rng = np.random.default_rng(77 * nb + world)
+    A, rowptr, col, val = _band_system(nb, w, closed, set(iso), rng)
+    b = rng.normal(size=6 * nb)
+    x = np.zeros(6 * nb)
+    L = emul.lib()
+    ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    L.emul_bcr_dist_solve.argtypes = [C.c_int, ip, ip, dp, C.c_double, dp, C.c_int, dp]
+    lam = 0.17
+    rc = L.emul_bcr_dist_solve(nb, rowptr.ctypes.data_as(ip), col.ctypes.data_as(ip), val.ctypes.data_as(dp), lam,
+                               b.ctypes.data_as(dp), world, x.ctypes.data_as(dp))
+    nc = nb - len(iso)
+    if (nc // w) < 2 * world:
+        assert rc == importlib.import_module("visual-inertial-odometry_b200").capi.VIO_ERR_UNSUPPORTED
+        return
+    assert rc == 0, rc
+    ref = np.linalg.solve(A + lam * np.eye(6 * nb), b)
+    assert np.abs(x - ref).max() <= 1e-11 * np.abs(ref).max()
