@@ -347,11 +347,9 @@ def run_ours(args):
         sharded = None
         if world > 1 and not args.no_parity:
             pose_n, _, invd_n = p.get_vertices()
-            # landmarks this rank owns (the others keep their initial values in get_vertices): the packer's edge-balanced cut
-            edge_ptr = np.searchsorted(scene.rp_landmark, np.arange(L + 1), side="left")
-            cuts = importlib.import_module(PKG + ".dist").shard_ranges(edge_ptr, world)
+            # landmarks this rank owns (the others keep their initial values in get_vertices)
             owned = np.zeros(L, bool)
-            owned[cuts[rank]:cuts[rank + 1]] = True
+            owned[p.owned_landmarks()] = True
             sharded = {"pose": pose_n, "invd": invd_n, "owned": owned, "trace": list(st.chi2_trace[:st.n_trace]),
                        "chi2_final": st.chi2_final, "iterations": st.iterations}
         # ---- end to end through the C-ABI with host state buffers -------------------------------------------
@@ -463,7 +461,7 @@ def run_ours(args):
             "config": {"workload": args.workload, **wl, "edges": E, "landmarks": L, "cameras": C,
                        "lm_flavour": "v17", "reduced_solver": solver_used, "reduced_solver_requested": args.solver,
                        "schedule": "Solve(K) from the perturbed initial state (natural LM damping schedule)",
-                       "parallelism": f"landmark_shard{world}", "collective": (args.collective if world > 1 else None), "l2": "inputs (>=520 MB of edge records) larger than L2",
+                       "parallelism": f"landmark_shard{world}" + ("+distributed_reduced_solve" if (world > 1 and st.solver_used == capi.SOLVER_BCR and os.environ.get("VIO_B200_SHARD_LEGACY") is None) else ""), "collective": (args.collective if world > 1 else None), "l2": "inputs (>=520 MB of edge records) larger than L2",
                        "scene_gen_s": round(t_gen, 2), "pack_upload_s": round(t_pack, 2)},
             "lm": {"trial_steps": int(st.trial_steps), "accepted": int(st.accepted_steps),
                    "linearizations": int(st.linearizations), "pcg_iterations": int(st.pcg_iterations),

@@ -206,6 +206,9 @@ int vio_device_count(void);
 /* ---- graph / state -------------------------------------------------------------------------- */
 int vio_set_graph(vio_problem *p, const vio_graph *g);
 int vio_get_dims(const vio_problem *p, vio_dims *out);
+/* the caller's landmark indices this handle (rank) owns, in its packed order (all landmarks when unsharded): at most `cap`
+ * entries are written, *count receives their number */
+int vio_get_owned_landmarks(const vio_problem *p, int32_t *out, int64_t cap, int64_t *count);
 int vio_set_allreduce(vio_problem *p, vio_allreduce_fn fn, void *user);
 /* Native multi-GPU path: one process (or thread) per GPU, NCCL over NVLink / NVSwitch, no callback into the host
  * language.  The library loads libnccl.so.2 at run time (dlopen; VIO_ERR_UNSUPPORTED when it is absent) and issues its

@@ -92,7 +92,7 @@ EXPORTS = [
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
     "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
     "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_get_coarse", "vio_preintegrate", "vio_get_solver_ms", "vio_set_points", "vio_get_points", "vio_get_point_system", "vio_marginalize",
-    "vio_nccl_unique_id", "vio_nccl_init", "vio_set_nccl_comm",
+    "vio_nccl_unique_id", "vio_nccl_init", "vio_set_nccl_comm", "vio_get_owned_landmarks",
 ]
 
 _lib = None
@@ -363,6 +363,15 @@ class Problem:
 
     def set_shard(self, rank, world):
         self._ck(self._L.vio_set_shard(self._h, rank, world))
+
+    def owned_landmarks(self):
+        """Indices (into the scene's landmark arrays) of the landmarks this handle / rank owns."""
+        n = C.c_int64()
+        self._L.vio_get_owned_landmarks.argtypes = [C.c_void_p, _ip, C.c_int64, C.POINTER(C.c_int64)]
+        self._ck(self._L.vio_get_owned_landmarks(self._h, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), np.int32)
+        self._ck(self._L.vio_get_owned_landmarks(self._h, out.ctypes.data_as(_ip), n.value, C.byref(n)))
+        return out[:n.value]
 
     def nccl_init(self, rank, world, unique_id):
         """Native NCCL path: create the communicator inside libvio_b200.so (collective over all ranks) and set the shard.

@@ -188,6 +188,18 @@ struct vio_problem {
     DBuf<int> bcr_blk_node, bcr_blk_loc, bcr_node_size;
     DBuf<double> bcr_pool, bcr_bv, bcr_xv;
     DBuf<unsigned> bcr_flags;
+    // multi-GPU block cyclic reduction (BcrDistPlan): local open chain + replicated interface system
+    bool shard_by_node = false;  // the packer sharded the landmarks by node range
+    int dist_state = 0;          // 0 not tried, 1 usable, -1 not applicable
+    bool dist_on = false;        // the current linearisation was left UN-reduced: every rank holds its share of S (set by do_linearize)
+    BcrDistPlan dbcr;
+    DBuf<BcrItem> d_litems, d_iitems;
+    DBuf<long long> d_dst;
+    DBuf<int> d_blk_lnode, d_node_size;
+    DBuf<double> d_pool, d_bv, d_xv, d_ibuf, d_ixv;  // d_ibuf = [b of the interface nodes | interface tiles]
+    DBuf<unsigned> d_lflags, d_iflags;
+    DBuf<uint8_t> d_own_row;
+    size_t d_ioff = 0;           // doubles in front of the interface tiles inside d_ibuf
     bool cz_have_inverse = false, cz_refreshed = false, cz_reuse_policy = false;
     double cz_last_iters = 0, cz_ref_iters = 0, cz_reuse_factor = 1.5;
     int pcg_grid = -1, pcg_br = 0, pcg_win = 0;
@@ -304,6 +316,20 @@ vio_lm_opts default_opts() {
     return o;
 }
 
+// in-place sum over the ranks of `count` doubles at device pointer ptr, ordered on the handle's stream
+bool is_sharded(const vio_problem *p) { return p->shard_world > 1 && (p->nccl_comm || p->allreduce); }
+int dist_sum(vio_problem *p, double *ptr, int64_t count) {
+    if (p->nccl_comm) {
+        NcclApi &api = nccl_api();
+        const int rc = api.AllReduce(ptr, ptr, (size_t)count, VIO_NCCL_FLOAT64, VIO_NCCL_SUM, p->nccl_comm, p->stream);
+        if (rc != 0) return fail(p, VIO_ERR_CUDA, "ncclAllReduce failed: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
+        return VIO_OK;
+    }
+    const int rc = p->allreduce(ptr, count, (void *)p->stream, p->allreduce_user);
+    if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+    return VIO_OK;
+}
+
 // host plan + device tables of the block cyclic reduction, once per graph.  Returns true when the pattern qualifies.
 bool bcr_prepare(vio_problem *p) {
     if (p->bcr_state != 0) return p->bcr_state > 0;
@@ -338,6 +364,46 @@ bool bcr_prepare(vio_problem *p) {
     return true;
 }
 
+// multi-GPU tables of the block cyclic reduction (needs bcr_prepare); true when this handle solves its reduced system in the
+// distributed way: node-range landmark shards, local open chain, all-reduced interface system
+bool dist_prepare(vio_problem *p) {
+    if (p->dist_state != 0) return p->dist_state > 0;
+    p->dist_state = -1;
+    if (!p->shard_by_node || !is_sharded(p) || !bcr_prepare(p)) return false;
+    bcr_dist_plan(p->bcr, p->h_rowptr, p->h_col, p->shard_rank, p->shard_world, p->dbcr);
+    const BcrDistPlan &D = p->dbcr;
+    if (!D.ok) return false;
+    const BcrPlan &Y = p->bcr;
+    const size_t MM = (size_t)Y.M * Y.ld;
+    const int m = D.m, W = D.world;
+    cudaStream_t s = p->stream;
+    std::vector<int> nsz(m + 1, Y.mb);  // the next rank's interface node (local m) is never padded here
+    for (int j = 0; j < m; ++j) nsz[j] = Y.node_size[(D.lo + j) % Y.n];
+    std::vector<uint8_t> own(p->P, 0);
+    for (int i = 0; i < p->NB; ++i) {
+        const bool mine = Y.blk_node[i] < 0 ? p->shard_rank == 0 : (D.blk_lnode[i] >= 0 && D.blk_lnode[i] < m);
+        for (int c = 0; c < 6; ++c) own[6 * (size_t)i + c] = mine ? 1 : 0;
+    }
+    p->d_ioff = ((size_t)W * Y.M + 1) & ~(size_t)1;
+    bool ok = true;
+    ok &= upload(p->d_litems, D.local.items.data(), D.local.items.size(), s) == cudaSuccess;
+    ok &= upload(p->d_iitems, D.iface.items.data(), D.iface.items.size(), s) == cudaSuccess;
+    ok &= upload(p->d_dst, D.dst.data(), D.dst.size(), s) == cudaSuccess;
+    ok &= upload(p->d_blk_lnode, D.blk_lnode.data(), D.blk_lnode.size(), s) == cudaSuccess;
+    ok &= upload(p->d_node_size, nsz.data(), nsz.size(), s) == cudaSuccess;
+    ok &= upload(p->d_own_row, own.data(), own.size(), s) == cudaSuccess;
+    ok &= p->d_pool.alloc(MM * D.local.n_slots) == cudaSuccess;
+    ok &= p->d_bv.alloc((size_t)(m + 1) * Y.M) == cudaSuccess && p->d_xv.alloc((size_t)(m + 1) * Y.M) == cudaSuccess;
+    ok &= p->d_ibuf.alloc(p->d_ioff + MM * D.iface.n_slots) == cudaSuccess && p->d_ixv.alloc((size_t)W * Y.M) == cudaSuccess;
+    ok &= p->d_lflags.alloc(D.local.items.size() + 4) == cudaSuccess && p->d_iflags.alloc(D.iface.items.size() + 4) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(p->d_lflags.p, 0, (D.local.items.size() + 4) * sizeof(unsigned), s) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(p->d_iflags.p, 0, (D.iface.items.size() + 4) * sizeof(unsigned), s) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+    if (!ok) { (void)cudaGetLastError(); return false; }
+    p->dist_state = 1;
+    return true;
+}
+
 int resolve_solver(vio_problem *p, const vio_lm_opts &o) {
     if (o.solver != VIO_SOLVER_AUTO) return o.solver;
     if (p->storage == VIO_STORAGE_BSR) {
@@ -346,20 +412,6 @@ int resolve_solver(vio_problem *p, const vio_lm_opts &o) {
         return (p->NB >= 256 && p->coop_ok && !p->env_pcg_plain) ? VIO_SOLVER_BLOCK_PCG_2L : VIO_SOLVER_BLOCK_PCG;
     }
     return o.flavour == VIO_LM_V15 ? VIO_SOLVER_REF_PCG : VIO_SOLVER_DENSE_CHOL;
-}
-
-// in-place sum over the ranks of `count` doubles at device pointer ptr, ordered on the handle's stream
-bool is_sharded(const vio_problem *p) { return p->shard_world > 1 && (p->nccl_comm || p->allreduce); }
-int dist_sum(vio_problem *p, double *ptr, int64_t count) {
-    if (p->nccl_comm) {
-        NcclApi &api = nccl_api();
-        const int rc = api.AllReduce(ptr, ptr, (size_t)count, VIO_NCCL_FLOAT64, VIO_NCCL_SUM, p->nccl_comm, p->stream);
-        if (rc != 0) return fail(p, VIO_ERR_CUDA, "ncclAllReduce failed: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
-        return VIO_OK;
-    }
-    const int rc = p->allreduce(ptr, count, (void *)p->stream, p->allreduce_user);
-    if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
-    return VIO_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -411,12 +463,13 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
         p->launches++;
     }
     if (ev) CK(cudaEventRecord(ev->b, p->stream));
-    // pose-only factors are owned by shard 0 so the all-reduce counts them once
+    // pose-only factors are counted once: the SE3 priors this rank kept (the packer's se3_keep: all of them on rank 0, or
+    // those of the rank's own cameras with node-range shards), IMU factors and the dense prior on rank 0
+    if (p->n_se3 > 0) {
+        k_se3prior<<<grid_for(p->n_se3, 64), 64, 0, p->stream>>>(v, se3_view(p));
+        p->launches++;
+    }
     if (p->shard_rank == 0) {
-        if (p->n_se3 > 0) {
-            k_se3prior<<<grid_for(p->n_se3, 64), 64, 0, p->stream>>>(v, se3_view(p));
-            p->launches++;
-        }
         if (p->n_imu > 0) {
             imu_linearize(p->imu, v, p->gravity, p->stream);
             p->launches++;
@@ -427,7 +480,10 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
             p->launches++;
         }
     }
-    if (is_sharded(p)) {
+    // multi-GPU: with node-range shards and the block cyclic reduction every rank keeps its share of the reduced system (only
+    // the interface system and the pose update cross the ranks, see do_solve_step); otherwise S is summed over the ranks here
+    p->dist_on = is_sharded(p) && resolve_solver(p, o) == VIO_SOLVER_BCR && dist_prepare(p);
+    if (is_sharded(p) && !p->dist_on) {
         const int rc = dist_sum(p, p->sys.p, (int64_t)sys_n);
         if (rc) return rc;
     }
@@ -463,11 +519,11 @@ int do_chi2(vio_problem *p, const vio_lm_opts &o, double *out) {
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p + 1280, 256, other, 1);
         p->launches += 2;
     }
+    if (p->n_se3 > 0) {
+        k_se3prior_chi2<<<1, 32, 0, p->stream>>>(v, se3_view(p), other);
+        p->launches++;
+    }
     if (p->shard_rank == 0) {
-        if (p->n_se3 > 0) {
-            k_se3prior_chi2<<<1, 32, 0, p->stream>>>(v, se3_view(p), other);
-            p->launches++;
-        }
         if (p->n_imu > 0) {
             imu_chi2(p->imu, v, p->gravity, other, p->stream);
             p->launches++;
@@ -491,6 +547,10 @@ int do_chi2(vio_problem *p, const vio_lm_opts &o, double *out) {
 }
 
 int do_maxdiag(vio_problem *p, double *out) {
+    if (p->dist_on) {  // un-reduced linearisation: diag(H_pp) of the cameras near a rank boundary is split between two ranks
+        const int rc = dist_sum(p, p->view.hdiag, (int64_t)p->P);
+        if (rc) return rc;
+    }
     k_maxdiag<<<RED_BLOCKS, 256, 0, p->stream>>>(p->view, p->partial.p);
     int n_part = RED_BLOCKS;
     if (p->Lx > 0) {
@@ -781,6 +841,54 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         const size_t MM = (size_t)Y.M * Y.ld;
         EvPair *evp = p->ev_pcg_used < p->ev_pcg.size() ? &p->ev_pcg[p->ev_pcg_used++] : nullptr;
         if (evp) CK(cudaEventRecord(evp->a, p->stream));
+        if (dist_prepare(p)) {
+            // ---- multi-GPU: this rank's share of S covers its own nodes and the next rank's interface node
+            const BcrDistPlan &D = p->dbcr;
+            const int m = D.m, W = D.world, r = D.rank, M = Y.M;
+            const int nL = (int)D.local.items.size(), nI = (int)D.iface.items.size();
+            double *itiles = p->d_ibuf.p + p->d_ioff;
+            CK(cudaMemsetAsync(p->d_pool.p, 0, (size_t)(2 * m + 1) * MM * sizeof(double), p->stream));
+            CK(cudaMemsetAsync(p->d_bv.p, 0, (size_t)(m + 1) * M * sizeof(double), p->stream));
+            CK(cudaMemsetAsync(p->d_ibuf.p, 0, (p->d_ioff + 2 * (size_t)W * MM) * sizeof(double), p->stream));
+            CK(cudaMemsetAsync(p->d_lflags.p + nL, 0, 4 * sizeof(unsigned), p->stream));
+            CK(cudaMemsetAsync(p->d_iflags.p + nI, 0, 4 * sizeof(unsigned), p->stream));
+            CK(cudaMemsetAsync(p->info.p + 2, 0, sizeof(int), p->stream));
+            k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->d_dst.p, p->nnzb, v.bS, p->d_blk_lnode.p, p->bcr_blk_loc.p,
+                                                             p->d_node_size.p, p->NB, m + 1, M, Y.ld, lambda, p->d_pool.p, p->d_bv.p);
+            const unsigned epoch = ++p->bcr_epoch;
+            BcrView lv;
+            lv.n = m + 1; lv.M = M; lv.ld = Y.ld; lv.nbuf = p->bcr_nbuf; lv.items = p->d_litems.p; lv.pool = p->d_pool.p;
+            lv.bv = p->d_bv.p; lv.xv = p->d_xv.p; lv.flags = p->d_lflags.p; lv.epoch = epoch; lv.info = p->info.p + 2; lv.prof = nullptr;
+            lv.xpool = itiles;
+            // (1) local elimination between the two pinned interface nodes (+ export of the coupling left between them)
+            lv.first_item = 0; lv.n_items = D.local.n_elim_items; lv.counter = p->d_lflags.p + nL;
+            k_bcr_run<<<std::min(p->num_sms, std::max(1, lv.n_items)), BCR_THREADS, p->bcr_smem, p->stream>>>(lv);
+            // this rank's share of interface nodes r and r+1: D and b of its two end nodes
+            const int ia = r, ib = (r + 1) % W;
+            CK(cudaMemcpyAsync(itiles + (size_t)ia * MM, p->d_pool.p, MM * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+            CK(cudaMemcpyAsync(itiles + (size_t)ib * MM, p->d_pool.p + (size_t)m * MM, MM * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+            CK(cudaMemcpyAsync(p->d_ibuf.p + (size_t)ia * M, p->d_bv.p, M * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+            CK(cudaMemcpyAsync(p->d_ibuf.p + (size_t)ib * M, p->d_bv.p + (size_t)m * M, M * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+            // (2) the interface system = sum over the ranks; solved redundantly by everybody
+            { const int rc = dist_sum(p, p->d_ibuf.p, (int64_t)(p->d_ioff + 2 * (size_t)W * MM)); if (rc) return rc; }
+            BcrView iv = lv;
+            iv.n = W; iv.items = p->d_iitems.p; iv.pool = itiles; iv.bv = p->d_ibuf.p; iv.xv = p->d_ixv.p; iv.flags = p->d_iflags.p;
+            iv.xpool = nullptr; iv.first_item = 0; iv.n_items = nI; iv.counter = p->d_iflags.p + nI;
+            k_bcr_run<<<std::min(p->num_sms, nI), BCR_THREADS, p->bcr_smem, p->stream>>>(iv);
+            CK(cudaMemcpyAsync(p->d_xv.p, p->d_ixv.p + (size_t)ia * M, M * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+            CK(cudaMemcpyAsync(p->d_xv.p + (size_t)m * M, p->d_ixv.p + (size_t)ib * M, M * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+            // (3) back-substitution of the interior
+            lv.first_item = D.local.n_elim_items; lv.n_items = nL; lv.counter = p->d_lflags.p + nL + 1;
+            if (lv.n_items > lv.first_item)
+                k_bcr_run<<<std::min(p->num_sms, lv.n_items - lv.first_item), BCR_THREADS, p->bcr_smem, p->stream>>>(lv);
+            // (4) owned part of dx_p, summed over the ranks (isolated blocks: rank 0)
+            CK(cudaMemsetAsync(v.dxp, 0, (size_t)p->P * sizeof(double), p->stream));
+            k_bcr_finish<<<grid_for(p->NB, 256), 256, 0, p->stream>>>(p->d_xv.p, p->bcr_blk_node.p, p->d_blk_lnode.p, p->bcr_blk_loc.p, p->NB, M, m,
+                                                                    r == 0 ? 1 : 0, v.S, p->bsr_diag.p, v.bS, lambda, v.dxp, p->info.p + 2);
+            { const int rc = dist_sum(p, v.dxp, (int64_t)p->P); if (rc) return rc; }
+            if (evp) CK(cudaEventRecord(evp->b, p->stream));
+            p->launches += 5;
+        } else {
         // node tiles D_i and level-0 couplings E_i are rebuilt from S + lambda I; the W tiles behind them are overwritten
         CK(cudaMemsetAsync(p->bcr_pool.p, 0, 2 * (size_t)Y.n * MM * sizeof(double), p->stream));
         CK(cudaMemsetAsync(p->bcr_bv.p, 0, (size_t)Y.n * Y.M * sizeof(double), p->stream));
@@ -792,16 +900,18 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         bv.n = Y.n; bv.M = Y.M; bv.ld = Y.ld; bv.nbuf = p->bcr_nbuf; bv.n_items = (int)Y.items.size(); bv.items = p->bcr_items.p; bv.pool = p->bcr_pool.p;
         bv.bv = p->bcr_bv.p; bv.xv = p->bcr_xv.p; bv.flags = p->bcr_flags.p; bv.counter = p->bcr_flags.p + Y.items.size();
         bv.epoch = ++p->bcr_epoch; bv.info = p->info.p + 2;
+        bv.first_item = 0; bv.xpool = nullptr;
         bv.prof = nullptr;
         if (p->env_profile) {
             if (p->prof.n < 32) { CK(p->prof.alloc(32)); CK(cudaMemsetAsync(p->prof.p, 0, 32 * sizeof(unsigned long long), p->stream)); }
             bv.prof = p->prof.p + 16;
         }
         k_bcr_run<<<std::min(p->num_sms, bv.n_items), BCR_THREADS, p->bcr_smem, p->stream>>>(bv);
-        k_bcr_finish<<<grid_for(p->NB, 256), 256, 0, p->stream>>>(p->bcr_xv.p, p->bcr_blk_node.p, p->bcr_blk_loc.p, p->NB, Y.M, v.S,
-                                                                p->bsr_diag.p, v.bS, lambda, v.dxp, p->info.p + 2);
+        k_bcr_finish<<<grid_for(p->NB, 256), 256, 0, p->stream>>>(p->bcr_xv.p, p->bcr_blk_node.p, p->bcr_blk_node.p, p->bcr_blk_loc.p, p->NB, Y.M,
+                                                                Y.n, 1, v.S, p->bsr_diag.p, v.bS, lambda, v.dxp, p->info.p + 2);
         if (evp) CK(cudaEventRecord(evp->b, p->stream));
         p->launches += 3;
+        }
     } else if (solver == VIO_SOLVER_BLOCK_CHOL) {
         if (p->storage != VIO_STORAGE_BSR) return fail(p, VIO_ERR_INVALID, "block Cholesky needs BSR storage");
         const int nb = p->NB;
@@ -846,16 +956,18 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p + 1280, 256, p->scal.p + 5, 1);
         p->launches += 3;
     }
-    if (is_sharded(p)) {
-        const int rc = dist_sum(p, p->scal.p + 4, 2);
-        if (rc) return rc;
-    }
     {
+        // pose part of scale = dx^T (lambda dx + b) and |dx|^2.  Un-reduced linearisation: b_p is this rank's share (the sum over the
+        // ranks is linear in it) and the lambda |dx|^2 / |dx|^2 terms are counted on the rows the rank owns
         const int g = grid_for(p->P, 256, 64);
-        k_pose_scale<<<g, 256, 0, p->stream>>>(v, lambda, p->partial.p + 1024, p->partial2.p + 1024);
+        k_pose_scale<<<g, 256, 0, p->stream>>>(v, lambda, p->dist_on ? p->d_own_row.p : nullptr, p->partial.p + 1024, p->partial2.p + 1024);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p + 1024, g, p->scal.p + 6, 0);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p + 1024, g, p->scal.p + 7, 0);
         p->launches += 3;
+    }
+    if (is_sharded(p)) {
+        const int rc = dist_sum(p, p->scal.p + 4, p->dist_on ? 4 : 2);
+        if (rc) return rc;
     }
     CK(cudaGetLastError());
     return VIO_OK;
@@ -1089,12 +1201,14 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     p->cz_have_inverse = false;
     p->bchol_ready = false;
     p->bcr_state = 0;
+    p->dist_state = 0;
+    p->shard_by_node = K.shard_by_node;
     { const char *ev = getenv("VIO_B200_COARSE_REUSE"); p->cz_reuse_policy = !ev || atoi(ev) != 0; }  // default on
     { const char *ev = getenv("VIO_B200_COARSE_REUSE_FACTOR"); if (ev && atof(ev) >= 1.0) p->cz_reuse_factor = atof(ev); }
     const int C = K.C, NSB = K.NSB, L = K.L, P = K.P, NB = K.NB;
     const long long E = K.E;
     p->C = C; p->NSB = NSB; p->L = L; p->P = P; p->NB = NB; p->E = E; p->storage = K.storage; p->nnzb = K.nnzb;
-    p->Lglobal = K.Lglobal; p->s_count = K.s_count; p->n_se3 = g->n_se3prior; p->n_imu = g->n_imu;
+    p->Lglobal = K.Lglobal; p->s_count = K.s_count; p->n_se3 = (int)K.se3_keep.size(); p->n_imu = g->n_imu;
     p->h_pose_off = K.pose_off; p->h_sb_off = K.sb_off; p->h_rowptr = K.rowptr; p->h_col = K.col;
     p->lm_global = K.lm_global;
     if (E <= (4 << 20)) { p->h_lm_host = K.lm_host; p->h_lm_eptr = K.lm_eptr; p->h_e_pose_j = K.e_pose_j; }
@@ -1156,9 +1270,24 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
         CK(p->dxx.alloc(3 * (size_t)K.Lx));
         CK(cudaMemsetAsync(p->dxx.p, 0, 3 * (size_t)K.Lx * sizeof(double), s));
     }
-    if (g->n_se3prior > 0) {
-        CK(upload(p->sp_pose, g->sp_pose, (size_t)g->n_se3prior, s)); CK(upload(p->sp_p, g->sp_p, 3 * (size_t)g->n_se3prior, s));
-        CK(upload(p->sp_q, g->sp_q, 4 * (size_t)g->n_se3prior, s)); CK(upload(p->sp_info, g->sp_info, 36 * (size_t)g->n_se3prior, s));
+    {
+        // the SE3 priors this rank accumulates (all of them without sharding)
+        const int ns = (int)K.se3_keep.size();
+        p->n_se3 = ns;
+        if (ns > 0) {
+            std::vector<int> sp(ns);
+            std::vector<double> pp(3 * (size_t)ns), qq(4 * (size_t)ns), ii(36 * (size_t)ns);
+            for (int a = 0; a < ns; ++a) {
+                const int k = K.se3_keep[a];
+                sp[a] = g->sp_pose[k];
+                std::copy(g->sp_p + 3 * (size_t)k, g->sp_p + 3 * (size_t)k + 3, pp.begin() + 3 * (size_t)a);
+                std::copy(g->sp_q + 4 * (size_t)k, g->sp_q + 4 * (size_t)k + 4, qq.begin() + 4 * (size_t)a);
+                std::copy(g->sp_info + 36 * (size_t)k, g->sp_info + 36 * (size_t)k + 36, ii.begin() + 36 * (size_t)a);
+            }
+            CK(upload(p->sp_pose, sp.data(), (size_t)ns, s)); CK(upload(p->sp_p, pp.data(), pp.size(), s));
+            CK(upload(p->sp_q, qq.data(), qq.size(), s)); CK(upload(p->sp_info, ii.data(), ii.size(), s));
+            CK(cudaStreamSynchronize(s));
+        }
     }
     CK(upload(p->imu.blk_off, K.blk_off.data(), (size_t)NB, s)); CK(upload(p->imu.blk_dim, K.blk_dim.data(), (size_t)NB, s));
     CK(upload(p->imu.blk_fixed, K.blk_fixed.data(), (size_t)NB, s));
@@ -1186,6 +1315,15 @@ int vio_get_dims(const vio_problem *p, vio_dims *out) {
     if (!p || !out || !p->has_graph) return VIO_ERR_STATE;
     out->P = p->P; out->M = p->Lglobal; out->n_pose_blocks = p->NB; out->storage = p->storage;
     out->nnz_blocks = p->nnzb; out->n_reproj = p->E; out->n_groups = p->use_grouped ? p->n_groups : 0; out->reserved = p->L;
+    return VIO_OK;
+}
+
+int vio_get_owned_landmarks(const vio_problem *p, int32_t *out, int64_t cap, int64_t *count) {
+    if (!p || !p->has_graph) return VIO_ERR_STATE;
+    const int64_t n = (int64_t)p->lm_global.size();
+    if (count) *count = n;
+    if (out)
+        for (int64_t k = 0; k < n && k < cap; ++k) out[k] = p->lm_global[k];
     return VIO_OK;
 }
 
@@ -1570,6 +1708,18 @@ int vio_get_schur_bsr(vio_problem *p, int32_t *rowptr, int32_t *col, double *val
     CK(cudaSetDevice(p->device));
     if (rowptr) memcpy(rowptr, p->h_rowptr.data(), p->h_rowptr.size() * sizeof(int));
     if (col) memcpy(col, p->h_col.data(), p->h_col.size() * sizeof(int));
+    if (p->dist_on) {
+        // un-reduced linearisation: the tap returns the SUM over the ranks (a collective call: every rank must make it)
+        DBuf<double> tmp;
+        CK(tmp.alloc(p->s_count + (size_t)p->P));
+        CK(cudaMemcpyAsync(tmp.p, p->sys.p, p->s_count * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        CK(cudaMemcpyAsync(tmp.p + p->s_count, p->bS.p, p->P * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+        { const int rc = dist_sum(p, tmp.p, (int64_t)(p->s_count + (size_t)p->P)); if (rc) return rc; }
+        if (val) CK(cudaMemcpyAsync(val, tmp.p, p->s_count * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (bS) CK(cudaMemcpyAsync(bS, tmp.p + p->s_count, p->P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        return VIO_OK;
+    }
     if (val) CK(cudaMemcpyAsync(val, p->sys.p, p->s_count * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (bS) CK(cudaMemcpyAsync(bS, p->bS.p, p->P * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));

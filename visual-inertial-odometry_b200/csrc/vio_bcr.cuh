@@ -21,6 +21,8 @@ struct BcrView {
     double *bv, *xv;     // [n][M]
     unsigned *flags;     // [n_items] = epoch when the item is complete
     unsigned *counter;   // work queue head (zeroed before the launch)
+    int first_item;      // this launch executes items [first_item, n_items)
+    double *xpool;       // BCR_EXPORT target tiles (the interface system of the multi-GPU solve), else nullptr
     unsigned epoch;
     int *info;           // != 0: a pivot was not positive
     unsigned long long *prof;  // optional [8] cycle counters (VIO_B200_PROFILE=1): dependency wait, updates + couplings, Cholesky,
@@ -52,16 +54,22 @@ __global__ void __launch_bounds__(256) k_bcr_load(const double *__restrict__ val
 }
 
 // ---- finish: gather x, solve the isolated 6x6 blocks ------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bcr_finish(const double *__restrict__ xv, const int *__restrict__ blk_node, const int *__restrict__ blk_loc,
-                                                    int nb, int M, const double *__restrict__ val, const int *__restrict__ diag,
+__global__ void __launch_bounds__(256) k_bcr_finish(const double *__restrict__ xv, const int *__restrict__ blk_gnode, const int *__restrict__ blk_node,
+                                                    const int *__restrict__ blk_loc, int nb, int M, int own_hi, int do_iso,
+                                                    const double *__restrict__ val, const int *__restrict__ diag,
                                                     const double *__restrict__ b, double lambda, double *__restrict__ x, int *info) {
+    // blk_gnode: node of the global partition (-1: isolated block); blk_node: node index into xv (multi-GPU: the rank's LOCAL
+    // node, owned when < own_hi; other blocks are left untouched - x was zeroed and is summed over the ranks afterwards)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb) return;
-    if (blk_node[i] >= 0) {
+    if (blk_gnode[i] >= 0) {
+        if (blk_node[i] >= 0 && blk_node[i] < own_hi) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) x[6 * (size_t)i + c] = xv[(size_t)blk_node[i] * M + 6 * blk_loc[i] + c];
+            for (int c = 0; c < 6; ++c) x[6 * (size_t)i + c] = xv[(size_t)blk_node[i] * M + 6 * blk_loc[i] + c];
+        }
         return;
     }
+    if (!do_iso) return;
     double A[36], y[6];
     const double *d = val + 36 * (size_t)diag[i];
 #pragma unroll
@@ -460,7 +468,7 @@ __global__ void __launch_bounds__(BCR_THREADS, 1) k_bcr_run(BcrView s) {
         __syncthreads();  // the previous item's shared-memory traffic is over (and the barrier is initialised)
         if (tid == 0) idx_s = atomicAdd(s.counter, 1u);
         __syncthreads();
-        const unsigned idx = idx_s;
+        const unsigned idx = idx_s + (unsigned)s.first_item;
         if (idx >= (unsigned)s.n_items) return;
         if (tid < (int)(sizeof(BcrItem) / sizeof(int))) reinterpret_cast<int *>(&it_s)[tid] = reinterpret_cast<const int *>(s.items + idx)[tid];
         __syncthreads();
@@ -471,7 +479,21 @@ __global__ void __launch_bounds__(BCR_THREADS, 1) k_bcr_run(BcrView s) {
         BCR_MARK(0);
         const BcrItem &it = it_s;
         const size_t node_off = (size_t)it.node * MM;
-        if (it.kind & BCR_BACKSUB) {
+        if (it.kind & BCR_EXPORT) {
+            // open chain: the coupling left between the two pinned ends, -pool[a]^T pool[b], goes to the interface system
+            if (tid == 0) {
+                bcr_fence_async();
+                bcr_mbar_expect(&ldbar, 2u * tile_bytes);
+                bcr_bulk_load(BCR_OPA(0), s.pool + (size_t)it.cl_a * MM, tile_bytes, &ldbar);
+                bcr_bulk_load(BCR_OPB(0), s.pool + (size_t)it.cl_b * MM, tile_bytes, &ldbar);
+            }
+            bcr_mbar_wait(&ldbar, ph);
+            ph ^= 1u;
+            __syncthreads();
+            double *out = s.xpool + (size_t)it.cl_slot * MM;
+            auto st = [&](int i, int j, double v0, double v1) { __stcg(reinterpret_cast<double2 *>(out + (size_t)i * LD + j), make_double2(-v0, -v1)); };
+            bcr_mma_tn<false, false>(BCR_OPA(0), BCR_OPB(0), BCR_OPB(0), M, LD, st, st);
+        } else if (it.kind & BCR_BACKSUB) {
             // x_k = U (y_k - W_l x_l - W_r x_r): the three tiles come in as one bulk batch, every dot product is one warp wide
             const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
             const bool hl = it.left >= 0, hr = it.right >= 0;

@@ -794,12 +794,15 @@ __global__ void __launch_bounds__(256) k_backsub(DevView v, double lambda, doubl
     block_sum_to(n2, partial_n2);
 }
 
-__global__ void __launch_bounds__(256) k_pose_scale(DevView v, double lambda, double *partial_scale, double *partial_n2) {
+// own: nullptr, or (multi-GPU, un-reduced b_p) 1 for the rows this rank owns - the quadratic terms are counted there only
+__global__ void __launch_bounds__(256) k_pose_scale(DevView v, double lambda, const uint8_t *__restrict__ own, double *partial_scale,
+                                                    double *partial_n2) {
     double sc = 0.0, n2 = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.P; i += gridDim.x * blockDim.x) {
         const double d = v.dxp[i];
-        sc += d * (lambda * d + v.bp[i]);
-        n2 += d * d;
+        const double mine = (own == nullptr || own[i]) ? 1.0 : 0.0;
+        sc += d * (mine * lambda * d + v.bp[i]);
+        n2 += mine * d * d;
     }
     block_sum_to(sc, partial_scale);
     block_sum_to(n2, partial_n2);

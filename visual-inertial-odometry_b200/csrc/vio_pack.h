@@ -14,6 +14,8 @@
 #include <vector>
 #include "../../include/vio_b200.h"
 
+#include "vio_bcr.h"
+
 struct PackedGraph {
     int C = 0, NSB = 0, NB = 0, P = 0, L = 0, Lglobal = 0, storage = 1;
     bool ext_free = false;    // the extrinsic VertexPose is being estimated (4-vertex EdgeReprojection, 4th Jacobian)
@@ -40,6 +42,10 @@ struct PackedGraph {
     std::vector<long long> g_pairinfo;
     std::vector<double> ell_pjx, ell_pjy;
     std::vector<int> ell_edge;
+    // multi-GPU, node-range sharding (see pack_graph): this rank keeps the landmarks hosted by the cameras of ITS nodes of the
+    // block-cyclic-reduction partition, so its share of S stays inside its own nodes and the next rank's interface node
+    bool shard_by_node = false;
+    std::vector<int> se3_keep;   // SE3 priors this rank accumulates (indices into the caller's arrays)
 };
 
 inline int pack_fail(std::string &err, int code, const char *fmt, ...) {
@@ -50,6 +56,40 @@ inline int pack_fail(std::string &err, int code, const char *fmt, ...) {
     va_end(ap);
     err = buf;
     return code;
+}
+
+// co-visibility pattern of the inverse-depth landmarks over the pose blocks (+ diagonal): rows[a] = blocks coupled with a
+inline void covis_rows(const vio_graph *g, const std::vector<int> &cnt, const std::vector<int> &eorder, const std::vector<int> &pose_blk, int NB,
+                       int Lg, std::vector<std::vector<int>> &rows) {
+    rows.assign(NB, std::vector<int>());
+    for (int k = 0; k < NB; ++k) rows[k].push_back(k);
+    auto add = [&](int a, int b) {
+        auto &r = rows[a];
+        if (std::find(r.begin(), r.end(), b) == r.end()) r.push_back(b);
+    };
+    std::vector<int> set, last;
+    for (int l = 0; l < Lg; ++l) {
+        set.clear();
+        if (cnt[l] == cnt[l + 1]) continue;
+        set.push_back(pose_blk[g->rp_pose_i[eorder[cnt[l]]]]);
+        for (int k = cnt[l]; k < cnt[l + 1]; ++k) set.push_back(pose_blk[g->rp_pose_j[eorder[k]]]);
+        if (set == last) continue;
+        for (size_t a = 0; a < set.size(); ++a)
+            for (size_t b = 0; b < set.size(); ++b) add(set[a], set[b]);
+        last = set;
+    }
+}
+inline void covis_pattern(const vio_graph *g, const std::vector<int> &cnt, const std::vector<int> &eorder, const std::vector<int> &pose_blk, int NB,
+                          int Lg, std::vector<int> &rowptr, std::vector<int> &col) {
+    std::vector<std::vector<int>> rows;
+    covis_rows(g, cnt, eorder, pose_blk, NB, Lg, rows);
+    rowptr.assign(NB + 1, 0);
+    col.clear();
+    for (int k = 0; k < NB; ++k) {
+        std::sort(rows[k].begin(), rows[k].end());
+        col.insert(col.end(), rows[k].begin(), rows[k].end());
+        rowptr[k + 1] = (int)col.size();
+    }
 }
 
 inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, PackedGraph &K, std::string &err, int batch = 1) {
@@ -127,21 +167,81 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         std::vector<int> cur(cnt.begin(), cnt.end() - 1);
         for (long long e = 0; e < Eg; ++e) eorder[cur[g->rp_landmark[e]]++] = (int)e;
     }
-    // shard: contiguous landmark ranges balanced by edge count
-    int l_begin = 0, l_end = Lg;
+    // ---- which landmarks this rank keeps
+    // Legacy sharding: contiguous landmark ranges balanced by edge count; the whole reduced system is all-reduced.
+    // Node-range sharding (chosen when the reduced system is block-sparse, a cyclic block band the block cyclic reduction
+    // covers, with at least two nodes per rank, and every landmark is observed only from its host's node and the node
+    // after it): rank r keeps the landmarks hosted in its nodes; nothing outside its own nodes and the next rank's first
+    // node is touched, so only the W-node interface system and the pose update cross the ranks.
+    std::vector<int> lsel;
+    K.shard_by_node = false;
+    K.se3_keep.clear();
+    for (int k = 0; k < g->n_se3prior; ++k)
+        if (shard_rank == 0) K.se3_keep.push_back(k);
     if (shard_world > 1) {
-        auto cut = [&](int r) -> int {
-            if (r <= 0) return 0;
-            if (r >= shard_world) return Lg;
-            long long target = Eg * r / shard_world;
-            return (int)(std::lower_bound(cnt.begin(), cnt.end(), (int)target) - cnt.begin());
-        };
-        l_begin = std::min(cut(shard_rank), Lg);
-        l_end = std::min(cut(shard_rank + 1), Lg);
-        if (l_end < l_begin) l_end = l_begin;
+        int st0 = g->storage;
+        if (st0 == VIO_STORAGE_AUTO) st0 = (NSB == 0 && P > 2048 && !K.ext_free) ? VIO_STORAGE_BSR : VIO_STORAGE_DENSE;
+        const bool try_nodes = st0 == VIO_STORAGE_BSR && NSB == 0 && g->n_imu == 0 && g->n_point == 0 && g->n_reproj_xyz == 0 && batch == 1 &&
+                               getenv("VIO_B200_SHARD_LEGACY") == nullptr;
+        if (try_nodes) {
+            std::vector<int> rp0, cl0;
+            covis_pattern(g, cnt, eorder, pose_blk, NB, Lg, rp0, cl0);
+            BcrPlan P0;
+            bcr_partition(NB, rp0, cl0, P0);
+            if (P0.ok && P0.n >= 2 * shard_world) {
+                const int n = P0.n;
+                auto owner = [&](int node) {
+                    int r = (int)(((long long)node * shard_world + shard_world - 1) / n);  // smallest r with lo_r > node, minus one
+                    while (r > 0 && bcr_rank_lo(n, shard_world, r) > node) --r;
+                    while (r + 1 < shard_world && bcr_rank_lo(n, shard_world, r + 1) <= node) ++r;
+                    return r;
+                };
+                bool local_ok = true;
+                for (int l = 0; l < Lg && local_ok; ++l) {
+                    if (cnt[l] == cnt[l + 1]) continue;
+                    const int a = P0.blk_node[pose_blk[g->rp_pose_i[eorder[cnt[l]]]]];
+                    if (a < 0) { local_ok = false; break; }
+                    for (int k = cnt[l]; k < cnt[l + 1]; ++k) {
+                        const int b = P0.blk_node[pose_blk[g->rp_pose_j[eorder[k]]]];
+                        if (b < 0 || (b - a + n) % n > 1) { local_ok = false; break; }
+                    }
+                }
+                for (int k = 0; k < g->n_se3prior && local_ok; ++k)
+                    if (P0.blk_node[pose_blk[g->sp_pose[k]]] < 0 && !(g->pose_fixed && g->pose_fixed[g->sp_pose[k]])) local_ok = false;
+                if (local_ok) {
+                    K.shard_by_node = true;
+                    for (int l = 0; l < Lg; ++l) {
+                        if (cnt[l] == cnt[l + 1]) { if (shard_rank == 0) lsel.push_back(l); continue; }
+                        if (owner(P0.blk_node[pose_blk[g->rp_pose_i[eorder[cnt[l]]]]]) == shard_rank) lsel.push_back(l);
+                    }
+                    K.se3_keep.clear();
+                    for (int k = 0; k < g->n_se3prior; ++k) {
+                        const int nd = P0.blk_node[pose_blk[g->sp_pose[k]]];
+                        if ((nd < 0 ? 0 : owner(nd)) == shard_rank) K.se3_keep.push_back(k);
+                    }
+                }
+            }
+        }
     }
-    const int L = l_end - l_begin;
-    const long long E = (long long)cnt[l_end] - cnt[l_begin];
+    if (!K.shard_by_node) {
+        int l_begin = 0, l_end = Lg;
+        if (shard_world > 1) {
+            auto cut = [&](int r) -> int {
+                if (r <= 0) return 0;
+                if (r >= shard_world) return Lg;
+                long long target = Eg * r / shard_world;
+                return (int)(std::lower_bound(cnt.begin(), cnt.end(), (int)target) - cnt.begin());
+            };
+            l_begin = std::min(cut(shard_rank), Lg);
+            l_end = std::min(cut(shard_rank + 1), Lg);
+            if (l_end < l_begin) l_end = l_begin;
+        }
+        lsel.resize(l_end - l_begin);
+        for (int ll = 0; ll < l_end - l_begin; ++ll) lsel[ll] = l_begin + ll;
+    }
+    const int L = (int)lsel.size();
+    long long E = 0;
+    for (int l : lsel) E += cnt[l + 1] - cnt[l];
     std::vector<int> &lm_host = K.lm_host, &lm_eptr = K.lm_eptr, &e_pose_j = K.e_pose_j;
     std::vector<double> &pix = K.pix, &piy = K.piy, &piz = K.piz, &pjx = K.pjx, &pjy = K.pjy, &invd = K.invd;
     lm_host.assign(L, 0); lm_eptr.assign(L + 1, 0); e_pose_j.assign(E, 0);
@@ -150,14 +250,18 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     // local landmark order: sorted by host pose (stable) so that landmarks sharing a host are contiguous and
     // can be grouped; landmarks without edges go last.
     std::vector<int> lorder(L);
-    for (int ll = 0; ll < L; ++ll) lorder[ll] = l_begin + ll;
+    for (int ll = 0; ll < L; ++ll) lorder[ll] = lsel[ll];
     auto host_of = [&](int l) { return cnt[l] == cnt[l + 1] ? 0x7fffffff : g->rp_pose_i[eorder[cnt[l]]]; };
     {
         // scenes are usually generated host by host: skip the sort when the order is already non-decreasing
         std::vector<int> hkey(L);
-        for (int ll = 0; ll < L; ++ll) hkey[ll] = host_of(l_begin + ll);
-        if (!std::is_sorted(hkey.begin(), hkey.end()))
-            std::stable_sort(lorder.begin(), lorder.end(), [&](int a, int b) { return hkey[a - l_begin] < hkey[b - l_begin]; });
+        for (int ll = 0; ll < L; ++ll) hkey[ll] = host_of(lsel[ll]);
+        if (!std::is_sorted(hkey.begin(), hkey.end())) {
+            std::vector<int> idx(L);
+            for (int ll = 0; ll < L; ++ll) idx[ll] = ll;
+            std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return hkey[a] < hkey[b]; });
+            for (int ll = 0; ll < L; ++ll) lorder[ll] = lsel[idx[ll]];
+        }
     }
     int ecur = 0;
     for (int ll = 0; ll < L; ++ll) {
@@ -227,23 +331,13 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         s_count = (size_t)P * Pper;
     } else {
         // global pattern (all shards must agree): co-visibility of every landmark + diagonal
-        std::vector<std::vector<int>> rows(NB);
-        for (int k = 0; k < NB; ++k) rows[k].push_back(k);
+        std::vector<std::vector<int>> rows;
+        covis_rows(g, cnt, eorder, pose_blk, NB, Lg, rows);
         auto add = [&](int a, int b) {
             auto &r = rows[a];
             if (std::find(r.begin(), r.end(), b) == r.end()) r.push_back(b);
         };
-        std::vector<int> set, last;
-        for (int l = 0; l < Lg; ++l) {
-            set.clear();
-            if (cnt[l] == cnt[l + 1]) continue;
-            set.push_back(pose_blk[g->rp_pose_i[eorder[cnt[l]]]]);
-            for (int k = cnt[l]; k < cnt[l + 1]; ++k) set.push_back(pose_blk[g->rp_pose_j[eorder[k]]]);
-            if (set == last) continue;
-            for (size_t a = 0; a < set.size(); ++a)
-                for (size_t b = 0; b < set.size(); ++b) add(set[a], set[b]);
-            last = set;
-        }
+        std::vector<int> set;
         for (int l = 0; l < Lx; ++l) {
             set.clear();
             for (int k = K.px_eptr[l]; k < K.px_eptr[l + 1]; ++k) set.push_back(pose_blk[K.ex_pose[k]]);
