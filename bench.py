@@ -34,6 +34,13 @@ WORKLOADS = {
     "tiny_ba_100_cams_10k_landmarks": dict(n_cam=100, n_landmark=10000, k_obs=11, seed=3),
 }
 DEFAULT_WORKLOAD = "config5_ba_10k_cams_1m_landmarks_10m_obs"
+# BASELINE.json configs[0..2]: single problems that fit one CTA's worth of reduced system (dense storage, P = 120 / 126 / 171)
+SMALL_WORKLOADS = {
+    "config1_monoba_20x300_v15": dict(kind="monoba", ver=15),   # TestMonoBA as committed: v15 LM + reference PCG (missing first step)
+    "config1_monoba_20x300_v17": dict(kind="monoba", ver=17),   # the same scene, v17 LM + exact reduced solve, fixed identity extrinsic vertex
+    "config2_vins_window": dict(kind="window", ver=17),          # 11 keyframes, 1000 features, 10 IMU edges, 171-dim marginalisation prior
+    "config3_batched_4096_windows": dict(kind="batch", ver=17, n=4096),  # config 2 from seeds 2..4097, one lock-step batch call
+}
 METRIC = "reprojection_edges_per_sec"
 UNIT = "edges/s"
 
@@ -518,6 +525,185 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
+
+def host_info():
+    model = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except Exception:
+        pass
+    return {"nproc": os.cpu_count(), "cpu_model": model, "affinity": sorted(os.sched_getaffinity(0))[:4] + (["..."] if len(os.sched_getaffinity(0)) > 4 else [])}
+
+
+def _gen_window(seed):
+    from tests.scenes_extra import window_scene
+    return window_scene(seed=seed).export()
+
+
+def small_scene(vio, wl, n_batch):
+    """Scenes of BASELINE configs 1-3: TestMonoBA draw for draw; the VINS-style window built through the
+    unmodified reference's IntegrationBase + Marginalize (oracle/_ref/libref17.so, which travels with the repo)."""
+    if wl["kind"] == "monoba":
+        return [vio.scenes.monoba(20, 300, with_ext=(wl["ver"] == 17))]
+    from tests.scenes_extra import window_scene
+    if wl["kind"] == "window":
+        return [window_scene(seed=2)]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 32)) as pool:
+        dicts = pool.map(_gen_window, range(2, 2 + n_batch), chunksize=8)
+    return [vio.Scene.from_dict(d) for d in dicts]
+
+
+def run_small(args):
+    """Configs 1-3: one (or 4096) sliding-window sized problems.  A step = one LM iteration of Problem::Solve."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # replicas only (SURVEY 8e): these problems are too small to shard
+    vio = importlib.import_module(PKG)
+    capi = vio.capi
+    wl = SMALL_WORKLOADS[args.workload]
+    ver = wl["ver"]
+    n_batch = (args.batch_n or wl.get("n", 1)) if wl["kind"] == "batch" else 1
+    t0 = time.perf_counter()
+    scenes = small_scene(vio, wl, n_batch)
+    t_gen = time.perf_counter() - t0
+    s0 = scenes[0]
+    E_all = int(sum(sc.rp_landmark.shape[0] for sc in scenes))
+    K = int(args.steps)
+    flav = capi.LM_V15 if ver == 15 else capi.LM_V17
+    opts = vio.make_opts(flavour=flav, fixed_iterations=1)
+    line = {"metric": METRIC, "unit": UNIT, "n_gpus": 1, "warmup": int(args.warmup), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "problems": len(scenes), "edges": E_all, "P": int(s0.P),
+                       "landmarks_per_problem": int(s0.inv_depth.shape[0]), "lm_flavour": f"v{ver}", "scene_gen_s": round(t_gen, 2),
+                       "l2": "problem resident in L2 (single sliding-window sized graph: the reference's own operating point)",
+                       "parallelism": "single_problem" if len(scenes) == 1 else "lockstep_batch"},
+            "host": host_info()}
+    if args.impl == "reference":
+        # the UNMODIFIED reference backend (oracle/_ref) on the same scene(s), one core
+        from tests import refshim
+        if not refshim.available(ver):
+            emit({"impl": "reference", "unavailable": "oracle/_ref/libref%d.so not built" % ver})
+            return
+        sample = scenes[:max(1, min(len(scenes), 4))]
+        for _ in range(min(args.warmup, 1)):
+            refshim.solve(ver, sample[0], K)
+        t0 = time.perf_counter()
+        its = 0
+        for sc in sample:
+            its += refshim.solve(ver, sc, K)["iterations"]
+        dt = time.perf_counter() - t0
+        E_s = sum(sc.rp_landmark.shape[0] for sc in sample) / len(sample)
+        val = E_s * its / dt
+        line.update({"impl": "reference", "value": val, "steps": int(its), "ms_per_step": 1e3 * dt / max(its, 1),
+                     "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference",
+                                      "sample": f"unmodified v{ver} backend::Problem::Solve({K}) on {len(sample)} of the {len(scenes)} problem(s) of this workload"},
+                     "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        emit(line)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(0)
+    sampler = ClockSampler(0)
+    if wl["kind"] == "batch":
+        kw = dict(lockstep=True, max_chunk=0)
+        for _ in range(2):
+            capi.solve_batched(scenes, K, opts, **kw)   # warm-up at the measured size (the entry keeps its handle + staging)
+        sampler.start()
+        reps, dts, iters, lat = 3, [], 0, []
+        for _ in range(reps):
+            outs, dt = capi.solve_batched(scenes, K, opts, **kw)
+            dts.append(dt)
+            iters = sum(o["stats"].iterations for o in outs)
+            lat = np.array([o["stats"].ms_total for o in outs])
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        dt = float(np.median(dts))
+        e_it = sum(sc.rp_landmark.shape[0] * o["stats"].iterations for sc, o in zip(scenes, outs))
+        # device part: the chunks' LM loops (every item reports its chunk's loop time; chunks of 1024 run one after the other)
+        dev_s = float(np.sum(np.unique(lat))) * 1e-3
+        line.update({"value": e_it / dev_s if dev_s > 0 else None, "steps": int(iters), "ms_per_step": 1e3 * dt / max(iters, 1),
+                     "problems_per_sec": len(scenes) / dt, "lm_iters_per_sec": iters / dt,
+                     "e2e": {"value": e_it / dt, "unit": UNIT, "seconds_per_call": dt,
+                             "h2d_bytes_per_step": int(52 * E_all // max(K, 1)), "d2h_bytes_per_step": int(8 * sum(sc.inv_depth.shape[0] + 16 * sc.pose.shape[0] for sc in scenes) // max(K, 1)),
+                             "call": "vio_solve_batched_lockstep(host graphs): pack + H2D + Solve(K) per window + D2H, two-slot pipeline"},
+                     "latency_ms": {"p50": float(np.percentile(lat, 50)), "p95": float(np.percentile(lat, 95)),
+                                    "note": "per item = its chunk's LM loop (all windows of a chunk finish together)"},
+                     "value_note": "value = sum(edges x LM iterations) / device time of the chunks' LM loops; e2e = the same over the wall time of the call",
+                     "roofline": {"kernel": "k_chol_batch (one CTA per window, 171 x 171 Cholesky in shared memory)", "bound": "fp64", "achieved": None,
+                                  "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                                  "note": "latency bound: P column steps x 3 barriers per window; see DESIGN.md section 4"},
+                     "gpu_launches": None, "clocks": sampler.summary()})
+    else:
+        sc = s0
+        p = vio.Problem(device=0)
+        p.set_graph(sc)
+        for _ in range(max(args.warmup, 3)):
+            p.set_vertices(pose=sc.pose, speedbias=sc.speedbias if sc.speedbias.size else None, inv_depth=sc.inv_depth)
+            if sc.prior is not None:
+                p.set_prior(sc.prior["H"], sc.prior["b"], sc.prior.get("err"), sc.prior.get("jt_inv"))
+            p.solve(K, opts)
+        sampler.start()
+        reps, ms_dev, iters, t_e2e = 20, 0.0, 0, 0.0
+        launches0 = p.launch_count()
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            p.set_vertices(pose=sc.pose, speedbias=sc.speedbias if sc.speedbias.size else None, inv_depth=sc.inv_depth)
+            if sc.prior is not None:
+                p.set_prior(sc.prior["H"], sc.prior["b"], sc.prior.get("err"), sc.prior.get("jt_inv"))
+            st = p.solve(K, opts)
+            p.get_vertices()
+            t_e2e += time.perf_counter() - t0
+            ms_dev += st.ms_total
+            iters += st.iterations
+        launches = p.launch_count() - launches0
+        t0 = time.perf_counter()
+        q = vio.Problem(device=0)
+        q.set_graph(sc)
+        st_d = q.solve(K, opts)
+        q.get_vertices()
+        t_drop = time.perf_counter() - t0
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        E = int(sc.rp_landmark.shape[0])
+        lin_ms, lin_n = p.kernel_ms()
+        fp64_peak = capi.measure_fp64_peak(0)
+        hbm_peak, peak_src = measured_peaks()
+        flops = E * (400.0 + 416.0) + 2.0 * sc.inv_depth.shape[0] * sc.P * sc.P  # linearise + JtWJ per edge, Schur per landmark (dense S)
+        line.update({"value": E * iters / (ms_dev * 1e-3), "steps": int(iters // reps), "ms_per_step": ms_dev / max(iters, 1),
+                     "lm_iters_per_sec": iters / (ms_dev * 1e-3), "solve_ms": ms_dev / reps, "solver": SOLVER_NAMES.get(int(st.solver_used)),
+                     "lm": {"chi2_initial": st.chi2_initial, "chi2_final": st.chi2_final, "iterations": int(st.iterations), "trial_steps": int(st.trial_steps)},
+                     "e2e": {"value": E * iters / t_e2e, "unit": UNIT, "seconds_per_call": t_e2e / reps,
+                             "h2d_bytes_per_step": int(8 * (sc.pose.size + sc.speedbias.size + sc.inv_depth.size) // max(K, 1)),
+                             "d2h_bytes_per_step": int(8 * (sc.pose.size + sc.speedbias.size + sc.inv_depth.size) // max(K, 1)),
+                             "call": "vio_set_vertices (+ vio_set_prior) -> vio_solve(K) -> vio_get_vertices, graph resident"},
+                     "dropin": {"value": E * st_d.iterations / t_drop, "unit": UNIT, "seconds_per_call": t_drop,
+                                "call": "vio_create -> vio_set_graph -> vio_solve(K) -> vio_get_vertices"},
+                     "roofline": {"kernel": "k_linearize_grouped", "bound": "fp64", "achieved": (flops / (lin_ms * 1e-3) / 1e12) if lin_ms > 0 else None,
+                                  "peak": fp64_peak, "unit": "TFLOP/s",
+                                  "frac": (flops / (lin_ms * 1e-3) / 1e12 / fp64_peak) if (lin_ms > 0 and fp64_peak) else None, "traffic": None,
+                                  "kernel_ms": lin_ms, "hbm_peak": hbm_peak,
+                                  "note": "a single window fills a handful of the 148 SMs: launch latency and the one-CTA dense Cholesky bound "
+                                          "the step, not a roofline (DESIGN.md section 4)"},
+                     "gpu_launches": int(launches // reps), "clocks": sampler.summary()})
+    if not args.no_cpu:
+        from tests import refshim
+        if refshim.available(ver):
+            sample = scenes[:1]
+            t0 = time.perf_counter()
+            its = refshim.solve(ver, sample[0], K)["iterations"]
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": sample[0].rp_landmark.shape[0] * its / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                                    "ms_per_solve": 1e3 * dt,
+                                    "sample": f"unmodified v{ver} backend::Problem::Solve({K}) on problem 0 of this workload (same scene, same iterations)"}
+    emit(line)
+
+
 def main():
     # stdout carries exactly one JSON line: native libraries (NCCL prints its version banner with printf at communicator
     # creation) get stderr as their fd 1 for the whole run, the JSON goes to the saved descriptor
@@ -530,7 +716,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + list(SMALL_WORKLOADS))
+    ap.add_argument("--batch-n", type=int, default=0, help="config 3: number of windows (default 4096)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--solver", "--pcg", dest="solver", default="auto", choices=list(SOLVERS),
                     help="reduced solver on the block-sparse S: auto (= block cyclic reduction on a camera ring), bcr, block PCG "
@@ -541,7 +728,9 @@ def main():
     ap.add_argument("--pcg-max-iter", type=int, default=0, help="cap PCG iterations (profiling runs only; 0 = 2P like the reference)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload in SMALL_WORKLOADS:
+        run_small(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
