@@ -164,41 +164,38 @@ def sub_scene(vio, s, lm_begin, lm_end, with_ext):
     return t
 
 
-def cpu_reference_rate(vio, scene, steps, warmup, target_s=12.0):
-    """The reference's own CPU path on a bounded sample of the workload.
+def cpu_reference_rate(vio, scene, steps, warmup, target_s=12.0, full=False):
+    """The reference's own CPU path, one core (the reference has no active threading).
 
-    oracle/_ref present -> the UNMODIFIED v17 backend: Problem::Solve(1) (MakeHessian + Schur + LDLT + chi2) on a
-    sample of landmarks small enough for its dense (P+M)^2 containers.  Otherwise the plain-C oracle port.
-    Single thread: the reference has no active threading.
+    oracle/_ref present -> `sparse17`: Problem::Solve restated with block-sparse containers around the reference's OWN
+    compiled Edge / Vertex code (oracle/ref_sparse17.cpp; reproduces the unmodified Problem::Solve to 1e-13 where that
+    fits in memory) - on the whole workload (full=True, the reference arm) or on the landmarks of its first cameras
+    (the bounded cpu_baseline leg).  Otherwise the plain-C oracle port's linearisation pass.
     """
     from tests import oraclelib as orc
     from tests import refshim
     L = scene.inv_depth.shape[0]
     out = {"cores": 1}
-    if refshim.available(17):
-        n_lm = min(2000, L)
-        sub = sub_scene(vio, scene, 0, n_lm, with_ext=True)
+    if refshim.available(17) and hasattr(refshim, "sparse_solve"):
+        if full:
+            sub, n_lm = scene, L
+            if sub.ext_pose < 0:
+                sub = sub_scene(vio, scene, 0, L, with_ext=True)
+        else:
+            # ~4 us per edge and pass, three passes per LM iteration: size the sample for about target_s seconds
+            n_lm = int(min(L, max(2000, target_s / (2 * 3 * 4e-6) / 10)))
+            sub = sub_scene(vio, scene, 0, n_lm, with_ext=True)
         E_s = sub.rp_landmark.shape[0]
-        times = []
-        for k in range(warmup + steps):
-            # steady-state cost of one LM iteration = (t[Solve(3)] - t[Solve(1)]) / 2: leaves out the initial
-            # MakeHessian + ComputeLambdaInitLM (our Solve(K) timing includes them, amortised over K: conservative)
-            t0 = time.perf_counter()
-            r1 = refshim.solve(17, sub, 1)
-            t1 = time.perf_counter()
-            r3 = refshim.solve(17, sub, 3)
-            t3 = time.perf_counter()
-            extra = max(r3["iterations"] - r1["iterations"], 1)
-            dt = ((t3 - t1) - (t1 - t0)) / extra
-            if k >= warmup:
-                times.append(dt)
-            if sum(times) > target_s and len(times) >= 1:
-                break
-        t = float(np.mean(times))
-        out.update(kind="reference", value=E_s / t, unit=UNIT, ms_per_step=t * 1e3, steps_run=len(times),
-                   sample=f"unmodified v17 backend::Problem::Solve(1) on landmarks [0,{n_lm}) of the workload "
-                          f"({E_s} edges, {sub.pose.shape[0]} poses; dense (P+M)^2 containers cap the sample size); "
-                          f"edges/s = E_sample / steady-state time per LM iteration (t[Solve(3)]-t[Solve(1)])/2")
+        K = max(1, min(int(steps), 2))
+        r = refshim.sparse_solve(sub, K, fixed_iterations=True)
+        its = max(int(r["iterations"]), 1)
+        # steady-state time per LM iteration: the initial MakeHessian + chi2 (1 of its+1 linearisations / chi2 passes) left out
+        t = (r["t_total"] - r["t_linearize"] / (its + 1) - r["t_chi2"] / (its + 1)) / its
+        out.update(kind="reference", value=E_s / t, unit=UNIT, ms_per_step=t * 1e3, steps_run=its, same_config=bool(full),
+                   breakdown_s={"linearize": r["t_linearize"], "reduced_solve_backsub": r["t_solve"], "chi2": r["t_chi2"], "total": r["t_total"]},
+                   sample=(f"reference Edge/Vertex code + block-sparse containers + Eigen SimplicialLDLT (oracle/ref_sparse17.cpp), "
+                           f"Solve({K}) on {'the whole workload' if full else f'landmarks [0,{n_lm}) of the workload'} "
+                           f"({E_s} edges, {sub.pose.shape[0]} poses); edges/s = E / steady-state seconds per LM iteration"))
     else:
         orc.lib()
         n_cal = min(20000, L)
@@ -215,7 +212,7 @@ def cpu_reference_rate(vio, scene, steps, warmup, target_s=12.0):
             if sum(times) > target_s:
                 break
         t = float(np.mean(times))
-        out.update(kind="port", value=e1 / t, unit=UNIT, ms_per_step=t * 1e3, steps_run=len(times),
+        out.update(kind="port", value=e1 / t, unit=UNIT, ms_per_step=t * 1e3, steps_run=len(times), same_config=False,
                    sample=f"plain-C oracle port, MakeHessian+Schur pass over landmarks [0,{n_lm}) ({e1} edges); reduced "
                           f"solve not included")
     return out
@@ -228,15 +225,16 @@ def run_reference(args):
     vio = importlib.import_module(PKG)
     wl = WORKLOADS[args.workload]
     scene = vio.scenes.ring(**wl)
-    r = cpu_reference_rate(vio, scene, args.steps, min(args.warmup, 1), target_s=60.0)
+    r = cpu_reference_rate(vio, scene, args.steps, min(args.warmup, 1), target_s=60.0, full=True)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps_run"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, **wl},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                         "same_config": r.get("same_config"), "breakdown_s": r.get("breakdown_s")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "host": {"nproc": os.cpu_count()},
+        "host": host_info(),
     }
     emit(line)
 
@@ -499,7 +497,8 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             cb = cpu_reference_rate(vio, scene, steps=3, warmup=1, target_s=12.0)
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
-                                    "sample": cb["sample"]}
+                                    "sample": cb["sample"], "ms_per_step": cb["ms_per_step"], "breakdown_s": cb.get("breakdown_s")}
+            line["host"] = host_info()
         emit(line)
         if parity is not None and not parity["ok"]:
             sys.stderr.write("parity_vs_n1 FAILED: %s\n" % json.dumps(parity))

@@ -42,6 +42,11 @@ int REF_FN(solve)(const vio_graph *g, const ref_prior *prior, int32_t iterations
 /* the same with the VertexPointXYZ estimates (n_point x 3) read back as well */
 int REF_FN(solve_points)(const vio_graph *g, const ref_prior *prior, int32_t iterations, double *pose, double *speedbias,
                          double *inv_depth, double *point_xyz, double *b_prior_out, double *err_prior_out, ref_result *res);
+/* v17 only (ref_sparse17.cpp): Problem::Solve restated with block-sparse containers around the reference's own
+ * Edge / Vertex code - the at-scale CPU baseline and parity target (inverse-depth landmarks, fixed extrinsic vertex,
+ * SE3 priors).  timing[4] = seconds in linearise, reduced solve + back-substitution, chi2 passes, total. */
+int ref17_sparse_solve(const vio_graph *g, int32_t iterations, int32_t fixed_iterations, double *pose_out, double *inv_depth_out,
+                       ref_result *res, double *timing);
 #ifdef __cplusplus
 }
 #endif

@@ -114,3 +114,22 @@ def solve(ver, scene, iterations):
                chi2_final=res.chi2_final, lambda_final=res.lambda_final, ms_solve=res.ms_solve, ms_hessian=res.ms_hessian,
                b_prior=bpo, err_prior=epo)
     return out
+
+
+def sparse_solve(scene, iterations, fixed_iterations=False):
+    """Problem::Solve restated with block-sparse containers around the reference's own Edge / Vertex code
+    (oracle/ref_sparse17.cpp): the at-scale CPU baseline and parity target.  v17, inverse-depth landmarks, fixed ext vertex."""
+    L = _lib(17)
+    g, keep = scene.to_c()
+    pose = np.zeros_like(scene.pose)
+    invd = np.zeros_like(scene.inv_depth)
+    res = RefResult()
+    timing = np.zeros(4)
+    L.ref17_sparse_solve.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p,
+                                     C.POINTER(C.c_double)]
+    rc = L.ref17_sparse_solve(C.byref(g), iterations, int(bool(fixed_iterations)), _d(pose), _d(invd), C.byref(res), _d(timing))
+    assert rc == 0, rc
+    n = min(res.iterations, capi.TRACE_MAX)
+    return dict(pose=pose, inv_depth=invd, iterations=res.iterations, chi2_trace=np.array(res.chi2_trace[:n]),
+                lambda_trace=np.array(res.lambda_trace[:n]), chi2_final=res.chi2_final, lambda_final=res.lambda_final,
+                t_linearize=timing[0], t_solve=timing[1], t_chi2=timing[2], t_total=timing[3])

@@ -781,3 +781,26 @@ def test_config5_size_parity(vio):
         assert np.abs(pose - pose2).max() <= FINAL_TOL * np.abs(pose2).max()
         assert np.abs(invd - invd2).max() <= FINAL_TOL * np.abs(invd2).max()
         del q
+
+
+def test_ring_solve_vs_sparse_reference(vio, refshim):
+    """At-scale parity target (SURVEY.md 8d): Problem::Solve restated with block-sparse containers around the reference's OWN
+    compiled Edge / Vertex code (oracle/ref_sparse17.cpp; equals the unmodified dense Problem::Solve to 1e-13 on TestMonoBA).
+    A 300-camera / 30 000-landmark / 300 000-edge ring - 25x what the dense reference can hold - solved by both:
+    initial cost and lambda, cost trace, final cost, poses and inverse depths within north_star's tolerances."""
+    _need_ref(refshim, 17)
+    capi = vio.capi
+    s = vio.scenes.ring(n_cam=300, n_landmark=30000, k_obs=11, seed=12, with_ext=True)
+    ref = refshim.sparse_solve(s, 4, fixed_iterations=True)
+    s.storage = capi.STORAGE_BSR
+    p = vio.Problem()
+    p.set_graph(s)
+    st = p.solve(4, vio.make_opts(flavour=capi.LM_V17, fixed_iterations=1))
+    assert st.solver_used == capi.SOLVER_BCR
+    assert st.iterations == ref["iterations"]
+    assert np.allclose(st.chi2_trace[:st.n_trace], ref["chi2_trace"], rtol=FINAL_TOL, atol=0)
+    assert np.allclose(st.lambda_trace[:st.n_trace], ref["lambda_trace"], rtol=FINAL_TOL, atol=0)
+    assert abs(st.chi2_final - ref["chi2_final"]) <= FINAL_TOL * ref["chi2_final"]
+    pose, _, invd = p.get_vertices()
+    assert np.abs(pose - ref["pose"]).max() <= FINAL_TOL * np.abs(ref["pose"]).max()
+    assert np.abs(invd - ref["inv_depth"]).max() <= FINAL_TOL * np.abs(ref["inv_depth"]).max()

@@ -297,3 +297,21 @@ def test_hessian_nullspace_known_answer(vio):
     # the other draw order does not reproduce it
     sv0 = np.linalg.svd(orc.nullspace_hessian(vio.scenes.nullspace(draw_order=0)), compute_uv=False)
     assert np.abs(sv0[:113] / ref[:113] - 1).max() > 1e-2
+
+
+def test_sparse_reference_restatement_equals_unmodified_solve(vio):
+    """oracle/ref_sparse17.cpp (block-sparse containers + Eigen SimplicialLDLT around the reference's own Edge / Vertex code)
+    reproduces the UNMODIFIED dense Problem::Solve of the v17 backend on TestMonoBA 20 x 300: same iteration count, cost and
+    lambda traces to 1e-12, final estimates to 1e-12 - which is what makes it the at-scale CPU baseline / parity target."""
+    from tests import refshim
+    if not refshim.available(17):
+        pytest.skip("oracle/_ref/libref17.so not built")
+    s = vio.scenes.monoba(20, 300, with_ext=True)
+    r1 = refshim.solve(17, s, 10)
+    r2 = refshim.sparse_solve(s, 10)
+    assert r1["iterations"] == r2["iterations"]
+    n = r2["iterations"]
+    assert np.allclose(r1["chi2_trace"][:n], r2["chi2_trace"], rtol=1e-12, atol=0)
+    assert np.allclose(r1["lambda_trace"][:n], r2["lambda_trace"], rtol=1e-12, atol=0)
+    assert abs(r1["chi2_final"] - r2["chi2_final"]) <= 1e-12 * r1["chi2_final"]
+    assert np.abs(r1["pose"] - r2["pose"]).max() <= 1e-12 and np.abs(r1["inv_depth"] - r2["inv_depth"]).max() <= 1e-12
