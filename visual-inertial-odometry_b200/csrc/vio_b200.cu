@@ -34,6 +34,7 @@
 #include "vio_bchol.cuh"
 #include "vio_bcr.h"
 #include "vio_bcr.cuh"
+#include "vio_dchol.cuh"
 
 #define VIO_VERSION_STR "vio_b200 0.1 (sm_100a)"
 
@@ -179,7 +180,7 @@ struct vio_problem {
     // block cyclic reduction (vio_bcr.*): plan built lazily per graph; bcr_state 0 = not tried, 1 = usable, -1 = pattern refused
     BcrPlan bcr;
     int bcr_state = 0;
-    bool env_no_bcr = false;
+    bool env_no_bcr = false, env_chol_legacy = false;
     unsigned bcr_epoch = 0;
     size_t bcr_smem = 0;
     int bcr_nbuf = 5;
@@ -587,7 +588,11 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
     if (solver == VIO_SOLVER_DENSE_CHOL) {
         if (p->storage != VIO_STORAGE_DENSE) return fail(p, VIO_ERR_INVALID, "dense Cholesky needs dense storage");
         const size_t tri_bytes = ((size_t)P * (P + 1) / 2 + P) * sizeof(double);
-        if (tri_bytes <= 220 * 1024) {
+        if (P <= DCH_MAX_P && !p->env_chol_legacy) {
+            // blocked (panels of 4, look-ahead, DMMA trailing updates): ~10x fewer barriers than the column-by-column kernel
+            CK(RAISE_SMEM(k_dense_chol_blocked));
+            k_dense_chol_blocked<<<1, DCH_THREADS, dch_smem_bytes(P), p->stream>>>(v.S, v.bS, lambda, P, v.dxp, p->info.p);
+        } else if (tri_bytes <= 220 * 1024) {
             if (!p->chol_smem_set) {
                 CK(RAISE_SMEM(k_dense_chol_smem));
                 p->chol_smem_set = true;
@@ -1077,6 +1082,7 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
         p->env_multikernel = getenv("VIO_B200_PCG_MULTIKERNEL") != nullptr;
         p->env_pcg_plain = getenv("VIO_B200_PCG_PLAIN") != nullptr;
         p->env_no_bcr = getenv("VIO_B200_NO_BCR") != nullptr;
+        p->env_chol_legacy = getenv("VIO_B200_CHOL_LEGACY") != nullptr;
         if (sms > 0) p->num_sms = sms;
     }
     if (cudaEventCreate(&p->ev_solve0) != cudaSuccess || cudaEventCreate(&p->ev_solve1) != cudaSuccess) {
@@ -2137,6 +2143,7 @@ static int lockstep_prepare(vio_problem *p, LockstepCache &cache, vio_batch_item
     const size_t tri_bytes = ((size_t)Pper * (Pper + 1) / 2 + Pper) * sizeof(double);
     if (tri_bytes > 220 * 1024) return fail(p, VIO_ERR_UNSUPPORTED, "lock-step batch: P=%d per problem does not fit the shared-memory Cholesky", Pper);
     CK(RAISE_SMEM(k_chol_batch));
+    CK(RAISE_SMEM(k_chol_batch_blocked));
     // ---- per-problem landmark / IMU-edge ranges (items are contiguous in the merged pack) ---------------------------
     std::vector<int> lm_prob(std::max(L, 1), 0), lm_rng(B + 1, 0), imu_rng(B + 1, 0);
     for (int k = 0; k <= B; ++k) { lm_rng[k] = (int)Loff[k]; imu_rng[k] = k * NI; }
@@ -2277,7 +2284,11 @@ static int lockstep_run(vio_problem *p, LockstepCache &cache, vio_batch_item *it
         CK(cudaMemcpyAsync(p->b_act.p, h_act.data(), B, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(p->b_lambda.p, h_lambda.data(), B * sizeof(double), cudaMemcpyHostToDevice, st));
         // SolveLinearSystem for every active problem
-        k_chol_batch<<<B, 512, tri_bytes, st>>>(p->view.S, p->view.bS, p->b_lambda.p, p->b_act.p, Pper, p->view.dxp);
+        if (Pper <= DCH_MAX_P && !p->env_chol_legacy)
+            k_chol_batch_blocked<<<B, DCH_THREADS, dch_smem_bytes(Pper), st>>>(p->view.S, p->view.bS, p->b_lambda.p, p->b_act.p, Pper, p->view.dxp,
+                                                                             p->info.p);
+        else
+            k_chol_batch<<<B, 512, tri_bytes, st>>>(p->view.S, p->view.bS, p->b_lambda.p, p->b_act.p, Pper, p->view.dxp);
         k_backsub_batch<<<B, 256, 0, st>>>(p->view, p->lm_rng.p, p->b_lambda.p, p->b_out.p);
         p->launches += 2;
         // UpdateStates (masked)
