@@ -180,7 +180,9 @@ struct vio_problem {
     // block cyclic reduction (vio_bcr.*): plan built lazily per graph; bcr_state 0 = not tried, 1 = usable, -1 = pattern refused
     BcrPlan bcr;
     int bcr_state = 0;
-    bool env_no_bcr = false, env_chol_legacy = false;
+    bool env_no_bcr = false, env_chol_legacy = false, env_schur_fused = false;
+    size_t schur_smem = 0, edge_smem = 0;
+    int edge_warps = 4;
     unsigned bcr_epoch = 0;
     size_t bcr_smem = 0;
     int bcr_nbuf = 5;
@@ -450,8 +452,21 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
             if (p->prof.n < 32) { CK(p->prof.alloc(32)); CK(cudaMemsetAsync(p->prof.p, 0, 32 * sizeof(unsigned long long), p->stream)); }
             gv.prof = p->prof.p;
         }
-        if (with_schur) k_linearize_grouped<true><<<p->n_groups, p->group_threads, p->group_smem, p->stream>>>(v, gv);
-        else k_linearize_grouped<false><<<p->n_groups, p->group_threads, p->group_smem, p->stream>>>(v, gv);
+        if (with_schur && p->env_schur_fused) {
+            k_linearize_grouped<true><<<p->n_groups, p->group_threads, p->group_smem, p->stream>>>(v, gv);
+        } else {
+            // edges + J^T W J + rows of H_lp, then (with_schur) the Schur complement of every group on the FP64 tensor cores
+            switch (p->edge_warps) {
+            case 2: k_lin_edges<64, 6><<<p->n_groups, 64, p->edge_smem, p->stream>>>(v, gv); break;
+            case 3: k_lin_edges<96, 4><<<p->n_groups, 96, p->edge_smem, p->stream>>>(v, gv); break;
+            case 5: k_lin_edges<160, 2><<<p->n_groups, 160, p->edge_smem, p->stream>>>(v, gv); break;
+            default: k_lin_edges<128, 3><<<p->n_groups, 128, p->edge_smem, p->stream>>>(v, gv); break;
+            }
+            if (with_schur) {
+                k_schur_groups<<<p->n_groups, VIO_SCHUR_THREADS, p->schur_smem, p->stream>>>(v, gv);
+                p->launches++;
+            }
+        }
         p->launches++;
     } else if (p->L > 0) {
         if (with_schur) k_linearize_lm<true><<<grid_for(p->L, 128), 128, 0, p->stream>>>(v);
@@ -1083,6 +1098,7 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
         p->env_pcg_plain = getenv("VIO_B200_PCG_PLAIN") != nullptr;
         p->env_no_bcr = getenv("VIO_B200_NO_BCR") != nullptr;
         p->env_chol_legacy = getenv("VIO_B200_CHOL_LEGACY") != nullptr;
+        p->env_schur_fused = getenv("VIO_B200_SCHUR_FUSED") != nullptr;
         if (sms > 0) p->num_sms = sms;
     }
     if (cudaEventCreate(&p->ev_solve0) != cudaSuccess || cudaEventCreate(&p->ev_solve1) != cudaSuccess) {
@@ -1258,6 +1274,27 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
         CK(upload(p->g_pairinfo, K.g_pairinfo.data(), K.g_pairinfo.size(), s));
         CK(upload(p->ell_pjx, K.ell_pjx.data(), K.ell_pjx.size(), s)); CK(upload(p->ell_pjy, K.ell_pjy.data(), K.ell_pjy.size(), s));
         CK(upload(p->ell_edge, K.ell_edge.data(), K.ell_edge.size(), s));
+        {
+            // largest group decides the Schur kernel's shared memory (ns slots, nlm landmarks per group header)
+            size_t mx = 0;
+            for (int gi = 0; gi < K.n_groups; ++gi) mx = std::max(mx, schur_smem_bytes(K.g_hdr[8 * (size_t)gi + 1], K.g_hdr[8 * (size_t)gi + 3]));
+            p->schur_smem = mx;
+            CK(RAISE_SMEM(k_schur_groups));
+            // edge kernel: 2..5 warps per CTA (VIO_B200_EDGE_WARPS; default 4), shared memory of the largest group
+            int ew = 4;
+            if (const char *ev = getenv("VIO_B200_EDGE_WARPS")) ew = atoi(ev);
+            if (ew < 2 || ew > VIO_EDGE_WARPS_MAX) ew = 4;
+            p->edge_warps = ew;
+            size_t me = 0;
+            for (int gi = 0; gi < K.n_groups; ++gi) me = std::max(me, edges_smem_bytes(K.g_hdr[8 * (size_t)gi + 1], K.g_hdr[8 * (size_t)gi + 3], ew));
+            p->edge_smem = me;
+            switch (ew) {
+            case 2: CK(raise_smem_cap((const void *)k_lin_edges<64, 6>)); break;
+            case 3: CK(raise_smem_cap((const void *)k_lin_edges<96, 4>)); break;
+            case 5: CK(raise_smem_cap((const void *)k_lin_edges<160, 2>)); break;
+            default: CK(raise_smem_cap((const void *)k_lin_edges<128, 3>)); break;
+            }
+        }
         CK(RAISE_SMEM(k_linearize_grouped<true>));
         CK(RAISE_SMEM(k_linearize_grouped<false>));
         // landmarks without edges are outside every group: their outputs stay zero

@@ -424,3 +424,436 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         atomicAdd(gv.prof + 7, ns1 - prof_ns0_);
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_lin_edges — the edge half of the split pipeline (round 2): residuals, Jacobian algebra, J^T W J / J^T W r of every group,
+// the per-landmark H_ll, b_l and the rows of H_lp; the Schur complement itself is k_schur_groups' (below).
+// Same per-edge arithmetic and the same warp <-> observer slot, lane <-> landmark mapping as k_linearize_grouped, but sized
+// for SEVERAL small CTAs per SM instead of one big one, so that the serial phases of one group (setup, host chain,
+// landmark sums, flush) overlap the edge phase of its neighbours:
+//   * 2..5 warps per CTA, at most 168 registers (launch bounds keep 12 warps resident per SM),
+//   * no group tile T and no shared copy of H_lp (the rows go straight to HBM; back-substitution and the Schur kernel read them),
+//   * the per-(landmark, slot) matrices M, m are not kept: every warp adds them into ITS OWN partial per-landmark sums
+//     lmS[warp][landmark][9] (a warp walks its slots one after the other, lanes are distinct landmarks: no races, no
+//     atomics, fixed order), the landmark phase adds the <= 5 partials.
+// Shared memory: ~45 KB for a 100-landmark, 11-slot group with 4 warps (the fused kernel: 169 KB).
+// Reference dataflow replaced: Problem::MakeHessian (A15/backend/problem.cc:280-337; A17/src/backend/problem.cc:303-389).
+// ------------------------------------------------------------------------------------------------------------------
+#define VIO_EDGE_WARPS_MAX 5
+__host__ __device__ inline size_t edges_smem_bytes(int ns, int nlm, int nw) {
+    // doubles: pc[ns][12] rjric[ns][9] lmh[nlm][17] lmS[nw][nlm][9] red[ns][48] bvec[ns][12]; ints: pose_id[ns] fixed[ns] off[ns]
+    const size_t dbl = (size_t)ns * 12 + (size_t)ns * 9 + (size_t)nlm * 17 + (size_t)nw * nlm * 9 + (size_t)ns * 48 + (size_t)ns * 12;
+    return dbl * sizeof(double) + 3 * (size_t)ns * sizeof(int);
+}
+__device__ __forceinline__ int pair_index(int a, int b, int ns) { return a * ns - (a * (a - 1)) / 2 + (b - a); }
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_lin_edges(DevView v, GroupView gv) {
+    extern __shared__ double sm[];
+    const GroupHdr h = gv.hdr[blockIdx.x];
+    const int ns = h.ns, nlm = h.nlm;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    constexpr int LHS = 17;
+    double *pc = sm;                                  // [ns][12]
+    double *rjric = pc + (size_t)ns * 12;             // [ns][9]
+    double *lmh = rjric + (size_t)ns * 9;             // [nlm][17]  pw(3) g(3) G(9)
+    double *lmS = lmh + (size_t)nlm * LHS;            // [nw][nlm][9]  per-warp partial sums of M(6) m(3)
+    double *red = lmS + (size_t)nw * nlm * 9;         // [ns][48]
+    double *bvec = red + (size_t)ns * 48;             // [ns][12]  bp(6) hdiag(6)
+    int *pose_id = (int *)(bvec + (size_t)ns * 12);   // [ns]
+    int *pfix = pose_id + ns;
+    int *poff = pfix + ns;
+
+    long long prof_t_ = gv.prof ? clock64() : 0;
+    unsigned long long prof_ns0_ = 0;
+    if (gv.prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ns0_));
+    // ---- phase 0: slot table, pose cache ------------------------------------------------------------------------
+    for (int s = tid; s < ns; s += nt) {
+        const int pid = s == 0 ? h.host : gv.slot_pose[h.slot0 + s];
+        pose_id[s] = pid;
+        pfix[s] = v.pose_fixed[pid];
+        poff[s] = v.pose_off[pid];
+    }
+    for (int i = tid; i < ns * 12; i += nt) {
+        const int s = i / 12, k = i - 12 * s;
+        const int pid = s == 0 ? h.host : gv.slot_pose[h.slot0 + s];
+        pc[i] = v.poseRT[16 * (size_t)pid + k];
+    }
+    for (int i = tid; i < ns * 48; i += nt) red[i] = 0.0;
+    // slots of a warp: 1 + wid, 1 + wid + nw, ...; a warp without a slot leaves its partial sums untouched: zero them
+    if (1 + wid >= ns)
+        for (int i = lane; i < nlm * 9; i += 32) lmS[(size_t)wid * nlm * 9 + i] = 0.0;
+    __syncthreads();
+    for (int s = tid; s < ns; s += nt) mat3_mul(pc + 12 * (size_t)s, v.Ric, rjric + 9 * (size_t)s);
+    const bool hfix = pfix[0] != 0;
+    VIO_PROF_MARK(0);
+
+    // ---- phase 0.5: per-landmark host chain (needs pc only) ----------------------------------------------------------
+    for (int l = tid; l < nlm; l += nt) {
+        const int gl = h.lm0 + l;
+        const double lam = v.invdep[gl];
+        const double pts_i[3] = {v.lm_pix[gl], v.lm_piy[gl], v.lm_piz[gl]};
+        const double pci[3] = {pts_i[0] / lam, pts_i[1] / lam, pts_i[2] / lam};
+        double pbi[3], pw[3], tmp[3], g[3], G[9];
+        mat3_mul_vec(v.Ric, pci, pbi);
+        pbi[0] += v.tic[0]; pbi[1] += v.tic[1]; pbi[2] += v.tic[2];
+        mat3_mul_vec(pc, pbi, pw);
+        pw[0] += pc[9]; pw[1] += pc[10]; pw[2] += pc[11];
+        mat3_mul_vec(v.Ric, pts_i, tmp);
+        mat3_mul_vec(pc, tmp, g);
+        const double il2 = -1.0 / (lam * lam);
+        mat3_mul_hat(pc, pbi, G);
+        double *o = lmh + LHS * (size_t)l;
+        o[0] = pw[0]; o[1] = pw[1]; o[2] = pw[2];
+        o[3] = g[0] * il2; o[4] = g[1] * il2; o[5] = g[2] * il2;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o[6 + k] = -G[k];
+    }
+    __syncthreads();
+    VIO_PROF_MARK(1);
+
+    // ---- phase 1: edges, slot-major.  warp <-> slot, lanes <-> landmarks ----------------------------------------
+    double *myS = lmS + (size_t)wid * nlm * 9;
+    for (int s = 1 + wid; s < ns; s += nw) {
+        const double *RTj = pc + 12 * (size_t)s;
+        const double *RjRic = rjric + 9 * (size_t)s;
+        const bool jfix = pfix[s] != 0;
+        const bool first = s == 1 + wid;  // the warp's first slot initialises its partial sums
+        double acc[48];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) acc[k] = 0.0;
+        const size_t ebase = (size_t)h.ell0 + (size_t)(s - 1) * nlm;
+        double n_pjx = 0.0, n_pjy = 0.0;
+        int n_edge = -1;
+        if (lane < nlm) { n_pjx = gv.ell_pjx[ebase + lane]; n_pjy = gv.ell_pjy[ebase + lane]; n_edge = gv.ell_edge[ebase + lane]; }
+        for (int l = lane; l < nlm; l += 32) {
+            const double pjx = n_pjx, pjy = n_pjy;
+            const int edge = n_edge;
+            if (l + 32 < nlm) { n_pjx = gv.ell_pjx[ebase + l + 32]; n_pjy = gv.ell_pjy[ebase + l + 32]; n_edge = gv.ell_edge[ebase + l + 32]; }
+            double *ls = myS + 9 * (size_t)l;
+            if (pjx != pjx) {  // NaN: this landmark is not observed from slot s
+                if (first) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) ls[k] = 0.0;
+                }
+                continue;
+            }
+            const double *lh = lmh + LHS * (size_t)l;
+            const double pw[3] = {lh[0], lh[1], lh[2]};
+            double pcj[3], pbj[3], r[2];
+            reproj_residual(v.Ric, v.tic, RTj, pw, pjx, pjy, pcj, pbj, r);
+            const double iz = 1.0 / pcj[2];
+            const double rx = -pcj[0] * iz * iz, ry = -pcj[1] * iz * iz;
+            double B[6];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                B[c] = iz * RjRic[3 * c + 0] + rx * RjRic[3 * c + 2];
+                B[3 + c] = iz * RjRic[3 * c + 1] + ry * RjRic[3 * c + 2];
+            }
+            double rho0, drho, W[3];
+            robust_weights(v.rp_loss, v.rp_delta, v.rp_info, r, rho0, drho, W);
+            double WB[6];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                WB[c] = W[0] * B[c] + W[1] * B[3 + c];
+                WB[3 + c] = W[1] * B[c] + W[2] * B[3 + c];
+            }
+            double M[9];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) M[3 * a + b] = B[a] * WB[b] + B[3 + a] * WB[3 + b];
+            const double dc = drho * v.rp_info;
+            const double m[3] = {dc * (B[0] * r[0] + B[3] * r[1]), dc * (B[1] * r[0] + B[4] * r[1]),
+                                 dc * (B[2] * r[0] + B[5] * r[1])};
+            if (first) {
+                ls[0] = M[0]; ls[1] = M[1]; ls[2] = M[2]; ls[3] = M[4]; ls[4] = M[5]; ls[5] = M[8];
+                ls[6] = m[0]; ls[7] = m[1]; ls[8] = m[2];
+            } else {
+                ls[0] += M[0]; ls[1] += M[1]; ls[2] += M[2]; ls[3] += M[4]; ls[4] += M[5]; ls[5] += M[8];
+                ls[6] += m[0]; ls[7] += m[1]; ls[8] += m[2];
+            }
+            double2 *wog = reinterpret_cast<double2 *>(v.wo + 6 * (size_t)edge);
+            if (jfix) {
+                wog[0] = make_double2(0.0, 0.0); wog[1] = make_double2(0.0, 0.0); wog[2] = make_double2(0.0, 0.0);
+                continue;
+            }
+            double N[9], MN[9], NMN[9], Ntm[3], Mg[3], NtMg[3];
+            mat3_mul_hat(RTj, pbj, N);
+            mat3_mul(M, N, MN);
+            mat3t_mul(N, MN, NMN);
+            mat3t_mul_vec(N, m, Ntm);
+            const double g[3] = {lh[3], lh[4], lh[5]};
+            mat3_mul_vec(M, g, Mg);
+            mat3t_mul_vec(N, Mg, NtMg);
+            wog[0] = make_double2(-Mg[0], -Mg[1]); wog[1] = make_double2(-Mg[2], NtMg[0]); wog[2] = make_double2(NtMg[1], NtMg[2]);
+            acc[0] += M[0]; acc[1] += M[1]; acc[2] += M[2]; acc[3] += M[4]; acc[4] += M[5]; acc[5] += M[8];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[6 + k] += MN[k];
+            acc[33] += NMN[0]; acc[34] += NMN[1]; acc[35] += NMN[2]; acc[36] += NMN[4]; acc[37] += NMN[5]; acc[38] += NMN[8];
+            acc[39] += m[0]; acc[40] += m[1]; acc[41] += m[2];
+            acc[42] += Ntm[0]; acc[43] += Ntm[1]; acc[44] += Ntm[2];
+            if (!hfix) {
+                const double *G = lh + 6;
+                double GtM[9], GtMN[9];
+                mat3t_mul(G, M, GtM);
+                mat3t_mul(G, MN, GtMN);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { acc[15 + k] += GtM[k]; acc[24 + k] += GtMN[k]; }
+            }
+        }
+        const int base = reduce_scatter48(acc, lane);
+        red[48 * (size_t)s + base] = acc[0];
+        if (!(lane & 1)) red[48 * (size_t)s + base + 1] = acc[1];
+    }
+    __syncthreads();
+    VIO_PROF_MARK(2);
+
+    // ---- phase 1.5: per-landmark sums -> H_ll, b_l, host row of H_lp, host blocks ------------------------------
+    {
+        const int ncopy = min(nw, ns - 1) > 0 ? nw : 0;  // every warp's copy is initialised (first slot or zero fill)
+        double hb[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) hb[k] = 0.0;
+        for (int l = tid; l < nlm; l += nt) {
+            double Ms[6] = {0, 0, 0, 0, 0, 0}, ms[3] = {0, 0, 0};
+            for (int c = 0; c < ncopy; ++c) {
+                const double *q = lmS + ((size_t)c * nlm + l) * 9;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) Ms[k] += q[k];
+                ms[0] += q[6]; ms[1] += q[7]; ms[2] += q[8];
+            }
+            const double *lh = lmh + LHS * (size_t)l;
+            const double g[3] = {lh[3], lh[4], lh[5]};
+            const double *G = lh + 6;
+            const double Msf[9] = {Ms[0], Ms[1], Ms[2], Ms[1], Ms[3], Ms[4], Ms[2], Ms[4], Ms[5]};
+            double Mg[3];
+            mat3_mul_vec(Msf, g, Mg);
+            const double Hll = g[0] * Mg[0] + g[1] * Mg[1] + g[2] * Mg[2];
+            const double bl = -(g[0] * ms[0] + g[1] * ms[1] + g[2] * ms[2]);
+            const int gl = h.lm0 + l;
+            v.Hll[gl] = Hll;
+            v.bl[gl] = bl;
+            double wh[6] = {0, 0, 0, 0, 0, 0};
+            if (!hfix) {
+                double GtMg[3], MG[9], GtMG[9], Gtm[3];
+                mat3t_mul_vec(G, Mg, GtMg);
+                wh[0] = Mg[0]; wh[1] = Mg[1]; wh[2] = Mg[2]; wh[3] = GtMg[0]; wh[4] = GtMg[1]; wh[5] = GtMg[2];
+                mat3_mul(Msf, G, MG);
+                mat3t_mul(G, MG, GtMG);
+                mat3t_mul_vec(G, ms, Gtm);
+                hb[0] += Msf[0]; hb[1] += Msf[1]; hb[2] += Msf[2]; hb[3] += MG[0]; hb[4] += MG[1]; hb[5] += MG[2];
+                hb[6] += Msf[4]; hb[7] += Msf[5]; hb[8] += MG[3]; hb[9] += MG[4]; hb[10] += MG[5];
+                hb[11] += Msf[8]; hb[12] += MG[6]; hb[13] += MG[7]; hb[14] += MG[8];
+                hb[15] += GtMG[0]; hb[16] += GtMG[1]; hb[17] += GtMG[2];
+                hb[18] += GtMG[4]; hb[19] += GtMG[5];
+                hb[20] += GtMG[8];
+                hb[21] -= ms[0]; hb[22] -= ms[1]; hb[23] -= ms[2]; hb[24] -= Gtm[0]; hb[25] -= Gtm[1]; hb[26] -= Gtm[2];
+            }
+            double2 *whg = reinterpret_cast<double2 *>(v.wh + 6 * (size_t)gl);
+            whg[0] = make_double2(wh[0], wh[1]); whg[1] = make_double2(wh[2], wh[3]); whg[2] = make_double2(wh[4], wh[5]);
+        }
+        // block reduction of the 27 host values: warp reduce-scatter, then the warps add their parts one after the other
+        // (fixed order: the result does not depend on scheduling)
+        const int base = reduce_scatter32(hb, lane);
+        for (int w2 = 0; w2 < nw; ++w2) {
+            if (w2 == wid && wid * 32 < nlm && base < 27) red[base] += hb[0];
+            __syncthreads();
+        }
+    }
+    VIO_PROF_MARK(3);
+
+    // ---- b_p and diag(H_pp) of every slot ----------------------------------------------------------------------
+    for (int idx = tid; idx < ns * 6; idx += nt) {
+        const int s = idx / 6, k = idx - 6 * s;
+        double bp, hd;
+        if (s == 0) {
+            bp = red[21 + k];
+            hd = red[sym6_index(k, k)];
+        } else {
+            const double *R = red + 48 * (size_t)s;
+            bp = k < 3 ? R[39 + k] : -R[42 + (k - 3)];
+            hd = k < 3 ? R[sym3_index(k, k)] : R[33 + sym3_index(k - 3, k - 3)];
+        }
+        if (!pfix[s]) {
+            atomicAdd(v.bp + poff[s] + k, bp);
+            atomicAdd(v.hdiag + poff[s] + k, hd);
+        }
+    }
+    VIO_PROF_MARK(4);
+    VIO_PROF_MARK(5);
+    // ---- flush of the direct (J^T W J) blocks: (0,0), (0,s), (s,s) -- one RED.F64 per element ----------------------------
+    const int nblk = 2 * ns - 1;  // block 0 = (0,0); 1..ns-1 = (0,s); ns..2ns-2 = (s,s)
+    for (int idx = tid; idx < nblk * 36; idx += nt) {
+        const int bi = idx / 36, k = idx - 36 * bi, r = k / 6, c = k - 6 * r;
+        int a, b;
+        if (bi == 0) { a = 0; b = 0; }
+        else if (bi < ns) { a = 0; b = bi; }
+        else { a = bi - ns + 1; b = a; }
+        const long long info = gv.pairinfo[h.pair0 + pair_index(a, b, ns)];
+        const int flags = (int)(info & 3);
+        if (flags == 3) continue;
+        if (flags == 2 && r > c) continue;
+        const size_t off = (size_t)(info >> 2);
+        const size_t e = flags == 1 ? (size_t)c * gv.ld + r : (size_t)r * gv.ld + c;
+        double val;
+        if (b == 0) {
+            val = red[sym6_index(r, c)];
+        } else if (a == 0) {
+            const double *R = red + 48 * (size_t)b;  // (0,s) = [[-A1, A2],[-A3, A4]]
+            if (r < 3 && c < 3) val = -R[sym3_index(r, c)];
+            else if (r < 3) val = R[6 + 3 * r + (c - 3)];
+            else if (c < 3) val = -R[15 + 3 * (r - 3) + c];
+            else val = R[24 + 3 * (r - 3) + (c - 3)];
+        } else {
+            const double *R = red + 48 * (size_t)a;  // (s,s) = [[A1, -A2],[-A2^T, A5]]
+            if (r < 3 && c < 3) val = R[sym3_index(r, c)];
+            else if (r < 3) val = -R[6 + 3 * r + (c - 3)];
+            else if (c < 3) val = -R[6 + 3 * c + (r - 3)];
+            else val = R[33 + sym3_index(r - 3, c - 3)];
+        }
+        if (val != 0.0) atomicAdd(v.S + off + e, val);
+    }
+    VIO_PROF_MARK(6);
+    if (gv.prof && threadIdx.x == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        atomicAdd(gv.prof + 7, ns1 - prof_ns0_);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_schur_groups — the Schur complement of a landmark group as ONE symmetric rank-nlm update on the FP64 tensor cores
+// (round 2; the second half of the split pipeline).  Per group, with W (nlm x 6 ns) = the landmarks' rows of H_lp (host row
+// from wh, observer rows from wo via the group's ELL edge table), h = 1 / H_ll and V = diag(sqrt h) [W | b_l]:
+//     -V^T V  -> the 6x6 blocks (a, b), a <= b, of the reduced camera system   (A17/src/backend/problem.cc:412-431)
+//     and, in its last column, b_corr = W^T diag(h) b_l                          (:424-427)
+// Scaling the rows by sqrt(h) once while they are gathered keeps the inner loop free of FP64 multiplies and lets both DMMA
+// operands come from the same array.  The upper-triangular 8x8 tiles are dealt out evenly (row-major runs of at most
+// VIO_SCHUR_TPW tiles per warp and pass, so consecutive tiles of a warp share their row fragment); the k loop runs over
+// landmarks in steps of 4; fragments are 4 landmarks x 8 consecutive columns of V (row stride padded against bank
+// conflicts).  The finished tiles go straight from the accumulator registers to S with one RED.F64 per element.
+// Few registers and ~60 KB of shared memory: three CTAs per SM.
+// ------------------------------------------------------------------------------------------------------------------
+#define VIO_SCHUR_THREADS 256
+#define VIO_SCHUR_TPW 6
+__host__ __device__ inline int schur_ldw(int ns) {
+    int ld = 6 * ns + 1;            // + the b_l column
+    ld = (ld + 7) & ~7;             // whole 8-column tiles
+    while (!(ld % 16 == 4 || ld % 16 == 12)) ld += 4;  // the 4 rows of a fragment land on distinct bank groups
+    return ld;
+}
+__host__ __device__ inline size_t schur_smem_bytes(int ns, int nlm) {
+    const int kp = (nlm + 3) & ~3, npairs = ns * (ns + 1) / 2;
+    return (size_t)kp * schur_ldw(ns) * sizeof(double) + (size_t)npairs * sizeof(long long) + 2 * (size_t)ns * sizeof(int);
+}
+__device__ __forceinline__ void schur_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(VIO_SCHUR_THREADS, 3) k_schur_groups(DevView v, GroupView gv) {
+    extern __shared__ __align__(16) double ssm[];
+    const GroupHdr h = gv.hdr[blockIdx.x];
+    const int ns = h.ns, nlm = h.nlm, npairs = ns * (ns + 1) / 2;
+    const int kp = (nlm + 3) & ~3, LDW = schur_ldw(ns), D = 6 * ns;  // column D of V holds sqrt(h) b_l
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5, g = lane >> 2, q = lane & 3;
+    double *W = ssm;                                   // [kp][LDW]
+    long long *pinfo_s = (long long *)(W + (size_t)kp * LDW);  // [npairs]
+    int *poff = (int *)(pinfo_s + npairs);             // [ns]
+    int *pfix = poff + ns;
+    for (int s = tid; s < ns; s += nt) {
+        const int pid = s == 0 ? h.host : gv.slot_pose[h.slot0 + s];
+        pfix[s] = v.pose_fixed[pid];
+        poff[s] = v.pose_off[pid];
+    }
+    for (int p = tid; p < npairs; p += nt) pinfo_s[p] = gv.pairinfo[h.pair0 + p];
+    // ---- gather V: 6 doubles per (landmark, slot) as three 16-byte loads, scaled by sqrt(1 / H_ll)
+    for (int t = tid; t < kp * ns; t += nt) {
+        const int s = t / kp, l = t - s * kp;  // landmarks fastest: the ELL edge table is read coalesced
+        double2 w01 = make_double2(0.0, 0.0), w23 = w01, w45 = w01;
+        if (l < nlm) {
+            const double *src = nullptr;
+            if (s == 0) src = v.wh + 6 * (size_t)(h.lm0 + l);
+            else {
+                const int e = gv.ell_edge[(size_t)h.ell0 + (size_t)(s - 1) * nlm + l];
+                if (e >= 0) src = v.wo + 6 * (size_t)e;
+            }
+            if (src) {
+                const double hll = v.Hll[h.lm0 + l];
+                const double sc = hll > 0.0 ? rsqrt(hll) : 0.0;
+                const double2 *s2 = reinterpret_cast<const double2 *>(src);
+                w01 = s2[0]; w23 = s2[1]; w45 = s2[2];
+                w01.x *= sc; w01.y *= sc; w23.x *= sc; w23.y *= sc; w45.x *= sc; w45.y *= sc;
+            }
+        }
+        double *dst = W + (size_t)l * LDW + 6 * s;
+        dst[0] = w01.x; dst[1] = w01.y; dst[2] = w23.x; dst[3] = w23.y; dst[4] = w45.x; dst[5] = w45.y;
+    }
+    for (int l = tid; l < kp; l += nt) {
+        double b = 0.0;
+        if (l < nlm) {
+            const double hll = v.Hll[h.lm0 + l];
+            b = hll > 0.0 ? v.bl[h.lm0 + l] * rsqrt(hll) : 0.0;
+        }
+        double *row = W + (size_t)l * LDW;
+        row[D] = b;
+        for (int c = D + 1; c < LDW; ++c) row[c] = 0.0;
+    }
+    __syncthreads();
+    // ---- tiles (ti <= tj) of the (D + 1)-column product: warp w takes the row-major run [w * per, (w + 1) * per)
+    const int TR = (D + 1 + 7) >> 3, ntiles = TR * (TR + 1) / 2;
+    const int per = (ntiles + nw - 1) / nw;
+    const int wbeg = warp * per, wend = min(ntiles, wbeg + per);
+    for (int t0 = wbeg; t0 < wend; t0 += VIO_SCHUR_TPW) {
+        int ti[VIO_SCHUR_TPW], tj[VIO_SCHUR_TPW];
+        double c[VIO_SCHUR_TPW][2];
+#pragma unroll
+        for (int u = 0; u < VIO_SCHUR_TPW; ++u) {
+            // invert t = ti * TR - ti (ti - 1) / 2 + (tj - ti); slots past the run repeat its last tile and are not flushed
+            int t = min(t0 + u, wend - 1), a = 0;
+            while (t >= TR - a) { t -= TR - a; ++a; }
+            ti[u] = a; tj[u] = a + t;
+            c[u][0] = c[u][1] = 0.0;
+        }
+        const int nact = min(VIO_SCHUR_TPW, wend - t0);
+        const double *row = W + (size_t)q * LDW + g;
+#pragma unroll 2
+        for (int k0 = 0; k0 < kp; k0 += 4, row += 4 * (size_t)LDW) {
+            double a[VIO_SCHUR_TPW], b[VIO_SCHUR_TPW];
+#pragma unroll
+            for (int u = 0; u < VIO_SCHUR_TPW; ++u) {
+                b[u] = row[8 * tj[u]];
+                a[u] = (u > 0 && ti[u] == ti[u - 1]) ? a[u - 1] : row[8 * ti[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < VIO_SCHUR_TPW; ++u)
+                if (u < nact) schur_dmma(c[u][0], c[u][1], a[u], b[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < VIO_SCHUR_TPW; ++u) {
+            if (u >= nact) continue;
+            const int i = 8 * ti[u] + g;
+            if (i >= D) continue;
+            const int sa = i / 6, r = i - 6 * sa;
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+                const int j = 8 * tj[u] + 2 * q + e2;
+                const double val = c[u][e2];
+                if (j > D || val == 0.0) continue;
+                if (j == D) {  // b_corr of row i
+                    if (!pfix[sa]) atomicAdd(v.bcorr + poff[sa] + r, val);
+                    continue;
+                }
+                const int sb = j / 6, cc = j - 6 * sb;
+                if (sa > sb) continue;
+                const long long info = pinfo_s[sa * ns - (sa * (sa - 1)) / 2 + (sb - sa)];
+                const int flags = (int)(info & 3);
+                if (flags == 3) continue;
+                if (flags == 2 && r > cc) continue;
+                const size_t off = (size_t)(info >> 2);
+                const size_t el = flags == 1 ? (size_t)cc * gv.ld + r : (size_t)r * gv.ld + cc;
+                atomicAdd(v.S + off + el, -val);
+            }
+        }
+    }
+}
