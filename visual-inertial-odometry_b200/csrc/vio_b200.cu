@@ -182,7 +182,7 @@ struct vio_problem {
     int bcr_state = 0;
     bool env_no_bcr = false, env_chol_legacy = false, env_schur_fused = false;
     size_t schur_smem = 0, edge_smem = 0;
-    int edge_warps = 4;
+    int edge_warps = 4, edge_spw = 1;
     unsigned bcr_epoch = 0;
     size_t bcr_smem = 0;
     int bcr_nbuf = 5;
@@ -434,6 +434,23 @@ int do_pose_prep(vio_problem *p) {
     return VIO_OK;
 }
 
+// the edge kernel comes in (warps per CTA) x (slots per round) instantiations; cap_only raises the dynamic shared-memory cap
+template <int MAXT, int MINB, int SPW>
+static int lin_edges_inst(vio_problem *p, const DevView &v, const GroupView &gv, bool cap_only) {
+    if (cap_only) { CK(raise_smem_cap((const void *)k_lin_edges<MAXT, MINB, SPW>)); return VIO_OK; }
+    k_lin_edges<MAXT, MINB, SPW><<<p->n_groups, MAXT, p->edge_smem, p->stream>>>(v, gv);
+    return VIO_OK;
+}
+static int launch_lin_edges(vio_problem *p, const DevView &v, const GroupView &gv, bool cap_only) {
+    const bool two = p->edge_spw == 2;
+    switch (p->edge_warps) {
+    case 2: return two ? lin_edges_inst<64, 6, 2>(p, v, gv, cap_only) : lin_edges_inst<64, 6, 1>(p, v, gv, cap_only);
+    case 3: return two ? lin_edges_inst<96, 4, 2>(p, v, gv, cap_only) : lin_edges_inst<96, 4, 1>(p, v, gv, cap_only);
+    case 5: return two ? lin_edges_inst<160, 2, 2>(p, v, gv, cap_only) : lin_edges_inst<160, 2, 1>(p, v, gv, cap_only);
+    default: return two ? lin_edges_inst<128, 3, 2>(p, v, gv, cap_only) : lin_edges_inst<128, 3, 1>(p, v, gv, cap_only);
+    }
+}
+
 int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
     const DevView &v = p->view;
     const size_t sys_n = p->s_count + 3 * (size_t)p->P;
@@ -456,12 +473,7 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
             k_linearize_grouped<true><<<p->n_groups, p->group_threads, p->group_smem, p->stream>>>(v, gv);
         } else {
             // edges + J^T W J + rows of H_lp, then (with_schur) the Schur complement of every group on the FP64 tensor cores
-            switch (p->edge_warps) {
-            case 2: k_lin_edges<64, 6><<<p->n_groups, 64, p->edge_smem, p->stream>>>(v, gv); break;
-            case 3: k_lin_edges<96, 4><<<p->n_groups, 96, p->edge_smem, p->stream>>>(v, gv); break;
-            case 5: k_lin_edges<160, 2><<<p->n_groups, 160, p->edge_smem, p->stream>>>(v, gv); break;
-            default: k_lin_edges<128, 3><<<p->n_groups, 128, p->edge_smem, p->stream>>>(v, gv); break;
-            }
+            launch_lin_edges(p, v, gv, false);
             if (with_schur) {
                 k_schur_groups<<<p->n_groups, VIO_SCHUR_THREADS, p->schur_smem, p->stream>>>(v, gv);
                 p->launches++;
@@ -1288,12 +1300,16 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
             size_t me = 0;
             for (int gi = 0; gi < K.n_groups; ++gi) me = std::max(me, edges_smem_bytes(K.g_hdr[8 * (size_t)gi + 1], K.g_hdr[8 * (size_t)gi + 3], ew));
             p->edge_smem = me;
-            switch (ew) {
-            case 2: CK(raise_smem_cap((const void *)k_lin_edges<64, 6>)); break;
-            case 3: CK(raise_smem_cap((const void *)k_lin_edges<96, 4>)); break;
-            case 5: CK(raise_smem_cap((const void *)k_lin_edges<160, 2>)); break;
-            default: CK(raise_smem_cap((const void *)k_lin_edges<128, 3>)); break;
+            // slots per round: 1 (32 landmarks x 1 slot) or 2 (16 landmarks x 2 slots), whichever needs fewer rounds
+            long long r1 = 0, r2 = 0;
+            for (int gi = 0; gi < K.n_groups; ++gi) {
+                const int ns = K.g_hdr[8 * (size_t)gi + 1], nlm = K.g_hdr[8 * (size_t)gi + 3];
+                r1 += (long long)((nlm + 31) / 32) * (ns - 1);
+                r2 += (long long)((nlm + 15) / 16) * (ns / 2);
             }
+            p->edge_spw = r2 < r1 ? 2 : 1;
+            if (const char *ev = getenv("VIO_B200_EDGE_SPW")) p->edge_spw = atoi(ev) == 2 ? 2 : 1;
+            { const int rc_cap = launch_lin_edges(p, p->view, GroupView(), true); if (rc_cap) return rc_cap; }
         }
         CK(RAISE_SMEM(k_linearize_grouped<true>));
         CK(RAISE_SMEM(k_linearize_grouped<false>));

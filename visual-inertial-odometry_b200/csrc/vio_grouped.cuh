@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         pair_a[p] = a;
         pair_b[p] = a + rem;
     }
-    if (!h.pad) {  // pad = 1: every landmark of the group is observed from every slot -> all entries get written
+    if (!(h.pad & 1)) {  // bit 0: every landmark of the group is observed from every slot -> all entries get written
         for (size_t i = tid; i < (size_t)nlm * ns * 6; i += nt) w[i] = 0.0;
         for (size_t i = tid; i < (size_t)nlm * LMS; i += nt) lmM[i] = 0.0;
     }
@@ -441,36 +441,48 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
 // ------------------------------------------------------------------------------------------------------------------
 #define VIO_EDGE_WARPS_MAX 5
 __host__ __device__ inline size_t edges_smem_bytes(int ns, int nlm, int nw) {
-    // doubles: pc[ns][12] rjric[ns][9] lmh[nlm][17] lmS[nw][nlm][9] red[ns][48] bvec[ns][12]; ints: pose_id[ns] fixed[ns] off[ns]
-    const size_t dbl = (size_t)ns * 12 + (size_t)ns * 9 + (size_t)nlm * 17 + (size_t)nw * nlm * 9 + (size_t)ns * 48 + (size_t)ns * 12;
-    return dbl * sizeof(double) + 3 * (size_t)ns * sizeof(int);
+    // doubles: red[ns][48] lmh[nlm][15] lmS[nw][nlm][9] pc[ns][12] rjric[ns][9] pinfo[2 ns - 1]; ints: fixed[ns] off[ns]
+    const size_t dbl = (size_t)ns * 48 + (size_t)nlm * 15 + (size_t)nw * nlm * 9 + (size_t)ns * 12 + (size_t)ns * 9 + 2 * (size_t)ns;
+    return dbl * sizeof(double) + 2 * (size_t)ns * sizeof(int);
 }
 __device__ __forceinline__ int pair_index(int a, int b, int ns) { return a * ns - (a * (a - 1)) / 2 + (b - a); }
+// sum of a 48-vector over the 16 lanes of a half-warp, scattered: afterwards the lane holds elements base .. base + 2 in v[0..2]
+__device__ __forceinline__ int reduce_scatter48_half(double *v, int lane) {
+    int base = 0;
+    rs_step<48>(v, lane & 8, 8); base += (lane & 8) ? 24 : 0;
+    rs_step<24>(v, lane & 4, 4); base += (lane & 4) ? 12 : 0;
+    rs_step<12>(v, lane & 2, 2); base += (lane & 2) ? 6 : 0;
+    rs_step<6>(v, lane & 1, 1);  base += (lane & 1) ? 3 : 0;
+    return base;
+}
 
-template <int MAXT, int MINB>
+// SPW = observer slots a warp evaluates per round: 1 (32 landmarks x 1 slot) or 2 (16 landmarks x 2 slots: half-warp = slot).
+// The host picks whichever needs fewer rounds for the graph (100 landmarks x 10 observer slots: 40 rounds vs 35).
+template <int MAXT, int MINB, int SPW>
 __global__ void __launch_bounds__(MAXT, MINB) k_lin_edges(DevView v, GroupView gv) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
+    constexpr int LPW = 32 / SPW;
     const GroupHdr h = gv.hdr[blockIdx.x];
     const int ns = h.ns, nlm = h.nlm;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    constexpr int LHS = 17;
-    double *pc = sm;                                  // [ns][12]
-    double *rjric = pc + (size_t)ns * 12;             // [ns][9]
-    double *lmh = rjric + (size_t)ns * 9;             // [nlm][17]  pw(3) g(3) G(9)
+    const int sub = lane / LPW, ll = lane - sub * LPW;
+    constexpr int LHS = 15;                           // odd stride: lane = landmark accesses hit distinct banks
+    double *red = sm;                                 // [ns][48]
+    double *lmh = red + (size_t)ns * 48;              // [nlm][15]  pw(3) g(3) G(9)
     double *lmS = lmh + (size_t)nlm * LHS;            // [nw][nlm][9]  per-warp partial sums of M(6) m(3)
-    double *red = lmS + (size_t)nw * nlm * 9;         // [ns][48]
-    double *bvec = red + (size_t)ns * 48;             // [ns][12]  bp(6) hdiag(6)
-    int *pose_id = (int *)(bvec + (size_t)ns * 12);   // [ns]
-    int *pfix = pose_id + ns;
+    double *pc = lmS + (size_t)nw * nlm * 9;          // [ns][12]
+    double *rjric = pc + (size_t)ns * 12;             // [ns][9]
+    long long *pinfo_s = (long long *)(rjric + (size_t)ns * 9);  // [2 ns - 1]: (0,0), (0,s), (s,s)
+    int *pfix = (int *)(pinfo_s + 2 * ns);            // [ns]
     int *poff = pfix + ns;
 
     long long prof_t_ = gv.prof ? clock64() : 0;
     unsigned long long prof_ns0_ = 0;
     if (gv.prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ns0_));
     // ---- phase 0: slot table, pose cache ------------------------------------------------------------------------
+    const int nsp = (ns - 1 + SPW - 1) / SPW;  // rounds of SPW observer slots; warp w takes w, w + nw, ...
     for (int s = tid; s < ns; s += nt) {
         const int pid = s == 0 ? h.host : gv.slot_pose[h.slot0 + s];
-        pose_id[s] = pid;
         pfix[s] = v.pose_fixed[pid];
         poff[s] = v.pose_off[pid];
     }
@@ -479,9 +491,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_lin_edges(DevView v, GroupView g
         const int pid = s == 0 ? h.host : gv.slot_pose[h.slot0 + s];
         pc[i] = v.poseRT[16 * (size_t)pid + k];
     }
-    for (int i = tid; i < ns * 48; i += nt) red[i] = 0.0;
-    // slots of a warp: 1 + wid, 1 + wid + nw, ...; a warp without a slot leaves its partial sums untouched: zero them
-    if (1 + wid >= ns)
+    for (int bi = tid; bi < 2 * ns - 1; bi += nt) {
+        const int a = bi < ns ? 0 : bi - ns + 1, b = bi < ns ? bi : a;
+        pinfo_s[bi] = gv.pairinfo[h.pair0 + pair_index(a, b, ns)];
+    }
+    for (int i = tid; i < 48; i += nt) red[i] = 0.0;
+    // a warp without any slot leaves its partial sums untouched: zero them
+    if (wid >= nsp)
         for (int i = lane; i < nlm * 9; i += 32) lmS[(size_t)wid * nlm * 9 + i] = 0.0;
     __syncthreads();
     for (int s = tid; s < ns; s += nt) mat3_mul(pc + 12 * (size_t)s, v.Ric, rjric + 9 * (size_t)s);
@@ -491,9 +507,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_lin_edges(DevView v, GroupView g
     // ---- phase 0.5: per-landmark host chain (needs pc only) ----------------------------------------------------------
     for (int l = tid; l < nlm; l += nt) {
         const int gl = h.lm0 + l;
-        const double lam = v.invdep[gl];
+        const double il = vio_rcp(v.invdep[gl]);
         const double pts_i[3] = {v.lm_pix[gl], v.lm_piy[gl], v.lm_piz[gl]};
-        const double pci[3] = {pts_i[0] / lam, pts_i[1] / lam, pts_i[2] / lam};
+        const double pci[3] = {pts_i[0] * il, pts_i[1] * il, pts_i[2] * il};
         double pbi[3], pw[3], tmp[3], g[3], G[9];
         mat3_mul_vec(v.Ric, pci, pbi);
         pbi[0] += v.tic[0]; pbi[1] += v.tic[1]; pbi[2] += v.tic[2];
@@ -501,7 +517,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_lin_edges(DevView v, GroupView g
         pw[0] += pc[9]; pw[1] += pc[10]; pw[2] += pc[11];
         mat3_mul_vec(v.Ric, pts_i, tmp);
         mat3_mul_vec(pc, tmp, g);
-        const double il2 = -1.0 / (lam * lam);
+        const double il2 = -(il * il);
         mat3_mul_hat(pc, pbi, G);
         double *o = lmh + LHS * (size_t)l;
         o[0] = pw[0]; o[1] = pw[1]; o[2] = pw[2];
@@ -512,77 +528,104 @@ __global__ void __launch_bounds__(MAXT, MINB) k_lin_edges(DevView v, GroupView g
     __syncthreads();
     VIO_PROF_MARK(1);
 
-    // ---- phase 1: edges, slot-major.  warp <-> slot, lanes <-> landmarks ----------------------------------------
+    // ---- phase 1: edges.  warp <-> SPW observer slots at a time, lanes <-> landmarks (x slot) -------------------------
     double *myS = lmS + (size_t)wid * nlm * 9;
-    for (int s = 1 + wid; s < ns; s += nw) {
-        const double *RTj = pc + 12 * (size_t)s;
-        const double *RjRic = rjric + 9 * (size_t)s;
-        const bool jfix = pfix[s] != 0;
-        const bool first = s == 1 + wid;  // the warp's first slot initialises its partial sums
+    bool first = true;  // the warp's first round initialises its partial sums
+    for (int sp = wid; sp < nsp; sp += nw, first = false) {
+        const int s = 1 + sp * SPW + sub;
+        const bool sv = SPW == 1 || s < ns;  // SPW = 2 and an odd number of observer slots: the upper half idles in the last round
+        const int sc = sv ? s : ns - 1;
+        const double *RTj = pc + 12 * (size_t)sc;
+        const double *RjRic = rjric + 9 * (size_t)sc;
+        const bool jfix = pfix[sc] != 0;
         double acc[48];
 #pragma unroll
         for (int k = 0; k < 48; ++k) acc[k] = 0.0;
-        const size_t ebase = (size_t)h.ell0 + (size_t)(s - 1) * nlm;
+        const size_t ebase = (size_t)h.ell0 + (size_t)(sc - 1) * nlm;
         double n_pjx = 0.0, n_pjy = 0.0;
         int n_edge = -1;
-        if (lane < nlm) { n_pjx = gv.ell_pjx[ebase + lane]; n_pjy = gv.ell_pjy[ebase + lane]; n_edge = gv.ell_edge[ebase + lane]; }
-        for (int l = lane; l < nlm; l += 32) {
+        if (ll < nlm) { n_pjx = gv.ell_pjx[ebase + ll]; n_pjy = gv.ell_pjy[ebase + ll]; n_edge = gv.ell_edge[ebase + ll]; }
+        // SPW = 2: uniform trip count (the exchange between the half-warps below needs every lane)
+        for (int l0 = 0; SPW == 2 ? l0 < nlm : l0 + ll < nlm; l0 += LPW) {
+            const int l = l0 + ll;
             const double pjx = n_pjx, pjy = n_pjy;
             const int edge = n_edge;
-            if (l + 32 < nlm) { n_pjx = gv.ell_pjx[ebase + l + 32]; n_pjy = gv.ell_pjy[ebase + l + 32]; n_edge = gv.ell_edge[ebase + l + 32]; }
-            double *ls = myS + 9 * (size_t)l;
-            if (pjx != pjx) {  // NaN: this landmark is not observed from slot s
-                if (first) {
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) ls[k] = 0.0;
-                }
-                continue;
-            }
-            const double *lh = lmh + LHS * (size_t)l;
-            const double pw[3] = {lh[0], lh[1], lh[2]};
+            if (l + LPW < nlm) { n_pjx = gv.ell_pjx[ebase + l + LPW]; n_pjy = gv.ell_pjy[ebase + l + LPW]; n_edge = gv.ell_edge[ebase + l + LPW]; }
+            const bool inr = SPW == 1 || l < nlm;
+            const bool valid = inr && sv && pjx == pjx;  // NaN: this landmark is not observed from slot s
+            const double *lh = lmh + LHS * (size_t)(inr ? l : 0);
             double pcj[3], pbj[3], r[2];
-            reproj_residual(v.Ric, v.tic, RTj, pw, pjx, pjy, pcj, pbj, r);
-            const double iz = 1.0 / pcj[2];
-            const double rx = -pcj[0] * iz * iz, ry = -pcj[1] * iz * iz;
-            double B[6];
+            double M[9], m[3];
+            if (valid) {
+                const double pw[3] = {lh[0], lh[1], lh[2]};
+                const double d[3] = {pw[0] - RTj[9], pw[1] - RTj[10], pw[2] - RTj[11]};
+                mat3t_mul_vec(RTj, d, pbj);
+                const double e[3] = {pbj[0] - v.tic[0], pbj[1] - v.tic[1], pbj[2] - v.tic[2]};
+                mat3t_mul_vec(v.Ric, e, pcj);
+                const double iz = vio_rcp(pcj[2]);
+                const double xz = pcj[0] * iz, yz = pcj[1] * iz;
+                r[0] = xz - pjx;
+                r[1] = yz - pjy;
+                const double rx = -xz * iz, ry = -yz * iz;
+                double B[6];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                B[c] = iz * RjRic[3 * c + 0] + rx * RjRic[3 * c + 2];
-                B[3 + c] = iz * RjRic[3 * c + 1] + ry * RjRic[3 * c + 2];
+                for (int c = 0; c < 3; ++c) {
+                    B[c] = iz * RjRic[3 * c + 0] + rx * RjRic[3 * c + 2];
+                    B[3 + c] = iz * RjRic[3 * c + 1] + ry * RjRic[3 * c + 2];
+                }
+                double rho0, drho, W[3];
+                robust_weights(v.rp_loss, v.rp_delta, v.rp_info, r, rho0, drho, W);
+                double WB[6];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    WB[c] = W[0] * B[c] + W[1] * B[3 + c];
+                    WB[3 + c] = W[1] * B[c] + W[2] * B[3 + c];
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = a; b < 3; ++b) M[3 * a + b] = B[a] * WB[b] + B[3 + a] * WB[3 + b];
+                M[3] = M[1]; M[6] = M[2]; M[7] = M[5];
+                const double dc = drho * v.rp_info;
+                const double r0 = dc * r[0], r1 = dc * r[1];
+                m[0] = B[0] * r0 + B[3] * r1;
+                m[1] = B[1] * r0 + B[4] * r1;
+                m[2] = B[2] * r0 + B[5] * r1;
+            } else if (SPW == 2 || first) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) M[k] = 0.0;
+                m[0] = m[1] = m[2] = 0.0;
             }
-            double rho0, drho, W[3];
-            robust_weights(v.rp_loss, v.rp_delta, v.rp_info, r, rho0, drho, W);
-            double WB[6];
+            // per-landmark sums of M (6) and m (3) over the slots: into the warp's own partial sums
+            if (SPW == 2) {
+                double q9[9] = {M[0], M[1], M[2], M[4], M[5], M[8], m[0], m[1], m[2]};
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                WB[c] = W[0] * B[c] + W[1] * B[3 + c];
-                WB[3 + c] = W[1] * B[c] + W[2] * B[3 + c];
+                for (int k = 0; k < 9; ++k) q9[k] += __shfl_xor_sync(0xffffffffu, q9[k], 16);
+                if (inr) {  // both halves hold the sum: the lower half stores 0..4, the upper half 5..8
+                    double *ls = myS + 9 * (size_t)l;
+                    if (sub == 0) {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) ls[k] = first ? q9[k] : ls[k] + q9[k];
+                    } else {
+#pragma unroll
+                        for (int k = 5; k < 9; ++k) ls[k] = first ? q9[k] : ls[k] + q9[k];
+                    }
+                }
+            } else if (valid || first) {
+                double *ls = myS + 9 * (size_t)l;
+                const double q9[9] = {M[0], M[1], M[2], M[4], M[5], M[8], m[0], m[1], m[2]};
+#pragma unroll
+                for (int k = 0; k < 9; ++k) ls[k] = first ? q9[k] : ls[k] + q9[k];
             }
-            double M[9];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 3; ++b) M[3 * a + b] = B[a] * WB[b] + B[3 + a] * WB[3 + b];
-            const double dc = drho * v.rp_info;
-            const double m[3] = {dc * (B[0] * r[0] + B[3] * r[1]), dc * (B[1] * r[0] + B[4] * r[1]),
-                                 dc * (B[2] * r[0] + B[5] * r[1])};
-            if (first) {
-                ls[0] = M[0]; ls[1] = M[1]; ls[2] = M[2]; ls[3] = M[4]; ls[4] = M[5]; ls[5] = M[8];
-                ls[6] = m[0]; ls[7] = m[1]; ls[8] = m[2];
-            } else {
-                ls[0] += M[0]; ls[1] += M[1]; ls[2] += M[2]; ls[3] += M[4]; ls[4] += M[5]; ls[5] += M[8];
-                ls[6] += m[0]; ls[7] += m[1]; ls[8] += m[2];
-            }
+            if (!valid) continue;
             double2 *wog = reinterpret_cast<double2 *>(v.wo + 6 * (size_t)edge);
             if (jfix) {
                 wog[0] = make_double2(0.0, 0.0); wog[1] = make_double2(0.0, 0.0); wog[2] = make_double2(0.0, 0.0);
                 continue;
             }
-            double N[9], MN[9], NMN[9], Ntm[3], Mg[3], NtMg[3];
+            double N[9], MN[9], Mg[3], NtMg[3];
             mat3_mul_hat(RTj, pbj, N);
             mat3_mul(M, N, MN);
-            mat3t_mul(N, MN, NMN);
-            mat3t_mul_vec(N, m, Ntm);
             const double g[3] = {lh[3], lh[4], lh[5]};
             mat3_mul_vec(M, g, Mg);
             mat3t_mul_vec(N, Mg, NtMg);
@@ -590,28 +633,44 @@ __global__ void __launch_bounds__(MAXT, MINB) k_lin_edges(DevView v, GroupView g
             acc[0] += M[0]; acc[1] += M[1]; acc[2] += M[2]; acc[3] += M[4]; acc[4] += M[5]; acc[5] += M[8];
 #pragma unroll
             for (int k = 0; k < 9; ++k) acc[6 + k] += MN[k];
-            acc[33] += NMN[0]; acc[34] += NMN[1]; acc[35] += NMN[2]; acc[36] += NMN[4]; acc[37] += NMN[5]; acc[38] += NMN[8];
+            // products that are only ever summed are accumulated by their FMA chains directly (no separate DMUL / DADD)
+#define VIO_ACC3T(dst, A_, i_, B_, j_) dst = fma(A_[i_], B_[j_], fma(A_[3 + i_], B_[3 + j_], fma(A_[6 + i_], B_[6 + j_], dst)))
+            VIO_ACC3T(acc[33], N, 0, MN, 0); VIO_ACC3T(acc[34], N, 0, MN, 1); VIO_ACC3T(acc[35], N, 0, MN, 2);  // N^T M N, upper triangle
+            VIO_ACC3T(acc[36], N, 1, MN, 1); VIO_ACC3T(acc[37], N, 1, MN, 2); VIO_ACC3T(acc[38], N, 2, MN, 2);
             acc[39] += m[0]; acc[40] += m[1]; acc[41] += m[2];
-            acc[42] += Ntm[0]; acc[43] += Ntm[1]; acc[44] += Ntm[2];
+            acc[42] = fma(N[0], m[0], fma(N[3], m[1], fma(N[6], m[2], acc[42])));  // N^T m
+            acc[43] = fma(N[1], m[0], fma(N[4], m[1], fma(N[7], m[2], acc[43])));
+            acc[44] = fma(N[2], m[0], fma(N[5], m[1], fma(N[8], m[2], acc[44])));
             if (!hfix) {
                 const double *G = lh + 6;
-                double GtM[9], GtMN[9];
-                mat3t_mul(G, M, GtM);
-                mat3t_mul(G, MN, GtMN);
 #pragma unroll
-                for (int k = 0; k < 9; ++k) { acc[15 + k] += GtM[k]; acc[24 + k] += GtMN[k]; }
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        VIO_ACC3T(acc[15 + 3 * a + b], G, a, M, b);   // G^T M
+                        VIO_ACC3T(acc[24 + 3 * a + b], G, a, MN, b);  // G^T M N
+                    }
+            }
+#undef VIO_ACC3T
+        }
+        if (SPW == 1) {
+            const int base = reduce_scatter48(acc, lane);
+            red[48 * (size_t)s + base] = acc[0];
+            if (!(lane & 1)) red[48 * (size_t)s + base + 1] = acc[1];
+        } else {
+            const int base = reduce_scatter48_half(acc, lane);
+            if (sv) {
+                double *R = red + 48 * (size_t)s + base;
+                R[0] = acc[0]; R[1] = acc[1]; R[2] = acc[2];
             }
         }
-        const int base = reduce_scatter48(acc, lane);
-        red[48 * (size_t)s + base] = acc[0];
-        if (!(lane & 1)) red[48 * (size_t)s + base + 1] = acc[1];
     }
     __syncthreads();
     VIO_PROF_MARK(2);
 
     // ---- phase 1.5: per-landmark sums -> H_ll, b_l, host row of H_lp, host blocks ------------------------------
     {
-        const int ncopy = min(nw, ns - 1) > 0 ? nw : 0;  // every warp's copy is initialised (first slot or zero fill)
+        const int ncopy = nw;  // every warp's copy is initialised (its first round, or the zero fill of phase 0)
         double hb[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) hb[k] = 0.0;
@@ -686,27 +745,23 @@ __global__ void __launch_bounds__(MAXT, MINB) k_lin_edges(DevView v, GroupView g
     const int nblk = 2 * ns - 1;  // block 0 = (0,0); 1..ns-1 = (0,s); ns..2ns-2 = (s,s)
     for (int idx = tid; idx < nblk * 36; idx += nt) {
         const int bi = idx / 36, k = idx - 36 * bi, r = k / 6, c = k - 6 * r;
-        int a, b;
-        if (bi == 0) { a = 0; b = 0; }
-        else if (bi < ns) { a = 0; b = bi; }
-        else { a = bi - ns + 1; b = a; }
-        const long long info = gv.pairinfo[h.pair0 + pair_index(a, b, ns)];
+        const long long info = pinfo_s[bi];
         const int flags = (int)(info & 3);
         if (flags == 3) continue;
         if (flags == 2 && r > c) continue;
         const size_t off = (size_t)(info >> 2);
         const size_t e = flags == 1 ? (size_t)c * gv.ld + r : (size_t)r * gv.ld + c;
         double val;
-        if (b == 0) {
+        if (bi == 0) {
             val = red[sym6_index(r, c)];
-        } else if (a == 0) {
-            const double *R = red + 48 * (size_t)b;  // (0,s) = [[-A1, A2],[-A3, A4]]
+        } else if (bi < ns) {
+            const double *R = red + 48 * (size_t)bi;  // (0,s) = [[-A1, A2],[-A3, A4]]
             if (r < 3 && c < 3) val = -R[sym3_index(r, c)];
             else if (r < 3) val = R[6 + 3 * r + (c - 3)];
             else if (c < 3) val = -R[15 + 3 * (r - 3) + c];
             else val = R[24 + 3 * (r - 3) + (c - 3)];
         } else {
-            const double *R = red + 48 * (size_t)a;  // (s,s) = [[A1, -A2],[-A2^T, A5]]
+            const double *R = red + 48 * (size_t)(bi - ns + 1);  // (s,s) = [[A1, -A2],[-A2^T, A5]]
             if (r < 3 && c < 3) val = R[sym3_index(r, c)];
             else if (r < 3) val = -R[6 + 3 * r + (c - 3)];
             else if (c < 3) val = -R[6 + 3 * c + (r - 3)];
@@ -724,135 +779,265 @@ __global__ void __launch_bounds__(MAXT, MINB) k_lin_edges(DevView v, GroupView g
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_schur_groups — the Schur complement of a landmark group as ONE symmetric rank-nlm update on the FP64 tensor cores
-// (round 2; the second half of the split pipeline).  Per group, with W (nlm x 6 ns) = the landmarks' rows of H_lp (host row
-// from wh, observer rows from wo via the group's ELL edge table), h = 1 / H_ll and V = diag(sqrt h) [W | b_l]:
-//     -V^T V  -> the 6x6 blocks (a, b), a <= b, of the reduced camera system   (A17/src/backend/problem.cc:412-431)
-//     and, in its last column, b_corr = W^T diag(h) b_l                          (:424-427)
-// Scaling the rows by sqrt(h) once while they are gathered keeps the inner loop free of FP64 multiplies and lets both DMMA
-// operands come from the same array.  The upper-triangular 8x8 tiles are dealt out evenly (row-major runs of at most
-// VIO_SCHUR_TPW tiles per warp and pass, so consecutive tiles of a warp share their row fragment); the k loop runs over
-// landmarks in steps of 4; fragments are 4 landmarks x 8 consecutive columns of V (row stride padded against bank
-// conflicts).  The finished tiles go straight from the accumulator registers to S with one RED.F64 per element.
-// Few registers and ~60 KB of shared memory: three CTAs per SM.
+// (round 2; the second half of the split pipeline).  Per group, with the landmarks' rows of H_lp
+//     V = [ wo (nlm x 6 (ns - 1), observer slots 1 .. ns - 1) | wh (nlm x 6, host slot) | b_l ]      and  h = 1 / H_ll:
+//     -V^T diag(h) V  -> the 6x6 blocks of the reduced camera system   (A17/src/backend/problem.cc:412-431)
+//     and, in its last column, b_corr = W^T diag(h) b_l                 (:424-427)
+// * Operands: the observer rows of a group are ONE contiguous slab of `wo` when every landmark stores its edges in slot
+//   order (header bit 1, set by the packer - true for tracked features), the host rows one slab of `wh`: a single thread
+//   issues two TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) and the CTA waits on the barrier once, while the
+//   other threads compute h and the lookup tables.  The DMMA fragments are read from that very layout (row stride
+//   6 (ns - 1) doubles; 60 at 11 slots is conflict-free), no transposition, no scaling pass: the A fragments are multiplied
+//   by h on the fly (3 DMUL per 9 DMMA).  Other groups (ragged tracks, strides that would bank-conflict) are gathered by
+//   hand into a padded copy of the same layout, six 16-byte chunks per thread in flight.
+// * Work unit = a 3 x 3 block of 8x8 tiles (tile sets si <= sj): 6 fragment loads feed 9 DMMAs per k step.
+//   In V^T h V the A fragment of tile row t and the B fragment of tile column t are the same shared-memory words
+//   (lane (g, q) holds V[k0 + q][8 t + g]).
+// * Flush: every lane looks its rows / columns up once per unit in a per-column table (slot, row-in-block) and a full
+//   ns x ns table of block offsets (both orientations), then issues one RED.F64 per element straight from the accumulators.
+// ~55 KB of shared memory: four CTAs per SM, so load, DMMA and flush phases of different groups overlap.
 // ------------------------------------------------------------------------------------------------------------------
-#define VIO_SCHUR_THREADS 256
-#define VIO_SCHUR_TPW 6
-__host__ __device__ inline int schur_ldw(int ns) {
-    int ld = 6 * ns + 1;            // + the b_l column
-    ld = (ld + 7) & ~7;             // whole 8-column tiles
-    while (!(ld % 16 == 4 || ld % 16 == 12)) ld += 4;  // the 4 rows of a fragment land on distinct bank groups
+#define VIO_SCHUR_THREADS 192
+__host__ __device__ inline bool schur_stride_ok(int ld) { return ld % 16 == 4 || ld % 16 == 12; }
+__host__ __device__ inline int schur_ldo(int ns, bool direct) {
+    int ld = 6 * (ns - 1);
+    if (direct && schur_stride_ok(ld)) return ld;  // the TMA path keeps the global layout
+    ld = (ld + 1) & ~1;
+    while (!schur_stride_ok(ld)) ld += 2;  // the 4 rows of a fragment land on distinct bank groups
     return ld;
 }
 __host__ __device__ inline size_t schur_smem_bytes(int ns, int nlm) {
-    const int kp = (nlm + 3) & ~3, npairs = ns * (ns + 1) / 2;
-    return (size_t)kp * schur_ldw(ns) * sizeof(double) + (size_t)npairs * sizeof(long long) + 2 * (size_t)ns * sizeof(int);
+    const int kp = (nlm + 3) & ~3, tr = (6 * ns + 1 + 7) >> 3;
+    const int ldo = schur_ldo(ns, false) > 6 * (ns - 1) ? schur_ldo(ns, false) : 6 * (ns - 1);
+    // doubles: wo_s[kp][ldo] wh_s[kp][6] hq[kp] bq[kp] zero[2]; i64: tab[ns][ns] mbar; ints: colinfo[8 tr] poff[ns] pfix[ns]
+    return ((size_t)kp * ldo + (size_t)kp * 6 + 2 * (size_t)kp + 2) * sizeof(double) + ((size_t)ns * ns + 1) * sizeof(long long) +
+           ((size_t)8 * tr + 2 * (size_t)ns) * sizeof(int);
 }
 __device__ __forceinline__ void schur_dmma(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ unsigned grp_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void grp_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(grp_saddr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void grp_mbar_expect(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(grp_saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void grp_bulk_load(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(grp_saddr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(grp_saddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void grp_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GRP_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GRP_DONE;\n"
+        "bra GRP_WAIT;\n"
+        "GRP_DONE:\n"
+        "}\n" ::"r"(grp_saddr(bar)),
+        "r"(parity)
+        : "memory");
+}
 
-__global__ void __launch_bounds__(VIO_SCHUR_THREADS, 3) k_schur_groups(DevView v, GroupView gv) {
+__global__ void __launch_bounds__(VIO_SCHUR_THREADS, 4) k_schur_groups(DevView v, GroupView gv) {
     extern __shared__ __align__(16) double ssm[];
     const GroupHdr h = gv.hdr[blockIdx.x];
     const int ns = h.ns, nlm = h.nlm, npairs = ns * (ns + 1) / 2;
-    const int kp = (nlm + 3) & ~3, LDW = schur_ldw(ns), D = 6 * ns;  // column D of V holds sqrt(h) b_l
+    const int kp = (nlm + 3) & ~3, NO = 6 * (ns - 1), D = 6 * ns;  // columns: [0, NO) observers, [NO, D) host, D = b_l
+    const int TR = (D + 1 + 7) >> 3;
+    const bool direct = (h.pad & 2) != 0 && schur_stride_ok(NO);
+    const int LDO = direct ? NO : schur_ldo(ns, false);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5, g = lane >> 2, q = lane & 3;
-    double *W = ssm;                                   // [kp][LDW]
-    long long *pinfo_s = (long long *)(W + (size_t)kp * LDW);  // [npairs]
-    int *poff = (int *)(pinfo_s + npairs);             // [ns]
+    double *wo_s = ssm;                                 // [kp][LDO]
+    double *wh_s = wo_s + (size_t)kp * LDO;             // [kp][6]
+    double *hq = wh_s + (size_t)kp * 6;                 // [kp]  1 / H_ll (0 for padding rows and empty landmarks)
+    double *bq = hq + kp;                               // [kp]  b_l
+    double *zero = bq + kp;                             // [2]
+    long long *tab = (long long *)(zero + 2);           // [ns][ns]  (offset << 2) | flags of block (a, b), both orientations
+    unsigned long long *mbar = (unsigned long long *)(tab + (size_t)ns * ns);
+    int *colinfo = (int *)(mbar + 1);                   // [8 TR]  slot << 8 | row-in-block; -1 = b column, -2 = padding
+    int *poff = colinfo + 8 * TR;                       // [ns]
     int *pfix = poff + ns;
+    if (tid == 0) grp_mbar_init(mbar, 1);
+    __syncthreads();
+    if (direct) {
+        if (tid == 0) {
+            const int e0 = gv.ell_edge[h.ell0];
+            const unsigned bo = (unsigned)nlm * NO * sizeof(double), bh = (unsigned)nlm * 6 * sizeof(double);
+            grp_mbar_expect(mbar, bo + bh);
+            grp_bulk_load(wo_s, v.wo + 6 * (size_t)e0, bo, mbar);
+            grp_bulk_load(wh_s, v.wh + 6 * (size_t)h.lm0, bh, mbar);
+        }
+        // rows nlm .. kp - 1 are outside the copies: zero them
+        for (int i = tid; i < (kp - nlm) * NO; i += nt) wo_s[(size_t)nlm * NO + i] = 0.0;
+        for (int i = tid; i < (kp - nlm) * 6; i += nt) wh_s[(size_t)nlm * 6 + i] = 0.0;
+    } else {
+        // gather: thread <-> one 16-byte chunk (row l, slot s, part 0..2); nt is a multiple of 3, so (l, s) advance by a fixed
+        // (dq, dr) per round; six chunks per thread are in flight at a time (index loads, then row loads, then stores)
+        constexpr int U = 6;
+        const int per = nt / 3, dq = per / ns, dr = per - dq * ns;
+        const int part = tid % 3, rs0 = tid / 3;
+        int l = rs0 / ns, s = rs0 - l * ns;
+        while (l < kp) {
+            int lu[U], su[U], eu[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                lu[u] = l; su[u] = s;
+                l += dq; s += dr;
+                if (s >= ns) { s -= ns; ++l; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                eu[u] = -1;
+                if (lu[u] < nlm && su[u] > 0) eu[u] = gv.ell_edge[(size_t)h.ell0 + (size_t)(su[u] - 1) * nlm + lu[u]];
+            }
+            double2 wv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                wv[u] = make_double2(0.0, 0.0);
+                if (lu[u] < nlm) {
+                    if (su[u] == 0) wv[u] = reinterpret_cast<const double2 *>(v.wh + 6 * (size_t)(h.lm0 + lu[u]))[part];
+                    else if (eu[u] >= 0) wv[u] = reinterpret_cast<const double2 *>(v.wo + 6 * (size_t)eu[u])[part];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (lu[u] >= kp) continue;
+                double *dst = su[u] == 0 ? wh_s + (size_t)lu[u] * 6 : wo_s + (size_t)lu[u] * LDO + 6 * (su[u] - 1);
+                reinterpret_cast<double2 *>(dst)[part] = wv[u];
+            }
+        }
+    }
+    // ---- tables (overlap the copies)
     for (int s = tid; s < ns; s += nt) {
         const int pid = s == 0 ? h.host : gv.slot_pose[h.slot0 + s];
         pfix[s] = v.pose_fixed[pid];
         poff[s] = v.pose_off[pid];
     }
-    for (int p = tid; p < npairs; p += nt) pinfo_s[p] = gv.pairinfo[h.pair0 + p];
-    // ---- gather V: 6 doubles per (landmark, slot) as three 16-byte loads, scaled by sqrt(1 / H_ll)
-    for (int t = tid; t < kp * ns; t += nt) {
-        const int s = t / kp, l = t - s * kp;  // landmarks fastest: the ELL edge table is read coalesced
-        double2 w01 = make_double2(0.0, 0.0), w23 = w01, w45 = w01;
-        if (l < nlm) {
-            const double *src = nullptr;
-            if (s == 0) src = v.wh + 6 * (size_t)(h.lm0 + l);
-            else {
-                const int e = gv.ell_edge[(size_t)h.ell0 + (size_t)(s - 1) * nlm + l];
-                if (e >= 0) src = v.wo + 6 * (size_t)e;
-            }
-            if (src) {
-                const double hll = v.Hll[h.lm0 + l];
-                const double sc = hll > 0.0 ? rsqrt(hll) : 0.0;
-                const double2 *s2 = reinterpret_cast<const double2 *>(src);
-                w01 = s2[0]; w23 = s2[1]; w45 = s2[2];
-                w01.x *= sc; w01.y *= sc; w23.x *= sc; w23.y *= sc; w45.x *= sc; w45.y *= sc;
-            }
-        }
-        double *dst = W + (size_t)l * LDW + 6 * s;
-        dst[0] = w01.x; dst[1] = w01.y; dst[2] = w23.x; dst[3] = w23.y; dst[4] = w45.x; dst[5] = w45.y;
+    for (int p = tid; p < npairs; p += nt) {
+        int a = 0, rem = p;
+        while (rem >= ns - a) { rem -= ns - a; ++a; }
+        const int b = a + rem;
+        const long long info = gv.pairinfo[h.pair0 + p];
+        tab[a * ns + b] = info;
+        if (a != b) tab[b * ns + a] = (info & 3) < 2 ? (info ^ 1) : info;  // the same block seen from the other side: transposed
+    }
+    for (int c = tid; c < 8 * TR; c += nt) {
+        int ci;
+        if (c < NO) { const int sl = c / 6; ci = ((sl + 1) << 8) | (c - 6 * sl); }
+        else if (c < D) ci = c - NO;  // host slot 0
+        else ci = c == D ? -1 : -2;
+        colinfo[c] = ci;
     }
     for (int l = tid; l < kp; l += nt) {
-        double b = 0.0;
+        double x = 0.0, b = 0.0;
         if (l < nlm) {
             const double hll = v.Hll[h.lm0 + l];
-            b = hll > 0.0 ? v.bl[h.lm0 + l] * rsqrt(hll) : 0.0;
+            if (hll != 0.0) x = 1.0 / hll;
+            b = v.bl[h.lm0 + l];
         }
-        double *row = W + (size_t)l * LDW;
-        row[D] = b;
-        for (int c = D + 1; c < LDW; ++c) row[c] = 0.0;
+        hq[l] = x; bq[l] = b;
     }
+    if (tid == 0) { zero[0] = 0.0; zero[1] = 0.0; }
     __syncthreads();
-    // ---- tiles (ti <= tj) of the (D + 1)-column product: warp w takes the row-major run [w * per, (w + 1) * per)
-    const int TR = (D + 1 + 7) >> 3, ntiles = TR * (TR + 1) / 2;
-    const int per = (ntiles + nw - 1) / nw;
-    const int wbeg = warp * per, wend = min(ntiles, wbeg + per);
-    for (int t0 = wbeg; t0 < wend; t0 += VIO_SCHUR_TPW) {
-        int ti[VIO_SCHUR_TPW], tj[VIO_SCHUR_TPW];
-        double c[VIO_SCHUR_TPW][2];
+    if (direct) grp_mbar_wait(mbar, 0);
+    // ---- units: tile sets si <= sj of three tile rows / columns each
+    const int nsets = (TR + 2) / 3, nunits = nsets * (nsets + 1) / 2;
+    for (int u = warp; u < nunits; u += nw) {
+        int si = 0, rem = u;
+        while (rem >= nsets - si) { rem -= nsets - si; ++si; }
+        const int sj = si + rem;
+        // per-lane fragment pointers (row q, column 8 t + g of V) and row strides of the unit's six tiles
+        const double *fp[6];
+        int fs[6];
 #pragma unroll
-        for (int u = 0; u < VIO_SCHUR_TPW; ++u) {
-            // invert t = ti * TR - ti (ti - 1) / 2 + (tj - ti); slots past the run repeat its last tile and are not flushed
-            int t = min(t0 + u, wend - 1), a = 0;
-            while (t >= TR - a) { t -= TR - a; ++a; }
-            ti[u] = a; tj[u] = a + t;
-            c[u][0] = c[u][1] = 0.0;
+        for (int x = 0; x < 6; ++x) {
+            const int t = x < 3 ? 3 * si + x : 3 * sj + (x - 3), c = 8 * t + g;
+            if (t >= TR || c > D) { fp[x] = zero; fs[x] = 0; }
+            else if (c < NO) { fp[x] = wo_s + (size_t)q * LDO + c; fs[x] = 4 * LDO; }
+            else if (c < D) { fp[x] = wh_s + (size_t)q * 6 + (c - NO); fs[x] = 24; }
+            else { fp[x] = bq + q; fs[x] = 4; }
         }
-        const int nact = min(VIO_SCHUR_TPW, wend - t0);
-        const double *row = W + (size_t)q * LDW + g;
+        double c[3][3][2];
+#pragma unroll
+        for (int x = 0; x < 3; ++x)
+#pragma unroll
+            for (int y = 0; y < 3; ++y) c[x][y][0] = c[x][y][1] = 0.0;
+        const double *hp = hq + q;
+        if (si == sj) {
 #pragma unroll 2
-        for (int k0 = 0; k0 < kp; k0 += 4, row += 4 * (size_t)LDW) {
-            double a[VIO_SCHUR_TPW], b[VIO_SCHUR_TPW];
-#pragma unroll
-            for (int u = 0; u < VIO_SCHUR_TPW; ++u) {
-                b[u] = row[8 * tj[u]];
-                a[u] = (u > 0 && ti[u] == ti[u - 1]) ? a[u - 1] : row[8 * ti[u]];
+            for (int k0 = 0; k0 < kp; k0 += 4) {
+                const double hh = hp[k0];
+                const double f0 = *fp[0], f1 = *fp[1], f2 = *fp[2];
+                fp[0] += fs[0]; fp[1] += fs[1]; fp[2] += fs[2];
+                const double a0 = f0 * hh, a1 = f1 * hh, a2 = f2 * hh;
+                schur_dmma(c[0][0][0], c[0][0][1], a0, f0);
+                schur_dmma(c[0][1][0], c[0][1][1], a0, f1);
+                schur_dmma(c[0][2][0], c[0][2][1], a0, f2);
+                schur_dmma(c[1][1][0], c[1][1][1], a1, f1);
+                schur_dmma(c[1][2][0], c[1][2][1], a1, f2);
+                schur_dmma(c[2][2][0], c[2][2][1], a2, f2);
             }
+        } else {
+#pragma unroll 2
+            for (int k0 = 0; k0 < kp; k0 += 4) {
+                const double hh = hp[k0];
+                const double a0 = *fp[0] * hh, a1 = *fp[1] * hh, a2 = *fp[2] * hh;
+                const double b0 = *fp[3], b1 = *fp[4], b2 = *fp[5];
 #pragma unroll
-            for (int u = 0; u < VIO_SCHUR_TPW; ++u)
-                if (u < nact) schur_dmma(c[u][0], c[u][1], a[u], b[u]);
+                for (int x = 0; x < 6; ++x) fp[x] += fs[x];
+                schur_dmma(c[0][0][0], c[0][0][1], a0, b0);
+                schur_dmma(c[0][1][0], c[0][1][1], a0, b1);
+                schur_dmma(c[0][2][0], c[0][2][1], a0, b2);
+                schur_dmma(c[1][0][0], c[1][0][1], a1, b0);
+                schur_dmma(c[1][1][0], c[1][1][1], a1, b1);
+                schur_dmma(c[1][2][0], c[1][2][1], a1, b2);
+                schur_dmma(c[2][0][0], c[2][0][1], a2, b0);
+                schur_dmma(c[2][1][0], c[2][1][1], a2, b1);
+                schur_dmma(c[2][2][0], c[2][2][1], a2, b2);
+            }
+        }
+        // ---- flush: lane (g, q) holds rows 8 ti + g and columns 8 tj + 2 q + {0, 1} of every tile
+        int ri[3], cj[3][2];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const int ti = 3 * si + x, tj = 3 * sj + x;
+            ri[x] = ti < TR ? colinfo[8 * ti + g] : -2;
+            cj[x][0] = tj < TR ? colinfo[8 * tj + 2 * q] : -2;
+            cj[x][1] = tj < TR ? colinfo[8 * tj + 2 * q + 1] : -2;
         }
 #pragma unroll
-        for (int u = 0; u < VIO_SCHUR_TPW; ++u) {
-            if (u >= nact) continue;
-            const int i = 8 * ti[u] + g;
-            if (i >= D) continue;
-            const int sa = i / 6, r = i - 6 * sa;
+        for (int x = 0; x < 3; ++x) {
+            if (ri[x] < 0) continue;  // padding or the b_l column as a row
+            const int sa = ri[x] >> 8, r = ri[x] & 255;
+            const bool afix = pfix[sa] != 0;
+            const int aoff = poff[sa] + r;
 #pragma unroll
-            for (int e2 = 0; e2 < 2; ++e2) {
-                const int j = 8 * tj[u] + 2 * q + e2;
-                const double val = c[u][e2];
-                if (j > D || val == 0.0) continue;
-                if (j == D) {  // b_corr of row i
-                    if (!pfix[sa]) atomicAdd(v.bcorr + poff[sa] + r, val);
-                    continue;
+            for (int y = 0; y < 3; ++y) {
+                if (si == sj && x > y) continue;
+#pragma unroll
+                for (int e2 = 0; e2 < 2; ++e2) {
+                    const int cc2 = cj[y][e2];
+                    const double val = c[x][y][e2];
+                    if (cc2 == -2 || val == 0.0) continue;
+                    if (cc2 == -1) {  // b_corr of row i
+                        if (!afix) atomicAdd(v.bcorr + aoff, val);
+                        continue;
+                    }
+                    // diagonal tiles hold (i, j) and (j, i): keep i <= j in column order
+                    if (si == sj && x == y && 2 * q + e2 < g) continue;
+                    const int sb = cc2 >> 8, cc = cc2 & 255;
+                    const long long info = tab[sa * ns + sb];
+                    const int flags = (int)(info & 3);
+                    if (flags == 3) continue;
+                    const size_t off = (size_t)(info >> 2);
+                    const size_t el = flags == 1 ? (size_t)cc * gv.ld + r : (size_t)r * gv.ld + cc;
+                    atomicAdd(v.S + off + el, -val);
                 }
-                const int sb = j / 6, cc = j - 6 * sb;
-                if (sa > sb) continue;
-                const long long info = pinfo_s[sa * ns - (sa * (sa - 1)) / 2 + (sb - sa)];
-                const int flags = (int)(info & 3);
-                if (flags == 3) continue;
-                if (flags == 2 && r > cc) continue;
-                const size_t off = (size_t)(info >> 2);
-                const size_t el = flags == 1 ? (size_t)cc * gv.ld + r : (size_t)r * gv.ld + cc;
-                atomicAdd(v.S + off + el, -val);
             }
         }
     }

@@ -262,9 +262,9 @@ VIO_HD void reproj_residual(const double Ric[9], const double tic[3], const doub
     mat3t_mul_vec(RTj, d, pbj);
     const double e[3] = {pbj[0] - tic[0], pbj[1] - tic[1], pbj[2] - tic[2]};
     mat3t_mul_vec(Ric, e, pcj);
-    const double z = pcj[2];
-    r[0] = pcj[0] / z - pjx;  // two true divisions like the reference (edge_reprojection.cc:38): kept for 1-ulp parity
-    r[1] = pcj[1] / z - pjy;
+    const double iz = vio_rcp(pcj[2]);  // one reciprocal (1 ulp) instead of the reference's two divisions (edge_reprojection.cc:38)
+    r[0] = pcj[0] * iz - pjx;
+    r[1] = pcj[1] * iz - pjy;
 }
 
 // robust weights (A17/src/backend/edge.cc:39-74) for information = c*I2:

@@ -15,6 +15,22 @@
 
 #define VIO_HD __host__ __device__ __forceinline__
 
+// 1 / z to ~1 ulp without the slow-path branch of the IEEE division: 20-bit hardware estimate + two Newton steps.
+// (z is a depth or an inverse depth here: never denormal; 0 / inf / NaN still come out as inf / 0 / NaN.)
+VIO_HD double vio_rcp(double z) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z));
+    double e = fma(-z, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-z, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+#else
+    return 1.0 / z;
+#endif
+}
+
 struct Mat3 {
     double m[9];  // row-major
 };

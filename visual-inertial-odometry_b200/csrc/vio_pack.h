@@ -449,7 +449,7 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
                 const int ell0 = (int)K.ell_pjx.size(), pair0 = (int)K.g_pairinfo.size(), slot0 = (int)K.g_slot_pose.size();
                 int full = 1;
                 for (int l = la; l < lb; ++l) if (lm_eptr[l + 1] - lm_eptr[l] != ns - 1) full = 0;
-                const int hdr[8] = {host, ns, la, nlm, ell0, pair0, slot0, full};
+                const int hdr[8] = {host, ns, la, nlm, ell0, pair0, slot0, full};  // [7]: bit 0 full, bit 1 edges in slot order (below)
                 K.g_hdr.insert(K.g_hdr.end(), hdr, hdr + 8);
                 K.g_slot_pose.insert(K.g_slot_pose.end(), slots.begin(), slots.end());
                 const double qnan = std::numeric_limits<double>::quiet_NaN();
@@ -462,6 +462,16 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
                         const size_t idx = (size_t)ell0 + (size_t)(sl - 1) * nlm + (l - la);
                         K.ell_pjx[idx] = pjx[e]; K.ell_pjy[idx] = pjy[e]; K.ell_edge[idx] = e;
                     }
+                if (full) {
+                    // every landmark's edges stored in slot order, landmarks back to back: edge(l, s) = e0 + l (ns - 1) + (s - 1),
+                    // so the Schur kernel's gather needs no index loads
+                    bool direct = true;
+                    const int e0 = lm_eptr[la];
+                    for (int l = la; l < lb && direct; ++l)
+                        for (int k = 0; k < ns - 1; ++k)
+                            if (K.ell_edge[(size_t)ell0 + (size_t)k * nlm + (l - la)] != e0 + (l - la) * (ns - 1) + k) { direct = false; break; }
+                    if (direct) K.g_hdr[K.g_hdr.size() - 1] |= 2;
+                }
                 for (int a = 0; a < ns && K.grouped_ok; ++a)
                     for (int b = a; b < ns; ++b) {
                         const int pa = slots[a], pb = slots[b];
