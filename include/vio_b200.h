@@ -143,6 +143,14 @@ typedef struct vio_graph {
     const int32_t *rx_point;     /* n_reproj_xyz                                           */
     const int32_t *rx_pose;      /* observing pose index                                   */
     const double *rx_obs;        /* n_reproj_xyz x 2 (obs_.head<2>())                      */
+
+    /* Fixed landmark-class vertices (Vertex::SetFixed on a VertexInverseDepth / VertexPointXYZ), may be NULL (= none).
+     * MakeHessian skips the Jacobian blocks of ANY fixed vertex (A17/src/backend/problem.cc:325,340): H_ll, b_l and the
+     * H_lp rows of a fixed landmark are zero, the pose blocks of its edges are kept.  The reference's own Schur step
+     * then inverts that zero H_mm block (problem.cc:421-425: inf, NaN in S - every trial step is rejected); here the
+     * block is left out of the Schur complement and of the back-substitution, i.e. the landmark is a constant.        */
+    const uint8_t *landmark_fixed; /* n_landmark                                            */
+    const uint8_t *point_fixed;    /* n_point                                               */
 } vio_graph;
 
 /* ---- LM options / statistics -------------------------------------------------------------- */

@@ -80,6 +80,7 @@ bool build(const vio_graph *g, Built &B) {
         VecX x(1);
         x[0] = g->inv_depth[i];
         v->SetParameters(x);
+        if (g->landmark_fixed && g->landmark_fixed[i]) v->SetFixed();
         B.problem->AddVertex(v);
         B.landmarks.push_back(v);
     }
@@ -105,6 +106,7 @@ bool build(const vio_graph *g, Built &B) {
         VecX x(3);
         for (int k = 0; k < 3; ++k) x[k] = g->point_xyz[3 * i + k];
         v->SetParameters(x);
+        if (g->point_fixed && g->point_fixed[i]) v->SetFixed();
         B.problem->AddVertex(v);
         B.points.push_back(v);
     }

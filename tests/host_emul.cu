@@ -50,6 +50,7 @@ void setup_packed(const vio_graph *g, const double *pose, HostProblem &H) {
     quat_to_R(K.qic, v.Ric);
     for (int k = 0; k < 3; ++k) v.tic[k] = K.tic[k];
     v.lm_host = K.lm_host.data(); v.lm_eptr = K.lm_eptr.data();
+    v.lm_fixed = K.lm_fixed.empty() ? nullptr : K.lm_fixed.data();
     v.lm_pix = K.pix.data(); v.lm_piy = K.piy.data(); v.lm_piz = K.piz.data();
     v.e_pose_j = K.e_pose_j.data(); v.e_pjx = K.pjx.data(); v.e_pjy = K.pjy.data();
     v.rp_info = g->rp_info; v.rp_loss = g->rp_loss; v.rp_delta = g->rp_loss_delta;

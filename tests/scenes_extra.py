@@ -254,6 +254,28 @@ def xyz_scene(kind):
     raise ValueError(kind)
 
 
+FIXED_LM = (3, 17, 18)
+FIXED_PT = (0, 5, 39)
+
+
+def fixed_scene(kind):
+    """Scenes with FIXED landmark-class vertices behind tests/golden/fixed*_6x40_v17_lin.npz (make_golden_fixedlm.py)."""
+    vio = importlib.import_module("visual-inertial-odometry_b200")
+    sc = vio.scenes
+    f = np.zeros(40, np.uint8)
+    if kind == "lm":
+        s = sc.monoba(6, 40, with_ext=True)
+        f[list(FIXED_LM)] = 1
+        s.landmark_fixed = f
+        return s
+    if kind == "pt":
+        s = sc.to_xyz(sc.monoba(6, 40, with_ext=True), noise=0.01, seed=1)
+        f[list(FIXED_PT)] = 1
+        s.point_fixed = f
+        return s
+    raise ValueError(kind)
+
+
 def extfree_scene(n_pose=6, n_feat=40):
     """TestMonoBA scene in the v17 4-vertex form with the extrinsic VertexPose NOT fixed (ESTIMATE_EXTRINSIC=1): every
     EdgeReprojection contributes its 4th Jacobian (A17/src/backend/edge_reprojection.cc:97-103)."""

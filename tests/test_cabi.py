@@ -30,7 +30,7 @@ def test_struct_layouts_match_header(vio):
     lib = vio.capi.lib()
     for which, cls in enumerate((vio.capi.VioGraph, vio.capi.VioLmOpts, vio.capi.VioStats, vio.capi.VioDims)):
         assert lib.vio_struct_size(which) == C.sizeof(cls), cls
-    assert C.sizeof(vio.capi.VioGraph) == 432
+    assert C.sizeof(vio.capi.VioGraph) == 448
 
 
 def test_no_cpu_fallback(vio):

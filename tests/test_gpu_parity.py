@@ -804,3 +804,82 @@ def test_ring_solve_vs_sparse_reference(vio, refshim):
     pose, _, invd = p.get_vertices()
     assert np.abs(pose - ref["pose"]).max() <= FINAL_TOL * np.abs(ref["pose"]).max()
     assert np.abs(invd - ref["inv_depth"]).max() <= FINAL_TOL * np.abs(ref["inv_depth"]).max()
+
+
+def _constant_landmark_step(H, b, P, fixed_rows, lam):
+    """(S, bS, dx) from a reference Hessian with some landmark rows FIXED (zero rows / columns): the fixed blocks are left
+    out of the Schur complement and of the back-substitution (their dx is 0), the others are eliminated block by block
+    exactly like Problem::SolveLinearSystem (A17/src/backend/problem.cc:406-449) does."""
+    n = H.shape[0]
+    free = np.array([i for i in range(P, n) if i not in fixed_rows], int)
+    Hpp, Hpm, Hmm = H[:P, :P], H[:P, free], H[np.ix_(free, free)]
+    Hmm_inv = np.linalg.inv(Hmm)  # block diagonal (1x1 or 3x3 blocks)
+    S = Hpp - Hpm @ Hmm_inv @ Hpm.T
+    bS = b[:P] - Hpm @ Hmm_inv @ b[free]
+    dxp = np.linalg.solve(S + lam * np.eye(P), bS)
+    dx = np.zeros(n)
+    dx[:P] = dxp
+    dx[free] = Hmm_inv @ (b[free] - Hpm.T @ dxp)
+    return S, bS, dx
+
+
+@pytest.mark.parametrize("kind", ["lm", "pt"])
+def test_fixed_landmarks_vs_golden(vio, kind):
+    """Vertex::SetFixed on landmark-class vertices (SURVEY 8a `Vertex`; VERDICT r1 'generality'): H and b against the
+    unmodified reference's MakeHessian (zero rows / columns for the fixed landmarks, A17/src/backend/problem.cc:325,340);
+    Schur complement and step against the block elimination of THAT H with the fixed blocks left out (the reference's own
+    SolveLinearSystem inverts their zero H_mm block - inf/NaN - so it has no value to compare with); a Solve leaves the
+    fixed landmarks untouched and still converges."""
+    import os
+    from tests.scenes_extra import fixed_scene, FIXED_LM, FIXED_PT
+    g = _gold("fixedlm_6x40_v17_lin.npz" if kind == "lm" else "fixedpt_6x40_v17_lin.npz")
+    s = fixed_scene(kind)
+    opts = vio.make_opts(flavour=vio.capi.LM_V17, solver=vio.capi.SOLVER_DENSE_CHOL)
+    p = vio.Problem()
+    p.set_graph(s)
+    H, b = p.get_hessian(opts)
+    assert rel_max(H, g["H"]) <= H_TOL and rel_l2(b, g["b"]) <= H_TOL
+    assert abs(p.chi2(opts) - float(g["chi2"])) <= 1e-12 * float(g["chi2"])
+    P = s.P
+    if kind == "lm":
+        fixed_rows = {P + l for l in FIXED_LM}
+    else:
+        fixed_rows = {P + 3 * l + k for l in FIXED_PT for k in range(3)}
+    for r in fixed_rows:
+        assert not H[r].any() and not H[:, r].any() and b[r] == 0.0
+    lam = float(g["lam"])
+    Sg, bSg, dxg = _constant_landmark_step(g["H"], g["b"], P, fixed_rows, lam)
+    p.linearize(opts)
+    S, bS = p.get_schur()
+    assert rel_max(S, Sg) <= H_TOL and rel_l2(bS, bSg) <= H_TOL
+    p.solve_step(lam, opts)
+    dxp, dxl = p.get_delta()
+    dx = np.concatenate([dxp, dxl])
+    if kind == "pt":
+        _, _, dxx = p.get_point_system()
+        dx = np.concatenate([dx, dxx.ravel()])
+    assert rel_l2(dx, dxg) <= 1e-8
+    assert all(dx[r] == 0.0 for r in fixed_rows)
+    # Solve: fixed landmarks stay where they are, the cost still goes down
+    p2 = vio.Problem()
+    p2.set_graph(s)
+    st = p2.solve(8, opts)
+    assert st.chi2_final < 0.05 * st.chi2_initial
+    if kind == "lm":
+        _, _, invd = p2.get_vertices()
+        assert all(invd[l] == s.inv_depth[l] for l in FIXED_LM)
+        assert np.abs(invd - s.inv_depth).max() > 1e-4  # the others moved
+    else:
+        pts = p2.get_points()
+        assert all((pts[l] == s.point_xyz[l]).all() for l in FIXED_PT)
+        assert np.abs(pts - s.point_xyz).max() > 1e-4
+    # the grouped kernels and the per-landmark kernel agree
+    if kind == "lm":
+        os.environ["VIO_B200_LINEARIZE"] = "generic"
+        try:
+            p3 = vio.Problem()
+            p3.set_graph(s)
+            H3, b3 = p3.get_hessian(opts)
+        finally:
+            os.environ.pop("VIO_B200_LINEARIZE")
+        assert rel_max(H3, H) <= 1e-12 and rel_l2(b3, b) <= 1e-12

@@ -315,3 +315,27 @@ def test_sparse_reference_restatement_equals_unmodified_solve(vio):
     assert np.allclose(r1["lambda_trace"][:n], r2["lambda_trace"], rtol=1e-12, atol=0)
     assert abs(r1["chi2_final"] - r2["chi2_final"]) <= 1e-12 * r1["chi2_final"]
     assert np.abs(r1["pose"] - r2["pose"]).max() <= 1e-12 and np.abs(r1["inv_depth"] - r2["inv_depth"]).max() <= 1e-12
+
+
+def test_fixed_landmark_hessian_emulated_vs_golden(vio):
+    """Vertex::SetFixed on an inverse-depth landmark: the device per-landmark body (compiled for the host, tests/host_emul.cu)
+    against H, b of the unmodified reference's MakeHessian (tests/golden/fixedlm_6x40_v17_lin.npz): zero rows / columns
+    for the fixed landmarks (A17/src/backend/problem.cc:325,340), everything else unchanged; the Schur complement leaves
+    the fixed blocks out."""
+    from tests import emul
+    from tests.scenes_extra import fixed_scene, FIXED_LM
+    if not emul.available():
+        pytest.skip("tests/libhost_emul.so not built")
+    g = np.load(os.path.join(GOLD, "fixedlm_6x40_v17_lin.npz"))
+    s = fixed_scene("lm")
+    H, b = emul.hessian(s)
+    assert np.abs(H - g["H"]).max() <= 1e-9 * np.abs(g["H"]).max()
+    assert np.linalg.norm(b - g["b"]) <= 1e-9 * np.linalg.norm(g["b"])
+    P = s.P
+    for l in FIXED_LM:
+        assert not H[P + l].any() and not H[:, P + l].any() and b[P + l] == 0.0
+    free = np.array([P + l for l in range(40) if l not in FIXED_LM])
+    Hg = g["H"]
+    Sg = Hg[:P, :P] - (Hg[:P, free] / np.diag(Hg)[free]) @ Hg[free, :P]
+    S, bS = emul.schur(s)
+    assert np.abs(S - Sg).max() <= 1e-9 * np.abs(Sg).max()

@@ -43,6 +43,7 @@ class VioGraph(C.Structure):
         ("storage", C.c_int32),
         ("n_point", C.c_int32), ("reserved_xyz", C.c_int32), ("point_xyz", _dp),
         ("n_reproj_xyz", C.c_int64), ("rx_point", _ip), ("rx_pose", _ip), ("rx_obs", _dp),
+        ("landmark_fixed", _bp), ("point_fixed", _bp),
     ]
 
 
@@ -191,6 +192,8 @@ class Scene:
         self.rx_point = np.zeros(0, np.int32)
         self.rx_pose = np.zeros(0, np.int32)
         self.rx_obs = np.zeros((0, 2))
+        self.landmark_fixed = None  # uint8 per inverse-depth landmark / per point (Vertex::SetFixed), None = none fixed
+        self.point_fixed = None
         self.gravity = np.array([0.0, 0.0, 9.81])
         self.storage = STORAGE_AUTO
         # generator extras (not part of the graph)
@@ -220,6 +223,10 @@ class Scene:
             self.speedbias_fixed = c(self.speedbias_fixed, np.uint8)
         if self.pclass_order is not None:
             self.pclass_order = c(self.pclass_order, np.int32)
+        if self.landmark_fixed is not None:
+            self.landmark_fixed = c(self.landmark_fixed, np.uint8)
+        if self.point_fixed is not None:
+            self.point_fixed = c(self.point_fixed, np.uint8)
 
     def to_c(self):
         """-> (VioGraph, keepalive list).  Arrays are borrowed: keep `self` alive during the call."""
@@ -272,6 +279,8 @@ class Scene:
         g.point_xyz = _d(self.point_xyz)
         g.n_reproj_xyz = self.rx_point.shape[0]
         g.rx_point, g.rx_pose, g.rx_obs = _i(self.rx_point), _i(self.rx_pose), _d(self.rx_obs)
+        g.landmark_fixed = _b(self.landmark_fixed)
+        g.point_fixed = _b(self.point_fixed)
         return g, keep
 
     @property
@@ -280,7 +289,7 @@ class Scene:
 
     _ARRAYS = ("pose", "pose_fixed", "speedbias", "speedbias_fixed", "pclass_order", "inv_depth", "rp_landmark",
                "rp_pose_i", "rp_pose_j", "rp_pts_i", "rp_pts_j", "q_ic", "t_ic", "sp_pose", "sp_p", "sp_q", "sp_info",
-               "gravity", "pose_gt", "inv_depth_gt", "point_xyz", "rx_point", "rx_pose", "rx_obs")
+               "gravity", "pose_gt", "inv_depth_gt", "point_xyz", "rx_point", "rx_pose", "rx_obs", "landmark_fixed", "point_fixed")
     _SCALARS = ("rp_info", "rp_loss", "rp_loss_delta", "ext_pose", "storage")
 
     def export(self):

@@ -119,6 +119,8 @@ struct vio_problem {
     DBuf<uint8_t> pose_fixed, sb_fixed;
     DBuf<int> pose_off, sb_off, pose_blk;
     DBuf<int> lm_host, lm_eptr, e_pose_j;
+    DBuf<uint8_t> lm_fixed, pt_fixed;  // fixed landmark-class vertices; has_*_fixed says whether the view points at them
+    bool has_lm_fixed = false, has_pt_fixed = false;
     DBuf<double> lm_pix, lm_piy, lm_piz, e_pjx, e_pjy;
     DBuf<double> Hll, bl, wh, wo, we;
     bool ext_free = false;
@@ -291,6 +293,7 @@ void fill_view(vio_problem *p) {
     v.pose_off = p->pose_off.p; v.sb_off = p->sb_off.p; v.pose_blk = p->pose_blk.p;
     v.poseRT = p->poseRT.p;
     v.lm_host = p->lm_host.p; v.lm_eptr = p->lm_eptr.p;
+    v.lm_fixed = p->has_lm_fixed ? p->lm_fixed.p : nullptr; v.pt_fixed = p->has_pt_fixed ? p->pt_fixed.p : nullptr;
     v.lm_pix = p->lm_pix.p; v.lm_piy = p->lm_piy.p; v.lm_piz = p->lm_piz.p;
     v.e_pose_j = p->e_pose_j.p; v.e_pjx = p->e_pjx.p; v.e_pjy = p->e_pjy.p;
     v.Hll = p->Hll.p; v.bl = p->bl.p; v.wh = p->wh.p; v.wo = p->wo.p;
@@ -1260,6 +1263,10 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     CK(upload(p->pose_blk, K.pose_blk.data(), (size_t)C, s));
     CK(p->poseRT.alloc(16 * (size_t)C));
     CK(upload(p->lm_host, K.lm_host.data(), (size_t)L, s)); CK(upload(p->lm_eptr, K.lm_eptr.data(), (size_t)L + 1, s));
+    p->has_lm_fixed = !K.lm_fixed.empty() && L > 0;
+    if (p->has_lm_fixed) CK(upload(p->lm_fixed, K.lm_fixed.data(), (size_t)L, s));
+    p->has_pt_fixed = !K.pt_fixed.empty() && K.Lx > 0;
+    if (p->has_pt_fixed) CK(upload(p->pt_fixed, K.pt_fixed.data(), (size_t)K.Lx, s));
     CK(upload(p->lm_pix, K.pix.data(), (size_t)L, s)); CK(upload(p->lm_piy, K.piy.data(), (size_t)L, s));
     CK(upload(p->lm_piz, K.piz.data(), (size_t)L, s));
     CK(upload(p->e_pose_j, K.e_pose_j.data(), (size_t)E, s));
@@ -1292,23 +1299,29 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
             for (int gi = 0; gi < K.n_groups; ++gi) mx = std::max(mx, schur_smem_bytes(K.g_hdr[8 * (size_t)gi + 1], K.g_hdr[8 * (size_t)gi + 3]));
             p->schur_smem = mx;
             CK(RAISE_SMEM(k_schur_groups));
-            // edge kernel: 2..5 warps per CTA (VIO_B200_EDGE_WARPS; default 4), shared memory of the largest group
-            int ew = 4;
-            if (const char *ev = getenv("VIO_B200_EDGE_WARPS")) ew = atoi(ev);
-            if (ew < 2 || ew > VIO_EDGE_WARPS_MAX) ew = 4;
-            p->edge_warps = ew;
+            // edge kernel: warps per CTA (2..4) x observer slots per round (1: 32 landmarks x 1 slot, 2: 16 landmarks x 2 slots).
+            // A CTA lasts as long as its busiest warp and 12 warps are resident per SM whatever the CTA size, so the
+            // throughput of a shape goes like 1 / (warps x rounds of the busiest warp): take the cheapest combination.
+            // VIO_B200_EDGE_WARPS / VIO_B200_EDGE_SPW override (tuning knobs).
+            int best_w = 2, best_spw = 1;
+            double best_cost = 1e300;
+            for (int spw = 1; spw <= 2; ++spw)
+                for (int w = 2; w <= 4; ++w) {
+                    double cost = 0.0;
+                    for (int gi = 0; gi < K.n_groups; ++gi) {
+                        const int ns = K.g_hdr[8 * (size_t)gi + 1], nlm = K.g_hdr[8 * (size_t)gi + 3];
+                        const int units = (ns - 1 + spw - 1) / spw, per_warp = (units + w - 1) / w;
+                        const int rounds = (nlm + 32 / spw - 1) / (32 / spw);
+                        cost += (double)w * (per_warp * (rounds + 0.5) + 1.5);  // + the slot reduction and the serial phases
+                    }
+                    if (cost < best_cost) { best_cost = cost; best_w = w; best_spw = spw; }
+                }
+            if (const char *ev = getenv("VIO_B200_EDGE_WARPS")) { const int w = atoi(ev); if (w >= 2 && w <= VIO_EDGE_WARPS_MAX) best_w = w; }
+            if (const char *ev = getenv("VIO_B200_EDGE_SPW")) best_spw = atoi(ev) == 2 ? 2 : 1;
+            p->edge_warps = best_w; p->edge_spw = best_spw;
             size_t me = 0;
-            for (int gi = 0; gi < K.n_groups; ++gi) me = std::max(me, edges_smem_bytes(K.g_hdr[8 * (size_t)gi + 1], K.g_hdr[8 * (size_t)gi + 3], ew));
+            for (int gi = 0; gi < K.n_groups; ++gi) me = std::max(me, edges_smem_bytes(K.g_hdr[8 * (size_t)gi + 1], K.g_hdr[8 * (size_t)gi + 3], best_w));
             p->edge_smem = me;
-            // slots per round: 1 (32 landmarks x 1 slot) or 2 (16 landmarks x 2 slots), whichever needs fewer rounds
-            long long r1 = 0, r2 = 0;
-            for (int gi = 0; gi < K.n_groups; ++gi) {
-                const int ns = K.g_hdr[8 * (size_t)gi + 1], nlm = K.g_hdr[8 * (size_t)gi + 3];
-                r1 += (long long)((nlm + 31) / 32) * (ns - 1);
-                r2 += (long long)((nlm + 15) / 16) * (ns / 2);
-            }
-            p->edge_spw = r2 < r1 ? 2 : 1;
-            if (const char *ev = getenv("VIO_B200_EDGE_SPW")) p->edge_spw = atoi(ev) == 2 ? 2 : 1;
             { const int rc_cap = launch_lin_edges(p, p->view, GroupView(), true); if (rc_cap) return rc_cap; }
         }
         CK(RAISE_SMEM(k_linearize_grouped<true>));
@@ -1600,14 +1613,16 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
             RC(do_solve_step(p, o, lambda, (solver_now == VIO_SOLVER_DENSE_CHOL || solver_now == VIO_SOLVER_BLOCK_CHOL || solver_now == VIO_SOLVER_BCR) ? nullptr : &pit));
             st->trial_steps++;
             st->pcg_iterations += pit;
-            // scalars of this trial step: scale and |dx|^2
+            // scalars of this trial step: scale and |dx|^2.  Only the v15 loop looks at them before the update (its
+            // |dx|^2 stop test); otherwise they ride on the chi2 read-back below (one host sync per trial step, not two).
             CK(cudaMemcpyAsync(p->h_scal + 4, p->scal.p + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-            CK(cudaStreamSynchronize(p->stream));
-            const double dot = p->h_scal[4] + p->h_scal[6];
-            const double dx2 = p->h_scal[5] + p->h_scal[7];
-            if (v15 && !o.fixed_iterations && (dx2 <= 1e-6 || false_cnt > 10)) {
-                stop = true;
-                break;
+            if (v15 && !o.fixed_iterations) {
+                CK(cudaStreamSynchronize(p->stream));
+                const double dx2_now = p->h_scal[5] + p->h_scal[7];
+                if (dx2_now <= 1e-6 || false_cnt > 10) {
+                    stop = true;
+                    break;
+                }
             }
             if (v15 && o.fixed_iterations && false_cnt > 10) {
                 stop = true;
@@ -1615,9 +1630,10 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
             }
             RC(do_apply(p, o));
             // IsGoodStepInLM
-            const double scale = v15 ? dot + 1e-3 : 0.5 * dot + 1e-6;
             double temp_chi = 0.0;
-            RC(do_chi2(p, o, &temp_chi));
+            RC(do_chi2(p, o, &temp_chi));  // synchronises the stream: h_scal[4..7] have arrived as well
+            const double dot = p->h_scal[4] + p->h_scal[6];
+            const double scale = v15 ? dot + 1e-3 : 0.5 * dot + 1e-6;
             const double rho = (chi - temp_chi) / scale;
             if (rho > 0 && std::isfinite(temp_chi)) {
                 double alpha = 1.0 - std::pow(2 * rho - 1, 3);

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_backsub_batch(DevView v, const int *lm_
             const double *dj = v.dxp + v.pose_off[v.e_pose_j[e]];
             for (int q = 0; q < 6; ++q) t -= w[q] * dj[q];
         }
-        const double d = t / v.Hll[l];
+        const double d = (v.lm_fixed && v.lm_fixed[l]) ? 0.0 : t / v.Hll[l];  // fixed landmark: constant
         v.dxl[l] = d;
         sc += d * (lambda * d + bl);
         n2 += d * d;

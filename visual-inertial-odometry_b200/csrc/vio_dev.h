@@ -52,4 +52,6 @@ struct DevView {
     const int *px_eptr, *ex_pose;        // [Lx+1], [Ex]
     const double *ex_ox, *ex_oy;         // [Ex]
     double *Hxx, *bx, *wx, *dxx;         // [Lx][6] sym 3x3 (xx xy xz yy yz zz), [Lx][3], [Ex][18] H_lp rows 3x6, [Lx][3]
+    // fixed landmark-class vertices (nullptr = none): Jacobian blocks skipped, left out of Schur and back-substitution
+    const uint8_t *lm_fixed, *pt_fixed;  // [L] (packed order), [Lx]
 };

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
         pw[0] += pc[9]; pw[1] += pc[10]; pw[2] += pc[11];
         mat3_mul_vec(v.Ric, pts_i, tmp);
         mat3_mul_vec(pc, tmp, g);
-        const double il2 = -1.0 / (lam * lam);
+        const double il2 = (v.lm_fixed && v.lm_fixed[gl]) ? 0.0 : -1.0 / (lam * lam);  // fixed landmark: J_lambda = 0
         mat3_mul_hat(pc, pbi, G);
         double *o = lmh + LHS * (size_t)l;
         o[0] = pw[0]; o[1] = pw[1]; o[2] = pw[2];
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(VIO_GROUP_THREADS_MAX) k_linearize_grouped(Dev
             const int gl = h.lm0 + l;
             v.Hll[gl] = Hll;
             v.bl[gl] = bl;
-            hinv[l] = 1.0 / Hll;
+            hinv[l] = (v.lm_fixed && v.lm_fixed[gl]) ? 0.0 : 1.0 / Hll;
             blv[l] = bl;
             double wh[6] = {0, 0, 0, 0, 0, 0};
             if (!hfix) {
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_lin_edges(DevView v, GroupView g
         pw[0] += pc[9]; pw[1] += pc[10]; pw[2] += pc[11];
         mat3_mul_vec(v.Ric, pts_i, tmp);
         mat3_mul_vec(pc, tmp, g);
-        const double il2 = -(il * il);
+        const double il2 = (v.lm_fixed && v.lm_fixed[gl]) ? 0.0 : -(il * il);  // fixed landmark: J_lambda = 0
         mat3_mul_hat(pc, pbi, G);
         double *o = lmh + LHS * (size_t)l;
         o[0] = pw[0]; o[1] = pw[1]; o[2] = pw[2];

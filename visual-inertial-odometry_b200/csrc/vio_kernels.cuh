@@ -318,7 +318,9 @@ VIO_HD void linearize_landmark(const DevView &v, int l) {
     double g[3];
     mat3_mul_vec(v.Ric, pts_i, tmp);
     mat3_mul_vec(RTh, tmp, g);
-    const double il2 = -1.0 / (lam * lam);
+    // a fixed landmark has no Jacobian block (MakeHessian skips fixed vertices): J_lambda = B g = 0
+    const bool lfix = v.lm_fixed && v.lm_fixed[l];
+    const double il2 = lfix ? 0.0 : -1.0 / (lam * lam);
     g[0] *= il2; g[1] *= il2; g[2] *= il2;
     // G = -Ri hat(p_bi)
     double G[9];
@@ -558,7 +560,7 @@ VIO_HD void linearize_landmark(const DevView &v, int l) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) wep[k] = wes[k];
     }
-    if (!WITH_SCHUR) return;
+    if (!WITH_SCHUR || lfix) return;  // a fixed landmark is a constant: nothing to eliminate
     // Schur complement: S -= Hpl Hll^-1 Hlp ; bS -= Hpl Hll^-1 bl     (landmark diagonal is never damped)
     // vertex list: host (a = -1), observers (0 .. n_obs-1) and, when it is being estimated, the extrinsic vertex (a = n_obs)
     const double inv = 1.0 / Hll;
@@ -785,7 +787,7 @@ __global__ void __launch_bounds__(256) k_backsub(DevView v, double lambda, doubl
 #pragma unroll
             for (int k = 0; k < 6; ++k) t -= w[k] * dx[k];
         }
-        const double d = t / v.Hll[l];
+        const double d = (v.lm_fixed && v.lm_fixed[l]) ? 0.0 : t / v.Hll[l];  // fixed landmark: constant
         v.dxl[l] = d;
         sc += d * (lambda * d + bl);
         n2 += d * d;

@@ -59,7 +59,7 @@ __global__ void k_marg_reproj(DevView v, MargEdgeView m, double *H, double *b, i
         double Rp[3], col[3];
         mat3_mul_vec(v.Ric, pts_i, Rp);
         mat3_mul_vec(ARi, Rp, col);
-        const double il2 = -1.0 / (lam * lam);
+        const double il2 = (v.lm_fixed && v.lm_fixed[l]) ? 0.0 : -1.0 / (lam * lam);  // fixed landmark: no Jacobian block
         for (int a = 0; a < 3; ++a) Jf[19 * a + 0] = col[a] * il2;
     }
     // pose_i: [A, A Ri * -hat(p_bi)]

@@ -26,6 +26,7 @@ struct PackedGraph {
     std::vector<uint8_t> blk_fixed, pose_fixed, sb_fixed, row_fixed;
     double qic[4], tic[3];
     std::vector<int> lm_global, lm_host, lm_eptr, e_pose_j;
+    std::vector<uint8_t> lm_fixed, pt_fixed;  // empty = none fixed
     std::vector<double> pix, piy, piz, pjx, pjy, invd;
     std::vector<int> rowptr, col, tr, diag;
     // VertexPointXYZ landmarks (caller order) and their EdgeReprojectionXYZ observations, CSR by point
@@ -247,6 +248,12 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     lm_host.assign(L, 0); lm_eptr.assign(L + 1, 0); e_pose_j.assign(E, 0);
     pix.assign(L, 0.0); piy.assign(L, 0.0); piz.assign(L, 1.0); pjx.assign(E, 0.0); pjy.assign(E, 0.0); invd.assign(L, 0.0);
     K.lm_global.resize(L);
+    {
+        bool any = false;
+        if (g->landmark_fixed)
+            for (int l = 0; l < Lg && !any; ++l) any = g->landmark_fixed[l] != 0;
+        K.lm_fixed.assign(any ? (size_t)L : 0, 0);
+    }
     // local landmark order: sorted by host pose (stable) so that landmarks sharing a host are contiguous and
     // can be grouped; landmarks without edges go last.
     std::vector<int> lorder(L);
@@ -268,6 +275,7 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         const int l = lorder[ll];
         K.lm_global[ll] = l;
         invd[ll] = g->inv_depth[l];
+        if (!K.lm_fixed.empty()) K.lm_fixed[ll] = g->landmark_fixed[l] ? 1 : 0;
         lm_eptr[ll] = ecur;
         for (int k = cnt[l]; k < cnt[l + 1]; ++k) {
             const int e = eorder[k];
@@ -297,6 +305,10 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         return pack_fail(err, VIO_ERR_UNSUPPORTED, "VertexPointXYZ landmarks are not supported with sharding / lock-step batches");
     if (Ex > 0x7fffffffLL) return pack_fail(err, VIO_ERR_UNSUPPORTED, "more than 2^31 EdgeReprojectionXYZ edges");
     K.Lx = Lx; K.Ex = Ex;
+    K.pt_fixed.clear();
+    if (g->point_fixed)
+        for (int l = 0; l < Lx; ++l)
+            if (g->point_fixed[l]) { K.pt_fixed.assign(g->point_fixed, g->point_fixed + Lx); break; }
     K.px_eptr.assign((size_t)Lx + 1, 0); K.ex_pose.assign(Ex, 0); K.ex_ox.assign(Ex, 0.0); K.ex_oy.assign(Ex, 0.0);
     {
         for (long long e = 0; e < Ex; ++e) {
@@ -555,6 +567,12 @@ struct PackedMerge {
         for (int q = 0; q < 3; ++q) m.tic[q] = ks[0].tic[q];
         m.pose_off.resize(m.C); m.sb_off.resize(m.NSB); m.pose_blk.resize(m.C); m.blk_off.resize(m.NB); m.blk_dim.resize(m.NB);
         m.blk_fixed.resize(m.NB); m.pose_fixed.resize(m.C); m.sb_fixed.resize(m.NSB); m.row_fixed.resize(m.P);
+        {
+            bool any = false;
+            for (int k = 0; k < B; ++k) any = any || !ks[k].lm_fixed.empty();
+            m.lm_fixed.assign(any ? (size_t)m.L : 0, 0);
+            m.pt_fixed.clear();
+        }
         m.lm_global.resize(m.L); m.lm_host.resize(m.L); m.lm_eptr.resize((size_t)m.L + 1); m.e_pose_j.resize(m.E);
         m.pix.resize(m.L); m.piy.resize(m.L); m.piz.resize(m.L); m.invd.resize(m.L); m.pjx.resize(m.E); m.pjy.resize(m.E);
         m.lm_eptr[m.L] = (int)m.E;
@@ -587,6 +605,7 @@ struct PackedMerge {
             for (int l = 0; l < K.L; ++l) {
                 m.lm_global[l0 + l] = K.lm_global[l] + l0; m.lm_host[l0 + l] = K.lm_host[l] + c0; m.lm_eptr[l0 + l] = K.lm_eptr[l] + e0;
             }
+            if (K.L && !m.lm_fixed.empty() && !K.lm_fixed.empty()) std::copy(K.lm_fixed.begin(), K.lm_fixed.end(), m.lm_fixed.begin() + l0);
             if (K.L) {
                 std::copy(K.pix.begin(), K.pix.end(), m.pix.begin() + l0); std::copy(K.piy.begin(), K.piy.end(), m.piy.begin() + l0);
                 std::copy(K.piz.begin(), K.piz.end(), m.piz.begin() + l0); std::copy(K.invd.begin(), K.invd.end(), m.invd.begin() + l0);

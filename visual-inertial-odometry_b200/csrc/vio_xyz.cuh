@@ -71,9 +71,14 @@ VIO_HD void linearize_point(const DevView &v, int l) {
     const int e0 = v.px_eptr[l], e1 = v.px_eptr[l + 1];
     const double X[3] = {v.pt[3 * (size_t)l], v.pt[3 * (size_t)l + 1], v.pt[3 * (size_t)l + 2]};
     double Hs[6] = {0, 0, 0, 0, 0, 0}, bs[3] = {0, 0, 0};
+    const bool pfix = v.pt_fixed && v.pt_fixed[l];
     for (int e = e0; e < e1; ++e) {
         XyzEdge E;
         xyz_edge(v, X, e, E);
+        if (pfix) {  // fixed point: no Jacobian block (MakeHessian skips fixed vertices)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) E.JX[c] = 0.0;
+        }
         double rho0, drho, W[3];
         robust_weights(v.rp_loss, v.rp_delta, v.rp_info, E.r, rho0, drho, W);
         const double dc = drho * v.rp_info;
@@ -117,7 +122,7 @@ VIO_HD void linearize_point(const DevView &v, int l) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) Ho[k] = Hs[k];
     bo[0] = bs[0]; bo[1] = bs[1]; bo[2] = bs[2];
-    if (!WITH_SCHUR || e0 == e1) return;
+    if (!WITH_SCHUR || e0 == e1 || pfix) return;
     // Schur complement of the 3x3 landmark block: S -= Hpl Hll^-1 Hlp ; bS -= Hpl Hll^-1 bl
     double Hi[9];
     inv3_sym(Hs, Hi);
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(256) k_chi2_xyz(DevView v, double *partial) {
 VIO_HD void backsub_point(const DevView &v, int l, double lambda, double &sc, double &n2) {
     const int e0 = v.px_eptr[l], e1 = v.px_eptr[l + 1];
     double *dx = v.dxx + 3 * (size_t)l;
-    if (e0 == e1) { dx[0] = dx[1] = dx[2] = 0.0; return; }
+    if (e0 == e1 || (v.pt_fixed && v.pt_fixed[l])) { dx[0] = dx[1] = dx[2] = 0.0; return; }  // no edges, or a fixed point
     const double *b = v.bx + 3 * (size_t)l;
     double t[3] = {b[0], b[1], b[2]};
     for (int e = e0; e < e1; ++e) {

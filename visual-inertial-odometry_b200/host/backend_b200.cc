@@ -221,7 +221,7 @@ void Problem::SetOrdering() {
 // everything Problem::Solve / Marginalize hand to the C-ABI: flat arrays + the vertex objects to write back into
 struct PackB200 {
     std::vector<double> pose, sb, invd;
-    std::vector<uint8_t> pose_fixed, sb_fixed;
+    std::vector<uint8_t> pose_fixed, sb_fixed, lm_fixed, pt_fixed;
     std::vector<int32_t> pclass;
     std::unordered_map<unsigned long, int> pose_idx, sb_idx, lm_idx;
     std::vector<std::shared_ptr<Vertex>> pose_v, sb_v, lm_v;
@@ -238,7 +238,7 @@ struct PackB200 {
 bool Problem::PackGraphB200(PackB200 &K) {
     auto &pose = K.pose; auto &sb = K.sb; auto &invd = K.invd; auto &pose_fixed = K.pose_fixed; auto &sb_fixed = K.sb_fixed;
     auto &pclass = K.pclass; auto &pose_idx = K.pose_idx; auto &sb_idx = K.sb_idx; auto &lm_idx = K.lm_idx;
-    auto &pose_v = K.pose_v; auto &sb_v = K.sb_v; auto &lm_v = K.lm_v;
+    auto &pose_v = K.pose_v; auto &sb_v = K.sb_v; auto &lm_v = K.lm_v; auto &lm_fixed = K.lm_fixed;
     auto &rp_lm = K.rp_lm; auto &rp_i = K.rp_i; auto &rp_j = K.rp_j; auto &sp_pose = K.sp_pose;
     auto &imu_pi = K.imu_pi; auto &imu_si = K.imu_si; auto &imu_pj = K.imu_pj; auto &imu_sj = K.imu_sj;
     auto &rp_pti = K.rp_pti; auto &rp_ptj = K.rp_ptj; auto &sp_p = K.sp_p; auto &sp_q = K.sp_q; auto &sp_info = K.sp_info;
@@ -264,15 +264,15 @@ bool Problem::PackGraphB200(PackB200 &K) {
             for (int k = 0; k < 9; ++k) sb.push_back(x[k]);
             sb_fixed.push_back(v->IsFixed());
         } else if (t == "VertexInverseDepth") {
-            if (v->IsFixed()) { std::cerr << "vio_b200: fixed landmarks are not supported" << std::endl; return false; }
             lm_idx[v->Id()] = (int)lm_v.size();
             lm_v.push_back(v);
             invd.push_back(x[0]);
+            lm_fixed.push_back(v->IsFixed());
         } else if (t == "VertexPointXYZ") {
-            if (v->IsFixed()) { std::cerr << "vio_b200: fixed landmarks are not supported" << std::endl; return false; }
             K.pt_idx[v->Id()] = (int)K.pt_v.size();
             K.pt_v.push_back(v);
             for (int k = 0; k < 3; ++k) K.pt.push_back(x[k]);
+            K.pt_fixed.push_back(v->IsFixed());
         } else {
             std::cerr << "vio_b200: vertex type " << t << " is not on the device path" << std::endl;
             return false;
@@ -388,6 +388,9 @@ bool Problem::PackGraphB200(PackB200 &K) {
     g.storage = VIO_STORAGE_AUTO;
     g.n_point = (int32_t)K.pt_v.size(); g.point_xyz = K.pt.data();
     g.n_reproj_xyz = (int64_t)K.rx_point.size(); g.rx_point = K.rx_point.data(); g.rx_pose = K.rx_pose.data(); g.rx_obs = K.rx_obs.data();
+    // fixed landmark-class vertices are constants on the device path (see vio_b200.h)
+    g.landmark_fixed = lm_fixed.empty() ? nullptr : lm_fixed.data();
+    g.point_fixed = K.pt_fixed.empty() ? nullptr : K.pt_fixed.data();
 
     return true;
 }
