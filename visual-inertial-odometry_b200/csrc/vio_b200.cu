@@ -1247,8 +1247,11 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     p->C = C; p->NSB = NSB; p->L = L; p->P = P; p->NB = NB; p->E = E; p->storage = K.storage; p->nnzb = K.nnzb;
     p->Lglobal = K.Lglobal; p->s_count = K.s_count; p->n_se3 = (int)K.se3_keep.size(); p->n_imu = g->n_imu;
     p->h_pose_off = K.pose_off; p->h_sb_off = K.sb_off; p->h_rowptr = K.rowptr; p->h_col = K.col;
-    p->lm_global = K.lm_global;
-    if (E <= (4 << 20)) { p->h_lm_host = K.lm_host; p->h_lm_eptr = K.lm_eptr; p->h_e_pose_j = K.e_pose_j; }
+    p->lm_global.assign(K.lm_global.begin(), K.lm_global.end());
+    if (E <= (4 << 20)) {
+        p->h_lm_host.assign(K.lm_host.begin(), K.lm_host.end()); p->h_lm_eptr.assign(K.lm_eptr.begin(), K.lm_eptr.end());
+        p->h_e_pose_j.assign(K.e_pose_j.begin(), K.e_pose_j.end());
+    }
     else { p->h_lm_host.clear(); p->h_lm_eptr.clear(); p->h_e_pose_j.clear(); }
     p->h_imu_pose_i.assign(g->imu_pose_i, g->imu_pose_i + (g->n_imu > 0 ? g->n_imu : 0));
     p->h_imu_pose_j.assign(g->imu_pose_j, g->imu_pose_j + (g->n_imu > 0 ? g->n_imu : 0));

@@ -4,17 +4,37 @@
 // (/root/reference/workspace/assignments/17-vins-initialization/vins-mono/src/backend/problem.cc:256-285):
 // pose-class vertices get consecutive offsets in creation order, landmarks follow.
 #pragma once
+#include <chrono>
 #include <algorithm>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <limits>
+#include <memory>
+#include <utility>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/vio_b200.h"
 
 #include "vio_bcr.h"
+
+// std::vector whose resize() leaves new elements uninitialised: the per-edge arrays (hundreds of MB at 10M edges) are
+// written exactly once by the packer's worker threads, which then also take their first-touch page faults in parallel
+// instead of one thread zero-filling everything first (that alone was a quarter of vio_set_graph).
+template <class T>
+struct pack_alloc : std::allocator<T> {
+    template <class U> struct rebind { using other = pack_alloc<U>; };
+    pack_alloc() = default;
+    template <class U> pack_alloc(const pack_alloc<U> &) {}
+    template <class U, class... A>
+    void construct(U *q, A &&...a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void *)q) U;
+        else ::new ((void *)q) U(std::forward<A>(a)...);
+    }
+};
+template <class T> using pvec = std::vector<T, pack_alloc<T>>;
 
 struct PackedGraph {
     int C = 0, NSB = 0, NB = 0, P = 0, L = 0, Lglobal = 0, storage = 1;
@@ -25,9 +45,9 @@ struct PackedGraph {
     std::vector<int> pose_off, sb_off, pose_blk, blk_off, blk_dim;
     std::vector<uint8_t> blk_fixed, pose_fixed, sb_fixed, row_fixed;
     double qic[4], tic[3];
-    std::vector<int> lm_global, lm_host, lm_eptr, e_pose_j;
+    pvec<int> lm_global, lm_host, lm_eptr, e_pose_j;
     std::vector<uint8_t> lm_fixed, pt_fixed;  // empty = none fixed
-    std::vector<double> pix, piy, piz, pjx, pjy, invd;
+    pvec<double> pix, piy, piz, pjx, pjy, invd;
     std::vector<int> rowptr, col, tr, diag;
     // VertexPointXYZ landmarks (caller order) and their EdgeReprojectionXYZ observations, CSR by point
     int Lx = 0;
@@ -41,8 +61,8 @@ struct PackedGraph {
     std::vector<int> g_hdr;        // 8 ints per group: host ns lm0 nlm ell0 pair0 slot0 pad
     std::vector<int> g_slot_pose;  // per group ns entries (entry 0 = host)
     std::vector<long long> g_pairinfo;
-    std::vector<double> ell_pjx, ell_pjy;
-    std::vector<int> ell_edge;
+    pvec<double> ell_pjx, ell_pjy;
+    pvec<int> ell_edge;
     // multi-GPU, node-range sharding (see pack_graph): this rank keeps the landmarks hosted by the cameras of ITS nodes of the
     // block-cyclic-reduction partition, so its share of S stays inside its own nodes and the next rank's interface node
     bool shard_by_node = false;
@@ -59,17 +79,35 @@ inline int pack_fail(std::string &err, int code, const char *fmt, ...) {
     return code;
 }
 
+// Host threads for the O(E) passes of the packer (VIO_B200_PACK_THREADS overrides; small graphs stay on the caller's thread:
+// the lock-step batch path already packs one problem per thread).
+inline int pack_threads(long long work) {
+    if (work < (1 << 18)) return 1;
+    int t = (int)std::thread::hardware_concurrency();
+    if (const char *ev = getenv("VIO_B200_PACK_THREADS")) t = atoi(ev);
+    return std::max(1, std::min(t, 16));
+}
+template <class F>
+inline void pack_parallel(int nthreads, F &&body) {  // body(thread index)
+    if (nthreads <= 1) { body(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(nthreads - 1);
+    for (int t = 1; t < nthreads; ++t) th.emplace_back([&body, t] { body(t); });
+    body(0);
+    for (auto &x : th) x.join();
+}
+
 // co-visibility pattern of the inverse-depth landmarks over the pose blocks (+ diagonal): rows[a] = blocks coupled with a
-inline void covis_rows(const vio_graph *g, const std::vector<int> &cnt, const std::vector<int> &eorder, const std::vector<int> &pose_blk, int NB,
-                       int Lg, std::vector<std::vector<int>> &rows) {
+template <class EO>
+inline void covis_rows_range(const vio_graph *g, const std::vector<int> &cnt, const EO &eorder, const std::vector<int> &pose_blk, int NB,
+                             int l_begin, int l_end, std::vector<std::vector<int>> &rows) {
     rows.assign(NB, std::vector<int>());
-    for (int k = 0; k < NB; ++k) rows[k].push_back(k);
     auto add = [&](int a, int b) {
         auto &r = rows[a];
         if (std::find(r.begin(), r.end(), b) == r.end()) r.push_back(b);
     };
     std::vector<int> set, last;
-    for (int l = 0; l < Lg; ++l) {
+    for (int l = l_begin; l < l_end; ++l) {
         set.clear();
         if (cnt[l] == cnt[l + 1]) continue;
         set.push_back(pose_blk[g->rp_pose_i[eorder[cnt[l]]]]);
@@ -80,7 +118,28 @@ inline void covis_rows(const vio_graph *g, const std::vector<int> &cnt, const st
         last = set;
     }
 }
-inline void covis_pattern(const vio_graph *g, const std::vector<int> &cnt, const std::vector<int> &eorder, const std::vector<int> &pose_blk, int NB,
+// landmark ranges on the packer's host threads, then the union per block row (+ the diagonal)
+template <class EO>
+inline void covis_rows(const vio_graph *g, const std::vector<int> &cnt, const EO &eorder, const std::vector<int> &pose_blk, int NB,
+                       int Lg, std::vector<std::vector<int>> &rows) {
+    const int nth = pack_threads((long long)cnt[Lg]);
+    std::vector<std::vector<std::vector<int>>> part(nth);
+    pack_parallel(nth, [&](int t) {
+        covis_rows_range(g, cnt, eorder, pose_blk, NB, (int)((long long)Lg * t / nth), (int)((long long)Lg * (t + 1) / nth), part[t]);
+    });
+    rows.assign(NB, std::vector<int>());
+    pack_parallel(nth, [&](int t) {
+        for (int k = (int)((long long)NB * t / nth); k < (int)((long long)NB * (t + 1) / nth); ++k) {
+            auto &r = rows[k];
+            r.push_back(k);
+            for (int u = 0; u < nth; ++u)
+                for (int b : part[u][k])
+                    if (std::find(r.begin(), r.end(), b) == r.end()) r.push_back(b);
+        }
+    });
+}
+template <class EO>
+inline void covis_pattern(const vio_graph *g, const std::vector<int> &cnt, const EO &eorder, const std::vector<int> &pose_blk, int NB,
                           int Lg, std::vector<int> &rowptr, std::vector<int> &col) {
     std::vector<std::vector<int>> rows;
     covis_rows(g, cnt, eorder, pose_blk, NB, Lg, rows);
@@ -93,7 +152,20 @@ inline void covis_pattern(const vio_graph *g, const std::vector<int> &cnt, const
     }
 }
 
+struct PackTimer {  // VIO_B200_PACK_PROFILE=1: phase times of pack_graph on stderr
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PackTimer() : on(getenv("VIO_B200_PACK_PROFILE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[vio_b200 pack] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, PackedGraph &K, std::string &err, int batch = 1) {
+    PackTimer ptm;
     const int C = g->n_pose, NSB = g->n_speedbias, Lg = g->n_landmark;
     const long long Eg = g->n_reproj;
     if (C < 0 || NSB < 0 || Lg < 0 || Eg < 0) return pack_fail(err, VIO_ERR_INVALID, "negative size");
@@ -154,20 +226,49 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         for (int k = 0; k < 3; ++k) tic[k] = g->t_ic[k];
     }
     // ---- landmark-sorted edge CSR (global), checks -------------------------------------------
+    // (drivers add the edges of a landmark back to back, usually landmark after landmark: then rp_landmark is already
+    // non-decreasing, the CSR offsets are the positions where it changes and the edge order is the identity)
     std::vector<int> cnt(Lg + 1, 0);
-    for (long long e = 0; e < Eg; ++e) {
-        int l = g->rp_landmark[e];
-        if (l < 0 || l >= Lg) return pack_fail(err, VIO_ERR_INVALID, "edge %lld: landmark out of range", e);
-        int a = g->rp_pose_i[e], b = g->rp_pose_j[e];
-        if (a < 0 || a >= C || b < 0 || b >= C) return pack_fail(err, VIO_ERR_INVALID, "edge %lld: pose out of range", e);
-        cnt[l + 1]++;
-    }
-    for (int l = 0; l < Lg; ++l) cnt[l + 1] += cnt[l];
-    std::vector<int> eorder(Eg);
+    pvec<int> eorder;
+    eorder.resize(Eg);
     {
-        std::vector<int> cur(cnt.begin(), cnt.end() - 1);
-        for (long long e = 0; e < Eg; ++e) eorder[cur[g->rp_landmark[e]]++] = (int)e;
+        const int nth = pack_threads(Eg);
+        std::vector<long long> bad_l(nth, -1), bad_p(nth, -1);
+        std::vector<char> sorted_t(nth, 1);
+        pack_parallel(nth, [&](int t) {
+            const long long ea = Eg * t / nth, eb = Eg * (t + 1) / nth;
+            int prev = ea > 0 ? g->rp_landmark[ea - 1] : 0;
+            for (long long e = ea; e < eb; ++e) {
+                const int l = g->rp_landmark[e];
+                if (l < 0 || l >= Lg) { if (bad_l[t] < 0) bad_l[t] = e; continue; }
+                const int a = g->rp_pose_i[e], b = g->rp_pose_j[e];
+                if (a < 0 || a >= C || b < 0 || b >= C) { if (bad_p[t] < 0) bad_p[t] = e; }
+                if (l < prev) sorted_t[t] = 0;
+                prev = l;
+                eorder[e] = (int)e;
+            }
+        });
+        bool sorted = true;
+        for (int t = 0; t < nth; ++t) {
+            if (bad_l[t] >= 0) return pack_fail(err, VIO_ERR_INVALID, "edge %lld: landmark out of range", bad_l[t]);
+            if (bad_p[t] >= 0) return pack_fail(err, VIO_ERR_INVALID, "edge %lld: pose out of range", bad_p[t]);
+            sorted = sorted && sorted_t[t];
+        }
+        if (sorted) {
+            int l = 0;  // cnt[k] = first edge of landmark k
+            for (long long e = 0; e < Eg; ++e) {
+                const int le = g->rp_landmark[e];
+                while (l < le) cnt[++l] = (int)e;
+            }
+            while (l < Lg) cnt[++l] = (int)Eg;
+        } else {
+            for (long long e = 0; e < Eg; ++e) cnt[g->rp_landmark[e] + 1]++;
+            for (int l = 0; l < Lg; ++l) cnt[l + 1] += cnt[l];
+            std::vector<int> cur(cnt.begin(), cnt.end() - 1);
+            for (long long e = 0; e < Eg; ++e) eorder[cur[g->rp_landmark[e]]++] = (int)e;
+        }
     }
+    ptm.mark("validate + edge CSR order");
     // ---- which landmarks this rank keeps
     // Legacy sharding: contiguous landmark ranges balanced by edge count; the whole reduced system is all-reduced.
     // Node-range sharding (chosen when the reduced system is block-sparse, a cyclic block band the block cyclic reduction
@@ -243,11 +344,13 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
     const int L = (int)lsel.size();
     long long E = 0;
     for (int l : lsel) E += cnt[l + 1] - cnt[l];
-    std::vector<int> &lm_host = K.lm_host, &lm_eptr = K.lm_eptr, &e_pose_j = K.e_pose_j;
-    std::vector<double> &pix = K.pix, &piy = K.piy, &piz = K.piz, &pjx = K.pjx, &pjy = K.pjy, &invd = K.invd;
-    lm_host.assign(L, 0); lm_eptr.assign(L + 1, 0); e_pose_j.assign(E, 0);
-    pix.assign(L, 0.0); piy.assign(L, 0.0); piz.assign(L, 1.0); pjx.assign(E, 0.0); pjy.assign(E, 0.0); invd.assign(L, 0.0);
+    pvec<int> &lm_host = K.lm_host, &lm_eptr = K.lm_eptr, &e_pose_j = K.e_pose_j;
+    pvec<double> &pix = K.pix, &piy = K.piy, &piz = K.piz, &pjx = K.pjx, &pjy = K.pjy, &invd = K.invd;
+    // uninitialised: every entry is written below (landmarks without edges get the defaults there)
+    lm_host.resize(L); lm_eptr.resize((size_t)L + 1); e_pose_j.resize(E);
+    pix.resize(L); piy.resize(L); piz.resize(L); pjx.resize(E); pjy.resize(E); invd.resize(L);
     K.lm_global.resize(L);
+    ptm.mark("  (allocate SoA)");
     {
         bool any = false;
         if (g->landmark_fixed)
@@ -270,30 +373,45 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
             for (int ll = 0; ll < L; ++ll) lorder[ll] = lsel[idx[ll]];
         }
     }
-    int ecur = 0;
-    for (int ll = 0; ll < L; ++ll) {
-        const int l = lorder[ll];
-        K.lm_global[ll] = l;
-        invd[ll] = g->inv_depth[l];
-        if (!K.lm_fixed.empty()) K.lm_fixed[ll] = g->landmark_fixed[l] ? 1 : 0;
-        lm_eptr[ll] = ecur;
-        for (int k = cnt[l]; k < cnt[l + 1]; ++k) {
-            const int e = eorder[k];
-            const int le = ecur++;
-            if (k == cnt[l]) {
-                lm_host[ll] = g->rp_pose_i[e];
-                pix[ll] = g->rp_pts_i[3 * (size_t)e]; piy[ll] = g->rp_pts_i[3 * (size_t)e + 1]; piz[ll] = g->rp_pts_i[3 * (size_t)e + 2];
-            } else if (g->rp_pose_i[e] != lm_host[ll] || g->rp_pts_i[3 * (size_t)e] != pix[ll] ||
-                       g->rp_pts_i[3 * (size_t)e + 1] != piy[ll] || g->rp_pts_i[3 * (size_t)e + 2] != piz[ll]) {
-                return pack_fail(err, VIO_ERR_UNSUPPORTED,
-                            "landmark %d: edges disagree on host pose / host observation (see vio_b200.h preconditions)", l);
+    ptm.mark("  (landmark order)");
+    {
+        long long ecur = 0;
+        for (int ll = 0; ll < L; ++ll) { lm_eptr[ll] = (int)ecur; ecur += cnt[lorder[ll] + 1] - cnt[lorder[ll]]; }
+    }
+    {
+        const int nth = pack_threads(E);
+        std::vector<int> bad(nth, -1);
+        pack_parallel(nth, [&](int t) {
+            const int la = (int)((long long)L * t / nth), lb = (int)((long long)L * (t + 1) / nth);
+            for (int ll = la; ll < lb; ++ll) {
+                const int l = lorder[ll];
+                K.lm_global[ll] = l;
+                invd[ll] = g->inv_depth[l];
+                if (!K.lm_fixed.empty()) K.lm_fixed[ll] = g->landmark_fixed[l] ? 1 : 0;
+                int le = lm_eptr[ll];
+                if (cnt[l] == cnt[l + 1]) { lm_host[ll] = 0; pix[ll] = 0.0; piy[ll] = 0.0; piz[ll] = 1.0; }
+                for (int k = cnt[l]; k < cnt[l + 1]; ++k, ++le) {
+                    const int e = eorder[k];
+                    if (k == cnt[l]) {
+                        lm_host[ll] = g->rp_pose_i[e];
+                        pix[ll] = g->rp_pts_i[3 * (size_t)e]; piy[ll] = g->rp_pts_i[3 * (size_t)e + 1]; piz[ll] = g->rp_pts_i[3 * (size_t)e + 2];
+                    } else if (g->rp_pose_i[e] != lm_host[ll] || g->rp_pts_i[3 * (size_t)e] != pix[ll] ||
+                               g->rp_pts_i[3 * (size_t)e + 1] != piy[ll] || g->rp_pts_i[3 * (size_t)e + 2] != piz[ll]) {
+                        if (bad[t] < 0) bad[t] = l;
+                    }
+                    e_pose_j[le] = g->rp_pose_j[e];
+                    pjx[le] = g->rp_pts_j[2 * (size_t)e];
+                    pjy[le] = g->rp_pts_j[2 * (size_t)e + 1];
+                }
             }
-            e_pose_j[le] = g->rp_pose_j[e];
-            pjx[le] = g->rp_pts_j[2 * (size_t)e];
-            pjy[le] = g->rp_pts_j[2 * (size_t)e + 1];
-        }
+        });
+        for (int t = 0; t < nth; ++t)
+            if (bad[t] >= 0)
+                return pack_fail(err, VIO_ERR_UNSUPPORTED,
+                                 "landmark %d: edges disagree on host pose / host observation (see vio_b200.h preconditions)", bad[t]);
     }
     lm_eptr[L] = (int)E;
+    ptm.mark("landmark-sorted SoA copy");
 
     // ---- VertexPointXYZ observations, CSR by point ---------------------------------------------------
     const int Lx = g->n_point;
@@ -376,6 +494,7 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         s_count = (size_t)nnzb * 36;
     }
 
+    ptm.mark("storage pattern (BSR)");
     // ---- landmark groups (same host, <= VIO_PACK_NS_MAX pose slots, shared-memory budget) ---------------------
     {
         const int NS_MAX = 22;
@@ -400,107 +519,160 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
             off = 36LL * (it - col.begin());
             return true;
         };
-        K.grouped_ok = true;
-        K.n_groups = 0; K.group_smem_max = 0;
-        K.g_hdr.clear(); K.g_slot_pose.clear(); K.g_pairinfo.clear(); K.ell_pjx.clear(); K.ell_pjy.clear(); K.ell_edge.clear();
-        {
-            // the ELL arrays hold every edge once plus padding: reserve up front instead of growing group by group
-            const size_t cap = (size_t)E + (size_t)E / 4 + 1024;
-            K.ell_pjx.reserve(cap); K.ell_pjy.reserve(cap); K.ell_edge.reserve(cap);
-            const size_t ng = (size_t)L / (size_t)std::max(1, target_lm / 2) + 16;
-            K.g_hdr.reserve(8 * ng); K.g_slot_pose.reserve(NS_MAX * ng / 2); K.g_pairinfo.reserve(ng * 70);
-        }
-        int max_obs_slots = 0;
-        int l0 = 0;
-        std::vector<int> slots;  // slot -> pose (slot 0 = host)
-        std::vector<int> slot_of_pose(C, -1);
-        std::vector<int> seen_stamp(C, 0);  // evaluation (a landmark may be tried twice: last of a run, first of the next) that last listed this pose
-        int stamp = 0;
-        while (l0 < L && K.grouped_ok) {
-            if (lm_eptr[l0] == lm_eptr[l0 + 1]) break;  // only edge-less landmarks remain
-            const int host = lm_host[l0];
-            slots.assign(1, host);
-            slot_of_pose[host] = 0;
-            int l1 = l0;
-            while (l1 < L && lm_eptr[l1] != lm_eptr[l1 + 1] && lm_host[l1] == host && (l1 - l0) < 128) {
-                // would this landmark fit?
-                ++stamp;
-                int added = 0;
-                bool bad = false;
-                for (int e = lm_eptr[l1]; e < lm_eptr[l1 + 1]; ++e) {
-                    const int pj = e_pose_j[e];
-                    if (pj == host || seen_stamp[pj] == stamp) { bad = true; break; }  // observer == host, or seen twice
-                    seen_stamp[pj] = stamp;
-                    if (slot_of_pose[pj] < 0) { slot_of_pose[pj] = (int)slots.size(); slots.push_back(pj); ++added; }
-                }
-                if (bad) { K.grouped_ok = false; break; }
-                const int ns_new = (int)slots.size();
-                if (ns_new > NS_MAX || smem_bytes(ns_new, l1 - l0 + 1) > SMEM_BUDGET) {
-                    // undo this landmark's slots and close the group (a single landmark that does not fit: irregular)
-                    for (int k = 0; k < added; ++k) { slot_of_pose[slots.back()] = -1; slots.pop_back(); }
-                    if (l1 == l0) K.grouped_ok = false;
-                    break;
-                }
-                ++l1;
+        // Groups never span two hosts, so the landmark range is cut at host boundaries into one chunk per host thread.
+        // Pass 1 (per chunk): group boundaries, slot tables, pair tables, ELL sizes.  The chunks' tables are concatenated
+        // (small), which fixes every group's offset into the ELL arrays.  Pass 2 (per chunk): the ELL tiles are written
+        // straight into the final arrays - no per-chunk copies of the per-edge data, first-touch page faults in parallel.
+        struct GroupPart {
+            std::vector<int> g_hdr, g_slot_pose;
+            std::vector<long long> g_pairinfo;
+            size_t ell = 0;
+            bool ok = true;
+            int n_groups = 0, max_obs_slots = 0;
+            size_t smem_max = 0;
+        };
+        auto plan = [&](int lbeg, int lend, GroupPart &O) {
+            {
+                const size_t ng = (size_t)(lend - lbeg) / (size_t)std::max(1, target_lm / 2) + 16;
+                O.g_hdr.reserve(8 * ng); O.g_slot_pose.reserve(NS_MAX * ng / 2); O.g_pairinfo.reserve(ng * 70);
             }
-            for (int p2 : slots) slot_of_pose[p2] = -1;
-            if (!K.grouped_ok) break;
-            // split the feasible run [l0, l1) evenly into chunks of about `target_lm` landmarks
-            const int nrun = l1 - l0;
-            const int nchunk = (nrun + target_lm - 1) / target_lm;
-            for (int ch = 0; ch < nchunk && K.grouped_ok; ++ch) {
-                const int la = l0 + (int)((long long)nrun * ch / nchunk), lb = l0 + (int)((long long)nrun * (ch + 1) / nchunk);
+            int l0 = lbeg;
+            std::vector<int> slots;  // slot -> pose (slot 0 = host)
+            std::vector<int> slot_of_pose(C, -1);
+            std::vector<int> seen_stamp(C, 0);  // evaluation (a landmark may be tried twice: last of a run, first of the next) that last listed this pose
+            int stamp = 0;
+            while (l0 < lend && O.ok) {
+                if (lm_eptr[l0] == lm_eptr[l0 + 1]) break;  // only edge-less landmarks remain
+                const int host = lm_host[l0];
                 slots.assign(1, host);
                 slot_of_pose[host] = 0;
-                for (int l = la; l < lb; ++l)
-                    for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
+                int l1 = l0;
+                while (l1 < lend && lm_eptr[l1] != lm_eptr[l1 + 1] && lm_host[l1] == host && (l1 - l0) < 128) {
+                    // would this landmark fit?
+                    ++stamp;
+                    int added = 0;
+                    bool bad = false;
+                    for (int e = lm_eptr[l1]; e < lm_eptr[l1 + 1]; ++e) {
                         const int pj = e_pose_j[e];
-                        if (slot_of_pose[pj] < 0) { slot_of_pose[pj] = (int)slots.size(); slots.push_back(pj); }
+                        if (pj == host || seen_stamp[pj] == stamp) { bad = true; break; }  // observer == host, or seen twice
+                        seen_stamp[pj] = stamp;
+                        if (slot_of_pose[pj] < 0) { slot_of_pose[pj] = (int)slots.size(); slots.push_back(pj); ++added; }
                     }
-                const int ns = (int)slots.size(), nlm = lb - la;
-                const int ell0 = (int)K.ell_pjx.size(), pair0 = (int)K.g_pairinfo.size(), slot0 = (int)K.g_slot_pose.size();
-                int full = 1;
-                for (int l = la; l < lb; ++l) if (lm_eptr[l + 1] - lm_eptr[l] != ns - 1) full = 0;
-                const int hdr[8] = {host, ns, la, nlm, ell0, pair0, slot0, full};  // [7]: bit 0 full, bit 1 edges in slot order (below)
-                K.g_hdr.insert(K.g_hdr.end(), hdr, hdr + 8);
-                K.g_slot_pose.insert(K.g_slot_pose.end(), slots.begin(), slots.end());
-                const double qnan = std::numeric_limits<double>::quiet_NaN();
-                K.ell_pjx.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, qnan);
-                K.ell_pjy.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, 0.0);
-                K.ell_edge.resize((size_t)ell0 + (size_t)(ns - 1) * nlm, -1);
-                for (int l = la; l < lb; ++l)
-                    for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
-                        const int sl = slot_of_pose[e_pose_j[e]];
-                        const size_t idx = (size_t)ell0 + (size_t)(sl - 1) * nlm + (l - la);
-                        K.ell_pjx[idx] = pjx[e]; K.ell_pjy[idx] = pjy[e]; K.ell_edge[idx] = e;
+                    if (bad) { O.ok = false; break; }
+                    const int ns_new = (int)slots.size();
+                    if (ns_new > NS_MAX || smem_bytes(ns_new, l1 - l0 + 1) > SMEM_BUDGET) {
+                        // undo this landmark's slots and close the group (a single landmark that does not fit: irregular)
+                        for (int k = 0; k < added; ++k) { slot_of_pose[slots.back()] = -1; slots.pop_back(); }
+                        if (l1 == l0) O.ok = false;
+                        break;
                     }
-                if (full) {
-                    // every landmark's edges stored in slot order, landmarks back to back: edge(l, s) = e0 + l (ns - 1) + (s - 1),
-                    // so the Schur kernel's gather needs no index loads
-                    bool direct = true;
-                    const int e0 = lm_eptr[la];
-                    for (int l = la; l < lb && direct; ++l)
-                        for (int k = 0; k < ns - 1; ++k)
-                            if (K.ell_edge[(size_t)ell0 + (size_t)k * nlm + (l - la)] != e0 + (l - la) * (ns - 1) + k) { direct = false; break; }
-                    if (direct) K.g_hdr[K.g_hdr.size() - 1] |= 2;
+                    ++l1;
                 }
-                for (int a = 0; a < ns && K.grouped_ok; ++a)
-                    for (int b = a; b < ns; ++b) {
-                        const int pa = slots[a], pb = slots[b];
-                        long long off = 0, info;
-                        const bool fa = g->pose_fixed && g->pose_fixed[pa], fb = g->pose_fixed && g->pose_fixed[pb];
-                        if (fa || fb) info = 3;
-                        else if (a == b) { if (!block_off(pa, pa, off)) { K.grouped_ok = false; break; } info = (off << 2) | 2; }
-                        else if (pose_off[pa] < pose_off[pb]) { if (!block_off(pa, pb, off)) { K.grouped_ok = false; break; } info = (off << 2) | 0; }
-                        else { if (!block_off(pb, pa, off)) { K.grouped_ok = false; break; } info = (off << 2) | 1; }
-                        K.g_pairinfo.push_back(info);
-                    }
-                K.group_smem_max = std::max(K.group_smem_max, smem_bytes(ns, nlm));
-                max_obs_slots = std::max(max_obs_slots, ns - 1);
                 for (int p2 : slots) slot_of_pose[p2] = -1;
-                K.n_groups++;
+                if (!O.ok) break;
+                // split the feasible run [l0, l1) evenly into chunks of about `target_lm` landmarks
+                const int nrun = l1 - l0;
+                const int nchunk = (nrun + target_lm - 1) / target_lm;
+                for (int ch = 0; ch < nchunk && O.ok; ++ch) {
+                    const int la = l0 + (int)((long long)nrun * ch / nchunk), lb = l0 + (int)((long long)nrun * (ch + 1) / nchunk);
+                    slots.assign(1, host);
+                    slot_of_pose[host] = 0;
+                    for (int l = la; l < lb; ++l)
+                        for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
+                            const int pj = e_pose_j[e];
+                            if (slot_of_pose[pj] < 0) { slot_of_pose[pj] = (int)slots.size(); slots.push_back(pj); }
+                        }
+                    const int ns = (int)slots.size(), nlm = lb - la;
+                    const int pair0 = (int)O.g_pairinfo.size(), slot0 = (int)O.g_slot_pose.size();
+                    if (O.ell + (size_t)(ns - 1) * nlm > 0x7fffffffULL) { O.ok = false; break; }
+                    const int ell0 = (int)O.ell;
+                    O.ell += (size_t)(ns - 1) * nlm;
+                    int full = 1;
+                    for (int l = la; l < lb; ++l) if (lm_eptr[l + 1] - lm_eptr[l] != ns - 1) full = 0;
+                    const int hdr[8] = {host, ns, la, nlm, ell0, pair0, slot0, full};  // [7]: bit 0 full, bit 1 edges in slot order (pass 2)
+                    O.g_hdr.insert(O.g_hdr.end(), hdr, hdr + 8);
+                    O.g_slot_pose.insert(O.g_slot_pose.end(), slots.begin(), slots.end());
+                    for (int a = 0; a < ns && O.ok; ++a)
+                        for (int b = a; b < ns; ++b) {
+                            const int pa = slots[a], pb = slots[b];
+                            long long off = 0, info;
+                            const bool fa = g->pose_fixed && g->pose_fixed[pa], fb = g->pose_fixed && g->pose_fixed[pb];
+                            if (fa || fb) info = 3;
+                            else if (a == b) { if (!block_off(pa, pa, off)) { O.ok = false; break; } info = (off << 2) | 2; }
+                            else if (pose_off[pa] < pose_off[pb]) { if (!block_off(pa, pb, off)) { O.ok = false; break; } info = (off << 2) | 0; }
+                            else { if (!block_off(pb, pa, off)) { O.ok = false; break; } info = (off << 2) | 1; }
+                            O.g_pairinfo.push_back(info);
+                        }
+                    O.smem_max = std::max(O.smem_max, smem_bytes(ns, nlm));
+                    O.max_obs_slots = std::max(O.max_obs_slots, ns - 1);
+                    for (int p2 : slots) slot_of_pose[p2] = -1;
+                    O.n_groups++;
+                }
+                l0 = l1;
             }
-            l0 = l1;
+        };
+        const int nth = pack_threads(E);
+        std::vector<int> cut(nth + 1, L);
+        cut[0] = 0;
+        for (int t = 1; t < nth; ++t) {
+            int c = std::max(cut[t - 1], (int)((long long)L * t / nth));
+            while (c < L && c > 0 && lm_host[c] == lm_host[c - 1] && lm_eptr[c] != lm_eptr[c + 1]) ++c;  // next host boundary
+            cut[t] = c;
+        }
+        std::vector<GroupPart> parts(nth);
+        pack_parallel(nth, [&](int t) { if (cut[t] < cut[t + 1]) plan(cut[t], cut[t + 1], parts[t]); });
+        K.grouped_ok = true;
+        K.n_groups = 0; K.group_smem_max = 0;
+        int max_obs_slots = 0;
+        std::vector<size_t> oh(nth + 1, 0), os(nth + 1, 0), op(nth + 1, 0), ox(nth + 1, 0);
+        for (int t = 0; t < nth; ++t) {
+            const GroupPart &O = parts[t];
+            K.grouped_ok = K.grouped_ok && O.ok;
+            K.n_groups += O.n_groups; K.group_smem_max = std::max(K.group_smem_max, O.smem_max);
+            max_obs_slots = std::max(max_obs_slots, O.max_obs_slots);
+            oh[t + 1] = oh[t] + O.g_hdr.size(); os[t + 1] = os[t] + O.g_slot_pose.size();
+            op[t + 1] = op[t] + O.g_pairinfo.size(); ox[t + 1] = ox[t] + O.ell;
+        }
+        if (ox[nth] > 0x7fffffffULL || op[nth] > 0x7fffffffULL) K.grouped_ok = false;
+        K.g_hdr.clear(); K.g_slot_pose.clear(); K.g_pairinfo.clear(); K.ell_pjx.clear(); K.ell_pjy.clear(); K.ell_edge.clear();
+        if (K.grouped_ok) {
+            K.g_hdr.resize(oh[nth]); K.g_slot_pose.resize(os[nth]); K.g_pairinfo.resize(op[nth]);
+            K.ell_pjx.resize(ox[nth]); K.ell_pjy.resize(ox[nth]); K.ell_edge.resize(ox[nth]);  // uninitialised: pass 2 writes every entry
+            pack_parallel(nth, [&](int t) {
+                const GroupPart &O = parts[t];
+                std::copy(O.g_slot_pose.begin(), O.g_slot_pose.end(), K.g_slot_pose.begin() + os[t]);
+                std::copy(O.g_pairinfo.begin(), O.g_pairinfo.end(), K.g_pairinfo.begin() + op[t]);
+                std::vector<int> slot_of_pose(C, -1);
+                const double qnan = std::numeric_limits<double>::quiet_NaN();
+                for (size_t i = 0; i < O.g_hdr.size(); i += 8) {
+                    int *h = &K.g_hdr[oh[t] + i];
+                    for (int k = 0; k < 8; ++k) h[k] = O.g_hdr[i + k];
+                    h[4] += (int)ox[t]; h[5] += (int)op[t]; h[6] += (int)os[t];
+                    const int ns = h[1], la = h[2], nlm = h[3], lb = la + nlm;
+                    const size_t ell0 = (size_t)h[4];
+                    const int *slots = &K.g_slot_pose[h[6]];
+                    for (int sl = 0; sl < ns; ++sl) slot_of_pose[slots[sl]] = sl;
+                    double *ex = &K.ell_pjx[ell0], *ey = &K.ell_pjy[ell0];
+                    int *ee = &K.ell_edge[ell0];
+                    const size_t cnt_e = (size_t)(ns - 1) * nlm;
+                    if (!(h[7] & 1)) {  // ragged group: missing observations are NaN / -1
+                        for (size_t k = 0; k < cnt_e; ++k) { ex[k] = qnan; ey[k] = 0.0; ee[k] = -1; }
+                    }
+                    bool direct = (h[7] & 1) != 0;
+                    const int e0 = lm_eptr[la];
+                    for (int l = la; l < lb; ++l)
+                        for (int e = lm_eptr[l]; e < lm_eptr[l + 1]; ++e) {
+                            const int sl = slot_of_pose[e_pose_j[e]];
+                            const size_t idx = (size_t)(sl - 1) * nlm + (l - la);
+                            ex[idx] = pjx[e]; ey[idx] = pjy[e]; ee[idx] = e;
+                            // every landmark's edges stored in slot order, landmarks back to back: edge(l, s) = e0 + l (ns - 1) + (s - 1),
+                            // so the Schur kernel reads the group's H_lp rows as one slab (TMA bulk copy) without index loads
+                            if (e != e0 + (l - la) * (ns - 1) + (sl - 1)) direct = false;
+                        }
+                    if (direct) h[7] |= 2;
+                    for (int sl = 0; sl < ns; ++sl) slot_of_pose[slots[sl]] = -1;
+                }
+            });
         }
         if (K.n_groups == 0 || K.ext_free) K.grouped_ok = false;
         // one observer slot per warp, 4..10 warps (VIO_B200_GROUP_WARPS overrides; tuning knob)
@@ -512,6 +684,7 @@ inline int pack_graph(const vio_graph *g, int shard_rank, int shard_world, Packe
         K.group_threads = 32 * nwarp;
     }
 
+    ptm.mark("groups + ELL");
     K.C = C; K.NSB = NSB; K.NB = NB; K.P = P; K.L = L; K.Lglobal = Lg; K.E = E; K.storage = storage; K.nnzb = nnzb;
     K.s_count = s_count; K.batch = batch; K.Pper = Pper;
     K.pose_fixed.assign(C, 0); K.sb_fixed.assign(NSB, 0);
@@ -581,7 +754,7 @@ struct PackedMerge {
         m.n_groups = m.grouped_ok ? (int)Gb[B] : 0; m.group_threads = threads; m.group_smem_max = smem;
         if (m.grouped_ok) {
             m.g_hdr.resize(8 * (size_t)Gb[B]); m.g_slot_pose.resize(Sb[B]); m.g_pairinfo.resize(Pb[B]);
-            m.ell_pjx.resize(Xb[B]); m.ell_pjy.resize(Xb[B]); m.ell_edge.resize(Xb[B]);
+            m.ell_pjx.resize(Xb[B]); m.ell_pjy.resize(Xb[B]); m.ell_edge.resize(Xb[B]);  // every entry is written by fill()
         } else {
             m.g_hdr.clear(); m.g_slot_pose.clear(); m.g_pairinfo.clear(); m.ell_pjx.clear(); m.ell_pjy.clear(); m.ell_edge.clear();
         }
