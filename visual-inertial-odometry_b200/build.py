@@ -84,12 +84,13 @@ def build_backend(force=False):
                   "-L" + HERE, "-lvio_backend", "-lvio_b200", "-Wl,-rpath,$ORIGIN/../visual-inertial-odometry_b200"] + dyn)
     # this repository's own VertexPointXYZ / EdgeReprojectionXYZ driver (tests/xyz_ba_driver.cc): the test suite also
     # builds the same source against the unmodified reference backend and compares the two binaries
-    drv = os.path.join(ROOT, "tests", "xyz_ba_driver.cc")
-    exe = os.path.join(ROOT, "build", "xyz_ba_b200")
-    if os.path.exists(drv) and (force or _newer(exe, [out, drv])):
-        os.makedirs(os.path.dirname(exe), exist_ok=True)
-        _run(["g++", "-std=c++14", "-O2", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + eigen, drv, "-o", exe,
-              "-L" + HERE, "-lvio_backend", "-lvio_b200", "-Wl,-rpath,$ORIGIN/../visual-inertial-odometry_b200"] + dyn)
+    for src_name, exe_name in (("xyz_ba_driver.cc", "xyz_ba_b200"), ("frame_stream_driver.cc", "frame_stream_b200")):
+        drv = os.path.join(ROOT, "tests", src_name)
+        exe = os.path.join(ROOT, "build", exe_name)
+        if os.path.exists(drv) and (force or _newer(exe, [out, drv])):
+            os.makedirs(os.path.dirname(exe), exist_ok=True)
+            _run(["g++", "-std=c++14", "-O2", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + eigen, drv, "-o", exe,
+                  "-L" + HERE, "-lvio_backend", "-lvio_b200", "-Wl,-rpath,$ORIGIN/../visual-inertial-odometry_b200"] + dyn)
     return out
 
 

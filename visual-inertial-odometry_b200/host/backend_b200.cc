@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cmath>
 #include <iostream>
+#include <mutex>
 #include <stdexcept>
 
 #include <Eigen/Dense>
@@ -138,10 +139,50 @@ EdgeImuB200::EdgeImuB200(const ImuPreintegrationB200 &pre)
 void EdgeImuB200::ComputeResidual() { device_only("EdgeImu::ComputeResidual"); }
 void EdgeImuB200::ComputeJacobians() { device_only("EdgeImu::ComputeJacobians"); }
 
+// ---- device handles outlive Problem objects ---------------------------------------------------------------------------
+// The VINS estimator builds a NEW Problem for every frame (A17/src/estimator.cpp:902-1037 problemSolve, :693-829
+// MargOldFrame), solves it once and drops it.  A C-ABI handle owns a stream, events, pinned staging and the device
+// buffers of the packed graph; creating one costs more than solving a window.  Handles therefore go back to a small
+// per-device pool when their Problem dies and the next Problem's vio_set_graph reuses the buffers (same window size:
+// no allocation at all).  SURVEY 8(f-2): "reuse previous window's device buffers".
+namespace {
+struct HandlePool {
+    std::mutex mu;
+    std::vector<std::pair<int, vio_problem *>> idle;
+};
+HandlePool &handle_pool() {
+    static HandlePool *p = new HandlePool();  // never destroyed: the CUDA context may be gone before static destructors run
+    return *p;
+}
+vio_problem *acquire_handle(int device) {
+    {
+        HandlePool &hp = handle_pool();
+        std::lock_guard<std::mutex> lk(hp.mu);
+        for (size_t i = 0; i < hp.idle.size(); ++i)
+            if (hp.idle[i].first == device) {
+                vio_problem *h = hp.idle[i].second;
+                hp.idle.erase(hp.idle.begin() + i);
+                return h;
+            }
+    }
+    vio_problem *h = nullptr;
+    if (vio_create(device, nullptr, &h) != VIO_OK) return nullptr;
+    return h;
+}
+void release_handle(int device, vio_problem *h) {
+    HandlePool &hp = handle_pool();
+    {
+        std::lock_guard<std::mutex> lk(hp.mu);
+        if (hp.idle.size() < 4) { hp.idle.emplace_back(device, h); return; }
+    }
+    vio_destroy(h);
+}
+}  // namespace
+
 // ---- Problem ------------------------------------------------------------------------------------------------------
 Problem::Problem(ProblemType problemType, bool v17_flavour) : problemType_(problemType), v17_(v17_flavour) {}
 Problem::~Problem() {
-    if (handle_) vio_destroy(handle_);
+    if (handle_) release_handle(device_, handle_);
     if (v17_) global_vertex_id = 0;  // the v17 destructor does this (vins-mono/src/backend/problem.cc:38-41)
 }
 
@@ -408,8 +449,8 @@ bool Problem::Solve(int iterations) {
     auto &pose = K.pose; auto &sb = K.sb; auto &invd = K.invd;
     auto &pose_v = K.pose_v; auto &sb_v = K.sb_v; auto &lm_v = K.lm_v;
     if (!handle_) {
-        int rc = vio_create(device_, nullptr, &handle_);
-        if (rc != VIO_OK) throw std::runtime_error("vio_b200: no CUDA device (the GPU backend has no CPU fallback)");
+        handle_ = acquire_handle(device_);
+        if (!handle_) throw std::runtime_error("vio_b200: no CUDA device (the GPU backend has no CPU fallback)");
     }
     int rc = vio_set_graph(handle_, &g);
     if (rc != VIO_OK) { std::cerr << "vio_b200: " << vio_last_error(handle_) << std::endl; return false; }
@@ -470,8 +511,8 @@ bool Problem::Solve(int iterations) {
 bool Problem::SolveGenericB200(int iterations) {
     const auto t0 = std::chrono::steady_clock::now();
     if (!handle_) {
-        int rc = vio_create(device_, nullptr, &handle_);
-        if (rc != VIO_OK) throw std::runtime_error("vio_b200: no CUDA device (the GPU backend has no CPU fallback)");
+        handle_ = acquire_handle(device_);
+        if (!handle_) throw std::runtime_error("vio_b200: no CUDA device (the GPU backend has no CPU fallback)");
     }
     // ordering: vertices in id order at consecutive offsets (a single vertex in every reference driver)
     int n = 0;
@@ -613,8 +654,8 @@ bool Problem::Marginalize(const std::vector<std::shared_ptr<Vertex>> margVertexs
     if (!PackGraphB200(K)) return false;
     if ((int)ordering_poses_ != pose_dim) { std::cerr << "vio_b200: pose_dim does not match the pose-class dimension" << std::endl; return false; }
     if (!handle_) {
-        int rc = vio_create(device_, nullptr, &handle_);
-        if (rc != VIO_OK) throw std::runtime_error("vio_b200: no CUDA device (the GPU backend has no CPU fallback)");
+        handle_ = acquire_handle(device_);
+        if (!handle_) throw std::runtime_error("vio_b200: no CUDA device (the GPU backend has no CPU fallback)");
     }
     int rc = vio_set_graph(handle_, &K.g);
     if (rc != VIO_OK) { std::cerr << "vio_b200: " << vio_last_error(handle_) << std::endl; return false; }
