@@ -90,3 +90,55 @@ def test_bal_problem_solved_on_device():
     assert st.iterations == ref["iterations"]
     assert abs(st.chi2_final - ref["chi2_final"]) <= 1e-6 * ref["chi2_final"]
     assert np.abs(pts - ref["point_xyz"]).max() <= 1e-6 * np.abs(ref["point_xyz"]).max()
+
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_bal_fixture_against_the_reference_reader_and_camera_model():
+    """tests/golden/bal_fixture.txt through bal.py against the reference side (tests/golden/bal_fixture_ref.npz, written
+    by make_golden_bal.py from oracle/_ref/bal_ref = the reference's own BALProblem reader, bal.cpp, unmodified, plus its
+    camera model restated from bal_g2o.cpp:25-42, 94-109 with the reference's Sophus): the same indices, observations,
+    cameras and points are parsed, and the predicted pixel of every observation agrees to 1e-9 px."""
+    vio = importlib.import_module("visual-inertial-odometry_b200")
+    g = np.load(os.path.join(GOLD, "bal_fixture_ref.npz"))
+    b = vio.bal.read_bal(os.path.join(GOLD, "bal_fixture.txt"))
+    assert np.array_equal(b["cam_index"], g["cam_index"]) and np.array_equal(b["pt_index"], g["pt_index"])
+    for k in ("obs", "cameras", "points"):
+        assert np.array_equal(b[k], g[k]), k  # both sides parse the same decimal strings
+    pred = vio.bal.bal_project(b)
+    assert np.abs(pred - g["pred"]).max() <= 1e-9
+    rms_ref = np.sqrt(((g["pred"] - g["obs"]) ** 2).sum(1).mean())
+    assert abs(vio.bal.bal_reprojection_error(b) - rms_ref) <= 1e-9
+    # the scene mapping keeps that residual: chi2 of the backend's factor = sum |undistorted residual|^2
+    from tests import oraclelib as orc
+    s = vio.bal.bal_to_scene(b)
+    f = b["cameras"][b["cam_index"], 6]
+    rms_norm = np.sqrt(orc.chi2(s, vio.capi.LM_V15) / len(f))
+    assert abs(rms_norm * f.mean() - rms_ref) < 0.05 * rms_ref
+
+
+@pytest.mark.gpu
+def test_bal_fixture_solved_on_device():
+    """the committed BAL fixture on the device: pixel RMS (the reference-side camera model) goes from 5 px to the
+    0.3 px noise level; estimates agree with the CPU oracle"""
+    vio = importlib.import_module("visual-inertial-odometry_b200")
+    from tests import oraclelib as orc
+    b = vio.bal.read_bal(os.path.join(GOLD, "bal_fixture.txt"))
+    rms0 = vio.bal.bal_reprojection_error(b)
+    s = vio.bal.bal_to_scene(b, fix_first=2)
+    opts = vio.make_opts(flavour=vio.capi.LM_V17)
+    p = vio.Problem()
+    p.set_graph(s)
+    st = p.solve(15, opts)
+    pose, _, _ = p.get_vertices()
+    pts = p.get_points()
+    out = vio.bal.scene_to_bal(s, pts, pose)
+    out["cameras"][:, 6:] = b["cameras"][:, 6:]
+    out["obs"] = b["obs"]
+    rms1 = vio.bal.bal_reprojection_error(out)
+    assert rms0 > 4.0 and rms1 < 0.5, (rms0, rms1)
+    ref = orc.solve(s, 15, opts)
+    assert st.iterations == ref["iterations"]
+    assert abs(st.chi2_final - ref["chi2_final"]) <= 1e-6 * ref["chi2_final"]
+    assert np.abs(pts - ref["point_xyz"]).max() <= 1e-6 * np.abs(ref["point_xyz"]).max()

@@ -144,6 +144,19 @@ def scene_to_bal(scene, points, poses, f=500.0, k1=0.0, k2=0.0):
     return dict(cam_index=scene.rx_pose.copy(), pt_index=scene.rx_point.copy(), obs=pix, cameras=cams, points=points.copy())
 
 
+def bal_project(bal):
+    """predicted pixel of every observation with the file's own camera model (VertexPoseAndIntrinsics::project,
+    01-bal-g2o/src/bal_g2o.cpp:94-109) -> [n_obs, 2]"""
+    cams, pts = bal["cameras"], bal["points"]
+    out = np.zeros((len(bal["obs"]), 2))
+    for i, (c, k) in enumerate(zip(bal["cam_index"], bal["pt_index"])):
+        P = _rodrigues(cams[c, :3]) @ pts[k] + cams[c, 3:6]
+        p = -P[:2] / P[2]
+        r2 = p @ p
+        out[i] = cams[c, 6] * (1 + cams[c, 7] * r2 + cams[c, 8] * r2 * r2) * p
+    return out
+
+
 def bal_reprojection_error(bal):
     """RMS BAL residual in pixels with the file's own camera model (independent of the scene conversion)"""
     cams, pts = bal["cameras"], bal["points"]
