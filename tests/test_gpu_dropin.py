@@ -120,8 +120,9 @@ def test_frame_stream_driver_matches_reference_backend():
     for f in range(5):
         assert po[f].shape == pr[f].shape
         assert np.abs(po[f] - pr[f]).max() <= 2e-3  # v15 flavour: inexact reference PCG
-    # 6 printed decimals; the final RED.F64 flush into S is order-dependent at the 1e-16 level
-    assert np.abs(po[2] - po[0]).max() <= 2e-6 and np.abs(po[3] - po[1]).max() <= 2e-6
+    # the final RED.F64 flush into S is order-dependent at the 1e-16 level and the v15 flavour's inexact PCG (stopped at
+    # |r| <= 1e-6 |b|) turns that into ~1e-5 run-to-run differences; a leak between Problems would be gross
+    assert np.abs(po[2] - po[0]).max() <= 1e-4 and np.abs(po[3] - po[1]).max() <= 1e-4
     ms = [float(x) for x in re.findall(r"landmarks\): ([0-9.]+) ms", o.stderr)]
     assert len(ms) == 5
     print("frame wall times (ms):", ms)

@@ -119,6 +119,11 @@ struct vio_problem {
     DBuf<uint8_t> pose_fixed, sb_fixed;
     DBuf<int> pose_off, sb_off, pose_blk;
     DBuf<int> lm_host, lm_eptr, e_pose_j;
+    // caller order <-> packed order of the inverse depths on the device (vio_set_vertices / vio_get_vertices): unsharded
+    // handles with every landmark packed; lm_identity: the caller's landmarks were already host-sorted
+    DBuf<int> d_lm_global;
+    DBuf<double> lm_stage;
+    bool lm_perm_on_device = false, lm_identity = false;
     DBuf<uint8_t> lm_fixed, pt_fixed;  // fixed landmark-class vertices; has_*_fixed says whether the view points at them
     bool has_lm_fixed = false, has_pt_fixed = false;
     DBuf<double> lm_pix, lm_piy, lm_piz, e_pjx, e_pjy;
@@ -1266,6 +1271,14 @@ static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &
     CK(upload(p->pose_blk, K.pose_blk.data(), (size_t)C, s));
     CK(p->poseRT.alloc(16 * (size_t)C));
     CK(upload(p->lm_host, K.lm_host.data(), (size_t)L, s)); CK(upload(p->lm_eptr, K.lm_eptr.data(), (size_t)L + 1, s));
+    p->lm_perm_on_device = L > 0 && L == K.Lglobal && p->shard_world == 1;
+    p->lm_identity = false;
+    if (p->lm_perm_on_device) {
+        bool ident = true;
+        for (int l = 0; l < L && ident; ++l) ident = K.lm_global[l] == l;
+        p->lm_identity = ident;
+        if (!ident) { CK(upload(p->d_lm_global, K.lm_global.data(), (size_t)L, s)); CK(p->lm_stage.alloc((size_t)K.Lglobal)); }
+    }
     p->has_lm_fixed = !K.lm_fixed.empty() && L > 0;
     if (p->has_lm_fixed) CK(upload(p->lm_fixed, K.lm_fixed.data(), (size_t)L, s));
     p->has_pt_fixed = !K.pt_fixed.empty() && K.Lx > 0;
@@ -1436,16 +1449,37 @@ int vio_get_prior(vio_problem *p, double *b, double *err) {
     return VIO_OK;
 }
 
+__global__ void k_gather_lm(const double *__restrict__ src, const int *__restrict__ idx, int n, double *__restrict__ dst) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < n) dst[l] = src[idx[l]];
+}
+__global__ void k_scatter_lm(const double *__restrict__ src, const int *__restrict__ idx, int n, double *__restrict__ dst) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < n) dst[idx[l]] = src[l];
+}
+
 int vio_set_vertices(vio_problem *p, const double *pose, const double *sb, const double *invd) {
     if (!p || !p->has_graph) return VIO_ERR_STATE;
     CK(cudaSetDevice(p->device));
     if (pose) CK(cudaMemcpyAsync(p->pose.p, pose, 7 * (size_t)p->C * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     if (sb && p->NSB) CK(cudaMemcpyAsync(p->sb.p, sb, 9 * (size_t)p->NSB * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     if (invd && p->L) {
-        std::vector<double> loc(p->L);
-        for (int l = 0; l < p->L; ++l) loc[l] = invd[p->lm_global[l]];
-        CK(cudaMemcpyAsync(p->invdep.p, loc.data(), (size_t)p->L * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-        CK(cudaStreamSynchronize(p->stream));
+        if (p->lm_perm_on_device) {
+            // caller order -> packed (host-sorted) order on the device: one DMA from the caller's buffer, one gather kernel
+            // (no host-side permutation pass, no pageable bounce buffer)
+            if (p->lm_identity) {
+                CK(cudaMemcpyAsync(p->invdep.p, invd, (size_t)p->L * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+            } else {
+                CK(cudaMemcpyAsync(p->lm_stage.p, invd, (size_t)p->Lglobal * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+                k_gather_lm<<<grid_for(p->L, 256), 256, 0, p->stream>>>(p->lm_stage.p, p->d_lm_global.p, p->L, p->invdep.p);
+                p->launches++;
+            }
+        } else {
+            std::vector<double> loc(p->L);
+            for (int l = 0; l < p->L; ++l) loc[l] = invd[p->lm_global[l]];
+            CK(cudaMemcpyAsync(p->invdep.p, loc.data(), (size_t)p->L * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+            CK(cudaStreamSynchronize(p->stream));
+        }
     }
     CK(cudaStreamSynchronize(p->stream));
     p->linearized = false;
@@ -1461,8 +1495,18 @@ int vio_get_vertices(vio_problem *p, double *pose, double *sb, double *invd) {
     if (sb && p->NSB) CK(cudaMemcpyAsync(sb, p->sb.p, 9 * (size_t)p->NSB * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     std::vector<double> loc;
     if (invd && p->L) {
-        loc.resize(p->L);
-        CK(cudaMemcpyAsync(loc.data(), p->invdep.p, (size_t)p->L * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        if (p->lm_perm_on_device) {  // unsharded: every landmark is ours, the whole array is written
+            if (p->lm_identity) {
+                CK(cudaMemcpyAsync(invd, p->invdep.p, (size_t)p->L * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+            } else {
+                k_scatter_lm<<<grid_for(p->L, 256), 256, 0, p->stream>>>(p->invdep.p, p->d_lm_global.p, p->L, p->lm_stage.p);
+                p->launches++;
+                CK(cudaMemcpyAsync(invd, p->lm_stage.p, (size_t)p->Lglobal * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+            }
+        } else {
+            loc.resize(p->L);
+            CK(cudaMemcpyAsync(loc.data(), p->invdep.p, (size_t)p->L * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        }
     }
     CK(cudaStreamSynchronize(p->stream));
     // a shard only writes the landmarks it owns
