@@ -124,6 +124,7 @@ struct vio_problem {
     DBuf<int> d_lm_global;
     DBuf<double> lm_stage;
     bool lm_perm_on_device = false, lm_identity = false;
+    bool s_mirrored = true;  // block-sparse S: lower triangle valid (see ensure_mirrored)
     DBuf<uint8_t> lm_fixed, pt_fixed;  // fixed landmark-class vertices; has_*_fixed says whether the view points at them
     bool has_lm_fixed = false, has_pt_fixed = false;
     DBuf<double> lm_pix, lm_piy, lm_piz, e_pjx, e_pjy;
@@ -526,11 +527,17 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
     if (p->storage == VIO_STORAGE_DENSE) {
         dim3 b(32, 8), g((p->Pper + 31) / 32, (p->Pper + 7) / 8, p->batch);
         k_mirror_dense<<<g, b, 0, p->stream>>>(p->sys.p, p->Pper);
+        p->s_mirrored = true;
+        p->launches++;
+    } else if (with_schur && !p->env_no_bcr && resolve_solver(p, o) == VIO_SOLVER_BCR) {
+        p->s_mirrored = false;  // the cyclic reduction's loader reads the upper triangle only: no mirror pass (ensure_mirrored)
     } else {
         k_mirror_bsr<<<grid_for(p->nnzb * 36, 256), 256, 0, p->stream>>>(v);
+        p->s_mirrored = true;
+        p->launches++;
     }
     k_finalize_b<<<grid_for(p->P, 128), 128, 0, p->stream>>>(v);
-    p->launches += 2;
+    p->launches++;
     CK(cudaGetLastError());
     p->linearized = with_schur;
     return VIO_OK;
@@ -615,9 +622,18 @@ int do_maxdiag(vio_problem *p, double *out) {
 }
 
 // SolveLinearSystem: reduced solve + back-substitution.  Leaves scale/|dx|^2 partial sums in scal[4..7].
+// the lower triangle of a block-sparse S is filled on demand (solvers other than the cyclic reduction, debug taps)
+static void ensure_mirrored(vio_problem *p) {
+    if (p->storage != VIO_STORAGE_BSR || p->s_mirrored) return;
+    k_mirror_bsr<<<grid_for(p->nnzb * 36, 256), 256, 0, p->stream>>>(p->view);
+    p->s_mirrored = true;
+    p->launches++;
+}
+
 int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *pcg_iters) {
     const DevView &v = p->view;
     const int solver = resolve_solver(p, o);
+    if (solver != VIO_SOLVER_BCR) ensure_mirrored(p);
     const int P = p->P;
     if (pcg_iters) *pcg_iters = 0;
     if (solver == VIO_SOLVER_DENSE_CHOL) {
@@ -893,7 +909,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             CK(cudaMemsetAsync(p->d_lflags.p + nL, 0, 4 * sizeof(unsigned), p->stream));
             CK(cudaMemsetAsync(p->d_iflags.p + nI, 0, 4 * sizeof(unsigned), p->stream));
             CK(cudaMemsetAsync(p->info.p + 2, 0, sizeof(int), p->stream));
-            k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->d_dst.p, p->nnzb, v.bS, p->d_blk_lnode.p, p->bcr_blk_loc.p,
+            k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->d_dst.p, v.bsr_tr, p->nnzb, v.bS, p->d_blk_lnode.p, p->bcr_blk_loc.p,
                                                              p->d_node_size.p, p->NB, m + 1, M, Y.ld, lambda, p->d_pool.p, p->d_bv.p);
             const unsigned epoch = ++p->bcr_epoch;
             BcrView lv;
@@ -934,7 +950,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         CK(cudaMemsetAsync(p->bcr_bv.p, 0, (size_t)Y.n * Y.M * sizeof(double), p->stream));
         CK(cudaMemsetAsync(p->bcr_flags.p + Y.items.size(), 0, sizeof(unsigned), p->stream));
         CK(cudaMemsetAsync(p->info.p + 2, 0, sizeof(int), p->stream));
-        k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->bcr_dst.p, p->nnzb, v.bS, p->bcr_blk_node.p, p->bcr_blk_loc.p,
+        k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->bcr_dst.p, v.bsr_tr, p->nnzb, v.bS, p->bcr_blk_node.p, p->bcr_blk_loc.p,
                                                          p->bcr_node_size.p, p->NB, Y.n, Y.M, Y.ld, lambda, p->bcr_pool.p, p->bcr_bv.p);
         BcrView bv;
         bv.n = Y.n; bv.M = Y.M; bv.ld = Y.ld; bv.nbuf = p->bcr_nbuf; bv.n_items = (int)Y.items.size(); bv.items = p->bcr_items.p; bv.pool = p->bcr_pool.p;
@@ -1803,6 +1819,7 @@ int vio_get_kernel_ms(vio_problem *p, double *ms, int64_t *launches) {
 int vio_get_schur(vio_problem *p, double *S, double *bS) {
     if (!p || !p->has_graph || !p->linearized) return VIO_ERR_STATE;
     CK(cudaSetDevice(p->device));
+    ensure_mirrored(p);
     const int P = p->P;
     if (S) {
         if (p->storage == VIO_STORAGE_DENSE) {
@@ -1830,6 +1847,7 @@ int vio_get_schur_bsr(vio_problem *p, int32_t *rowptr, int32_t *col, double *val
     CK(cudaSetDevice(p->device));
     if (rowptr) memcpy(rowptr, p->h_rowptr.data(), p->h_rowptr.size() * sizeof(int));
     if (col) memcpy(col, p->h_col.data(), p->h_col.size() * sizeof(int));
+    ensure_mirrored(p);
     if (p->dist_on) {
         // un-reduced linearisation: the tap returns the SUM over the ranks (a collective call: every rank must make it)
         DBuf<double> tmp;

@@ -30,7 +30,10 @@ struct BcrView {
 };
 
 // ---- loader ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bcr_load(const double *__restrict__ val, const long long *__restrict__ dst, long long nnzb,
+// Only the upper block triangle of S (and the upper element triangle of its diagonal blocks) has to be valid: a lower
+// block is read as the transpose of its partner `tr` (BSR blocks are stored row-major, so tr[k] < k marks a lower block) -
+// the k_mirror_bsr pass over the 60 MB of S is not needed in front of this solver.
+__global__ void __launch_bounds__(256) k_bcr_load(const double *__restrict__ val, const long long *__restrict__ dst, const int *__restrict__ tr, long long nnzb,
                                                   const double *__restrict__ b, const int *__restrict__ blk_node,
                                                   const int *__restrict__ blk_loc, const int *__restrict__ node_size, int nb, int n, int M, int LD,
                                                   double lambda, double *__restrict__ pool, double *__restrict__ bv) {
@@ -41,7 +44,9 @@ __global__ void __launch_bounds__(256) k_bcr_load(const double *__restrict__ val
         const long long d = dst[k];
         if (d < 0) continue;
         const bool dg = (d & BCR_DST_DIAG) != 0;
-        pool[(d & ~BCR_DST_DIAG) + (long long)(e / 6) * LD + e % 6] = val[t] + ((dg && e % 7 == 0) ? lambda : 0.0);
+        const int r = e / 6, c = e - 6 * r, kt = tr[k];
+        const double x = (kt < k || (kt == k && r > c)) ? val[36 * (long long)kt + 6 * c + r] : val[t];
+        pool[(d & ~BCR_DST_DIAG) + (long long)r * LD + c] = x + ((dg && r == c) ? lambda : 0.0);
     }
     for (long long t = t0; t < (long long)n * M; t += stride) {  // identity padding of ragged nodes
         const int a = (int)(t / M), q = (int)(t % M);
@@ -73,7 +78,10 @@ __global__ void __launch_bounds__(256) k_bcr_finish(const double *__restrict__ x
     double A[36], y[6];
     const double *d = val + 36 * (size_t)diag[i];
 #pragma unroll
-    for (int e = 0; e < 36; ++e) A[e] = d[e] + (e % 7 == 0 ? lambda : 0.0);
+    for (int e = 0; e < 36; ++e) {  // only the upper element triangle of a diagonal block needs to be valid (see k_bcr_load)
+        const int r = e / 6, c = e % 6;
+        A[e] = (r > c ? d[6 * c + r] : d[e]) + (r == c ? lambda : 0.0);
+    }
 #pragma unroll
     for (int c = 0; c < 6; ++c) y[c] = b[6 * (size_t)i + c];
 #pragma unroll
