@@ -883,3 +883,44 @@ def test_fixed_landmarks_vs_golden(vio, kind):
         finally:
             os.environ.pop("VIO_B200_LINEARIZE")
         assert rel_max(H3, H) <= 1e-12 and rel_l2(b3, b) <= 1e-12
+
+
+@pytest.mark.parametrize("scene_name", ["window", "ring_bcr", "monoba"])
+def test_graph_replay_matches_plain_launches(vio, scene_name, monkeypatch):
+    """vio_solve replays the v17 LM body (reduced solve, back-substitution, UpdateStates, chi2; MakeHessian + Schur) as two
+    CUDA graphs from the second trial step on.  Same kernels, same order, lambda handed over through device memory: traces
+    and states must be those of plain launches to 1e-9 (VIO_B200_NO_GRAPH), on a repeated solve of the same handle too."""
+    capi = vio.capi
+    if scene_name == "window":
+        s = _window(vio)
+    elif scene_name == "ring_bcr":
+        s = vio.scenes.ring(n_cam=333, n_landmark=6000, k_obs=5, seed=4)
+        s.storage = capi.STORAGE_BSR
+    else:
+        s = vio.scenes.monoba(20, 300, with_ext=True)
+    opts = vio.make_opts(flavour=capi.LM_V17)
+    out = []
+    for no_graph in (True, False):
+        if no_graph:
+            monkeypatch.setenv("VIO_B200_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("VIO_B200_NO_GRAPH", raising=False)
+        p = vio.Problem()
+        p.set_graph(s)
+        runs = []
+        for rep in range(2):
+            p.set_vertices(s.pose, s.speedbias if s.speedbias is not None and len(s.speedbias) else None, s.inv_depth)
+            if scene_name == "window":
+                p.set_graph(s)  # the prior is updated by a solve: start both repetitions from the same prior
+            st = p.solve(8, opts)
+            pose, sb, invd = p.get_vertices()
+            runs.append((st.iterations, st.trial_steps, np.array(st.chi2_trace[:st.n_trace]), np.array(st.lambda_trace[:st.n_trace]),
+                         pose.copy(), invd.copy()))
+        out.append(runs)
+    for rep in range(2):
+        a, b = out[0][rep], out[1][rep]
+        assert a[0] == b[0] and a[1] == b[1]
+        # not bitwise: the RED.F64 flushes into S land in a different order from run to run
+        assert np.allclose(a[2], b[2], rtol=1e-9, atol=0) and np.allclose(a[3], b[3], rtol=1e-9, atol=0)
+        assert np.abs(a[4] - b[4]).max() <= 1e-9 * np.abs(a[4]).max() and np.abs(a[5] - b[5]).max() <= 1e-9 * np.abs(a[5]).max()
+    assert out[1][0][1] >= 2  # more than one trial step: the graph path did run

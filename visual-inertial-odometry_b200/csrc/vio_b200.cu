@@ -125,6 +125,17 @@ struct vio_problem {
     DBuf<double> lm_stage;
     bool lm_perm_on_device = false, lm_identity = false;
     bool s_mirrored = true;  // block-sparse S: lower triangle valid (see ensure_mirrored)
+    // ---- CUDA-graph replay of the v17 LM body (vio_solve): G_trial = [lambda H2D, reduced solve, back-substitution, LM scalars,
+    // UpdateStates, chi2, scalar read-back], G_lin = [MakeHessian + Schur].  Built by stream capture on the second iteration of
+    // a solve, kept until the graph / prior / options change.  Kernels read lambda through lam_dev while a graph is captured.
+    cudaGraphExec_t g_trial = nullptr, g_lin = nullptr;
+    int g_trial_launches = 0, g_lin_launches = 0, g_key_solver = -1, g_key_flags = -1;
+    cudaEvent_t gev_sol_a = nullptr, gev_sol_b = nullptr, gev_lin_a = nullptr, gev_lin_b = nullptr;
+    bool graph_disabled = false, capturing = false, env_no_graph = false;
+    DBuf<double> d_lambda;
+    const double *lam_dev = nullptr;
+    double g_sol_ms = 0.0, g_lin_ms = 0.0;
+    long long g_sol_n = 0, g_lin_n = 0;
     DBuf<uint8_t> lm_fixed, pt_fixed;  // fixed landmark-class vertices; has_*_fixed says whether the view points at them
     bool has_lm_fixed = false, has_pt_fixed = false;
     DBuf<double> lm_pix, lm_piy, lm_piz, e_pjx, e_pjy;
@@ -329,6 +340,47 @@ vio_lm_opts default_opts() {
 }
 
 // in-place sum over the ranks of `count` doubles at device pointer ptr, ordered on the handle's stream
+// CUDA-graph replay of the LM body (see vio_solve): dropped whenever the graph, the prior or the buffers change
+void graphs_drop(vio_problem *p) {
+    if (p->g_trial) { cudaGraphExecDestroy(p->g_trial); p->g_trial = nullptr; }
+    if (p->g_lin) { cudaGraphExecDestroy(p->g_lin); p->g_lin = nullptr; }
+    p->g_key_solver = -1; p->g_key_flags = -1;
+}
+// Stream-captures body() into an executable graph.  Nothing runs during the capture; on any failure the handle falls back to
+// plain launches for good (graph_disabled) and the caller executes the step the ordinary way.
+template <class F>
+bool graph_capture(vio_problem *p, cudaGraphExec_t *out, int *n_launches, F &&body) {
+    const auto l0 = p->launches;
+    if (cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        (void)cudaGetLastError();
+        p->graph_disabled = true;
+        return false;
+    }
+    p->capturing = true; p->lam_dev = p->d_lambda.p;
+    const int rc = body();
+    p->capturing = false; p->lam_dev = nullptr;
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(p->stream, &g);
+    *n_launches = (int)(p->launches - l0);
+    p->launches = l0;
+    cudaGraphExec_t ex = nullptr;
+    bool ok = rc == VIO_OK && e == cudaSuccess && g != nullptr;
+    if (ok) ok = cudaGraphInstantiate(&ex, g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+    if (!ok) {
+        (void)cudaGetLastError();
+        p->graph_disabled = true;
+        return false;
+    }
+    *out = ex;
+    return true;
+}
+bool graph_mode_ok(vio_problem *p, const vio_lm_opts &o, int solver) {
+    if (p->graph_disabled || p->env_no_graph || p->env_profile || o.flavour != VIO_LM_V17 || p->stream == nullptr) return false;
+    if (p->shard_world != 1 || p->ext_free || p->batch != 1) return false;
+    if (solver == VIO_SOLVER_BCR) return true;
+    return solver == VIO_SOLVER_DENSE_CHOL && p->storage == VIO_STORAGE_DENSE && p->P <= DCH_MAX_P && !p->env_chol_legacy;
+}
 bool is_sharded(const vio_problem *p) { return p->shard_world > 1 && (p->nccl_comm || p->allreduce); }
 int dist_sum(vio_problem *p, double *ptr, int64_t count) {
     if (p->nccl_comm) {
@@ -466,8 +518,9 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
     CK(cudaMemsetAsync(p->sys.p, 0, sys_n * sizeof(double), p->stream));
     { const int rc_pp = do_pose_prep(p); if (rc_pp) return rc_pp; }
     EvPair *ev = nullptr;
-    if (p->ev_lin_used < p->ev_lin.size()) ev = &p->ev_lin[p->ev_lin_used++];
+    if (!p->capturing && p->ev_lin_used < p->ev_lin.size()) ev = &p->ev_lin[p->ev_lin_used++];
     if (ev) CK(cudaEventRecord(ev->a, p->stream));
+    if (p->capturing) CK(cudaEventRecordWithFlags(p->gev_lin_a, p->stream, cudaEventRecordExternal));
     if (p->L > 0 && p->use_grouped) {
         GroupView gv;
         gv.n_groups = p->n_groups; gv.ld = p->storage == VIO_STORAGE_DENSE ? p->Pper : 6;
@@ -500,6 +553,7 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
         p->launches++;
     }
     if (ev) CK(cudaEventRecord(ev->b, p->stream));
+    if (p->capturing) CK(cudaEventRecordWithFlags(p->gev_lin_b, p->stream, cudaEventRecordExternal));
     // pose-only factors are counted once: the SE3 priors this rank kept (the packer's se3_keep: all of them on rank 0, or
     // those of the rank's own cameras with node-range shards), IMU factors and the dense prior on rank 0
     if (p->n_se3 > 0) {
@@ -544,7 +598,8 @@ int do_linearize(vio_problem *p, const vio_lm_opts &o, bool with_schur) {
 }
 
 // chi2 at the current state -> host double (synchronises)
-int do_chi2(vio_problem *p, const vio_lm_opts &o, double *out) {
+// chi2 at the current state: kernels + the copy of its two partial sums into h_scal[0..1] (no synchronisation)
+int do_chi2_enqueue(vio_problem *p, const vio_lm_opts &o) {
     const DevView &v = p->view;
     { const int rc_pp = do_pose_prep(p); if (rc_pp) return rc_pp; }
     double *acc = p->scal.p + 0;
@@ -582,6 +637,10 @@ int do_chi2(vio_problem *p, const vio_lm_opts &o, double *out) {
         if (rc) return rc;
     }
     CK(cudaMemcpyAsync(p->h_scal, p->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    return VIO_OK;
+}
+int do_chi2(vio_problem *p, const vio_lm_opts &o, double *out) {
+    { const int rc = do_chi2_enqueue(p, o); if (rc) return rc; }
     CK(cudaStreamSynchronize(p->stream));
     double chi = p->h_scal[0] + p->h_scal[1];
     if (o.flavour == VIO_LM_V17) chi *= 0.5;
@@ -642,7 +701,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         if (P <= DCH_MAX_P && !p->env_chol_legacy) {
             // blocked (panels of 4, look-ahead, DMMA trailing updates): ~10x fewer barriers than the column-by-column kernel
             CK(RAISE_SMEM(k_dense_chol_blocked));
-            k_dense_chol_blocked<<<1, DCH_THREADS, dch_smem_bytes(P), p->stream>>>(v.S, v.bS, lambda, P, v.dxp, p->info.p);
+            k_dense_chol_blocked<<<1, DCH_THREADS, dch_smem_bytes(P), p->stream>>>(v.S, v.bS, lambda, P, v.dxp, p->info.p, p->lam_dev);
         } else if (tri_bytes <= 220 * 1024) {
             if (!p->chol_smem_set) {
                 CK(RAISE_SMEM(k_dense_chol_smem));
@@ -895,8 +954,9 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                         BCR_MAX_M / 6);
         const BcrPlan &Y = p->bcr;
         const size_t MM = (size_t)Y.M * Y.ld;
-        EvPair *evp = p->ev_pcg_used < p->ev_pcg.size() ? &p->ev_pcg[p->ev_pcg_used++] : nullptr;
+        EvPair *evp = (!p->capturing && p->ev_pcg_used < p->ev_pcg.size()) ? &p->ev_pcg[p->ev_pcg_used++] : nullptr;
         if (evp) CK(cudaEventRecord(evp->a, p->stream));
+        if (p->capturing) CK(cudaEventRecordWithFlags(p->gev_sol_a, p->stream, cudaEventRecordExternal));
         if (dist_prepare(p)) {
             // ---- multi-GPU: this rank's share of S covers its own nodes and the next rank's interface node
             const BcrDistPlan &D = p->dbcr;
@@ -910,7 +970,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             CK(cudaMemsetAsync(p->d_iflags.p + nI, 0, 4 * sizeof(unsigned), p->stream));
             CK(cudaMemsetAsync(p->info.p + 2, 0, sizeof(int), p->stream));
             k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->d_dst.p, v.bsr_tr, p->nnzb, v.bS, p->d_blk_lnode.p, p->bcr_blk_loc.p,
-                                                             p->d_node_size.p, p->NB, m + 1, M, Y.ld, lambda, p->d_pool.p, p->d_bv.p);
+                                                             p->d_node_size.p, p->NB, m + 1, M, Y.ld, lambda, p->d_pool.p, p->d_bv.p, p->lam_dev);
             const unsigned epoch = ++p->bcr_epoch;
             BcrView lv;
             lv.n = m + 1; lv.M = M; lv.ld = Y.ld; lv.nbuf = p->bcr_nbuf; lv.items = p->d_litems.p; lv.pool = p->d_pool.p;
@@ -940,7 +1000,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             // (4) owned part of dx_p, summed over the ranks (isolated blocks: rank 0)
             CK(cudaMemsetAsync(v.dxp, 0, (size_t)p->P * sizeof(double), p->stream));
             k_bcr_finish<<<grid_for(p->NB, 256), 256, 0, p->stream>>>(p->d_xv.p, p->bcr_blk_node.p, p->d_blk_lnode.p, p->bcr_blk_loc.p, p->NB, M, m,
-                                                                    r == 0 ? 1 : 0, v.S, p->bsr_diag.p, v.bS, lambda, v.dxp, p->info.p + 2);
+                                                                    r == 0 ? 1 : 0, v.S, p->bsr_diag.p, v.bS, lambda, v.dxp, p->info.p + 2, p->lam_dev);
             { const int rc = dist_sum(p, v.dxp, (int64_t)p->P); if (rc) return rc; }
             if (evp) CK(cudaEventRecord(evp->b, p->stream));
             p->launches += 5;
@@ -951,12 +1011,14 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         CK(cudaMemsetAsync(p->bcr_flags.p + Y.items.size(), 0, sizeof(unsigned), p->stream));
         CK(cudaMemsetAsync(p->info.p + 2, 0, sizeof(int), p->stream));
         k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->bcr_dst.p, v.bsr_tr, p->nnzb, v.bS, p->bcr_blk_node.p, p->bcr_blk_loc.p,
-                                                         p->bcr_node_size.p, p->NB, Y.n, Y.M, Y.ld, lambda, p->bcr_pool.p, p->bcr_bv.p);
+                                                         p->bcr_node_size.p, p->NB, Y.n, Y.M, Y.ld, lambda, p->bcr_pool.p, p->bcr_bv.p, p->lam_dev);
         BcrView bv;
         bv.n = Y.n; bv.M = Y.M; bv.ld = Y.ld; bv.nbuf = p->bcr_nbuf; bv.n_items = (int)Y.items.size(); bv.items = p->bcr_items.p; bv.pool = p->bcr_pool.p;
         bv.bv = p->bcr_bv.p; bv.xv = p->bcr_xv.p; bv.flags = p->bcr_flags.p; bv.counter = p->bcr_flags.p + Y.items.size();
         bv.epoch = ++p->bcr_epoch; bv.info = p->info.p + 2;
         bv.first_item = 0; bv.xpool = nullptr;
+        // a replayed graph keeps the epoch it was captured with: the item flags of the previous replay must not look complete
+        if (p->capturing) CK(cudaMemsetAsync(p->bcr_flags.p, 0, Y.items.size() * sizeof(unsigned), p->stream));
         bv.prof = nullptr;
         if (p->env_profile) {
             if (p->prof.n < 32) { CK(p->prof.alloc(32)); CK(cudaMemsetAsync(p->prof.p, 0, 32 * sizeof(unsigned long long), p->stream)); }
@@ -964,8 +1026,9 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         }
         k_bcr_run<<<std::min(p->num_sms, bv.n_items), BCR_THREADS, p->bcr_smem, p->stream>>>(bv);
         k_bcr_finish<<<grid_for(p->NB, 256), 256, 0, p->stream>>>(p->bcr_xv.p, p->bcr_blk_node.p, p->bcr_blk_node.p, p->bcr_blk_loc.p, p->NB, Y.M,
-                                                                Y.n, 1, v.S, p->bsr_diag.p, v.bS, lambda, v.dxp, p->info.p + 2);
+                                                                Y.n, 1, v.S, p->bsr_diag.p, v.bS, lambda, v.dxp, p->info.p + 2, p->lam_dev);
         if (evp) CK(cudaEventRecord(evp->b, p->stream));
+        if (p->capturing) CK(cudaEventRecordWithFlags(p->gev_sol_b, p->stream, cudaEventRecordExternal));
         p->launches += 3;
         }
     } else if (solver == VIO_SOLVER_BLOCK_CHOL) {
@@ -999,7 +1062,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
     }
     // landmarks + LM scalars
     if (p->L > 0) {
-        k_backsub<<<RED_BLOCKS, 256, 0, p->stream>>>(v, lambda, p->partial.p, p->partial2.p);
+        k_backsub<<<RED_BLOCKS, 256, 0, p->stream>>>(v, lambda, p->partial.p, p->partial2.p, p->lam_dev);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p, RED_BLOCKS, p->scal.p + 4, 0);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p, RED_BLOCKS, p->scal.p + 5, 0);
         p->launches += 3;
@@ -1007,7 +1070,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         CK(cudaMemsetAsync(p->scal.p + 4, 0, 2 * sizeof(double), p->stream));
     }
     if (p->Lx > 0) {
-        k_backsub_xyz<<<256, 256, 0, p->stream>>>(v, lambda, p->partial.p + 1280, p->partial2.p + 1280);
+        k_backsub_xyz<<<256, 256, 0, p->stream>>>(v, lambda, p->partial.p + 1280, p->partial2.p + 1280, p->lam_dev);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p + 1280, 256, p->scal.p + 4, 1);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p + 1280, 256, p->scal.p + 5, 1);
         p->launches += 3;
@@ -1016,7 +1079,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         // pose part of scale = dx^T (lambda dx + b) and |dx|^2.  Un-reduced linearisation: b_p is this rank's share (the sum over the
         // ranks is linear in it) and the lambda |dx|^2 / |dx|^2 terms are counted on the rows the rank owns
         const int g = grid_for(p->P, 256, 64);
-        k_pose_scale<<<g, 256, 0, p->stream>>>(v, lambda, p->dist_on ? p->d_own_row.p : nullptr, p->partial.p + 1024, p->partial2.p + 1024);
+        k_pose_scale<<<g, 256, 0, p->stream>>>(v, lambda, p->dist_on ? p->d_own_row.p : nullptr, p->partial.p + 1024, p->partial2.p + 1024, p->lam_dev);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p + 1024, g, p->scal.p + 6, 0);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p + 1024, g, p->scal.p + 7, 0);
         p->launches += 3;
@@ -1134,6 +1197,7 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
         p->env_pcg_plain = getenv("VIO_B200_PCG_PLAIN") != nullptr;
         p->env_no_bcr = getenv("VIO_B200_NO_BCR") != nullptr;
         p->env_chol_legacy = getenv("VIO_B200_CHOL_LEGACY") != nullptr;
+        p->env_no_graph = getenv("VIO_B200_NO_GRAPH") != nullptr;
         p->env_schur_fused = getenv("VIO_B200_SCHUR_FUSED") != nullptr;
         if (sms > 0) p->num_sms = sms;
     }
@@ -1163,6 +1227,9 @@ void vio_destroy(vio_problem *p) {
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
     if (p->nccl_comm && p->nccl_owned) nccl_api().CommDestroy(p->nccl_comm);
+    graphs_drop(p);
+    for (cudaEvent_t e : {p->gev_sol_a, p->gev_sol_b, p->gev_lin_a, p->gev_lin_b})
+        if (e) cudaEventDestroy(e);
     for (auto *vec : {&p->ev_lin, &p->ev_pcg, &p->ev_coarse})
         for (auto &e : *vec) {
             cudaEventDestroy(e.a);
@@ -1256,6 +1323,7 @@ static int set_graph_impl(vio_problem *p, const vio_graph *g, int batch) {
 // are not read any more)
 static int upload_packed(vio_problem *p, const vio_graph *g, const PackedGraph &K) {
     p->batch = K.batch; p->Pper = K.Pper;
+    graphs_drop(p);  // captured launches hold the old buffers' addresses and sizes
     p->cz_have_inverse = false;
     p->bchol_ready = false;
     p->bcr_state = 0;
@@ -1434,6 +1502,7 @@ int vio_get_owned_landmarks(const vio_problem *p, int32_t *out, int64_t cap, int
 int vio_set_prior(vio_problem *p, int32_t dim, const double *H, const double *b, int32_t err_dim, const double *err,
                   const double *jt) {
     if (!p || !p->has_graph) return VIO_ERR_STATE;
+    graphs_drop(p);
     if (dim == 0) {
         p->prior_dim = 0; p->err_dim = 0;
         p->linearized = false; p->lm_valid = false; p->cz_have_inverse = false;
@@ -1623,6 +1692,7 @@ int vio_rollback_step(vio_problem *p, const vio_lm_opts *opts) {
 // -------------------------------------------------------------------------------------------------
 // Problem::Solve
 // -------------------------------------------------------------------------------------------------
+// ---- CUDA-graph replay of the LM body ------------------------------------------------------------------------------------
 int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_stats *st) {
     if (!p || !p->has_graph) return VIO_ERR_STATE;
     CK(cudaSetDevice(p->device));
@@ -1637,6 +1707,9 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
     const cudaEvent_t ev0 = p->ev_solve0, ev1 = p->ev_solve1;
     CK(cudaEventRecord(ev0, p->stream));
     p->ev_lin_used = 0; p->ev_pcg_used = 0; p->ev_coarse_used = 0; p->pcg_iters_acc = 0.0;
+    p->g_sol_ms = 0.0; p->g_lin_ms = 0.0; p->g_sol_n = 0; p->g_lin_n = 0;
+    bool g_lin_pending = false;  // a replayed linearisation whose events have not been read yet
+    int trials_this_call = 0;
     int rc;
 #define RC(x)                       \
     do {                            \
@@ -1673,6 +1746,47 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
         while (!ok && (v15 || false_cnt < 10)) {
             int64_t pit = 0;
             const int solver_now = resolve_solver(p, o);
+            // From the second trial step of a call on (everything lazily allocated exists by then) the body is replayed as a
+            // CUDA graph: one launch instead of ~20, lambda handed over through device memory, one scalar read-back.
+            bool replay = graph_mode_ok(p, o, solver_now) && (trials_this_call > 0 || p->g_trial != nullptr);
+            const int gflags = (int)o.flavour | (p->prior_dim > 0 ? 4 : 0) | (p->err_dim > 0 ? 8 : 0);
+            if (replay && (p->g_key_solver != solver_now || p->g_key_flags != gflags)) graphs_drop(p);
+            if (replay && !p->g_trial) {
+                if (p->d_lambda.n < 1) CK(p->d_lambda.alloc(1));
+                if (!p->gev_sol_a) {
+                    CK(cudaEventCreate(&p->gev_sol_a)); CK(cudaEventCreate(&p->gev_sol_b));
+                    CK(cudaEventCreate(&p->gev_lin_a)); CK(cudaEventCreate(&p->gev_lin_b));
+                }
+                replay = graph_capture(p, &p->g_trial, &p->g_trial_launches, [&]() -> int {
+                    if (cudaMemcpyAsync(p->d_lambda.p, p->h_scal + 16, sizeof(double), cudaMemcpyHostToDevice, p->stream) != cudaSuccess) return VIO_ERR_CUDA;
+                    int r2 = do_solve_step(p, o, 0.0, nullptr);  // lambda comes from d_lambda
+                    if (r2) return r2;
+                    if (cudaMemcpyAsync(p->h_scal + 4, p->scal.p + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess) return VIO_ERR_CUDA;
+                    r2 = do_apply(p, o);
+                    if (r2) return r2;
+                    return do_chi2_enqueue(p, o);
+                });
+                if (replay) { p->g_key_solver = solver_now; p->g_key_flags = gflags; }
+            }
+            trials_this_call++;
+            double temp_chi = 0.0;
+            if (replay) {
+                p->h_scal[16] = lambda;
+                CK(cudaGraphLaunch(p->g_trial, p->stream));
+                p->launches += p->g_trial_launches;
+                st->trial_steps++;
+                CK(cudaStreamSynchronize(p->stream));
+                if (g_lin_pending) {
+                    float t = 0;
+                    if (cudaEventElapsedTime(&t, p->gev_lin_a, p->gev_lin_b) == cudaSuccess) { p->g_lin_ms += t; p->g_lin_n++; } else (void)cudaGetLastError();
+                    g_lin_pending = false;
+                }
+                if (solver_now == VIO_SOLVER_BCR) {
+                    float t = 0;
+                    if (cudaEventElapsedTime(&t, p->gev_sol_a, p->gev_sol_b) == cudaSuccess) { p->g_sol_ms += t; p->g_sol_n++; } else (void)cudaGetLastError();
+                }
+                temp_chi = 0.5 * (p->h_scal[0] + p->h_scal[1]);
+            } else {
             RC(do_solve_step(p, o, lambda, (solver_now == VIO_SOLVER_DENSE_CHOL || solver_now == VIO_SOLVER_BLOCK_CHOL || solver_now == VIO_SOLVER_BCR) ? nullptr : &pit));
             st->trial_steps++;
             st->pcg_iterations += pit;
@@ -1693,8 +1807,8 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
             }
             RC(do_apply(p, o));
             // IsGoodStepInLM
-            double temp_chi = 0.0;
             RC(do_chi2(p, o, &temp_chi));  // synchronises the stream: h_scal[4..7] have arrived as well
+            }
             const double dot = p->h_scal[4] + p->h_scal[6];
             const double scale = v15 ? dot + 1e-3 : 0.5 * dot + 1e-6;
             const double rho = (chi - temp_chi) / scale;
@@ -1711,7 +1825,17 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
                 ok = false;
             }
             if (ok) {
-                RC(do_linearize(p, o, true));
+                bool lin_replay = replay && !p->graph_disabled;
+                if (lin_replay && !p->g_lin)
+                    lin_replay = graph_capture(p, &p->g_lin, &p->g_lin_launches, [&]() -> int { return do_linearize(p, o, true); });
+                if (lin_replay) {
+                    CK(cudaGraphLaunch(p->g_lin, p->stream));
+                    p->launches += p->g_lin_launches;
+                    p->linearized = true;
+                    g_lin_pending = true;
+                } else {
+                    RC(do_linearize(p, o, true));
+                }
                 st->linearizations++;
                 st->accepted_steps++;
                 false_cnt = 0;
@@ -1733,23 +1857,33 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
 #undef RC
     CK(cudaEventRecord(ev1, p->stream));
     CK(cudaStreamSynchronize(p->stream));
+    if (g_lin_pending) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, p->gev_lin_a, p->gev_lin_b) == cudaSuccess) { p->g_lin_ms += t; p->g_lin_n++; } else (void)cudaGetLastError();
+    }
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
     st->ms_total = ms;
-    double lin = 0;
+    double lin = p->g_lin_ms;  // replayed linearisations (events inside the graph) + plainly launched ones
     for (size_t i = 0; i < p->ev_lin_used; ++i) {
         float t = 0;
         cudaEventElapsedTime(&t, p->ev_lin[i].a, p->ev_lin[i].b);
         lin += t;
     }
     st->ms_linearize = lin;
-    p->last_lin_ms = p->ev_lin_used ? lin / p->ev_lin_used : 0.0;
-    p->last_lin_launches = (int64_t)p->ev_lin_used;
     {
-        double tp = 0, tc = 0;
+        const long long nlin = (long long)p->ev_lin_used + p->g_lin_n;
+        p->last_lin_ms = nlin ? lin / nlin : 0.0;
+        p->last_lin_launches = (int64_t)nlin;
+    }
+    {
+        double tp = p->g_sol_ms, tc = 0;
         for (size_t i = 0; i < p->ev_pcg_used; ++i) { float t = 0; cudaEventElapsedTime(&t, p->ev_pcg[i].a, p->ev_pcg[i].b); tp += t; }
         for (size_t i = 0; i < p->ev_coarse_used; ++i) { float t = 0; cudaEventElapsedTime(&t, p->ev_coarse[i].a, p->ev_coarse[i].b); tc += t; }
-        p->last_pcg_ms = p->ev_pcg_used ? tp / p->ev_pcg_used : 0.0; p->last_pcg_launches = (int64_t)p->ev_pcg_used;
+        {
+            const long long nsol = (long long)p->ev_pcg_used + p->g_sol_n;
+            p->last_pcg_ms = nsol ? tp / nsol : 0.0; p->last_pcg_launches = (int64_t)nsol;
+        }
         p->last_coarse_ms = p->ev_coarse_used ? tc / p->ev_coarse_used : 0.0; p->last_coarse_launches = (int64_t)p->ev_coarse_used;
         p->last_pcg_iters = p->pcg_iters_acc;
         st->ms_reduced_solve = tp + tc;

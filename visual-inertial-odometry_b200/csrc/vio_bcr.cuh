@@ -36,7 +36,8 @@ struct BcrView {
 __global__ void __launch_bounds__(256) k_bcr_load(const double *__restrict__ val, const long long *__restrict__ dst, const int *__restrict__ tr, long long nnzb,
                                                   const double *__restrict__ b, const int *__restrict__ blk_node,
                                                   const int *__restrict__ blk_loc, const int *__restrict__ node_size, int nb, int n, int M, int LD,
-                                                  double lambda, double *__restrict__ pool, double *__restrict__ bv) {
+                                                  double lambda, double *__restrict__ pool, double *__restrict__ bv, const double *lam_p = nullptr) {
+    if (lam_p) lambda = *lam_p;
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (long long t = t0; t < nnzb * 36; t += stride) {
         const long long k = t / 36;
@@ -62,7 +63,9 @@ __global__ void __launch_bounds__(256) k_bcr_load(const double *__restrict__ val
 __global__ void __launch_bounds__(256) k_bcr_finish(const double *__restrict__ xv, const int *__restrict__ blk_gnode, const int *__restrict__ blk_node,
                                                     const int *__restrict__ blk_loc, int nb, int M, int own_hi, int do_iso,
                                                     const double *__restrict__ val, const int *__restrict__ diag,
-                                                    const double *__restrict__ b, double lambda, double *__restrict__ x, int *info) {
+                                                    const double *__restrict__ b, double lambda, double *__restrict__ x, int *info,
+                                                    const double *lam_p = nullptr) {
+    if (lam_p) lambda = *lam_p;
     // blk_gnode: node of the global partition (-1: isolated block); blk_node: node index into xv (multi-GPU: the rank's LOCAL
     // node, owned when < own_hi; other blocks are left untouched - x was zeroed and is summed over the ranks afterwards)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -246,8 +246,9 @@ __device__ __forceinline__ void dch_solve(const double *__restrict__ S, const do
 
 // single system (vio_solve on a dense sliding-window problem)
 __global__ void __launch_bounds__(DCH_THREADS, 1) k_dense_chol_blocked(const double *__restrict__ S, const double *__restrict__ b, double lambda,
-                                                                       int P, double *__restrict__ x, int *info) {
+                                                                       int P, double *__restrict__ x, int *info, const double *lam_p = nullptr) {
     extern __shared__ __align__(16) double dch_sm[];
+    if (lam_p) lambda = *lam_p;
     if (threadIdx.x == 0) *info = 0;
     dch_solve(S, b, lambda, P, x, info, dch_sm);
 }

@@ -764,7 +764,10 @@ __global__ void k_maxdiag(DevView v, double *partial) {
 // back-substitution and the LM scalars of IsGoodStepInLM
 // ------------------------------------------------------------------------------------------------
 // dxl = Hll^-1 (bl - Hlp dxp); also partial sums of  dx_l (lambda dx_l + b_l)  and dx_l^2
-__global__ void __launch_bounds__(256) k_backsub(DevView v, double lambda, double *partial_scale, double *partial_n2) {
+// lam_p (here and in the other kernels that take the damping): when not null, lambda is read from device memory - the LM body
+// is replayed as a CUDA graph whose kernel parameters are frozen while lambda changes every iteration
+__global__ void __launch_bounds__(256) k_backsub(DevView v, double lambda, double *partial_scale, double *partial_n2, const double *lam_p = nullptr) {
+    if (lam_p) lambda = *lam_p;
     double sc = 0.0, n2 = 0.0;
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < v.L; l += gridDim.x * blockDim.x) {
         const int e0 = v.lm_eptr[l], e1 = v.lm_eptr[l + 1];
@@ -798,7 +801,8 @@ __global__ void __launch_bounds__(256) k_backsub(DevView v, double lambda, doubl
 
 // own: nullptr, or (multi-GPU, un-reduced b_p) 1 for the rows this rank owns - the quadratic terms are counted there only
 __global__ void __launch_bounds__(256) k_pose_scale(DevView v, double lambda, const uint8_t *__restrict__ own, double *partial_scale,
-                                                    double *partial_n2) {
+                                                    double *partial_n2, const double *lam_p = nullptr) {
+    if (lam_p) lambda = *lam_p;
     double sc = 0.0, n2 = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.P; i += gridDim.x * blockDim.x) {
         const double d = v.dxp[i];

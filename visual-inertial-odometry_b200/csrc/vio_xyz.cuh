@@ -206,7 +206,8 @@ VIO_HD void backsub_point(const DevView &v, int l, double lambda, double &sc, do
         n2 += d * d;
     }
 }
-__global__ void __launch_bounds__(256) k_backsub_xyz(DevView v, double lambda, double *part_scale, double *part_n2) {
+__global__ void __launch_bounds__(256) k_backsub_xyz(DevView v, double lambda, double *part_scale, double *part_n2, const double *lam_p = nullptr) {
+    if (lam_p) lambda = *lam_p;
     double sc = 0.0, n2 = 0.0;
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < v.Lx; l += gridDim.x * blockDim.x) backsub_point(v, l, lambda, sc, n2);
     block_sum_to(sc, part_scale);
