@@ -1062,7 +1062,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
     }
     // landmarks + LM scalars
     if (p->L > 0) {
-        k_backsub<<<RED_BLOCKS, 256, 0, p->stream>>>(v, lambda, p->partial.p, p->partial2.p, p->lam_dev);
+        k_backsub<<<RED_BLOCKS, VIO_BACKSUB_THREADS, 0, p->stream>>>(v, lambda, p->partial.p, p->partial2.p, p->lam_dev);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p, RED_BLOCKS, p->scal.p + 4, 0);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p, RED_BLOCKS, p->scal.p + 5, 0);
         p->launches += 3;

@@ -766,31 +766,88 @@ __global__ void k_maxdiag(DevView v, double *partial) {
 // dxl = Hll^-1 (bl - Hlp dxp); also partial sums of  dx_l (lambda dx_l + b_l)  and dx_l^2
 // lam_p (here and in the other kernels that take the damping): when not null, lambda is read from device memory - the LM body
 // is replayed as a CUDA graph whose kernel parameters are frozen while lambda changes every iteration
-__global__ void __launch_bounds__(256) k_backsub(DevView v, double lambda, double *partial_scale, double *partial_n2, const double *lam_p = nullptr) {
+// Mapping: a warp takes 32 consecutive landmarks; their observer rows of H_lp are one contiguous run of `wo` (edges are stored
+// landmark by landmark), read lane <-> edge (48 contiguous bytes per lane, three 16-byte loads: fully coalesced) and summed per
+// landmark by a segmented warp scan in a fixed order; the host row, b_l and H_ll are read lane <-> landmark.
+#define VIO_BACKSUB_THREADS 512
+__global__ void __launch_bounds__(VIO_BACKSUB_THREADS) k_backsub(DevView v, double lambda, double *partial_scale, double *partial_n2,
+                                                                 const double *lam_p = nullptr) {
+    __shared__ double s_obs[VIO_BACKSUB_THREADS];
     if (lam_p) lambda = *lam_p;
     double sc = 0.0, n2 = 0.0;
-    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < v.L; l += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    double *obs = s_obs + (threadIdx.x & ~31);
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+    for (int l0 = wg * 32; l0 < v.L; l0 += nwg * 32) {
+        const int nl = min(32, v.L - l0), l = l0 + min(lane, nl - 1);
+        const bool mine = lane < nl;
         const int e0 = v.lm_eptr[l], e1 = v.lm_eptr[l + 1];
-        if (e0 == e1) { v.dxl[l] = 0.0; continue; }
-        const double bl = v.bl[l];
-        double t = bl;
-        const double *wh = v.wh + 6 * (size_t)l;
-        const double *dh = v.dxp + v.pose_off[v.lm_host[l]];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) t -= wh[k] * dh[k];
-        for (int e = e0; e < e1; ++e) {
-            const double *w = v.wo + 6 * (size_t)e;
-            const double *dj = v.dxp + v.pose_off[v.e_pose_j[e]];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) t -= w[k] * dj[k];
+        const int E0 = __shfl_sync(0xffffffffu, e0, 0), E1 = __shfl_sync(0xffffffffu, e1, nl - 1);
+        // per-landmark operands first: their loads are in flight while the edge rounds run
+        const double bl = v.bl[l], hll = v.Hll[l];
+        double th = 0.0;
+        {
+            const double2 *wh = reinterpret_cast<const double2 *>(v.wh + 6 * (size_t)l);
+            const double *dh = v.dxp + v.pose_off[v.lm_host[l]];
+            const double2 w0 = wh[0], w1 = wh[1], w2 = wh[2];
+            th = w0.x * dh[0] + w0.y * dh[1] + w1.x * dh[2] + w1.y * dh[3] + w2.x * dh[4] + w2.y * dh[5];
         }
+        obs[lane] = 0.0;
+        __syncwarp();
+        // software pipeline: the row and the observer index of the NEXT round are requested before this round is reduced
+        double2 n0 = make_double2(0.0, 0.0), n1 = n0, n2_ = n0;
+        int nj = 0;
+        if (E0 + lane < E1) {
+            const double2 *w = reinterpret_cast<const double2 *>(v.wo + 6 * (size_t)(E0 + lane));
+            n0 = w[0]; n1 = w[1]; n2_ = w[2];
+            nj = v.e_pose_j[E0 + lane];
+        }
+        for (int eb = E0; eb < E1; eb += 32) {
+            const int e = eb + lane;
+            const bool ev = e < E1;
+            const double2 w0 = n0, w1 = n1, w2 = n2_;
+            const int j = nj;
+            if (e + 32 < E1) {
+                const double2 *w = reinterpret_cast<const double2 *>(v.wo + 6 * (size_t)(e + 32));
+                n0 = w[0]; n1 = w[1]; n2_ = w[2];
+                nj = v.e_pose_j[e + 32];
+            }
+            double part = 0.0;
+            if (ev) {
+                const double *dj = v.dxp + v.pose_off[j];
+                part = w0.x * dj[0] + w0.y * dj[1] + w1.x * dj[2] + w1.y * dj[3] + w2.x * dj[4] + w2.y * dj[5];
+            }
+            // landmark of this edge, relative to l0: the last r with eptr[l0 + r] <= e (binary search over the lanes' e0)
+            int r = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int cand = r + step;
+                const int ce0 = __shfl_sync(0xffffffffu, e0, cand & 31);
+                if (cand < nl && ce0 <= e) r = cand;
+            }
+            if (!ev) r = -1;
+            // segmented inclusive scan: afterwards the last lane of a run of equal r holds the run's sum
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, part, off);
+                const int ur = __shfl_up_sync(0xffffffffu, r, off);
+                if (lane >= off && ur == r) part += up;
+            }
+            const int rn = __shfl_down_sync(0xffffffffu, r, 1);
+            if (ev && (lane == 31 || rn != r)) obs[r] += part;  // one writer per landmark and round
+            __syncwarp();
+        }
+        double t = bl - th - obs[lane];
+        __syncwarp();
         if (v.ext_pose >= 0) {  // free extrinsic vertex
             const double *w = v.we + 6 * (size_t)l;
             const double *dx = v.dxp + v.pose_off[v.ext_pose];
 #pragma unroll
             for (int k = 0; k < 6; ++k) t -= w[k] * dx[k];
         }
-        const double d = (v.lm_fixed && v.lm_fixed[l]) ? 0.0 : t / v.Hll[l];  // fixed landmark: constant
+        if (!mine) continue;
+        if (e0 == e1) { v.dxl[l] = 0.0; continue; }
+        const double d = (v.lm_fixed && v.lm_fixed[l]) ? 0.0 : t / hll;  // fixed landmark: constant
         v.dxl[l] = d;
         sc += d * (lambda * d + bl);
         n2 += d * d;
