@@ -701,10 +701,15 @@ __global__ void __launch_bounds__(256) k_chi2_lm(DevView v, double *partial) {
         pbi[0] += v.tic[0]; pbi[1] += v.tic[1]; pbi[2] += v.tic[2];
         mat3_mul_vec(RTh, pbi, pw);
         pw[0] += RTh[9]; pw[1] += RTh[10]; pw[2] += RTh[11];
+        // the next edge's observer index and observation are requested while the current residual is evaluated
+        int nj = v.e_pose_j[e0];
+        double n_pjx = v.e_pjx[e0], n_pjy = v.e_pjy[e0];
         for (int e = e0; e < e1; ++e) {
-            const double *RTj = v.poseRT + 16 * (size_t)v.e_pose_j[e];
+            const double *RTj = v.poseRT + 16 * (size_t)nj;
+            const double pjx = n_pjx, pjy = n_pjy;
+            if (e + 1 < e1) { nj = v.e_pose_j[e + 1]; n_pjx = v.e_pjx[e + 1]; n_pjy = v.e_pjy[e + 1]; }
             double pcj[3], pbj[3], r[2];
-            reproj_residual(v.Ric, v.tic, RTj, pw, v.e_pjx[e], v.e_pjy[e], pcj, pbj, r);
+            reproj_residual(v.Ric, v.tic, RTj, pw, pjx, pjy, pcj, pbj, r);
             const double e2 = v.rp_info * (r[0] * r[0] + r[1] * r[1]);
             if (v.rp_loss == 0) chi += e2;
             else {
