@@ -39,15 +39,29 @@ __global__ void __launch_bounds__(256) k_bcr_load(const double *__restrict__ val
                                                   double lambda, double *__restrict__ pool, double *__restrict__ bv, const double *lam_p = nullptr) {
     if (lam_p) lambda = *lam_p;
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long t = t0; t < nnzb * 36; t += stride) {
-        const long long k = t / 36;
-        const int e = (int)(t - 36 * k);
+    // one thread per (block, row): 32-bit index arithmetic (a 64-bit division per element used to dominate this kernel), the
+    // six values of a row are independent loads
+    for (long long t = t0; t < nnzb * 6; t += stride) {
+        const unsigned tu = (unsigned)t;  // nnzb * 6 < 2^32 (checked by the plan)
+        const unsigned k = tu / 6u;
+        const int r = (int)(tu - 6u * k);
         const long long d = dst[k];
         if (d < 0) continue;
         const bool dg = (d & BCR_DST_DIAG) != 0;
-        const int r = e / 6, c = e - 6 * r, kt = tr[k];
-        const double x = (kt < k || (kt == k && r > c)) ? val[36 * (long long)kt + 6 * c + r] : val[t];
-        pool[(d & ~BCR_DST_DIAG) + (long long)r * LD + c] = x + ((dg && r == c) ? lambda : 0.0);
+        const unsigned kt = (unsigned)tr[k];
+        double x[6];
+        if (kt < k) {
+            const double *src = val + 36 * (long long)kt + r;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) x[c] = src[6 * c];
+        } else {
+            const double *src = val + 36 * (long long)k;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) x[c] = (kt == k && r > c) ? src[6 * c + r] : src[6 * r + c];
+        }
+        double *out = pool + (d & ~BCR_DST_DIAG) + (long long)r * LD;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) out[c] = x[c] + ((dg && c == r) ? lambda : 0.0);
     }
     for (long long t = t0; t < (long long)n * M; t += stride) {  // identity padding of ragged nodes
         const int a = (int)(t / M), q = (int)(t % M);
