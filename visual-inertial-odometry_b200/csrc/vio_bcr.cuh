@@ -386,7 +386,9 @@ __device__ __forceinline__ void bcr_chol_inv(double *__restrict__ D, double *__r
                     const int c = 8 * (bnd - nbD) + g;
                     rv = c < k0;
                     C = U + (rv ? c : 0) * LD;
-                    const double2 u01 = *reinterpret_cast<const double2 *>(C + j0), u23 = *reinterpret_cast<const double2 *>(C + j0 + 2);
+                    // lanes without a row read nothing (a dummy read of row 0 would race with the band that owns it)
+                    const double2 zz = make_double2(0.0, 0.0);
+                    const double2 u01 = rv ? *reinterpret_cast<const double2 *>(C + j0) : zz, u23 = rv ? *reinterpret_cast<const double2 *>(C + j0 + 2) : zz;
                     const double g0 = u01.x * p0;
                     const double g1 = (u01.y - s01 * g0) * p1;
                     const double g2 = (u23.x - s02 * g0 - s12 * g1) * p2;
@@ -407,7 +409,7 @@ __device__ __forceinline__ void bcr_chol_inv(double *__restrict__ D, double *__r
                         cv[u] = rv && kc < M;
                         b[u] = Vc[4 * min(kb, M - 1) + q];
                         if (kb >= M) b[u] = 0.0;
-                        c[u] = *reinterpret_cast<const double2 *>(C + min(kc, M - 2));
+                        c[u] = cv[u] ? *reinterpret_cast<const double2 *>(C + kc) : make_double2(0.0, 0.0);
                     }
 #pragma unroll
                     for (int u = 0; u < BCR_CHUNK; ++u) bcr_dmma(c[u].x, c[u].y, a, b[u]);

@@ -66,6 +66,8 @@ __device__ __forceinline__ void dch_panel_factor(double (&r)[4][NPASS], double (
     const double y1 = (ry[1] - l10 * y0) * p1;
     const double y2 = (ry[2] - l20 * y0 - l21 * y1) * p2;
     const double y3 = (ry[3] - l30 * y0 - l31 * y1 - l32 * y2) * p3;
+    // every lane has read the rows, the 4x4 block and y of this panel (in the caller) before any lane overwrites them
+    __syncwarp();
 #pragma unroll
     for (int sp = 0; sp < NPASS; ++sp) {
         const int k = j0 + lane + 32 * sp;
@@ -201,7 +203,7 @@ __device__ __forceinline__ void dch_solve_impl(const double *__restrict__ S, con
                         cv[u] = rv && kc < Pp && kc >= cfirst;
                         bb[u] = Vc[4 * min(kb, Pp - 1) + q];
                         if (kb >= Pp) bb[u] = 0.0;
-                        c[u] = *reinterpret_cast<const double2 *>(C + (cv[u] ? kc : cfirst));
+                        c[u] = cv[u] ? *reinterpret_cast<const double2 *>(C + kc) : make_double2(0.0, 0.0);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) dch_dmma(c[u].x, c[u].y, a, bb[u]);
