@@ -469,7 +469,7 @@ def run_ours(args):
             "config": {"workload": args.workload, **wl, "edges": E, "landmarks": L, "cameras": C,
                        "lm_flavour": "v17", "reduced_solver": solver_used, "reduced_solver_requested": args.solver,
                        "schedule": "Solve(K) from the perturbed initial state (natural LM damping schedule)",
-                       "parallelism": f"landmark_shard{world}" + ("+distributed_reduced_solve" if (world > 1 and st.solver_used == capi.SOLVER_BCR and os.environ.get("VIO_B200_SHARD_LEGACY") is None) else ""), "collective": (args.collective if world > 1 else None), "l2": "inputs (>=520 MB of edge records) larger than L2",
+                       "parallelism": f"landmark_shard{world}" + ("+distributed_reduced_solve" if (world > 1 and st.solver_used == capi.SOLVER_BCR and os.environ.get("VIO_B200_SHARD_LEGACY") is None) else ""), "collective": ((("nvlink_peer_memory_kernel+nccl" if p.p2p_enabled() else "nccl") if args.collective == "native" else "hook") if world > 1 else None), "l2": "inputs (>=520 MB of edge records) larger than L2",
                        "scene_gen_s": round(t_gen, 2), "pack_upload_s": round(t_pack, 2)},
             "lm": {"trial_steps": int(st.trial_steps), "accepted": int(st.accepted_steps),
                    "linearizations": int(st.linearizations), "pcg_iterations": int(st.pcg_iterations),

@@ -230,6 +230,12 @@ int vio_set_allreduce(vio_problem *p, vio_allreduce_fn fn, void *user);
 int vio_nccl_unique_id(void *id128);
 int vio_nccl_init(vio_problem *p, int rank, int world, const void *id128);
 int vio_set_nccl_comm(vio_problem *p, void *nccl_comm, int rank, int world);
+/* Both calls also set up (collectively) an NVLink peer-memory mailbox between the ranks' handles (CUDA IPC): the small
+ * all-reduces of the distributed reduced solve - interface system, pose update, LM scalars - then run as ONE kernel of this
+ * library that stores into the peers' memory and sums in rank order (csrc/vio_p2p.cuh) instead of an ncclAllReduce; larger
+ * reductions stay on NCCL.  Falls back to NCCL on every rank when any rank cannot export / open a mailbox
+ * (VIO_B200_NO_P2P=1 forces the fallback).  vio_p2p_enabled: 1 when the mailbox path is active on this handle. */
+int vio_p2p_enabled(const vio_problem *p);
 /* landmark sharding (call before vio_set_graph with the FULL graph on every rank): rank r keeps a
  * contiguous, edge-balanced range of landmarks and their observations; pose-class vertices, the
  * reduced-system sparsity pattern and the LM scalars are replicated. Pose-only factors (SE3 prior,

@@ -93,7 +93,7 @@ EXPORTS = [
     "vio_get_hessian", "vio_get_schur", "vio_get_schur_bsr", "vio_get_delta", "vio_get_b", "vio_get_landmark_diag",
     "vio_get_kernel_ms", "vio_launch_count", "vio_measure_fp64_peak", "vio_dense_accumulate", "vio_dense_chi2",
     "vio_dense_solve", "vio_dense_get", "vio_solve_batched", "vio_solve_batched_lockstep", "vio_lockstep_release", "vio_get_coarse", "vio_preintegrate", "vio_get_solver_ms", "vio_set_points", "vio_get_points", "vio_get_point_system", "vio_marginalize",
-    "vio_nccl_unique_id", "vio_nccl_init", "vio_set_nccl_comm", "vio_get_owned_landmarks",
+    "vio_nccl_unique_id", "vio_nccl_init", "vio_set_nccl_comm", "vio_get_owned_landmarks", "vio_p2p_enabled",
 ]
 
 _lib = None
@@ -127,6 +127,8 @@ def lib():
         L.vio_nccl_unique_id.argtypes = [C.c_void_p]
         L.vio_nccl_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vio_set_nccl_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.vio_p2p_enabled.argtypes = [C.c_void_p]
+        L.vio_p2p_enabled.restype = C.c_int
         L.vio_set_prior.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, C.c_int32, _dp, _dp]
         L.vio_get_prior.argtypes = [C.c_void_p, _dp, _dp]
         L.vio_set_vertices.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -387,6 +389,10 @@ class Problem:
         unique_id: the 128 bytes of nccl_unique_id() made on rank 0 and shipped to every rank by the caller."""
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._ck(self._L.vio_nccl_init(self._h, rank, world, buf))
+
+    def p2p_enabled(self):
+        """True when the small all-reduces of the distributed solve go through the NVLink peer-memory mailbox (vio_p2p.cuh)."""
+        return bool(self._L.vio_p2p_enabled(self._h))
 
     def set_allreduce(self, pyfunc):
         """pyfunc(dev_ptr:int, count:int, stream:int) -> 0 on success."""

@@ -35,6 +35,7 @@
 #include "vio_bcr.h"
 #include "vio_bcr.cuh"
 #include "vio_dchol.cuh"
+#include "vio_p2p.cuh"
 
 #define VIO_VERSION_STR "vio_b200 0.1 (sm_100a)"
 
@@ -96,6 +97,13 @@ struct vio_problem {
     void *allreduce_user = nullptr;
     void *nccl_comm = nullptr;  // ncclComm_t (vio_nccl_init / vio_set_nccl_comm); takes precedence over the hook
     bool nccl_owned = false;
+    // NVLink peer-memory mailbox for the small all-reduces of the distributed solve (vio_p2p.cuh); set up by p2p_setup
+    bool p2p_ready = false;
+    void *p2p_block = nullptr;            // local mailbox: slots, flags, counter
+    void *p2p_peer[VIO_P2P_MAX_WORLD] = {};  // peers' mailboxes (cudaIpcOpenMemHandle)
+    P2pView p2p_view;
+    unsigned p2p_epoch = 0;
+    long long p2p_calls = 0;
     int shard_rank = 0, shard_world = 1;
 
     // sizes
@@ -383,6 +391,12 @@ bool graph_mode_ok(vio_problem *p, const vio_lm_opts &o, int solver) {
 }
 bool is_sharded(const vio_problem *p) { return p->shard_world > 1 && (p->nccl_comm || p->allreduce); }
 int dist_sum(vio_problem *p, double *ptr, int64_t count) {
+    if (p->p2p_ready && count <= VIO_P2P_CAP_DOUBLES) {
+        k_p2p_allreduce<<<VIO_P2P_CTAS, VIO_P2P_THREADS, 0, p->stream>>>(p->p2p_view, ptr, (int)count, ++p->p2p_epoch);
+        p->launches++;
+        p->p2p_calls++;
+        return VIO_OK;
+    }
     if (p->nccl_comm) {
         NcclApi &api = nccl_api();
         const int rc = api.AllReduce(ptr, ptr, (size_t)count, VIO_NCCL_FLOAT64, VIO_NCCL_SUM, p->nccl_comm, p->stream);
@@ -391,6 +405,70 @@ int dist_sum(vio_problem *p, double *ptr, int64_t count) {
     }
     const int rc = p->allreduce(ptr, count, (void *)p->stream, p->allreduce_user);
     if (rc != 0) return fail(p, VIO_ERR_CUDA, "allreduce hook failed (%d)", rc);
+    return VIO_OK;
+}
+
+// ---- NVLink peer-memory mailbox (vio_p2p.cuh).  Collective over the communicator's ranks; falls back to NCCL (p2p_ready stays
+// false on EVERY rank) when any rank cannot allocate, export or open a mailbox - e.g. two handles inside one process.
+void p2p_teardown(vio_problem *p) {
+    p->p2p_ready = false;
+    for (int r = 0; r < VIO_P2P_MAX_WORLD; ++r)
+        if (p->p2p_peer[r]) { cudaIpcCloseMemHandle(p->p2p_peer[r]); p->p2p_peer[r] = nullptr; }
+    if (p->p2p_block) { cudaFree(p->p2p_block); p->p2p_block = nullptr; }
+}
+int p2p_setup(vio_problem *p) {
+    p2p_teardown(p);
+    const int W = p->shard_world, me = p->shard_rank;
+    if (!p->nccl_comm || W < 2 || W > VIO_P2P_MAX_WORLD || getenv("VIO_B200_NO_P2P")) return VIO_OK;
+    NcclApi &api = nccl_api();
+    const size_t slot_bytes = 2 * (size_t)W * VIO_P2P_CAP_DOUBLES * sizeof(double), flag_bytes = (size_t)W * 32 * sizeof(unsigned);
+    const size_t total = slot_bytes + flag_bytes + 256;
+    bool ok = cudaMalloc(&p->p2p_block, total) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok) ok = cudaMemset(p->p2p_block, 0, total) == cudaSuccess && cudaIpcGetMemHandle(&mine, p->p2p_block) == cudaSuccess;
+    if (!ok) (void)cudaGetLastError();
+    // exchange the 64-byte handles: one double per byte through a sum all-reduce (exact), plus one "failed" counter
+    const int HB = (int)sizeof(cudaIpcMemHandle_t);
+    std::vector<double> h((size_t)W * HB + 1, 0.0);
+    for (int i = 0; i < HB; ++i) h[(size_t)me * HB + i] = (double)((const unsigned char *)&mine)[i];
+    h[(size_t)W * HB] = ok ? 0.0 : 1.0;
+    DBuf<double> d;
+    CK(d.alloc(h.size()));
+    CK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (api.AllReduce(d.p, d.p, h.size(), VIO_NCCL_FLOAT64, VIO_NCCL_SUM, p->nccl_comm, p->stream) != 0) return fail(p, VIO_ERR_CUDA, "ncclAllReduce failed (p2p setup)");
+    CK(cudaMemcpyAsync(h.data(), d.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    bool all_ok = h[(size_t)W * HB] == 0.0;
+    if (all_ok) {
+        for (int r = 0; r < W && ok; ++r) {
+            if (r == me) continue;
+            cudaIpcMemHandle_t hr;
+            for (int i = 0; i < HB; ++i) ((unsigned char *)&hr)[i] = (unsigned char)h[(size_t)r * HB + i];
+            if (cudaIpcOpenMemHandle(&p->p2p_peer[r], hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                (void)cudaGetLastError();
+                p->p2p_peer[r] = nullptr;
+                ok = false;
+            }
+        }
+    }
+    // second agreement round: did every rank open every mailbox?  (also the barrier behind the memsets above)
+    double flag = (ok && all_ok) ? 0.0 : 1.0;
+    CK(cudaMemcpyAsync(d.p, &flag, sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (api.AllReduce(d.p, d.p, 1, VIO_NCCL_FLOAT64, VIO_NCCL_SUM, p->nccl_comm, p->stream) != 0) return fail(p, VIO_ERR_CUDA, "ncclAllReduce failed (p2p setup)");
+    CK(cudaMemcpyAsync(&flag, d.p, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (flag != 0.0) { p2p_teardown(p); return VIO_OK; }
+    P2pView &pv = p->p2p_view;
+    pv.rank = me; pv.world = W;
+    for (int r = 0; r < W; ++r) {
+        char *base = (char *)(r == me ? p->p2p_block : p->p2p_peer[r]);
+        pv.slots[r] = (double *)base;
+        pv.flags[r] = (unsigned *)(base + slot_bytes);
+    }
+    pv.counter = (unsigned *)((char *)p->p2p_block + slot_bytes + flag_bytes);
+    p->p2p_epoch = 0;
+    p->p2p_ready = true;
     return VIO_OK;
 }
 
@@ -1226,6 +1304,7 @@ void vio_destroy(vio_problem *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
+    p2p_teardown(p);
     if (p->nccl_comm && p->nccl_owned) nccl_api().CommDestroy(p->nccl_comm);
     graphs_drop(p);
     for (cudaEvent_t e : {p->gev_sol_a, p->gev_sol_b, p->gev_lin_a, p->gev_lin_b})
@@ -1279,7 +1358,7 @@ int vio_nccl_init(vio_problem *p, int rank, int world, const void *id128) {
     p->nccl_owned = true;
     p->shard_rank = rank;
     p->shard_world = world;
-    return VIO_OK;
+    return p2p_setup(p);
 }
 
 int vio_set_nccl_comm(vio_problem *p, void *nccl_comm, int rank, int world) {
@@ -1291,8 +1370,12 @@ int vio_set_nccl_comm(vio_problem *p, void *nccl_comm, int rank, int world) {
     p->nccl_owned = false;
     p->shard_rank = rank;
     p->shard_world = world;
-    return VIO_OK;
+    if (!nccl_comm) { p2p_teardown(p); return VIO_OK; }
+    CK(cudaSetDevice(p->device));
+    return p2p_setup(p);
 }
+
+int vio_p2p_enabled(const vio_problem *p) { return p && p->p2p_ready ? 1 : 0; }
 
 int vio_set_shard(vio_problem *p, int rank, int world) {
     if (!p || world < 1 || rank < 0 || rank >= world) return VIO_ERR_INVALID;
