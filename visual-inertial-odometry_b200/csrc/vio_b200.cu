@@ -102,7 +102,6 @@ struct vio_problem {
     void *p2p_block = nullptr;            // local mailbox: slots, flags, counter
     void *p2p_peer[VIO_P2P_MAX_WORLD] = {};  // peers' mailboxes (cudaIpcOpenMemHandle)
     P2pView p2p_view;
-    unsigned p2p_epoch = 0;
     long long p2p_calls = 0;
     int shard_rank = 0, shard_world = 1;
 
@@ -139,7 +138,7 @@ struct vio_problem {
     cudaGraphExec_t g_trial = nullptr, g_lin = nullptr;
     int g_trial_launches = 0, g_lin_launches = 0, g_key_solver = -1, g_key_flags = -1;
     cudaEvent_t gev_sol_a = nullptr, gev_sol_b = nullptr, gev_lin_a = nullptr, gev_lin_b = nullptr;
-    bool graph_disabled = false, capturing = false, env_no_graph = false;
+    bool graph_disabled = false, capturing = false, env_no_graph = false, env_no_graph_dist = false;
     DBuf<double> d_lambda;
     const double *lam_dev = nullptr;
     double g_sol_ms = 0.0, g_lin_ms = 0.0;
@@ -385,14 +384,17 @@ bool graph_capture(vio_problem *p, cudaGraphExec_t *out, int *n_launches, F &&bo
 }
 bool graph_mode_ok(vio_problem *p, const vio_lm_opts &o, int solver) {
     if (p->graph_disabled || p->env_no_graph || p->env_profile || o.flavour != VIO_LM_V17 || p->stream == nullptr) return false;
-    if (p->shard_world != 1 || p->ext_free || p->batch != 1) return false;
+    if (p->ext_free || p->batch != 1) return false;
+    // multi-GPU: only the distributed cyclic reduction with every exchange step on the peer-memory kernel (no NCCL call and no
+    // host callback inside a captured graph); all ranks take the same decision (same plan, same collective setup)
+    if (p->shard_world != 1) return solver == VIO_SOLVER_BCR && p->dist_on && p->p2p_ready && !p->env_no_graph_dist;
     if (solver == VIO_SOLVER_BCR) return true;
     return solver == VIO_SOLVER_DENSE_CHOL && p->storage == VIO_STORAGE_DENSE && p->P <= DCH_MAX_P && !p->env_chol_legacy;
 }
 bool is_sharded(const vio_problem *p) { return p->shard_world > 1 && (p->nccl_comm || p->allreduce); }
 int dist_sum(vio_problem *p, double *ptr, int64_t count) {
     if (p->p2p_ready && count <= VIO_P2P_CAP_DOUBLES) {
-        k_p2p_allreduce<<<VIO_P2P_CTAS, VIO_P2P_THREADS, 0, p->stream>>>(p->p2p_view, ptr, (int)count, ++p->p2p_epoch);
+        k_p2p_allreduce<<<VIO_P2P_CTAS, VIO_P2P_THREADS, 0, p->stream>>>(p->p2p_view, ptr, (int)count);
         p->launches++;
         p->p2p_calls++;
         return VIO_OK;
@@ -467,7 +469,6 @@ int p2p_setup(vio_problem *p) {
         pv.flags[r] = (unsigned *)(base + slot_bytes);
     }
     pv.counter = (unsigned *)((char *)p->p2p_block + slot_bytes + flag_bytes);
-    p->p2p_epoch = 0;
     p->p2p_ready = true;
     return VIO_OK;
 }
@@ -1050,6 +1051,10 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
             k_bcr_load<<<4 * p->num_sms, 256, 0, p->stream>>>(v.S, p->d_dst.p, v.bsr_tr, p->nnzb, v.bS, p->d_blk_lnode.p, p->bcr_blk_loc.p,
                                                              p->d_node_size.p, p->NB, m + 1, M, Y.ld, lambda, p->d_pool.p, p->d_bv.p, p->lam_dev);
             const unsigned epoch = ++p->bcr_epoch;
+            if (p->capturing) {  // a replayed graph keeps its epoch: no item flag of the previous replay may look complete
+                CK(cudaMemsetAsync(p->d_lflags.p, 0, (size_t)nL * sizeof(unsigned), p->stream));
+                CK(cudaMemsetAsync(p->d_iflags.p, 0, (size_t)nI * sizeof(unsigned), p->stream));
+            }
             BcrView lv;
             lv.n = m + 1; lv.M = M; lv.ld = Y.ld; lv.nbuf = p->bcr_nbuf; lv.items = p->d_litems.p; lv.pool = p->d_pool.p;
             lv.bv = p->d_bv.p; lv.xv = p->d_xv.p; lv.flags = p->d_lflags.p; lv.epoch = epoch; lv.info = p->info.p + 2; lv.prof = nullptr;
@@ -1081,6 +1086,7 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
                                                                     r == 0 ? 1 : 0, v.S, p->bsr_diag.p, v.bS, lambda, v.dxp, p->info.p + 2, p->lam_dev);
             { const int rc = dist_sum(p, v.dxp, (int64_t)p->P); if (rc) return rc; }
             if (evp) CK(cudaEventRecord(evp->b, p->stream));
+            if (p->capturing) CK(cudaEventRecordWithFlags(p->gev_sol_b, p->stream, cudaEventRecordExternal));
             p->launches += 5;
         } else {
         // node tiles D_i and level-0 couplings E_i are rebuilt from S + lambda I; the W tiles behind them are overwritten
@@ -1276,6 +1282,7 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
         p->env_no_bcr = getenv("VIO_B200_NO_BCR") != nullptr;
         p->env_chol_legacy = getenv("VIO_B200_CHOL_LEGACY") != nullptr;
         p->env_no_graph = getenv("VIO_B200_NO_GRAPH") != nullptr;
+        p->env_no_graph_dist = getenv("VIO_B200_NO_GRAPH_DIST") != nullptr;
         p->env_schur_fused = getenv("VIO_B200_SCHUR_FUSED") != nullptr;
         if (sms > 0) p->num_sms = sms;
     }

@@ -24,7 +24,9 @@ struct P2pView {
     int rank, world;
     double *slots[VIO_P2P_MAX_WORLD];     // base of rank r's mailbox: [2 parities][world][CAP] doubles
     unsigned *flags[VIO_P2P_MAX_WORLD];   // base of rank r's flag words: [world] (stride 32 words)
-    unsigned *counter;                    // local: CTAs that finished their pushes
+    unsigned *counter;                    // local: [0] CTAs that finished their pushes, [1] CTAs that finished their sums,
+                                          // [2] reductions completed so far (the epoch lives on the device so that a CUDA graph
+                                          // can replay the kernel with frozen parameters)
 };
 
 __device__ __forceinline__ unsigned p2p_ld_acquire_sys(const unsigned *p) {
@@ -37,8 +39,11 @@ __device__ __forceinline__ void p2p_st_release_sys(unsigned *p, unsigned v) {
 }
 
 // buf[0..count) := sum over the ranks of their buf, in place.  count <= VIO_P2P_CAP_DOUBLES, buf 16-byte aligned.
-__global__ void __launch_bounds__(VIO_P2P_THREADS) k_p2p_allreduce(P2pView pv, double *__restrict__ buf, int count, unsigned epoch) {
+__global__ void __launch_bounds__(VIO_P2P_THREADS) k_p2p_allreduce(P2pView pv, double *__restrict__ buf, int count) {
     const int me = pv.rank, W = pv.world;
+    // every rank runs the same sequence of reductions: the local count of completed ones + 1 is the same number everywhere.
+    // It is bumped by the LAST CTA to leave the kernel, i.e. after every CTA has read it here.
+    const unsigned epoch = *reinterpret_cast<volatile unsigned *>(pv.counter + 2) + 1u;
     const int par = epoch & 1;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     // double2 part (16-byte aligned buffers) + scalar rest; a thread owns the SAME elements in the push and in the sum
@@ -84,5 +89,14 @@ __global__ void __launch_bounds__(VIO_P2P_THREADS) k_p2p_allreduce(P2pView pv, d
         double s = 0.0;
         for (int r = 0; r < W; ++r) s += r == me ? buf[i] : __ldcv(mine + (size_t)r * VIO_P2P_CAP_DOUBLES + i);
         buf[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(pv.counter + 1, 1u) == gridDim.x - 1) {
+            pv.counter[1] = 0;
+            __threadfence();
+            pv.counter[2] = epoch;
+        }
     }
 }
