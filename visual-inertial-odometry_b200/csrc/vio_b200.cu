@@ -139,6 +139,7 @@ struct vio_problem {
     int g_trial_launches = 0, g_lin_launches = 0, g_key_solver = -1, g_key_flags = -1;
     cudaEvent_t gev_sol_a = nullptr, gev_sol_b = nullptr, gev_lin_a = nullptr, gev_lin_b = nullptr;
     bool graph_disabled = false, capturing = false, env_no_graph = false, env_no_graph_dist = false;
+    int env_dch_threads = 256;  // VIO_B200_DCH_THREADS: CTA size of the single-system blocked dense Cholesky (64 .. 512)
     DBuf<double> d_lambda;
     const double *lam_dev = nullptr;
     double g_sol_ms = 0.0, g_lin_ms = 0.0;
@@ -683,7 +684,8 @@ int do_chi2_enqueue(vio_problem *p, const vio_lm_opts &o) {
     { const int rc_pp = do_pose_prep(p); if (rc_pp) return rc_pp; }
     double *acc = p->scal.p + 0;
     if (p->L > 0) {
-        k_chi2_lm<<<RED_BLOCKS, 256, 0, p->stream>>>(v, p->partial.p);
+        if (p->E < (1LL << 18)) k_chi2_lm_small<<<RED_BLOCKS, 256, 0, p->stream>>>(v, p->partial.p);  // windows, TestMonoBA
+        else k_chi2_lm<<<RED_BLOCKS, 256, 0, p->stream>>>(v, p->partial.p);
         k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p, RED_BLOCKS, acc, 0);
         p->launches += 2;
     } else {
@@ -779,8 +781,13 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         const size_t tri_bytes = ((size_t)P * (P + 1) / 2 + P) * sizeof(double);
         if (P <= DCH_MAX_P && !p->env_chol_legacy) {
             // blocked (panels of 4, look-ahead, DMMA trailing updates): ~10x fewer barriers than the column-by-column kernel
-            CK(RAISE_SMEM(k_dense_chol_blocked));
-            k_dense_chol_blocked<<<1, DCH_THREADS, dch_smem_bytes(P), p->stream>>>(v.S, v.bS, lambda, P, v.dxp, p->info.p, p->lam_dev);
+            if (p->env_dch_threads <= 256) {
+                CK(RAISE_SMEM(k_dense_chol_blocked<256>));
+                k_dense_chol_blocked<256><<<1, p->env_dch_threads, dch_smem_bytes(P), p->stream>>>(v.S, v.bS, lambda, P, v.dxp, p->info.p, p->lam_dev);
+            } else {
+                CK(RAISE_SMEM(k_dense_chol_blocked<512>));
+                k_dense_chol_blocked<512><<<1, p->env_dch_threads, dch_smem_bytes(P), p->stream>>>(v.S, v.bS, lambda, P, v.dxp, p->info.p, p->lam_dev);
+            }
         } else if (tri_bytes <= 220 * 1024) {
             if (!p->chol_smem_set) {
                 CK(RAISE_SMEM(k_dense_chol_smem));
@@ -1283,6 +1290,7 @@ int vio_create(int device, void *cuda_stream, vio_problem **out) {
         p->env_chol_legacy = getenv("VIO_B200_CHOL_LEGACY") != nullptr;
         p->env_no_graph = getenv("VIO_B200_NO_GRAPH") != nullptr;
         p->env_no_graph_dist = getenv("VIO_B200_NO_GRAPH_DIST") != nullptr;
+        if (const char *ev = getenv("VIO_B200_DCH_THREADS")) { const int t = atoi(ev); if (t >= 64 && t <= 512 && t % 32 == 0) p->env_dch_threads = t; }
         p->env_schur_fused = getenv("VIO_B200_SCHUR_FUSED") != nullptr;
         if (sms > 0) p->num_sms = sms;
     }

@@ -246,8 +246,10 @@ __device__ __forceinline__ void dch_solve(const double *__restrict__ S, const do
     else dch_solve_impl<6>(S, b, lambda, P, x, info, sm);
 }
 
-// single system (vio_solve on a dense sliding-window problem)
-__global__ void __launch_bounds__(DCH_THREADS, 1) k_dense_chol_blocked(const double *__restrict__ S, const double *__restrict__ b, double lambda,
+// single system (vio_solve on a dense sliding-window problem).  MAXT = 256 (176 registers) or 512 (128 registers: more worker
+// warps for the trailing update, a few spills on the look-ahead warp)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_dense_chol_blocked(const double *__restrict__ S, const double *__restrict__ b, double lambda,
                                                                        int P, double *__restrict__ x, int *info, const double *lam_p = nullptr) {
     extern __shared__ __align__(16) double dch_sm[];
     if (lam_p) lambda = *lam_p;

@@ -722,6 +722,59 @@ __global__ void __launch_bounds__(256) k_chi2_lm(DevView v, double *partial) {
     block_sum_to(chi, partial);
 }
 
+// The same sum for SMALL graphs (sliding windows, TestMonoBA): with a few hundred landmarks the kernel above is one latency
+// chain of ~20 edges per thread on a handful of warps.  Here a warp takes LPW landmarks (lane <-> landmark for the host chain
+// p_w) and walks their contiguous run of edges lane <-> edge; an edge finds its landmark by a binary search over the lanes'
+// first-edge indices and fetches p_w by shuffle.  (On large scenes this mapping loses: the observers' R, t become a many-way
+// gather instead of a broadcast - 320 us against 75 us at config 5.)
+__global__ void __launch_bounds__(256) k_chi2_lm_small(DevView v, double *partial) {
+    double chi = 0.0;
+    const int lane = threadIdx.x & 31;
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
+    const int LPW = v.L >= 8 * nwg ? 8 : 2;
+    for (int l0 = wg * LPW; l0 < v.L; l0 += nwg * LPW) {
+        const int nl = min(LPW, v.L - l0), l = l0 + min(lane, nl - 1);
+        const int e0 = v.lm_eptr[l], e1 = v.lm_eptr[l + 1];
+        const int E0 = __shfl_sync(0xffffffffu, e0, 0), E1 = __shfl_sync(0xffffffffu, e1, nl - 1);
+        double pw[3];
+        {
+            const int h = v.lm_host[l];
+            const double lam = v.invdep[l];
+            const double *RTh = v.poseRT + 16 * (size_t)h;
+            const double pci[3] = {v.lm_pix[l] / lam, v.lm_piy[l] / lam, v.lm_piz[l] / lam};
+            double pbi[3];
+            mat3_mul_vec(v.Ric, pci, pbi);
+            pbi[0] += v.tic[0]; pbi[1] += v.tic[1]; pbi[2] += v.tic[2];
+            mat3_mul_vec(RTh, pbi, pw);
+            pw[0] += RTh[9]; pw[1] += RTh[10]; pw[2] += RTh[11];
+        }
+        for (int eb = E0; eb < E1; eb += 32) {
+            const int e = eb + lane;
+            const bool ev = e < E1;
+            int r = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int cand = r + step;
+                const int ce0 = __shfl_sync(0xffffffffu, e0, cand & 31);
+                if (cand < nl && ce0 <= e) r = cand;
+            }
+            const double pwe[3] = {__shfl_sync(0xffffffffu, pw[0], r), __shfl_sync(0xffffffffu, pw[1], r), __shfl_sync(0xffffffffu, pw[2], r)};
+            if (!ev) continue;
+            const double *RTj = v.poseRT + 16 * (size_t)v.e_pose_j[e];
+            double pcj[3], pbj[3], rr[2];
+            reproj_residual(v.Ric, v.tic, RTj, pwe, v.e_pjx[e], v.e_pjy[e], pcj, pbj, rr);
+            const double e2 = v.rp_info * (rr[0] * rr[0] + rr[1] * rr[1]);
+            if (v.rp_loss == 0) chi += e2;
+            else {
+                double rho[3];
+                loss_compute(v.rp_loss, v.rp_delta, e2, rho);
+                chi += rho[0];
+            }
+        }
+    }
+    block_sum_to(chi, partial);
+}
+
 // ------------------------------------------------------------------------------------------------
 // finalize reduced system after (all-reduced) accumulation: mirror the upper triangle, bS = bp - bcorr
 // ------------------------------------------------------------------------------------------------
@@ -783,8 +836,11 @@ __global__ void __launch_bounds__(VIO_BACKSUB_THREADS) k_backsub(DevView v, doub
     const int lane = threadIdx.x & 31;
     double *obs = s_obs + (threadIdx.x & ~31);
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwg = (gridDim.x * blockDim.x) >> 5;
-    for (int l0 = wg * 32; l0 < v.L; l0 += nwg * 32) {
-        const int nl = min(32, v.L - l0), l = l0 + min(lane, nl - 1);
+    // landmarks per warp: 32 on large scenes; small graphs (a sliding window has ~1000 landmarks) spread over more warps, or a
+    // handful of warps would walk all the edge rounds one after the other
+    const int LPW = v.L >= 32 * nwg ? 32 : (v.L >= 8 * nwg ? 8 : 2);
+    for (int l0 = wg * LPW; l0 < v.L; l0 += nwg * LPW) {
+        const int nl = min(LPW, v.L - l0), l = l0 + min(lane, nl - 1);
         const bool mine = lane < nl;
         const int e0 = v.lm_eptr[l], e1 = v.lm_eptr[l + 1];
         const int E0 = __shfl_sync(0xffffffffu, e0, 0), E1 = __shfl_sync(0xffffffffu, e1, nl - 1);
