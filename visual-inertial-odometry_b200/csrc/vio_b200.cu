@@ -470,6 +470,8 @@ int p2p_setup(vio_problem *p) {
         pv.flags[r] = (unsigned *)(base + slot_bytes);
     }
     pv.counter = (unsigned *)((char *)p->p2p_block + slot_bytes + flag_bytes);
+    pv.err = (unsigned *)(p->h_scal + 40);  // pinned host memory: the kernel can store to it, vio_solve reads it after its syncs
+    *pv.err = 0;
     p->p2p_ready = true;
     return VIO_OK;
 }
@@ -1907,6 +1909,8 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
             // IsGoodStepInLM
             RC(do_chi2(p, o, &temp_chi));  // synchronises the stream: h_scal[4..7] have arrived as well
             }
+            if (p->p2p_ready && *reinterpret_cast<volatile unsigned *>(p->h_scal + 40) != 0)
+                return fail(p, VIO_ERR_CUDA, "peer-memory all-reduce: rank %u did not arrive within 10 s", *reinterpret_cast<volatile unsigned *>(p->h_scal + 40) - 1u);
             const double dot = p->h_scal[4] + p->h_scal[6];
             const double scale = v15 ? dot + 1e-3 : 0.5 * dot + 1e-6;
             const double rho = (chi - temp_chi) / scale;
@@ -1955,6 +1959,9 @@ int vio_solve(vio_problem *p, int32_t iterations, const vio_lm_opts *opts, vio_s
 #undef RC
     CK(cudaEventRecord(ev1, p->stream));
     CK(cudaStreamSynchronize(p->stream));
+    if (p->p2p_ready && *reinterpret_cast<volatile unsigned *>(p->h_scal + 40) != 0)
+        return fail(p, VIO_ERR_CUDA, "peer-memory all-reduce: rank %u did not arrive within 10 s (a rank failed or left the collective sequence)",
+                    *reinterpret_cast<volatile unsigned *>(p->h_scal + 40) - 1u);
     if (g_lin_pending) {
         float t = 0;
         if (cudaEventElapsedTime(&t, p->gev_lin_a, p->gev_lin_b) == cudaSuccess) { p->g_lin_ms += t; p->g_lin_n++; } else (void)cudaGetLastError();

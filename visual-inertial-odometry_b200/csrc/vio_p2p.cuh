@@ -24,6 +24,7 @@ struct P2pView {
     int rank, world;
     double *slots[VIO_P2P_MAX_WORLD];     // base of rank r's mailbox: [2 parities][world][CAP] doubles
     unsigned *flags[VIO_P2P_MAX_WORLD];   // base of rank r's flag words: [world] (stride 32 words)
+    unsigned *err;                        // pinned host word (device-visible): set when a peer's flag does not arrive in time
     unsigned *counter;                    // local: [0] CTAs that finished their pushes, [1] CTAs that finished their sums,
                                           // [2] reductions completed so far (the epoch lives on the device so that a CUDA graph
                                           // can replay the kernel with frozen parameters)
@@ -72,7 +73,14 @@ __global__ void __launch_bounds__(VIO_P2P_THREADS) k_p2p_allreduce(P2pView pv, d
     // ---- 3. wait for the peers, sum in rank order
     if (threadIdx.x < W && (int)threadIdx.x != me) {
         const unsigned *f = pv.flags[me] + 32 * threadIdx.x;
-        while ((int)(p2p_ld_acquire_sys(f) - epoch) < 0) __nanosleep(20);
+        // a rank that died or left the collective sequence must not hang the others' GPUs: give up after ~10 s, tell the host
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(p2p_ld_acquire_sys(f) - epoch) < 0) {
+            __nanosleep(20);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ull) { *reinterpret_cast<volatile unsigned *>(pv.err) = 1u + threadIdx.x; break; }
+        }
     }
     __syncthreads();
     const double *mine = pv.slots[me] + (size_t)par * W * VIO_P2P_CAP_DOUBLES;
