@@ -1153,12 +1153,16 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
     } else {
         return fail(p, VIO_ERR_INVALID, "unknown solver %d", solver);
     }
-    // landmarks + LM scalars
+    // landmarks + LM scalars.  Without XYZ landmarks (their sums are added on top) the four fixed-order sums are one launch.
+    const bool sum4 = p->Lx == 0;
     if (p->L > 0) {
         k_backsub<<<RED_BLOCKS, VIO_BACKSUB_THREADS, 0, p->stream>>>(v, lambda, p->partial.p, p->partial2.p, p->lam_dev);
-        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p, RED_BLOCKS, p->scal.p + 4, 0);
-        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p, RED_BLOCKS, p->scal.p + 5, 0);
-        p->launches += 3;
+        p->launches++;
+        if (!sum4) {
+            k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p, RED_BLOCKS, p->scal.p + 4, 0);
+            k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p, RED_BLOCKS, p->scal.p + 5, 0);
+            p->launches += 2;
+        }
     } else {
         CK(cudaMemsetAsync(p->scal.p + 4, 0, 2 * sizeof(double), p->stream));
     }
@@ -1173,9 +1177,19 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
         // ranks is linear in it) and the lambda |dx|^2 / |dx|^2 terms are counted on the rows the rank owns
         const int g = grid_for(p->P, 256, 64);
         k_pose_scale<<<g, 256, 0, p->stream>>>(v, lambda, p->dist_on ? p->d_own_row.p : nullptr, p->partial.p + 1024, p->partial2.p + 1024, p->lam_dev);
-        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p + 1024, g, p->scal.p + 6, 0);
-        k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p + 1024, g, p->scal.p + 7, 0);
-        p->launches += 3;
+        p->launches++;
+        if (sum4) {
+            Sum4 a;
+            a.partial[0] = p->partial.p; a.partial[1] = p->partial2.p; a.partial[2] = p->partial.p + 1024; a.partial[3] = p->partial2.p + 1024;
+            a.out[0] = p->scal.p + 4; a.out[1] = p->scal.p + 5; a.out[2] = p->scal.p + 6; a.out[3] = p->scal.p + 7;
+            a.n[0] = a.n[1] = p->L > 0 ? RED_BLOCKS : 0; a.n[2] = a.n[3] = g;
+            k_sum_partials4<<<4, 256, 0, p->stream>>>(a);
+            p->launches++;
+        } else {
+            k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial.p + 1024, g, p->scal.p + 6, 0);
+            k_sum_partials<<<1, 256, 0, p->stream>>>(p->partial2.p + 1024, g, p->scal.p + 7, 0);
+            p->launches += 2;
+        }
     }
     if (is_sharded(p)) {
         const int rc = dist_sum(p, p->scal.p + 4, p->dist_on ? 4 : 2);
@@ -1187,10 +1201,8 @@ int do_solve_step(vio_problem *p, const vio_lm_opts &o, double lambda, int64_t *
 
 int do_apply(vio_problem *p, const vio_lm_opts &o) {
     const DevView &v = p->view;
-    k_update_pose<<<grid_for(p->C, 128), 128, 0, p->stream>>>(v, 1.0, 1);
-    if (p->NSB > 0) k_update_sb<<<grid_for(p->NSB, 128), 128, 0, p->stream>>>(v, 1.0, 1);
-    if (p->L > 0) k_update_lm<<<grid_for(p->L, 256), 256, 0, p->stream>>>(v, 1.0, 1);
-    p->launches += 1 + (p->NSB > 0) + (p->L > 0);
+    k_update_all<<<grid_for(std::max<long long>(std::max(p->C, p->NSB), p->L), 128), 128, 0, p->stream>>>(v, 1.0, 1);
+    p->launches += 1;
     if (p->Lx > 0) {
         k_update_xyz<<<grid_for(3LL * p->Lx, 256), 256, 0, p->stream>>>(v, 1.0, 1);
         p->launches++;

@@ -111,6 +111,27 @@ __global__ void k_sum_partials(const double *partial, int n, double *out, int ac
     if (threadIdx.x == 0) *out = accumulate ? (*out + sm[0]) : sm[0];
 }
 
+// four fixed-order sums in one launch (blockIdx.x selects the array): the LM scalars of a trial step
+struct Sum4 {
+    const double *partial[4];
+    double *out[4];
+    int n[4];  // 0: skip
+};
+__global__ void k_sum_partials4(Sum4 a) {
+    __shared__ double sm[256];
+    const int w = blockIdx.x;
+    if (a.n[w] <= 0) return;
+    double t = 0.0;
+    for (int i = threadIdx.x; i < a.n[w]; i += blockDim.x) t += a.partial[w][i];
+    sm[threadIdx.x] = t;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *a.out[w] = sm[0];
+}
+
 __global__ void k_max_partials(const double *partial, int n, double *out) {
     __shared__ double sm[256];
     double t = 0.0;
@@ -971,6 +992,24 @@ __global__ void k_update_lm(DevView v, double sign, int backup) {
     if (v.act && !v.act[v.lm_prob[l]]) return;
     if (backup) v.invdep_bak[l] = v.invdep[l];
     v.invdep[l] += sign * v.dxl[l];
+}
+// UpdateStates of all three vertex classes in one launch (thread i: pose i, speed-bias i, landmark i)
+__global__ void k_update_all(DevView v, double sign, int backup) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v.C) update_pose(v, i, sign, backup);
+    if (i < v.NSB && !(v.act && !v.act[i / v.NSBper])) {
+        double *p = v.sb + 9 * (size_t)i;
+        const double *d = v.dxp + v.sb_off[i];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (backup) v.sb_bak[9 * (size_t)i + k] = p[k];
+            p[k] += sign * d[k];
+        }
+    }
+    if (i < v.L && !(v.act && !v.act[v.lm_prob[i]])) {
+        if (backup) v.invdep_bak[i] = v.invdep[i];
+        v.invdep[i] += sign * v.dxl[i];
+    }
 }
 __global__ void k_restore(DevView v) {  // v.act (batch): restore only the problems whose step was rejected
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
