@@ -11,7 +11,9 @@
 #include "vio_dev.h"
 #include "vio_bcr.h"
 
-#define BCR_THREADS 256
+#ifndef BCR_THREADS
+#define BCR_THREADS 384
+#endif
 
 struct BcrView {
     int n, M, ld, n_items;  // ld: row stride of a tile (BcrPlan::ld)
@@ -366,8 +368,11 @@ __device__ __forceinline__ void bcr_chol_inv(double *__restrict__ D, double *__r
                 }
                 bcr_panel_factor<NPASS>(r, blk, k0, lane, M, V + (cur ^ 1) * 4 * M, sc + (cur ^ 1) * 16, info);
             }
-        } else {
-            const int wk = warp - 1, nwk = nw - 1;  // worker index / count
+        } else if ((warp & 3) != 0) {
+            // workers = the warps that do NOT share warp 0's scheduler (warp id mod 4 picks the SM sub-partition): a DMMA holds
+            // the FP64 pipe of its sub-partition for 16 cycles, and every one issued next to warp 0 lengthens the dependent
+            // DFMA chain of the look-ahead factorisation, which is the critical path of the whole panel loop
+            const int wk = warp - 1 - (warp >> 2), nwk = nw - ((nw + 3) >> 2);  // worker index / count
             const int nD = max(0, M - k0 - BCR_PANEL);   // trailing rows of D below the next panel: rows k0+4 ..
             const int nbD = (nD + 7) >> 3, nbU = (k0 + 7) >> 3;  // 8-row bands of D, and of rows 0 .. j0+3 of U
             const int nct = (M - k0 + 7) >> 3;               // 8-column tiles from column k0
