@@ -1387,6 +1387,7 @@ int vio_nccl_init(vio_problem *p, int rank, int world, const void *id128) {
     p->nccl_owned = true;
     p->shard_rank = rank;
     p->shard_world = world;
+    graphs_drop(p);  // captured LM graphs belong to the previous sharding
     return p2p_setup(p);
 }
 
@@ -1399,6 +1400,7 @@ int vio_set_nccl_comm(vio_problem *p, void *nccl_comm, int rank, int world) {
     p->nccl_owned = false;
     p->shard_rank = rank;
     p->shard_world = world;
+    graphs_drop(p);  // captured LM graphs belong to the previous sharding
     if (!nccl_comm) { p2p_teardown(p); return VIO_OK; }
     CK(cudaSetDevice(p->device));
     return p2p_setup(p);
@@ -1410,6 +1412,7 @@ int vio_set_shard(vio_problem *p, int rank, int world) {
     if (!p || world < 1 || rank < 0 || rank >= world) return VIO_ERR_INVALID;
     p->shard_rank = rank;
     p->shard_world = world;
+    graphs_drop(p);  // captured LM graphs belong to the previous sharding
     return VIO_OK;
 }
 
